@@ -1,0 +1,323 @@
+/*
+ * clskd.h — C ABI of libclskd_sm100.so: the B200 (sm_100a) kernels behind the
+ * DCCRN teacher->student distillation step of KhanhNguyen4999/Speech-Enhancement-CLSKD.
+ *
+ * The reference has no FFI (it is pure PyTorch); every entry point below replaces
+ * one or more torch library call sites of the reference, cited as file:line
+ * relative to the reference tree.  A maintainer binds them with ctypes
+ * (see INTEGRATION.md); there are no torch types in any signature.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the caller allocates all outputs and workspaces; kernels never allocate or sync;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *  - return 0 on success, <0 on error (CLSKD_ERR_*); clskd_last_error() gives the
+ *    thread-local message;
+ *  - activations are "channels-last" [B, T, F, C] (C fastest) described by explicit
+ *    element strides, so logical NCHW views of the reference ([B, C, F, T]) need no copy;
+ *  - dtype tags: CLSKD_F32 / CLSKD_BF16.  Accumulation is always fp32 (fp64 for
+ *    BatchNorm / loss reductions).
+ */
+#ifndef CLSKD_H_
+#define CLSKD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLSKD_F32 0
+#define CLSKD_BF16 1
+
+#define CLSKD_OK 0
+#define CLSKD_ERR_ARG (-1)
+#define CLSKD_ERR_CUDA (-2)
+#define CLSKD_ERR_UNSUPPORTED (-3)
+
+#define CLSKD_MAX_TAPS 16
+
+const char* clskd_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+int clskd_abi_version(void);
+/* 1 if the library was compiled with the tcgen05/TMA kernels (always 1 for sm_100a builds). */
+int clskd_has_tcgen05(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Tap-list implicit GEMM ("tapconv"): the one contraction that every convolution-like
+ * operator of the path lowers to.
+ *
+ *   Y[b,to,fo,n] = bias[n] + sum_j sum_c X[b, to+dt[j], fo*sf+df[j], c] * W[j][c][n]
+ *
+ * with X read as zero outside [0,Ti) x [0,Fi).  X may be the channel-concatenation of two
+ * sources (skip connections: replaces complex_cat, tools_for_model.py:181-190).
+ * Replaces: F.conv1d (tools_for_model.py:57), F.conv_transpose1d (:100), the four nn.Conv2d of
+ * ComplexConv2d (:252-256), the four nn.ConvTranspose2d of ComplexConvTranspose2d (:320-324),
+ * nn.Linear (:171-172), the LSTM input projections (:164-167), ABF's 1x1/3x3 convs
+ * (framework.py:180,184,189), and all of their data gradients.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ClskdTapConv {
+  const void* x0;          /* source 0, element (b,t,f,c) at x0[b*x0_sB + t*x0_sT + f*x0_sF + c] */
+  const void* x1;          /* source 1 or NULL */
+  int64_t x0_sB, x0_sT, x0_sF;
+  int64_t x1_sB, x1_sT, x1_sF;
+  int32_t c0, c1;          /* channels of source 0 / 1 (c1 = 0 when x1 is NULL) */
+  int32_t B, To, Fo;       /* output grid; rows M = B*To*Fo */
+  int32_t Ti, Fi;          /* valid input extents */
+  int32_t sf;              /* input-f step per output f */
+  int32_t ntaps;
+  int32_t dt[CLSKD_MAX_TAPS];
+  int32_t df[CLSKD_MAX_TAPS];
+  const void* w;           /* fwd: [ntaps][c0+c1][N] fp32 (CUDA-core path) or [ntaps][N][c0+c1] bf16 (tcgen05 path) */
+  const float* bias;       /* [N] fp32 or NULL */
+  int32_t N;
+  void* y;                 /* element (b,to,fo,n) at y[b*y_sB + to*y_sT + fo*y_sF + n] */
+  int64_t y_sB, y_sT, y_sF;
+  int32_t x_dtype, y_dtype;
+  int32_t accumulate;      /* 1: Y += result (fp32 outputs only) */
+} ClskdTapConv;
+
+/* fp32 CUDA-core implicit GEMM (exact-fp32 policy, and layers too small for a UMMA tile) */
+int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream);
+/* bf16 tcgen05/TMA implicit GEMM; requires (c0+c1)%16==0, c0%16==0, N%16==0, bf16 x/w,
+ * dense [B,Ti,Fi,C] sources (see clskd_tapconv_umma_supported). */
+int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream);
+int clskd_tapconv_umma_supported(const ClskdTapConv* d);
+
+/* weight gradient of the same contraction:
+ *   dW[j][c][n] = sum_{b,to,fo} X[b,to+dt[j],fo*sf+df[j],c] * dY[b,to,fo,n]     (fp32 out)
+ * `d->y` is dY (read), `d->w` is dW (written, fp32 [ntaps][c0+c1][N]).  dW is zeroed by the call
+ * unless d->accumulate. */
+int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / packing helpers
+ * ------------------------------------------------------------------------------------------ */
+/* dst[i0..i3 @ dst_strides] <- src[i0..i3 @ src_strides] over `shape` (4 dims, element strides,
+ * i3 fastest); dtype conversion allowed.  The one layout adapter of the path. */
+int clskd_strided_copy4d(const void* src, int src_dtype, const int64_t* src_strides, void* dst,
+                         int dst_dtype, const int64_t* dst_strides, const int64_t* shape,
+                         void* stream);
+/* out[i] = sum over the entry pair (table[2i], table[2i+1]) of (+/-) src_sel[off], with entry
+ * e = off*4 + neg*2 + sel (sel 0: a, sel 1: b) and e<0 -> skipped.
+ * Builds the 2x-wide block weight [[Wr,-Wi],[Wi,Wr]] of a complex convolution
+ * (tools_for_model.py:252-259, :320-327) in whatever order a kernel wants. */
+int clskd_pack_gather(const float* a, const float* b, const int32_t* table, int64_t n, void* out,
+                      int out_dtype, void* stream);
+/* dst[j] = s0*src[i0] + s1*src[i1], table entry pair (e0,e1) with e = idx*2 + neg, e<0 -> skipped.
+ * Folds the block-weight gradient back onto the reference's separate real/imag parameters. */
+int clskd_unpack_gather2(const float* src, const int32_t* table2, int64_t n, float* dst,
+                         int accumulate, void* stream);
+/* zero / reflect padding of waveforms: dst[b, i] = src[b, map(i - left)], i in [0, L+left+right).
+ * mode 0: zeros (ConvSTFT, tools_for_model.py:56); mode 1: reflect (torch.stft center=True,
+ * framework.py:27). dst is fp32. */
+int clskd_pad1d(const void* src, int src_dtype, int64_t src_sB, int B, int L, int left, int right,
+                int mode, float* dst, void* stream);
+/* gradient of clskd_pad1d: dsrc[b,i] = sum of ddst entries that read it (fp32). */
+int clskd_pad1d_bwd(const float* ddst, int B, int L, int left, int right, int mode, float* dsrc,
+                    int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm2d (+PReLU) over channels-last rows.  Replaces nn.BatchNorm2d + nn.PReLU
+ * (DCCRN.py:80-82,123-126) and the BatchNorm2d inside ABF (framework.py:181,185).
+ * ------------------------------------------------------------------------------------------ */
+/* per-channel sums over M rows of a dense [M, C] matrix: sum[c] = sum x, sumsq[c] = sum x*x (fp64);
+ * outputs are zeroed by the call. */
+int clskd_colstats(const void* x, int dtype, int64_t M, int C, double* sum, double* sumsq,
+                   void* stream);
+/* finalize training statistics: mean/invstd (fp32 [C]) from the fp64 sums; updates running stats
+ * with `momentum` using the unbiased variance exactly like torch (running_* may be NULL). */
+int clskd_bn_finalize(const double* sum, const double* sumsq, int64_t M, int C, float eps,
+                      float momentum, float* mean, float* invstd, float* running_mean,
+                      float* running_var, void* stream);
+/* eval statistics: mean = running_mean, invstd = rsqrt(running_var + eps) */
+int clskd_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
+                        float* mean, float* invstd, void* stream);
+/* y = prelu((x-mean)*invstd*gamma+beta); slope is a DEVICE scalar pointer or NULL (identity). */
+int clskd_bn_act_fwd(const void* x, int x_dtype, int64_t M, int C, const float* mean,
+                     const float* invstd, const float* gamma, const float* beta,
+                     const float* slope, void* y, int y_dtype, void* stream);
+/* backward pass 1: per-channel sums of dz and dz*xhat where dz = dy * prelu'(bn(x)); also
+ * dslope = sum dy*min(0,bn(x)).  sums are fp64 [C], dslope fp64 scalar (NULL ok); zeroed by the call. */
+int clskd_bn_act_bwd_stats(const void* x, int x_dtype, const void* dy, int dy_dtype, int64_t M,
+                           int C, const float* mean, const float* invstd, const float* gamma,
+                           const float* beta, const float* slope, double* sum_dz,
+                           double* sum_dz_xhat, double* dslope, void* stream);
+/* backward pass 2: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (training) or
+ * gamma*invstd*dz (eval: training=0); also writes dgamma/dbeta (fp32 [C], may be NULL) and
+ * dslope_out (fp32 scalar, may be NULL). */
+int clskd_bn_act_bwd_apply(const void* x, int x_dtype, const void* dy, int dy_dtype, int64_t M,
+                           int C, const float* mean, const float* invstd, const float* gamma,
+                           const float* beta, const float* slope, const double* sum_dz,
+                           const double* sum_dz_xhat, const double* dslope, int training, void* dx,
+                           int dx_dtype, float* dgamma, float* dbeta, float* dslope_out,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Complex BatchNorm (Trabelsi 2x2 whitening), tools_for_model.py:398-508.  x is [M, 2*Cc]
+ * (real half then imag half of the channel axis).
+ * ------------------------------------------------------------------------------------------ */
+/* moments: s[0..4][Cc] = sum xr, xi, xr*xr, xr*xi, xi*xi (fp64, zeroed by the call) */
+int clskd_cbn_moments(const void* x, int dtype, int64_t M, int Cc, double* s, void* stream);
+/* training=1: stats from moments + running update (lerp, biased moments like the reference);
+ * training=0: stats from running buffers.  coef[7][Cc] = Mr, Mi, Zrr, Zri, Zir, Zii, (unused);
+ * also saves whitening terms needed by backward in `saved` [8][Cc]. */
+int clskd_cbn_finalize(const double* s, int64_t M, int Cc, float eps, float momentum, int training,
+                       const float* Wrr, const float* Wri, const float* Wii, float* RMr, float* RMi,
+                       float* RVrr, float* RVri, float* RVii, float* coef, void* stream);
+int clskd_cbn_apply(const void* x, int x_dtype, int64_t M, int Cc, const float* coef,
+                    const float* Br, const float* Bi, void* y, int y_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mask / spectrum kernels (DCCRN.py:153,159,207-232)
+ * spec / out_spec are interleaved complex spectra [B, T, 257, 2]; mask is the last decoder
+ * output [B, T(+offset), 256, 2] addressed by strides (DC bin mask is zero, DCCRN.py:209-210).
+ * mode: 0 = 'E', 1 = 'C', 2 = 'R'.
+ * ------------------------------------------------------------------------------------------ */
+int clskd_mask_fwd(const float* spec, const void* mask, int mask_dtype, int64_t m_sB, int64_t m_sT,
+                   int B, int T, int nbins, int mode, float* out_spec, float* mask_padded,
+                   void* stream);
+/* gradient wrt the mask (spec is data): dmask has the mask's strides/dtype */
+int clskd_mask_bwd(const float* spec, const void* mask, int mask_dtype, int64_t m_sB, int64_t m_sT,
+                   int B, int T, int nbins, int mode, const float* dout_spec, void* dmask,
+                   int dmask_dtype, int64_t dm_sB, int64_t dm_sT, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * iSTFT overlap-add (tools_for_model.py:100-107) + squeeze/clamp (DCCRN.py:235-237)
+ * frames [B, T, win] fp32 (synthesis-basis GEMM output) -> wav [B, L], L = (T-1)*hop+win-2*trim
+ * wav[b,i] = clamp( sum_t frames[b,t,i+trim-t*hop] / (coff[i+trim]+1e-8), -1, 1 )
+ * coff = overlap-added window^2 (computed in-kernel from `window`; window NULL: no normalisation,
+ * which is the plain conv_transpose1d used as the data gradient of the framing GEMM).
+ * ------------------------------------------------------------------------------------------ */
+int clskd_ola_fwd(const float* frames, const float* window, int B, int T, int win, int hop,
+                  int trim, int do_clamp, float* wav, void* stream);
+/* dframes[b,t,k] = dwav[b, t*hop+k-trim] / (coff+1e-8) * (|wav| < 1 or !do_clamp), 0 outside */
+int clskd_ola_bwd(const float* dwav, const float* wav, const float* window, int B, int T, int win,
+                  int hop, int trim, int do_clamp, float* dframes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Time-domain objectives (tools_for_loss.py:30-47,83-97), MSE (DCCRN.py:260-261)
+ * kind: 0 = si_snr(s1,s2), 1 = sdr(s1,s2), 2 = si_sdr(reference=s1, estimation=s2), 3 = mse.
+ * out is one fp32 scalar; `part` is a [B,4] fp64 workspace that bwd re-uses.
+ * ------------------------------------------------------------------------------------------ */
+int clskd_wave_loss_fwd(const float* s1, const float* s2, int B, int L, int kind, float eps,
+                        double* part, float* out, void* stream);
+/* ds1 (and/or ds2, either may be NULL) = gout * d out / d s */
+int clskd_wave_loss_bwd(const float* s1, const float* s2, int B, int L, int kind, float eps,
+                        const double* part, const float* gout, float* ds1, float* ds2,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * STFT-magnitude losses (framework.py:16-68): inputs are the interleaved spectra
+ * [M, nbins, 2] of prediction x and target y.
+ *   part[0] = sum |log ymag - log xmag|, part[1] = sum (ymag-xmag)^2, part[2] = sum ymag^2
+ *   mag = sqrt(clamp(re^2+im^2, 1e-7));  n = number of (row, bin) pairs
+ *   out[0] = sqrt(part[1])/sqrt(part[2]) (spectral convergence), out[1] = part[0]/n (log-mag L1)
+ * ------------------------------------------------------------------------------------------ */
+int clskd_stftmag_loss_fwd(const float* xs, const float* ys, int64_t n, double* part, float* out,
+                           void* stream);
+/* dxs = g_mag * d(mean|log y - log x|)/dxs + g_sc * d(||y-x||_F/||y||_F)/dxs; g_* are host floats
+ * already containing the upstream gradient and the mean/factor scaling. */
+int clskd_stftmag_loss_bwd(const float* xs, const float* ys, int64_t n, const double* part,
+                           const float* gout_mag, const float* gout_sc, float scale_mag,
+                           float scale_sc, float* dxs, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SPKD (framework.py:150-172): Gram G = Z Z^T over the flattened feature axis, L1 row
+ * normalisation, squared Frobenius distance, /B^2.
+ * ------------------------------------------------------------------------------------------ */
+/* G[B,B] (fp32) = Z Z^T (+= when accumulate); Z is [B, K] with row stride ldz (elements). */
+int clskd_gram_fwd(const void* z, int dtype, int B, int64_t K, int64_t ldz, float* G,
+                   int accumulate, void* stream);
+/* loss (fp32 scalar) = || rownorm1(Gt) - rownorm1(Gs) ||_F^2 * scale; also dGs = dloss/dGs (fp32
+ * [B,B], may be NULL) for a unit upstream gradient. */
+int clskd_spkd_loss(const float* Gt, const float* Gs, int B, float scale, float* loss, float* dGs,
+                    void* stream);
+/* dZ[i,:] = gout * sum_j (dG[i,j] + dG[j,i]) Z[j,:] */
+int clskd_gram_bwd(const void* z, int dtype, int B, int64_t K, int64_t ldz, const float* dG,
+                   const float* gout, void* dz, int dz_dtype, int64_t lddz, int accumulate,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LSTM recurrence (nn.LSTM inside NavieComplexLSTM, tools_for_model.py:144-147,164-167).
+ * `pre` holds the input projections + both biases (gate order i,f,g,o).  R = P*Bp rows share one
+ * weight set (P parts, e.g. {real,imag} inputs, of Bp batch rows each); the pre-activation of
+ * (set s, time t, row r=(p,b), gate g) is at
+ *     pre[s*pre_set_stride + p*pre_pstride + t*pre_tstride + b*pre_ld + g].
+ * `whh_t` is W_hh transposed, [nsets][H][4H] fp32 (w_bf16=1 keeps it as bf16 in shared memory:
+ * the bf16 policy for H up to 128).  Outputs are dense: h [nsets][P][T][Bp][H]; for training also
+ * gates [nsets][P][T][Bp][4H] (post-activation) and c [nsets][P][T][Bp][H] (NULL to skip).
+ * ------------------------------------------------------------------------------------------ */
+int clskd_lstm_fwd(const float* pre, const float* whh_t, int T, int R, int Bp, int H, int nsets,
+                   int64_t pre_pstride, int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride,
+                   int64_t whh_set_stride, int w_bf16, float* h, float* gates, float* c,
+                   void* stream);
+/* BPTT: given dh_out (gradient wrt every h_t, layout of h) produces dpre (gradient wrt the
+ * pre-activations, addressed like `pre`).  gates/c are the saved forward tensors; `whh` is
+ * W_hh [nsets][4H][H] fp32. */
+int clskd_lstm_bwd(const float* dh_out, const float* whh, const float* gates, const float* c, int T,
+                   int R, int Bp, int H, int nsets, int64_t whh_set_stride, int64_t pre_pstride,
+                   int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride, float* dpre,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ABF helpers (framework.py:206-224)
+ * ------------------------------------------------------------------------------------------ */
+/* nearest resize along F of a dense [B,T,Fi,C] tensor to [B,T,Fo,C] (F.interpolate nearest) */
+int clskd_resize_f_fwd(const void* x, int dtype, int64_t BT, int Fi, int Fo, int C, void* y,
+                       void* stream);
+int clskd_resize_f_bwd(const void* dy, int dtype, int64_t BT, int Fi, int Fo, int C, void* dx,
+                       void* stream);
+/* out = x*sigmoid(z0) + y*sigmoid(z1); z is [M,2] logits (fp32) */
+int clskd_att_blend_fwd(const void* x, const void* y, int dtype, const float* z, int64_t M, int C,
+                        void* out, void* stream);
+int clskd_att_blend_bwd(const void* x, const void* y, int dtype, const float* z, const void* dout,
+                        int64_t M, int C, void* dx, void* dy, float* dz, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * hcl (framework.py:287-306): adaptive average pooling of a dense [B,T,F,C] map to (l,l) per
+ * channel over the logical (H=F, W=T) plane -> out [B, C, l, l] fp32.
+ * ------------------------------------------------------------------------------------------ */
+int clskd_adaptive_pool_fwd(const void* x, int dtype, int B, int T, int F, int C, int l,
+                            float* out, void* stream);
+int clskd_adaptive_pool_bwd(const float* dout, int B, int T, int F, int C, int l, void* dx,
+                            int dtype, int accumulate, void* stream);
+/* out[0] (+)= scale * sum (a-b)^2 ; generic dtype */
+int clskd_sqdiff_sum(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n,
+                     double* out, void* stream);
+/* da (+)= g * 2*(a-b) with g = gout[0]*scale */
+int clskd_sqdiff_bwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n,
+                     const float* gout, float scale, void* da, int da_dtype, int accumulate,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer (optim.Adam, distill.py:202-204): flat fp32 buffers.
+ * ------------------------------------------------------------------------------------------ */
+int clskd_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale,
+                    void* stream);
+
+/* gradient bucket: flat[offsets[i]..offsets[i+1]) = fp32 tensor at device address ptrs[i]
+ * (zeros when ptrs[i] == 0).  `ptrs` (uint64[n]) and `offsets` (int64[n+1]) are DEVICE arrays;
+ * total = offsets[n].  One launch builds the flat bucket that NCCL all-reduces and Adam consumes. */
+int clskd_multi_pack_f32(const void* ptrs, const int64_t* offsets, int n, int64_t total,
+                         float* flat, void* stream);
+
+/* small utilities */
+int clskd_fill_f32(float* p, int64_t n, float v, void* stream);
+int clskd_axpy_f32(float* y, const float* x, int64_t n, float a, void* stream);
+/* out = a*x + b*y (y may be NULL): the rr-ii / ir+ri combination of the complex LSTM
+ * (tools_for_model.py:168-169) and its gradient. */
+int clskd_axpby_f32(const float* x, const float* y, float a, float b, float* out, int64_t n,
+                    void* stream);
+/* out[0] = sum_i w[i]*in[i] over n fp32 scalars given as an array of device pointers is not
+ * needed: losses are combined by the autograd graph on the host side. */
+
+/* fp64 -> fp32 scalar conversion with scaling: out[i] = (float)(in[i]*scale) */
+int clskd_f64_to_f32(const double* in, int n, double scale, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLSKD_H_ */

@@ -1,0 +1,196 @@
+"""DCCRN: deep complex convolution recurrent network on B200-native kernels.
+
+Same class name, constructor signature, submodule names (`stft`, `istft`, `encoder`, `enhance`,
+`decoder` - the hook targets of feature_extraction) and `state_dict` keys as the reference
+(DCCRN.py:14-257), but the forward is a chain of fused sm_100a kernels on channels-last
+activations: framed-window DFT GEMM -> 6x (complex conv as one 2x-wide implicit GEMM -> BatchNorm
+statistics -> normalise+PReLU) -> complex LSTM (batched projections + persistent recurrence) ->
+6x (skip connection as a second K segment -> sub-pixel complex transposed conv -> BN+PReLU) ->
+trig-free polar mask -> synthesis GEMM + overlap-add + clamp.
+"""
+import torch
+import torch.nn as nn
+
+from . import config as cfg
+from . import ops
+from .clstm import NavieComplexLSTM
+from .ops import MaskFn, dense, strided_copy_into, to_logical, to_phys
+from .tools_for_loss import mse, sdr, si_sdr, si_snr
+from .tools_for_model import (BatchNorm2d, ComplexBatchNorm, ComplexConv2d, ComplexConvTranspose2d, ConvBNAct,
+                              ConviSTFT, ConvSTFT, PReLU)
+
+
+class _ToLstmFn(torch.autograd.Function):
+    """encoder output (physical [B,T,F,2Cc]) -> X [2,T,B,Cc*F] with feature index c*F+f
+    (the permute/reshape of DCCRN.py:178-184)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        B, T, F, C = x.shape
+        Cc = C // 2
+        X = torch.empty((2, T, B, Cc * F), dtype=dtype, device=x.device)
+        for p in range(2):
+            strided_copy_into(x[..., p * Cc:(p + 1) * Cc].permute(1, 0, 3, 2), X[p].view(T, B, Cc, F))
+        ctx.meta = (x.shape, x.dtype)
+        return X
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, dt = ctx.meta
+        B, T, F, C = shape
+        Cc = C // 2
+        g = dense(g)
+        dx = torch.empty(shape, dtype=dt, device=g.device)
+        for p in range(2):
+            strided_copy_into(g[p].view(T, B, Cc, F).permute(1, 0, 3, 2), dx[..., p * Cc:(p + 1) * Cc])
+        return dx, None
+
+
+class _FromLstmFn(torch.autograd.Function):
+    """LSTM outputs (real, imag), each [T,B,Cc*F] -> physical [B,T,F,2Cc] (DCCRN.py:188-199)."""
+
+    @staticmethod
+    def forward(ctx, r, i, F, dtype):
+        T, B, D = r.shape
+        Cc = D // F
+        out = torch.empty((B, T, F, 2 * Cc), dtype=dtype, device=r.device)
+        for p, y in enumerate((r, i)):
+            strided_copy_into(y.reshape(T, B, Cc, F).permute(1, 0, 3, 2), out[..., p * Cc:(p + 1) * Cc])
+        ctx.meta = (r.shape, r.dtype, i.dtype, F)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, dtr, dti, F = ctx.meta
+        T, B, D = shape
+        Cc = D // F
+        g = dense(g)
+        outs = []
+        for p, dt in enumerate((dtr, dti)):
+            d = torch.empty(shape, dtype=dt, device=g.device)
+            strided_copy_into(g[..., p * Cc:(p + 1) * Cc].permute(1, 0, 3, 2), d.view(T, B, Cc, F))
+            outs.append(d)
+        return outs[0], outs[1], None, None
+
+
+class _TrimFirstFn(torch.autograd.Function):
+    """physical [B,T+1,F,C] -> view [B,T,F,C] without column 0 (DCCRN.py:205)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.meta = (x.shape, x.dtype)
+        return x[:, 1:]
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, dt = ctx.meta
+        dx = torch.empty(shape, dtype=dt, device=g.device)
+        dx[:, 0].zero_()
+        strided_copy_into(g, dx[:, 1:])
+        return dx
+
+
+class DCCRN(nn.Module):
+
+    def __init__(self, rnn_layers=cfg.rnn_layers, rnn_units=cfg.rnn_units, win_len=cfg.win_len,
+                 win_inc=cfg.win_inc, fft_len=cfg.fft_len, win_type=cfg.window_type, masking_mode='E',
+                 use_clstm=False, use_cbn=False, kernel_size=5, kernel_num=[16, 32, 64, 128, 256, 256]):
+        """rnn_layers: number of LSTM layers; rnn_units / kernel_num count real+imag channels."""
+        super().__init__()
+        self.win_len, self.win_inc, self.fft_len, self.win_type = win_len, win_inc, fft_len, win_type
+        self.rnn_units = rnn_units
+        self.input_dim = self.output_dim = win_len
+        self.hidden_layers = rnn_layers
+        self.kernel_size = kernel_size
+        self.kernel_num = [2] + list(kernel_num)
+        self.masking_mode = masking_mode
+        self.use_clstm = use_clstm
+        if not use_clstm:
+            raise NotImplementedError("DCCRN: only the complex-LSTM bottleneck (use_clstm=True, 'DCCRN-CL') is "
+                                      "implemented on this path")
+        self.fix = True
+        self.stft = ConvSTFT(win_len, win_inc, fft_len, win_type, 'complex', fix=True)
+        self.istft = ConviSTFT(win_len, win_inc, fft_len, win_type, 'complex', fix=True)
+
+        def norm(ch):
+            return ComplexBatchNorm(ch) if use_cbn else BatchNorm2d(ch)
+
+        kn = self.kernel_num
+        self.encoder = nn.ModuleList()
+        self.decoder = nn.ModuleList()
+        for idx in range(len(kn) - 1):
+            self.encoder.append(ConvBNAct(
+                ComplexConv2d(kn[idx], kn[idx + 1], kernel_size=(kernel_size, 2), stride=(2, 1), padding=(2, 1)),
+                norm(kn[idx + 1]), PReLU()))
+        hidden_dim = fft_len // (2 ** len(kn))
+        rnns = []
+        for idx in range(rnn_layers):
+            rnns.append(NavieComplexLSTM(
+                input_size=hidden_dim * kn[-1] if idx == 0 else rnn_units, hidden_size=rnn_units,
+                bidirectional=False, batch_first=False,
+                projection_dim=hidden_dim * kn[-1] if idx == rnn_layers - 1 else None))
+        self.enhance = nn.Sequential(*rnns)
+        for idx in range(len(kn) - 1, 0, -1):
+            conv = ComplexConvTranspose2d(kn[idx] * 2, kn[idx - 1], kernel_size=(kernel_size, 2), stride=(2, 1),
+                                          padding=(2, 0), output_padding=(1, 0))
+            self.decoder.append(ConvBNAct(conv, norm(kn[idx - 1]), PReLU()) if idx != 1 else ConvBNAct(conv))
+        self.flatten_parameters()
+
+    def flatten_parameters(self):
+        pass
+
+    def forward(self, inputs, lens=None, is_feat=None):
+        ops._require_cuda(inputs)
+        act = ops.policy.act_dtype
+        spec = self.stft.spectrum(inputs, interleaved=True)            # fp32 [B, T, 257, 2]
+        # DC bin dropped (DCCRN.py:162); logical [B, 2, 256, T]
+        out = to_logical(dense(spec[:, :, 1:, :]))
+        encoder_out = []
+        for layer in self.encoder:
+            out = layer(out)
+            encoder_out.append(out)
+        # ---- complex LSTM bottleneck
+        x = to_phys(out, need_dense=True)
+        F = x.shape[2]
+        X = _ToLstmFn.apply(x, act)
+        r, i = self.enhance([X[0], X[1]])
+        out = to_logical(_FromLstmFn.apply(r, i, F, act))
+        # ---- decoder: skip connections are the second K segment of each transposed conv
+        for idx in range(len(self.decoder)):
+            out = self.decoder[idx](out, encoder_out[-1 - idx])
+            out = to_logical(_TrimFirstFn.apply(to_phys(out)))
+        mask = to_phys(out)                                            # [B, T, 256, 2] (batch-strided view)
+        if mask.stride(3) != 1 or mask.stride(2) != 2:
+            mask = dense(mask)
+        want = is_feat is not True
+        out_spec, mp = MaskFn.apply(spec, mask, self.masking_mode, want)
+        B, T = out_spec.shape[0], out_spec.shape[1]
+        out_wav = self.istft.synthesize(out_spec.view(B, T, -1), interleaved=True, clamp=True)
+        if is_feat is True:
+            return out_wav
+        mask_real, mask_imag = mp[..., 0].permute(0, 2, 1), mp[..., 1].permute(0, 2, 1)
+        real, imag = out_spec[..., 0].permute(0, 2, 1), out_spec[..., 1].permute(0, 2, 1)
+        return mask_real, mask_imag, real, imag, out_wav
+
+    def get_params(self, weight_decay=0.0):
+        weights = [p for n, p in self.named_parameters() if 'bias' not in n]
+        biases = [p for n, p in self.named_parameters() if 'bias' in n]
+        return [{'params': weights, 'weight_decay': weight_decay}, {'params': biases, 'weight_decay': 0.0}]
+
+    def loss(self, inputs, labels, real_spec=None, img_spec=None, loss_mode=cfg.loss_mode):
+        """Loss dispatcher (reference DCCRN.py:259-411).  The waveform objectives are implemented;
+        the mel (LMS) and PMSQE modes depend on asteroid code outside this path."""
+        if loss_mode == 'MSE':
+            return mse(inputs, labels)
+        if loss_mode == 'SDR':
+            return -sdr(labels, inputs)
+        if loss_mode == 'SI-SNR':
+            return -si_snr(inputs, labels)
+        if loss_mode == 'SI-SDR':
+            return -si_sdr(labels, inputs)
+        if loss_mode == 'MSE+SI-SNR':
+            return (1 * -si_snr(inputs, labels) + 100 * mse(inputs, labels)) / 101
+        if loss_mode == 'SI-SNR+SI-SDR':
+            return (-si_snr(inputs, labels) + -si_sdr(inputs, labels)) / 2
+        raise NotImplementedError("loss_mode %r needs the mel/PMSQE code of asteroid, which is outside the "
+                                  "distillation path implemented here" % (loss_mode,))

@@ -1,0 +1,226 @@
+"""Distillation training steps (reference: KnowledgeDistillation.training_step of distill.py:72-148,
+distill_SPKD.py:69-87, distill_MSE.py:70-90, distill_STFT.py:67-84, distill_ReviewKD.py:69-139 and
+the optimizer of distill.py:202-204) as plain functions over the local DCCRN, plus a small trainer
+that owns a flat parameter / gradient bucket, the fused Adam kernel and the NCCL gradient
+all-reduce for data-parallel runs (one process per GPU, utterances sharded across ranks).
+
+Differences from the reference loop that are deliberate:
+  * the teacher runs in eval mode under no_grad and the student forward runs ONCE per step
+    (`faithful=True` restores train-mode teacher BatchNorm and the duplicated student forward);
+  * the ABF fusion modules are persistent and trainable by default; `fresh_abf=True` re-creates
+    them with new random weights every step like the reference does.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import config as cfg
+from . import feature_extraction, ops
+from .framework import MultiResolutionSTFTLoss, SPKDLoss, build_review_kd, hcl
+from .ops import call
+from .tools_for_loss import mse
+
+
+def _taps(model, X, grad):
+    """One forward of `model` with feature hooks -> (wav [B,L], encoder maps, decoder maps (pre-trim),
+    lstm real [B,T,D], lstm imag [B,T,D])."""
+    ext = feature_extraction.DCCRN(model)
+    try:
+        with torch.set_grad_enabled(grad):
+            wav = model(X, is_feat=True)
+    finally:
+        ext.remove_hook()
+    fm = ext.feature_maps
+    real, imag = fm["clstm"][0]
+    # the local LSTM is time-major; SPKD flattens from dim 1, so make the taps batch-first
+    return wav, fm["encoder"], fm["decoder"], real.transpose(0, 1), imag.transpose(0, 1)
+
+
+class DistillStep(nn.Module):
+    """loss = base + distillation term, for mode in
+    'clskd' | 'spkd_all' | 'spkd' | 'mse' | 'stft' | 'reviewkd'."""
+
+    def __init__(self, teacher, student, mode='clskd', faithful=False, fresh_abf=False, base='stft'):
+        super().__init__()
+        self.teacher, self.student = teacher, student
+        for p in self.teacher.parameters():
+            p.requires_grad = False
+        self.mode, self.faithful, self.fresh_abf, self.base = mode, faithful, fresh_abf, base
+        if mode == 'reviewkd':   # distill_ReviewKD.py:56
+            self.stft_loss = MultiResolutionSTFTLoss(fft_sizes=[512], win_lengths=[32], hop_sizes=[16])
+        else:                    # distill.py:59
+            self.stft_loss = MultiResolutionSTFTLoss(fft_sizes=[512], win_lengths=[400], hop_sizes=[100])
+        self.abf_encoder = None
+        self.abf_decoder = None
+        self.last_terms = {}
+
+    # ---- ABF management
+    def _abfs(self, s_enc, s_dec, t_enc, t_dec):
+        if self.fresh_abf or self.abf_encoder is None:
+            enc = build_review_kd(s_enc, 'encoder', out_channels=[m.shape[1] for m in t_enc])
+            dec = build_review_kd(s_dec, 'decoder', out_channels=[m.shape[1] for m in t_dec][::-1])
+            if self.fresh_abf:
+                for p in list(enc.parameters()) + list(dec.parameters()):
+                    p.requires_grad = False
+                return enc, dec
+            self.abf_encoder, self.abf_decoder = enc, dec
+        self.abf_encoder.feature_maps = s_enc
+        self.abf_decoder.feature_maps = s_dec
+        return self.abf_encoder, self.abf_decoder
+
+    def materialize(self, X):
+        """Create the persistent ABF modules (their shapes depend on the feature maps)."""
+        if self.mode in ('clskd', 'reviewkd') and not self.fresh_abf and self.abf_encoder is None:
+            with torch.no_grad():
+                _, t_enc, t_dec, _, _ = _taps(self.teacher, X, False)
+                _, s_enc, s_dec, _, _ = _taps(self.student, X, False)
+            self._abfs(s_enc, s_dec, t_enc, t_dec)
+
+    def trainable_parameters(self):
+        ps = [p for p in self.student.parameters() if p.requires_grad]
+        for m in (self.abf_encoder, self.abf_decoder):
+            if m is not None:
+                ps += [p for p in m.parameters() if p.requires_grad]
+        return ps
+
+    def _base(self, pred, y):
+        if self.base == 'si_snr':
+            from .tools_for_loss import si_snr
+            return -si_snr(pred, y)
+        return self.stft_loss(pred, y.reshape(pred.shape))[1]
+
+    def forward(self, X, y):
+        teacher, student = self.teacher, self.student
+        if not self.faithful:
+            teacher.eval()
+        terms = {}
+        feature_modes = self.mode in ('clskd', 'spkd_all', 'reviewkd')
+        if feature_modes:
+            t_wav, t_enc, t_dec, t_re, t_im = _taps(teacher, X, self.faithful)
+            s_wav, s_enc, s_dec, s_re, s_im = _taps(student, X, True)
+            if self.faithful:
+                s_wav = student(X, is_feat=True)        # the reference runs the student twice (distill.py:100)
+            terms['base'] = self._base(s_wav, y)
+            if self.mode == 'spkd_all':
+                f_enc, f_dec = s_enc, s_dec
+            else:
+                abf_e, abf_d = self._abfs(s_enc, s_dec, t_enc, t_dec)
+                f_enc, f_dec = abf_e(X), abf_d(X)
+            if self.mode == 'reviewkd':
+                terms['encoder'] = hcl(f_enc, t_enc)
+                terms['decoder'] = hcl(f_dec, t_dec)
+                terms['clstm_real'] = hcl([s_re.unsqueeze(1)], [t_re.unsqueeze(1)]) if s_re.shape == t_re.shape \
+                    else SPKDLoss(s_re, t_re, 'batchmean')()
+                terms['clstm_img'] = hcl([s_im.unsqueeze(1)], [t_im.unsqueeze(1)]) if s_im.shape == t_im.shape \
+                    else SPKDLoss(s_im, t_im, 'batchmean')()
+            else:
+                terms['encoder'] = sum(SPKDLoss(sf, tf, 'batchmean')() for sf, tf in zip(f_enc, t_enc))
+                terms['decoder'] = sum(SPKDLoss(sf, tf, 'batchmean')() for sf, tf in zip(f_dec, t_dec))
+                terms['clstm_real'] = SPKDLoss(s_re, t_re, reduction='batchmean')()
+                terms['clstm_img'] = SPKDLoss(s_im, t_im, reduction='batchmean')()
+        else:
+            s_wav = student(X, is_feat=True)
+            with torch.no_grad():
+                t_wav = teacher(X, is_feat=True)
+            terms['base'] = self._base(s_wav, y)
+            if self.mode == 'spkd':
+                terms['kd'] = SPKDLoss(s_wav.unsqueeze(1), t_wav.unsqueeze(1), reduction='batchmean')()
+            elif self.mode == 'mse':
+                terms['kd'] = mse(s_wav, t_wav)
+            elif self.mode == 'stft':
+                terms['kd'] = self.stft_loss(s_wav, t_wav)[1]
+            else:
+                raise ValueError("unknown distillation mode %r" % (self.mode,))
+        self.last_terms = terms
+        loss = None
+        for v in terms.values():
+            loss = v if loss is None else loss + v
+        return loss
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (distill.py:202-204) on one flat fp32 bucket: parameters are
+    re-pointed to views of `flat_p`, gradients are packed into `flat_g` by one kernel, optionally
+    averaged across ranks with one NCCL all-reduce, and updated by one fused Adam kernel."""
+
+    def __init__(self, params, lr=cfg.learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("FlatAdam: no parameters")
+        dev = self.params[0].device
+        ops._require_cuda(*self.params)
+        sizes = [p.numel() for p in self.params]
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + s)
+        self.total = offs[-1]
+        self.flat_p = torch.empty(self.total, dtype=torch.float32, device=dev)
+        for p, o, s in zip(self.params, offs[:-1], sizes):
+            self.flat_p[o:o + s].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + s].view(p.shape)
+        self.flat_g = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
+        self._ptr_host = torch.empty(len(sizes), dtype=torch.int64).pin_memory()
+        self._ptr_dev = torch.empty(len(sizes), dtype=torch.int64, device=dev)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.step_count = 0
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def pack_grads(self):
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
+                g = ops.dense(g, torch.float32)
+                p.grad = g
+            self._ptr_host[i] = g.data_ptr() if g is not None else 0
+        self._ptr_dev.copy_(self._ptr_host, non_blocking=True)
+        call("clskd_multi_pack_f32", self._ptr_dev.data_ptr(), self.offsets.data_ptr(), len(self.params),
+             self.total, self.flat_g.data_ptr(), ops._stream())
+        return self.flat_g
+
+    def step(self, world_size=1):
+        """flat_g must hold the (summed over ranks) gradient; it is divided by world_size."""
+        self.step_count += 1
+        call("clskd_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
+             self.v.data_ptr(), self.total, float(self.lr), float(self.betas[0]), float(self.betas[1]),
+             float(self.eps), float(self.weight_decay), self.step_count, 1.0 / world_size, ops._stream())
+
+
+class DistillTrainer:
+    """One process per GPU.  `train_step(X, y)` = teacher fwd + student fwd + distillation losses +
+    backward + gradient all-reduce (when torch.distributed is initialised) + Adam."""
+
+    def __init__(self, teacher, student, mode='clskd', lr=cfg.learning_rate, weight_decay=0.0,
+                 faithful=False, fresh_abf=False, base='stft', example_input=None):
+        self.step_fn = DistillStep(teacher, student, mode, faithful, fresh_abf, base)
+        self.student = student
+        if example_input is not None:
+            self.step_fn.materialize(example_input)
+        self.opt = None
+        self.lr, self.weight_decay = lr, weight_decay
+
+    def _ensure_opt(self, X):
+        if self.opt is None:
+            self.step_fn.materialize(X)
+            self.opt = FlatAdam(self.step_fn.trainable_parameters(), lr=self.lr, weight_decay=self.weight_decay)
+
+    def train_step(self, X, y):
+        import torch.distributed as dist
+        self._ensure_opt(X)
+        self.student.train()
+        self.opt.zero_grad()
+        loss = self.step_fn(X, y)
+        loss.backward()
+        g = self.opt.pack_grads()
+        world = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        self.opt.step(world)
+        return loss.detach()

@@ -1,0 +1,44 @@
+"""Feature taps (reference: feature_extraction.py:3-50): forward hooks on the encoder / decoder
+blocks and the complex LSTM of a DCCRN.  Works on the reference's model and on clskd_b200.DCCRN
+alike, because the B200 model keeps the same submodule tree."""
+
+
+class DCCRN:
+    def __init__(self, model):
+        self.model = model
+        self.feature_maps = {"encoder": [], "decoder": [], "clstm": []}
+        self._handles = []
+        for blk in model.encoder:
+            self._handles.append(blk.register_forward_hook(self._tap("encoder")))
+        for blk in model.decoder:
+            self._handles.append(blk.register_forward_hook(self._tap("decoder")))
+        self._handles.append(model.enhance.register_forward_hook(self._tap("clstm")))
+        # reference attribute names
+        n_enc, n_dec = len(model.encoder), len(model.decoder)
+        self.handle_encoder = self._handles[:n_enc]
+        self.handle_decoder = self._handles[n_enc:n_enc + n_dec]
+        self.handle_clstm = self._handles[-1]
+
+    def _tap(self, key):
+        def hook(module, inputs, output):
+            self.feature_maps[key].append(output)
+        return hook
+
+    # reference method names
+    def encoder_hook(self, module, input, output):
+        self.feature_maps["encoder"].append(output)
+
+    def decoder_hook(self, module, input, output):
+        self.feature_maps["decoder"].append(output)
+
+    def enhance_hook(self, module, input, output):
+        self.feature_maps["clstm"].append(output)
+
+    def remove_hook(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    def extract_feature_maps(self, input):
+        self.model(input)
+        return self.feature_maps

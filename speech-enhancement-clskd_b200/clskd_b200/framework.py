@@ -1,0 +1,314 @@
+"""Distillation losses on B200-native kernels, with the reference's class/function names
+(framework.py:16-306): multi-resolution STFT loss, SPKD, attention-based fusion (ABF) /
+ReviewKD, and the hierarchical context loss.
+
+  * STFT losses: reflect-pad + framed-window DFT GEMM (centred hann basis) + one fused
+    magnitude/log/L1/Frobenius reduction kernel (no cuFFT, no intermediate magnitude tensors).
+  * SPKD: split-K Gram kernel that reads every feature element once, tiny [B,B] epilogue
+    (L1 row normalisation, squared Frobenius distance), gradient dZ = (dG + dG^T) Z.
+  * ABF: 1x1 / 3x3 convolutions on the same tap-list implicit-GEMM kernels as the model, BatchNorm
+    in the fused statistics+normalise kernels, nearest resize and sigmoid attention blend fused.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import (AdaptivePoolFn, AttBlendFn, ConvPlan, FramedGemmFn, Pad1dFn, ResizeFFn, SPKDFn, SqDiffMeanFn,
+                  StftMagLossFn, TapConvFn, _codes, dense, to_logical, to_phys)
+from .tools_for_model import BatchNorm2d, ConvBNAct
+
+
+# ---------------------------------------------------------------------------------------------
+# STFT magnitude losses (framework.py:16-146)
+# ---------------------------------------------------------------------------------------------
+
+def _centred_basis(fft_size, win_length, window):
+    """[win_length, 2*(fft_size/2+1)] interleaved (re, im) DFT basis of a window centred in the
+    fft frame, i.e. torch.stft(n_fft, win_length, window) restricted to the window's support."""
+    off = (fft_size - win_length) // 2
+    n = (np.arange(win_length, dtype=np.float64) + off)[:, None]
+    k = np.arange(fft_size // 2 + 1, dtype=np.float64)[None, :]
+    ang = 2.0 * np.pi * n * k / fft_size
+    w = window.detach().cpu().double().numpy()[:, None]
+    basis = np.stack([np.cos(ang) * w, -np.sin(ang) * w], axis=2).reshape(win_length, -1)
+    return torch.from_numpy(basis.astype(np.float32))
+
+
+class _StftFrontEnd:
+    """Interleaved spectrum of torch.stft(x, n_fft, hop, win, window, center=True, reflect)."""
+
+    def __init__(self, fft_size, hop_size, win_length):
+        self.fft_size, self.hop, self.win = fft_size, hop_size, win_length
+        self._plans = {}
+
+    def plan(self, basis):
+        dev = basis.device
+        if dev not in self._plans:
+            K, N = basis.shape
+            self._plans[dev] = ConvPlan("conv", _codes((K, N), 0)[None, None], 1, 0, 0, K, 0, None, K * N, 0, dev)
+        return self._plans[dev]
+
+    def __call__(self, x, basis):
+        if x.dim() != 2:
+            x = x.reshape(-1, x.shape[-1])
+        L = x.shape[-1]
+        off = (self.fft_size - self.win) // 2
+        left = self.fft_size // 2 - off
+        T = 1 + L // self.hop
+        right = (T - 1) * self.hop + self.win - L - left
+        if right < 0:          # trailing samples that no frame covers
+            x = x[:, :L + right]
+            right = 0
+        xpad = Pad1dFn.apply(x, left, right, 1)
+        spec = FramedGemmFn.apply(self.plan(basis), basis.view(-1), xpad, self.win, self.hop)   # [B, T, 2*nb]
+        return spec.view(spec.shape[0], spec.shape[1], -1, 2)
+
+
+def stft(x, fft_size, hop_size, win_length, window):
+    """Magnitude spectrogram (B, #frames, fft_size//2+1), sqrt(clamp(re^2+im^2, 1e-7))."""
+    basis = _centred_basis(fft_size, win_length, window).to(x.device)
+    spec = _StftFrontEnd(fft_size, hop_size, win_length)(x, basis)
+    return torch.sqrt(torch.clamp(spec[..., 0] ** 2 + spec[..., 1] ** 2, min=1e-7))
+
+
+class SpectralConvergengeLoss(nn.Module):
+    def forward(self, x_mag, y_mag):
+        return torch.norm(y_mag - x_mag, p="fro") / torch.norm(y_mag, p="fro")
+
+
+class LogSTFTMagnitudeLoss(nn.Module):
+    def forward(self, x_mag, y_mag):
+        return torch.mean(torch.abs(torch.log(y_mag) - torch.log(x_mag)))
+
+
+class STFTLoss(nn.Module):
+    """forward(x, y) -> (spectral convergence, log-magnitude L1), both from one fused reduction."""
+
+    def __init__(self, fft_size=1024, shift_size=120, win_length=600, window="hann_window"):
+        super().__init__()
+        self.fft_size, self.shift_size, self.win_length = fft_size, shift_size, win_length
+        self.register_buffer("window", getattr(torch, window)(win_length))
+        self.register_buffer("basis", _centred_basis(fft_size, win_length, self.window), persistent=False)
+        self.spectral_convergenge_loss = SpectralConvergengeLoss()
+        self.log_stft_magnitude_loss = LogSTFTMagnitudeLoss()
+        self._front = _StftFrontEnd(fft_size, shift_size, win_length)
+
+    def forward(self, x, y):
+        ops._require_cuda(x, y)
+        if self.basis.device != x.device:
+            self.to(x.device)
+        xs = self._front(x, self.basis)
+        with torch.no_grad():
+            ys = self._front(y.detach(), self.basis)
+        sc_loss, mag_loss = StftMagLossFn.apply(xs, ys)
+        return sc_loss, mag_loss
+
+
+class MultiResolutionSTFTLoss(nn.Module):
+    def __init__(self, fft_sizes=[1024, 2048, 512], hop_sizes=[120, 240, 50], win_lengths=[600, 1200, 240],
+                 window="hann_window", factor_sc=0.1, factor_mag=0.1):
+        super().__init__()
+        assert len(fft_sizes) == len(hop_sizes) == len(win_lengths)
+        self.stft_losses = nn.ModuleList(STFTLoss(fs, ss, wl, window)
+                                         for fs, ss, wl in zip(fft_sizes, hop_sizes, win_lengths))
+        self.factor_sc, self.factor_mag = factor_sc, factor_mag
+
+    def forward(self, x, y):
+        sc_loss, mag_loss = 0.0, 0.0
+        for f in self.stft_losses:
+            sc_l, mag_l = f(x, y)
+            sc_loss = sc_loss + sc_l
+            mag_loss = mag_loss + mag_l
+        n = len(self.stft_losses)
+        return self.factor_sc * (sc_loss / n), self.factor_mag * (mag_loss / n)
+
+
+# ---------------------------------------------------------------------------------------------
+# SPKD (framework.py:150-172)
+# ---------------------------------------------------------------------------------------------
+
+def _any_order_flat(x):
+    """A dense tensor holding x's elements per batch row in SOME fixed order.  The Gram matrix sums
+    over the flattened axis, so the channels-last physical tensor can be used as is."""
+    if x.dim() == 4:
+        p = x.permute(0, 3, 2, 1)
+        if p.is_contiguous():
+            return p
+    if x.is_contiguous():
+        return x
+    return dense(x)
+
+
+class SPKDLoss(nn.Module):
+    """Similarity-preserving KD: || rownorm_1(Z_t Z_t^T) - rownorm_1(Z_s Z_s^T) ||_F^2 (/B^2 for
+    'batchmean').  As in the reference the tensors are given to the constructor and forward()
+    takes no arguments.  The teacher feature is a constant of the loss."""
+
+    def __init__(self, student_output, teacher_output, reduction, **kwargs):
+        super().__init__()
+        self.student_outputs = student_output
+        self.teacher_outputs = teacher_output
+        self.reduction = reduction
+
+    def forward(self, *args, **kwargs):
+        zs, zt = self.student_outputs, self.teacher_outputs
+        ops._require_cuda(zs, zt)
+        B = zt.shape[0]
+        scale = 1.0 / (B * B) if self.reduction == 'batchmean' else 1.0
+        return SPKDFn.apply(_any_order_flat(zs), _any_order_flat(zt.detach()), scale)
+
+
+# ---------------------------------------------------------------------------------------------
+# ABF / ReviewKD (framework.py:176-284)
+# ---------------------------------------------------------------------------------------------
+
+class RealConv2d(nn.Module):
+    """nn.Conv2d-compatible parameters (`weight` [Cout,Cin,KH,KW], optional `bias`), stride 1,
+    symmetric zero padding; kernel axis 0 runs over F, axis 1 over T (NCHW = [B,C,F,T])."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, padding=0, bias=True):
+        super().__init__()
+        ks = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+        pd = (padding, padding) if isinstance(padding, int) else tuple(padding)
+        self.in_channels, self.out_channels, self.kernel_size, self.padding = in_channels, out_channels, ks, pd
+        self.weight = nn.Parameter(torch.empty((out_channels, in_channels) + ks))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if bias:
+            bound = 1.0 / math.sqrt(in_channels * ks[0] * ks[1])
+            self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-bound, bound))
+        else:
+            self.register_parameter('bias', None)
+        self._plans = {}
+
+    def plan(self, c0=None):
+        dev = self.weight.device
+        c0 = self.in_channels if c0 is None else c0
+        key = (dev, c0)
+        if key not in self._plans:
+            code = _codes(tuple(self.weight.shape), 0).transpose(2, 3, 1, 0)
+            bt = None
+            if self.bias is not None:
+                j = np.arange(self.out_channels)
+                bt = np.stack([j * 4, np.full_like(j, -1)], 1).astype(np.int32)
+            self._plans[key] = ConvPlan("conv", code, 1, self.padding[0], self.padding[1], c0,
+                                        self.in_channels - c0, bt, self.weight.numel(), 0, dev,
+                                        t_extra=2 * self.padding[1])
+        return self._plans[key]
+
+    def forward_phys(self, x0, x1=None, out_dtype=None):
+        plan = self.plan(x0.shape[-1] if x1 is not None else None)
+        return TapConvFn.apply(plan, x0, x1, self.weight, None, self.bias, None, out_dtype or x0.dtype)
+
+    def forward(self, inputs):
+        return to_logical(self.forward_phys(to_phys(inputs)))
+
+
+class ABF(nn.Module):
+    """Attention-based fusion block.  forward(x, y, shape, out_shape, feature_type) -> (out, fused)
+    x: student map [B, in, H, W]; y: fused map of the next-deeper level [B, mid, H', W]."""
+
+    def __init__(self, in_channel, mid_channel, out_channel, fuse):
+        super().__init__()
+        self.conv1 = ConvBNAct(RealConv2d(in_channel, mid_channel, 1, bias=False), BatchNorm2d(mid_channel))
+        self.conv2 = ConvBNAct(RealConv2d(mid_channel, out_channel, 3, padding=1, bias=False),
+                               BatchNorm2d(out_channel))
+        self.att_conv = nn.Sequential(RealConv2d(mid_channel * 2, 2, 1), nn.Sigmoid()) if fuse else None
+        nn.init.kaiming_uniform_(self.conv1[0].weight, a=1)
+        nn.init.kaiming_uniform_(self.conv2[0].weight, a=1)
+
+    def forward(self, x, y=None, shape=None, out_shape=None, feature_type=None):
+        xp = self.conv1.forward_phys(to_phys(x))
+        if self.att_conv is not None:
+            yp = to_phys(y, xp.dtype, need_dense=True)
+            if yp.shape[1] != xp.shape[1]:
+                raise NotImplementedError("ABF: residual and feature maps must share the time axis")
+            if yp.shape[2] != shape:
+                yp = ResizeFFn.apply(yp, shape)          # F.interpolate(y, (shape, w), 'nearest')
+            z = self.att_conv[0].forward_phys(xp, yp, torch.float32)      # logits [B,T,F,2]
+            xp = AttBlendFn.apply(xp, yp, z)             # x*sigmoid(z0) + y*sigmoid(z1)
+        if out_shape is not None and xp.shape[2] != out_shape:
+            xp = ResizeFFn.apply(xp, out_shape)
+        out = self.conv2.forward_phys(xp)
+        return to_logical(out), to_logical(xp)
+
+
+class ReviewKD(nn.Module):
+    """Chain of ABFs from the deepest level to the shallowest (framework.py:226-263).
+    in_channels / out_channels are listed shallow -> deep; shapes / out_shapes deep -> shallow."""
+
+    def __init__(self, in_channels, out_channels, shapes, out_shapes, feature_maps, ft_type):
+        super().__init__()
+        self.shapes = shapes
+        self.out_shapes = shapes if out_shapes is None else out_shapes
+        self.feature_maps = feature_maps
+        self.ft_type = ft_type
+        mid_channel = min(512, in_channels[-1])
+        last = len(in_channels) - 1
+        blocks = [ABF(cin, mid_channel, out_channels[idx], idx < last) for idx, cin in enumerate(in_channels)]
+        self.abfs = nn.ModuleList(blocks[::-1])
+        if len(feature_maps) and torch.is_tensor(feature_maps[0]):
+            self.to(feature_maps[0].device)
+
+    def forward(self, x=None):
+        if self.ft_type not in ('encoder', 'decoder'):
+            raise ValueError("ft_type must be 'encoder' or 'decoder'")
+        maps = self.feature_maps[::-1] if self.ft_type == 'encoder' else list(self.feature_maps)
+        out, res = self.abfs[0](maps[0], out_shape=self.out_shapes[0], feature_type=self.ft_type)
+        results = [out]
+        for fmap, abf, shape, out_shape in zip(maps[1:], self.abfs[1:], self.shapes[1:], self.out_shapes[1:]):
+            out, res = abf(fmap, res, shape, out_shape, feature_type=self.ft_type)
+            if self.ft_type == 'encoder':
+                results.insert(0, out)
+            else:
+                results.append(out)
+        return results
+
+
+_REF_TEACHER_CHANNELS = [32, 64, 128, 256, 256, 256]
+
+
+def build_review_kd(feature_maps, ft_type, out_channels=None):
+    """ReviewKD for a list of student feature maps.  The reference hard-codes the channel / shape
+    lists of its asteroid student (framework.py:266-284); here they are read off the maps, which
+    reproduces those lists for that model and also fits the local DCCRN.  `out_channels`
+    (shallow -> deep) defaults to the reference's teacher widths."""
+    if ft_type == 'encoder':
+        in_channels = [m.shape[1] for m in feature_maps]
+        shapes = [m.shape[2] for m in feature_maps][::-1]
+    elif ft_type == 'decoder':
+        in_channels = [m.shape[1] for m in feature_maps][::-1]
+        shapes = [m.shape[2] for m in feature_maps]
+    else:
+        raise ValueError("ft_type must be 'encoder' or 'decoder'")
+    if out_channels is None:
+        out_channels = _REF_TEACHER_CHANNELS[:len(in_channels)]
+    return ReviewKD(in_channels, list(out_channels), shapes, list(shapes), feature_maps, ft_type)
+
+
+# ---------------------------------------------------------------------------------------------
+# hcl (framework.py:287-306)
+# ---------------------------------------------------------------------------------------------
+
+def hcl(fstudent, fteacher, t_type=None):
+    """Hierarchical context loss: MSE plus MSEs of adaptive-average-pooled (4,2,1) pyramids with
+    weights 1/2, 1/4, 1/8, normalised.  Accepts [B,C,H,W] maps (the reference unpacks three
+    dims from four-dimensional maps and cannot run; this is the intended computation)."""
+    loss_all = 0.0
+    for fs, ft in zip(fstudent, fteacher):
+        while fs.dim() < 4:
+            fs, ft = fs.unsqueeze(0), ft.unsqueeze(0)
+        h = fs.shape[2]
+        ps, pt = to_phys(fs, need_dense=True), to_phys(ft.detach(), need_dense=True)
+        loss = SqDiffMeanFn.apply(ps, pt)
+        cnt, tot = 1.0, 1.0
+        for l in (4, 2, 1):
+            if l >= h:
+                continue
+            cnt /= 2.0
+            loss = loss + SqDiffMeanFn.apply(AdaptivePoolFn.apply(ps, l), AdaptivePoolFn.apply(pt, l)) * cnt
+            tot += cnt
+        loss_all = loss_all + loss / tot
+    return loss_all

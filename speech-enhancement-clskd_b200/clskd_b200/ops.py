@@ -1,0 +1,924 @@
+"""Host-side plumbing between torch tensors and the C ABI: precision policy, tensor-layout
+helpers, the tap-list convolution plans and every autograd Function of the path.
+
+Internal ("physical") activation layout is channels-last [B, T, F, C]; the reference's logical
+NCHW tensors [B, C, F, T] are exposed as `.permute(0, 3, 2, 1)` views of it (no copies).
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TapConv, call
+
+# --------------------------------------------------------------------------------------------
+# precision policy
+# --------------------------------------------------------------------------------------------
+
+
+class _Policy:
+    """fp32: fp32 activations, fp32 FMA contractions (exact-parity policy, <=1e-5 waveform error).
+    bf16: bf16 activations/weights on the tcgen05 tensor cores with fp32 accumulation; STFT/iSTFT,
+    BatchNorm statistics, LSTM state, mask math and all loss reductions stay fp32/fp64."""
+
+    def __init__(self):
+        self.name = "fp32"
+        self.act_dtype = torch.float32
+        self.use_umma = False
+
+
+policy = _Policy()
+
+
+def set_precision(name: str):
+    if name not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    policy.name = name
+    policy.act_dtype = torch.float32 if name == "fp32" else torch.bfloat16
+    policy.use_umma = name == "bf16"
+
+
+def get_precision() -> str:
+    return policy.name
+
+
+def _tag(dtype):
+    if dtype == torch.float32:
+        return _lib.F32
+    if dtype == torch.bfloat16:
+        return _lib.BF16
+    raise RuntimeError("clskd_b200: unsupported dtype %s (fp32 / bf16 only)" % dtype)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("clskd_b200 runs on CUDA tensors only (no CPU fallback); got a %s tensor"
+                               % t.device)
+
+
+def _ptr(t, offset=0):
+    if t is None:
+        return None
+    return t.data_ptr() + offset * t.element_size()
+
+
+def _f32c(t):
+    """fp32 contiguous version of a (small) parameter tensor without launching kernels if possible."""
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t
+    return t.detach().float().contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# layout helpers
+# --------------------------------------------------------------------------------------------
+
+def _pad4(v, fill):
+    v = list(v)
+    while len(v) < 4:
+        v.insert(0, fill)
+    if len(v) > 4:
+        raise RuntimeError("strided copy supports up to 4 dims")
+    return v
+
+
+def strided_copy_into(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[...] = src[...] for two same-shape (<=4-D) strided views; dtype conversion allowed."""
+    _require_cuda(src, dst)
+    if tuple(src.shape) != tuple(dst.shape):
+        raise RuntimeError("strided_copy_into: shape mismatch %s vs %s" % (tuple(src.shape), tuple(dst.shape)))
+    shape = _pad4(src.shape, 1)
+    call("clskd_strided_copy4d", src.data_ptr(), _tag(src.dtype), (ctypes.c_int64 * 4)(*_pad4(src.stride(), 0)),
+         dst.data_ptr(), _tag(dst.dtype), (ctypes.c_int64 * 4)(*_pad4(dst.stride(), 0)),
+         (ctypes.c_int64 * 4)(*shape), _stream())
+    return dst
+
+
+def strided_copy(src: torch.Tensor, dtype=None) -> torch.Tensor:
+    """Dense copy of an arbitrary <=4-D strided view, with optional dtype conversion."""
+    dst = torch.empty(src.shape, dtype=dtype or src.dtype, device=src.device)
+    return strided_copy_into(src, dst)
+
+
+class _DenseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.in_dtype = x.dtype
+        return strided_copy(x, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = dense(g, ctx.in_dtype) if (g.dtype != ctx.in_dtype or not g.is_contiguous()) else g
+        return g, None
+
+
+def dense(x: torch.Tensor, dtype=None) -> torch.Tensor:
+    """x as a contiguous tensor of `dtype` (own copy kernel; identity when already so)."""
+    dtype = dtype or x.dtype
+    if x.dtype == dtype and x.is_contiguous():
+        return x
+    if x.requires_grad and torch.is_grad_enabled():
+        return _DenseFn.apply(x, dtype)
+    return strided_copy(x, dtype)
+
+
+def to_phys(x_logical: torch.Tensor, dtype=None, need_dense=False) -> torch.Tensor:
+    """logical [B, C, F, T] -> physical [B, T, F, C] with unit channel stride (a view whenever the
+    logical tensor is itself a view of a physical one; copied by the layout kernel otherwise)."""
+    p = x_logical.permute(0, 3, 2, 1)
+    dtype = dtype or p.dtype
+    if p.dtype == dtype and not need_dense and (p.shape[3] == 1 or p.stride(3) == 1) and \
+            (p.shape[2] == 1 or p.stride(2) == p.shape[3]):
+        return p
+    return dense(p, dtype)
+
+
+def to_logical(x_phys: torch.Tensor) -> torch.Tensor:
+    return x_phys.permute(0, 3, 2, 1)
+
+
+# --------------------------------------------------------------------------------------------
+# tap-list convolution plans
+# --------------------------------------------------------------------------------------------
+
+@dataclass
+class Launch:
+    """One tapconv launch: taps, input stride, and where its outputs go (sub-pixel phase)."""
+    dt: List[int]
+    df: List[int]
+    sf: int = 1          # input-f step per output row
+    osf: int = 1         # output f = osf*m + ooff
+    ooff: int = 0
+    blk: Optional[np.ndarray] = None      # int64 codes [ntaps][K][N] (host)
+    device: Optional[torch.device] = None
+    _t_cn: Optional[torch.Tensor] = None
+    _t_nc: Optional[torch.Tensor] = None
+    K: int = 0           # contraction channels (c)
+    N: int = 0           # output channels (n)
+    c_lo: int = 0        # for dgrad launches: slice [c_lo, c_lo+N) of the input channels
+    woff: int = 0        # offset of this launch's dW block in the concatenated wgrad buffer
+
+    # pack tables (int32 pairs on the device), built on first use: [tap][c][n] and [tap][n][c]
+    @property
+    def t_cn(self):
+        if self._t_cn is None:
+            self._t_cn = torch.from_numpy(_pairs(self.blk.reshape(-1))).to(self.device)
+        return self._t_cn
+
+    @property
+    def t_nc(self):
+        if self._t_nc is None:
+            self._t_nc = torch.from_numpy(_pairs(self.blk.transpose(0, 2, 1).reshape(-1))).to(self.device)
+        return self._t_nc
+
+
+def _codes(shape, sel):
+    n = int(np.prod(shape))
+    return (np.arange(n, dtype=np.int64) * 4 + sel).reshape(shape)
+
+
+def _neg(code):
+    return code + 2
+
+
+def _pairs(code_flat):
+    """int32 pair table from a flat array of single codes."""
+    t = np.full((code_flat.size, 2), -1, dtype=np.int32)
+    t[:, 0] = code_flat.astype(np.int32)
+    return t
+
+
+class ConvPlan:
+    """Everything static about one convolution-like layer: forward / data-gradient / weight-gradient
+    launches and the gather tables that build packed weights from (and fold gradients back onto)
+    the reference's parameter tensors.
+
+    `block` is an int64 code array [KF, KT, Ctot, N] (see clskd_pack_gather) describing the dense
+    real-valued weight of the layer in terms of the parameter tensors a (sel 0) and b (sel 1).
+    kind 'conv': Y[t,f] = sum X[t - pt + kt, f*sf - pf + kf]      (strided convolution)
+    kind 'deconv': Y[ti - pt + kt, fi*sf - pf + kf] += X[ti, fi]  (transposed convolution)
+    """
+
+    def __init__(self, kind, block, sf, pf, pt, c0, c1, bias_table, na, nb, device,
+                 t_extra=0, f_extra=0):
+        self.kind, self.sf, self.pf, self.pt = kind, sf, pf, pt
+        KF, KT, Ctot, N = block.shape
+        self.KF, self.KT, self.Ctot, self.N = KF, KT, Ctot, N
+        self.c0, self.c1 = c0, c1
+        assert c0 + c1 == Ctot
+        self.t_extra, self.f_extra = t_extra, f_extra   # output-size corrections (see out_size)
+        self.na, self.nb = na, nb                       # numel of parameter a / b
+        self.device = device
+        self.fwd: List[Launch] = []
+        self.dgrad: List[List[Launch]] = [[], []]       # per source
+        taps = [(kf, kt) for kf in range(KF) for kt in range(KT)]
+
+        def mk(sel_taps, dts, dfs, sf_, osf, ooff, transpose=False, c_lo=0, c_n=None):
+            blk = np.stack([block[kf, kt] for kf, kt in sel_taps], 0)      # [ntaps, Ctot, N]
+            if c_n is not None:
+                blk = blk[:, c_lo:c_lo + c_n, :]
+            if transpose:                                                   # dgrad: contract n
+                blk = blk.transpose(0, 2, 1)
+            return Launch(dt=dts, df=dfs, sf=sf_, osf=osf, ooff=ooff, K=blk.shape[1], N=blk.shape[2],
+                          c_lo=c_lo, blk=blk, device=device)
+
+        if kind == "conv":
+            self.fwd.append(mk(taps, [kt - pt for _, kt in taps], [kf - pf for kf, _ in taps], sf, 1, 0))
+            for src, (lo, cn) in enumerate(((0, c0), (c0, c1))):
+                if cn == 0:
+                    continue
+                for p in range(sf):
+                    sel = [(kf, kt) for kf, kt in taps if (kf - pf - p) % sf == 0]
+                    if not sel:
+                        continue
+                    self.dgrad[src].append(mk(sel, [-(kt - pt) for _, kt in sel],
+                                              [(p - (kf - pf)) // sf for kf, _ in sel], 1, sf, p,
+                                              transpose=True, c_lo=lo, c_n=cn))
+        elif kind == "deconv":
+            for p in range(sf):
+                sel = [(kf, kt) for kf, kt in taps if (p + pf - kf) % sf == 0]
+                if not sel:
+                    continue
+                self.fwd.append(mk(sel, [pt - kt for _, kt in sel], [(p + pf - kf) // sf for kf, _ in sel],
+                                   1, sf, p))
+            for src, (lo, cn) in enumerate(((0, c0), (c0, c1))):
+                if cn == 0:
+                    continue
+                self.dgrad[src].append(mk(taps, [kt - pt for _, kt in taps], [kf - pf for kf, _ in taps],
+                                          sf, 1, 0, transpose=True, c_lo=lo, c_n=cn))
+        else:
+            raise ValueError(kind)
+
+        # ---- wgrad: concatenated dW buffers of the forward launches -> parameters a / b
+        off = 0
+        for l in self.fwd:
+            l.woff = off
+            off += l.blk.size
+        self.wcat = off
+        self._unpack = [None, None]
+        # ---- bias: bias_table is an int32 pair table [N,2] over (bias_a, bias_b) or None
+        self.bias_table = None
+        self.bias_unpack_a = self.bias_unpack_b = None
+        if bias_table is not None:
+            self.bias_table = torch.from_numpy(bias_table.astype(np.int32)).to(device)
+            nba = nbb = 0
+            ents = {0: {}, 1: {}}
+            for i in range(bias_table.shape[0]):
+                for e in bias_table[i]:
+                    if e >= 0:
+                        ents[e & 1].setdefault(e >> 2, []).append(i * 2 + ((e >> 1) & 1))
+            for sel in (0, 1):
+                if ents[sel]:
+                    n = max(ents[sel]) + 1
+                    t = np.full((n, 2), -1, dtype=np.int32)
+                    for j, es in ents[sel].items():
+                        for k, e in enumerate(es[:2]):
+                            t[j, k] = e
+                    tt = torch.from_numpy(t).to(device)
+                    if sel == 0:
+                        self.bias_unpack_a = tt
+                    else:
+                        self.bias_unpack_b = tt
+
+    def _unpack_table(self, sel):
+        """[n_param, 2] int32 table: where each parameter element sits in the concatenated dW buffer."""
+        if self._unpack[sel] is None:
+            n = self.na if sel == 0 else self.nb
+            idx_all, val_all = [], []
+            for l in self.fwd:
+                codes = l.blk.reshape(-1)
+                pos = np.nonzero((codes >= 0) & ((codes & 1) == sel))[0]
+                e = codes[pos]
+                idx_all.append(e >> 2)
+                val_all.append((l.woff + pos) * 2 + ((e >> 1) & 1))
+            idx = np.concatenate(idx_all)
+            val = np.concatenate(val_all)
+            order = np.argsort(idx, kind="stable")
+            idx, val = idx[order], val[order]
+            rank = np.arange(idx.size) - np.searchsorted(idx, idx, side="left")
+            assert rank.size == 0 or rank.max() <= 1, "a parameter element may appear at most twice"
+            t = np.full((n, 2), -1, dtype=np.int32)
+            t[idx, rank] = val.astype(np.int32)
+            self._unpack[sel] = torch.from_numpy(t).to(self.device)
+        return self._unpack[sel]
+
+    @property
+    def unpack_a(self):
+        return self._unpack_table(0)
+
+    @property
+    def unpack_b(self):
+        return self._unpack_table(1) if self.nb else None
+
+    # output extents for an input of (Ti, Fi)
+    def out_size(self, Ti, Fi):
+        if self.kind == "conv":
+            To = Ti + self.t_extra - (self.KT - 1)
+            Fo = (Fi + 2 * self.pf - self.KF) // self.sf + 1
+        else:
+            To = (Ti - 1) - 2 * self.pt + self.KT + self.t_extra
+            Fo = (Fi - 1) * self.sf - 2 * self.pf + self.KF + self.f_extra
+        return To, Fo
+
+
+def pack_weights(table, a, b, dtype):
+    n = table.shape[0]
+    out = torch.empty(n, dtype=dtype, device=table.device)
+    call("clskd_pack_gather", a.data_ptr(), b.data_ptr() if b is not None else None,
+         table.data_ptr(), n, out.data_ptr(), _tag(dtype), _stream())
+    return out
+
+
+def unpack_grads(src, table2, n):
+    dst = torch.empty(n, dtype=torch.float32, device=src.device)
+    call("clskd_unpack_gather2", src.data_ptr(), table2.data_ptr(), n, dst.data_ptr(), 0, _stream())
+    return dst
+
+
+def _fill_desc(d: TapConv, x0, x0_off, x0_str, x1, x1_off, x1_str, c0, c1, B, To, Fo, Ti, Fi, l: Launch,
+               w, bias, N, y, y_off, y_str, accumulate=False):
+    d.x0 = _ptr(x0, x0_off)
+    d.x1 = _ptr(x1, x1_off) if x1 is not None else None
+    d.x0_sB, d.x0_sT, d.x0_sF = x0_str
+    if x1 is not None:
+        d.x1_sB, d.x1_sT, d.x1_sF = x1_str
+    d.c0, d.c1 = c0, c1
+    d.B, d.To, d.Fo, d.Ti, d.Fi = B, To, Fo, Ti, Fi
+    d.sf = l.sf
+    d.ntaps = len(l.dt)
+    for i, (a, b_) in enumerate(zip(l.dt, l.df)):
+        d.dt[i] = a
+        d.df[i] = b_
+    d.w = w.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.N = N
+    d.y = _ptr(y, y_off)
+    d.y_sB, d.y_sT, d.y_sF = y_str
+    d.x_dtype = _tag(x0.dtype)
+    d.y_dtype = _tag(y.dtype)
+    d.accumulate = 1 if accumulate else 0
+
+
+def _umma_ok(d: TapConv) -> bool:
+    if not policy.use_umma:
+        return False
+    return bool(_lib.load().clskd_tapconv_umma_supported(ctypes.byref(d)))
+
+
+umma_launches = 0
+core_launches = 0
+
+
+def _view_of(t):
+    """(elem_offset, (sB, sT, sF)) of a 4-D [B,T,F,C] tensor whose channel stride is 1."""
+    if t.dim() != 4 or (t.shape[3] > 1 and t.stride(3) != 1):
+        raise RuntimeError("tapconv operand must be a 4-D [B,T,F,C] tensor with unit channel stride")
+    return 0, (t.stride(0), t.stride(1), t.stride(2))
+
+
+def run_tapconv(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, a, b, bias, y, x0_view=None, x1_view=None,
+                y_view=None, accumulate=False, allow_umma=True):
+    """Run one launch.  *_view = (elem_offset, (sB, sT, sF)) override the tensors' own strides."""
+    global umma_launches, core_launches
+    x0_off, x0_str = x0_view if x0_view is not None else _view_of(x0)
+    if x1 is not None:
+        x1_off, x1_str = x1_view if x1_view is not None else _view_of(x1)
+    else:
+        x1_off, x1_str = 0, (0, 0, 0)
+    y_off, y_str = y_view if y_view is not None else _view_of(y)
+    d = TapConv()
+    _fill_desc(d, x0, x0_off, x0_str, x1, x1_off, x1_str, c0, c1, B, To, Fo, Ti, Fi, l, x0, bias,
+               l.N, y, y_off, y_str, accumulate)
+    if allow_umma and _umma_ok(d):
+        w = pack_weights(l.t_nc, a, b, torch.bfloat16)
+        d.w = w.data_ptr()
+        call("clskd_tapconv_fwd_umma", ctypes.byref(d), _stream())
+        umma_launches += 1
+    else:
+        w = pack_weights(l.t_cn, a, b, torch.float32)
+        d.w = w.data_ptr()
+        call("clskd_tapconv_fwd", ctypes.byref(d), _stream())
+        core_launches += 1
+    return y
+
+
+def run_wgrad(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, dy, dw_out, x0_view=None, x1_view=None,
+              dy_view=None):
+    x0_off, x0_str = x0_view if x0_view is not None else _view_of(x0)
+    if x1 is not None:
+        x1_off, x1_str = x1_view if x1_view is not None else _view_of(x1)
+    else:
+        x1_off, x1_str = 0, (0, 0, 0)
+    y_off, y_str = dy_view if dy_view is not None else _view_of(dy)
+    d = TapConv()
+    _fill_desc(d, x0, x0_off, x0_str, x1, x1_off, x1_str, c0, c1, B, To, Fo, Ti, Fi, l, dw_out, None,
+               l.N, dy, y_off, y_str, False)
+    call("clskd_tapconv_wgrad", ctypes.byref(d), _stream())
+
+
+def _chan_ok(t):
+    """usable as a tapconv operand without a copy: 4-D, unit channel stride"""
+    return t.dim() == 4 and (t.shape[3] == 1 or t.stride(3) == 1)
+
+
+class TapConvFn(torch.autograd.Function):
+    """Generic convolution-like operator on physical tensors.
+
+    forward(plan, x0, x1, a, b, bias_a, bias_b) -> y [B, To, Fo, N]
+    x0/x1: dense [B, Ti, Fi, c0/c1]; a/b: parameter tensors referenced by the plan's tables.
+    """
+
+    @staticmethod
+    def forward(ctx, plan: ConvPlan, x0, x1, a, b, bias_a, bias_b, out_dtype):
+        _require_cuda(x0, x1, a)
+        if not _chan_ok(x0):
+            x0 = strided_copy(x0)
+        if x1 is not None and (not _chan_ok(x1) or x1.dtype != x0.dtype):
+            x1 = strided_copy(x1, x0.dtype)
+        B, Ti, Fi, _ = x0.shape
+        To, Fo = plan.out_size(Ti, Fi)
+        a32 = _f32c(a)
+        b32 = _f32c(b) if b is not None else None
+        bias = None
+        if plan.bias_table is not None and bias_a is not None:
+            bias = pack_weights(plan.bias_table, _f32c(bias_a), _f32c(bias_b) if bias_b is not None else None,
+                                torch.float32)
+        y = torch.empty((B, To, Fo, plan.N), dtype=out_dtype, device=x0.device)
+        for l in plan.fwd:
+            Fo_l = Fo // l.osf
+            yv = (l.ooff * plan.N, (To * Fo * plan.N, Fo * plan.N, l.osf * plan.N))
+            run_tapconv(x0, x1, plan.c0, plan.c1, B, To, Fo_l, Ti, Fi, l, a32, b32, bias, y, y_view=yv)
+        ctx.plan = plan
+        ctx.save_for_backward(x0, x1, a, b)
+        ctx.has_bias = (bias_a is not None, bias_b is not None)
+        ctx.dims = (B, Ti, Fi, To, Fo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        plan: ConvPlan = ctx.plan
+        x0, x1, a, b = ctx.saved_tensors
+        B, Ti, Fi, To, Fo = ctx.dims
+        dy = dense(dy, dy.dtype)
+        a32 = _f32c(a)
+        b32 = _f32c(b) if b is not None else None
+        need = ctx.needs_input_grad
+        dx0 = dx1 = da = db = dba = dbb = None
+        # ---- data gradients
+        for src, (xs, cn) in enumerate(((x0, plan.c0), (x1, plan.c1))):
+            if xs is None or not need[1 + src]:
+                continue
+            dx = torch.empty(xs.shape, dtype=xs.dtype, device=xs.device)
+            for l in plan.dgrad[src]:
+                Fi_l = Fi // l.osf
+                yv = (l.ooff * cn, (Ti * Fi * cn, Fi * cn, l.osf * cn))
+                run_tapconv(dy, None, plan.N, 0, B, Ti, Fi_l, To, Fo, l, a32, b32, None, dx, y_view=yv)
+            if src == 0:
+                dx0 = dx
+            else:
+                dx1 = dx
+        # ---- weight gradients
+        if need[3] or (b is not None and need[4]):
+            dwcat = torch.empty(plan.wcat, dtype=torch.float32, device=dy.device)
+            for l in plan.fwd:
+                Fo_l = Fo // l.osf
+                dyv = (l.ooff * plan.N, (To * Fo * plan.N, Fo * plan.N, l.osf * plan.N))
+                dw_view = dwcat[l.woff:l.woff + len(l.dt) * plan.Ctot * plan.N]
+                run_wgrad(x0, x1, plan.c0, plan.c1, B, To, Fo_l, Ti, Fi, l, dy, dw_view, dy_view=dyv)
+            if need[3]:
+                da = unpack_grads(dwcat, plan.unpack_a, plan.na).view_as(a)
+            if b is not None and need[4]:
+                db = unpack_grads(dwcat, plan.unpack_b, plan.nb).view_as(b)
+        # ---- bias gradients
+        if (ctx.has_bias[0] and need[5]) or (ctx.has_bias[1] and need[6]):
+            s, _ = colstats(dy.view(-1, plan.N))
+            s32 = f64_to_f32(s)
+            if ctx.has_bias[0] and need[5]:
+                dba = unpack_grads(s32, plan.bias_unpack_a, plan.bias_unpack_a.shape[0])
+            if ctx.has_bias[1] and need[6]:
+                dbb = unpack_grads(s32, plan.bias_unpack_b, plan.bias_unpack_b.shape[0])
+        return None, dx0, dx1, da, db, dba, dbb, None
+
+
+# --------------------------------------------------------------------------------------------
+# small wrappers
+# --------------------------------------------------------------------------------------------
+
+def colstats(x2d):
+    """x2d dense [M, C] -> (sum fp64 [C], sumsq fp64 [C])"""
+    M, C = x2d.shape
+    s = torch.empty(2, C, dtype=torch.float64, device=x2d.device)
+    call("clskd_colstats", x2d.data_ptr(), _tag(x2d.dtype), M, C, s[0].data_ptr(), s[1].data_ptr(), _stream())
+    return s[0], s[1]
+
+
+def f64_to_f32(t, scale=1.0):
+    out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+    call("clskd_f64_to_f32", t.data_ptr(), t.numel(), float(scale), out.data_ptr(), _stream())
+    return out
+
+
+class BNActFn(torch.autograd.Function):
+    """y = prelu(batchnorm(x)) over the channel (last) axis of a dense physical tensor.
+    Replaces nn.BatchNorm2d + nn.PReLU (DCCRN.py:80-82); slope=None -> no activation."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, slope, running_mean, running_var, training, momentum, eps):
+        _require_cuda(x)
+        C = x.shape[-1]
+        M = x.numel() // C
+        dev = x.device
+        stats = torch.empty(2, C, dtype=torch.float32, device=dev)
+        mean, invstd = stats[0], stats[1]
+        use_batch = training or running_mean is None
+        if use_batch:
+            s, ss = colstats(x.view(M, C))
+            call("clskd_bn_finalize", s.data_ptr(), ss.data_ptr(), M, C, float(eps),
+                 float(momentum if momentum is not None else 0.0), mean.data_ptr(), invstd.data_ptr(),
+                 running_mean.data_ptr() if (running_mean is not None and training) else None,
+                 running_var.data_ptr() if (running_var is not None and training) else None, _stream())
+        else:
+            call("clskd_bn_eval_stats", running_mean.data_ptr(), running_var.data_ptr(), C, float(eps),
+                 mean.data_ptr(), invstd.data_ptr(), _stream())
+        y = torch.empty_like(x)
+        g32 = _f32c(gamma) if gamma is not None else None
+        b32 = _f32c(beta) if beta is not None else None
+        s32 = _f32c(slope) if slope is not None else None
+        call("clskd_bn_act_fwd", x.data_ptr(), _tag(x.dtype), M, C, mean.data_ptr(), invstd.data_ptr(),
+             _ptr(g32), _ptr(b32), _ptr(s32), y.data_ptr(), _tag(y.dtype), _stream())
+        ctx.save_for_backward(x, stats, gamma, beta, slope)
+        ctx.use_batch = use_batch
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, gamma, beta, slope = ctx.saved_tensors
+        C = x.shape[-1]
+        M = x.numel() // C
+        dy = dense(dy, x.dtype)
+        mean, invstd = stats[0], stats[1]
+        g32 = _f32c(gamma) if gamma is not None else None
+        b32 = _f32c(beta) if beta is not None else None
+        s32 = _f32c(slope) if slope is not None else None
+        sums = torch.empty(2 * C + 1, dtype=torch.float64, device=x.device)
+        p_dz, p_dzx, p_ds = sums.data_ptr(), sums.data_ptr() + 8 * C, sums.data_ptr() + 16 * C
+        call("clskd_bn_act_bwd_stats", x.data_ptr(), _tag(x.dtype), dy.data_ptr(), _tag(dy.dtype), M, C,
+             mean.data_ptr(), invstd.data_ptr(), _ptr(g32), _ptr(b32), _ptr(s32), p_dz, p_dzx, p_ds, _stream())
+        dx = torch.empty_like(x)
+        pg = torch.empty(2 * C + 1, dtype=torch.float32, device=x.device)
+        call("clskd_bn_act_bwd_apply", x.data_ptr(), _tag(x.dtype), dy.data_ptr(), _tag(dy.dtype), M, C,
+             mean.data_ptr(), invstd.data_ptr(), _ptr(g32), _ptr(b32), _ptr(s32), p_dz, p_dzx, p_ds,
+             1 if ctx.use_batch else 0, dx.data_ptr(), _tag(dx.dtype), pg.data_ptr(),
+             pg.data_ptr() + 4 * C, pg.data_ptr() + 8 * C, _stream())
+        dgamma = pg[:C].view_as(gamma) if gamma is not None else None
+        dbeta = pg[C:2 * C].view_as(beta) if beta is not None else None
+        dslope = pg[2 * C:].view_as(slope) if slope is not None else None
+        return dx, dgamma, dbeta, dslope, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# STFT / iSTFT (framed-window DFT as a GEMM)
+# --------------------------------------------------------------------------------------------
+
+def _gemm_plan(weight_kn: np.ndarray, device):
+    """ConvPlan of a plain GEMM Y[m, n] = sum_k X[m, k] W[k, n] whose weight is a fixed buffer;
+    the 'parameter' a is the flat weight itself."""
+    K, N = weight_kn.shape
+    block = _codes((1, 1, K, N), 0)
+    return ConvPlan("conv", block, 1, 0, 0, K, 0, None, K * N, 0, device)
+
+
+class FramedGemmFn(torch.autograd.Function):
+    """spec[b, t, :] = frames(xpad)[b, t, :] @ W   with frames(xpad)[b,t,k] = xpad[b, t*hop + k].
+    xpad is a dense fp32 [B, Lp] signal (already padded); W = plan weight [win, N]."""
+
+    @staticmethod
+    def forward(ctx, plan: ConvPlan, w_flat, xpad, win, hop):
+        B, Lp = xpad.shape
+        T = (Lp - win) // hop + 1
+        y = torch.empty((B, T, 1, plan.N), dtype=torch.float32, device=xpad.device)
+        run_tapconv(xpad, None, win, 0, B, T, 1, T, 1, plan.fwd[0], w_flat, None, None, y,
+                    x0_view=(0, (Lp, hop, 0)), allow_umma=False)
+        ctx.plan, ctx.win, ctx.hop, ctx.dims = plan, win, hop, (B, Lp, T)
+        ctx.save_for_backward(w_flat)
+        return y.view(B, T, plan.N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (w_flat,) = ctx.saved_tensors
+        plan, win, hop = ctx.plan, ctx.win, ctx.hop
+        B, Lp, T = ctx.dims
+        dy = dense(dy, torch.float32)
+        dframes = torch.empty((B, T, 1, win), dtype=torch.float32, device=dy.device)
+        run_tapconv(dy.view(B, T, 1, plan.N), None, plan.N, 0, B, T, 1, T, 1, plan.dgrad[0][0], w_flat, None,
+                    None, dframes, allow_umma=False)
+        # overlap-add of the frame gradients (plain conv_transpose1d): length (T-1)*hop+win <= Lp
+        Lo = (T - 1) * hop + win
+        dx = torch.zeros((B, Lp), dtype=torch.float32, device=dy.device) if Lo != Lp else \
+            torch.empty((B, Lp), dtype=torch.float32, device=dy.device)
+        tmp = dx if Lo == Lp else torch.empty((B, Lo), dtype=torch.float32, device=dy.device)
+        call("clskd_ola_fwd", dframes.data_ptr(), None, B, T, win, hop, 0, 0, tmp.data_ptr(), _stream())
+        if Lo != Lp:
+            dx[:, :Lo] = tmp
+        return None, None, dx, None, None
+
+
+class Pad1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, left, right, mode):
+        _require_cuda(x)
+        B, L = x.shape
+        if x.stride(1) != 1:
+            x = dense(x)
+        out = torch.empty((B, L + left + right), dtype=torch.float32, device=x.device)
+        call("clskd_pad1d", x.data_ptr(), _tag(x.dtype), x.stride(0), B, L, left, right, mode,
+             out.data_ptr(), _stream())
+        ctx.args = (B, L, left, right, mode, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, L, left, right, mode, dt = ctx.args
+        g = dense(g, torch.float32)
+        dx = torch.empty((B, L), dtype=torch.float32, device=g.device)
+        call("clskd_pad1d_bwd", g.data_ptr(), B, L, left, right, mode, dx.data_ptr(), 0, _stream())
+        if dt != torch.float32:
+            dx = dense(dx, dt)
+        return dx, None, None, None
+
+
+class OlaFn(torch.autograd.Function):
+    """wav = clamp(overlap_add(frames) / window^2-overlap)[trim:-trim]  (tools_for_model.py:100-107,
+    DCCRN.py:235-237)."""
+
+    @staticmethod
+    def forward(ctx, frames, window, hop, trim, do_clamp):
+        B, T, win = frames.shape
+        L = (T - 1) * hop + win - 2 * trim
+        wav = torch.empty((B, L), dtype=torch.float32, device=frames.device)
+        call("clskd_ola_fwd", frames.data_ptr(), _ptr(window), B, T, win, hop, trim, 1 if do_clamp else 0,
+             wav.data_ptr(), _stream())
+        ctx.args = (B, T, win, hop, trim, do_clamp)
+        ctx.save_for_backward(wav, window)
+        return wav
+
+    @staticmethod
+    def backward(ctx, g):
+        wav, window = ctx.saved_tensors
+        B, T, win, hop, trim, do_clamp = ctx.args
+        g = dense(g, torch.float32)
+        dframes = torch.empty((B, T, win), dtype=torch.float32, device=g.device)
+        call("clskd_ola_bwd", g.data_ptr(), wav.data_ptr(), _ptr(window), B, T, win, hop, trim,
+             1 if do_clamp else 0, dframes.data_ptr(), _stream())
+        return dframes, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# mask
+# --------------------------------------------------------------------------------------------
+_MODES = {"E": 0, "C": 1, "R": 2}
+
+
+class MaskFn(torch.autograd.Function):
+    """Applies the decoder mask to the noisy spectrum (DCCRN.py:207-232).
+    spec: fp32 [B, T, nb, 2]; mask: dense physical [B, T, nb-1, 2] (any act dtype).
+    Returns (out_spec [B,T,nb,2], mask_padded [B,T,nb,2] or None)."""
+
+    @staticmethod
+    def forward(ctx, spec, mask, mode, want_masks):
+        _require_cuda(spec, mask)
+        B, T, nb, _ = spec.shape
+        out = torch.empty_like(spec)
+        mp = torch.empty_like(spec) if want_masks else None
+        call("clskd_mask_fwd", spec.data_ptr(), mask.data_ptr(), _tag(mask.dtype), mask.stride(0),
+             mask.stride(1), B, T, nb, _MODES[mode], out.data_ptr(), _ptr(mp), _stream())
+        ctx.mode = mode
+        ctx.save_for_backward(spec, mask)
+        if mp is None:
+            return out, None
+        ctx.mark_non_differentiable(mp)
+        return out, mp
+
+    @staticmethod
+    def backward(ctx, g, _gmp):
+        spec, mask = ctx.saved_tensors
+        B, T, nb, _ = spec.shape
+        g = dense(g, torch.float32)
+        dmask = torch.empty(mask.shape, dtype=mask.dtype, device=mask.device)
+        call("clskd_mask_bwd", spec.data_ptr(), mask.data_ptr(), _tag(mask.dtype), mask.stride(0),
+             mask.stride(1), B, T, nb, _MODES[ctx.mode], g.data_ptr(), dmask.data_ptr(), _tag(dmask.dtype),
+             dmask.stride(0), dmask.stride(1), _stream())
+        return None, dmask, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------------------------
+_WAVE_KINDS = {"si_snr": 0, "sdr": 1, "si_sdr": 2, "mse": 3}
+
+
+class WaveLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s1, s2, kind, eps):
+        _require_cuda(s1, s2)
+        s1 = dense(s1.reshape(-1, s1.shape[-1]), torch.float32)
+        s2 = dense(s2.reshape(-1, s2.shape[-1]), torch.float32)
+        if s1.shape != s2.shape:
+            raise RuntimeError("wave loss: shape mismatch %s vs %s" % (tuple(s1.shape), tuple(s2.shape)))
+        B, L = s1.shape
+        part = torch.empty(B, 4, dtype=torch.float64, device=s1.device)
+        out = torch.empty((), dtype=torch.float32, device=s1.device)
+        call("clskd_wave_loss_fwd", s1.data_ptr(), s2.data_ptr(), B, L, _WAVE_KINDS[kind], float(eps),
+             part.data_ptr(), out.data_ptr(), _stream())
+        ctx.kind, ctx.eps = kind, eps
+        ctx.save_for_backward(s1, s2, part)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        s1, s2, part = ctx.saved_tensors
+        B, L = s1.shape
+        kind = ctx.kind
+        g = dense(g, torch.float32)
+        n1, n2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if kind == "si_snr" and n2:
+            raise RuntimeError("si_snr: gradient w.r.t. the reference signal is not implemented")
+        if kind == "si_sdr" and n1:
+            raise RuntimeError("si_sdr: gradient w.r.t. the reference signal is not implemented")
+        d1 = torch.empty_like(s1) if n1 else None
+        d2 = torch.empty_like(s2) if n2 else None
+        call("clskd_wave_loss_bwd", s1.data_ptr(), s2.data_ptr(), B, L, _WAVE_KINDS[kind], float(ctx.eps),
+             part.data_ptr(), g.data_ptr(), _ptr(d1), _ptr(d2), _stream())
+        return d1, d2, None, None
+
+
+class StftMagLossFn(torch.autograd.Function):
+    """(sc_loss, mag_loss) of framework.py:35-68 from interleaved spectra [M, nb, 2] (fp32)."""
+
+    @staticmethod
+    def forward(ctx, xs, ys):
+        xs, ys = dense(xs, torch.float32), dense(ys, torch.float32)
+        n = xs.numel() // 2
+        part = torch.empty(3, dtype=torch.float64, device=xs.device)
+        out = torch.empty(2, dtype=torch.float32, device=xs.device)
+        call("clskd_stftmag_loss_fwd", xs.data_ptr(), ys.data_ptr(), n, part.data_ptr(), out.data_ptr(),
+             _stream())
+        ctx.save_for_backward(xs, ys, part)
+        ctx.n = n
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_sc, g_mag):
+        xs, ys, part = ctx.saved_tensors
+        n = ctx.n
+        dxs = torch.empty_like(xs)
+        g_sc = dense(g_sc, torch.float32) if g_sc is not None else None
+        g_mag = dense(g_mag, torch.float32) if g_mag is not None else None
+        call("clskd_stftmag_loss_bwd", xs.data_ptr(), ys.data_ptr(), n, part.data_ptr(), _ptr(g_mag),
+             _ptr(g_sc), 1.0 / n, 1.0, dxs.data_ptr(), _stream())
+        return dxs, None
+
+
+def gram(z2d: torch.Tensor) -> torch.Tensor:
+    """G = Z Z^T (fp32 [B,B]) of a dense [B, K] matrix."""
+    B, K = z2d.shape
+    G = torch.empty(B, B, dtype=torch.float32, device=z2d.device)
+    call("clskd_gram_fwd", z2d.data_ptr(), _tag(z2d.dtype), B, K, z2d.stride(0), G.data_ptr(), 0, _stream())
+    return G
+
+
+class SPKDFn(torch.autograd.Function):
+    """SPKD loss (framework.py:157-172) between a student feature (needs grad) and a teacher
+    feature (constant): || rownorm1(Zt Zt^T) - rownorm1(Zs Zs^T) ||_F^2 * scale."""
+
+    @staticmethod
+    def forward(ctx, zs, zt, scale):
+        _require_cuda(zs, zt)
+        B = zs.shape[0]
+        zs2 = dense(zs).view(B, -1)
+        zt2 = dense(zt).view(zt.shape[0], -1)
+        if zt2.shape[0] != B:
+            raise RuntimeError("SPKD: batch mismatch %d vs %d" % (B, zt2.shape[0]))
+        Gs, Gt = gram(zs2), gram(zt2)
+        loss = torch.empty((), dtype=torch.float32, device=zs.device)
+        dGs = torch.empty_like(Gs) if ctx.needs_input_grad[0] else None
+        call("clskd_spkd_loss", Gt.data_ptr(), Gs.data_ptr(), B, float(scale), loss.data_ptr(), _ptr(dGs),
+             _stream())
+        ctx.save_for_backward(zs2, dGs)
+        ctx.shape = zs.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        zs2, dGs = ctx.saved_tensors
+        B, K = zs2.shape
+        g = dense(g, torch.float32)
+        dz = torch.empty_like(zs2)
+        call("clskd_gram_bwd", zs2.data_ptr(), _tag(zs2.dtype), B, K, zs2.stride(0), dGs.data_ptr(),
+             g.data_ptr(), dz.data_ptr(), _tag(dz.dtype), dz.stride(0), 0, _stream())
+        return dz.view(ctx.shape), None, None
+
+
+# --------------------------------------------------------------------------------------------
+# ABF helpers
+# --------------------------------------------------------------------------------------------
+
+class ResizeFFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Fo):
+        B, T, Fi, C = x.shape
+        y = torch.empty((B, T, Fo, C), dtype=x.dtype, device=x.device)
+        call("clskd_resize_f_fwd", x.data_ptr(), _tag(x.dtype), B * T, Fi, Fo, C, y.data_ptr(), _stream())
+        ctx.dims = (B, T, Fi, Fo, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        B, T, Fi, Fo, C = ctx.dims
+        g = dense(g)
+        dx = torch.empty((B, T, Fi, C), dtype=g.dtype, device=g.device)
+        call("clskd_resize_f_bwd", g.data_ptr(), _tag(g.dtype), B * T, Fi, Fo, C, dx.data_ptr(), _stream())
+        return dx, None
+
+
+class AttBlendFn(torch.autograd.Function):
+    """x*sigmoid(z0) + y*sigmoid(z1)  (framework.py:218-219); z fp32 [.., 2] logits."""
+
+    @staticmethod
+    def forward(ctx, x, y, z):
+        C = x.shape[-1]
+        M = x.numel() // C
+        out = torch.empty_like(x)
+        call("clskd_att_blend_fwd", x.data_ptr(), y.data_ptr(), _tag(x.dtype), z.data_ptr(), M, C,
+             out.data_ptr(), _stream())
+        ctx.save_for_backward(x, y, z)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, z = ctx.saved_tensors
+        C = x.shape[-1]
+        M = x.numel() // C
+        g = dense(g, x.dtype)
+        dx, dy, dz = torch.empty_like(x), torch.empty_like(y), torch.empty_like(z)
+        call("clskd_att_blend_bwd", x.data_ptr(), y.data_ptr(), _tag(x.dtype), z.data_ptr(), g.data_ptr(), M, C,
+             dx.data_ptr(), dy.data_ptr(), dz.data_ptr(), _stream())
+        return dx, dy, dz
+
+
+class SqDiffMeanFn(torch.autograd.Function):
+    """mean((a-b)^2): F.mse_loss (DCCRN.py:261, distill_MSE.py, hcl framework.py:293)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = dense(a), dense(b)
+        n = a.numel()
+        acc = torch.zeros(1, dtype=torch.float64, device=a.device)
+        call("clskd_sqdiff_sum", a.data_ptr(), _tag(a.dtype), b.data_ptr(), _tag(b.dtype), n, acc.data_ptr(),
+             _stream())
+        ctx.save_for_backward(a, b)
+        return f64_to_f32(acc, 1.0 / n).view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        n = a.numel()
+        g = dense(g, torch.float32)
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(a)
+            call("clskd_sqdiff_bwd", a.data_ptr(), _tag(a.dtype), b.data_ptr(), _tag(b.dtype), n, g.data_ptr(),
+                 1.0 / n, da.data_ptr(), _tag(da.dtype), 0, _stream())
+        if ctx.needs_input_grad[1]:
+            db = torch.empty_like(b)
+            call("clskd_sqdiff_bwd", b.data_ptr(), _tag(b.dtype), a.data_ptr(), _tag(a.dtype), n, g.data_ptr(),
+                 1.0 / n, db.data_ptr(), _tag(db.dtype), 0, _stream())
+        return da, db
+
+
+class AdaptivePoolFn(torch.autograd.Function):
+    """adaptive_avg_pool2d over the logical (F, T) plane of a physical [B,T,F,C] map -> [B,C,l,l]."""
+
+    @staticmethod
+    def forward(ctx, x, l):
+        B, T, F, C = x.shape
+        out = torch.empty((B, C, l, l), dtype=torch.float32, device=x.device)
+        call("clskd_adaptive_pool_fwd", x.data_ptr(), _tag(x.dtype), B, T, F, C, l, out.data_ptr(), _stream())
+        ctx.dims = (B, T, F, C, l, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, T, F, C, l, dt = ctx.dims
+        g = dense(g, torch.float32)
+        dx = torch.empty((B, T, F, C), dtype=dt, device=g.device)
+        call("clskd_adaptive_pool_bwd", g.data_ptr(), B, T, F, C, l, dx.data_ptr(), _tag(dt), 0, _stream())
+        return dx, None

@@ -1,0 +1,417 @@
+"""B200-native building blocks with the reference's names, constructor signatures and
+parameter/buffer names (reference: tools_for_model.py:15-524), so `state_dict`s interchange and
+`feature_extraction` hooks keep working.  Every forward runs hand-written sm_100a kernels through
+the C ABI (see ops.py); nothing here falls back to torch's conv / RNN / FFT library calls.
+
+Tensors follow the reference's logical shapes ([B, C, F, T], [T, B, D], [B, 514, T] ...); internally
+activations are channels-last [B, T, F, C] and the logical tensors are permuted views of them.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from scipy.signal import get_window
+
+from . import ops
+from .ops import (BNActFn, ConvPlan, FramedGemmFn, OlaFn, Pad1dFn, TapConvFn, _codes, _neg, call,
+                  dense, to_logical, to_phys)
+
+
+# ---------------------------------------------------------------------------------------------
+# STFT / iSTFT filterbanks (reference: tools_for_model.py:15-109)
+# ---------------------------------------------------------------------------------------------
+
+def init_kernels(win_len, win_inc, fft_len, win_type=None, invers=False):
+    """Windowed DFT analysis basis [fft_len+2, 1, win_len] (cos rows, then -sin rows) or, with
+    invers=True, the pseudo-inverse synthesis basis; plus the window [1, win_len, 1]."""
+    if win_type is None or win_type == 'None':
+        window = np.ones(win_len)
+    else:
+        window = get_window(win_type, win_len, fftbins=True)
+    n = np.arange(win_len, dtype=np.float64)[None, :]
+    k = np.arange(fft_len // 2 + 1, dtype=np.float64)[:, None]
+    ang = 2.0 * np.pi * k * n / fft_len
+    basis = np.concatenate([np.cos(ang), -np.sin(ang)], axis=0)      # [fft_len+2, win_len]
+    if invers:
+        basis = np.linalg.pinv(basis).T
+    basis = basis * window
+    return (torch.from_numpy(basis[:, None, :].astype(np.float32)),
+            torch.from_numpy(window[None, :, None].astype(np.float32)))
+
+
+def _default_fft_len(win_len):
+    return int(2 ** math.ceil(math.log2(win_len)))
+
+
+class ConvSTFT(nn.Module):
+    """STFT as a framed-window DFT GEMM.  forward: [B, L] or [B, 1, L] -> [B, fft_len+2, T]
+    (rows 0..N/2 real, then imag), T = (L + 2*(win_len-win_inc) - win_len)//win_inc + 1."""
+
+    def __init__(self, win_len, win_inc, fft_len=None, win_type='hamming', feature_type='real', fix=True):
+        super().__init__()
+        self.fft_len = _default_fft_len(win_len) if fft_len is None else fft_len
+        kernel, _ = init_kernels(win_len, win_inc, self.fft_len, win_type)
+        self.register_buffer('weight', kernel)
+        self.feature_type = feature_type
+        self.stride = win_inc
+        self.win_len = win_len
+        self.dim = self.fft_len
+        self._plans = {}
+
+    def _plan(self, interleaved):
+        key = (interleaved, self.weight.device)
+        if key not in self._plans:
+            nrow = self.fft_len + 2
+            code = _codes((nrow, self.win_len), 0).T                  # [k, n] -> weight[n, 0, k]
+            if interleaved:                                           # columns (bin, part)
+                nb = nrow // 2
+                order = np.stack([np.arange(nb), nb + np.arange(nb)], 1).reshape(-1)
+                code = code[:, order]
+            self._plans[key] = ConvPlan("conv", code[None, None], 1, 0, 0, self.win_len, 0, None,
+                                        self.weight.numel(), 0, self.weight.device)
+        return self._plans[key]
+
+    def spectrum(self, inputs, interleaved=True):
+        """[B, L] -> fp32 [B, T, nbins, 2] (interleaved) or [B, T, fft_len+2]."""
+        if inputs.dim() == 3:
+            inputs = inputs.squeeze(1)
+        pad = self.win_len - self.stride
+        xpad = Pad1dFn.apply(inputs, pad, pad, 0)
+        spec = FramedGemmFn.apply(self._plan(interleaved), self.weight.view(-1), xpad, self.win_len, self.stride)
+        if interleaved:
+            return spec.view(spec.shape[0], spec.shape[1], -1, 2)
+        return spec
+
+    def forward(self, inputs):
+        outputs = self.spectrum(inputs, interleaved=False).permute(0, 2, 1)
+        if self.feature_type == 'complex':
+            return outputs
+        dim = self.dim // 2 + 1
+        real, imag = outputs[:, :dim, :], outputs[:, dim:, :]
+        return torch.sqrt(real ** 2 + imag ** 2), torch.atan2(imag, real)
+
+
+class ConviSTFT(nn.Module):
+    """iSTFT: synthesis-basis GEMM + overlap-add with window^2 normalisation.
+    forward: [B, fft_len+2, T] (or mags [B, N/2+1, T] + phase) -> [B, 1, L]."""
+
+    def __init__(self, win_len, win_inc, fft_len=None, win_type='hamming', feature_type='real', fix=True):
+        super().__init__()
+        self.fft_len = _default_fft_len(win_len) if fft_len is None else fft_len
+        kernel, window = init_kernels(win_len, win_inc, self.fft_len, win_type, invers=True)
+        self.register_buffer('weight', kernel)
+        self.feature_type = feature_type
+        self.win_type = win_type
+        self.win_len = win_len
+        self.stride = win_inc
+        self.dim = self.fft_len
+        self.register_buffer('window', window)
+        self.register_buffer('enframe', torch.eye(win_len)[:, None, :])   # kept for state_dict parity
+        self._plans = {}
+
+    def _plan(self, interleaved):
+        key = (interleaved, self.weight.device)
+        if key not in self._plans:
+            nrow = self.fft_len + 2
+            code = _codes((nrow, self.win_len), 0)                    # [k=row, n=sample]
+            if interleaved:
+                nb = nrow // 2
+                order = np.stack([np.arange(nb), nb + np.arange(nb)], 1).reshape(-1)
+                code = code[order, :]
+            self._plans[key] = ConvPlan("conv", code[None, None], 1, 0, 0, nrow, 0, None,
+                                        self.weight.numel(), 0, self.weight.device)
+        return self._plans[key]
+
+    def synthesize(self, spec_rows, interleaved, clamp=False):
+        """spec_rows: fp32 dense [B, T, fft_len+2] -> wav [B, L]"""
+        B, T, K = spec_rows.shape
+        frames = TapConvFn.apply(self._plan(interleaved), spec_rows.view(B, T, 1, K), None,
+                                 self.weight.view(-1), None, None, None, torch.float32)
+        return OlaFn.apply(frames.view(B, T, self.win_len), self.window.view(-1), self.stride,
+                           self.win_len - self.stride, clamp)
+
+    def forward(self, inputs, phase=None):
+        if phase is not None:
+            inputs = torch.cat([inputs * torch.cos(phase), inputs * torch.sin(phase)], 1)
+        rows = dense(inputs.permute(0, 2, 1), torch.float32)
+        return self.synthesize(rows, interleaved=False).unsqueeze(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# complex conv / deconv (reference: tools_for_model.py:193-330)
+# ---------------------------------------------------------------------------------------------
+
+class _ConvParams(nn.Module):
+    """Parameter holder with nn.Conv2d's names (`weight`, `bias`)."""
+
+    def __init__(self, shape, nbias):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(shape))
+        self.bias = nn.Parameter(torch.zeros(nbias))
+        nn.init.normal_(self.weight, std=0.05)
+
+
+def _complex_block(code_r, code_i):
+    """[KF,KT,Cin,Cout] codes of Wr / Wi -> block [KF,KT,2Cin,2Cout] = [[Wr, Wi], [-Wi, Wr]]
+    (rows: real inputs then imag inputs; columns: real outputs then imag outputs)."""
+    top = np.concatenate([code_r, code_i], axis=3)
+    bot = np.concatenate([_neg(code_i), code_r], axis=3)
+    return np.concatenate([top, bot], axis=2)
+
+
+def _complex_bias_table(cout):
+    """bias = [br - bi, br + bi]  (a = real bias, b = imag bias)"""
+    j = np.arange(cout)
+    t = np.empty((2 * cout, 2), dtype=np.int32)
+    t[:cout, 0] = j * 4
+    t[:cout, 1] = j * 4 + 1 + 2
+    t[cout:, 0] = j * 4
+    t[cout:, 1] = j * 4 + 1
+    return t
+
+
+class ComplexConv2d(nn.Module):
+    """Complex convolution as ONE 2x-wide real contraction with block weight [[Wr,-Wi],[Wi,Wr]].
+    in_channels / out_channels count real+imag.  Input [B, in_channels, F, T] (real half of the
+    channels first), output [B, out_channels, F', T']."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=(1, 1), stride=(1, 1), padding=(0, 0),
+                 dilation=1, groups=1, causal=True, complex_axis=1):
+        super().__init__()
+        if dilation != 1 or groups != 1 or complex_axis != 1 or stride[1] != 1:
+            raise NotImplementedError("ComplexConv2d: only dilation=1, groups=1, complex_axis=1, "
+                                      "time stride 1 are implemented")
+        self.in_channels = in_channels // 2
+        self.out_channels = out_channels // 2
+        self.kernel_size = tuple(kernel_size)
+        self.stride = tuple(stride)
+        self.padding = tuple(padding)
+        self.causal = causal
+        self.groups = groups
+        self.dilation = dilation
+        self.complex_axis = complex_axis
+        shape = (self.out_channels, self.in_channels) + self.kernel_size
+        self.real_conv = _ConvParams(shape, self.out_channels)
+        self.imag_conv = _ConvParams(shape, self.out_channels)
+        self._plans = {}
+
+    def plan(self):
+        dev = self.real_conv.weight.device
+        if dev not in self._plans:
+            shape = tuple(self.real_conv.weight.shape)
+            cr = _codes(shape, 0).transpose(2, 3, 1, 0)
+            ci = _codes(shape, 1).transpose(2, 3, 1, 0)
+            n = self.real_conv.weight.numel()
+            pt = self.padding[1]
+            self._plans[dev] = ConvPlan("conv", _complex_block(cr, ci), self.stride[0], self.padding[0], pt,
+                                        2 * self.in_channels, 0, _complex_bias_table(self.out_channels),
+                                        n, n, dev, t_extra=pt if (pt != 0 and self.causal) else 2 * pt)
+        return self._plans[dev]
+
+    def forward_phys(self, x_phys, out_dtype=None):
+        return TapConvFn.apply(self.plan(), x_phys, None, self.real_conv.weight, self.imag_conv.weight,
+                               self.real_conv.bias, self.imag_conv.bias, out_dtype or ops.policy.act_dtype)
+
+    def forward(self, inputs):
+        x = to_phys(inputs)
+        return to_logical(self.forward_phys(x, x.dtype))
+
+
+class ComplexConvTranspose2d(nn.Module):
+    """Complex transposed convolution, sub-pixel decomposed (one dense contraction per output
+    frequency phase).  `forward_phys(x0, x1)` consumes the decoder's skip connection as a second
+    K segment instead of a materialised complex_cat."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=(1, 1), stride=(1, 1), padding=(0, 0),
+                 output_padding=(0, 0), causal=False, complex_axis=1, groups=1):
+        super().__init__()
+        if groups != 1 or complex_axis != 1 or stride[1] != 1:
+            raise NotImplementedError("ComplexConvTranspose2d: only groups=1, complex_axis=1, time stride 1")
+        self.in_channels = in_channels // 2
+        self.out_channels = out_channels // 2
+        self.kernel_size = tuple(kernel_size)
+        self.stride = tuple(stride)
+        self.padding = tuple(padding)
+        self.output_padding = tuple(output_padding)
+        self.groups = groups
+        self.complex_axis = complex_axis
+        shape = (self.in_channels, self.out_channels) + self.kernel_size
+        self.real_conv = _ConvParams(shape, self.out_channels)
+        self.imag_conv = _ConvParams(shape, self.out_channels)
+        self._plans = {}
+
+    def plan(self, ca=None):
+        """ca: complex channels of source 0 when the input is (x0, x1); None = single input."""
+        dev = self.real_conv.weight.device
+        key = (dev, ca)
+        if key not in self._plans:
+            shape = tuple(self.real_conv.weight.shape)
+            cin = self.in_channels
+            cr = _codes(shape, 0).transpose(2, 3, 0, 1)
+            ci = _codes(shape, 1).transpose(2, 3, 0, 1)
+            block = _complex_block(cr, ci)                     # rows [real 0..cin), [imag 0..cin)
+            c0, c1 = 2 * cin, 0
+            if ca is not None:
+                # reference cat order [r_a, r_b, i_a, i_b] (complex_cat) -> internal [r_a, i_a, r_b, i_b]
+                perm = np.concatenate([np.arange(0, ca), cin + np.arange(0, ca),
+                                       np.arange(ca, cin), cin + np.arange(ca, cin)])
+                block = block[:, :, perm, :]
+                c0, c1 = 2 * ca, 2 * (cin - ca)
+            n = self.real_conv.weight.numel()
+            self._plans[key] = ConvPlan("deconv", block, self.stride[0], self.padding[0], self.padding[1],
+                                        c0, c1, _complex_bias_table(self.out_channels), n, n, dev,
+                                        t_extra=self.output_padding[1], f_extra=self.output_padding[0])
+        return self._plans[key]
+
+    def forward_phys(self, x0, x1=None, out_dtype=None):
+        plan = self.plan(None if x1 is None else x0.shape[-1] // 2)
+        return TapConvFn.apply(plan, x0, x1, self.real_conv.weight, self.imag_conv.weight,
+                               self.real_conv.bias, self.imag_conv.bias, out_dtype or ops.policy.act_dtype)
+
+    def forward(self, inputs):
+        if isinstance(inputs, (tuple, list)):
+            inputs = torch.cat([inputs[0], inputs[1]], self.complex_axis)
+        x = to_phys(inputs)
+        return to_logical(self.forward_phys(x, None, x.dtype))
+
+
+def complex_cat(inputs, axis):
+    """[r_a, i_a], [r_b, i_b] -> [r_a, r_b, i_a, i_b] along `axis` (reference: tools_for_model.py:181-190).
+    Inside DCCRN the concat is never materialised; this is the API-parity version."""
+    parts = [torch.chunk(x, 2, axis) for x in inputs]
+    return torch.cat([p[0] for p in parts] + [p[1] for p in parts], axis)
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm / PReLU on channels-last activations (reference: DCCRN.py:80-82)
+# ---------------------------------------------------------------------------------------------
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d (same parameters/buffers) whose forward is the fused statistics + normalise
+    kernel pair; `forward_phys(x, slope)` additionally fuses the following PReLU."""
+
+    def forward_phys(self, x_phys, slope=None):
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        use_running = (not self.training) and self.track_running_stats
+        return BNActFn.apply(x_phys, self.weight, self.bias, slope,
+                             self.running_mean if self.track_running_stats else None,
+                             self.running_var if self.track_running_stats else None,
+                             not use_running, self.momentum, self.eps)
+
+    def forward(self, inputs):
+        return to_logical(self.forward_phys(to_phys(inputs, need_dense=True)))
+
+
+class PReLU(nn.PReLU):
+    """Single-slope PReLU; standalone forward = identity-statistics BNAct kernel."""
+
+    def forward(self, inputs):
+        if self.weight.numel() != 1:
+            raise NotImplementedError("PReLU: only num_parameters=1")
+        x = to_phys(inputs, need_dense=True) if inputs.dim() == 4 else dense(inputs)
+        C = x.shape[-1]
+        zero = torch.zeros(C, dtype=torch.float32, device=x.device)
+        one = torch.ones(C, dtype=torch.float32, device=x.device)
+        y = BNActFn.apply(x, None, None, self.weight, zero, one, False, 0.0, 0.0)
+        return to_logical(y) if inputs.dim() == 4 else y
+
+
+class cPReLU(nn.Module):
+    def __init__(self, complex_axis=1):
+        super().__init__()
+        self.r_prelu = PReLU()
+        self.i_prelu = PReLU()
+        self.complex_axis = complex_axis
+
+    def forward(self, inputs):
+        real, imag = torch.chunk(inputs, 2, self.complex_axis)
+        return torch.cat([self.r_prelu(real), self.i_prelu(imag)], self.complex_axis)
+
+
+class ComplexBatchNorm(nn.Module):
+    """Trabelsi-style complex batch norm (reference: tools_for_model.py:335-512).  Forward
+    (training and eval statistics) runs on the moments/whitening kernels; the backward pass of this
+    optional block (use_cbn=True, off by default) is not implemented."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True,
+                 complex_axis=1):
+        super().__init__()
+        self.num_features = num_features // 2
+        self.eps, self.momentum, self.affine = eps, momentum, affine
+        self.track_running_stats = track_running_stats
+        self.complex_axis = complex_axis
+        nf = self.num_features
+        if affine:
+            self.Wrr = nn.Parameter(torch.ones(nf))
+            self.Wri = nn.Parameter(torch.empty(nf).uniform_(-.9, .9))
+            self.Wii = nn.Parameter(torch.ones(nf))
+            self.Br = nn.Parameter(torch.zeros(nf))
+            self.Bi = nn.Parameter(torch.zeros(nf))
+        else:
+            for n in ('Wrr', 'Wri', 'Wii', 'Br', 'Bi'):
+                self.register_parameter(n, None)
+        if track_running_stats:
+            self.register_buffer('RMr', torch.zeros(nf))
+            self.register_buffer('RMi', torch.zeros(nf))
+            self.register_buffer('RVrr', torch.ones(nf))
+            self.register_buffer('RVri', torch.zeros(nf))
+            self.register_buffer('RVii', torch.ones(nf))
+            self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+        else:
+            for n in ('RMr', 'RMi', 'RVrr', 'RVri', 'RVii', 'num_batches_tracked'):
+                self.register_parameter(n, None)
+
+    def forward_phys(self, x, slope=None):
+        if torch.is_grad_enabled() and (x.requires_grad or (self.affine and self.Wrr.requires_grad)):
+            raise NotImplementedError("ComplexBatchNorm: backward is not implemented (forward-only block)")
+        Cc = self.num_features
+        M = x.numel() // (2 * Cc)
+        training = self.training or not self.track_running_stats
+        if self.training and self.track_running_stats:
+            self.num_batches_tracked.add_(1)
+        dev = x.device
+        coef = torch.empty(6, Cc, dtype=torch.float32, device=dev)
+        s = torch.empty(5, Cc, dtype=torch.float64, device=dev)
+        st = ops._stream()
+        if training:
+            call("clskd_cbn_moments", x.data_ptr(), ops._tag(x.dtype), M, Cc, s.data_ptr(), st)
+        rs = self.track_running_stats
+        P = lambda t: t.data_ptr() if t is not None else None
+        call("clskd_cbn_finalize", s.data_ptr(), M, Cc, float(self.eps), float(self.momentum or 0.0),
+             1 if training else 0, P(self.Wrr), P(self.Wri), P(self.Wii),
+             P(self.RMr) if rs else None, P(self.RMi) if rs else None, P(self.RVrr) if rs else None,
+             P(self.RVri) if rs else None, P(self.RVii) if rs else None, coef.data_ptr(), st)
+        y = torch.empty_like(x)
+        call("clskd_cbn_apply", x.data_ptr(), ops._tag(x.dtype), M, Cc, coef.data_ptr(), P(self.Br), P(self.Bi),
+             y.data_ptr(), ops._tag(y.dtype), st)
+        if slope is not None:
+            C = 2 * Cc
+            zero = torch.zeros(C, dtype=torch.float32, device=dev)
+            one = torch.ones(C, dtype=torch.float32, device=dev)
+            y = BNActFn.apply(y, None, None, slope, zero, one, False, 0.0, 0.0)
+        return y
+
+    def forward(self, inputs):
+        return to_logical(self.forward_phys(to_phys(inputs, need_dense=True)))
+
+
+class ConvBNAct(nn.Sequential):
+    """Sequential(conv, [norm, PReLU]) with the reference's child indices (`.0`, `.1`, `.2`) whose
+    forward runs the fused pipeline: contraction -> BN statistics -> normalise+PReLU in one pass.
+    Forward hooks on this module (feature_extraction) see the same output the reference's
+    nn.Sequential would produce."""
+
+    def forward_phys(self, x0, x1=None):
+        conv = self[0]
+        z = conv.forward_phys(x0, x1) if x1 is not None else conv.forward_phys(x0)
+        if len(self) == 1:
+            return z
+        slope = self[2].weight if len(self) > 2 else None
+        return self[1].forward_phys(z, slope)
+
+    def forward(self, inputs, skip=None):
+        x0 = to_phys(inputs)
+        x1 = to_phys(skip) if skip is not None else None
+        return to_logical(self.forward_phys(x0, x1))

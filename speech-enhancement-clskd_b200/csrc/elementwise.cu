@@ -1,0 +1,1278 @@
+// Memory-bound kernels of the DCCRN distillation path: layout/packing helpers, BatchNorm(+PReLU)
+// forward/backward, complex BatchNorm, the polar mask, iSTFT overlap-add, ABF helpers, Adam.
+// All are HBM-bound: coalesced, 128-bit vectorised where the shape allows, grids sized in
+// multiples of the SM count (grid-stride loops).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace clskd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+static inline int ew_grid(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+namespace {
+
+// ------------------------------------------------------------------------------- layout helpers
+template <typename TS, typename TD>
+__global__ void strided_copy4d_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n0,
+                                      int64_t n1, int64_t n2, int64_t n3, int64_t s0, int64_t s1,
+                                      int64_t s2, int64_t s3, int64_t d0, int64_t d1, int64_t d2,
+                                      int64_t d3) {
+  int64_t total = n0 * n1 * n2 * n3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i3 = i % n3, r = i / n3;
+    int64_t i2 = r % n2;
+    r /= n2;
+    int64_t i1 = r % n1, i0 = r / n1;
+    st_f(dst + i0 * d0 + i1 * d1 + i2 * d2 + i3 * d3,
+         ld_f(src + i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3));
+  }
+}
+
+template <typename TD>
+__global__ void pack_gather_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                   const int32_t* __restrict__ table, int64_t n,
+                                   TD* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      int32_t e = table[2 * i + k];
+      if (e >= 0) {
+        const float* s = (e & 1) ? b : a;
+        float t = s[e >> 2];
+        v += (e & 2) ? -t : t;
+      }
+    }
+    st_f(out + i, v);
+  }
+}
+
+__global__ void unpack_gather2_kernel(const float* __restrict__ src,
+                                      const int32_t* __restrict__ table2, int64_t n,
+                                      float* __restrict__ dst, int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v = accumulate ? dst[i] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      int32_t e = table2[2 * i + k];
+      if (e >= 0) {
+        float s = src[e >> 1];
+        v += (e & 1) ? -s : s;
+      }
+    }
+    dst[i] = v;
+  }
+}
+
+__device__ __forceinline__ int pad_map(int j, int L, int mode) {
+  // j = index into the unpadded signal (may be out of range)
+  if (j >= 0 && j < L) return j;
+  if (mode == 0) return -1;
+  // reflect (no edge repeat), valid for |overshoot| < L
+  if (j < 0) j = -j;
+  if (j >= L) j = 2 * (L - 1) - j;
+  return (j >= 0 && j < L) ? j : -1;
+}
+
+template <typename TS>
+__global__ void pad1d_kernel(const TS* __restrict__ src, int64_t src_sB, int B, int L, int left,
+                             int right, int mode, float* __restrict__ dst) {
+  int64_t Lp = (int64_t)L + left + right;
+  int64_t total = Lp * B;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / Lp);
+    int p = (int)(i - (int64_t)b * Lp);
+    int j = pad_map(p - left, L, mode);
+    dst[i] = j >= 0 ? ld_f(src + (int64_t)b * src_sB + j) : 0.f;
+  }
+}
+
+__global__ void pad1d_bwd_kernel(const float* __restrict__ ddst, int B, int L, int left, int right,
+                                 int mode, float* __restrict__ dsrc, int accumulate) {
+  int64_t Lp = (int64_t)L + left + right;
+  int64_t total = (int64_t)L * B;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / L);
+    int j = (int)(i - (int64_t)b * L);
+    const float* row = ddst + (int64_t)b * Lp;
+    float v = row[j + left];
+    if (mode == 1) {
+      // left reflection: padded index p = left - j (j in 1..left); right: p = left + 2(L-1) - j
+      if (j >= 1 && j <= left) v += row[left - j];
+      int p = left + 2 * (L - 1) - j;
+      if (j <= L - 2 && p >= left + L && p < Lp) v += row[p];
+    }
+    dsrc[i] = accumulate ? dsrc[i] + v : v;
+  }
+}
+
+// ------------------------------------------------------------------------------- BatchNorm
+// Column statistics of a dense [M, C] matrix.  Threads of a block are laid out so that a thread
+// always sees the same channel; per-thread fp32 partials over a bounded number of rows, then a
+// shared-memory fold and one fp64 atomic per (block, channel).
+constexpr int CS_ROWS_PER_THREAD = 64;
+
+template <typename T, int MODE>  // MODE 0: (x, x^2); MODE 1: bn backward sums
+__global__ void colstats_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int C,
+                                int rpb, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ slope,
+                                double* __restrict__ out0, double* __restrict__ out1,
+                                double* __restrict__ out2) {
+  extern __shared__ float sh[];  // [2 or 3][blockDim.x]
+  const int tid = threadIdx.x;
+  const int active = rpb * C;
+  const int c = tid % C;
+  const int r0 = tid / C;
+  const int64_t rows_per_block = (int64_t)rpb * CS_ROWS_PER_THREAD;
+  const int64_t mbeg = (int64_t)blockIdx.x * rows_per_block;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  if (tid < active) {
+    float mu = 0.f, is = 1.f, g = 1.f, bt = 0.f, sl = 1.f;
+    if (MODE == 1) {
+      mu = mean[c];
+      is = invstd[c];
+      g = gamma ? gamma[c] : 1.f;
+      bt = beta ? beta[c] : 0.f;
+      sl = slope ? slope[0] : 1.f;
+    }
+#pragma unroll 4
+    for (int it = 0; it < CS_ROWS_PER_THREAD; ++it) {
+      int64_t m = mbeg + r0 + (int64_t)it * rpb;
+      if (m >= M) break;
+      float v = ld_f(x + m * C + c);
+      if (MODE == 0) {
+        a0 += v;
+        a1 += v * v;
+      } else {
+        float xh = (v - mu) * is;
+        float u = xh * g + bt;
+        float d = ld_f(dy + m * C + c);
+        float dz = u > 0.f ? d : d * sl;
+        a0 += dz;
+        a1 += dz * xh;
+        a2 += u > 0.f ? 0.f : d * u;
+      }
+    }
+  }
+  sh[tid] = a0;
+  sh[blockDim.x + tid] = a1;
+  if (MODE == 1) sh[2 * blockDim.x + tid] = a2;
+  __syncthreads();
+  if (tid < C) {
+    double s0 = 0., s1 = 0., s2 = 0.;
+    for (int r = 0; r < rpb; ++r) {
+      s0 += sh[r * C + tid];
+      s1 += sh[blockDim.x + r * C + tid];
+      if (MODE == 1) s2 += sh[2 * blockDim.x + r * C + tid];
+    }
+    atomicAdd(out0 + tid, s0);
+    atomicAdd(out1 + tid, s1);
+    if (MODE == 1) {
+      // dslope is a single scalar: fold the C partials first
+      sh[tid] = (float)s2;
+    }
+  }
+  if (MODE == 1) {
+    __syncthreads();
+    if (tid == 0 && out2) {
+      double s = 0.;
+      for (int i = 0; i < C; ++i) s += sh[i];
+      atomicAdd(out2, s);
+    }
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq,
+                                   int64_t M, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ rmean, float* __restrict__ rvar) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mu = sum[c] / (double)M;
+  double var = sumsq[c] / (double)M - mu * mu;
+  if (var < 0.) var = 0.;
+  mean[c] = (float)mu;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mu;
+  if (rvar) {
+    double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+  }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                     int C, float eps, float* __restrict__ mean,
+                                     float* __restrict__ invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rmean[c];
+  invstd[c] = 1.f / sqrtf(rvar[c] + eps);
+}
+
+template <typename TX, typename TY>
+__global__ void bn_act_fwd_kernel(const TX* __restrict__ x, int64_t n4, int C,
+                                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ slope, TY* __restrict__ y) {
+  const float sl = slope ? slope[0] : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)((i * 4) % C);
+    float4 v = ld4(x + i * 4);
+    float in[4] = {v.x, v.y, v.z, v.w}, o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float sc = invstd[c + e] * (gamma ? gamma[c + e] : 1.f);
+      float u = (in[e] - mean[c + e]) * sc + (beta ? beta[c + e] : 0.f);
+      o[e] = u > 0.f ? u : u * sl;
+    }
+    st4(y + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+template <typename TX, typename TY>
+__global__ void bn_act_fwd_scalar_kernel(const TX* __restrict__ x, int64_t n, int C,
+                                         const float* __restrict__ mean,
+                                         const float* __restrict__ invstd,
+                                         const float* __restrict__ gamma,
+                                         const float* __restrict__ beta,
+                                         const float* __restrict__ slope, TY* __restrict__ y) {
+  const float sl = slope ? slope[0] : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float sc = invstd[c] * (gamma ? gamma[c] : 1.f);
+    float u = (ld_f(x + i) - mean[c]) * sc + (beta ? beta[c] : 0.f);
+    st_f(y + i, u > 0.f ? u : u * sl);
+  }
+}
+
+template <typename TX, typename TD, typename TO>
+__global__ void bn_act_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy,
+                                        int64_t n, int64_t M, int C, const float* __restrict__ mean,
+                                        const float* __restrict__ invstd,
+                                        const float* __restrict__ gamma,
+                                        const float* __restrict__ beta,
+                                        const float* __restrict__ slope,
+                                        const double* __restrict__ sum_dz,
+                                        const double* __restrict__ sum_dz_xhat, int training,
+                                        TO* __restrict__ dx) {
+  const float sl = slope ? slope[0] : 1.f;
+  const float invM = 1.f / (float)M;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float g = gamma ? gamma[c] : 1.f;
+    float is = invstd[c];
+    float xh = (ld_f(x + i) - mean[c]) * is;
+    float u = xh * g + (beta ? beta[c] : 0.f);
+    float d = ld_f(dy + i);
+    float dz = u > 0.f ? d : d * sl;
+    float r = dz;
+    if (training) r = dz - (float)sum_dz[c] * invM - xh * (float)sum_dz_xhat[c] * invM;
+    st_f(dx + i, g * is * r);
+  }
+}
+
+__global__ void bn_param_grads_kernel(const double* __restrict__ sum_dz,
+                                      const double* __restrict__ sum_dz_xhat,
+                                      const double* __restrict__ dslope, int C,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                      float* __restrict__ dslope_out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    if (dgamma) dgamma[c] = (float)sum_dz_xhat[c];
+    if (dbeta) dbeta[c] = (float)sum_dz[c];
+  }
+  if (c == 0 && dslope_out && dslope) dslope_out[0] = (float)dslope[0];
+}
+
+// ------------------------------------------------------------------------------- complex BN
+template <typename T>
+__global__ void cbn_moments_kernel(const T* __restrict__ x, int64_t M, int Cc, int rpb,
+                                   double* __restrict__ s) {
+  extern __shared__ float sh[];  // [5][blockDim.x]
+  const int tid = threadIdx.x;
+  const int active = rpb * Cc;
+  const int c = tid % Cc, r0 = tid / Cc;
+  const int64_t mbeg = (int64_t)blockIdx.x * rpb * CS_ROWS_PER_THREAD;
+  float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (tid < active) {
+    for (int it = 0; it < CS_ROWS_PER_THREAD; ++it) {
+      int64_t m = mbeg + r0 + (int64_t)it * rpb;
+      if (m >= M) break;
+      float xr = ld_f(x + m * 2 * Cc + c), xi = ld_f(x + m * 2 * Cc + Cc + c);
+      a[0] += xr; a[1] += xi; a[2] += xr * xr; a[3] += xr * xi; a[4] += xi * xi;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) sh[k * blockDim.x + tid] = a[k];
+  __syncthreads();
+  if (tid < Cc) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      double v = 0.;
+      for (int r = 0; r < rpb; ++r) v += sh[k * blockDim.x + r * Cc + tid];
+      atomicAdd(s + (int64_t)k * Cc + tid, v);
+    }
+  }
+}
+
+__global__ void cbn_finalize_kernel(const double* __restrict__ s, int64_t M, int Cc, float eps,
+                                    float momentum, int training, const float* __restrict__ Wrr,
+                                    const float* __restrict__ Wri, const float* __restrict__ Wii,
+                                    float* RMr, float* RMi, float* RVrr, float* RVri, float* RVii,
+                                    float* __restrict__ coef) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cc) return;
+  float Mr, Mi, Vrr, Vri, Vii;
+  if (training) {
+    double mr = s[c] / M, mi = s[Cc + c] / M;
+    Mr = (float)mr;
+    Mi = (float)mi;
+    Vrr = (float)(s[2 * Cc + c] / M - mr * mr);
+    Vri = (float)(s[3 * Cc + c] / M - mr * mi);
+    Vii = (float)(s[4 * Cc + c] / M - mi * mi);
+    if (RMr) {  // lerp_(new, w): old + w*(new-old)   (tools_for_model.py:433-434,455-457)
+      RMr[c] += momentum * (Mr - RMr[c]);
+      RMi[c] += momentum * (Mi - RMi[c]);
+      RVrr[c] += momentum * (Vrr - RVrr[c]);
+      RVri[c] += momentum * (Vri - RVri[c]);
+      RVii[c] += momentum * (Vii - RVii[c]);
+    }
+  } else {
+    Mr = RMr[c]; Mi = RMi[c]; Vrr = RVrr[c]; Vri = RVri[c]; Vii = RVii[c];
+  }
+  Vrr += eps;
+  Vii += eps;
+  float tau = Vrr + Vii;
+  float delta = Vrr * Vii - Vri * Vri;
+  float sq = sqrtf(delta);
+  float t = sqrtf(tau + 2.f * sq);
+  float rst = 1.f / (sq * t);
+  float Urr = (sq + Vii) * rst, Uii = (sq + Vrr) * rst, Uri = -Vri * rst;
+  float Zrr = Urr, Zri = Uri, Zir = Uri, Zii = Uii;
+  if (Wrr) {
+    float wrr = Wrr[c], wri = Wri[c], wii = Wii[c];
+    Zrr = wrr * Urr + wri * Uri;
+    Zri = wrr * Uri + wri * Uii;
+    Zir = wri * Urr + wii * Uri;
+    Zii = wri * Uri + wii * Uii;
+  }
+  coef[c] = Mr;
+  coef[Cc + c] = Mi;
+  coef[2 * Cc + c] = Zrr;
+  coef[3 * Cc + c] = Zri;
+  coef[4 * Cc + c] = Zir;
+  coef[5 * Cc + c] = Zii;
+}
+
+template <typename TX, typename TY>
+__global__ void cbn_apply_kernel(const TX* __restrict__ x, int64_t M, int Cc,
+                                 const float* __restrict__ coef, const float* __restrict__ Br,
+                                 const float* __restrict__ Bi, TY* __restrict__ y) {
+  int64_t total = M * Cc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cc);
+    int64_t m = i / Cc;
+    float xr = ld_f(x + m * 2 * Cc + c) - coef[c];
+    float xi = ld_f(x + m * 2 * Cc + Cc + c) - coef[Cc + c];
+    float yr = coef[2 * Cc + c] * xr + coef[3 * Cc + c] * xi + (Br ? Br[c] : 0.f);
+    float yi = coef[4 * Cc + c] * xr + coef[5 * Cc + c] * xi + (Bi ? Bi[c] : 0.f);
+    st_f(y + m * 2 * Cc + c, yr);
+    st_f(y + m * 2 * Cc + Cc + c, yi);
+  }
+}
+
+// ------------------------------------------------------------------------------- mask
+// One thread per (b,t,bin).  Trig-free polar mask: cos/sin of atan2 are the normalised
+// components, so est = tanh|m| * |s|_eps * (unit(s) * unit(m)) as a complex product.
+template <typename TM>
+__global__ void mask_fwd_kernel(const float* __restrict__ spec, const TM* __restrict__ mask,
+                                int64_t m_sB, int64_t m_sT, int B, int T, int nb, int mode,
+                                float* __restrict__ out, float* __restrict__ mask_padded) {
+  int64_t total = (int64_t)B * T * nb;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int f = (int)(i % nb);
+    int64_t bt = i / nb;
+    int t = (int)(bt % T), b = (int)(bt / T);
+    float2 s = *reinterpret_cast<const float2*>(spec + i * 2);
+    float mr = 0.f, mi = 0.f;
+    if (f > 0) {
+      const TM* mp = mask + (int64_t)b * m_sB + (int64_t)t * m_sT + (int64_t)(f - 1) * 2;
+      mr = ld_f(mp);
+      mi = ld_f(mp + 1);
+    }
+    float orr, oi;
+    if (mode == 0) {
+      float mags = sqrtf(s.x * s.x + s.y * s.y + 1e-8f);
+      float hs = sqrtf(s.x * s.x + s.y * s.y);
+      float cp = 1.f, sp = 0.f;
+      if (hs > 0.f) {
+        cp = s.x / hs;
+        sp = s.y / hs;
+      }
+      float mm = sqrtf(mr * mr + mi * mi);
+      float cq = 1.f, sq = 0.f;
+      if (mm > 0.f) {
+        cq = mr / mm;
+        sq = mi / mm;
+      }
+      float a = tanhf(mm) * mags;
+      orr = a * (cp * cq - sp * sq);
+      oi = a * (sp * cq + cp * sq);
+    } else if (mode == 1) {
+      orr = s.x * mr - s.y * mi;
+      oi = s.x * mi + s.y * mr;
+    } else {
+      orr = s.x * mr;
+      oi = s.y * mi;
+    }
+    *reinterpret_cast<float2*>(out + i * 2) = make_float2(orr, oi);
+    if (mask_padded) *reinterpret_cast<float2*>(mask_padded + i * 2) = make_float2(mr, mi);
+  }
+}
+
+template <typename TM, typename TD>
+__global__ void mask_bwd_kernel(const float* __restrict__ spec, const TM* __restrict__ mask,
+                                int64_t m_sB, int64_t m_sT, int B, int T, int nb, int mode,
+                                const float* __restrict__ dout, TD* __restrict__ dmask,
+                                int64_t dm_sB, int64_t dm_sT) {
+  int nbm = nb - 1;
+  int64_t total = (int64_t)B * T * nbm;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int fm = (int)(i % nbm);
+    int64_t bt = i / nbm;
+    int t = (int)(bt % T), b = (int)(bt / T);
+    int64_t si = (bt * nb + fm + 1) * 2;
+    float2 s = *reinterpret_cast<const float2*>(spec + si);
+    float2 g = *reinterpret_cast<const float2*>(dout + si);
+    const TM* mp = mask + (int64_t)b * m_sB + (int64_t)t * m_sT + (int64_t)fm * 2;
+    float mr = ld_f(mp), mi = ld_f(mp + 1);
+    float dmr = 0.f, dmi = 0.f;
+    if (mode == 0) {
+      float mags = sqrtf(s.x * s.x + s.y * s.y + 1e-8f);
+      float hs = sqrtf(s.x * s.x + s.y * s.y);
+      float cp = 1.f, sp = 0.f;
+      if (hs > 0.f) {
+        cp = s.x / hs;
+        sp = s.y / hs;
+      }
+      float mm = sqrtf(mr * mr + mi * mi);
+      if (mm > 0.f) {
+        float cq = mr / mm, sq = mi / mm;
+        float th = tanhf(mm);
+        float A = th * mags, dA = (1.f - th * th) * mags;
+        float ct = cp * cq - sp * sq, stt = sp * cq + cp * sq;
+        float Aom = A / mm;
+        // d out_r / d(mr,mi), d out_i / d(mr,mi)
+        float orr_mr = dA * cq * ct + Aom * stt * sq;
+        float orr_mi = dA * sq * ct - Aom * stt * cq;
+        float oi_mr = dA * cq * stt - Aom * ct * sq;
+        float oi_mi = dA * sq * stt + Aom * ct * cq;
+        dmr = g.x * orr_mr + g.y * oi_mr;
+        dmi = g.x * orr_mi + g.y * oi_mi;
+      }
+    } else if (mode == 1) {
+      dmr = g.x * s.x + g.y * s.y;
+      dmi = -g.x * s.y + g.y * s.x;
+    } else {
+      dmr = g.x * s.x;
+      dmi = g.y * s.y;
+    }
+    TD* dp = dmask + (int64_t)b * dm_sB + (int64_t)t * dm_sT + (int64_t)fm * 2;
+    st_f(dp, dmr);
+    st_f(dp + 1, dmi);
+  }
+}
+
+// ------------------------------------------------------------------------------- overlap-add
+__global__ void ola_fwd_kernel(const float* __restrict__ frames, const float* __restrict__ window,
+                               int B, int T, int win, int hop, int trim, int do_clamp,
+                               float* __restrict__ wav) {
+  const int L = (T - 1) * hop + win - 2 * trim;
+  int64_t total = (int64_t)B * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / L);
+    int p = (int)(i - (int64_t)b * L) + trim;
+    int thi = p / hop;
+    if (thi > T - 1) thi = T - 1;
+    int tlo = (p - win + hop) / hop;  // ceil((p-win+1)/hop) for p-win+1 >= 0
+    if (p - win + 1 <= 0) tlo = 0;
+    float acc = 0.f, coff = 0.f;
+    for (int t = tlo; t <= thi; ++t) {
+      int k = p - t * hop;
+      if (window) {
+        float w = window[k];
+        coff += w * w;
+      }
+      acc += frames[((int64_t)b * T + t) * win + k];
+    }
+    float v = window ? acc / (coff + 1e-8f) : acc;
+    if (do_clamp) v = fminf(1.f, fmaxf(-1.f, v));
+    wav[i] = v;
+  }
+}
+
+__global__ void ola_bwd_kernel(const float* __restrict__ dwav, const float* __restrict__ wav,
+                               const float* __restrict__ window, int B, int T, int win, int hop,
+                               int trim, int do_clamp, float* __restrict__ dframes) {
+  const int L = (T - 1) * hop + win - 2 * trim;
+  int64_t total = (int64_t)B * T * win;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % win);
+    int64_t bt = i / win;
+    int t = (int)(bt % T), b = (int)(bt / T);
+    int p = t * hop + k;
+    int j = p - trim;
+    float v = 0.f;
+    if (j >= 0 && j < L) {
+      bool pass = true;
+      if (do_clamp) {
+        float wv = wav[(int64_t)b * L + j];
+        pass = wv > -1.f && wv < 1.f;
+      }
+      if (pass) {
+        v = dwav[(int64_t)b * L + j];
+        if (window) {
+          int thi = p / hop;
+          if (thi > T - 1) thi = T - 1;
+          int tlo = (p - win + hop) / hop;
+          if (p - win + 1 <= 0) tlo = 0;
+          float coff = 0.f;
+          for (int tt = tlo; tt <= thi; ++tt) {
+            float w = window[p - tt * hop];
+            coff += w * w;
+          }
+          v /= (coff + 1e-8f);
+        }
+      }
+    }
+    dframes[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------- ABF helpers
+template <typename T>
+__global__ void resize_f_fwd_kernel(const T* __restrict__ x, int64_t BT, int Fi, int Fo, int C,
+                                    T* __restrict__ y) {
+  int64_t total = BT * Fo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t r = i / C;
+    int fo = (int)(r % Fo);
+    int64_t bt = r / Fo;
+    int fi = (int)(((int64_t)fo * Fi) / Fo);  // nearest: floor(fo * Fi / Fo)
+    y[i] = x[(bt * Fi + fi) * C + c];
+  }
+}
+
+template <typename T>
+__global__ void resize_f_bwd_kernel(const T* __restrict__ dy, int64_t BT, int Fi, int Fo, int C,
+                                    T* __restrict__ dx) {
+  int64_t total = BT * Fi * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t r = i / C;
+    int fi = (int)(r % Fi);
+    int64_t bt = r / Fi;
+    // outputs fo with floor(fo*Fi/Fo) == fi  <=>  fo in [ceil(fi*Fo/Fi), ceil((fi+1)*Fo/Fi) )
+    int lo = (int)(((int64_t)fi * Fo + Fi - 1) / Fi);
+    int hi = (int)(((int64_t)(fi + 1) * Fo + Fi - 1) / Fi);
+    float acc = 0.f;
+    for (int fo = lo; fo < hi && fo < Fo; ++fo) acc += ld_f(dy + (bt * Fo + fo) * C + c);
+    st_f(dx + i, acc);
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+
+template <typename T>
+__global__ void att_blend_fwd_kernel(const T* __restrict__ x, const T* __restrict__ y,
+                                     const float* __restrict__ z, int64_t M, int C,
+                                     T* __restrict__ out) {
+  int64_t total = M * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = i / C;
+    float z0 = sigmoidf_(z[2 * m]), z1 = sigmoidf_(z[2 * m + 1]);
+    st_f(out + i, ld_f(x + i) * z0 + ld_f(y + i) * z1);
+  }
+}
+
+// one warp per row: dx, dy elementwise; dz via warp reduction over channels
+template <typename T>
+__global__ void att_blend_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y,
+                                     const float* __restrict__ z, const T* __restrict__ dout,
+                                     int64_t M, int C, T* __restrict__ dx, T* __restrict__ dy,
+                                     float* __restrict__ dz) {
+  int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t m = warp; m < M; m += nwarps) {
+    float z0 = sigmoidf_(z[2 * m]), z1 = sigmoidf_(z[2 * m + 1]);
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      int64_t i = m * C + c;
+      float g = ld_f(dout + i);
+      float xv = ld_f(x + i), yv = ld_f(y + i);
+      st_f(dx + i, g * z0);
+      st_f(dy + i, g * z1);
+      s0 += g * xv;
+      s1 += g * yv;
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+      dz[2 * m] = s0 * z0 * (1.f - z0);
+      dz[2 * m + 1] = s1 * z1 * (1.f - z1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- hcl pooling
+// out[b,c,i,j] = mean over h in [floor(i*H/l), ceil((i+1)*H/l)), w likewise; H=F, W=T.
+// one block per (b,i,j); threads over channels, coalesced along C.
+template <typename T>
+__global__ void adaptive_pool_fwd_kernel(const T* __restrict__ x, int B, int Tn, int F, int C,
+                                         int l, float* __restrict__ out) {
+  int cell = blockIdx.x;
+  int j = cell % l, i = (cell / l) % l, b = cell / (l * l);
+  int h0 = (i * F) / l, h1 = ((i + 1) * F + l - 1) / l;
+  int w0 = (j * Tn) / l, w1 = ((j + 1) * Tn + l - 1) / l;
+  float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int w = w0; w < w1; ++w)
+      for (int h = h0; h < h1; ++h) acc += ld_f(x + (((int64_t)b * Tn + w) * F + h) * C + c);
+    out[(((int64_t)b * C + c) * l + i) * l + j] = acc * inv;
+  }
+}
+
+template <typename T>
+__global__ void adaptive_pool_bwd_kernel(const float* __restrict__ dout, int B, int Tn, int F,
+                                         int C, int l, T* __restrict__ dx, int accumulate) {
+  int64_t total = (int64_t)B * Tn * F * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C);
+    int64_t r = idx / C;
+    int h = (int)(r % F);
+    r /= F;
+    int w = (int)(r % Tn);
+    int b = (int)(r / Tn);
+    float acc = 0.f;
+    // cells whose window contains (h,w); windows of adjacent cells may overlap by one
+    for (int i = 0; i < l; ++i) {
+      int h0 = (i * F) / l, h1 = ((i + 1) * F + l - 1) / l;
+      if (h < h0 || h >= h1) continue;
+      for (int j = 0; j < l; ++j) {
+        int w0 = (j * Tn) / l, w1 = ((j + 1) * Tn + l - 1) / l;
+        if (w < w0 || w >= w1) continue;
+        acc += dout[(((int64_t)b * C + c) * l + i) * l + j] / (float)((h1 - h0) * (w1 - w0));
+      }
+    }
+    float v = accumulate ? ld_f(dx + idx) + acc : acc;
+    st_f(dx + idx, v);
+  }
+}
+
+template <typename TA, typename TB>
+__global__ void sqdiff_sum_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t n,
+                                  double* __restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float d = ld_f(a + i) - ld_f(b + i);
+    acc += (double)(d * d);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+template <typename TA, typename TB, typename TD>
+__global__ void sqdiff_bwd_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t n,
+                                  const float* __restrict__ gout, float scale, TD* __restrict__ da,
+                                  int accumulate) {
+  float g = gout[0] * scale * 2.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v = g * (ld_f(a + i) - ld_f(b + i));
+    if (accumulate) v += ld_f(da + i);
+    st_f(da + i, v);
+  }
+}
+
+// ------------------------------------------------------------------------------- optimizer etc
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2,
+                            float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float pi = p[i];
+    if (wd != 0.f) gi += wd * pi;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+__global__ void fill_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+__global__ void axpy_kernel(float* y, const float* x, int64_t n, float a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a,
+                             float b, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = a * x[i] + (y ? b * y[i] : 0.f);
+}
+// flat[offsets[i] .. offsets[i+1]) = tensor i (zeros when its pointer is null)
+__global__ void multi_pack_kernel(const unsigned long long* __restrict__ ptrs,
+                                  const int64_t* __restrict__ offsets, int n,
+                                  float* __restrict__ flat) {
+  int64_t total = offsets[n];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {  // last tensor whose offset <= i
+      int mid = (lo + hi + 1) >> 1;
+      if (offsets[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const float* src = reinterpret_cast<const float*>(ptrs[lo]);
+    flat[i] = src ? src[i - offsets[lo]] : 0.f;
+  }
+}
+__global__ void f64_to_f32_kernel(const double* in, int n, double scale, float* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)(in[i] * scale);
+}
+
+struct CsGeom {
+  int threads, rpb, grid;
+};
+static int colstats_geom(int64_t M, int C, CsGeom* g) {
+  if (C < 1 || C > 1024) return -1;
+  if (C <= 256) {
+    g->rpb = 256 / C;
+    g->threads = 256;
+  } else {
+    g->rpb = 1;
+    g->threads = (C + 31) / 32 * 32;
+  }
+  int64_t rows_per_block = (int64_t)g->rpb * CS_ROWS_PER_THREAD;
+  g->grid = (int)((M + rows_per_block - 1) / rows_per_block);
+  if (g->grid < 1) g->grid = 1;
+  return 0;
+}
+
+}  // namespace
+}  // namespace clskd
+
+using namespace clskd;
+#define ST ((cudaStream_t)stream)
+
+extern "C" const char* clskd_last_error(void) { return g_err; }
+extern "C" int clskd_abi_version(void) { return 1; }
+
+extern "C" int clskd_strided_copy4d(const void* src, int src_dtype, const int64_t* ss, void* dst,
+                                    int dst_dtype, const int64_t* ds, const int64_t* shape,
+                                    void* stream) {
+  CLSKD_CHECK_ARG(src && dst && ss && ds && shape, "clskd_strided_copy4d: null pointer");
+  int64_t total = shape[0] * shape[1] * shape[2] * shape[3];
+  if (total == 0) return CLSKD_OK;
+  int grid = ew_grid(total, 256);
+#define L(TS, TD)                                                                               \
+  strided_copy4d_kernel<TS, TD><<<grid, 256, 0, ST>>>((const TS*)src, (TD*)dst, shape[0], shape[1], \
+                                                      shape[2], shape[3], ss[0], ss[1], ss[2], ss[3], \
+                                                      ds[0], ds[1], ds[2], ds[3])
+  if (src_dtype == CLSKD_F32 && dst_dtype == CLSKD_F32) L(float, float);
+  else if (src_dtype == CLSKD_F32) L(float, __nv_bfloat16);
+  else if (dst_dtype == CLSKD_F32) L(__nv_bfloat16, float);
+  else L(__nv_bfloat16, __nv_bfloat16);
+#undef L
+  CLSKD_CHECK_LAUNCH("clskd_strided_copy4d");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_pack_gather(const float* a, const float* b, const int32_t* table, int64_t n,
+                                 void* out, int out_dtype, void* stream) {
+  CLSKD_CHECK_ARG(a && table && out, "clskd_pack_gather: null pointer");
+  if (n == 0) return CLSKD_OK;
+  int grid = ew_grid(n, 256);
+  if (out_dtype == CLSKD_F32)
+    pack_gather_kernel<float><<<grid, 256, 0, ST>>>(a, b ? b : a, table, n, (float*)out);
+  else
+    pack_gather_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>(a, b ? b : a, table, n,
+                                                           (__nv_bfloat16*)out);
+  CLSKD_CHECK_LAUNCH("clskd_pack_gather");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_unpack_gather2(const float* src, const int32_t* table2, int64_t n, float* dst,
+                                    int accumulate, void* stream) {
+  CLSKD_CHECK_ARG(src && table2 && dst, "clskd_unpack_gather2: null pointer");
+  if (n == 0) return CLSKD_OK;
+  unpack_gather2_kernel<<<ew_grid(n, 256), 256, 0, ST>>>(src, table2, n, dst, accumulate);
+  CLSKD_CHECK_LAUNCH("clskd_unpack_gather2");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_pad1d(const void* src, int src_dtype, int64_t src_sB, int B, int L, int left,
+                           int right, int mode, float* dst, void* stream) {
+  CLSKD_CHECK_ARG(src && dst, "clskd_pad1d: null pointer");
+  CLSKD_CHECK_ARG(mode == 0 || (left < L && right < L), "clskd_pad1d: reflect pad >= length");
+  int64_t total = ((int64_t)L + left + right) * B;
+  if (total == 0) return CLSKD_OK;
+  if (src_dtype == CLSKD_F32)
+    pad1d_kernel<float><<<ew_grid(total, 256), 256, 0, ST>>>((const float*)src, src_sB, B, L, left,
+                                                           right, mode, dst);
+  else
+    pad1d_kernel<__nv_bfloat16><<<ew_grid(total, 256), 256, 0, ST>>>(
+        (const __nv_bfloat16*)src, src_sB, B, L, left, right, mode, dst);
+  CLSKD_CHECK_LAUNCH("clskd_pad1d");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_pad1d_bwd(const float* ddst, int B, int L, int left, int right, int mode,
+                               float* dsrc, int accumulate, void* stream) {
+  CLSKD_CHECK_ARG(ddst && dsrc, "clskd_pad1d_bwd: null pointer");
+  int64_t total = (int64_t)L * B;
+  if (total == 0) return CLSKD_OK;
+  pad1d_bwd_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(ddst, B, L, left, right, mode, dsrc,
+                                                        accumulate);
+  CLSKD_CHECK_LAUNCH("clskd_pad1d_bwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_colstats(const void* x, int dtype, int64_t M, int C, double* sum,
+                              double* sumsq, void* stream) {
+  CLSKD_CHECK_ARG(x && sum && sumsq, "clskd_colstats: null pointer");
+  CsGeom g;
+  CLSKD_CHECK_ARG(colstats_geom(M, C, &g) == 0, "clskd_colstats: C=%d unsupported (1..1024)", C);
+  {
+    cudaError_t e__ = cudaSuccess;
+    e__ = cudaMemsetAsync(sum, 0, sizeof(double) * C, ST);
+    if (e__ == cudaSuccess) e__ = cudaMemsetAsync(sumsq, 0, sizeof(double) * C, ST);
+    if (e__ != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e__)); return CLSKD_ERR_CUDA; }
+  }
+  if (M == 0) return CLSKD_OK;
+  size_t sh = 2 * g.threads * sizeof(float);
+  CLSKD_DISPATCH_DTYPE(dtype, T,
+                       (colstats_kernel<T, 0><<<g.grid, g.threads, sh, ST>>>(
+                           (const T*)x, nullptr, M, C, g.rpb, nullptr, nullptr, nullptr, nullptr,
+                           nullptr, sum, sumsq, nullptr)));
+  CLSKD_CHECK_LAUNCH("clskd_colstats");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_bn_finalize(const double* sum, const double* sumsq, int64_t M, int C,
+                                 float eps, float momentum, float* mean, float* invstd,
+                                 float* running_mean, float* running_var, void* stream) {
+  CLSKD_CHECK_ARG(sum && sumsq && mean && invstd && M > 0, "clskd_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, ST>>>(sum, sumsq, M, C, eps, momentum, mean, invstd,
+                                                   running_mean, running_var);
+  CLSKD_CHECK_LAUNCH("clskd_bn_finalize");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_bn_eval_stats(const float* running_mean, const float* running_var, int C,
+                                   float eps, float* mean, float* invstd, void* stream) {
+  CLSKD_CHECK_ARG(running_mean && running_var && mean && invstd, "clskd_bn_eval_stats: null pointer");
+  bn_eval_stats_kernel<<<cdiv(C, 128), 128, 0, ST>>>(running_mean, running_var, C, eps, mean,
+                                                     invstd);
+  CLSKD_CHECK_LAUNCH("clskd_bn_eval_stats");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_bn_act_fwd(const void* x, int x_dtype, int64_t M, int C, const float* mean,
+                                const float* invstd, const float* gamma, const float* beta,
+                                const float* slope, void* y, int y_dtype, void* stream) {
+  CLSKD_CHECK_ARG(x && y && mean && invstd, "clskd_bn_act_fwd: null pointer");
+  int64_t n = M * C;
+  if (n == 0) return CLSKD_OK;
+  bool vec = (C % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+#define L(TX, TY)                                                                                 \
+  do {                                                                                            \
+    if (vec)                                                                                      \
+      bn_act_fwd_kernel<TX, TY><<<ew_grid(n / 4, 256), 256, 0, ST>>>(                             \
+          (const TX*)x, n / 4, C, mean, invstd, gamma, beta, slope, (TY*)y);                      \
+    else                                                                                          \
+      bn_act_fwd_scalar_kernel<TX, TY><<<ew_grid(n, 256), 256, 0, ST>>>(                          \
+          (const TX*)x, n, C, mean, invstd, gamma, beta, slope, (TY*)y);                          \
+  } while (0)
+  if (x_dtype == CLSKD_F32 && y_dtype == CLSKD_F32) L(float, float);
+  else if (x_dtype == CLSKD_F32) L(float, __nv_bfloat16);
+  else if (y_dtype == CLSKD_F32) L(__nv_bfloat16, float);
+  else L(__nv_bfloat16, __nv_bfloat16);
+#undef L
+  CLSKD_CHECK_LAUNCH("clskd_bn_act_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_bn_act_bwd_stats(const void* x, int x_dtype, const void* dy, int dy_dtype,
+                                      int64_t M, int C, const float* mean, const float* invstd,
+                                      const float* gamma, const float* beta, const float* slope,
+                                      double* sum_dz, double* sum_dz_xhat, double* dslope,
+                                      void* stream) {
+  CLSKD_CHECK_ARG(x && dy && mean && invstd && sum_dz && sum_dz_xhat,
+                  "clskd_bn_act_bwd_stats: null pointer");
+  CLSKD_CHECK_ARG(x_dtype == dy_dtype, "clskd_bn_act_bwd_stats: x/dy dtype must match");
+  CsGeom g;
+  CLSKD_CHECK_ARG(colstats_geom(M, C, &g) == 0, "clskd_bn_act_bwd_stats: C=%d unsupported", C);
+  {
+    cudaError_t e__ = cudaSuccess;
+    e__ = cudaMemsetAsync(sum_dz, 0, sizeof(double) * C, ST);
+    if (e__ == cudaSuccess) e__ = cudaMemsetAsync(sum_dz_xhat, 0, sizeof(double) * C, ST);
+    if (e__ == cudaSuccess && dslope) e__ = cudaMemsetAsync(dslope, 0, sizeof(double), ST);
+    if (e__ != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e__)); return CLSKD_ERR_CUDA; }
+  }
+  if (M == 0) return CLSKD_OK;
+  size_t sh = 3 * g.threads * sizeof(float);
+  CLSKD_DISPATCH_DTYPE(x_dtype, T,
+                       (colstats_kernel<T, 1><<<g.grid, g.threads, sh, ST>>>(
+                           (const T*)x, (const T*)dy, M, C, g.rpb, mean, invstd, gamma, beta, slope,
+                           sum_dz, sum_dz_xhat, dslope)));
+  CLSKD_CHECK_LAUNCH("clskd_bn_act_bwd_stats");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_bn_act_bwd_apply(const void* x, int x_dtype, const void* dy, int dy_dtype,
+                                      int64_t M, int C, const float* mean, const float* invstd,
+                                      const float* gamma, const float* beta, const float* slope,
+                                      const double* sum_dz, const double* sum_dz_xhat,
+                                      const double* dslope, int training, void* dx, int dx_dtype,
+                                      float* dgamma, float* dbeta, float* dslope_out,
+                                      void* stream) {
+  CLSKD_CHECK_ARG(x && dy && dx && mean && invstd && sum_dz && sum_dz_xhat,
+                  "clskd_bn_act_bwd_apply: null pointer");
+  CLSKD_CHECK_ARG(x_dtype == dy_dtype && x_dtype == dx_dtype,
+                  "clskd_bn_act_bwd_apply: dtypes must match");
+  int64_t n = M * C;
+  if (n > 0) {
+    CLSKD_DISPATCH_DTYPE(x_dtype, T,
+                         (bn_act_bwd_apply_kernel<T, T, T><<<ew_grid(n, 256), 256, 0, ST>>>(
+                             (const T*)x, (const T*)dy, n, M, C, mean, invstd, gamma, beta, slope,
+                             sum_dz, sum_dz_xhat, training, (T*)dx)));
+    CLSKD_CHECK_LAUNCH("clskd_bn_act_bwd_apply");
+  }
+  if (dgamma || dbeta || dslope_out) {
+    bn_param_grads_kernel<<<cdiv(C, 128), 128, 0, ST>>>(sum_dz, sum_dz_xhat, dslope, C, dgamma,
+                                                        dbeta, dslope_out);
+    CLSKD_CHECK_LAUNCH("clskd_bn_act_bwd_apply(param grads)");
+  }
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_cbn_moments(const void* x, int dtype, int64_t M, int Cc, double* s,
+                                 void* stream) {
+  CLSKD_CHECK_ARG(x && s, "clskd_cbn_moments: null pointer");
+  CsGeom g;
+  CLSKD_CHECK_ARG(colstats_geom(M, Cc, &g) == 0, "clskd_cbn_moments: Cc=%d unsupported", Cc);
+  {
+    cudaError_t e__ = cudaSuccess;
+    e__ = cudaMemsetAsync(s, 0, sizeof(double) * 5 * Cc, ST);
+    if (e__ != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e__)); return CLSKD_ERR_CUDA; }
+  }
+  if (M == 0) return CLSKD_OK;
+  size_t sh = 5 * g.threads * sizeof(float);
+  CLSKD_DISPATCH_DTYPE(dtype, T,
+                       (cbn_moments_kernel<T><<<g.grid, g.threads, sh, ST>>>((const T*)x, M, Cc,
+                                                                              g.rpb, s)));
+  CLSKD_CHECK_LAUNCH("clskd_cbn_moments");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_cbn_finalize(const double* s, int64_t M, int Cc, float eps, float momentum,
+                                  int training, const float* Wrr, const float* Wri,
+                                  const float* Wii, float* RMr, float* RMi, float* RVrr,
+                                  float* RVri, float* RVii, float* coef, void* stream) {
+  CLSKD_CHECK_ARG(coef && (training ? (s != nullptr && M > 0) : (RMr && RMi && RVrr && RVri && RVii)),
+                  "clskd_cbn_finalize: bad arguments");
+  cbn_finalize_kernel<<<cdiv(Cc, 128), 128, 0, ST>>>(s, M, Cc, eps, momentum, training, Wrr, Wri,
+                                                     Wii, RMr, RMi, RVrr, RVri, RVii, coef);
+  CLSKD_CHECK_LAUNCH("clskd_cbn_finalize");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_cbn_apply(const void* x, int x_dtype, int64_t M, int Cc, const float* coef,
+                               const float* Br, const float* Bi, void* y, int y_dtype,
+                               void* stream) {
+  CLSKD_CHECK_ARG(x && y && coef, "clskd_cbn_apply: null pointer");
+  CLSKD_CHECK_ARG(x_dtype == y_dtype, "clskd_cbn_apply: dtypes must match");
+  if (M * Cc == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(x_dtype, T,
+                       (cbn_apply_kernel<T, T><<<ew_grid(M * Cc, 256), 256, 0, ST>>>(
+                           (const T*)x, M, Cc, coef, Br, Bi, (T*)y)));
+  CLSKD_CHECK_LAUNCH("clskd_cbn_apply");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_mask_fwd(const float* spec, const void* mask, int mask_dtype, int64_t m_sB,
+                              int64_t m_sT, int B, int T, int nbins, int mode, float* out_spec,
+                              float* mask_padded, void* stream) {
+  CLSKD_CHECK_ARG(spec && mask && out_spec, "clskd_mask_fwd: null pointer");
+  CLSKD_CHECK_ARG(mode >= 0 && mode <= 2, "clskd_mask_fwd: mode %d (0='E',1='C',2='R')", mode);
+  int64_t total = (int64_t)B * T * nbins;
+  if (total == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(mask_dtype, TM,
+                       (mask_fwd_kernel<TM><<<ew_grid(total, 256), 256, 0, ST>>>(
+                           spec, (const TM*)mask, m_sB, m_sT, B, T, nbins, mode, out_spec,
+                           mask_padded)));
+  CLSKD_CHECK_LAUNCH("clskd_mask_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_mask_bwd(const float* spec, const void* mask, int mask_dtype, int64_t m_sB,
+                              int64_t m_sT, int B, int T, int nbins, int mode,
+                              const float* dout_spec, void* dmask, int dmask_dtype, int64_t dm_sB,
+                              int64_t dm_sT, void* stream) {
+  CLSKD_CHECK_ARG(spec && mask && dout_spec && dmask, "clskd_mask_bwd: null pointer");
+  CLSKD_CHECK_ARG(mask_dtype == dmask_dtype, "clskd_mask_bwd: mask/dmask dtype must match");
+  int64_t total = (int64_t)B * T * (nbins - 1);
+  if (total == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(mask_dtype, TM,
+                       (mask_bwd_kernel<TM, TM><<<ew_grid(total, 256), 256, 0, ST>>>(
+                           spec, (const TM*)mask, m_sB, m_sT, B, T, nbins, mode, dout_spec,
+                           (TM*)dmask, dm_sB, dm_sT)));
+  CLSKD_CHECK_LAUNCH("clskd_mask_bwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_ola_fwd(const float* frames, const float* window, int B, int T, int win,
+                             int hop, int trim, int do_clamp, float* wav, void* stream) {
+  CLSKD_CHECK_ARG(frames && wav, "clskd_ola_fwd: null pointer");
+  CLSKD_CHECK_ARG(win >= hop && hop > 0 && T >= 1 && trim >= 0, "clskd_ola_fwd: bad geometry");
+  int L = (T - 1) * hop + win - 2 * trim;
+  CLSKD_CHECK_ARG(L > 0, "clskd_ola_fwd: too few frames");
+  int64_t total = (int64_t)B * L;
+  ola_fwd_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(frames, window, B, T, win, hop, trim, do_clamp,
+                                                      wav);
+  CLSKD_CHECK_LAUNCH("clskd_ola_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_ola_bwd(const float* dwav, const float* wav, const float* window, int B, int T,
+                             int win, int hop, int trim, int do_clamp, float* dframes,
+                             void* stream) {
+  CLSKD_CHECK_ARG(dwav && dframes && (wav || !do_clamp), "clskd_ola_bwd: null pointer");
+  int64_t total = (int64_t)B * T * win;
+  if (total == 0) return CLSKD_OK;
+  ola_bwd_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(dwav, wav, window, B, T, win, hop, trim,
+                                                      do_clamp, dframes);
+  CLSKD_CHECK_LAUNCH("clskd_ola_bwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_resize_f_fwd(const void* x, int dtype, int64_t BT, int Fi, int Fo, int C,
+                                  void* y, void* stream) {
+  CLSKD_CHECK_ARG(x && y && Fi > 0 && Fo > 0, "clskd_resize_f_fwd: bad arguments");
+  int64_t total = BT * Fo * C;
+  if (total == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(dtype, T,
+                       (resize_f_fwd_kernel<T><<<ew_grid(total, 256), 256, 0, ST>>>(
+                           (const T*)x, BT, Fi, Fo, C, (T*)y)));
+  CLSKD_CHECK_LAUNCH("clskd_resize_f_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_resize_f_bwd(const void* dy, int dtype, int64_t BT, int Fi, int Fo, int C,
+                                  void* dx, void* stream) {
+  CLSKD_CHECK_ARG(dy && dx && Fi > 0 && Fo > 0, "clskd_resize_f_bwd: bad arguments");
+  int64_t total = BT * Fi * C;
+  if (total == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(dtype, T,
+                       (resize_f_bwd_kernel<T><<<ew_grid(total, 256), 256, 0, ST>>>(
+                           (const T*)dy, BT, Fi, Fo, C, (T*)dx)));
+  CLSKD_CHECK_LAUNCH("clskd_resize_f_bwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_att_blend_fwd(const void* x, const void* y, int dtype, const float* z,
+                                   int64_t M, int C, void* out, void* stream) {
+  CLSKD_CHECK_ARG(x && y && z && out, "clskd_att_blend_fwd: null pointer");
+  if (M * C == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(dtype, T,
+                       (att_blend_fwd_kernel<T><<<ew_grid(M * C, 256), 256, 0, ST>>>(
+                           (const T*)x, (const T*)y, z, M, C, (T*)out)));
+  CLSKD_CHECK_LAUNCH("clskd_att_blend_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_att_blend_bwd(const void* x, const void* y, int dtype, const float* z,
+                                   const void* dout, int64_t M, int C, void* dx, void* dy,
+                                   float* dz, void* stream) {
+  CLSKD_CHECK_ARG(x && y && z && dout && dx && dy && dz, "clskd_att_blend_bwd: null pointer");
+  if (M * C == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(dtype, T,
+                       (att_blend_bwd_kernel<T><<<ew_grid(M * 32, 256), 256, 0, ST>>>(
+                           (const T*)x, (const T*)y, z, (const T*)dout, M, C, (T*)dx, (T*)dy, dz)));
+  CLSKD_CHECK_LAUNCH("clskd_att_blend_bwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_adaptive_pool_fwd(const void* x, int dtype, int B, int T, int F, int C, int l,
+                                       float* out, void* stream) {
+  CLSKD_CHECK_ARG(x && out && l >= 1, "clskd_adaptive_pool_fwd: bad arguments");
+  if ((int64_t)B * T * F * C == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(dtype, TT,
+                       (adaptive_pool_fwd_kernel<TT><<<B * l * l, 128, 0, ST>>>((const TT*)x, B, T,
+                                                                                 F, C, l, out)));
+  CLSKD_CHECK_LAUNCH("clskd_adaptive_pool_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_adaptive_pool_bwd(const float* dout, int B, int T, int F, int C, int l,
+                                       void* dx, int dtype, int accumulate, void* stream) {
+  CLSKD_CHECK_ARG(dout && dx && l >= 1, "clskd_adaptive_pool_bwd: bad arguments");
+  int64_t total = (int64_t)B * T * F * C;
+  if (total == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(dtype, TT,
+                       (adaptive_pool_bwd_kernel<TT><<<ew_grid(total, 256), 256, 0, ST>>>(
+                           dout, B, T, F, C, l, (TT*)dx, accumulate)));
+  CLSKD_CHECK_LAUNCH("clskd_adaptive_pool_bwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_sqdiff_sum(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n,
+                                double* out, void* stream) {
+  CLSKD_CHECK_ARG(a && b && out, "clskd_sqdiff_sum: null pointer");
+  if (n == 0) return CLSKD_OK;
+  int grid = ew_grid(n, 256);
+  if (grid > sm_count() * 4) grid = sm_count() * 4;
+#define L(TA, TB) sqdiff_sum_kernel<TA, TB><<<grid, 256, 0, ST>>>((const TA*)a, (const TB*)b, n, out)
+  if (a_dtype == CLSKD_F32 && b_dtype == CLSKD_F32) L(float, float);
+  else if (a_dtype == CLSKD_F32) L(float, __nv_bfloat16);
+  else if (b_dtype == CLSKD_F32) L(__nv_bfloat16, float);
+  else L(__nv_bfloat16, __nv_bfloat16);
+#undef L
+  CLSKD_CHECK_LAUNCH("clskd_sqdiff_sum");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_sqdiff_bwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n,
+                                const float* gout, float scale, void* da, int da_dtype,
+                                int accumulate, void* stream) {
+  CLSKD_CHECK_ARG(a && b && gout && da, "clskd_sqdiff_bwd: null pointer");
+  CLSKD_CHECK_ARG(a_dtype == da_dtype, "clskd_sqdiff_bwd: a/da dtype must match");
+  if (n == 0) return CLSKD_OK;
+  int grid = ew_grid(n, 256);
+#define L(TA, TB)                                                                              \
+  sqdiff_bwd_kernel<TA, TB, TA><<<grid, 256, 0, ST>>>((const TA*)a, (const TB*)b, n, gout, scale, \
+                                                      (TA*)da, accumulate)
+  if (a_dtype == CLSKD_F32 && b_dtype == CLSKD_F32) L(float, float);
+  else if (a_dtype == CLSKD_F32) L(float, __nv_bfloat16);
+  else if (b_dtype == CLSKD_F32) L(__nv_bfloat16, float);
+  else L(__nv_bfloat16, __nv_bfloat16);
+#undef L
+  CLSKD_CHECK_LAUNCH("clskd_sqdiff_bwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int step,
+                               float grad_scale, void* stream) {
+  CLSKD_CHECK_ARG(p && g && m && v && step >= 1, "clskd_adam_step: bad arguments");
+  if (n == 0) return CLSKD_OK;
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<ew_grid(n, 256), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                                               bc1, sqrtf(bc2), grad_scale);
+  CLSKD_CHECK_LAUNCH("clskd_adam_step");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_fill_f32(float* p, int64_t n, float v, void* stream) {
+  CLSKD_CHECK_ARG(p || n == 0, "clskd_fill_f32: null pointer");
+  if (n == 0) return CLSKD_OK;
+  fill_kernel<<<ew_grid(n, 256), 256, 0, ST>>>(p, n, v);
+  CLSKD_CHECK_LAUNCH("clskd_fill_f32");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_axpy_f32(float* y, const float* x, int64_t n, float a, void* stream) {
+  CLSKD_CHECK_ARG((y && x) || n == 0, "clskd_axpy_f32: null pointer");
+  if (n == 0) return CLSKD_OK;
+  axpy_kernel<<<ew_grid(n, 256), 256, 0, ST>>>(y, x, n, a);
+  CLSKD_CHECK_LAUNCH("clskd_axpy_f32");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_axpby_f32(const float* x, const float* y, float a, float b, float* out,
+                               int64_t n, void* stream) {
+  CLSKD_CHECK_ARG((x && out) || n == 0, "clskd_axpby_f32: null pointer");
+  if (n == 0) return CLSKD_OK;
+  axpby_kernel<<<ew_grid(n, 256), 256, 0, ST>>>(x, y, a, b, out, n);
+  CLSKD_CHECK_LAUNCH("clskd_axpby_f32");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_multi_pack_f32(const void* ptrs, const int64_t* offsets, int n, int64_t total,
+                                    float* flat, void* stream) {
+  CLSKD_CHECK_ARG(ptrs && offsets && flat && n >= 1, "clskd_multi_pack_f32: bad arguments");
+  if (total == 0) return CLSKD_OK;
+  multi_pack_kernel<<<ew_grid(total, 256), 256, 0, ST>>>((const unsigned long long*)ptrs, offsets, n,
+                                                        flat);
+  CLSKD_CHECK_LAUNCH("clskd_multi_pack_f32");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_f64_to_f32(const double* in, int n, double scale, float* out, void* stream) {
+  CLSKD_CHECK_ARG(in && out, "clskd_f64_to_f32: null pointer");
+  if (n == 0) return CLSKD_OK;
+  f64_to_f32_kernel<<<cdiv(n, 128), 128, 0, ST>>>(in, n, scale, out);
+  CLSKD_CHECK_LAUNCH("clskd_f64_to_f32");
+  return CLSKD_OK;
+}

@@ -1,0 +1,282 @@
+// LSTM recurrence of the complex LSTM (NavieComplexLSTM, tools_for_model.py:138-178).
+//
+// The input projections (x W_ih^T + b_ih + b_hh) are batched GEMMs done by tapconv; what is left
+// is strictly sequential: per time step a [RB x H] x [H x 4H] product plus the gate math.  That is
+// latency bound, so one persistent CTA owns RB=4 batch rows of one weight set for the whole
+// sequence: W_hh stays resident in shared memory (fp32 up to H=64, bf16 up to H=128; larger falls
+// back to L2-resident global reads), h lives in shared memory, c in a register, and the next step's
+// pre-activations are prefetched while the current step computes.  The four LSTM passes of a
+// complex layer (2 weight sets x {real,imag} rows) run concurrently as independent CTAs.
+#include "common.cuh"
+
+namespace clskd {
+namespace {
+
+constexpr int RB = 4;
+
+__device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + expf(-v)); }
+
+// WMODE 0: W^T fp32 in smem; 1: W^T bf16 in smem; 2: W^T read from global (L2)
+template <int WMODE>
+__global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ whh_t,
+                                int T, int R, int Bp, int H, int64_t pre_pstride,
+                                int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride,
+                                int64_t whh_set_stride, float* __restrict__ h_out,
+                                float* __restrict__ gates_out, float* __restrict__ c_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int G = 4 * H;
+  const int tid = threadIdx.x;  // gate row g
+  const int set = blockIdx.y;
+  const int r0 = blockIdx.x * RB;
+  const int64_t out_set_stride = (int64_t)T * R * H;
+  pre += (int64_t)set * pre_set_stride;
+  whh_t += (int64_t)set * whh_set_stride;
+  h_out += (int64_t)set * out_set_stride;
+  if (gates_out) gates_out += (int64_t)set * out_set_stride * 4;
+  if (c_out) c_out += (int64_t)set * out_set_stride;
+
+  float* h_s = reinterpret_cast<float*>(smem_raw);          // [RB][H]
+  float* g_s = h_s + RB * H;                                  // [RB][4H]
+  float* w_f = g_s + RB * G;                                  // [H][4H] fp32 (WMODE 0)
+  __nv_bfloat16* w_b = reinterpret_cast<__nv_bfloat16*>(w_f); // [H][4H] bf16 (WMODE 1)
+
+  if (WMODE == 0) {
+    for (int i = tid; i < H * G; i += blockDim.x) w_f[i] = whh_t[i];
+  } else if (WMODE == 1) {
+    for (int i = tid; i < H * G; i += blockDim.x) w_b[i] = __float2bfloat16_rn(whh_t[i]);
+  }
+  for (int i = tid; i < RB * H; i += blockDim.x) h_s[i] = 0.f;
+
+  // cell ownership: thread tid -> (row cr, unit cj); valid because blockDim = 4H = RB*H
+  const int cr = tid / H, cj = tid - cr * H;
+  float c_state = 0.f;
+
+  // row r -> (part, batch): pre row base and output row index (without the time term)
+  int64_t prow[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    int rr = min(r0 + r, R - 1);
+    prow[r] = (int64_t)(rr / Bp) * pre_pstride + (int64_t)(rr % Bp) * pre_ld + tid;
+  }
+  float pcur[RB], pnext[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    pcur[r] = (r0 + r < R && T > 0) ? pre[prow[r]] : 0.f;
+    pnext[r] = 0.f;
+  }
+  // output row of this thread's cell: ((part*T + t)*Bp + b)
+  const int crow = min(r0 + cr, R - 1);
+  const int64_t orow_base = (int64_t)(crow / Bp) * T * Bp + (crow % Bp);
+  __syncthreads();
+
+  for (int t = 0; t < T; ++t) {
+    if (t + 1 < T) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+        if (r0 + r < R) pnext[r] = pre[prow[r] + (int64_t)(t + 1) * pre_tstride];
+    }
+    float acc[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = pcur[r];
+    for (int k = 0; k < H; k += 4) {
+      float w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (WMODE == 0) w[e] = w_f[(k + e) * G + tid];
+        else if (WMODE == 1) w[e] = __bfloat162float(w_b[(k + e) * G + tid]);
+        else w[e] = __ldg(whh_t + (int64_t)(k + e) * G + tid);
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        float4 hv = *reinterpret_cast<const float4*>(h_s + r * H + k);
+        acc[r] = fmaf(w[0], hv.x, acc[r]);
+        acc[r] = fmaf(w[1], hv.y, acc[r]);
+        acc[r] = fmaf(w[2], hv.z, acc[r]);
+        acc[r] = fmaf(w[3], hv.w, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) g_s[r * G + tid] = acc[r];
+    __syncthreads();
+    // gate math: one (row, unit) per thread
+    {
+      float gi = sigm(g_s[cr * G + cj]);
+      float gf = sigm(g_s[cr * G + H + cj]);
+      float gg = tanhf(g_s[cr * G + 2 * H + cj]);
+      float go = sigm(g_s[cr * G + 3 * H + cj]);
+      c_state = gf * c_state + gi * gg;
+      float hv = go * tanhf(c_state);
+      h_s[cr * H + cj] = hv;
+      if (r0 + cr < R) {
+        int64_t row = orow_base + (int64_t)t * Bp;
+        h_out[row * H + cj] = hv;
+        if (gates_out) {
+          float* gp = gates_out + row * G;
+          gp[cj] = gi;
+          gp[H + cj] = gf;
+          gp[2 * H + cj] = gg;
+          gp[3 * H + cj] = go;
+        }
+        if (c_out) c_out[row * H + cj] = c_state;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RB; ++r) pcur[r] = pnext[r];
+  }
+}
+
+// BPTT.  Thread tid = (q, k): phase A treats it as cell (row q, unit k); phase B as the partial
+// dot product over gate quarter q for hidden unit k.  W_hh [4H][H] in smem (WMODE 0) or global (2).
+template <int WMODE>
+__global__ void lstm_bwd_kernel(const float* __restrict__ dh_out, const float* __restrict__ whh,
+                                const float* __restrict__ gates, const float* __restrict__ c_all,
+                                int T, int R, int Bp, int H, int64_t whh_set_stride,
+                                int64_t pre_pstride, int64_t pre_tstride, int64_t pre_ld,
+                                int64_t pre_set_stride, float* __restrict__ dpre) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int G = 4 * H;
+  const int tid = threadIdx.x;
+  const int set = blockIdx.y;
+  const int r0 = blockIdx.x * RB;
+  const int64_t set_stride_h = (int64_t)T * R * H;
+  dh_out += (int64_t)set * set_stride_h;
+  c_all += (int64_t)set * set_stride_h;
+  gates += (int64_t)set * set_stride_h * 4;
+  dpre += (int64_t)set * pre_set_stride;
+  whh += (int64_t)set * whh_set_stride;
+
+  float* dp_s = reinterpret_cast<float*>(smem_raw);  // [RB][4H]
+  float* part_s = dp_s + RB * G;                     // [4][RB][H]
+  float* w_s = part_s + 4 * RB * H;                  // [4H][H] (WMODE 0)
+  if (WMODE == 0)
+    for (int i = tid; i < G * H; i += blockDim.x) w_s[i] = whh[i];
+  for (int i = tid; i < 4 * RB * H; i += blockDim.x) part_s[i] = 0.f;
+  __syncthreads();
+
+  const int q = tid / H, k = tid - q * H;  // q in 0..3 (== RB rows)
+  const bool row_ok = (r0 + q) < R;
+  const int rq = min(r0 + q, R - 1);
+  const int64_t orow_base = (int64_t)(rq / Bp) * T * Bp + (rq % Bp);
+  const int64_t prow_base = (int64_t)(rq / Bp) * pre_pstride + (int64_t)(rq % Bp) * pre_ld;
+  float dc_next = 0.f;
+
+  for (int t = T - 1; t >= 0; --t) {
+    // ---- phase A: cell (row q, unit k)
+    float di = 0.f, df = 0.f, dg = 0.f, dout = 0.f;
+    if (row_ok) {
+      int64_t row = orow_base + (int64_t)t * Bp;
+      float dh = dh_out[row * H + k] + part_s[(0 * RB + q) * H + k] + part_s[(1 * RB + q) * H + k] +
+                 part_s[(2 * RB + q) * H + k] + part_s[(3 * RB + q) * H + k];
+      const float* gp = gates + row * G;
+      float gi = gp[k], gf = gp[H + k], gg = gp[2 * H + k], go = gp[3 * H + k];
+      float ct = c_all[row * H + k];
+      float cprev = t > 0 ? c_all[(row - Bp) * H + k] : 0.f;
+      float tc = tanhf(ct);
+      dout = dh * tc * go * (1.f - go);
+      float dc = dh * go * (1.f - tc * tc) + dc_next;
+      di = dc * gg * gi * (1.f - gi);
+      df = dc * cprev * gf * (1.f - gf);
+      dg = dc * gi * (1.f - gg * gg);
+      dc_next = dc * gf;
+      float* dp = dpre + prow_base + (int64_t)t * pre_tstride;
+      dp[k] = di;
+      dp[H + k] = df;
+      dp[2 * H + k] = dg;
+      dp[3 * H + k] = dout;
+    }
+    __syncthreads();  // everyone has consumed part_s
+    dp_s[q * G + k] = di;
+    dp_s[q * G + H + k] = df;
+    dp_s[q * G + 2 * H + k] = dg;
+    dp_s[q * G + 3 * H + k] = dout;
+    __syncthreads();
+    // ---- phase B: partial dh_rec[r][k] over gate quarter q
+    float acc[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+    const int gbeg = q * H;
+    for (int g = 0; g < H; g += 4) {
+      float w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (WMODE == 0) w[e] = w_s[(gbeg + g + e) * H + k];
+        else w[e] = __ldg(whh + (int64_t)(gbeg + g + e) * H + k);
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        float4 dv = *reinterpret_cast<const float4*>(dp_s + r * G + gbeg + g);
+        acc[r] = fmaf(w[0], dv.x, acc[r]);
+        acc[r] = fmaf(w[1], dv.y, acc[r]);
+        acc[r] = fmaf(w[2], dv.z, acc[r]);
+        acc[r] = fmaf(w[3], dv.w, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) part_s[(q * RB + r) * H + k] = acc[r];
+    __syncthreads();
+  }
+}
+
+constexpr size_t kSmemLimit = 200 * 1024;
+
+}  // namespace
+}  // namespace clskd
+
+using namespace clskd;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int clskd_lstm_fwd(const float* pre, const float* whh_t, int T, int R, int Bp, int H,
+                              int nsets, int64_t pre_pstride, int64_t pre_tstride, int64_t pre_ld,
+                              int64_t pre_set_stride, int64_t whh_set_stride, int w_bf16, float* h,
+                              float* gates, float* c, void* stream) {
+  CLSKD_CHECK_ARG(pre && whh_t && h, "clskd_lstm_fwd: null pointer");
+  CLSKD_CHECK_ARG(H >= 4 && H % 4 == 0 && 4 * H <= 1024, "clskd_lstm_fwd: H=%d unsupported (4..256, multiple of 4)", H);
+  CLSKD_CHECK_ARG(T >= 0 && R >= 1 && nsets >= 1 && Bp >= 1 && R % Bp == 0, "clskd_lstm_fwd: bad extents");
+  if (T == 0) return CLSKD_OK;
+  const int G = 4 * H;
+  size_t base = sizeof(float) * ((size_t)RB * H + (size_t)RB * G);
+  size_t w32 = sizeof(float) * (size_t)H * G, w16 = w32 / 2;
+  dim3 grid(cdiv(R, RB), nsets);
+  cudaError_t e;
+#define LSTM_FWD_ARGS pre, whh_t, T, R, Bp, H, pre_pstride, pre_tstride, pre_ld, pre_set_stride, whh_set_stride, h, gates, c
+  if (!w_bf16 && base + w32 <= kSmemLimit) {
+    e = cudaFuncSetAttribute(lstm_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
+    if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+    lstm_fwd_kernel<0><<<grid, G, base + w32, ST>>>(LSTM_FWD_ARGS);
+  } else if (w_bf16 && base + w16 <= kSmemLimit) {
+    e = cudaFuncSetAttribute(lstm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w16));
+    if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+    lstm_fwd_kernel<1><<<grid, G, base + w16, ST>>>(LSTM_FWD_ARGS);
+  } else {
+    lstm_fwd_kernel<2><<<grid, G, base, ST>>>(LSTM_FWD_ARGS);
+  }
+#undef LSTM_FWD_ARGS
+  CLSKD_CHECK_LAUNCH("clskd_lstm_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_lstm_bwd(const float* dh_out, const float* whh, const float* gates,
+                              const float* c, int T, int R, int Bp, int H, int nsets,
+                              int64_t whh_set_stride, int64_t pre_pstride, int64_t pre_tstride,
+                              int64_t pre_ld, int64_t pre_set_stride, float* dpre, void* stream) {
+  CLSKD_CHECK_ARG(dh_out && whh && gates && c && dpre, "clskd_lstm_bwd: null pointer");
+  CLSKD_CHECK_ARG(H >= 4 && H % 4 == 0 && 4 * H <= 1024, "clskd_lstm_bwd: H=%d unsupported", H);
+  CLSKD_CHECK_ARG(R >= 1 && Bp >= 1 && R % Bp == 0, "clskd_lstm_bwd: bad extents");
+  if (T == 0) return CLSKD_OK;
+  const int G = 4 * H;
+  size_t base = sizeof(float) * ((size_t)RB * G + 4 * (size_t)RB * H);
+  size_t w32 = sizeof(float) * (size_t)H * G;
+  dim3 grid(cdiv(R, RB), nsets);
+#define LSTM_BWD_ARGS dh_out, whh, gates, c, T, R, Bp, H, whh_set_stride, pre_pstride, pre_tstride, pre_ld, pre_set_stride, dpre
+  if (base + w32 <= kSmemLimit) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
+    if (e != cudaSuccess) { set_error("clskd_lstm_bwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+    lstm_bwd_kernel<0><<<grid, G, base + w32, ST>>>(LSTM_BWD_ARGS);
+  } else {
+    lstm_bwd_kernel<2><<<grid, G, base, ST>>>(LSTM_BWD_ARGS);
+  }
+#undef LSTM_BWD_ARGS
+  CLSKD_CHECK_LAUNCH("clskd_lstm_bwd");
+  return CLSKD_OK;
+}

@@ -1,0 +1,373 @@
+// Tap-list implicit GEMM on CUDA cores (fp32 FMA, fp32 accumulate).
+//
+// This is the exact-fp32 policy of every convolution-like operator on the DCCRN path and the
+// fallback for layers whose channel counts are below a UMMA tile (enc0: K=20, dec5: N=20, the
+// ABF attention conv: N=2).  The bf16 tensor-core version of the same contraction lives in
+// tapconv_umma.cu.  See clskd.h for the contraction definition.
+#include "common.cuh"
+
+namespace clskd {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+struct RowInfo {
+  int b, t, f;
+};
+
+// ------------------------------------------------------------------------------------------
+// forward: Y[M,N] = im2col(X)[M,Ktot] * W[Ktot,N]
+// ------------------------------------------------------------------------------------------
+template <typename TX, typename TY, bool VEC>
+__global__ void __launch_bounds__(NT) tapconv_fwd_kernel(ClskdTapConv d) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  __shared__ int rowB[BM], rowT[BM], rowF[BM];
+
+  const int tid = threadIdx.x;
+  const int64_t M = (int64_t)d.B * d.To * d.Fo;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int Ctot = d.c0 + d.c1;
+  const int Ktot = d.ntaps * Ctot;
+  const TX* x0 = reinterpret_cast<const TX*>(d.x0);
+  const TX* x1 = reinterpret_cast<const TX*>(d.x1);
+  const float* w = reinterpret_cast<const float*>(d.w);
+
+  if (tid < BM) {
+    int64_t m = m0 + tid;
+    if (m < M) {
+      int f = (int)(m % d.Fo);
+      int64_t r = m / d.Fo;
+      rowF[tid] = f;
+      rowT[tid] = (int)(r % d.To);
+      rowB[tid] = (int)(r / d.To);
+    } else {
+      rowB[tid] = -1;
+      rowT[tid] = 0;
+      rowF[tid] = 0;
+    }
+  }
+  __syncthreads();
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int a_row = tid >> 2;        // 0..63
+  const int a_k4 = (tid & 3) * 4;    // 0,4,8,12
+  const int b_k = tid >> 4;          // 0..15
+  const int b_n4 = (tid & 15) * 4;   // 0..60
+  const int ty = tid >> 4, tx = tid & 15;
+
+  const int rb = rowB[a_row], rt = rowT[a_row], rf = rowF[a_row];
+
+  for (int kk = 0; kk < Ktot; kk += BK) {
+    // ---- A tile (gather)
+    float av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rb >= 0) {
+      if (VEC) {
+        // Ctot % 16 == 0 and c0 % 16 == 0: the 16-wide chunk sits in one tap and one source
+        int kg = kk + a_k4;
+        int tap = kg / Ctot;
+        int c = kg - tap * Ctot;
+        int ti = rt + d.dt[tap], fi = rf * d.sf + d.df[tap];
+        if (ti >= 0 && ti < d.Ti && fi >= 0 && fi < d.Fi) {
+          float4 v;
+          if (c < d.c0)
+            v = ld4(x0 + (int64_t)rb * d.x0_sB + (int64_t)ti * d.x0_sT + (int64_t)fi * d.x0_sF + c);
+          else
+            v = ld4(x1 + (int64_t)rb * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF +
+                    (c - d.c0));
+          av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int kg = kk + a_k4 + e;
+          if (kg < Ktot) {
+            int tap = kg / Ctot;
+            int c = kg - tap * Ctot;
+            int ti = rt + d.dt[tap], fi = rf * d.sf + d.df[tap];
+            if (ti >= 0 && ti < d.Ti && fi >= 0 && fi < d.Fi) {
+              if (c < d.c0)
+                av[e] = ld_f(x0 + (int64_t)rb * d.x0_sB + (int64_t)ti * d.x0_sT +
+                             (int64_t)fi * d.x0_sF + c);
+              else
+                av[e] = ld_f(x1 + (int64_t)rb * d.x1_sB + (int64_t)ti * d.x1_sT +
+                             (int64_t)fi * d.x1_sF + (c - d.c0));
+            }
+          }
+        }
+      }
+    }
+    // ---- B tile
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      int kg = kk + b_k;
+      if (kg < Ktot) {
+        int n = n0 + b_n4;
+        const float* wp = w + (int64_t)kg * d.N + n;
+        if (VEC && n + 3 < d.N) {
+          float4 v = *reinterpret_cast<const float4*>(wp);
+          bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < d.N) bv[e] = wp[e];
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) As[a_k4 + e][a_row] = av[e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) Bs[b_k][b_n4 + e] = bv[e];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float ar[4] = {a.x, a.y, a.z, a.w};
+      float br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+
+  // ---- epilogue
+  TY* y = reinterpret_cast<TY*>(d.y);
+  const int n = n0 + tx * 4;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (d.bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < d.N) bias[j] = d.bias[n + j];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = ty * 4 + i;
+    int b = rowB[r];
+    if (b < 0) continue;
+    TY* yp = y + (int64_t)b * d.y_sB + (int64_t)rowT[r] * d.y_sT + (int64_t)rowF[r] * d.y_sF + n;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n + j < d.N) {
+        float v = acc[i][j] + bias[j];
+        if (d.accumulate) v += ld_f(yp + j);
+        st_f(yp + j, v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dW[Ktot,N] = im2col(X)^T [Ktot,M] * dY[M,N], split over M with fp32 atomics
+// ------------------------------------------------------------------------------------------
+constexpr int WK = 16;  // rows of M per step
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(NT) tapconv_wgrad_kernel(ClskdTapConv d, int64_t rows_per_split) {
+  __shared__ float As[WK][BM + 4];  // [m][kg]
+  __shared__ float Bs[WK][BN + 4];  // [m][n]
+
+  const int tid = threadIdx.x;
+  const int64_t M = (int64_t)d.B * d.To * d.Fo;
+  const int kg0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int Ctot = d.c0 + d.c1;
+  const int Ktot = d.ntaps * Ctot;
+  const TX* x0 = reinterpret_cast<const TX*>(d.x0);
+  const TX* x1 = reinterpret_cast<const TX*>(d.x1);
+  const TY* dy = reinterpret_cast<const TY*>(d.y);
+  float* dw = reinterpret_cast<float*>(const_cast<void*>(d.w));
+
+  const int64_t mbeg = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t mend = min(M, mbeg + rows_per_split);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // loader mapping: row r = tid/16 (0..15), 4 consecutive columns starting at (tid%16)*4
+  const int l_r = tid >> 4;
+  const int l_c4 = (tid & 15) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  // decode this thread's 4 kg columns once
+  int tapv[4], cv[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int kg = kg0 + l_c4 + e;
+    if (kg < Ktot) {
+      tapv[e] = kg / Ctot;
+      cv[e] = kg - tapv[e] * Ctot;
+    } else {
+      tapv[e] = -1;
+      cv[e] = 0;
+    }
+  }
+
+  for (int64_t mm = mbeg; mm < mend; mm += WK) {
+    int64_t m = mm + l_r;
+    float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < mend) {
+      int f = (int)(m % d.Fo);
+      int64_t r = m / d.Fo;
+      int t = (int)(r % d.To);
+      int b = (int)(r / d.To);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (tapv[e] >= 0) {
+          int ti = t + d.dt[tapv[e]], fi = f * d.sf + d.df[tapv[e]];
+          if (ti >= 0 && ti < d.Ti && fi >= 0 && fi < d.Fi) {
+            int c = cv[e];
+            if (c < d.c0)
+              av[e] = ld_f(x0 + (int64_t)b * d.x0_sB + (int64_t)ti * d.x0_sT +
+                           (int64_t)fi * d.x0_sF + c);
+            else
+              av[e] = ld_f(x1 + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT +
+                           (int64_t)fi * d.x1_sF + (c - d.c0));
+          }
+        }
+      }
+      const TY* yp = dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int n = n0 + l_c4 + e;
+        if (n < d.N) bv[e] = ld_f(yp + n);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      As[l_r][l_c4 + e] = av[e];
+      Bs[l_r][l_c4 + e] = bv[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float ar[4] = {a.x, a.y, a.z, a.w};
+      float br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int kg = kg0 + ty * 4 + i;
+    if (kg >= Ktot) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < d.N) atomicAdd(dw + (int64_t)kg * d.N + n, acc[i][j]);
+    }
+  }
+}
+
+int check_desc(const ClskdTapConv* d, const char* who) {
+  CLSKD_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
+  CLSKD_CHECK_ARG(d->x0 && d->w && d->y, "%s: null tensor pointer", who);
+  CLSKD_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= CLSKD_MAX_TAPS, "%s: ntaps=%d out of range", who,
+                  d->ntaps);
+  CLSKD_CHECK_ARG(d->c0 >= 1 && d->c1 >= 0 && (d->c1 == 0 || d->x1), "%s: bad channel split", who);
+  CLSKD_CHECK_ARG(d->B >= 0 && d->To >= 0 && d->Fo >= 0 && d->N >= 1 && d->sf >= 1,
+                  "%s: bad extents", who);
+  CLSKD_CHECK_ARG((d->x_dtype == CLSKD_F32 || d->x_dtype == CLSKD_BF16) &&
+                      (d->y_dtype == CLSKD_F32 || d->y_dtype == CLSKD_BF16),
+                  "%s: bad dtype tag", who);
+  return CLSKD_OK;
+}
+
+bool vec_ok(const ClskdTapConv* d) {
+  int Ctot = d->c0 + d->c1;
+  if (Ctot % 16 || d->c0 % 16 || d->N % 4) return false;
+  int xe = d->x_dtype == CLSKD_F32 ? 4 : 2;
+  // 4-element vector loads: 16 B (fp32) / 8 B (bf16) alignment of bases and strides
+  auto al = [&](const void* p, int64_t a, int64_t b, int64_t c) {
+    return ((uintptr_t)p % (4 * xe) == 0) && a % 4 == 0 && b % 4 == 0 && c % 4 == 0;
+  };
+  if (!al(d->x0, d->x0_sB, d->x0_sT, d->x0_sF)) return false;
+  if (d->c1 && !al(d->x1, d->x1_sB, d->x1_sT, d->x1_sF)) return false;
+  if ((uintptr_t)d->w % 16) return false;
+  return true;
+}
+
+}  // namespace
+
+}  // namespace clskd
+
+using namespace clskd;
+
+extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
+  int rc = check_desc(d, "clskd_tapconv_fwd");
+  if (rc) return rc;
+  CLSKD_CHECK_ARG(!(d->accumulate && d->y_dtype != CLSKD_F32),
+                  "clskd_tapconv_fwd: accumulate needs fp32 output");
+  int64_t M = (int64_t)d->B * d->To * d->Fo;
+  if (M == 0) return CLSKD_OK;
+  dim3 grid(cdiv(M, BM), cdiv(d->N, BN));
+  cudaStream_t st = (cudaStream_t)stream;
+  bool vec = vec_ok(d);
+#define LAUNCH(TX, TY)                                                        \
+  do {                                                                        \
+    if (vec) tapconv_fwd_kernel<TX, TY, true><<<grid, NT, 0, st>>>(*d);       \
+    else tapconv_fwd_kernel<TX, TY, false><<<grid, NT, 0, st>>>(*d);          \
+  } while (0)
+  if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32) LAUNCH(float, float);
+  else if (d->x_dtype == CLSKD_F32) LAUNCH(float, __nv_bfloat16);
+  else if (d->y_dtype == CLSKD_F32) LAUNCH(__nv_bfloat16, float);
+  else LAUNCH(__nv_bfloat16, __nv_bfloat16);
+#undef LAUNCH
+  CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream) {
+  int rc = check_desc(d, "clskd_tapconv_wgrad");
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int Ktot = d->ntaps * (d->c0 + d->c1);
+  int64_t M = (int64_t)d->B * d->To * d->Fo;
+  if (!d->accumulate) {
+    cudaError_t e = cudaMemsetAsync(const_cast<void*>(d->w), 0, sizeof(float) * (size_t)Ktot * d->N, st);
+    if (e != cudaSuccess) {
+      set_error("clskd_tapconv_wgrad: memset failed: %s", cudaGetErrorString(e));
+      return CLSKD_ERR_CUDA;
+    }
+  }
+  if (M == 0) return CLSKD_OK;
+  int tiles = cdiv(Ktot, BM) * cdiv(d->N, BN);
+  int target = sm_count() * 6;
+  int splits = target / tiles;
+  if (splits < 1) splits = 1;
+  int64_t max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits > 65535) splits = 65535;
+  int64_t rows = (M + splits - 1) / splits;
+  rows = (rows + WK - 1) / WK * WK;
+  splits = (int)((M + rows - 1) / rows);
+  dim3 grid(cdiv(Ktot, BM), cdiv(d->N, BN), splits);
+  if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32)
+    tapconv_wgrad_kernel<float, float><<<grid, NT, 0, st>>>(*d, rows);
+  else if (d->x_dtype == CLSKD_F32)
+    tapconv_wgrad_kernel<float, __nv_bfloat16><<<grid, NT, 0, st>>>(*d, rows);
+  else if (d->y_dtype == CLSKD_F32)
+    tapconv_wgrad_kernel<__nv_bfloat16, float><<<grid, NT, 0, st>>>(*d, rows);
+  else
+    tapconv_wgrad_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, NT, 0, st>>>(*d, rows);
+  CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad");
+  return CLSKD_OK;
+}

@@ -1,0 +1,445 @@
+// Tap-list implicit GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), bf16
+// operands, fp32 accumulation in tensor memory.
+//
+//   Y[b,to,fo,n] = bias[n] + sum_j sum_c X[b, to+dt[j], fo*sf+df[j], c] * W[j][n][c]
+//
+// One CTA computes a 128 x BLOCK_N output tile: the 128 rows are a (t_tile x fo_tile) patch of one
+// utterance, so that for every tap the A operand is ONE TMA box of the channels-last activation
+// tensor viewed as the 5-D tensor (C, f-parity, F/sf, T, B); the tap only shifts the box
+// coordinates, and frequency/time zero padding (and the ragged last time tile) come for free from
+// TMA out-of-bounds zero fill.  The skip connection of the decoder is a second tensor map that
+// supplies the upper K range (no materialised concat).  B is the packed block weight
+// [tap][n][c] (K-major).  Both operands land in 128/64/32-byte swizzled K-major shared memory and
+// are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16 per instruction) issued by one thread.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue (tcgen05.ld -> bias -> bf16/fp32 -> global).  Two CTAs are resident per
+// SM (<=3-4 stages each) so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace clskd {
+namespace {
+
+constexpr int UM = 128;       // UMMA M
+constexpr int kThreads = 192;
+
+struct UmmaParams {
+  int B, To, Fo;
+  int t_tile, fo_tile, f_tiles, t_tiles, tiles_n;
+  int block_n, block_k;
+  int chunks0, chunks_tot;  // K chunks of source 0 / total per tap
+  int ntaps;
+  int tap_t[CLSKD_MAX_TAPS];   // time offset
+  int tap_p[CLSKD_MAX_TAPS];   // parity coordinate (df mod sf)
+  int tap_f[CLSKD_MAX_TAPS];   // floor(df / sf)
+  int stages;
+  uint32_t a_bytes, b_bytes;   // per stage, padded to 1024
+  uint32_t tx_bytes;           // bytes actually delivered per stage
+  uint32_t sbo;                // stride byte offset >> 4
+  uint32_t layout_type;        // UMMA smem layout type (2 = SW128, 4 = SW64, 6 = SW32)
+  uint32_t tmem_cols;
+  void* y;
+  int64_t y_sB, y_sT, y_sF;
+  int y_dtype;
+  const float* bias;
+  int N;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar), done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo, uint32_t layout) {
+  uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);            // start address, LBO = 1 (unused)
+  uint32_t hi = (sbo & 0x3FFFu) | (1u << 14) | (layout << 29);    // SBO, version = 1, layout type
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB, const UmmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  // 1024-byte aligned operand ring
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                             ~(uintptr_t)1023);
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile decode
+  const int tile = blockIdx.x;
+  const int n_tile = tile % p.tiles_n;
+  int r = tile / p.tiles_n;
+  const int f_blk = r % p.f_tiles;
+  r /= p.f_tiles;
+  const int t_blk = r % p.t_tiles;
+  const int b = r / p.t_tiles;
+  const int t0 = t_blk * p.t_tile, f0 = f_blk * p.fo_tile, n0 = n_tile * p.block_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_smem)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int num_k = p.ntaps * p.chunks_tot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_k; ++it) {
+        const int tap = it / p.chunks_tot;
+        const int ch = it - tap * p.chunks_tot;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+        uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
+        uint8_t* b_dst = a_dst + p.a_bytes;
+        const bool src0 = ch < p.chunks0;
+        const int cc = (src0 ? ch : ch - p.chunks0) * p.block_k;
+        tma_load_5d(a_dst, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.tap_p[tap],
+                    f0 + p.tap_f[tap], t0 + p.tap_t[tap], b);
+        tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * p.block_k, n0, tap);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, K-major both, N, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                             ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      const int ksteps = p.block_k / 16;
+      for (int it = 0; it < num_k; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
+        const uint32_t b_addr = a_addr + p.a_bytes;
+        const uint64_t adesc = make_smem_desc(a_addr, p.sbo, p.layout_type);
+        const uint64_t bdesc = make_smem_desc(b_addr, p.sbo, p.layout_type);
+        for (int k = 0; k < ksteps; ++k) {
+          // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                    (it | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;        // row of the 128-row tile
+    const int t_local = row / p.fo_tile;
+    const int f_local = row - t_local * p.fo_tile;
+    const int t = t0 + t_local, f = f0 + f_local;
+    const bool valid = t < p.To && f < p.Fo;
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int64_t yoff = (int64_t)b * p.y_sB + (int64_t)t * p.y_sT + (int64_t)f * p.y_sF + n0;
+    for (int c = 0; c < p.block_n; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      float o[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+      if (p.bias) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
+      }
+      if (valid) {
+        if (p.y_dtype == CLSKD_BF16) {
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c;
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          reinterpret_cast<uint4*>(yp)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          reinterpret_cast<uint4*>(yp)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+          float* yp = reinterpret_cast<float*>(p.y) + yoff + c;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            reinterpret_cast<float4*>(yp)[e] =
+                make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// dense source check + geometry; returns nullptr if supported, else a reason
+const char* umma_unsupported(const ClskdTapConv* d) {
+  if (d->x_dtype != CLSKD_BF16) return "x must be bf16";
+  const int Ctot = d->c0 + d->c1;
+  if (Ctot % 16 || d->c0 % 16) return "channels must be multiples of 16";
+  if (d->N % 16) return "N must be a multiple of 16";
+  if (d->N > 128 && d->N % 128) return "N > 128 must be a multiple of 128";
+  if (d->sf != 1 && d->sf != 2) return "sf must be 1 or 2";
+  if (!is_pow2(d->Fo) || (d->Fo > 128 && d->Fo % 128)) return "Fo must be a power of two";
+  if (d->accumulate) return "accumulate unsupported";
+  if (d->Fi % d->sf) return "Fi must be a multiple of sf";
+  auto chk = [&](const void* x, int64_t sB, int64_t sT, int64_t sF) -> const char* {
+    if ((uintptr_t)x % 16) return "x not 16-byte aligned";
+    if ((sB * 2) % 16 || (sT * 2) % 16 || (sF * 2) % 16) return "x strides not 16-byte multiples";
+    return nullptr;
+  };
+  if (const char* r = chk(d->x0, d->x0_sB, d->x0_sT, d->x0_sF)) return r;
+  if (d->c1)
+    if (const char* r = chk(d->x1, d->x1_sB, d->x1_sT, d->x1_sF)) return r;
+  if ((uintptr_t)d->w % 16 || (uintptr_t)d->y % 16) return "w/y not 16-byte aligned";
+  int ye = d->y_dtype == CLSKD_BF16 ? 2 : 4;
+  if ((d->y_sB * ye) % 16 || (d->y_sT * ye) % 16 || (d->y_sF * ye) % 16)
+    return "y strides not 16-byte multiples";
+  if (!get_encode()) return "cuTensorMapEncodeTiled unavailable";
+  return nullptr;
+}
+
+int encode_act(EncodeTiledFn enc, CUtensorMap* tm, const void* x, int C, int sf, int Fi, int Ti,
+               int B, int64_t sB, int64_t sT, int64_t sF, int block_k, int fo_tile, int t_tile,
+               CUtensorMapSwizzle sw) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)sf, (cuuint64_t)(Fi / sf), (cuuint64_t)Ti,
+                        (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)sF * 2, (cuuint64_t)sF * 2 * sf, (cuuint64_t)sT * 2,
+                           (cuuint64_t)sB * 2};
+  cuuint32_t box[5] = {(cuuint32_t)block_k, 1, (cuuint32_t)fo_tile, (cuuint32_t)t_tile, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
+
+}  // namespace
+}  // namespace clskd
+
+using namespace clskd;
+
+extern "C" int clskd_has_tcgen05(void) { return 1; }
+
+extern "C" int clskd_tapconv_umma_supported(const ClskdTapConv* d) {
+  if (!d) return 0;
+  return umma_unsupported(d) == nullptr ? 1 : 0;
+}
+
+extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
+  CLSKD_CHECK_ARG(d && d->x0 && d->w && d->y, "clskd_tapconv_fwd_umma: null pointer");
+  CLSKD_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= CLSKD_MAX_TAPS, "clskd_tapconv_fwd_umma: ntaps");
+  if (const char* why = umma_unsupported(d)) {
+    set_error("clskd_tapconv_fwd_umma: unsupported: %s", why);
+    return CLSKD_ERR_UNSUPPORTED;
+  }
+  const int64_t M = (int64_t)d->B * d->To * d->Fo;
+  if (M == 0) return CLSKD_OK;
+  EncodeTiledFn enc = get_encode();
+  const int Ctot = d->c0 + d->c1;
+
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B; p.To = d->To; p.Fo = d->Fo;
+  p.fo_tile = d->Fo < UM ? d->Fo : UM;
+  p.t_tile = UM / p.fo_tile;
+  p.f_tiles = d->Fo / p.fo_tile;
+  p.t_tiles = cdiv(d->To, p.t_tile);
+  p.block_n = d->N <= 128 ? d->N : 128;
+  p.tiles_n = d->N / p.block_n;
+  // largest K chunk that divides both sources
+  int bk = 64;
+  while (bk > 16 && (d->c0 % bk || (d->c1 % bk))) bk >>= 1;
+  p.block_k = bk;
+  p.chunks0 = d->c0 / bk;
+  p.chunks_tot = Ctot / bk;
+  p.ntaps = d->ntaps;
+  for (int j = 0; j < d->ntaps; ++j) {
+    int df = d->df[j];
+    int fl = df >= 0 ? df / d->sf : -((-df + d->sf - 1) / d->sf);  // floor division
+    p.tap_t[j] = d->dt[j];
+    p.tap_f[j] = fl;
+    p.tap_p[j] = df - fl * d->sf;
+  }
+  auto pad1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  p.a_bytes = pad1k((uint32_t)UM * bk * 2);
+  p.b_bytes = pad1k((uint32_t)p.block_n * bk * 2);
+  p.tx_bytes = (uint32_t)UM * bk * 2 + (uint32_t)p.block_n * bk * 2;
+  p.sbo = (uint32_t)(8 * bk * 2) >> 4;
+  CUtensorMapSwizzle sw;
+  if (bk == 64) { p.layout_type = 2; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
+  else if (bk == 32) { p.layout_type = 4; sw = CU_TENSOR_MAP_SWIZZLE_64B; }
+  else { p.layout_type = 6; sw = CU_TENSOR_MAP_SWIZZLE_32B; }
+  int cols = 32;
+  while (cols < p.block_n) cols <<= 1;
+  p.tmem_cols = (uint32_t)cols;
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+  int stages = (int)((100 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  const int num_k = p.ntaps * p.chunks_tot;
+  if (stages > num_k) stages = num_k < 1 ? 1 : num_k;
+  p.stages = stages;
+  p.y = d->y; p.y_sB = d->y_sB; p.y_sT = d->y_sT; p.y_sF = d->y_sF; p.y_dtype = d->y_dtype;
+  p.bias = d->bias; p.N = d->N;
+
+  CUtensorMap tmA0, tmA1, tmB;
+  int rc = encode_act(enc, &tmA0, d->x0, d->c0, d->sf, d->Fi, d->Ti, d->B, d->x0_sB, d->x0_sT,
+                      d->x0_sF, bk, p.fo_tile, p.t_tile, sw);
+  if (rc) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(x0) failed: %d", rc); return CLSKD_ERR_CUDA; }
+  if (d->c1) {
+    rc = encode_act(enc, &tmA1, d->x1, d->c1, d->sf, d->Fi, d->Ti, d->B, d->x1_sB, d->x1_sT,
+                    d->x1_sF, bk, p.fo_tile, p.t_tile, sw);
+    if (rc) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(x1) failed: %d", rc); return CLSKD_ERR_CUDA; }
+  } else {
+    tmA1 = tmA0;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Ctot, (cuuint64_t)d->N, (cuuint64_t)d->ntaps};
+    cuuint64_t strides[2] = {(cuuint64_t)Ctot * 2, (cuuint64_t)Ctot * 2 * d->N};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.block_n, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(w) failed: %d", (int)r); return CLSKD_ERR_CUDA; }
+  }
+  const int64_t tiles = (int64_t)d->B * p.t_tiles * p.f_tiles * p.tiles_n;
+  CLSKD_CHECK_ARG(tiles <= 2147483647LL, "clskd_tapconv_fwd_umma: too many tiles");
+  size_t smem = (size_t)stages * stage_bytes + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapconv_umma_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("clskd_tapconv_fwd_umma: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+    smem_set = smem;
+  }
+  tapconv_umma_kernel<<<(unsigned)tiles, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, p);
+  CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd_umma");
+  return CLSKD_OK;
+}
