@@ -72,6 +72,8 @@ class DistillStep(nn.Module):
     def materialize(self, X):
         """Create the persistent ABF modules (their shapes depend on the feature maps)."""
         if self.mode in ('clskd', 'reviewkd') and not self.fresh_abf and self.abf_encoder is None:
+            if not self.faithful:
+                self.teacher.eval()
             with torch.no_grad():
                 _, t_enc, t_dec, _, _ = _taps(self.teacher, X, False)
                 _, s_enc, s_dec, _, _ = _taps(self.student, X, False)
@@ -163,7 +165,7 @@ class FlatAdam:
         self.m = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
-        self._ptr_host = torch.empty(len(sizes), dtype=torch.int64).pin_memory()
+        self._ptr_host = torch.empty(len(sizes), dtype=torch.int64, pin_memory=dev.type == 'cuda')
         self._ptr_dev = torch.empty(len(sizes), dtype=torch.int64, device=dev)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0

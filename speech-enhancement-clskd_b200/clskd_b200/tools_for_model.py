@@ -36,8 +36,8 @@ def init_kernels(win_len, win_inc, fft_len, win_type=None, invers=False):
     if invers:
         basis = np.linalg.pinv(basis).T
     basis = basis * window
-    return (torch.from_numpy(basis[:, None, :].astype(np.float32)),
-            torch.from_numpy(window[None, :, None].astype(np.float32)))
+    return (torch.from_numpy(np.ascontiguousarray(basis[:, None, :], dtype=np.float32)),
+            torch.from_numpy(np.ascontiguousarray(window[None, :, None], dtype=np.float32)))
 
 
 def _default_fft_len(win_len):

@@ -1,0 +1,155 @@
+"""GPU-only parity tests of the bf16 / tcgen05 policy: the tensor-core implicit GEMM against the
+fp32 CUDA-core kernel and the CPU oracle on identical (bf16-representable) operands, and the full
+model / distillation step against the oracle within the north_star bf16 tolerances
+(enhanced-waveform max-abs error <= 1e-3, loss relative error <= 1e-3)."""
+import pytest
+import torch
+
+from util import full_sd, golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def cuda_dev():
+    import clskd_b200
+    assert torch.cuda.is_available()
+    clskd_b200._lib.load()
+    yield torch.device("cuda:0")
+    clskd_b200.set_precision("fp32")
+
+
+def _round_params(mod):
+    for p in mod.parameters():
+        p.data = p.data.bfloat16().float()
+
+
+@pytest.mark.parametrize("cin,cout,F,T,B", [(32, 64, 64, 37, 3), (64, 128, 16, 130, 2), (256, 256, 8, 65, 2),
+                                            (16, 32, 128, 9, 1)])
+def test_umma_complex_conv_vs_fp32_kernel_and_oracle(cuda_dev, cin, cout, F, T, B):
+    import clskd_b200
+    from clskd_b200 import ops
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(cin + F)
+    conv = tm.ComplexConv2d(cin, cout, kernel_size=(5, 2), stride=(2, 1), padding=(2, 1))
+    conv.real_conv.bias.data.normal_(generator=g)
+    conv.imag_conv.bias.data.normal_(generator=g)
+    _round_params(conv)
+    x = torch.randn(B, cin, F, T, generator=g).bfloat16().float()
+    ref = D.complex_conv2d(x, conv.real_conv.weight, conv.real_conv.bias, conv.imag_conv.weight, conv.imag_conv.bias)
+    conv = conv.to(cuda_dev)
+    xp = x.permute(0, 3, 2, 1).contiguous().to(cuda_dev).bfloat16()        # physical [B,T,F,C]
+    with torch.no_grad():
+        clskd_b200.set_precision("bf16")
+        n0 = ops.umma_launches
+        y_umma = conv.forward_phys(xp, torch.float32)
+        assert ops.umma_launches == n0 + 1, "tcgen05 path was not taken"
+        clskd_b200.set_precision("fp32")
+        y_core = conv.forward_phys(xp, torch.float32)
+    y_umma, y_core = y_umma.permute(0, 3, 2, 1).cpu(), y_core.permute(0, 3, 2, 1).cpu()
+    scale = ref.abs().max().item()
+    assert (y_core - ref).abs().max().item() < 2e-5 * max(scale, 1)
+    assert (y_umma - ref).abs().max().item() < 2e-5 * max(scale, 1)      # same operands, fp32 accumulation
+
+
+@pytest.mark.parametrize("cin,cskip,cout,F,T,B", [(64, 64, 32, 8, 33, 2), (256, 256, 256, 4, 70, 2), (32, 32, 16, 64, 11, 1)])
+def test_umma_complex_deconv_with_skip_vs_oracle(cuda_dev, cin, cskip, cout, F, T, B):
+    import clskd_b200
+    from clskd_b200 import ops
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(cin + F)
+    dec = tm.ComplexConvTranspose2d(cin + cskip, cout, kernel_size=(5, 2), stride=(2, 1), padding=(2, 0),
+                                    output_padding=(1, 0))
+    dec.real_conv.bias.data.normal_(generator=g)
+    _round_params(dec)
+    a = torch.randn(B, cin, F, T, generator=g).bfloat16().float()
+    s = torch.randn(B, cskip, F, T, generator=g).bfloat16().float()
+    ref = D.complex_deconv2d(D.complex_cat([a, s], 1), dec.real_conv.weight, dec.real_conv.bias,
+                             dec.imag_conv.weight, dec.imag_conv.bias)
+    dec = dec.to(cuda_dev)
+    ap = a.permute(0, 3, 2, 1).contiguous().to(cuda_dev).bfloat16()
+    sp = s.permute(0, 3, 2, 1).contiguous().to(cuda_dev).bfloat16()
+    with torch.no_grad():
+        clskd_b200.set_precision("bf16")
+        n0 = ops.umma_launches
+        y = dec.forward_phys(ap, sp, torch.float32)
+        assert ops.umma_launches == n0 + 2, "two sub-pixel tcgen05 launches expected"
+    y = y.permute(0, 3, 2, 1).cpu()
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() < 2e-5 * max(ref.abs().max().item(), 1)
+
+
+def test_umma_bf16_output_and_3x3(cuda_dev):
+    """ABF's 3x3 real conv (9 taps, stride 1) with bf16 output"""
+    import clskd_b200
+    from clskd_b200 import framework as fw
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    conv = fw.RealConv2d(64, 128, 3, padding=1, bias=False)
+    _round_params(conv)
+    x = torch.randn(2, 64, 16, 21, generator=g).bfloat16().float()
+    ref = torch.nn.functional.conv2d(x, conv.weight, padding=1)
+    conv = conv.to(cuda_dev)
+    xp = x.permute(0, 3, 2, 1).contiguous().to(cuda_dev).bfloat16()
+    with torch.no_grad():
+        clskd_b200.set_precision("bf16")
+        n0 = ops.umma_launches
+        y = conv.forward_phys(xp)
+        assert ops.umma_launches == n0 + 1 and y.dtype == torch.bfloat16
+    y = y.float().permute(0, 3, 2, 1).cpu()
+    assert (y - ref).abs().max().item() < 1e-2 * ref.abs().max().item()      # bf16 output rounding (2^-8)
+
+
+@pytest.mark.parametrize("width", ["golden_teacher", "half"])
+def test_bf16_forward_waveform_tolerance(cuda_dev, width):
+    import clskd_b200
+    from clskd_b200 import ops
+    from oracle import dccrn_oracle as D
+    if width == "golden_teacher":
+        g = golden("dccrn.pt")
+        cfg, sd, x = g["teacher_cfg"], full_sd(g["t_sd"]), g["X"]
+    else:
+        cfg = dict(kernel_num=[16, 32, 64, 128, 128, 128], rnn_units=128)
+        sd = D.make_state_dict(cfg["kernel_num"], cfg["rnn_units"], seed=5)
+        x = 0.1 * torch.randn(2, 6000, generator=torch.Generator().manual_seed(1))
+    m = clskd_b200.DCCRN(rnn_units=cfg["rnn_units"], masking_mode="E", use_clstm=True, kernel_num=cfg["kernel_num"])
+    m.load_state_dict(sd)
+    m = m.to(cuda_dev).eval()
+    with torch.no_grad():
+        ref = D.dccrn_forward(sd, x)[-1]
+        clskd_b200.set_precision("bf16")
+        n0 = ops.umma_launches
+        wav = m(x.to(cuda_dev), is_feat=True).float().cpu()
+    assert ops.umma_launches > n0
+    assert (wav - ref).abs().max().item() <= 1e-3
+
+
+def test_bf16_distill_step_loss_tolerance(cuda_dev):
+    import clskd_b200
+    from clskd_b200.distill import DistillStep
+    from oracle import dccrn_oracle as D
+    from oracle import losses_oracle as LO
+    cfg_t = dict(kernel_num=[32, 64, 64, 64, 64, 64], rnn_units=64)
+    cfg_s = dict(kernel_num=[16, 32, 32, 32, 32, 32], rnn_units=32)
+    t_sd = D.make_state_dict(cfg_t["kernel_num"], cfg_t["rnn_units"], seed=1)
+    s_sd = D.make_state_dict(cfg_s["kernel_num"], cfg_s["rnn_units"], seed=2)
+
+    def mk(cfg, sd):
+        m = clskd_b200.DCCRN(rnn_units=cfg["rnn_units"], masking_mode="E", use_clstm=True, kernel_num=cfg["kernel_num"])
+        m.load_state_dict(sd)
+        return m.to(cuda_dev)
+    g = torch.Generator().manual_seed(0)
+    X, y = 0.1 * torch.randn(4, 4000, generator=g), 0.1 * torch.randn(4, 4000, generator=g)
+    ref, terms = LO.clskd_step_loss(t_sd, s_sd, X, y, mode="spkd_all")
+    clskd_b200.set_precision("bf16")
+    student = mk(cfg_s, s_sd)
+    student.train()
+    step = DistillStep(mk(cfg_t, t_sd), student, mode="spkd_all")
+    loss = step(X.to(cuda_dev), y.to(cuda_dev))
+    loss.backward()
+    for k, v in terms.items():
+        assert rel_err(step.last_terms[k].detach(), v.detach()) < 2e-2, k     # per-term (small SPKD terms are noisier)
+    assert rel_err(loss.detach(), ref.detach()) < 1e-3
+    assert all(torch.isfinite(p.grad).all() for p in student.parameters() if p.grad is not None)

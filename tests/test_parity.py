@@ -1,0 +1,387 @@
+"""Parity tests of the product against the reference's golden outputs and the oracle.
+
+Every test runs twice through the `dev` fixture:
+  * `emu`  (CPU, always): the numpy model of the C ABI (tests/cabi_emu.py) stands in for the CUDA
+    kernels, so the host-side logic - convolution plans, packing tables, stride arithmetic, the
+    autograd wiring, the ABF chain, the distillation steps, the flat-bucket optimizer - is checked
+    without a GPU;
+  * `cuda` (`-m gpu`, on a B200): the same assertions against the real sm_100a kernels through
+    the C ABI, fp32 policy (waveform tolerance 1e-5, loss tolerance 1e-3 relative or tighter).
+"""
+import pytest
+import torch
+
+from util import bn_shadowed_bias, check_summary, close, full_sd, golden, rel_err
+
+
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def dev(request, monkeypatch):
+    import clskd_b200
+    clskd_b200.set_precision("fp32")
+    if request.param == "emu":
+        import cabi_emu
+        cabi_emu.install(monkeypatch)
+        return torch.device("cpu")
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    clskd_b200._lib.load()          # raises if the CUDA library is missing: no fallback
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------ model
+def _build(cfg, sd, dev, masking_mode="E"):
+    import clskd_b200
+    m = clskd_b200.DCCRN(rnn_units=cfg["rnn_units"], masking_mode=masking_mode, use_clstm=True,
+                         kernel_num=cfg["kernel_num"])
+    m.load_state_dict(full_sd(sd))
+    return m.to(dev)
+
+
+def test_state_dict_keys_match_reference_layout():
+    import clskd_b200
+    from oracle.dccrn_oracle import make_state_dict
+    kn, ru = [8, 16, 32, 64, 64, 64], 64
+    m = clskd_b200.DCCRN(rnn_units=ru, use_clstm=True, kernel_num=kn)
+    ref = make_state_dict(kn, ru)
+    ours = m.state_dict()
+    assert set(ours) == set(ref)
+    for k in ref:
+        assert tuple(ours[k].shape) == tuple(ref[k].shape), k
+    assert sum(p.numel() for p in m.parameters()) == 231565
+
+
+@pytest.mark.parametrize("name", ["teacher", "student"])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_dccrn_forward_golden(dev, name, mode):
+    import clskd_b200
+    g = golden("dccrn.pt")
+    ref = g["%s_%s" % (name, mode)]
+    m = _build(g[name + "_cfg"], g["t_sd" if name == "teacher" else "s_sd"], dev)
+    m.train(mode == "train")
+    ext = clskd_b200.feature_extraction.DCCRN(m)
+    with torch.no_grad():
+        mr, mi, re, im, wav = m(g["X"].to(dev))
+    ext.remove_hook()
+    assert (wav.cpu() - ref["wav"]).abs().max().item() <= 1e-5          # north_star fp32 tolerance
+    for t, key in ((mr, "mask_real"), (mi, "mask_imag"), (re, "real"), (im, "imag")):
+        check_summary(t, ref[key], what=key)
+    fm = ext.feature_maps
+    for kind in ("encoder", "decoder"):
+        assert [tuple(t.shape) for t in fm[kind]] == ref[kind + "_shapes"]
+        for i, t in enumerate(fm[kind]):
+            check_summary(t, ref[kind][i], what="%s[%d]" % (kind, i))
+    assert [tuple(t.shape) for t in fm["clstm"][0]] == ref["clstm_shapes"]
+    for i, t in enumerate(fm["clstm"][0]):
+        check_summary(t, ref["clstm"][i], what="clstm[%d]" % i)
+    if mode == "train":
+        sd = m.state_dict()
+        for k, v in ref["running"].items():
+            assert torch.allclose(sd[k].cpu(), v, rtol=1e-5, atol=1e-6), k
+    else:
+        y = g["y"].to(dev)
+        for lm in ("SI-SNR", "MSE", "SDR", "SI-SDR"):
+            assert close(m.loss(wav, y, loss_mode=lm), ref["loss"][lm], atol=1e-5 if lm != "MSE" else 1e-9), lm
+
+
+@pytest.mark.parametrize("masking_mode", ["E", "C", "R"])
+def test_dccrn_forward_vs_oracle_all_mask_modes(dev, masking_mode):
+    from oracle import dccrn_oracle as D
+    kn, ru = [4, 8, 8, 16, 16, 16], 16
+    sd = D.make_state_dict(kn, ru, seed=11)
+    m = _build(dict(kernel_num=kn, rnn_units=ru), sd, dev, masking_mode)
+    m.eval()
+    x = 0.1 * torch.randn(3, 3000, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = D.dccrn_forward(sd, x, masking_mode=masking_mode)
+        out = m(x.to(dev))
+        wav_only = m(x.to(dev), is_feat=True)
+    for a, b in zip(out, ref):
+        assert (a.cpu() - b).abs().max().item() < 1e-5
+    assert torch.equal(wav_only, out[-1])
+
+
+def test_empty_and_ragged_inputs(dev):
+    """zero-length batch and lengths that are not a multiple of the hop (T = L//100 + 3 frames)"""
+    from oracle import dccrn_oracle as D
+    kn, ru = [4, 8, 8, 16, 16, 16], 16
+    sd = D.make_state_dict(kn, ru, seed=4)
+    m = _build(dict(kernel_num=kn, rnn_units=ru), sd, dev)
+    m.eval()
+    for L in (1237, 400, 99):
+        x = 0.1 * torch.randn(1, L, generator=torch.Generator().manual_seed(L))
+        with torch.no_grad():
+            ref = D.dccrn_forward(sd, x)[-1]
+            out = m(x.to(dev), is_feat=True)
+        assert out.shape == ref.shape == (1, (L // 100) * 100)
+        assert ref.numel() == 0 or (out.cpu() - ref).abs().max().item() < 1e-5, L
+
+
+def test_public_block_api(dev):
+    """the drop-in modules called through their public (logical NCHW) forward, like the reference's"""
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 6, 16, 9, generator=g)
+    conv = tm.ComplexConv2d(6, 10, kernel_size=(5, 2), stride=(2, 1), padding=(2, 1))
+    conv.real_conv.bias.data.normal_(generator=g)
+    conv.imag_conv.bias.data.normal_(generator=g)
+    ref = D.complex_conv2d(x, conv.real_conv.weight, conv.real_conv.bias, conv.imag_conv.weight, conv.imag_conv.bias)
+    with torch.no_grad():
+        assert torch.allclose(conv.to(dev)(x.to(dev)).cpu(), ref, atol=1e-5)
+    dec = tm.ComplexConvTranspose2d(6, 4, kernel_size=(5, 2), stride=(2, 1), padding=(2, 0), output_padding=(1, 0))
+    dec.real_conv.bias.data.normal_(generator=g)
+    ref = D.complex_deconv2d(x, dec.real_conv.weight, dec.real_conv.bias, dec.imag_conv.weight, dec.imag_conv.bias)
+    with torch.no_grad():
+        assert torch.allclose(dec.to(dev)(x.to(dev)).cpu(), ref, atol=1e-5)
+    a, b = torch.randn(2, 4, 3, 5, generator=g), torch.randn(2, 6, 3, 5, generator=g)
+    assert torch.equal(tm.complex_cat([a, b], 1), D.complex_cat([a, b], 1))
+    stft = tm.ConvSTFT(400, 100, 512, 'hamming', 'complex').to(dev)
+    istft = tm.ConviSTFT(400, 100, 512, 'hamming', 'complex').to(dev)
+    wav = 0.1 * torch.randn(2, 1600, generator=g)
+    spec = stft(wav.to(dev))
+    assert spec.shape == (2, 514, 19)
+    assert torch.allclose(spec.cpu(), D.conv_stft(wav, stft.weight.cpu(), 400, 100), atol=1e-5)
+    rec = istft(spec)
+    assert rec.shape == (2, 1, 1600) and (rec.squeeze(1).cpu() - wav).abs().max() < 1e-5     # round trip
+    bn = tm.BatchNorm2d(6).to(dev)
+    ref_bn = torch.nn.BatchNorm2d(6)
+    with torch.no_grad():
+        assert torch.allclose(bn(x.to(dev)).cpu(), ref_bn(x), atol=1e-5)
+        assert torch.allclose(bn.running_var.cpu(), ref_bn.running_var, atol=1e-6)
+        pr = tm.PReLU().to(dev)
+        assert torch.allclose(pr(x.to(dev)).cpu(), torch.nn.functional.prelu(x, torch.tensor([0.25])), atol=1e-6)
+
+
+def test_conv_block_gradients_vs_autograd(dev):
+    """conv / deconv(+skip) / BN+PReLU backward (dgrad, wgrad, bias, BN, slope) against torch autograd
+    of the oracle"""
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(2)
+    blk = tm.ConvBNAct(tm.ComplexConv2d(8, 12, kernel_size=(5, 2), stride=(2, 1), padding=(2, 1)),
+                       tm.BatchNorm2d(12), tm.PReLU()).to(dev)
+    dblk = tm.ConvBNAct(tm.ComplexConvTranspose2d(24, 6, kernel_size=(5, 2), stride=(2, 1), padding=(2, 0),
+                                                  output_padding=(1, 0)), tm.BatchNorm2d(6), tm.PReLU()).to(dev)
+    for b_ in (blk, dblk):
+        for n, p in b_.named_parameters():
+            if n.endswith("bias") or n.startswith("1."):
+                p.data = (p.data.cpu() + 0.3 * torch.randn(p.shape, generator=g)).to(dev)
+    x = torch.randn(2, 8, 16, 7, generator=g)
+    xd = x.clone().to(dev).requires_grad_(True)
+    h = blk(xd)                                   # [2,12,8,7]
+    y = dblk(h, h)                                # skip = same tensor: [2,6,16,8]
+    w = torch.randn(y.shape, generator=g)
+    (y * w.to(dev)).sum().backward()
+    # oracle
+    sd = {}
+    for pre, b_ in (("e.", blk), ("d.", dblk)):
+        for k, v in b_.state_dict().items():
+            sd[pre + k] = v.detach().cpu().clone().requires_grad_(v.is_floating_point() and "running" not in k)
+    xo = x.clone().requires_grad_(True)
+    ho = D.complex_conv2d(xo, sd["e.0.real_conv.weight"], sd["e.0.real_conv.bias"], sd["e.0.imag_conv.weight"],
+                          sd["e.0.imag_conv.bias"])
+    ho = D._bn_prelu(ho, sd, "e.", True)
+    yo = D.complex_deconv2d(D.complex_cat([ho, ho], 1), sd["d.0.real_conv.weight"], sd["d.0.real_conv.bias"],
+                            sd["d.0.imag_conv.weight"], sd["d.0.imag_conv.bias"])
+    yo = D._bn_prelu(yo, sd, "d.", True)
+    assert torch.allclose(y.detach().cpu(), yo.detach(), atol=2e-5)
+    (yo * w).sum().backward()
+    assert torch.allclose(xd.grad.cpu(), xo.grad, rtol=1e-3, atol=1e-4)
+    for pre, b_ in (("e.", blk), ("d.", dblk)):
+        for n, p in b_.named_parameters():
+            if n.endswith("_conv.bias"):
+                continue                      # shadowed by train-mode BN: zero up to rounding
+            ref = sd[pre + n].grad
+            assert torch.allclose(p.grad.cpu(), ref, rtol=2e-3, atol=2e-4 * ref.abs().max().item() + 1e-6), pre + n
+
+
+def test_complex_lstm(dev):
+    from clskd_b200.clstm import NavieComplexLSTM
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(1)
+    lstm = NavieComplexLSTM(input_size=24, hidden_size=16, projection_dim=24)
+    r, i = torch.randn(7, 3, 12, generator=g), torch.randn(7, 3, 12, generator=g)
+    sd = {"x." + k: v.clone() for k, v in lstm.state_dict().items()}
+    rr, ri = D.complex_lstm(r, i, sd, "x.", True)
+    lstm = lstm.to(dev)
+    rd = r.clone().to(dev).requires_grad_(True)
+    out = lstm([rd, i.to(dev)])
+    assert torch.allclose(out[0].cpu(), rr, atol=1e-5) and torch.allclose(out[1].cpu(), ri, atol=1e-5)
+    # BPTT against torch autograd of the oracle
+    (out[0].sum() + (out[1] ** 2).sum()).backward()
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    r2 = r.detach().clone().requires_grad_(True)
+    o2 = D.complex_lstm(r2, i, params, "x.", True)
+    (o2[0].sum() + (o2[1] ** 2).sum()).backward()
+    assert torch.allclose(rd.grad.cpu(), r2.grad, atol=1e-4)
+    for k, p in lstm.named_parameters():
+        assert torch.allclose(p.grad.cpu(), params["x." + k].grad, rtol=1e-3, atol=1e-4), k
+
+
+# ------------------------------------------------------------------------------------ losses
+def test_losses_golden(dev):
+    from clskd_b200 import framework as fw
+    from clskd_b200 import tools_for_loss as tl
+    L = golden("losses.pt")
+    a, b = L["a"].to(dev), L["b"].to(dev)
+    assert close(tl.si_snr(a, b), L["si_snr"]) and close(tl.sdr(a, b), L["sdr"]) and close(tl.si_sdr(a, b), L["si_sdr"])
+    zs, zt = L["zs"].to(dev), L["zt"].to(dev)
+    assert rel_err(fw.SPKDLoss(zs, zt, "batchmean")(), L["spkd_batchmean"]) < 1e-5
+    assert rel_err(fw.SPKDLoss(zs, zt, "sum")(), L["spkd_sum"]) < 1e-5
+    sx, sy = L["sx"].to(dev), L["sy"].to(dev)
+    sc, mag = fw.STFTLoss(512, 100, 400).to(dev)(sx, sy)
+    assert rel_err(sc, L["stft_512_100_400"][0]) < 1e-5 and rel_err(mag, L["stft_512_100_400"][1]) < 1e-5
+    for key, cfg in (("mrstft_distill", ([512], [100], [400])), ("mrstft_reviewkd", ([512], [16], [32])),
+                     ("mrstft_3res", ([256, 512, 128], [30, 60, 12], [150, 300, 60]))):
+        sc, mag = fw.MultiResolutionSTFTLoss(*cfg).to(dev)(sx, sy)
+        assert rel_err(sc, L[key][0]) < 1e-5 and rel_err(mag, L[key][1]) < 1e-5, key
+    check_summary(fw.stft(sx, 512, 100, 400, torch.hann_window(400).to(dev)), L["stft_mag_512"], what="stft_mag")
+
+
+def test_loss_gradients_vs_autograd(dev):
+    """autograd Functions of the objectives against torch autograd of the oracle"""
+    from clskd_b200 import framework as fw
+    from clskd_b200 import tools_for_loss as tl
+    from oracle import losses_oracle as LO
+    g = torch.Generator().manual_seed(3)
+    a = (0.3 * torch.randn(3, 700, generator=g))
+    b = a + 0.2 * torch.randn(3, 700, generator=g)
+    for ours, ref, wrt in ((tl.si_snr, LO.si_snr, 0), (tl.sdr, LO.sdr, 0), (tl.sdr, LO.sdr, 1), (tl.si_sdr, LO.si_sdr, 1),
+                           (tl.mse, torch.nn.functional.mse_loss, 0)):
+        args1 = [a.clone().to(dev), b.clone().to(dev)]
+        args2 = [a.clone(), b.clone()]
+        args1[wrt].requires_grad_(True)
+        args2[wrt].requires_grad_(True)
+        ours(*args1).backward()
+        ref(*args2).backward()
+        assert torch.allclose(args1[wrt].grad.cpu(), args2[wrt].grad, rtol=1e-3, atol=1e-6), (ours.__name__, wrt)
+    zs = torch.randn(5, 3, 4, 6, generator=g)
+    zt = torch.randn(5, 7, 4, 6, generator=g)
+    z1, z2 = zs.clone().to(dev).requires_grad_(True), zs.clone().requires_grad_(True)
+    fw.SPKDLoss(z1, zt.to(dev), "batchmean")().backward()
+    LO.spkd(z2, zt).backward()
+    assert torch.allclose(z1.grad.cpu(), z2.grad, rtol=1e-3, atol=1e-7)
+    x1, x2 = a.clone().to(dev).requires_grad_(True), a.clone().requires_grad_(True)
+    sc, mag = fw.STFTLoss(128, 30, 100).to(dev)(x1, b.to(dev))
+    (sc + 2 * mag).backward()
+    sc, mag = LO.stft_loss(x2, b, 128, 30, 100)
+    (sc + 2 * mag).backward()
+    assert torch.allclose(x1.grad.cpu(), x2.grad, rtol=1e-3, atol=1e-6)
+
+
+def test_hcl_vs_oracle(dev):
+    from clskd_b200 import framework as fw
+    from oracle import losses_oracle as LO
+    g = torch.Generator().manual_seed(9)
+    fs = [torch.randn(2, 6, 8, 11, generator=g), torch.randn(2, 4, 4, 11, generator=g), torch.randn(2, 4, 2, 5, generator=g)]
+    ft = [torch.randn(f.shape, generator=g) for f in fs]
+    f1 = [f.clone().to(dev).requires_grad_(True) for f in fs]
+    f2 = [f.clone().requires_grad_(True) for f in fs]
+    l1 = fw.hcl(f1, [t.to(dev) for t in ft])
+    l2 = LO.hcl(f2, ft)
+    assert rel_err(l1.detach(), l2.detach()) < 1e-5
+    l1.backward()
+    l2.backward()
+    for a, b in zip(f1, f2):
+        assert torch.allclose(a.grad.cpu(), b.grad, rtol=1e-3, atol=1e-7)
+
+
+def _load_abf(rk, sd):
+    own = rk.state_dict()
+    assert set(own) == set(sd), (sorted(set(own) ^ set(sd)))
+    rk.load_state_dict(sd)
+
+
+def test_review_kd_golden(dev):
+    import clskd_b200
+    from clskd_b200 import framework as fw
+    g, L = golden("dccrn.pt"), golden("losses.pt")
+    m = _build(g["student_cfg"], g["s_sd"], dev)
+    m.train()
+    ext = clskd_b200.feature_extraction.DCCRN(m)
+    X = g["X"].to(dev)
+    with torch.no_grad():
+        m(X)
+    ext.remove_hook()
+    s_enc, s_dec = ext.feature_maps["encoder"], ext.feature_maps["decoder"]
+    rk_enc = fw.build_review_kd(s_enc, "encoder", out_channels=g["teacher_cfg"]["kernel_num"])
+    rk_dec = fw.build_review_kd(s_dec, "decoder", out_channels=[64, 64, 32, 16, 8, 2][::-1])
+    _load_abf(rk_enc, L["abf_enc_sd"])
+    _load_abf(rk_dec, L["abf_dec_sd"])
+    with torch.no_grad():
+        f_enc, f_dec = rk_enc(X), rk_dec(X)
+    assert [tuple(t.shape) for t in f_enc] == L["abf_enc_shapes"]
+    assert [tuple(t.shape) for t in f_dec] == L["abf_dec_shapes"]
+    for i, t in enumerate(f_enc):
+        check_summary(t, L["abf_enc_out"][i], what="abf_enc[%d]" % i)
+    for i, t in enumerate(f_dec):
+        check_summary(t, L["abf_dec_out"][i], what="abf_dec[%d]" % i)
+
+
+# ------------------------------------------------------------------------------------ steps
+@pytest.mark.parametrize("mode", ["clskd", "spkd_all", "spkd", "mse", "stft"])
+def test_distill_step_golden(dev, mode):
+    from clskd_b200.distill import DistillStep
+    g, L, S = golden("dccrn.pt"), golden("losses.pt"), golden("step.pt")
+    ref = S[mode]
+    teacher = _build(g["teacher_cfg"], g["t_sd"], dev)
+    student = _build(g["student_cfg"], g["s_sd"], dev)
+    student.train()
+    X, y = g["X"].to(dev), g["y"].to(dev)
+    step = DistillStep(teacher, student, mode=mode)
+    if mode == "clskd":
+        step.materialize(X)
+        student.load_state_dict(full_sd(g["s_sd"]))      # materialize ran a train-mode forward
+        _load_abf(step.abf_encoder, L["abf_enc_sd"])
+        _load_abf(step.abf_decoder, L["abf_dec_sd"])
+    loss = step(X, y)
+    assert rel_err(loss.detach(), ref["loss"]) < 1e-4             # north_star: loss rel. error <= 1e-3
+    for k, v in ref["terms"].items():
+        assert rel_err(step.last_terms[k].detach(), v) < 1e-4, k
+    loss.backward()
+    params = dict(student.named_parameters())
+    for name, gref in ref["grads"].items():
+        if bn_shadowed_bias(name):
+            continue
+        assert params[name].grad is not None, name
+        check_summary(params[name].grad, gref, rtol=2e-3, atol=1e-7, what="grad " + name)
+    if mode == "clskd":
+        for key, rk in (("abf_enc_grads", step.abf_encoder), ("abf_dec_grads", step.abf_decoder)):
+            ps = dict(rk.named_parameters())
+            for name, gref in ref[key].items():
+                check_summary(ps[name].grad, gref, rtol=2e-3, atol=1e-7, what=key + " " + name)
+
+
+def test_flat_adam_matches_torch_adam(dev):
+    from clskd_b200.distill import FlatAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(5, 3), (7,), (2, 2)]
+    ps = [torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().cpu().clone()) for p in ps]
+    ours = FlatAdam(ps, lr=6e-4, weight_decay=5e-4)
+    ref = torch.optim.Adam(qs, lr=6e-4, weight_decay=5e-4)
+    for it in range(3):
+        for p, q in zip(ps, qs):
+            gr = torch.randn(p.shape, generator=g)
+            p.grad, q.grad = gr.clone().to(dev), gr.clone()
+        if it == 1:                                     # a parameter without a gradient packs as zeros
+            ps[2].grad = None
+            qs[2].grad = torch.zeros_like(qs[2])
+        ours.pack_grads()
+        ours.step()
+        ref.step()
+        for p, q in zip(ps, qs):
+            assert torch.allclose(p.detach().cpu(), q.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_trainer_step_decreases_loss(dev):
+    """three optimizer steps of the SPKD-all recipe on a fixed batch"""
+    from clskd_b200.distill import DistillTrainer
+    from oracle import dccrn_oracle as D
+    cfg_t, cfg_s = dict(kernel_num=[4, 8, 8, 16, 16, 16], rnn_units=16), dict(kernel_num=[2, 4, 4, 8, 8, 8], rnn_units=8)
+    teacher = _build(cfg_t, D.make_state_dict(cfg_t["kernel_num"], cfg_t["rnn_units"], seed=1), dev)
+    student = _build(cfg_s, D.make_state_dict(cfg_s["kernel_num"], cfg_s["rnn_units"], seed=2), dev)
+    g = torch.Generator().manual_seed(0)
+    X, y = (0.1 * torch.randn(2, 2000, generator=g)).to(dev), (0.1 * torch.randn(2, 2000, generator=g)).to(dev)
+    tr = DistillTrainer(teacher, student, mode="spkd_all", lr=1e-3)
+    losses = [float(tr.train_step(X, y)) for _ in range(4)]
+    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
