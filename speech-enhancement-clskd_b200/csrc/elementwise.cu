@@ -1093,11 +1093,12 @@ extern "C" int clskd_mask_bwd(const float* spec, const void* mask, int mask_dtyp
 
 extern "C" int clskd_ola_fwd(const float* frames, const float* window, int B, int T, int win,
                              int hop, int trim, int do_clamp, float* wav, void* stream) {
-  CLSKD_CHECK_ARG(frames && wav, "clskd_ola_fwd: null pointer");
   CLSKD_CHECK_ARG(win >= hop && hop > 0 && T >= 1 && trim >= 0, "clskd_ola_fwd: bad geometry");
   int L = (T - 1) * hop + win - 2 * trim;
-  CLSKD_CHECK_ARG(L > 0, "clskd_ola_fwd: too few frames");
+  CLSKD_CHECK_ARG(L >= 0, "clskd_ola_fwd: too few frames");
   int64_t total = (int64_t)B * L;
+  if (total == 0) return CLSKD_OK;  // an input shorter than one hop yields an empty waveform
+  CLSKD_CHECK_ARG(frames && wav, "clskd_ola_fwd: null pointer");
   ola_fwd_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(frames, window, B, T, win, hop, trim, do_clamp,
                                                       wav);
   CLSKD_CHECK_LAUNCH("clskd_ola_fwd");
