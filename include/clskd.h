@@ -90,6 +90,11 @@ int clskd_tapconv_umma_supported(const ClskdTapConv* d);
  * `d->y` is dY (read), `d->w` is dW (written, fp32 [ntaps][c0+c1][N]).  dW is zeroed by the call
  * unless d->accumulate. */
 int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream);
+/* the same weight gradient on the tcgen05 tensor cores (bf16 x and dY, fp32 dW, split-K over CTAs
+ * with fp32 reductions): requires c0%16==0, c1%16==0, N%16==0, power-of-two Fo, 16-byte aligned
+ * tensors/strides (see clskd_tapconv_wgrad_umma_supported). */
+int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream);
+int clskd_tapconv_wgrad_umma_supported(const ClskdTapConv* d);
 
 /* ------------------------------------------------------------------------------------------
  * Layout / packing helpers
@@ -230,6 +235,14 @@ int clskd_stftmag_loss_bwd(const float* xs, const float* ys, int64_t n, const do
 /* G[B,B] (fp32) = Z Z^T (+= when accumulate); Z is [B, K] with row stride ldz (elements). */
 int clskd_gram_fwd(const void* z, int dtype, int B, int64_t K, int64_t ldz, float* G,
                    int accumulate, void* stream);
+/* the same Gram product / gradient on the tcgen05 tensor cores (bf16 z, B <= 128, 16-byte aligned
+ * rows, K >= 4096): each feature element is read from HBM once, partial Grams stay in TMEM.
+ * clskd_gram_bwd_umma always overwrites dz. */
+int clskd_gram_umma_supported(const void* z, int dtype, int B, int64_t K, int64_t ldz);
+int clskd_gram_fwd_umma(const void* z, int dtype, int B, int64_t K, int64_t ldz, float* G,
+                        int accumulate, void* stream);
+int clskd_gram_bwd_umma(const void* z, int dtype, int B, int64_t K, int64_t ldz, const float* dG,
+                        const float* gout, void* dz, int dz_dtype, int64_t lddz, void* stream);
 /* loss (fp32 scalar) = || rownorm1(Gt) - rownorm1(Gs) ||_F^2 * scale; also dGs = dloss/dGs (fp32
  * [B,B], may be NULL) for a unit upstream gradient. */
 int clskd_spkd_loss(const float* Gt, const float* Gs, int B, float scale, float* loss, float* dGs,

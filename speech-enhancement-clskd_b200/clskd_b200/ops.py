@@ -421,7 +421,13 @@ def run_wgrad(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, dy, dw_out, x0_view=
     d = TapConv()
     _fill_desc(d, x0, x0_off, x0_str, x1, x1_off, x1_str, c0, c1, B, To, Fo, Ti, Fi, l, dw_out, None,
                l.N, dy, y_off, y_str, False)
-    call("clskd_tapconv_wgrad", ctypes.byref(d), _stream())
+    global umma_launches, core_launches
+    if policy.use_umma and _lib.load().clskd_tapconv_wgrad_umma_supported(ctypes.byref(d)):
+        call("clskd_tapconv_wgrad_umma", ctypes.byref(d), _stream())
+        umma_launches += 1
+    else:
+        call("clskd_tapconv_wgrad", ctypes.byref(d), _stream())
+        core_launches += 1
 
 
 def _chan_ok(t):
@@ -791,8 +797,22 @@ def gram(z2d: torch.Tensor) -> torch.Tensor:
     """G = Z Z^T (fp32 [B,B]) of a dense [B, K] matrix."""
     B, K = z2d.shape
     G = torch.empty(B, B, dtype=torch.float32, device=z2d.device)
-    call("clskd_gram_fwd", z2d.data_ptr(), _tag(z2d.dtype), B, K, z2d.stride(0), G.data_ptr(), 0, _stream())
+    if _gram_umma_ok(z2d):
+        call("clskd_gram_fwd_umma", z2d.data_ptr(), _tag(z2d.dtype), B, K, z2d.stride(0), G.data_ptr(), 0, _stream())
+    else:
+        call("clskd_gram_fwd", z2d.data_ptr(), _tag(z2d.dtype), B, K, z2d.stride(0), G.data_ptr(), 0, _stream())
     return G
+
+
+def _gram_umma_ok(z2d):
+    global umma_launches, core_launches
+    ok = policy.use_umma and z2d.dtype == torch.bfloat16 and bool(_lib.load().clskd_gram_umma_supported(
+        z2d.data_ptr(), _tag(z2d.dtype), z2d.shape[0], z2d.shape[1], z2d.stride(0)))
+    if ok:
+        umma_launches += 1
+    else:
+        core_launches += 1
+    return ok
 
 
 class SPKDFn(torch.autograd.Function):
@@ -822,8 +842,12 @@ class SPKDFn(torch.autograd.Function):
         B, K = zs2.shape
         g = dense(g, torch.float32)
         dz = torch.empty_like(zs2)
-        call("clskd_gram_bwd", zs2.data_ptr(), _tag(zs2.dtype), B, K, zs2.stride(0), dGs.data_ptr(),
-             g.data_ptr(), dz.data_ptr(), _tag(dz.dtype), dz.stride(0), 0, _stream())
+        if _gram_umma_ok(zs2):
+            call("clskd_gram_bwd_umma", zs2.data_ptr(), _tag(zs2.dtype), B, K, zs2.stride(0), dGs.data_ptr(),
+                 g.data_ptr(), dz.data_ptr(), _tag(dz.dtype), dz.stride(0), _stream())
+        else:
+            call("clskd_gram_bwd", zs2.data_ptr(), _tag(zs2.dtype), B, K, zs2.stride(0), dGs.data_ptr(),
+                 g.data_ptr(), dz.data_ptr(), _tag(dz.dtype), dz.stride(0), 0, _stream())
         return dz.view(ctx.shape), None, None
 
 

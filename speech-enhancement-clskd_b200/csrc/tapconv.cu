@@ -277,6 +277,206 @@ __global__ void __launch_bounds__(NT) tapconv_wgrad_kernel(ClskdTapConv d, int64
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// N <= 2 outputs per row (the mask-producing last decoder layer, ABF's 2-logit attention conv and
+// the data gradient of a 2-channel input): a GEMV per row, HBM-bound.  A warp reads a row's
+// K = ntaps*Ctot inputs with 16-byte loads (lane -> fixed 8-channel unit, so the lane's weights
+// live in registers), reduces with shuffles and writes the N outputs.  Rows whose K fits 16 lanes
+// or fewer share a warp.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8(const float* p, float* o) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* o) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    o[2 * i] = f.x;
+    o[2 * i + 1] = f.y;
+  }
+}
+
+struct N2Geom {
+  int U;      // 8-channel units per row = ntaps * Ctot / 8
+  int cpt;    // units per tap = Ctot / 8
+  int up2;    // lanes cooperating on one row (power of two, <= 32)
+};
+
+template <typename TX, int UPL>
+struct N2Units {
+  int tap[UPL];
+  int dt[UPL], df[UPL];
+  int64_t coff[UPL];   // channel offset inside the source
+  bool src1[UPL], ok[UPL];
+  __device__ __forceinline__ void init(const ClskdTapConv& d, const N2Geom& g, int ul) {
+#pragma unroll
+    for (int i = 0; i < UPL; ++i) {
+      int u = ul + i * g.up2;
+      ok[i] = u < g.U;
+      int uu = ok[i] ? u : 0;
+      tap[i] = uu / g.cpt;
+      int c = (uu - tap[i] * g.cpt) * 8;
+      src1[i] = c >= d.c0;
+      coff[i] = src1[i] ? c - d.c0 : c;
+      dt[i] = d.dt[tap[i]];
+      df[i] = d.df[tap[i]];
+    }
+  }
+  // loads the unit's 8 inputs for output row (b,t,f); returns false (zeros) when out of range
+  __device__ __forceinline__ bool load(const ClskdTapConv& d, int i, int b, int t, int f, float* x) const {
+    int ti = t + dt[i], fi = f * d.sf + df[i];
+    if (!ok[i] || ti < 0 || ti >= d.Ti || fi < 0 || fi >= d.Fi) return false;
+    if (src1[i])
+      ld8(reinterpret_cast<const TX*>(d.x1) + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF + coff[i], x);
+    else
+      ld8(reinterpret_cast<const TX*>(d.x0) + (int64_t)b * d.x0_sB + (int64_t)ti * d.x0_sT + (int64_t)fi * d.x0_sF + coff[i], x);
+    return true;
+  }
+};
+
+template <typename TX, typename TY, int UPL>
+__global__ void __launch_bounds__(256) tapconv_fwd_n2_kernel(ClskdTapConv d, N2Geom g) {
+  const int lane = threadIdx.x & 31;
+  const int ul = lane & (g.up2 - 1), sub = lane / g.up2, rpw = 32 / g.up2;
+  const int Ctot = d.c0 + d.c1;
+  const float* w = reinterpret_cast<const float*>(d.w);
+  N2Units<TX, UPL> un;
+  un.init(d, g, ul);
+  float wr[UPL][8][2];
+#pragma unroll
+  for (int i = 0; i < UPL; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        int64_t k = (int64_t)un.tap[i] * Ctot + (un.src1[i] ? d.c0 : 0) + un.coff[i] + e;
+        wr[i][e][n] = (un.ok[i] && n < d.N) ? w[k * d.N + n] : 0.f;
+      }
+  const float b0 = d.bias ? d.bias[0] : 0.f;
+  const float b1 = (d.bias && d.N > 1) ? d.bias[1] : 0.f;
+  const int64_t M = (int64_t)d.B * d.To * d.Fo;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  TY* y = reinterpret_cast<TY*>(d.y);
+  for (int64_t m0 = warp0 * rpw; m0 < M; m0 += nwarps * rpw) {
+    const int64_t m = m0 + sub;
+    const bool live = m < M;
+    const int64_t mm = live ? m : 0;
+    const int f = (int)(mm % d.Fo);
+    const int64_t r = mm / d.Fo;
+    const int t = (int)(r % d.To), b = (int)(r / d.To);
+    float a0 = 0.f, a1 = 0.f;
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < UPL; ++i) {
+        float x[8];
+        if (un.load(d, i, b, t, f, x)) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            a0 = fmaf(x[e], wr[i][e][0], a0);
+            a1 = fmaf(x[e], wr[i][e][1], a1);
+          }
+        }
+      }
+    }
+    for (int o = g.up2 >> 1; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (live && ul == 0) {
+      TY* yp = y + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF;
+      float v0 = a0 + b0, v1 = a1 + b1;
+      if (d.accumulate) {
+        v0 += ld_f(yp);
+        if (d.N > 1) v1 += ld_f(yp + 1);
+      }
+      st_f(yp, v0);
+      if (d.N > 1) st_f(yp + 1, v1);
+    }
+  }
+}
+
+// dW[k][n] for N <= 2: every lane accumulates its own 8-channel units over the rows its warp
+// visits (no cross-lane traffic in the loop), then shared-memory and global fp32 reductions.
+template <typename TX, typename TY, int UPL>
+__global__ void __launch_bounds__(256) tapconv_wgrad_n2_kernel(ClskdTapConv d, N2Geom g) {
+  extern __shared__ float red[];   // [U*8*2]
+  const int lane = threadIdx.x & 31;
+  const int ul = lane & (g.up2 - 1), sub = lane / g.up2, rpw = 32 / g.up2;
+  const int Ctot = d.c0 + d.c1;
+  N2Units<TX, UPL> un;
+  un.init(d, g, ul);
+  float acc[UPL][8][2];
+#pragma unroll
+  for (int i = 0; i < UPL; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e][0] = acc[i][e][1] = 0.f;
+  for (int i = threadIdx.x; i < g.U * 16; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int64_t M = (int64_t)d.B * d.To * d.Fo;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const TY* dy = reinterpret_cast<const TY*>(d.y);
+  for (int64_t m0 = warp0 * rpw; m0 < M; m0 += nwarps * rpw) {
+    const int64_t m = m0 + sub;
+    if (m >= M) continue;
+    const int f = (int)(m % d.Fo);
+    const int64_t r = m / d.Fo;
+    const int t = (int)(r % d.To), b = (int)(r / d.To);
+    const TY* yp = dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF;
+    const float g0 = ld_f(yp), g1 = d.N > 1 ? ld_f(yp + 1) : 0.f;
+#pragma unroll
+    for (int i = 0; i < UPL; ++i) {
+      float x[8];
+      if (un.load(d, i, b, t, f, x)) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc[i][e][0] = fmaf(x[e], g0, acc[i][e][0]);
+          acc[i][e][1] = fmaf(x[e], g1, acc[i][e][1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < UPL; ++i) {
+    if (!un.ok[i]) continue;
+    int u = ul + i * g.up2;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&red[(u * 8 + e) * 2], acc[i][e][0]);
+      atomicAdd(&red[(u * 8 + e) * 2 + 1], acc[i][e][1]);
+    }
+  }
+  __syncthreads();
+  float* dw = reinterpret_cast<float*>(const_cast<void*>(d.w));
+  for (int i = threadIdx.x; i < g.U * 16; i += blockDim.x) {
+    int n = i & 1, ke = i >> 1;             // ke = u*8+e = tap*Ctot + c (units are laid out in k order)
+    if (n < d.N) atomicAdd(dw + (int64_t)ke * d.N + n, red[i]);
+  }
+}
+
+bool n2_ok(const ClskdTapConv* d, N2Geom* g) {
+  const int Ctot = d->c0 + d->c1;
+  if (d->N > 2 || Ctot % 8 || d->c0 % 8) return false;
+  const int xe = d->x_dtype == CLSKD_F32 ? 4 : 2;
+  auto al = [&](const void* p, int64_t a, int64_t b, int64_t c) {
+    return ((uintptr_t)p % 16 == 0) && (a * xe) % 16 == 0 && (b * xe) % 16 == 0 && (c * xe) % 16 == 0;
+  };
+  if (!al(d->x0, d->x0_sB, d->x0_sT, d->x0_sF)) return false;
+  if (d->c1 && !al(d->x1, d->x1_sB, d->x1_sT, d->x1_sF)) return false;
+  g->cpt = Ctot / 8;
+  g->U = d->ntaps * g->cpt;
+  if (g->U > 128) return false;
+  int up2 = 1;
+  while (up2 < g->U && up2 < 32) up2 <<= 1;
+  g->up2 = up2;
+  return true;
+}
+
 int check_desc(const ClskdTapConv* d, const char* who) {
   CLSKD_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
   CLSKD_CHECK_ARG(d->x0 && d->w && d->y, "%s: null tensor pointer", who);
@@ -318,8 +518,29 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
                   "clskd_tapconv_fwd: accumulate needs fp32 output");
   int64_t M = (int64_t)d->B * d->To * d->Fo;
   if (M == 0) return CLSKD_OK;
-  dim3 grid(cdiv(M, BM), cdiv(d->N, BN));
   cudaStream_t st = (cudaStream_t)stream;
+  N2Geom g2;
+  if (n2_ok(d, &g2)) {
+    const int upl = cdiv(g2.U, g2.up2);   // 1, 2, 3 or 4 units per lane
+    const int64_t warps_needed = (M + (32 / g2.up2) - 1) / (32 / g2.up2);
+    int64_t blocks = (warps_needed + 7) / 8 / 4;
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    if (blocks < 1) blocks = 1;
+#define LAUNCH_N2(TX, TY)                                                                       \
+  do {                                                                                          \
+    if (upl <= 1) tapconv_fwd_n2_kernel<TX, TY, 1><<<(unsigned)blocks, 256, 0, st>>>(*d, g2);   \
+    else if (upl == 2) tapconv_fwd_n2_kernel<TX, TY, 2><<<(unsigned)blocks, 256, 0, st>>>(*d, g2); \
+    else tapconv_fwd_n2_kernel<TX, TY, 4><<<(unsigned)blocks, 256, 0, st>>>(*d, g2);            \
+  } while (0)
+    if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32) LAUNCH_N2(float, float);
+    else if (d->x_dtype == CLSKD_F32) LAUNCH_N2(float, __nv_bfloat16);
+    else if (d->y_dtype == CLSKD_F32) LAUNCH_N2(__nv_bfloat16, float);
+    else LAUNCH_N2(__nv_bfloat16, __nv_bfloat16);
+#undef LAUNCH_N2
+    CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(n2)");
+    return CLSKD_OK;
+  }
+  dim3 grid(cdiv(M, BM), cdiv(d->N, BN));
   bool vec = vec_ok(d);
 #define LAUNCH(TX, TY)                                                        \
   do {                                                                        \
@@ -349,6 +570,25 @@ extern "C" int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream) {
     }
   }
   if (M == 0) return CLSKD_OK;
+  N2Geom g2;
+  if (n2_ok(d, &g2) && M >= 1024) {
+    const int upl = cdiv(g2.U, g2.up2);
+    int blocks = sm_count() * 4;
+    const size_t sh = sizeof(float) * (size_t)g2.U * 16;
+#define LAUNCH_W2(TX, TY)                                                                         \
+  do {                                                                                            \
+    if (upl <= 1) tapconv_wgrad_n2_kernel<TX, TY, 1><<<blocks, 256, sh, st>>>(*d, g2);            \
+    else if (upl == 2) tapconv_wgrad_n2_kernel<TX, TY, 2><<<blocks, 256, sh, st>>>(*d, g2);       \
+    else tapconv_wgrad_n2_kernel<TX, TY, 4><<<blocks, 256, sh, st>>>(*d, g2);                     \
+  } while (0)
+    if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32) LAUNCH_W2(float, float);
+    else if (d->x_dtype == CLSKD_F32) LAUNCH_W2(float, __nv_bfloat16);
+    else if (d->y_dtype == CLSKD_F32) LAUNCH_W2(__nv_bfloat16, float);
+    else LAUNCH_W2(__nv_bfloat16, __nv_bfloat16);
+#undef LAUNCH_W2
+    CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad(n2)");
+    return CLSKD_OK;
+  }
   int tiles = cdiv(Ktot, BM) * cdiv(d->N, BN);
   int target = sm_count() * 6;
   int splits = target / tiles;

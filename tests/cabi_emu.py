@@ -65,6 +65,21 @@ class EmuLib:
     def clskd_tapconv_umma_supported(self, d):
         return 0
 
+    def clskd_tapconv_wgrad_umma_supported(self, d):
+        return 0
+
+    def clskd_gram_umma_supported(self, z, dt, B, K, ldz):
+        return 0
+
+    def clskd_gram_fwd_umma(self, *a):
+        raise RuntimeError("cabi_emu: the tcgen05 path has no CPU model")
+
+    def clskd_gram_bwd_umma(self, *a):
+        raise RuntimeError("cabi_emu: the tcgen05 path has no CPU model")
+
+    def clskd_tapconv_wgrad_umma(self, dref, stream):
+        raise RuntimeError("cabi_emu: the tcgen05 path has no CPU model")
+
     # ------------------------------------------------------------------ tapconv
     @staticmethod
     def _desc(dref):

@@ -153,3 +153,87 @@ def test_bf16_distill_step_loss_tolerance(cuda_dev):
         assert rel_err(step.last_terms[k].detach(), v.detach()) < 2e-2, k     # per-term (small SPKD terms are noisier)
     assert rel_err(loss.detach(), ref.detach()) < 1e-3
     assert all(torch.isfinite(p.grad).all() for p in student.parameters() if p.grad is not None)
+
+
+def _wgrad_both_policies(cuda_dev, mod, inputs, ops):
+    """weight gradients of `mod.forward_phys(*inputs)` under the bf16 (tcgen05) and fp32 (CUDA-core)
+    policies for the same bf16-representable operands and upstream gradient"""
+    import clskd_b200
+    g = torch.Generator().manual_seed(7)
+    res = {}
+    up = None
+    for pol in ("bf16", "fp32"):
+        clskd_b200.set_precision(pol)
+        mod.zero_grad()
+        n0 = ops.umma_launches
+        y = mod.forward_phys(*inputs)
+        if up is None:
+            up = torch.randn(y.shape, generator=g).bfloat16().float().to(cuda_dev)
+        (y.float() * up).sum().backward()
+        res[pol] = ({k: p.grad.detach().clone() for k, p in mod.named_parameters() if p.grad is not None},
+                    ops.umma_launches - n0)
+    return res
+
+
+@pytest.mark.parametrize("case", ["conv_64_128", "conv_32_64", "conv_16_32", "deconv_skip_128", "deconv_skip_64",
+                                  "abf3x3_128_256", "abf3x3_128_32", "abf1x1_32_128"])
+def test_umma_wgrad_vs_cuda_core(cuda_dev, case):
+    from clskd_b200 import framework as fw
+    from clskd_b200 import ops
+    from clskd_b200 import tools_for_model as tm
+    g = torch.Generator().manual_seed(len(case))
+
+    def act(B, T, F, C):
+        return torch.randn(B, T, F, C, generator=g).bfloat16().to(cuda_dev)
+    if case.startswith("conv_"):
+        cin, cout = (int(v) for v in case.split("_")[1:])
+        mod = tm.ComplexConv2d(cin, cout, kernel_size=(5, 2), stride=(2, 1), padding=(2, 1))
+        inputs = (act(3, 37, 32, cin),)
+    elif case.startswith("deconv_skip_"):
+        c = int(case.split("_")[2])
+        mod = tm.ComplexConvTranspose2d(2 * c, c // 2, kernel_size=(5, 2), stride=(2, 1), padding=(2, 0),
+                                        output_padding=(1, 0))
+        inputs = (act(2, 33, 16, c), act(2, 33, 16, c))
+    elif case.startswith("abf3x3_"):
+        cin, cout = (int(v) for v in case.split("_")[1:])
+        mod = fw.RealConv2d(cin, cout, 3, padding=1, bias=False)
+        inputs = (act(2, 41, 32, cin),)
+    else:
+        cin, cout = (int(v) for v in case.split("_")[1:])
+        mod = fw.RealConv2d(cin, cout, 1, bias=False)
+        inputs = (act(2, 41, 64, cin),)
+    _round_params(mod)
+    mod = mod.to(cuda_dev)
+    res = _wgrad_both_policies(cuda_dev, mod, inputs, ops)
+    assert res["bf16"][1] >= 2 and res["fp32"][1] == 0, "tcgen05 forward + wgrad launches expected"
+    for k, gref in res["fp32"][0].items():
+        gu = res["bf16"][0][k]
+        scale = gref.abs().max().item()
+        assert (gu - gref).abs().max().item() < 1e-4 * max(scale, 1.0), (case, k)
+
+
+@pytest.mark.parametrize("B,K", [(64, 128 * 643), (5, 40008), (128, 8192 + 64), (16, 4096)])
+def test_umma_gram_fwd_bwd_vs_torch(cuda_dev, B, K):
+    import clskd_b200
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(B)
+    z = torch.randn(B, K, generator=g).bfloat16()
+    zt = torch.randn(B, K // 2, generator=g).bfloat16()
+    zd = z.to(cuda_dev).requires_grad_(True)
+    clskd_b200.set_precision("bf16")
+    n0 = ops.umma_launches
+    G = ops.gram(zd.detach())
+    assert ops.umma_launches == n0 + 1, "tcgen05 Gram path was not taken"
+    ref = z.double() @ z.double().t()
+    assert (G.cpu().double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+    # SPKD loss + gradient through the tensor-core Gram / Gram-gradient kernels vs torch autograd (fp64)
+    from oracle import losses_oracle as LO
+    loss = ops.SPKDFn.apply(zd, zt.to(cuda_dev), 1.0 / (B * B))
+    loss.backward()
+    z64 = z.double().requires_grad_(True)
+    lref = LO.spkd(z64, zt.double())
+    lref.backward()
+    assert abs(float(loss) - float(lref)) < 1e-4 * abs(float(lref))
+    gref = z64.grad
+    err = (zd.grad.float().cpu().double() - gref).abs().max().item()
+    assert err < 1.5e-2 * gref.abs().max().item(), err          # dz is rounded to bf16 (2^-8 relative)
