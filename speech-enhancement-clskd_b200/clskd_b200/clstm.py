@@ -56,6 +56,7 @@ class _ClstmPlans:
         gg, kk = np.meshgrid(np.arange(G), np.arange(H), indexing="ij")
         t[:, 0] = ((kk * G + gg) * 2).reshape(-1)
         self.hh_unpack = torch.from_numpy(t).to(device)
+        self.cache = {}
 
 
 class ComplexLSTMLayerFn(torch.autograd.Function):
@@ -71,16 +72,22 @@ class ComplexLSTMLayerFn(torch.autograd.Function):
         wr_ih, wr_hh, br_ih, br_hh = f(wr_ih), f(wr_hh), f(br_ih), f(br_hh)
         wi_ih, wi_hh, bi_ih, bi_hh = f(wi_ih), f(wi_hh), f(bi_ih), f(bi_hh)
         # biases of both sets -> [8H]
-        bias8 = torch.empty(2 * G, dtype=torch.float32, device=dev)
-        call("clskd_pack_gather", br_ih.data_ptr(), br_hh.data_ptr(), plans.bias.data_ptr(), G,
-             bias8.data_ptr(), 0, st)
-        call("clskd_pack_gather", bi_ih.data_ptr(), bi_hh.data_ptr(), plans.bias.data_ptr(), G,
-             bias8.data_ptr() + 4 * G, 0, st)
+        bkey = (ops._wkey(br_ih, br_hh), ops._wkey(bi_ih, bi_hh))
+        ent = plans.cache.get("bias8")
+        if ent is not None and ent[0] == bkey:
+            bias8 = ent[1]
+        else:
+            bias8 = torch.empty(2 * G, dtype=torch.float32, device=dev)
+            call("clskd_pack_gather", br_ih.data_ptr(), br_hh.data_ptr(), plans.bias.data_ptr(), G,
+                 bias8.data_ptr(), 0, st)
+            call("clskd_pack_gather", bi_ih.data_ptr(), bi_hh.data_ptr(), plans.bias.data_ptr(), G,
+                 bias8.data_ptr() + 4 * G, 0, st)
+            plans.cache["bias8"] = (bkey, bias8)
         # input projections for both sets: rows (p,t,b) -> pre [2, T, B, 8H]
         pre = torch.empty((P, T, B, 2 * G), dtype=torch.float32, device=dev)
         run_tapconv(X.view(1, P * T, B, D), None, D, 0, 1, P * T, B, P * T, B, plans.ih.fwd[0], wr_ih, wi_ih,
                     bias8, pre.view(1, P * T, B, 2 * G))
-        whh_t = pack_weights(plans.whh_t, wr_hh, wi_hh, torch.float32)
+        whh_t = ops.packed_weights(plans.cache, "whh_t", lambda: plans.whh_t, wr_hh, wi_hh, torch.float32)
         train = any(ctx.needs_input_grad)   # False under torch.no_grad()
         h = torch.empty((2, P, T, B, H), dtype=torch.float32, device=dev)
         gates = torch.empty((2, P, T, B, G), dtype=torch.float32, device=dev) if train else None

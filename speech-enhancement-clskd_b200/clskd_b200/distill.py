@@ -192,6 +192,7 @@ class FlatAdam:
         call("clskd_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
              self.v.data_ptr(), self.total, float(self.lr), float(self.betas[0]), float(self.betas[1]),
              float(self.eps), float(self.weight_decay), self.step_count, 1.0 / world_size, ops._stream())
+        ops.invalidate_weight_cache()      # the kernel rewrote the parameters in place
 
 
 class DistillTrainer:

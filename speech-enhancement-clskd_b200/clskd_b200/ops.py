@@ -165,6 +165,7 @@ class Launch:
     N: int = 0           # output channels (n)
     c_lo: int = 0        # for dgrad launches: slice [c_lo, c_lo+N) of the input channels
     woff: int = 0        # offset of this launch's dW block in the concatenated wgrad buffer
+    _cache: dict = field(default_factory=dict)   # packed kernel-side weights keyed by parameter version
 
     # pack tables (int32 pairs on the device), built on first use: [tap][c][n] and [tap][n][c]
     @property
@@ -264,6 +265,7 @@ class ConvPlan:
             off += l.blk.size
         self.wcat = off
         self._unpack = [None, None]
+        self._cache = {}
         # ---- bias: bias_table is an int32 pair table [N,2] over (bias_a, bias_b) or None
         self.bias_table = None
         self.bias_unpack_a = self.bias_unpack_b = None
@@ -327,6 +329,32 @@ class ConvPlan:
             To = (Ti - 1) - 2 * self.pt + self.KT + self.t_extra
             Fo = (Fi - 1) * self.sf - 2 * self.pf + self.KF + self.f_extra
         return To, Fo
+
+
+weights_epoch = 0   # bumped by anything that rewrites parameters behind autograd's back (FlatAdam's kernel)
+
+
+def invalidate_weight_cache():
+    """Packed (kernel-layout) weights are cached per parameter version; call this after modifying
+    parameter storage in a way torch's version counters cannot see (e.g. through `.data`)."""
+    global weights_epoch
+    weights_epoch += 1
+
+
+def _wkey(a, b):
+    return (a.data_ptr(), a._version, b.data_ptr() if b is not None else 0, b._version if b is not None else 0,
+            weights_epoch)
+
+
+def packed_weights(cache, name, table_fn, a, b, dtype):
+    """pack_weights(table, a, b, dtype), memoised in `cache` until a / b change."""
+    key = _wkey(a, b)
+    ent = cache.get((name, dtype))
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    w = pack_weights(table_fn(), a, b, dtype)
+    cache[(name, dtype)] = (key, w)
+    return w
 
 
 def pack_weights(table, a, b, dtype):
@@ -398,12 +426,12 @@ def run_tapconv(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, a, b, bias, y, x0_
     _fill_desc(d, x0, x0_off, x0_str, x1, x1_off, x1_str, c0, c1, B, To, Fo, Ti, Fi, l, x0, bias,
                l.N, y, y_off, y_str, accumulate)
     if allow_umma and _umma_ok(d):
-        w = pack_weights(l.t_nc, a, b, torch.bfloat16)
+        w = packed_weights(l._cache, "nc", lambda: l.t_nc, a, b, torch.bfloat16)
         d.w = w.data_ptr()
         call("clskd_tapconv_fwd_umma", ctypes.byref(d), _stream())
         umma_launches += 1
     else:
-        w = pack_weights(l.t_cn, a, b, torch.float32)
+        w = packed_weights(l._cache, "cn", lambda: l.t_cn, a, b, torch.float32)
         d.w = w.data_ptr()
         call("clskd_tapconv_fwd", ctypes.byref(d), _stream())
         core_launches += 1
@@ -455,8 +483,8 @@ class TapConvFn(torch.autograd.Function):
         b32 = _f32c(b) if b is not None else None
         bias = None
         if plan.bias_table is not None and bias_a is not None:
-            bias = pack_weights(plan.bias_table, _f32c(bias_a), _f32c(bias_b) if bias_b is not None else None,
-                                torch.float32)
+            bias = packed_weights(plan._cache, "bias", lambda: plan.bias_table, _f32c(bias_a),
+                                  _f32c(bias_b) if bias_b is not None else None, torch.float32)
         y = torch.empty((B, To, Fo, plan.N), dtype=out_dtype, device=x0.device)
         for l in plan.fwd:
             Fo_l = Fo // l.osf

@@ -210,7 +210,7 @@ const char* wgrad_unsupported(const ClskdTapConv* d) {
   if (d->c1)
     if (const char* r = chk(d->x1, d->x1_sB, d->x1_sT, d->x1_sF)) return r;
   if (const char* r = chk(d->y, d->y_sB, d->y_sT, d->y_sF)) return r;
-  if ((int64_t)d->B * d->To * d->Fo < 4096) return "too few rows to amortise the split-K epilogue";
+  if ((int64_t)d->B * d->To * d->Fo < 512) return "too few rows to amortise the split-K epilogue";
   if (!get_encode()) return "cuTensorMapEncodeTiled unavailable";
   return nullptr;
 }

@@ -129,12 +129,23 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 
 // ---- host side
+// cuTensorMapEncodeTiled is a driver-API call: make sure this thread (e.g. an autograd worker) has
+// the primary context bound before the first one.
+inline void ensure_context() {
+  static thread_local bool done = false;
+  if (!done) {
+    cudaFree(nullptr);
+    done = true;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline EncodeTiledFn get_encode() {
+  ensure_context();
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
