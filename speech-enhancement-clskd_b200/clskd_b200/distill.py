@@ -161,6 +161,7 @@ class FlatAdam:
         for p, o, s in zip(self.params, offs[:-1], sizes):
             self.flat_p[o:o + s].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + s].view(p.shape)
+        ops.register_volatile_range(self.flat_p.data_ptr(), self.flat_p.data_ptr() + 4 * self.total)
         self.flat_g = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.m = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.total, dtype=torch.float32, device=dev)

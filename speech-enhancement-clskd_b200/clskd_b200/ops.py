@@ -335,15 +335,24 @@ weights_epoch = 0   # bumped by anything that rewrites parameters behind autogra
 
 
 def invalidate_weight_cache():
-    """Packed (kernel-layout) weights are cached per parameter version; call this after modifying
-    parameter storage in a way torch's version counters cannot see (e.g. through `.data`)."""
+    """Packed (kernel-layout) weights are cached per parameter version; FlatAdam calls this after its
+    kernel rewrote the flat parameter bucket (a registered volatile range) behind autograd's back."""
     global weights_epoch
     weights_epoch += 1
 
 
+_volatile_ranges = []   # [lo, hi) device-address ranges rewritten by kernels outside autograd (FlatAdam buckets)
+
+
+def register_volatile_range(lo, hi):
+    _volatile_ranges.append((lo, hi))
+
+
 def _wkey(a, b):
-    return (a.data_ptr(), a._version, b.data_ptr() if b is not None else 0, b._version if b is not None else 0,
-            weights_epoch)
+    pa = a.data_ptr()
+    pb = b.data_ptr() if b is not None else 0
+    vol = any(lo <= pa < hi or lo <= pb < hi for lo, hi in _volatile_ranges) if _volatile_ranges else False
+    return (pa, a._version, pb, b._version if b is not None else 0, weights_epoch if vol else -1)
 
 
 def packed_weights(cache, name, table_fn, a, b, dtype):

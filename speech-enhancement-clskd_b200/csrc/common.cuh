@@ -92,6 +92,23 @@ __device__ __forceinline__ T block_sum(T v, T* sh) {
   return v;
 }
 
+// 128-bit vectorised fast paths (elementwise_vec.cu); each returns false when the shape / alignment
+// does not qualify and the caller falls back to the scalar kernel.
+namespace vec {
+bool colstats(const void* x, const void* dy, int dtype, int mode, int64_t M, int C, const float* mean,
+              const float* invstd, const float* gamma, const float* beta, const float* slope, double* o0,
+              double* o1, double* o2, cudaStream_t st);
+bool bn_act_fwd(const void* x, int x_dtype, int64_t M, int C, const float* mean, const float* invstd,
+                const float* gamma, const float* beta, const float* slope, void* y, int y_dtype, cudaStream_t st);
+bool bn_act_bwd_apply(const void* x, const void* dy, int dtype, int64_t M, int C, const float* mean,
+                      const float* invstd, const float* gamma, const float* beta, const float* slope,
+                      const double* sum_dz, const double* sum_dz_xhat, int training, void* dx, cudaStream_t st);
+bool resize_f(const void* src, int dtype, int64_t BT, int Fi, int Fo, int C, void* dst, bool backward, cudaStream_t st);
+bool att_blend_fwd(const void* x, const void* y, int dtype, const float* z, int64_t M, int C, void* out, cudaStream_t st);
+bool att_blend_bwd(const void* x, const void* y, int dtype, const float* z, const void* dout, int64_t M, int C,
+                   void* dx, void* dy, float* dz, cudaStream_t st);
+}  // namespace vec
+
 // dispatch on a runtime dtype tag
 #define CLSKD_DISPATCH_DTYPE(tag, T, ...)                         \
   do {                                                            \

@@ -909,6 +909,10 @@ extern "C" int clskd_colstats(const void* x, int dtype, int64_t M, int C, double
     if (e__ != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e__)); return CLSKD_ERR_CUDA; }
   }
   if (M == 0) return CLSKD_OK;
+  if (vec::colstats(x, nullptr, dtype, 0, M, C, nullptr, nullptr, nullptr, nullptr, nullptr, sum, sumsq, nullptr, ST)) {
+    CLSKD_CHECK_LAUNCH("clskd_colstats(vec)");
+    return CLSKD_OK;
+  }
   size_t sh = 2 * g.threads * sizeof(float);
   CLSKD_DISPATCH_DTYPE(dtype, T,
                        (colstats_kernel<T, 0><<<g.grid, g.threads, sh, ST>>>(
@@ -943,6 +947,10 @@ extern "C" int clskd_bn_act_fwd(const void* x, int x_dtype, int64_t M, int C, co
   CLSKD_CHECK_ARG(x && y && mean && invstd, "clskd_bn_act_fwd: null pointer");
   int64_t n = M * C;
   if (n == 0) return CLSKD_OK;
+  if (vec::bn_act_fwd(x, x_dtype, M, C, mean, invstd, gamma, beta, slope, y, y_dtype, ST)) {
+    CLSKD_CHECK_LAUNCH("clskd_bn_act_fwd(vec)");
+    return CLSKD_OK;
+  }
   bool vec = (C % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
 #define L(TX, TY)                                                                                 \
   do {                                                                                            \
@@ -980,6 +988,10 @@ extern "C" int clskd_bn_act_bwd_stats(const void* x, int x_dtype, const void* dy
     if (e__ != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e__)); return CLSKD_ERR_CUDA; }
   }
   if (M == 0) return CLSKD_OK;
+  if (vec::colstats(x, dy, x_dtype, 1, M, C, mean, invstd, gamma, beta, slope, sum_dz, sum_dz_xhat, dslope, ST)) {
+    CLSKD_CHECK_LAUNCH("clskd_bn_act_bwd_stats(vec)");
+    return CLSKD_OK;
+  }
   size_t sh = 3 * g.threads * sizeof(float);
   CLSKD_DISPATCH_DTYPE(x_dtype, T,
                        (colstats_kernel<T, 1><<<g.grid, g.threads, sh, ST>>>(
@@ -1001,7 +1013,10 @@ extern "C" int clskd_bn_act_bwd_apply(const void* x, int x_dtype, const void* dy
   CLSKD_CHECK_ARG(x_dtype == dy_dtype && x_dtype == dx_dtype,
                   "clskd_bn_act_bwd_apply: dtypes must match");
   int64_t n = M * C;
-  if (n > 0) {
+  if (n > 0 && vec::bn_act_bwd_apply(x, dy, x_dtype, M, C, mean, invstd, gamma, beta, slope, sum_dz, sum_dz_xhat,
+                                     training, dx, ST)) {
+    CLSKD_CHECK_LAUNCH("clskd_bn_act_bwd_apply(vec)");
+  } else if (n > 0) {
     CLSKD_DISPATCH_DTYPE(x_dtype, T,
                          (bn_act_bwd_apply_kernel<T, T, T><<<ew_grid(n, 256), 256, 0, ST>>>(
                              (const T*)x, (const T*)dy, n, M, C, mean, invstd, gamma, beta, slope,
@@ -1122,6 +1137,10 @@ extern "C" int clskd_resize_f_fwd(const void* x, int dtype, int64_t BT, int Fi, 
   CLSKD_CHECK_ARG(x && y && Fi > 0 && Fo > 0, "clskd_resize_f_fwd: bad arguments");
   int64_t total = BT * Fo * C;
   if (total == 0) return CLSKD_OK;
+  if (vec::resize_f(x, dtype, BT, Fi, Fo, C, y, false, ST)) {
+    CLSKD_CHECK_LAUNCH("clskd_resize_f_fwd(vec)");
+    return CLSKD_OK;
+  }
   CLSKD_DISPATCH_DTYPE(dtype, T,
                        (resize_f_fwd_kernel<T><<<ew_grid(total, 256), 256, 0, ST>>>(
                            (const T*)x, BT, Fi, Fo, C, (T*)y)));
@@ -1134,6 +1153,10 @@ extern "C" int clskd_resize_f_bwd(const void* dy, int dtype, int64_t BT, int Fi,
   CLSKD_CHECK_ARG(dy && dx && Fi > 0 && Fo > 0, "clskd_resize_f_bwd: bad arguments");
   int64_t total = BT * Fi * C;
   if (total == 0) return CLSKD_OK;
+  if (vec::resize_f(dy, dtype, BT, Fi, Fo, C, dx, true, ST)) {
+    CLSKD_CHECK_LAUNCH("clskd_resize_f_bwd(vec)");
+    return CLSKD_OK;
+  }
   CLSKD_DISPATCH_DTYPE(dtype, T,
                        (resize_f_bwd_kernel<T><<<ew_grid(total, 256), 256, 0, ST>>>(
                            (const T*)dy, BT, Fi, Fo, C, (T*)dx)));
@@ -1145,6 +1168,10 @@ extern "C" int clskd_att_blend_fwd(const void* x, const void* y, int dtype, cons
                                    int64_t M, int C, void* out, void* stream) {
   CLSKD_CHECK_ARG(x && y && z && out, "clskd_att_blend_fwd: null pointer");
   if (M * C == 0) return CLSKD_OK;
+  if (vec::att_blend_fwd(x, y, dtype, z, M, C, out, ST)) {
+    CLSKD_CHECK_LAUNCH("clskd_att_blend_fwd(vec)");
+    return CLSKD_OK;
+  }
   CLSKD_DISPATCH_DTYPE(dtype, T,
                        (att_blend_fwd_kernel<T><<<ew_grid(M * C, 256), 256, 0, ST>>>(
                            (const T*)x, (const T*)y, z, M, C, (T*)out)));
@@ -1157,6 +1184,10 @@ extern "C" int clskd_att_blend_bwd(const void* x, const void* y, int dtype, cons
                                    float* dz, void* stream) {
   CLSKD_CHECK_ARG(x && y && z && dout && dx && dy && dz, "clskd_att_blend_bwd: null pointer");
   if (M * C == 0) return CLSKD_OK;
+  if (vec::att_blend_bwd(x, y, dtype, z, dout, M, C, dx, dy, dz, ST)) {
+    CLSKD_CHECK_LAUNCH("clskd_att_blend_bwd(vec)");
+    return CLSKD_OK;
+  }
   CLSKD_DISPATCH_DTYPE(dtype, T,
                        (att_blend_bwd_kernel<T><<<ew_grid(M * 32, 256), 256, 0, ST>>>(
                            (const T*)x, (const T*)y, z, (const T*)dout, M, C, (T*)dx, (T*)dy, dz)));

@@ -477,6 +477,132 @@ bool n2_ok(const ClskdTapConv* d, N2Geom* g) {
   return true;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K = ntaps*Ctot <= 32 inputs per row (the 2-channel spectrum entering the first encoder layer
+// and ABF's 1x1 conv on the 2-channel mask map, the data gradients of the 2-logit attention conv
+// and of the mask layer): an outer-product expansion, bound by the OUTPUT write.  One thread makes
+// 8 consecutive outputs of one row (one 16/32-byte store); the row's few inputs are broadcast loads.
+// ------------------------------------------------------------------------------------------
+constexpr int SK_MAXK = 32;
+
+__device__ __forceinline__ void st8(float* p, const float* v) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
+  uint4 u;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <typename TX>
+__device__ __forceinline__ float smallk_x(const ClskdTapConv& d, int k, int Ctot, int b, int t, int f) {
+  const int tap = k / Ctot, c = k - tap * Ctot;
+  const int ti = t + d.dt[tap], fi = f * d.sf + d.df[tap];
+  if (ti < 0 || ti >= d.Ti || fi < 0 || fi >= d.Fi) return 0.f;
+  if (c < d.c0)
+    return ld_f(reinterpret_cast<const TX*>(d.x0) + (int64_t)b * d.x0_sB + (int64_t)ti * d.x0_sT + (int64_t)fi * d.x0_sF + c);
+  return ld_f(reinterpret_cast<const TX*>(d.x1) + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF + (c - d.c0));
+}
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) tapconv_fwd_smallk_kernel(ClskdTapConv d, int Ktot) {
+  extern __shared__ float wsm[];   // [Ktot][N] + bias[N]
+  const int N = d.N, Ctot = d.c0 + d.c1;
+  const float* w = reinterpret_cast<const float*>(d.w);
+  for (int i = threadIdx.x; i < Ktot * N; i += blockDim.x) wsm[i] = w[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) wsm[Ktot * N + i] = d.bias ? d.bias[i] : 0.f;
+  __syncthreads();
+  const int tpr = N >> 3;                       // threads per row
+  const int64_t M = (int64_t)d.B * d.To * d.Fo;
+  const int64_t total = M * tpr;
+  TY* y = reinterpret_cast<TY*>(d.y);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n0 = (int)(i % tpr) * 8;
+    const int64_t m = i / tpr;
+    const int f = (int)(m % d.Fo);
+    const int64_t r = m / d.Fo;
+    const int t = (int)(r % d.To), b = (int)(r / d.To);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = wsm[Ktot * N + n0 + e];
+    for (int k = 0; k < Ktot; ++k) {
+      const float xv = smallk_x<TX>(d, k, Ctot, b, t, f);
+      const float4 w0 = *reinterpret_cast<const float4*>(&wsm[k * N + n0]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&wsm[k * N + n0 + 4]);
+      acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+      acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+      acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+      acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+    }
+    st8(y + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF + n0, acc);
+  }
+}
+
+// dW[k][n] for K <= 32: a thread owns 8 consecutive n and up to 8 k of the rows it visits (one
+// 16-byte read of dY per row, inputs broadcast), then shared-memory and global fp32 reductions.
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) tapconv_wgrad_smallk_kernel(ClskdTapConv d, int Ktot, int kchunks) {
+  extern __shared__ float red[];   // [Ktot][N]
+  const int N = d.N, Ctot = d.c0 + d.c1;
+  for (int i = threadIdx.x; i < Ktot * N; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int tpr = N >> 3;
+  const int per_row = tpr * kchunks;            // threads cooperating on one row
+  const int rows_par = blockDim.x / per_row;    // rows in flight per block
+  const int sub = threadIdx.x / per_row;
+  const int rem = threadIdx.x - sub * per_row;
+  const int kc = rem / tpr, n0 = (rem - kc * tpr) * 8;
+  const int k0 = kc * 8, kcnt = min(8, Ktot - k0);
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+  const int64_t M = (int64_t)d.B * d.To * d.Fo;
+  const TY* dy = reinterpret_cast<const TY*>(d.y);
+  if (sub < rows_par) {
+    for (int64_t m = (int64_t)blockIdx.x * rows_par + sub; m < M; m += (int64_t)gridDim.x * rows_par) {
+      const int f = (int)(m % d.Fo);
+      const int64_t r = m / d.Fo;
+      const int t = (int)(r % d.To), b = (int)(r / d.To);
+      float g[8];
+      ld8(dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF + n0, g);
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        if (a < kcnt) {
+          const float xv = smallk_x<TX>(d, k0 + a, Ctot, b, t, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[a][e] = fmaf(xv, g[e], acc[a][e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+      if (a < kcnt)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&red[(k0 + a) * N + n0 + e], acc[a][e]);
+  }
+  __syncthreads();
+  float* dw = reinterpret_cast<float*>(const_cast<void*>(d.w));
+  for (int i = threadIdx.x; i < Ktot * N; i += blockDim.x) atomicAdd(dw + i, red[i]);
+}
+
+bool smallk_ok(const ClskdTapConv* d, int* Ktot) {
+  *Ktot = d->ntaps * (d->c0 + d->c1);
+  if (*Ktot > SK_MAXK || d->N % 8 || d->N < 8 || d->N > 512 || d->accumulate) return false;
+  if (((size_t)*Ktot * d->N + d->N) * sizeof(float) > 46 * 1024) return false;   // weights staged in static-limit smem
+  const int ye = d->y_dtype == CLSKD_F32 ? 4 : 2;
+  return ((uintptr_t)d->y % 16 == 0) && (d->y_sB * ye) % 16 == 0 && (d->y_sT * ye) % 16 == 0 &&
+         (d->y_sF * ye) % 16 == 0;
+}
+
 int check_desc(const ClskdTapConv* d, const char* who) {
   CLSKD_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
   CLSKD_CHECK_ARG(d->x0 && d->w && d->y, "%s: null tensor pointer", who);
@@ -540,6 +666,23 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
     CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(n2)");
     return CLSKD_OK;
   }
+  int ktot_sk;
+  if (smallk_ok(d, &ktot_sk)) {
+    const int64_t total = M * (d->N / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+    const size_t sh = sizeof(float) * ((size_t)ktot_sk * d->N + d->N);
+    if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32)
+      tapconv_fwd_smallk_kernel<float, float><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);
+    else if (d->x_dtype == CLSKD_F32)
+      tapconv_fwd_smallk_kernel<float, __nv_bfloat16><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);
+    else if (d->y_dtype == CLSKD_F32)
+      tapconv_fwd_smallk_kernel<__nv_bfloat16, float><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);
+    else
+      tapconv_fwd_smallk_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);
+    CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(smallk)");
+    return CLSKD_OK;
+  }
   dim3 grid(cdiv(M, BM), cdiv(d->N, BN));
   bool vec = vec_ok(d);
 #define LAUNCH(TX, TY)                                                        \
@@ -588,6 +731,25 @@ extern "C" int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream) {
 #undef LAUNCH_W2
     CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad(n2)");
     return CLSKD_OK;
+  }
+  int ktot_sk;
+  if (smallk_ok(d, &ktot_sk) && M >= 1024 && d->N <= 256) {
+    const int kchunks = cdiv(ktot_sk, 8);
+    const int per_row = (d->N / 8) * kchunks;
+    if (per_row <= 256) {
+      int blocks = sm_count() * 4;
+      const size_t sh = sizeof(float) * (size_t)ktot_sk * d->N;
+      if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32)
+        tapconv_wgrad_smallk_kernel<float, float><<<blocks, 256, sh, st>>>(*d, ktot_sk, kchunks);
+      else if (d->x_dtype == CLSKD_F32)
+        tapconv_wgrad_smallk_kernel<float, __nv_bfloat16><<<blocks, 256, sh, st>>>(*d, ktot_sk, kchunks);
+      else if (d->y_dtype == CLSKD_F32)
+        tapconv_wgrad_smallk_kernel<__nv_bfloat16, float><<<blocks, 256, sh, st>>>(*d, ktot_sk, kchunks);
+      else
+        tapconv_wgrad_smallk_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, sh, st>>>(*d, ktot_sk, kchunks);
+      CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad(smallk)");
+      return CLSKD_OK;
+    }
   }
   int tiles = cdiv(Ktot, BM) * cdiv(d->N, BN);
   int target = sm_count() * 6;
