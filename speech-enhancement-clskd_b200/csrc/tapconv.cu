@@ -400,6 +400,69 @@ __global__ void __launch_bounds__(256) tapconv_fwd_n2_kernel(ClskdTapConv d, N2G
   }
 }
 
+// N <= 2 with many taps (ABF's 3x3 conv onto the 2-channel mask map: K = 9*128): lanes own the
+// 8-channel units of ONE tap (cpt <= 128 -> at most 4 units per lane), the tap loop is in the
+// kernel and the weights sit in shared memory transposed to [tap][e][unit] so that a warp's loads
+// are conflict free.
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) tapconv_fwd_n2_taps_kernel(ClskdTapConv d, int cpt) {
+  extern __shared__ float2 w2[];   // [ntaps][8][cpt]
+  const int Ctot = d.c0 + d.c1;
+  const float* w = reinterpret_cast<const float*>(d.w);
+  for (int i = threadIdx.x; i < d.ntaps * 8 * cpt; i += blockDim.x) {
+    const int cu = i % cpt, e = (i / cpt) & 7, tap = i / (8 * cpt);
+    const int64_t k = (int64_t)tap * Ctot + cu * 8 + e;
+    w2[i] = make_float2(w[k * d.N], d.N > 1 ? w[k * d.N + 1] : 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const float b0 = d.bias ? d.bias[0] : 0.f;
+  const float b1 = (d.bias && d.N > 1) ? d.bias[1] : 0.f;
+  const int64_t M = (int64_t)d.B * d.To * d.Fo;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const TX* x0 = reinterpret_cast<const TX*>(d.x0);
+  const TX* x1 = reinterpret_cast<const TX*>(d.x1);
+  TY* y = reinterpret_cast<TY*>(d.y);
+  for (int64_t m = warp0; m < M; m += nwarps) {
+    const int f = (int)(m % d.Fo);
+    const int64_t r = m / d.Fo;
+    const int t = (int)(r % d.To), b = (int)(r / d.To);
+    float a0 = 0.f, a1 = 0.f;
+    for (int tap = 0; tap < d.ntaps; ++tap) {
+      const int ti = t + d.dt[tap], fi = f * d.sf + d.df[tap];
+      if (ti < 0 || ti >= d.Ti || fi < 0 || fi >= d.Fi) continue;    // warp-uniform
+      const TX* r0 = x0 + (int64_t)b * d.x0_sB + (int64_t)ti * d.x0_sT + (int64_t)fi * d.x0_sF;
+      const TX* r1 = d.c1 ? x1 + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF : nullptr;
+      for (int cu = lane; cu < cpt; cu += 32) {
+        const int c = cu * 8;
+        float xv[8];
+        if (c < d.c0) ld8(r0 + c, xv);
+        else ld8(r1 + (c - d.c0), xv);
+        const float2* wp = w2 + (size_t)tap * 8 * cpt + cu;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float2 ww = wp[e * cpt];
+          a0 = fmaf(xv[e], ww.x, a0);
+          a1 = fmaf(xv[e], ww.y, a1);
+        }
+      }
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) {
+      TY* yp = y + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF;
+      float v0 = a0 + b0, v1 = a1 + b1;
+      if (d.accumulate) {
+        v0 += ld_f(yp);
+        if (d.N > 1) v1 += ld_f(yp + 1);
+      }
+      st_f(yp, v0);
+      if (d.N > 1) st_f(yp + 1, v1);
+    }
+  }
+}
+
 // dW[k][n] for N <= 2: every lane accumulates its own 8-channel units over the rows its warp
 // visits (no cross-lane traffic in the loop), then shared-memory and global fp32 reductions.
 template <typename TX, typename TY, int UPL>
@@ -470,7 +533,7 @@ bool n2_ok(const ClskdTapConv* d, N2Geom* g) {
   if (d->c1 && !al(d->x1, d->x1_sB, d->x1_sT, d->x1_sF)) return false;
   g->cpt = Ctot / 8;
   g->U = d->ntaps * g->cpt;
-  if (g->U > 128) return false;
+  if (g->cpt > 128) return false;          // more than 1024 input channels: generic kernel
   int up2 = 1;
   while (up2 < g->U && up2 < 32) up2 <<= 1;
   g->up2 = up2;
@@ -646,7 +709,24 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
   if (M == 0) return CLSKD_OK;
   cudaStream_t st = (cudaStream_t)stream;
   N2Geom g2;
-  if (n2_ok(d, &g2)) {
+  if (n2_ok(d, &g2) && g2.U > 128) {
+    int64_t blocks = (M + 7) / 8 / 4;
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    if (blocks < 1) blocks = 1;
+    const size_t sh = sizeof(float2) * (size_t)d->ntaps * 8 * g2.cpt;   // <= 16 taps * 8 * 128 * 8 B = 128 KB
+    if (sh <= 46 * 1024) {
+      if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32)
+        tapconv_fwd_n2_taps_kernel<float, float><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt);
+      else if (d->x_dtype == CLSKD_F32)
+        tapconv_fwd_n2_taps_kernel<float, __nv_bfloat16><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt);
+      else if (d->y_dtype == CLSKD_F32)
+        tapconv_fwd_n2_taps_kernel<__nv_bfloat16, float><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt);
+      else
+        tapconv_fwd_n2_taps_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt);
+      CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(n2 taps)");
+      return CLSKD_OK;
+    }
+  } else if (n2_ok(d, &g2)) {
     const int upl = cdiv(g2.U, g2.up2);   // 1, 2, 3 or 4 units per lane
     const int64_t warps_needed = (M + (32 / g2.up2) - 1) / (32 / g2.up2);
     int64_t blocks = (warps_needed + 7) / 8 / 4;
@@ -714,6 +794,24 @@ extern "C" int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream) {
   }
   if (M == 0) return CLSKD_OK;
   N2Geom g2;
+  if (n2_ok(d, &g2) && M >= 1024 && g2.U > 128) {
+    // many taps: one pass over the rows per group of taps whose units fit the register budget
+    const int tpg = 128 / g2.cpt;           // taps per group (cpt <= 128 -> >= 1)
+    const int Ctot_ = d->c0 + d->c1;
+    for (int t0 = 0; t0 < d->ntaps; t0 += tpg) {
+      ClskdTapConv sub = *d;
+      sub.ntaps = d->ntaps - t0 < tpg ? d->ntaps - t0 : tpg;
+      for (int j = 0; j < sub.ntaps; ++j) {
+        sub.dt[j] = d->dt[t0 + j];
+        sub.df[j] = d->df[t0 + j];
+      }
+      sub.w = reinterpret_cast<const float*>(d->w) + (size_t)t0 * Ctot_ * d->N;
+      sub.accumulate = 1;                   // dW was zeroed above (or the caller accumulates)
+      int rc2 = clskd_tapconv_wgrad(&sub, stream);
+      if (rc2) return rc2;
+    }
+    return CLSKD_OK;
+  }
   if (n2_ok(d, &g2) && M >= 1024) {
     const int upl = cdiv(g2.U, g2.up2);
     int blocks = sm_count() * 4;

@@ -385,3 +385,27 @@ def test_trainer_step_decreases_loss(dev):
     tr = DistillTrainer(teacher, student, mode="spkd_all", lr=1e-3)
     losses = [float(tr.train_step(X, y)) for _ in range(4)]
     assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("cin,cout,ks", [(128, 2, 3), (256, 2, 1), (2, 128, 1), (16, 1, 3), (2, 16, 3)])
+def test_narrow_real_convs_vs_torch(dev, cin, cout, ks):
+    """ABF's convolutions with very few output or input channels (the 2-channel mask map and the
+    2-logit attention conv) take dedicated GEMV / outer-product kernels: forward, dgrad, wgrad."""
+    from clskd_b200 import framework as fw
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    conv = fw.RealConv2d(cin, cout, ks, padding=ks // 2, bias=True)
+    x = torch.randn(2, cin, 16, 70, generator=g)
+    up = torch.randn(2, cout, 16, 70, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr, br = conv.weight.detach().clone().requires_grad_(True), conv.bias.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(xr, wr, br, padding=ks // 2)
+    (ref * up).sum().backward()
+    gw_ref, gb_ref = wr.grad, br.grad
+    conv = conv.to(dev)
+    xd = x.clone().to(dev).requires_grad_(True)
+    y = conv(xd)
+    (y * up.to(dev)).sum().backward()
+    assert torch.allclose(y.detach().cpu(), ref.detach(), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(xd.grad.cpu(), xr.grad, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(conv.weight.grad.cpu(), gw_ref, atol=2e-3, rtol=1e-3)
+    assert torch.allclose(conv.bias.grad.cpu(), gb_ref, atol=2e-3, rtol=1e-3)
