@@ -54,6 +54,8 @@ class DistillStep(nn.Module):
         self.abf_encoder = None
         self.abf_decoder = None
         self.last_terms = {}
+        self.overlap_teacher = True
+        self._side = None
 
     # ---- ABF management
     def _abfs(self, s_enc, s_dec, t_enc, t_dec):
@@ -99,8 +101,22 @@ class DistillStep(nn.Module):
         terms = {}
         feature_modes = self.mode in ('clskd', 'spkd_all', 'reviewkd')
         if feature_modes:
-            t_wav, t_enc, t_dec, t_re, t_im = _taps(teacher, X, self.faithful)
-            s_wav, s_enc, s_dec, s_re, s_im = _taps(student, X, True)
+            if X.is_cuda and not self.faithful and self.overlap_teacher:
+                # the frozen teacher and the student are independent until the losses: run the teacher
+                # on a side stream so that each model's latency-bound LSTM overlaps the other's convs
+                main = torch.cuda.current_stream()
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=X.device)
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    t_wav, t_enc, t_dec, t_re, t_im = _taps(teacher, X, False)
+                s_wav, s_enc, s_dec, s_re, s_im = _taps(student, X, True)
+                main.wait_stream(self._side)
+                for t in [t_wav, t_re, t_im] + list(t_enc) + list(t_dec):
+                    t.record_stream(main)
+            else:
+                t_wav, t_enc, t_dec, t_re, t_im = _taps(teacher, X, self.faithful)
+                s_wav, s_enc, s_dec, s_re, s_im = _taps(student, X, True)
             if self.faithful:
                 s_wav = student(X, is_feat=True)        # the reference runs the student twice (distill.py:100)
             terms['base'] = self._base(s_wav, y)

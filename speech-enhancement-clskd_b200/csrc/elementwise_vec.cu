@@ -182,16 +182,16 @@ __global__ void __launch_bounds__(VT) bn_act_bwd_apply_vec_kernel(const T* __res
 }
 
 // ------------------------------------------------------------------------------- ABF helpers
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(VT) resize_f_fwd_vec_kernel(const T* __restrict__ x, int64_t BT, int Fi, int Fo,
                                                               int C, T* __restrict__ y) {
-  const int tpr = C >> 3;
-  const int64_t total = BT * Fo * tpr;
-  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < total; i += (int64_t)gridDim.x * VT) {
+  const I tpr = C >> 3;
+  const I total = (I)BT * Fo * tpr;
+  for (I i = (I)blockIdx.x * VT + threadIdx.x; i < total; i += (I)gridDim.x * VT) {
     const int cg = (int)(i % tpr);
-    const int64_t r = i / tpr;
-    const int fo = (int)(r % Fo);
-    const int64_t bt = r / Fo;
+    const I r = i / tpr;
+    const int fo = (int)(r % (I)Fo);
+    const int64_t bt = r / (I)Fo;
     const int fi = (int)(((int64_t)fo * Fi) / Fo);
     *reinterpret_cast<uint4*>(y + i * 8) = *reinterpret_cast<const uint4*>(x + ((bt * Fi + fi) * C + cg * 8));
     if (sizeof(T) == 4)
@@ -199,16 +199,16 @@ __global__ void __launch_bounds__(VT) resize_f_fwd_vec_kernel(const T* __restric
   }
 }
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(VT) resize_f_bwd_vec_kernel(const T* __restrict__ dy, int64_t BT, int Fi, int Fo,
                                                               int C, T* __restrict__ dx) {
-  const int tpr = C >> 3;
-  const int64_t total = BT * Fi * tpr;
-  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < total; i += (int64_t)gridDim.x * VT) {
+  const I tpr = C >> 3;
+  const I total = (I)BT * Fi * tpr;
+  for (I i = (I)blockIdx.x * VT + threadIdx.x; i < total; i += (I)gridDim.x * VT) {
     const int cg = (int)(i % tpr);
-    const int64_t r = i / tpr;
-    const int fi = (int)(r % Fi);
-    const int64_t bt = r / Fi;
+    const I r = i / tpr;
+    const int fi = (int)(r % (I)Fi);
+    const int64_t bt = r / (I)Fi;
     const int lo = (int)(((int64_t)fi * Fo + Fi - 1) / Fi);
     int hi = (int)(((int64_t)(fi + 1) * Fo + Fi - 1) / Fi);
     if (hi > Fo) hi = Fo;
@@ -225,13 +225,13 @@ __global__ void __launch_bounds__(VT) resize_f_bwd_vec_kernel(const T* __restric
 
 __device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + __expf(-v)); }
 
-template <typename T>
+template <typename T, typename I>
 __global__ void __launch_bounds__(VT) att_blend_fwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ y,
                                                                const float* __restrict__ z, int64_t M, int C,
                                                                T* __restrict__ out) {
-  const int tpr = C >> 3;
-  const int64_t total = M * tpr;
-  for (int64_t i = (int64_t)blockIdx.x * VT + threadIdx.x; i < total; i += (int64_t)gridDim.x * VT) {
+  const I tpr = C >> 3;
+  const I total = (I)M * tpr;
+  for (I i = (I)blockIdx.x * VT + threadIdx.x; i < total; i += (I)gridDim.x * VT) {
     const int64_t m = i / tpr;
     const float2 zz = *reinterpret_cast<const float2*>(z + 2 * m);
     const float z0 = sigm(zz.x), z1 = sigm(zz.y);
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(VT) att_blend_bwd_vec_kernel(const T* __restri
     const int64_t i = it * stride + (int64_t)blockIdx.x * VT + threadIdx.x;
     const bool live = i < total;
     const int64_t ii = live ? i : 0;
-    const int64_t m = ii / tpr;
+    const int64_t m = ii < 0x7fffffffLL ? (int64_t)((unsigned)ii / (unsigned)tpr) : ii / tpr;
     const float2 zz = *reinterpret_cast<const float2*>(z + 2 * m);
     const float z0 = sigm(zz.x), z1 = sigm(zz.y);
     float g[8], a[8], b[8];
@@ -357,10 +357,13 @@ bool resize_f(const void* src, int dtype, int64_t BT, int Fi, int Fo, int C, voi
   if (C % 8 || !al16(src) || !al16(dst)) return false;
   const int64_t items = BT * (backward ? Fi : Fo) * (C / 8);
   const int grid = flat_grid(items);
+  const bool small = items + (int64_t)grid * VT < 4000000000LL;
   if (backward) {
-    CLSKD_DISPATCH_DTYPE(dtype, T, (resize_f_bwd_vec_kernel<T><<<grid, VT, 0, st>>>((const T*)src, BT, Fi, Fo, C, (T*)dst)));
+    if (small) { CLSKD_DISPATCH_DTYPE(dtype, T, (resize_f_bwd_vec_kernel<T, unsigned><<<grid, VT, 0, st>>>((const T*)src, BT, Fi, Fo, C, (T*)dst))); }
+    else { CLSKD_DISPATCH_DTYPE(dtype, T, (resize_f_bwd_vec_kernel<T, int64_t><<<grid, VT, 0, st>>>((const T*)src, BT, Fi, Fo, C, (T*)dst))); }
   } else {
-    CLSKD_DISPATCH_DTYPE(dtype, T, (resize_f_fwd_vec_kernel<T><<<grid, VT, 0, st>>>((const T*)src, BT, Fi, Fo, C, (T*)dst)));
+    if (small) { CLSKD_DISPATCH_DTYPE(dtype, T, (resize_f_fwd_vec_kernel<T, unsigned><<<grid, VT, 0, st>>>((const T*)src, BT, Fi, Fo, C, (T*)dst))); }
+    else { CLSKD_DISPATCH_DTYPE(dtype, T, (resize_f_fwd_vec_kernel<T, int64_t><<<grid, VT, 0, st>>>((const T*)src, BT, Fi, Fo, C, (T*)dst))); }
   }
   return true;
 }
@@ -368,7 +371,11 @@ bool resize_f(const void* src, int dtype, int64_t BT, int Fi, int Fo, int C, voi
 bool att_blend_fwd(const void* x, const void* y, int dtype, const float* z, int64_t M, int C, void* out, cudaStream_t st) {
   if (C % 8 || !al16(x) || !al16(y) || !al16(out) || ((uintptr_t)z % 8)) return false;
   const int grid = flat_grid(M * (C / 8));
-  CLSKD_DISPATCH_DTYPE(dtype, T, (att_blend_fwd_vec_kernel<T><<<grid, VT, 0, st>>>((const T*)x, (const T*)y, z, M, C, (T*)out)));
+  if (M * (C / 8) + (int64_t)grid * VT < 4000000000LL) {
+    CLSKD_DISPATCH_DTYPE(dtype, T, (att_blend_fwd_vec_kernel<T, unsigned><<<grid, VT, 0, st>>>((const T*)x, (const T*)y, z, M, C, (T*)out)));
+  } else {
+    CLSKD_DISPATCH_DTYPE(dtype, T, (att_blend_fwd_vec_kernel<T, int64_t><<<grid, VT, 0, st>>>((const T*)x, (const T*)y, z, M, C, (T*)out)));
+  }
   return true;
 }
 

@@ -300,6 +300,22 @@ __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* o) {
   }
 }
 
+// (b, t, f) of output row m; 32-bit divisions when the row count allows (checked on the host)
+__device__ __forceinline__ void row_decode(int64_t m, int To, int Fo, int& b, int& t, int& f) {
+  if (m < 0x7fffffffLL) {
+    const unsigned mm = (unsigned)m;
+    const unsigned r = mm / (unsigned)Fo;
+    f = (int)(mm - r * (unsigned)Fo);
+    b = (int)(r / (unsigned)To);
+    t = (int)(r - (unsigned)b * (unsigned)To);
+  } else {
+    f = (int)(m % Fo);
+    const int64_t r = m / Fo;
+    t = (int)(r % To);
+    b = (int)(r / To);
+  }
+}
+
 struct N2Geom {
   int U;      // 8-channel units per row = ntaps * Ctot / 8
   int cpt;    // units per tap = Ctot / 8
@@ -366,9 +382,8 @@ __global__ void __launch_bounds__(256) tapconv_fwd_n2_kernel(ClskdTapConv d, N2G
     const int64_t m = m0 + sub;
     const bool live = m < M;
     const int64_t mm = live ? m : 0;
-    const int f = (int)(mm % d.Fo);
-    const int64_t r = mm / d.Fo;
-    const int t = (int)(r % d.To), b = (int)(r / d.To);
+    int b, t, f;
+    row_decode(mm, d.To, d.Fo, b, t, f);
     float a0 = 0.f, a1 = 0.f;
     if (live) {
 #pragma unroll
@@ -425,9 +440,8 @@ __global__ void __launch_bounds__(256) tapconv_fwd_n2_taps_kernel(ClskdTapConv d
   const TX* x1 = reinterpret_cast<const TX*>(d.x1);
   TY* y = reinterpret_cast<TY*>(d.y);
   for (int64_t m = warp0; m < M; m += nwarps) {
-    const int f = (int)(m % d.Fo);
-    const int64_t r = m / d.Fo;
-    const int t = (int)(r % d.To), b = (int)(r / d.To);
+    int b, t, f;
+    row_decode(m, d.To, d.Fo, b, t, f);
     float a0 = 0.f, a1 = 0.f;
     for (int tap = 0; tap < d.ntaps; ++tap) {
       const int ti = t + d.dt[tap], fi = f * d.sf + d.df[tap];
@@ -487,9 +501,8 @@ __global__ void __launch_bounds__(256) tapconv_wgrad_n2_kernel(ClskdTapConv d, N
   for (int64_t m0 = warp0 * rpw; m0 < M; m0 += nwarps * rpw) {
     const int64_t m = m0 + sub;
     if (m >= M) continue;
-    const int f = (int)(m % d.Fo);
-    const int64_t r = m / d.Fo;
-    const int t = (int)(r % d.To), b = (int)(r / d.To);
+    int b, t, f;
+    row_decode(m, d.To, d.Fo, b, t, f);
     const TY* yp = dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF;
     const float g0 = ld_f(yp), g1 = d.N > 1 ? ld_f(yp + 1) : 0.f;
 #pragma unroll
@@ -574,7 +587,7 @@ __device__ __forceinline__ float smallk_x(const ClskdTapConv& d, int k, int Ctot
   return ld_f(reinterpret_cast<const TX*>(d.x1) + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF + (c - d.c0));
 }
 
-template <typename TX, typename TY>
+template <typename TX, typename TY, typename I>
 __global__ void __launch_bounds__(256) tapconv_fwd_smallk_kernel(ClskdTapConv d, int Ktot) {
   extern __shared__ float wsm[];   // [Ktot][N] + bias[N]
   const int N = d.N, Ctot = d.c0 + d.c1;
@@ -582,16 +595,16 @@ __global__ void __launch_bounds__(256) tapconv_fwd_smallk_kernel(ClskdTapConv d,
   for (int i = threadIdx.x; i < Ktot * N; i += blockDim.x) wsm[i] = w[i];
   for (int i = threadIdx.x; i < N; i += blockDim.x) wsm[Ktot * N + i] = d.bias ? d.bias[i] : 0.f;
   __syncthreads();
-  const int tpr = N >> 3;                       // threads per row
-  const int64_t M = (int64_t)d.B * d.To * d.Fo;
-  const int64_t total = M * tpr;
+  const I tpr = N >> 3;                         // threads per row
+  const I M = (I)d.B * d.To * d.Fo;
+  const I total = M * tpr;                      // I = unsigned when it fits 32 bits (cheap divisions)
   TY* y = reinterpret_cast<TY*>(d.y);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int n0 = (int)(i % tpr) * 8;
-    const int64_t m = i / tpr;
-    const int f = (int)(m % d.Fo);
-    const int64_t r = m / d.Fo;
-    const int t = (int)(r % d.To), b = (int)(r / d.To);
+    const I m = i / tpr;
+    const int f = (int)(m % (I)d.Fo);
+    const I r = m / (I)d.Fo;
+    const int t = (int)(r % (I)d.To), b = (int)(r / (I)d.To);
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = wsm[Ktot * N + n0 + e];
@@ -632,9 +645,8 @@ __global__ void __launch_bounds__(256) tapconv_wgrad_smallk_kernel(ClskdTapConv 
   const TY* dy = reinterpret_cast<const TY*>(d.y);
   if (sub < rows_par) {
     for (int64_t m = (int64_t)blockIdx.x * rows_par + sub; m < M; m += (int64_t)gridDim.x * rows_par) {
-      const int f = (int)(m % d.Fo);
-      const int64_t r = m / d.Fo;
-      const int t = (int)(r % d.To), b = (int)(r / d.To);
+      int b, t, f;
+      row_decode(m, d.To, d.Fo, b, t, f);
       float g[8];
       ld8(dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF + n0, g);
 #pragma unroll
@@ -752,14 +764,17 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
     int64_t blocks = (total + 255) / 256;
     if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
     const size_t sh = sizeof(float) * ((size_t)ktot_sk * d->N + d->N);
-    if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32)
-      tapconv_fwd_smallk_kernel<float, float><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);
-    else if (d->x_dtype == CLSKD_F32)
-      tapconv_fwd_smallk_kernel<float, __nv_bfloat16><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);
-    else if (d->y_dtype == CLSKD_F32)
-      tapconv_fwd_smallk_kernel<__nv_bfloat16, float><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);
-    else
-      tapconv_fwd_smallk_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);
+    const bool small = total + (int64_t)blocks * 256 < 4000000000LL;
+#define LAUNCH_SK(TX, TY)                                                                                \
+  do {                                                                                                   \
+    if (small) tapconv_fwd_smallk_kernel<TX, TY, unsigned><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk); \
+    else tapconv_fwd_smallk_kernel<TX, TY, int64_t><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);     \
+  } while (0)
+    if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32) LAUNCH_SK(float, float);
+    else if (d->x_dtype == CLSKD_F32) LAUNCH_SK(float, __nv_bfloat16);
+    else if (d->y_dtype == CLSKD_F32) LAUNCH_SK(__nv_bfloat16, float);
+    else LAUNCH_SK(__nv_bfloat16, __nv_bfloat16);
+#undef LAUNCH_SK
     CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(smallk)");
     return CLSKD_OK;
   }
