@@ -378,39 +378,47 @@ __global__ void __launch_bounds__(256) tapconv_fwd_n2_kernel(ClskdTapConv d, N2G
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   TY* y = reinterpret_cast<TY*>(d.y);
-  for (int64_t m0 = warp0 * rpw; m0 < M; m0 += nwarps * rpw) {
-    const int64_t m = m0 + sub;
-    const bool live = m < M;
-    const int64_t mm = live ? m : 0;
-    int b, t, f;
-    row_decode(mm, d.To, d.Fo, b, t, f);
-    float a0 = 0.f, a1 = 0.f;
-    if (live) {
+  constexpr int RB = (UPL == 1) ? 4 : (UPL == 2 ? 2 : 1);   // rows in flight per lane group
+  for (int64_t m0 = warp0 * rpw * RB; m0 < M; m0 += nwarps * rpw * RB) {
+    float x[RB][UPL][8];
+    bool ok[RB][UPL];
+    int rb[RB], rt[RB], rf[RB];
+    bool live[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const int64_t m = m0 + (int64_t)q * rpw + sub;
+      live[q] = m < M;
+      row_decode(live[q] ? m : 0, d.To, d.Fo, rb[q], rt[q], rf[q]);
+#pragma unroll
+      for (int i = 0; i < UPL; ++i) ok[q][i] = live[q] && un.load(d, i, rb[q], rt[q], rf[q], x[q][i]);
+    }
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int i = 0; i < UPL; ++i) {
-        float x[8];
-        if (un.load(d, i, b, t, f, x)) {
+        if (ok[q][i]) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            a0 = fmaf(x[e], wr[i][e][0], a0);
-            a1 = fmaf(x[e], wr[i][e][1], a1);
+            a0 = fmaf(x[q][i][e], wr[i][e][0], a0);
+            a1 = fmaf(x[q][i][e], wr[i][e][1], a1);
           }
         }
       }
-    }
-    for (int o = g.up2 >> 1; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    }
-    if (live && ul == 0) {
-      TY* yp = y + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF;
-      float v0 = a0 + b0, v1 = a1 + b1;
-      if (d.accumulate) {
-        v0 += ld_f(yp);
-        if (d.N > 1) v1 += ld_f(yp + 1);
+      for (int o = g.up2 >> 1; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
       }
-      st_f(yp, v0);
-      if (d.N > 1) st_f(yp + 1, v1);
+      if (live[q] && ul == 0) {
+        TY* yp = y + (int64_t)rb[q] * d.y_sB + (int64_t)rt[q] * d.y_sT + (int64_t)rf[q] * d.y_sF;
+        float v0 = a0 + b0, v1 = a1 + b1;
+        if (d.accumulate) {
+          v0 += ld_f(yp);
+          if (d.N > 1) v1 += ld_f(yp + 1);
+        }
+        st_f(yp, v0);
+        if (d.N > 1) st_f(yp + 1, v1);
+      }
     }
   }
 }
@@ -419,8 +427,8 @@ __global__ void __launch_bounds__(256) tapconv_fwd_n2_kernel(ClskdTapConv d, N2G
 // 8-channel units of ONE tap (cpt <= 128 -> at most 4 units per lane), the tap loop is in the
 // kernel and the weights sit in shared memory transposed to [tap][e][unit] so that a warp's loads
 // are conflict free.
-template <typename TX, typename TY>
-__global__ void __launch_bounds__(256) tapconv_fwd_n2_taps_kernel(ClskdTapConv d, int cpt) {
+template <typename TX, typename TY, int TB>
+__global__ void __launch_bounds__(256) tapconv_fwd_n2_taps_kernel(ClskdTapConv d, int cpt, int up2) {
   extern __shared__ float2 w2[];   // [ntaps][8][cpt]
   const int Ctot = d.c0 + d.c1;
   const float* w = reinterpret_cast<const float*>(d.w);
@@ -431,6 +439,7 @@ __global__ void __launch_bounds__(256) tapconv_fwd_n2_taps_kernel(ClskdTapConv d
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int ul = lane & (up2 - 1), sub = lane / up2, rpw = 32 / up2;   // up2 lanes share a row
   const float b0 = d.bias ? d.bias[0] : 0.f;
   const float b1 = (d.bias && d.N > 1) ? d.bias[1] : 0.f;
   const int64_t M = (int64_t)d.B * d.To * d.Fo;
@@ -439,32 +448,50 @@ __global__ void __launch_bounds__(256) tapconv_fwd_n2_taps_kernel(ClskdTapConv d
   const TX* x0 = reinterpret_cast<const TX*>(d.x0);
   const TX* x1 = reinterpret_cast<const TX*>(d.x1);
   TY* y = reinterpret_cast<TY*>(d.y);
-  for (int64_t m = warp0; m < M; m += nwarps) {
+  for (int64_t m0 = warp0 * rpw; m0 < M; m0 += nwarps * rpw) {
+    const int64_t m = m0 + sub;
+    const bool live = m < M;
     int b, t, f;
-    row_decode(m, d.To, d.Fo, b, t, f);
+    row_decode(live ? m : 0, d.To, d.Fo, b, t, f);
     float a0 = 0.f, a1 = 0.f;
-    for (int tap = 0; tap < d.ntaps; ++tap) {
-      const int ti = t + d.dt[tap], fi = f * d.sf + d.df[tap];
-      if (ti < 0 || ti >= d.Ti || fi < 0 || fi >= d.Fi) continue;    // warp-uniform
-      const TX* r0 = x0 + (int64_t)b * d.x0_sB + (int64_t)ti * d.x0_sT + (int64_t)fi * d.x0_sF;
-      const TX* r1 = d.c1 ? x1 + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF : nullptr;
-      for (int cu = lane; cu < cpt; cu += 32) {
-        const int c = cu * 8;
-        float xv[8];
-        if (c < d.c0) ld8(r0 + c, xv);
-        else ld8(r1 + (c - d.c0), xv);
-        const float2* wp = w2 + (size_t)tap * 8 * cpt + cu;
+    for (int cu = ul; cu < cpt; cu += up2) {          // the lane's units (same for every tap)
+      const int c = cu * 8;
+      const bool s1 = c >= d.c0;
+      for (int tap0 = 0; tap0 < d.ntaps; tap0 += TB) {
+        float xv[TB][8];
+        bool ok[TB];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float2 ww = wp[e * cpt];
-          a0 = fmaf(xv[e], ww.x, a0);
-          a1 = fmaf(xv[e], ww.y, a1);
+        for (int q = 0; q < TB; ++q) {                // TB taps' loads in flight together
+          const int tap = tap0 + q;
+          ok[q] = false;
+          if (live && tap < d.ntaps) {
+            const int ti = t + d.dt[tap], fi = f * d.sf + d.df[tap];
+            if (ti >= 0 && ti < d.Ti && fi >= 0 && fi < d.Fi) {
+              ok[q] = true;
+              if (s1) ld8(x1 + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF + (c - d.c0), xv[q]);
+              else ld8(x0 + (int64_t)b * d.x0_sB + (int64_t)ti * d.x0_sT + (int64_t)fi * d.x0_sF + c, xv[q]);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < TB; ++q) {
+          if (ok[q]) {
+            const float2* wp = w2 + (size_t)(tap0 + q) * 8 * cpt + cu;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float2 ww = wp[e * cpt];
+              a0 = fmaf(xv[q][e], ww.x, a0);
+              a1 = fmaf(xv[q][e], ww.y, a1);
+            }
+          }
         }
       }
     }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    if (lane == 0) {
+    for (int o = up2 >> 1; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (live && ul == 0) {
       TY* yp = y + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF;
       float v0 = a0 + b0, v1 = a1 + b1;
       if (d.accumulate) {
@@ -498,24 +525,34 @@ __global__ void __launch_bounds__(256) tapconv_wgrad_n2_kernel(ClskdTapConv d, N
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const TY* dy = reinterpret_cast<const TY*>(d.y);
-  for (int64_t m0 = warp0 * rpw; m0 < M; m0 += nwarps * rpw) {
-    const int64_t m = m0 + sub;
-    if (m >= M) continue;
-    int b, t, f;
-    row_decode(m, d.To, d.Fo, b, t, f);
-    const TY* yp = dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF;
-    const float g0 = ld_f(yp), g1 = d.N > 1 ? ld_f(yp + 1) : 0.f;
+  constexpr int RB = (UPL == 1) ? 4 : (UPL == 2 ? 2 : 1);   // rows in flight per lane group
+  for (int64_t m0 = warp0 * rpw * RB; m0 < M; m0 += nwarps * rpw * RB) {
+    float x[RB][UPL][8], g0[RB], g1[RB];
+    bool ok[RB][UPL];
 #pragma unroll
-    for (int i = 0; i < UPL; ++i) {
-      float x[8];
-      if (un.load(d, i, b, t, f, x)) {
+    for (int q = 0; q < RB; ++q) {
+      const int64_t m = m0 + (int64_t)q * rpw + sub;
+      const bool live = m < M;
+      int b, t, f;
+      row_decode(live ? m : 0, d.To, d.Fo, b, t, f);
+      const TY* yp = dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF;
+      g0[q] = live ? ld_f(yp) : 0.f;
+      g1[q] = (live && d.N > 1) ? ld_f(yp + 1) : 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          acc[i][e][0] = fmaf(x[e], g0, acc[i][e][0]);
-          acc[i][e][1] = fmaf(x[e], g1, acc[i][e][1]);
+      for (int i = 0; i < UPL; ++i) ok[q][i] = live && un.load(d, i, b, t, f, x[q][i]);
+    }
+#pragma unroll
+    for (int q = 0; q < RB; ++q)
+#pragma unroll
+      for (int i = 0; i < UPL; ++i) {
+        if (ok[q][i]) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[i][e][0] = fmaf(x[q][i][e], g0[q], acc[i][e][0]);
+            acc[i][e][1] = fmaf(x[q][i][e], g1[q], acc[i][e][1]);
+          }
         }
       }
-    }
   }
 #pragma unroll
   for (int i = 0; i < UPL; ++i) {
@@ -605,11 +642,15 @@ __global__ void __launch_bounds__(256) tapconv_fwd_smallk_kernel(ClskdTapConv d,
     const int f = (int)(m % (I)d.Fo);
     const I r = m / (I)d.Fo;
     const int t = (int)(r % (I)d.To), b = (int)(r / (I)d.To);
-    float acc[8];
+    float acc[8], xs[SK_MAXK];
+#pragma unroll
+    for (int k = 0; k < SK_MAXK; ++k) xs[k] = k < Ktot ? smallk_x<TX>(d, k, Ctot, b, t, f) : 0.f;   // all loads in flight
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = wsm[Ktot * N + n0 + e];
-    for (int k = 0; k < Ktot; ++k) {
-      const float xv = smallk_x<TX>(d, k, Ctot, b, t, f);
+#pragma unroll
+    for (int k = 0; k < SK_MAXK; ++k) {
+      if (k >= Ktot) break;
+      const float xv = xs[k];
       const float4 w0 = *reinterpret_cast<const float4*>(&wsm[k * N + n0]);
       const float4 w1 = *reinterpret_cast<const float4*>(&wsm[k * N + n0 + 4]);
       acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
@@ -644,19 +685,30 @@ __global__ void __launch_bounds__(256) tapconv_wgrad_smallk_kernel(ClskdTapConv 
   const int64_t M = (int64_t)d.B * d.To * d.Fo;
   const TY* dy = reinterpret_cast<const TY*>(d.y);
   if (sub < rows_par) {
-    for (int64_t m = (int64_t)blockIdx.x * rows_par + sub; m < M; m += (int64_t)gridDim.x * rows_par) {
-      int b, t, f;
-      row_decode(m, d.To, d.Fo, b, t, f);
-      float g[8];
-      ld8(dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF + n0, g);
+    constexpr int RB = 2;
+    for (int64_t m0 = (int64_t)blockIdx.x * rows_par * RB + sub; m0 < M; m0 += (int64_t)gridDim.x * rows_par * RB) {
+      float g[RB][8], xv[RB][8];
 #pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        if (a < kcnt) {
-          const float xv = smallk_x<TX>(d, k0 + a, Ctot, b, t, f);
+      for (int q = 0; q < RB; ++q) {
+        const int64_t m = m0 + (int64_t)q * rows_par;
+        const bool live = m < M;
+        int b, t, f;
+        row_decode(live ? m : 0, d.To, d.Fo, b, t, f);
+        if (live) {
+          ld8(dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF + n0, g[q]);
+        } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[a][e] = fmaf(xv, g[e], acc[a][e]);
+          for (int e = 0; e < 8; ++e) g[q][e] = 0.f;
         }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) xv[q][a] = (live && a < kcnt) ? smallk_x<TX>(d, k0 + a, Ctot, b, t, f) : 0.f;
       }
+#pragma unroll
+      for (int q = 0; q < RB; ++q)
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[a][e] = fmaf(xv[q][a], g[q][e], acc[a][e]);
     }
 #pragma unroll
     for (int a = 0; a < 8; ++a)
@@ -722,25 +774,29 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   N2Geom g2;
   if (n2_ok(d, &g2) && g2.U > 128) {
-    int64_t blocks = (M + 7) / 8 / 4;
+    int tup2 = 1;                                     // lanes per row: power of two covering cpt, <= 32
+    while (tup2 < g2.cpt && tup2 < 32) tup2 <<= 1;
+    int64_t blocks = (M / (32 / tup2) + 7) / 8 / 4;
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
     if (blocks < 1) blocks = 1;
     const size_t sh = sizeof(float2) * (size_t)d->ntaps * 8 * g2.cpt;   // <= 16 taps * 8 * 128 * 8 B = 128 KB
     if (sh <= 46 * 1024) {
       if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32)
-        tapconv_fwd_n2_taps_kernel<float, float><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt);
+        tapconv_fwd_n2_taps_kernel<float, float, 3><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt, tup2);
       else if (d->x_dtype == CLSKD_F32)
-        tapconv_fwd_n2_taps_kernel<float, __nv_bfloat16><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt);
+        tapconv_fwd_n2_taps_kernel<float, __nv_bfloat16, 3><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt, tup2);
       else if (d->y_dtype == CLSKD_F32)
-        tapconv_fwd_n2_taps_kernel<__nv_bfloat16, float><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt);
+        tapconv_fwd_n2_taps_kernel<__nv_bfloat16, float, 3><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt, tup2);
       else
-        tapconv_fwd_n2_taps_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt);
+        tapconv_fwd_n2_taps_kernel<__nv_bfloat16, __nv_bfloat16, 3><<<(unsigned)blocks, 256, sh, st>>>(*d, g2.cpt, tup2);
       CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(n2 taps)");
       return CLSKD_OK;
     }
   } else if (n2_ok(d, &g2)) {
     const int upl = cdiv(g2.U, g2.up2);   // 1, 2, 3 or 4 units per lane
-    const int64_t warps_needed = (M + (32 / g2.up2) - 1) / (32 / g2.up2);
+    const int rbat = upl <= 1 ? 4 : (upl == 2 ? 2 : 1);
+    const int64_t rows_per_warp_iter = (int64_t)(32 / g2.up2) * rbat;
+    const int64_t warps_needed = (M + rows_per_warp_iter - 1) / rows_per_warp_iter;
     int64_t blocks = (warps_needed + 7) / 8 / 4;
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
     if (blocks < 1) blocks = 1;
