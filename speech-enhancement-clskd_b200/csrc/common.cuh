@@ -109,6 +109,12 @@ bool att_blend_bwd(const void* x, const void* y, int dtype, const float* z, cons
                    void* dx, void* dy, float* dz, cudaStream_t st);
 }  // namespace vec
 
+// pointwise (1x1, dense) fast paths of the tap-list contraction (pointwise.cu); true = handled
+namespace pw {
+bool try_fwd(const ClskdTapConv* d, cudaStream_t st);
+bool try_wgrad(const ClskdTapConv* d, cudaStream_t st);
+}  // namespace pw
+
 // dispatch on a runtime dtype tag
 #define CLSKD_DISPATCH_DTYPE(tag, T, ...)                         \
   do {                                                            \

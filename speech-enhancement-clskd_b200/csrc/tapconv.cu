@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) tapconv_fwd_n2_kernel(ClskdTapConv d, N2G
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   TY* y = reinterpret_cast<TY*>(d.y);
-  constexpr int RB = (UPL == 1) ? 4 : (UPL == 2 ? 2 : 1);   // rows in flight per lane group
+  constexpr int RB = 1;   // rows per lane group and iteration (batching rows measured slower: the row index math dominates)
   for (int64_t m0 = warp0 * rpw * RB; m0 < M; m0 += nwarps * rpw * RB) {
     float x[RB][UPL][8];
     bool ok[RB][UPL];
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(256) tapconv_wgrad_n2_kernel(ClskdTapConv d, N
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const TY* dy = reinterpret_cast<const TY*>(d.y);
-  constexpr int RB = (UPL == 1) ? 4 : (UPL == 2 ? 2 : 1);   // rows in flight per lane group
+  constexpr int RB = 1;   // rows per lane group and iteration (batching rows measured slower: the row index math dominates)
   for (int64_t m0 = warp0 * rpw * RB; m0 < M; m0 += nwarps * rpw * RB) {
     float x[RB][UPL][8], g0[RB], g1[RB];
     bool ok[RB][UPL];
@@ -642,15 +642,11 @@ __global__ void __launch_bounds__(256) tapconv_fwd_smallk_kernel(ClskdTapConv d,
     const int f = (int)(m % (I)d.Fo);
     const I r = m / (I)d.Fo;
     const int t = (int)(r % (I)d.To), b = (int)(r / (I)d.To);
-    float acc[8], xs[SK_MAXK];
-#pragma unroll
-    for (int k = 0; k < SK_MAXK; ++k) xs[k] = k < Ktot ? smallk_x<TX>(d, k, Ctot, b, t, f) : 0.f;   // all loads in flight
+    float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = wsm[Ktot * N + n0 + e];
-#pragma unroll
-    for (int k = 0; k < SK_MAXK; ++k) {
-      if (k >= Ktot) break;
-      const float xv = xs[k];
+    for (int k = 0; k < Ktot; ++k) {
+      const float xv = smallk_x<TX>(d, k, Ctot, b, t, f);
       const float4 w0 = *reinterpret_cast<const float4*>(&wsm[k * N + n0]);
       const float4 w1 = *reinterpret_cast<const float4*>(&wsm[k * N + n0 + 4]);
       acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
@@ -772,6 +768,10 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
   int64_t M = (int64_t)d->B * d->To * d->Fo;
   if (M == 0) return CLSKD_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pw::try_fwd(d, st)) {
+    CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(pointwise)");
+    return CLSKD_OK;
+  }
   N2Geom g2;
   if (n2_ok(d, &g2) && g2.U > 128) {
     int tup2 = 1;                                     // lanes per row: power of two covering cpt, <= 32
@@ -794,7 +794,7 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
     }
   } else if (n2_ok(d, &g2)) {
     const int upl = cdiv(g2.U, g2.up2);   // 1, 2, 3 or 4 units per lane
-    const int rbat = upl <= 1 ? 4 : (upl == 2 ? 2 : 1);
+    const int rbat = 1;
     const int64_t rows_per_warp_iter = (int64_t)(32 / g2.up2) * rbat;
     const int64_t warps_needed = (M + rows_per_warp_iter - 1) / rows_per_warp_iter;
     int64_t blocks = (warps_needed + 7) / 8 / 4;
@@ -864,6 +864,10 @@ extern "C" int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream) {
     }
   }
   if (M == 0) return CLSKD_OK;
+  if (pw::try_wgrad(d, st)) {
+    CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad(pointwise)");
+    return CLSKD_OK;
+  }
   N2Geom g2;
   if (n2_ok(d, &g2) && M >= 1024 && g2.U > 128) {
     // many taps: one pass over the rows per group of taps whose units fit the register budget

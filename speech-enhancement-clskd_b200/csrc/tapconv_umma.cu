@@ -12,9 +12,11 @@
 // [tap][n][c] (K-major).  Both operands land in 128/64/32-byte swizzled K-major shared memory and
 // are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16 per instruction) issued by one thread.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2-5 = epilogue (tcgen05.ld -> bias -> bf16/fp32 -> global).  Two CTAs are resident per
-// SM (<=3-4 stages each) so one CTA's epilogue overlaps the other's main loop.
+// Persistent: one CTA per SM loops over its tiles.  Warp roles (192 threads): warp 0 = TMA
+// producer (runs ahead across tiles through the shared-memory ring), warp 1 = TMEM allocator + MMA
+// issuer, warps 2-5 = epilogue (tcgen05.ld -> bias -> bf16/fp32 -> global).  The accumulator is
+// double-buffered in TMEM (2 x BLOCK_N <= 512 columns), so the epilogue of tile i overlaps the main
+// loop of tile i+1, and barrier/TMEM set-up is paid once per CTA instead of once per tile.
 #include "umma.cuh"
 
 namespace clskd {
@@ -44,76 +46,74 @@ struct UmmaParams {
   int y_dtype;
   const float* bias;
   int N;
+  int num_tiles;
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   // 1024-byte aligned operand ring
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~(uintptr_t)1023);
   const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile decode
-  const int tile = blockIdx.x;
-  const int n_tile = tile % p.tiles_n;
-  int r = tile / p.tiles_n;
-  const int f_blk = r % p.f_tiles;
-  r /= p.f_tiles;
-  const int t_blk = r % p.t_tiles;
-  const int b = r / p.t_tiles;
-  const int t0 = t_blk * p.t_tile, f0 = f_blk * p.fo_tile, n0 = n_tile * p.block_n;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);     // every epilogue thread arrives
+    }
+    fence_barrier_init();
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(&tmem_base_smem)),
-                 "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-
   const int num_k = p.ntaps * p.chunks_tot;
 
+  // persistent: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (n tile fastest, so
+  // consecutive CTAs share the activation patch in L2)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < num_k; ++it) {
-        const int tap = it / p.chunks_tot;
-        const int ch = it - tap * p.chunks_tot;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], p.tx_bytes);
-        uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
-        uint8_t* b_dst = a_dst + p.a_bytes;
-        const bool src0 = ch < p.chunks0;
-        const int cc = (src0 ? ch : ch - p.chunks0) * p.block_k;
-        tma_load_5d(a_dst, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.tap_p[tap],
-                    f0 + p.tap_f[tap], t0 + p.tap_t[tap], b);
-        tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * p.block_k, n0, tap);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.tiles_n;
+        int r = tile / p.tiles_n;
+        const int f_blk = r % p.f_tiles;
+        r /= p.f_tiles;
+        const int t_blk = r % p.t_tiles;
+        const int b = r / p.t_tiles;
+        const int t0 = t_blk * p.t_tile, f0 = f_blk * p.fo_tile, n0 = n_tile * p.block_n;
+        for (int it = 0; it < num_k; ++it) {
+          const int tap = it / p.chunks_tot;
+          const int ch = it - tap * p.chunks_tot;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+          uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
+          uint8_t* b_dst = a_dst + p.a_bytes;
+          const bool src0 = ch < p.chunks0;
+          const int cc = (src0 ? ch : ch - p.chunks0) * p.block_k;
+          tma_load_5d(a_dst, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.tap_p[tap],
+                      f0 + p.tap_f[tap], t0 + p.tap_t[tap], b);
+          tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * p.block_k, n0, tap);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -126,25 +126,32 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       const int ksteps = p.block_k / 16;
-      for (int it = 0; it < num_k; ++it) {
-        mbar_wait(&full_bar[stage], phase);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
-        const uint32_t b_addr = a_addr + p.a_bytes;
-        const uint64_t adesc = make_smem_desc(a_addr, p.sbo, p.layout_type);
-        const uint64_t bdesc = make_smem_desc(b_addr, p.sbo, p.layout_type);
-        for (int k = 0; k < ksteps; ++k) {
-          // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                    (it | k) ? 1u : 0u);
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        mbar_wait(&tmem_empty_bar[as], ((local >> 1) & 1) ^ 1u);   // epilogue drained this accumulator
+        fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)(as * p.block_n);
+        for (int it = 0; it < num_k; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          fence_after();
+          const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_bytes;
+          const uint64_t adesc = make_smem_desc(a_addr, p.sbo, p.layout_type);
+          const uint64_t bdesc = make_smem_desc(b_addr, p.sbo, p.layout_type);
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
+            umma_bf16(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                      (it | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        umma_commit(&tmem_full_bar[as]);
       }
-      umma_commit(&tmem_full_bar);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -152,52 +159,59 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int row = q * 32 + lane;        // row of the 128-row tile
     const int t_local = row / p.fo_tile;
     const int f_local = row - t_local * p.fo_tile;
-    const int t = t0 + t_local, f = f0 + f_local;
-    const bool valid = t < p.To && f < p.Fo;
-    mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t yoff = (int64_t)b * p.y_sB + (int64_t)t * p.y_sT + (int64_t)f * p.y_sF + n0;
-    for (int c = 0; c < p.block_n; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      float o[16];
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const int n_tile = tile % p.tiles_n;
+      int r = tile / p.tiles_n;
+      const int f_blk = r % p.f_tiles;
+      r /= p.f_tiles;
+      const int t_blk = r % p.t_tiles;
+      const int b = r / p.t_tiles;
+      const int t = t_blk * p.t_tile + t_local, f = f_blk * p.fo_tile + f_local, n0 = n_tile * p.block_n;
+      const bool valid = t < p.To && f < p.Fo;
+      mbar_wait(&tmem_full_bar[as], (local >> 1) & 1);
+      fence_after();
+      const int64_t yoff = (int64_t)b * p.y_sB + (int64_t)t * p.y_sT + (int64_t)f * p.y_sF + n0;
+      for (int c = 0; c < p.block_n; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c), v);
+        float o[16];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
-      if (p.bias) {
+        for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+        if (p.bias) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
-      }
-      if (valid) {
-        if (p.y_dtype == CLSKD_BF16) {
-          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c;
-          uint32_t pk[8];
+          for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
+        }
+        if (valid) {
+          if (p.y_dtype == CLSKD_BF16) {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c;
+            uint32_t pk[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int e = 0; e < 8; ++e) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            reinterpret_cast<uint4*>(yp)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            reinterpret_cast<uint4*>(yp)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+            float* yp = reinterpret_cast<float*>(p.y) + yoff + c;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              reinterpret_cast<float4*>(yp)[e] =
+                  make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
           }
-          reinterpret_cast<uint4*>(yp)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          reinterpret_cast<uint4*>(yp)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        } else {
-          float* yp = reinterpret_cast<float*>(p.y) + yoff + c;
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            reinterpret_cast<float4*>(yp)[e] =
-                make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
         }
       }
+      fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
     }
   }
 
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  fence_before();
   __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(p.tmem_cols)
-                 : "memory");
-  }
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
-
 
 // dense source check + geometry; returns nullptr if supported, else a reason
 const char* umma_unsupported(const ClskdTapConv* d) {
@@ -205,7 +219,7 @@ const char* umma_unsupported(const ClskdTapConv* d) {
   const int Ctot = d->c0 + d->c1;
   if (Ctot % 16 || d->c0 % 16) return "channels must be multiples of 16";
   if (d->N % 16) return "N must be a multiple of 16";
-  if (d->N > 128 && d->N % 128) return "N > 128 must be a multiple of 128";
+  if (d->N > 256 && d->N % 128) return "N > 256 must be a multiple of 128";
   if (d->sf != 1 && d->sf != 2) return "sf must be 1 or 2";
   if (!is_pow2(d->Fo) || (d->Fo > 128 && d->Fo % 128)) return "Fo must be a power of two";
   if (d->accumulate) return "accumulate unsupported";
@@ -257,7 +271,7 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   p.t_tile = UM / p.fo_tile;
   p.f_tiles = d->Fo / p.fo_tile;
   p.t_tiles = cdiv(d->To, p.t_tile);
-  p.block_n = d->N <= 128 ? d->N : 128;
+  p.block_n = d->N <= 256 ? d->N : (d->N % 256 == 0 ? 256 : 128);
   p.tiles_n = d->N / p.block_n;
   // largest K chunk that divides both sources
   int bk = 64;
@@ -283,14 +297,14 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   else if (bk == 32) { p.layout_type = 4; sw = CU_TENSOR_MAP_SWIZZLE_64B; }
   else { p.layout_type = 6; sw = CU_TENSOR_MAP_SWIZZLE_32B; }
   int cols = 32;
-  while (cols < p.block_n) cols <<= 1;
+  while (cols < 2 * p.block_n) cols <<= 1;     // double-buffered accumulator
   p.tmem_cols = (uint32_t)cols;
   const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-  int stages = (int)((100 * 1024) / stage_bytes);
+  int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   const int num_k = p.ntaps * p.chunks_tot;
-  if (stages > num_k) stages = num_k < 1 ? 1 : num_k;
+  // (the ring runs ahead across tiles of the persistent loop, so it is not limited by num_k)
   p.stages = stages;
   p.y = d->y; p.y_sB = d->y_sB; p.y_sT = d->y_sT; p.y_sF = d->y_sF; p.y_dtype = d->y_dtype;
   p.bias = d->bias; p.N = d->N;
@@ -318,6 +332,7 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   }
   const int64_t tiles = (int64_t)d->B * p.t_tiles * p.f_tiles * p.tiles_n;
   CLSKD_CHECK_ARG(tiles <= 2147483647LL, "clskd_tapconv_fwd_umma: too many tiles");
+  p.num_tiles = (int)tiles;
   size_t smem = (size_t)stages * stage_bytes + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -326,7 +341,8 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
     if (e != cudaSuccess) { set_error("clskd_tapconv_fwd_umma: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
     smem_set = smem;
   }
-  tapconv_umma_kernel<<<(unsigned)tiles, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, p);
+  const unsigned grid = (unsigned)(tiles < (int64_t)sm_count() ? tiles : (int64_t)sm_count());
+  tapconv_umma_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, p);
   CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd_umma");
   return CLSKD_OK;
 }
