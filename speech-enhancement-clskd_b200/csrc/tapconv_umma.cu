@@ -47,11 +47,16 @@ struct UmmaParams {
   const float* bias;
   int N;
   int num_tiles;
+  // epilogue staging for the TMA store: sub-tiles of gw_y columns, [128 rows][gw_y] each, swizzled
+  int gw_y, es;                // columns per sub-tile, bytes per output element
+  uint32_t y_sub_bytes;        // 128 * gw_y * es
+  uint32_t stage_region;       // bytes of the operand ring (staging buffer follows it)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                    const __grid_constant__ CUtensorMap tmB, const UmmaParams p) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+                    const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
@@ -155,10 +160,14 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers (+bias, ->bf16/fp32) -> swizzled shared-memory staging -> TMA store: every
+    // global write is a full coalesced box; rows beyond To are clipped by the tensor map.
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;        // row of the 128-row tile
-    const int t_local = row / p.fo_tile;
-    const int f_local = row - t_local * p.fo_tile;
+    uint8_t* stg = ring + p.stage_region;
+    const uint32_t pitch = (uint32_t)(p.gw_y * p.es);          // 128 / 64 / 32 bytes
+    const uint32_t xr = pitch == 128 ? (uint32_t)(row & 7) : (pitch == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1));
+    const bool issuer = (threadIdx.x == 64);                    // first epilogue thread
     int local = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
@@ -168,11 +177,12 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       r /= p.f_tiles;
       const int t_blk = r % p.t_tiles;
       const int b = r / p.t_tiles;
-      const int t = t_blk * p.t_tile + t_local, f = f_blk * p.fo_tile + f_local, n0 = n_tile * p.block_n;
-      const bool valid = t < p.To && f < p.Fo;
+      const int n0 = n_tile * p.block_n;
       mbar_wait(&tmem_full_bar[as], (local >> 1) & 1);
       fence_after();
-      const int64_t yoff = (int64_t)b * p.y_sB + (int64_t)t * p.y_sT + (int64_t)f * p.y_sF + n0;
+      // the previous tile's TMA store must have finished reading the staging buffer
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = 0; c < p.block_n; c += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c), v);
@@ -183,29 +193,44 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
           for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
         }
-        if (valid) {
-          if (p.y_dtype == CLSKD_BF16) {
-            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c;
-            uint32_t pk[8];
+        const int sub = c / p.gw_y, col = c - sub * p.gw_y;
+        uint8_t* rowp = stg + (size_t)sub * p.y_sub_bytes + (size_t)row * pitch;
+        const uint32_t ch0 = (uint32_t)(col * p.es) >> 4;          // first 16-byte chunk of these 16 columns
+        if (p.es == 2) {
+          uint32_t pk[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            reinterpret_cast<uint4*>(yp)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            reinterpret_cast<uint4*>(yp)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-            float* yp = reinterpret_cast<float*>(p.y) + yoff + c;
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              reinterpret_cast<float4*>(yp)[e] =
-                  make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+          for (int e = 0; e < 8; ++e) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
           }
+          *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ xr) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ xr) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            *reinterpret_cast<float4*>(rowp + (((ch0 + e) ^ xr) << 4)) =
+                make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
         }
       }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
       fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
+      // make the generic-proxy smem writes visible to the async proxy, then one thread stores
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+        const int t0 = t_blk * p.t_tile, f0 = f_blk * p.fo_tile;
+        for (int sidx = 0; sidx < p.block_n / p.gw_y; ++sidx) {
+          asm volatile(
+              "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                  reinterpret_cast<uint64_t>(&tmY)),
+              "r"(smem_u32(stg + (size_t)sidx * p.y_sub_bytes)), "r"(n0 + sidx * p.gw_y), "r"(f0), "r"(t0), "r"(b)
+              : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
   }
 
   fence_before();
@@ -296,11 +321,24 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   if (bk == 64) { p.layout_type = 2; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
   else if (bk == 32) { p.layout_type = 4; sw = CU_TENSOR_MAP_SWIZZLE_64B; }
   else { p.layout_type = 6; sw = CU_TENSOR_MAP_SWIZZLE_32B; }
+  p.es = d->y_dtype == CLSKD_BF16 ? 2 : 4;
+  if (p.es == 4 && p.block_n > 128) {          // keep the fp32 staging tile <= 64 KB
+    p.block_n = 128;
+    p.tiles_n = d->N / p.block_n;
+  }
+  {
+    const int max_gw = 128 / p.es;             // 64 bf16 or 32 fp32 columns per 128-byte swizzle row
+    int gw = max_gw;
+    while (gw > 16 && p.block_n % gw) gw >>= 1;   // >= 16 columns: one tcgen05.ld chunk never straddles sub-tiles
+    p.gw_y = gw;
+  }
+  p.y_sub_bytes = (uint32_t)UM * p.gw_y * p.es;
   int cols = 32;
   while (cols < 2 * p.block_n) cols <<= 1;     // double-buffered accumulator
   p.tmem_cols = (uint32_t)cols;
   const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const uint32_t staging_bytes = (uint32_t)UM * p.block_n * p.es;
+  int stages = (int)((200 * 1024 - staging_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   const int num_k = p.ntaps * p.chunks_tot;
@@ -333,7 +371,19 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   const int64_t tiles = (int64_t)d->B * p.t_tiles * p.f_tiles * p.tiles_n;
   CLSKD_CHECK_ARG(tiles <= 2147483647LL, "clskd_tapconv_fwd_umma: too many tiles");
   p.num_tiles = (int)tiles;
-  size_t smem = (size_t)stages * stage_bytes + 1024;
+  p.stage_region = (uint32_t)stages * stage_bytes;
+  CUtensorMap tmY;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->Fo, (cuuint64_t)d->To, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->y_sF * p.es, (cuuint64_t)d->y_sT * p.es, (cuuint64_t)d->y_sB * p.es};
+    cuuint32_t box[4] = {(cuuint32_t)p.gw_y, (cuuint32_t)p.fo_tile, (cuuint32_t)p.t_tile, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmY, p.es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->y,
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(p.gw_y * p.es),
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(y) failed: %d", (int)r); return CLSKD_ERR_CUDA; }
+  }
+  size_t smem = (size_t)stages * stage_bytes + staging_bytes + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(tapconv_umma_kernel,
@@ -342,7 +392,7 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
     smem_set = smem;
   }
   const unsigned grid = (unsigned)(tiles < (int64_t)sm_count() ? tiles : (int64_t)sm_count());
-  tapconv_umma_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, p);
+  tapconv_umma_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmY, p);
   CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd_umma");
   return CLSKD_OK;
 }
