@@ -288,6 +288,22 @@ int clskd_att_blend_fwd(const void* x, const void* y, int dtype, const float* z,
 int clskd_att_blend_bwd(const void* x, const void* y, int dtype, const float* z, const void* dout,
                         int64_t M, int C, void* dx, void* dy, float* dz, void* stream);
 
+/* Tap-in-channel decomposition of a convolution-like layer with very few output channels (ABF's
+ * 3x3 conv onto the 2-channel mask map; the last, mask-producing transposed conv of the decoder):
+ * a pointwise GEMM first produces, at every INPUT position, the contribution to each (tap, n) pair
+ * as channels z[.., j*N+n]; these kernels then gather-sum the taps into the output grid
+ *     y[b,t,f,n] = bias[n] + sum_j z[b, t+dt[j], (f+df[j])/sf, j*N+n]
+ * (terms with (f+df[j]) not divisible by sf, or outside [0,Ti)x[0,Fi), are absent: sf = 1 is a
+ * stride-1 "same" conv, sf = 2 the sub-pixel structure of a stride-2 transposed conv), and scatter
+ * the gradient back  dz[b,ti,fi,j*N+n] = dy[b, ti-dt[j], fi*sf-df[j], n]  (channels >= ntaps*N of dz
+ * are zero).  z/dz are dense [B,Ti,Fi,Zc], y/dy dense [B,To,Fo,N]; dt_host/df_host are HOST arrays. */
+int clskd_tapsum_fwd(const void* z, int z_dtype, int B, int Ti, int Fi, int To, int Fo, int sf, int Zc,
+                     int ntaps, const int32_t* dt_host, const int32_t* df_host, int N,
+                     const float* bias, void* y, int y_dtype, void* stream);
+int clskd_tapsum_bwd(const void* dy, int dy_dtype, int B, int Ti, int Fi, int To, int Fo, int sf, int Zc,
+                     int ntaps, const int32_t* dt_host, const int32_t* df_host, int N, void* dz,
+                     int dz_dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * hcl (framework.py:287-306): adaptive average pooling of a dense [B,T,F,C] map to (l,l) per
  * channel over the logical (H=F, W=T) plane -> out [B, C, l, l] fp32.

@@ -198,7 +198,47 @@ class RealConv2d(nn.Module):
                                         t_extra=2 * self.padding[1])
         return self._plans[key]
 
+    def _narrow_plan(self):
+        """Tap-in-channel decomposition (tensor-core policy): a k x k "same" conv onto <= 2 channels
+        becomes a pointwise GEMM onto ntaps*N (zero-padded to a multiple of 16) channels, one per
+        (tap, n) pair, followed by a 9-point gather-sum; every pass then reads its input once."""
+        dev = self.weight.device
+        key = (dev, "narrow")
+        if key not in self._plans:
+            KF, KT = self.kernel_size
+            N, C = self.out_channels, self.in_channels
+            ntaps = KF * KT
+            Zc = (ntaps * N + 15) // 16 * 16
+            code = _codes(tuple(self.weight.shape), 0)                 # [N, C, KF, KT]
+            blk = np.full((C, Zc), -1, dtype=np.int64)
+            dts, dfs = [], []
+            j = 0
+            for kf in range(KF):
+                for kt in range(KT):
+                    for n in range(N):
+                        blk[:, j * N + n] = code[n, :, kf, kt]
+                    dts.append(kt - self.padding[1])
+                    dfs.append(kf - self.padding[0])
+                    j += 1
+            plan = ConvPlan("conv", blk[None, None], 1, 0, 0, C, 0, None, self.weight.numel(), 0, dev)
+            self._plans[key] = (plan, dts, dfs)
+        return self._plans[key]
+
+    def _use_narrow(self, x0, x1):
+        KF, KT = self.kernel_size
+        shape_ok = (x1 is None and self.bias is None and self.out_channels <= 2 and KF * KT > 1
+                    and KF * KT * self.out_channels <= 64 and KF == 2 * self.padding[0] + 1
+                    and KT == 2 * self.padding[1] + 1)
+        if ops.policy.narrow == "always":
+            return shape_ok
+        return (shape_ok and ops.policy.use_umma and self.in_channels % 16 == 0 and x0.dtype == torch.bfloat16)
+
     def forward_phys(self, x0, x1=None, out_dtype=None):
+        if self._use_narrow(x0, x1):
+            plan, dts, dfs = self._narrow_plan()
+            z = TapConvFn.apply(plan, x0, None, self.weight, None, None, None, x0.dtype)
+            return ops.TapSumFn.apply(z, dts, dfs, self.out_channels, (x0.shape[1], x0.shape[2]), 1,
+                                      out_dtype or x0.dtype, None, None, None)
         plan = self.plan(x0.shape[-1] if x1 is not None else None)
         return TapConvFn.apply(plan, x0, x1, self.weight, None, self.bias, None, out_dtype or x0.dtype)
 

@@ -28,6 +28,7 @@ class _Policy:
         self.name = "fp32"
         self.act_dtype = torch.float32
         self.use_umma = False
+        self.narrow = "auto"     # tap-in-channel decomposition of narrow convs: "auto" (tensor-core policy) / "always"
 
 
 policy = _Policy()
@@ -933,6 +934,52 @@ class AttBlendFn(torch.autograd.Function):
         call("clskd_att_blend_bwd", x.data_ptr(), y.data_ptr(), _tag(x.dtype), z.data_ptr(), g.data_ptr(), M, C,
              dx.data_ptr(), dy.data_ptr(), dz.data_ptr(), _stream())
         return dx, dy, dz
+
+
+class TapSumFn(torch.autograd.Function):
+    """y[b,t,f,n] = bias[n] + sum_j z[b, t+dt[j], (f+df[j])/sf, j*N+n]: the gather half of the
+    tap-in-channel decomposition of a narrow convolution (see clskd_tapsum_fwd in clskd.h).
+    `bias_plan` (a ConvPlan with a bias table) + bias_a / bias_b give the optional per-channel bias."""
+
+    @staticmethod
+    def forward(ctx, z, dts, dfs, N, out_size, sf, out_dtype, bias_plan, bias_a, bias_b):
+        B, Ti, Fi, Zc = z.shape
+        To, Fo = out_size
+        y = torch.empty((B, To, Fo, N), dtype=out_dtype, device=z.device)
+        n = len(dts)
+        dt = (ctypes.c_int32 * n)(*dts)
+        df = (ctypes.c_int32 * n)(*dfs)
+        bias = None
+        if bias_plan is not None and bias_a is not None:
+            bias = packed_weights(bias_plan._cache, "bias", lambda: bias_plan.bias_table, _f32c(bias_a),
+                                  _f32c(bias_b) if bias_b is not None else None, torch.float32)
+        call("clskd_tapsum_fwd", z.data_ptr(), _tag(z.dtype), B, Ti, Fi, To, Fo, sf, Zc, n, dt, df, N, _ptr(bias),
+             y.data_ptr(), _tag(y.dtype), _stream())
+        ctx.meta = (B, Ti, Fi, To, Fo, sf, Zc, dts, dfs, N, z.dtype)
+        ctx.bias_plan = bias_plan
+        ctx.has_bias = (bias_a is not None, bias_b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Ti, Fi, To, Fo, sf, Zc, dts, dfs, N, zdt = ctx.meta
+        g = dense(g)
+        dz = torch.empty((B, Ti, Fi, Zc), dtype=zdt, device=g.device)
+        n = len(dts)
+        dt = (ctypes.c_int32 * n)(*dts)
+        df = (ctypes.c_int32 * n)(*dfs)
+        call("clskd_tapsum_bwd", g.data_ptr(), _tag(g.dtype), B, Ti, Fi, To, Fo, sf, Zc, n, dt, df, N, dz.data_ptr(),
+             _tag(dz.dtype), _stream())
+        dba = dbb = None
+        plan = ctx.bias_plan
+        if plan is not None and (ctx.has_bias[0] or ctx.has_bias[1]):
+            s_, _ = colstats(g.view(-1, N))
+            s32 = f64_to_f32(s_)
+            if ctx.has_bias[0] and ctx.needs_input_grad[8]:
+                dba = unpack_grads(s32, plan.bias_unpack_a, plan.bias_unpack_a.shape[0])
+            if ctx.has_bias[1] and ctx.needs_input_grad[9]:
+                dbb = unpack_grads(s32, plan.bias_unpack_b, plan.bias_unpack_b.shape[0])
+        return dz, None, None, None, None, None, None, None, dba, dbb
 
 
 class SqDiffMeanFn(torch.autograd.Function):

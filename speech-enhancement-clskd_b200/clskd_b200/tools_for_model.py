@@ -264,8 +264,60 @@ class ComplexConvTranspose2d(nn.Module):
                                         t_extra=self.output_padding[1], f_extra=self.output_padding[0])
         return self._plans[key]
 
+    def _narrow_plan(self, ca):
+        """Tap-in-channel decomposition for a layer with ONE complex output channel (the mask-producing
+        last decoder layer): a pointwise GEMM onto (tap, real/imag) channels at every input position,
+        then the sub-pixel gather-sum of clskd_tapsum_fwd (sf = frequency stride)."""
+        dev = self.real_conv.weight.device
+        key = (dev, ca, "narrow")
+        if key not in self._plans:
+            full = self.plan(ca)                               # block codes incl. the skip permutation
+            KF, KT = self.kernel_size
+            N = 2 * self.out_channels
+            Zc = (KF * KT * N + 15) // 16 * 16
+            # recover the [KF,KT,Ctot,N] code block of the full plan from its forward launches
+            shape = tuple(self.real_conv.weight.shape)
+            cin = self.in_channels
+            cr = _codes(shape, 0).transpose(2, 3, 0, 1)
+            ci = _codes(shape, 1).transpose(2, 3, 0, 1)
+            block = _complex_block(cr, ci)
+            c0, c1 = 2 * cin, 0
+            if ca is not None:
+                perm = np.concatenate([np.arange(0, ca), cin + np.arange(0, ca),
+                                       np.arange(ca, cin), cin + np.arange(ca, cin)])
+                block = block[:, :, perm, :]
+                c0, c1 = 2 * ca, 2 * (cin - ca)
+            blk = np.full((2 * cin, Zc), -1, dtype=np.int64)
+            dts, dfs = [], []
+            j = 0
+            for kf in range(KF):
+                for kt in range(KT):
+                    blk[:, j * N:(j + 1) * N] = block[kf, kt]
+                    dts.append(self.padding[1] - kt)           # ti = to + pt - kt
+                    dfs.append(self.padding[0] - kf)           # fi = (fo + pf - kf) / sf
+                    j += 1
+            n = self.real_conv.weight.numel()
+            pw = ConvPlan("conv", blk[None, None], 1, 0, 0, c0, c1, None, n, n, dev)
+            self._plans[key] = (pw, dts, dfs, full)
+        return self._plans[key]
+
+    def _use_narrow(self, x0, x1):
+        ok = self.out_channels == 1 and self.kernel_size[0] * self.kernel_size[1] * 2 <= 64
+        if ops.policy.narrow == "always":
+            return ok
+        return (ok and ops.policy.use_umma and x0.dtype == torch.bfloat16 and x0.shape[-1] % 16 == 0
+                and (x1 is None or (x1.dtype == torch.bfloat16 and x1.shape[-1] % 16 == 0)))
+
     def forward_phys(self, x0, x1=None, out_dtype=None):
-        plan = self.plan(None if x1 is None else x0.shape[-1] // 2)
+        ca = None if x1 is None else x0.shape[-1] // 2
+        if self._use_narrow(x0, x1):
+            pw, dts, dfs, full = self._narrow_plan(ca)
+            z = TapConvFn.apply(pw, x0, x1, self.real_conv.weight, self.imag_conv.weight, None, None, x0.dtype)
+            To, Fo = full.out_size(x0.shape[1], x0.shape[2])
+            return ops.TapSumFn.apply(z, dts, dfs, 2 * self.out_channels, (To, Fo), self.stride[0],
+                                      out_dtype or ops.policy.act_dtype, full, self.real_conv.bias,
+                                      self.imag_conv.bias)
+        plan = self.plan(ca)
         return TapConvFn.apply(plan, x0, x1, self.real_conv.weight, self.imag_conv.weight,
                                self.real_conv.bias, self.imag_conv.bias, out_dtype or ops.policy.act_dtype)
 

@@ -288,6 +288,67 @@ __global__ void __launch_bounds__(PT) pw_wgrad_k_kernel(const TX* __restrict__ x
   for (int i = threadIdx.x; i < K * N; i += PT) atomicAdd(dw + i, red[i]);
 }
 
+// ------------------------------------------------------------------------------------------ tap sum
+struct TapList {
+  int n;
+  int dt[CLSKD_MAX_TAPS], df[CLSKD_MAX_TAPS];
+};
+
+template <typename TZ, typename TY>
+__global__ void __launch_bounds__(PT) tapsum_fwd_kernel(const TZ* __restrict__ z, int B, int Ti, int Fi, int To,
+                                                        int Fo, int sf, int Zc, TapList taps, int N,
+                                                        const float* __restrict__ bias, TY* __restrict__ y) {
+  const unsigned M = (unsigned)B * To * Fo;
+  for (unsigned m = blockIdx.x * PT + threadIdx.x; m < M; m += gridDim.x * PT) {
+    const unsigned r = m / (unsigned)Fo;
+    const int f = (int)(m - r * (unsigned)Fo);
+    const int b = (int)(r / (unsigned)To), t = (int)(r - (unsigned)b * (unsigned)To);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < taps.n; ++j) {
+      const int tt = t + taps.dt[j];
+      int ff = f + taps.df[j];
+      if (tt < 0 || tt >= Ti || ff < 0) continue;
+      if (sf > 1) {
+        if (ff % sf) continue;
+        ff /= sf;
+      }
+      if (ff >= Fi) continue;
+      const TZ* zp = z + (((int64_t)b * Ti + tt) * Fi + ff) * Zc + j * N;
+      for (int n = 0; n < N; ++n) acc[n] += ld_f(zp + n);
+    }
+    for (int n = 0; n < N; ++n) st_f(y + (int64_t)m * N + n, acc[n] + (bias ? bias[n] : 0.f));
+  }
+}
+
+// one thread per (input position, 8-channel group) of dz
+template <typename TD, typename TZ>
+__global__ void __launch_bounds__(PT) tapsum_bwd_kernel(const TD* __restrict__ dy, int B, int Ti, int Fi, int To,
+                                                        int Fo, int sf, int Zc, TapList taps, int N,
+                                                        TZ* __restrict__ dz) {
+  const unsigned gpr = (unsigned)Zc >> 3;
+  const unsigned total = (unsigned)B * Ti * Fi * gpr;
+  for (unsigned i = blockIdx.x * PT + threadIdx.x; i < total; i += gridDim.x * PT) {
+    const unsigned m = i / gpr;
+    const int c0 = (int)(i - m * gpr) * 8;
+    const unsigned r = m / (unsigned)Fi;
+    const int f = (int)(m - r * (unsigned)Fi);
+    const int b = (int)(r / (unsigned)Ti), t = (int)(r - (unsigned)b * (unsigned)Ti);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      const int j = c / N, n = c - j * N;
+      float v = 0.f;
+      if (j < taps.n) {
+        const int tt = t - taps.dt[j], ff = f * sf - taps.df[j];
+        if (tt >= 0 && tt < To && ff >= 0 && ff < Fo) v = ld_f(dy + (((int64_t)b * To + tt) * Fo + ff) * N + n);
+      }
+      o[e] = v;
+    }
+    st8(dz + (int64_t)m * Zc + c0, o);
+  }
+}
+
 inline bool al16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 
 // 1x1, stride 1, same extents, every operand dense over (B,T,F)
@@ -394,3 +455,55 @@ bool try_wgrad(const ClskdTapConv* d, cudaStream_t st) {
 
 }  // namespace pw
 }  // namespace clskd
+
+using namespace clskd;
+
+extern "C" int clskd_tapsum_fwd(const void* z, int z_dtype, int B, int Ti, int Fi, int To, int Fo, int sf, int Zc,
+                                int ntaps, const int32_t* dt_host, const int32_t* df_host, int N,
+                                const float* bias, void* y, int y_dtype, void* stream) {
+  CLSKD_CHECK_ARG(z && y && dt_host && df_host, "clskd_tapsum_fwd: null pointer");
+  CLSKD_CHECK_ARG(ntaps >= 1 && ntaps <= CLSKD_MAX_TAPS && N >= 1 && N <= 4 && ntaps * N <= Zc && sf >= 1,
+                  "clskd_tapsum_fwd: bad tap / channel counts");
+  const int64_t M = (int64_t)B * To * Fo;
+  CLSKD_CHECK_ARG(M < 4000000000LL && (int64_t)B * Ti * Fi * (Zc / 8 + 1) < 4000000000LL,
+                  "clskd_tapsum_fwd: tensor too large");
+  if (M == 0) return CLSKD_OK;
+  TapList tl;
+  tl.n = ntaps;
+  for (int j = 0; j < ntaps; ++j) { tl.dt[j] = dt_host[j]; tl.df[j] = df_host[j]; }
+  const int grid = pw_grid(M);
+  cudaStream_t st = (cudaStream_t)stream;
+#define L(TZ, TY) tapsum_fwd_kernel<TZ, TY><<<grid, PT, 0, st>>>((const TZ*)z, B, Ti, Fi, To, Fo, sf, Zc, tl, N, bias, (TY*)y)
+  if (z_dtype == CLSKD_F32 && y_dtype == CLSKD_F32) L(float, float);
+  else if (z_dtype == CLSKD_F32) L(float, __nv_bfloat16);
+  else if (y_dtype == CLSKD_F32) L(__nv_bfloat16, float);
+  else L(__nv_bfloat16, __nv_bfloat16);
+#undef L
+  CLSKD_CHECK_LAUNCH("clskd_tapsum_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_tapsum_bwd(const void* dy, int dy_dtype, int B, int Ti, int Fi, int To, int Fo, int sf, int Zc,
+                                int ntaps, const int32_t* dt_host, const int32_t* df_host, int N, void* dz,
+                                int dz_dtype, void* stream) {
+  CLSKD_CHECK_ARG(dy && dz && dt_host && df_host, "clskd_tapsum_bwd: null pointer");
+  CLSKD_CHECK_ARG(ntaps >= 1 && ntaps <= CLSKD_MAX_TAPS && N >= 1 && N <= 4 && ntaps * N <= Zc && Zc % 8 == 0 && sf >= 1,
+                  "clskd_tapsum_bwd: bad tap / channel counts");
+  CLSKD_CHECK_ARG(((uintptr_t)dz % 16) == 0, "clskd_tapsum_bwd: dz must be 16-byte aligned");
+  const int64_t M = (int64_t)B * Ti * Fi;
+  CLSKD_CHECK_ARG(M * (Zc / 8 + 1) < 4000000000LL, "clskd_tapsum_bwd: tensor too large");
+  if (M == 0) return CLSKD_OK;
+  TapList tl;
+  tl.n = ntaps;
+  for (int j = 0; j < ntaps; ++j) { tl.dt[j] = dt_host[j]; tl.df[j] = df_host[j]; }
+  const int grid = pw_grid(M * (Zc / 8));
+  cudaStream_t st = (cudaStream_t)stream;
+#define L(TD, TZ) tapsum_bwd_kernel<TD, TZ><<<grid, PT, 0, st>>>((const TD*)dy, B, Ti, Fi, To, Fo, sf, Zc, tl, N, (TZ*)dz)
+  if (dy_dtype == CLSKD_F32 && dz_dtype == CLSKD_F32) L(float, float);
+  else if (dy_dtype == CLSKD_F32) L(float, __nv_bfloat16);
+  else if (dz_dtype == CLSKD_F32) L(__nv_bfloat16, float);
+  else L(__nv_bfloat16, __nv_bfloat16);
+#undef L
+  CLSKD_CHECK_LAUNCH("clskd_tapsum_bwd");
+  return CLSKD_OK;
+}

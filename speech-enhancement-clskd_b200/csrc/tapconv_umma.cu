@@ -245,6 +245,7 @@ const char* umma_unsupported(const ClskdTapConv* d) {
   if (Ctot % 16 || d->c0 % 16) return "channels must be multiples of 16";
   if (d->N % 16) return "N must be a multiple of 16";
   if (d->N > 256 && d->N % 128) return "N > 256 must be a multiple of 128";
+  if (d->y_dtype != CLSKD_BF16 && d->N > 128 && d->N % 128) return "fp32 output: N > 128 must be a multiple of 128";
   if (d->sf != 1 && d->sf != 2) return "sf must be 1 or 2";
   if (!is_pow2(d->Fo) || (d->Fo > 128 && d->Fo % 128)) return "Fo must be a power of two";
   if (d->accumulate) return "accumulate unsupported";
@@ -297,6 +298,8 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   p.f_tiles = d->Fo / p.fo_tile;
   p.t_tiles = cdiv(d->To, p.t_tile);
   p.block_n = d->N <= 256 ? d->N : (d->N % 256 == 0 ? 256 : 128);
+  p.es = d->y_dtype == CLSKD_BF16 ? 2 : 4;
+  if (p.es == 4 && p.block_n > 128 && d->N % 128 == 0) p.block_n = 128;   // keep the fp32 staging tile <= 64 KB
   p.tiles_n = d->N / p.block_n;
   // largest K chunk that divides both sources
   int bk = 64;
@@ -321,11 +324,6 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   if (bk == 64) { p.layout_type = 2; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
   else if (bk == 32) { p.layout_type = 4; sw = CU_TENSOR_MAP_SWIZZLE_64B; }
   else { p.layout_type = 6; sw = CU_TENSOR_MAP_SWIZZLE_32B; }
-  p.es = d->y_dtype == CLSKD_BF16 ? 2 : 4;
-  if (p.es == 4 && p.block_n > 128) {          // keep the fp32 staging tile <= 64 KB
-    p.block_n = 128;
-    p.tiles_n = d->N / p.block_n;
-  }
   {
     const int max_gw = 128 / p.es;             // 64 bf16 or 32 fp32 columns per 128-byte swizzle row
     int gw = max_gw;

@@ -668,6 +668,42 @@ class EmuLib:
         DZ[:, 1] = (G * Y).sum(1) * Z[:, 1] * (1 - Z[:, 1])
         return 0
 
+    def clskd_tapsum_fwd(self, z, zdt, B, Ti, Fi, To, Fo, sf, Zc, ntaps, dt, df, N, bias, y, ydt, stream):
+        _need_f32(zdt), _need_f32(ydt)
+        Z = _arr(z, B * Ti * Fi * Zc).reshape(B, Ti, Fi, Zc)
+        Y = _arr(y, B * To * Fo * N).reshape(B, To, Fo, N)
+        acc = np.zeros((B, To, Fo, N), np.float32)
+        for j in range(ntaps):
+            for t in range(To):
+                tt = t + dt[j]
+                if tt < 0 or tt >= Ti:
+                    continue
+                for f in range(Fo):
+                    ff = f + df[j]
+                    if ff < 0 or ff % sf:
+                        continue
+                    ff //= sf
+                    if ff < Fi:
+                        acc[:, t, f] += Z[:, tt, ff, j * N:(j + 1) * N]
+        Y[...] = acc + (_arr(bias, N) if bias else 0)
+        return 0
+
+    def clskd_tapsum_bwd(self, dy, ddt, B, Ti, Fi, To, Fo, sf, Zc, ntaps, dt, df, N, dz, zdt, stream):
+        _need_f32(ddt), _need_f32(zdt)
+        G = _arr(dy, B * To * Fo * N).reshape(B, To, Fo, N)
+        D = _arr(dz, B * Ti * Fi * Zc).reshape(B, Ti, Fi, Zc)
+        D[...] = 0
+        for j in range(ntaps):
+            for t in range(Ti):
+                tt = t - dt[j]
+                if tt < 0 or tt >= To:
+                    continue
+                for f in range(Fi):
+                    ff = f * sf - df[j]
+                    if 0 <= ff < Fo:
+                        D[:, t, f, j * N:(j + 1) * N] = G[:, tt, ff]
+        return 0
+
     @staticmethod
     def _pool_bounds(n, l):
         return [((i * n) // l, ((i + 1) * n + l - 1) // l) for i in range(l)]

@@ -237,3 +237,35 @@ def test_umma_gram_fwd_bwd_vs_torch(cuda_dev, B, K):
     gref = z64.grad
     err = (zd.grad.float().cpu().double() - gref).abs().max().item()
     assert err < 1.5e-2 * gref.abs().max().item(), err          # dz is rounded to bf16 (2^-8 relative)
+
+
+@pytest.mark.parametrize("cin,cout,ks", [(128, 2, 3), (64, 1, 3), (32, 2, 5)])
+def test_tap_in_channel_narrow_conv_vs_torch(cuda_dev, cin, cout, ks):
+    """bf16 policy: k x k conv onto <= 2 channels = pointwise tcgen05 GEMM + tap gather-sum"""
+    import clskd_b200
+    from clskd_b200 import framework as fw
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(cin + ks)
+    conv = fw.RealConv2d(cin, cout, ks, padding=ks // 2, bias=False)
+    _round_params(conv)
+    x = torch.randn(2, cin, 32, 45, generator=g).bfloat16().float()
+    up = torch.randn(2, cout, 32, 45, generator=g).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    wr = conv.weight.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(xr, wr, padding=ks // 2)
+    (ref * up).sum().backward()
+    conv = conv.to(cuda_dev)
+    clskd_b200.set_precision("bf16")
+    xp = x.permute(0, 3, 2, 1).contiguous().to(cuda_dev).bfloat16().requires_grad_(True)
+    assert conv._use_narrow(xp, None)
+    n0 = ops.umma_launches
+    y = conv.forward_phys(xp, out_dtype=torch.float32)
+    (y * up.permute(0, 3, 2, 1).to(cuda_dev)).sum().backward()
+    assert ops.umma_launches >= n0 + 3                      # pointwise fwd, dgrad and wgrad on tensor cores
+    yl = y.detach().permute(0, 3, 2, 1).cpu()
+    s = ref.abs().max().item()
+    assert (yl - ref.detach()).abs().max().item() < 2e-2 * s       # z is rounded to bf16 per tap
+    gx = xp.grad.float().permute(0, 3, 2, 1).cpu()
+    assert (gx - xr.grad).abs().max().item() < 2e-2 * xr.grad.abs().max().item()
+    gw = conv.weight.grad.cpu()
+    assert (gw - wr.grad).abs().max().item() < 2e-2 * wr.grad.abs().max().item()

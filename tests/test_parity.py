@@ -409,3 +409,66 @@ def test_narrow_real_convs_vs_torch(dev, cin, cout, ks):
     assert torch.allclose(xd.grad.cpu(), xr.grad, atol=1e-4, rtol=1e-4)
     assert torch.allclose(conv.weight.grad.cpu(), gw_ref, atol=2e-3, rtol=1e-3)
     assert torch.allclose(conv.bias.grad.cpu(), gb_ref, atol=2e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("cin,cout,ks", [(16, 2, 3), (8, 1, 5)])
+def test_tap_in_channel_decomposition_vs_torch(dev, cin, cout, ks):
+    """the narrow-conv decomposition (pointwise GEMM onto (tap, n) channels + tap gather-sum and its
+    adjoint) forced on under the fp32 policy"""
+    from clskd_b200 import framework as fw
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(cin + ks)
+    conv = fw.RealConv2d(cin, cout, ks, padding=ks // 2, bias=False)
+    x = torch.randn(2, cin, 12, 19, generator=g)
+    up = torch.randn(2, cout, 12, 19, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = conv.weight.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(xr, wr, padding=ks // 2)
+    (ref * up).sum().backward()
+    conv = conv.to(dev)
+    ops.policy.narrow = "always"
+    try:
+        xp = x.permute(0, 3, 2, 1).contiguous().to(dev).requires_grad_(True)
+        assert conv._use_narrow(xp, None)
+        y = conv.forward_phys(xp)
+        (y * up.permute(0, 3, 2, 1).to(dev)).sum().backward()
+    finally:
+        ops.policy.narrow = "auto"
+    assert torch.allclose(y.detach().permute(0, 3, 2, 1).cpu(), ref.detach(), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(xp.grad.permute(0, 3, 2, 1).cpu(), xr.grad, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(conv.weight.grad.cpu(), wr.grad, atol=1e-3, rtol=1e-3)
+
+
+def test_mask_layer_decomposition_vs_oracle(dev):
+    """last decoder layer (complex transposed conv onto ONE complex channel, with skip input) through
+    the tap-in-channel path (forced on under the fp32 policy): forward, both data gradients, weights, bias"""
+    from clskd_b200 import ops
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(21)
+    dec = tm.ComplexConvTranspose2d(16, 2, kernel_size=(5, 2), stride=(2, 1), padding=(2, 0), output_padding=(1, 0))
+    dec.real_conv.bias.data.normal_(generator=g)
+    dec.imag_conv.bias.data.normal_(generator=g)
+    a = torch.randn(2, 8, 12, 9, generator=g)
+    sk = torch.randn(2, 8, 12, 9, generator=g)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    ar, sr = a.clone().requires_grad_(True), sk.clone().requires_grad_(True)
+    ref = D.complex_deconv2d(D.complex_cat([ar, sr], 1), sd["real_conv.weight"], sd["real_conv.bias"],
+                             sd["imag_conv.weight"], sd["imag_conv.bias"])
+    up = torch.randn(ref.shape, generator=g)
+    (ref * up).sum().backward()
+    dec = dec.to(dev)
+    ap = a.permute(0, 3, 2, 1).contiguous().to(dev).requires_grad_(True)
+    sp = sk.permute(0, 3, 2, 1).contiguous().to(dev).requires_grad_(True)
+    ops.policy.narrow = "always"
+    try:
+        assert dec._use_narrow(ap, sp)
+        y = dec.forward_phys(ap, sp, torch.float32)
+        (y * up.permute(0, 3, 2, 1).to(dev)).sum().backward()
+    finally:
+        ops.policy.narrow = "auto"
+    assert torch.allclose(y.detach().permute(0, 3, 2, 1).cpu(), ref.detach(), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(ap.grad.permute(0, 3, 2, 1).cpu(), ar.grad, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(sp.grad.permute(0, 3, 2, 1).cpu(), sr.grad, atol=1e-4, rtol=1e-4)
+    for k, p in dec.named_parameters():
+        assert torch.allclose(p.grad.cpu(), sd[k].grad, atol=1e-3, rtol=1e-3), k

@@ -11,7 +11,7 @@ pass=0; fail=0
 : > "$OUT/summary.txt"
 while read -r fn; do
   name=$(echo "$fn" | tr '/:' '__')
-  if timeout 600 python -m pytest "$fn" -m gpu -q -x --no-header -p no:cacheprovider > "$OUT/$name.log" 2>&1; then
+  if timeout ${GPU_TEST_TIMEOUT:-240} python -m pytest "$fn" -m gpu -q -x --no-header -p no:cacheprovider > "$OUT/$name.log" 2>&1; then
     echo "PASS $fn" >> "$OUT/summary.txt"; pass=$((pass+1))
   else
     echo "FAIL($?) $fn" >> "$OUT/summary.txt"; fail=$((fail+1))
