@@ -288,6 +288,24 @@ int clskd_att_blend_fwd(const void* x, const void* y, int dtype, const float* z,
 int clskd_att_blend_bwd(const void* x, const void* y, int dtype, const float* z, const void* dout,
                         int64_t M, int C, void* dx, void* dy, float* dz, void* stream);
 
+/* Fused middle stage of an ABF block (framework.py:209-219) on dense channels-last tensors:
+ *   xp = BN(z1) with the given per-channel mean / invstd / gamma / beta;  yv = y_prev resized
+ *   (nearest) from Fy to F frequency rows, Fy == F or 2*Fy == F;  logit_k = W_att[k] . [xp ; yv] + b_att[k];
+ *   xb = xp * sigmoid(logit_0) + yv * sigmoid(logit_1).
+ * z1, xb, dz1, gout: [B,T,F,C]; y_prev, dy: [B,T,Fy,C]; logits: fp32 [B,T,F,2] (saved for backward);
+ * watt: fp32 [2][2C] (nn.Conv2d(2C, 2, 1) weight, x channels first); batt: fp32 [2] or NULL.
+ * clskd_abf_mid_bwd runs the statistics pass and the apply pass: sums[2][C] = (sum dxp, sum dxp*xhat)
+ * (= dbeta, dgamma), dwatt[2][2C], dbatt[2] (all fp64, zeroed by the call), dz1 (BatchNorm backward
+ * with batch statistics when training != 0) and dy (adjoint of the resize). */
+int clskd_abf_mid_supported(int B, int T, int F, int Fy, int C);
+int clskd_abf_mid_fwd(const void* z1, const void* y, int dtype, int B, int T, int F, int Fy, int C,
+                      const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      const float* watt, const float* batt, void* xb, float* logits, void* stream);
+int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y, int dtype, int B, int T, int F,
+                      int Fy, int C, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, const float* watt, const float* logits, int training,
+                      double* sums, double* dwatt, double* dbatt, void* dz1, void* dy, void* stream);
+
 /* Tap-in-channel decomposition of a convolution-like layer with very few output channels (ABF's
  * 3x3 conv onto the 2-channel mask map; the last, mask-producing transposed conv of the decoder):
  * a pointwise GEMM first produces, at every INPUT position, the contribution to each (tap, n) pair

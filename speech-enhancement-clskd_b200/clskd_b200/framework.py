@@ -226,7 +226,7 @@ class RealConv2d(nn.Module):
 
     def _use_narrow(self, x0, x1):
         KF, KT = self.kernel_size
-        shape_ok = (x1 is None and self.bias is None and self.out_channels <= 2 and KF * KT > 1
+        shape_ok = (x1 is None and self.bias is None and self.out_channels <= 2 and 1 < KF * KT <= 16
                     and KF * KT * self.out_channels <= 64 and KF == 2 * self.padding[0] + 1
                     and KT == 2 * self.padding[1] + 1)
         if ops.policy.narrow == "always":
@@ -258,17 +258,32 @@ class ABF(nn.Module):
         self.att_conv = nn.Sequential(RealConv2d(mid_channel * 2, 2, 1), nn.Sigmoid()) if fuse else None
         nn.init.kaiming_uniform_(self.conv1[0].weight, a=1)
         nn.init.kaiming_uniform_(self.conv2[0].weight, a=1)
+        self.fused = True     # fused BN + resize + attention + blend kernel where the shapes allow
 
     def forward(self, x, y=None, shape=None, out_shape=None, feature_type=None):
-        xp = self.conv1.forward_phys(to_phys(x))
         if self.att_conv is not None:
-            yp = to_phys(y, xp.dtype, need_dense=True)
-            if yp.shape[1] != xp.shape[1]:
+            z1 = self.conv1[0].forward_phys(to_phys(x))                   # 1x1 conv, pre-BatchNorm
+            yp = to_phys(y, z1.dtype, need_dense=True)
+            if yp.shape[1] != z1.shape[1]:
                 raise NotImplementedError("ABF: residual and feature maps must share the time axis")
-            if yp.shape[2] != shape:
-                yp = ResizeFFn.apply(yp, shape)          # F.interpolate(y, (shape, w), 'nearest')
-            z = self.att_conv[0].forward_phys(xp, yp, torch.float32)      # logits [B,T,F,2]
-            xp = AttBlendFn.apply(xp, yp, z)             # x*sigmoid(z0) + y*sigmoid(z1)
+            if z1.shape[2] == shape and self.fused and ops.abf_mid_supported(z1, yp):
+                # BN + nearest resize + attention logits + sigmoid blend in one kernel
+                bn, att = self.conv1[1], self.att_conv[0]
+                if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+                use_running = (not bn.training) and bn.track_running_stats
+                xp = ops.AbfMidFn.apply(z1, yp, bn.weight, bn.bias, att.weight, att.bias,
+                                        bn.running_mean if bn.track_running_stats else None,
+                                        bn.running_var if bn.track_running_stats else None,
+                                        not use_running, bn.momentum, bn.eps)
+            else:
+                xp = self.conv1[1].forward_phys(z1, None)
+                if yp.shape[2] != shape:
+                    yp = ResizeFFn.apply(yp, shape)          # F.interpolate(y, (shape, w), 'nearest')
+                z = self.att_conv[0].forward_phys(xp, yp, torch.float32)      # logits [B,T,F,2]
+                xp = AttBlendFn.apply(xp, yp, z)             # x*sigmoid(z0) + y*sigmoid(z1)
+        else:
+            xp = self.conv1.forward_phys(to_phys(x))
         if out_shape is not None and xp.shape[2] != out_shape:
             xp = ResizeFFn.apply(xp, out_shape)
         out = self.conv2.forward_phys(xp)

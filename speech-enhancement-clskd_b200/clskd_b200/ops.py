@@ -936,6 +936,77 @@ class AttBlendFn(torch.autograd.Function):
         return dx, dy, dz
 
 
+class AbfMidFn(torch.autograd.Function):
+    """Fused ABF middle stage: BatchNorm(z1) -> nearest-resize(y_prev) -> 2-logit attention conv ->
+    sigmoid blend, one pass forward and two passes backward (clskd_abf_mid_* in clskd.h).
+    z1: dense [B,T,F,C] (1x1-conv output), y_prev: dense [B,T,Fy,C]; returns xb [B,T,F,C]."""
+
+    @staticmethod
+    def forward(ctx, z1, y_prev, gamma, beta, watt, batt, running_mean, running_var, training, momentum, eps):
+        B, T, F, C = z1.shape
+        Fy = y_prev.shape[2]
+        M = B * T * F
+        dev = z1.device
+        stats = torch.empty(2, C, dtype=torch.float32, device=dev)
+        mean, invstd = stats[0], stats[1]
+        use_batch = training or running_mean is None
+        if use_batch:
+            s, ss = colstats(z1.view(M, C))
+            call("clskd_bn_finalize", s.data_ptr(), ss.data_ptr(), M, C, float(eps),
+                 float(momentum if momentum is not None else 0.0), mean.data_ptr(), invstd.data_ptr(),
+                 running_mean.data_ptr() if (running_mean is not None and training) else None,
+                 running_var.data_ptr() if (running_var is not None and training) else None, _stream())
+        else:
+            call("clskd_bn_eval_stats", running_mean.data_ptr(), running_var.data_ptr(), C, float(eps),
+                 mean.data_ptr(), invstd.data_ptr(), _stream())
+        g32, b32 = _f32c(gamma), _f32c(beta)
+        w32 = _f32c(watt).view(2, 2 * C)
+        ba32 = _f32c(batt) if batt is not None else None
+        xb = torch.empty_like(z1)
+        logits = torch.empty((B, T, F, 2), dtype=torch.float32, device=dev)
+        call("clskd_abf_mid_fwd", z1.data_ptr(), y_prev.data_ptr(), _tag(z1.dtype), B, T, F, Fy, C, mean.data_ptr(),
+             invstd.data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(), _ptr(ba32), xb.data_ptr(),
+             logits.data_ptr(), _stream())
+        ctx.save_for_backward(z1, y_prev, stats, gamma, beta, watt, logits)
+        ctx.use_batch = use_batch
+        ctx.has_bias = batt is not None
+        return xb
+
+    @staticmethod
+    def backward(ctx, g):
+        z1, y_prev, stats, gamma, beta, watt, logits = ctx.saved_tensors
+        B, T, F, C = z1.shape
+        Fy = y_prev.shape[2]
+        dev = z1.device
+        g = dense(g, z1.dtype)
+        acc = torch.empty(2 * C + 4 * C + 2, dtype=torch.float64, device=dev)
+        sums, dwatt, dbatt = acc[:2 * C], acc[2 * C:6 * C], acc[6 * C:]
+        dz1 = torch.empty_like(z1)
+        dy = torch.empty_like(y_prev)
+        g32, b32 = _f32c(gamma), _f32c(beta)
+        w32 = _f32c(watt).view(2, 2 * C)
+        call("clskd_abf_mid_bwd", g.data_ptr(), z1.data_ptr(), y_prev.data_ptr(), _tag(z1.dtype), B, T, F, Fy, C,
+             stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(),
+             logits.data_ptr(), 1 if ctx.use_batch else 0, sums.data_ptr(), dwatt.data_ptr(), dbatt.data_ptr(),
+             dz1.data_ptr(), dy.data_ptr(), _stream())
+        a32 = f64_to_f32(acc)
+        dbeta, dgamma = a32[:C].view_as(beta), a32[C:2 * C].view_as(gamma)
+        dw = a32[2 * C:6 * C].view_as(watt)
+        db = a32[6 * C:] if ctx.has_bias else None
+        return dz1, dy, dgamma, dbeta, dw, db, None, None, None, None, None
+
+
+def abf_mid_supported(z1, y_prev):
+    if z1.dim() != 4 or y_prev.dim() != 4 or z1.dtype != y_prev.dtype:
+        return False
+    if not (z1.is_contiguous() and y_prev.is_contiguous()):
+        return False
+    B, T, F, C = z1.shape
+    if y_prev.shape[0] != B or y_prev.shape[1] != T or y_prev.shape[3] != C:
+        return False
+    return bool(_lib.load().clskd_abf_mid_supported(B, T, F, y_prev.shape[2], C))
+
+
 class TapSumFn(torch.autograd.Function):
     """y[b,t,f,n] = bias[n] + sum_j z[b, t+dt[j], (f+df[j])/sf, j*N+n]: the gather half of the
     tap-in-channel decomposition of a narrow convolution (see clskd_tapsum_fwd in clskd.h).

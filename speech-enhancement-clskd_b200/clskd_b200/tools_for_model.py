@@ -302,7 +302,7 @@ class ComplexConvTranspose2d(nn.Module):
         return self._plans[key]
 
     def _use_narrow(self, x0, x1):
-        ok = self.out_channels == 1 and self.kernel_size[0] * self.kernel_size[1] * 2 <= 64
+        ok = self.out_channels == 1 and self.kernel_size[0] * self.kernel_size[1] <= 16
         if ops.policy.narrow == "always":
             return ok
         return (ok and ops.policy.use_umma and x0.dtype == torch.bfloat16 and x0.shape[-1] % 16 == 0

@@ -1,0 +1,364 @@
+// Fused middle stage of the attention-based fusion block (ABF, framework.py:206-220):
+//
+//   xp     = BatchNorm(z1)                         (z1 = 1x1 conv of the student map, framework.py:209)
+//   yv     = nearest-resize(y_prev) along F        (framework.py:213-215, factor 1 or 2)
+//   logit  = W_att [xp ; yv] + b_att               (1x1 conv onto 2 logits, framework.py:217-218)
+//   xb     = xp * sigmoid(logit0) + yv * sigmoid(logit1)        (framework.py:219)
+//
+// Everything is row-local, so one kernel does it in a single pass (read z1, read y_prev, write xb
+// and the 2 logits per row) instead of the 9 tensor passes of BN-apply + resize + attention conv +
+// blend.  The backward is two passes (BatchNorm needs batch sums of the gradient first) that
+// recompute xp / yv / sigmoid from z1, y_prev and the saved logits instead of reading saved copies,
+// and produce dz1, dy_prev (resize adjoint fused), dW_att, db_att, dgamma, dbeta.
+//
+// Thread mapping: C/8 adjacent lanes own one row (each lane a fixed 8-channel group, so BN and
+// attention constants live in registers); rows are addressed flat; all accesses are 16-byte vectors.
+#include "common.cuh"
+
+namespace clskd {
+namespace {
+
+__device__ __forceinline__ void ld8(const float* p, float* o) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* o) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    o[2 * i] = f.x;
+    o[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
+  uint4 u;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + __expf(-v)); }
+
+constexpr int AT = 256;
+
+struct AbfGeom {
+  int64_t M;      // rows B*T*F
+  int F, Fy, C;   // F of this level, F of y_prev (F or F/2), channels
+  int tpr;        // lanes per row = C/8 (power of two <= 32)
+};
+
+// row m = (bt, f) -> flat row of y_prev
+__device__ __forceinline__ int64_t yrow(const AbfGeom& g, int64_t m) {
+  if (g.Fy == g.F) return m;
+  const int64_t bt = m / g.F;
+  const int f = (int)(m - bt * g.F);
+  return bt * g.Fy + (f >> 1);
+}
+
+// per-lane constants: BN scale/shift and the 4 attention weight vectors of the lane's 8 channels
+struct LaneConst {
+  float sc[8], sh[8], wx0[8], wx1[8], wy0[8], wy1[8];
+  __device__ __forceinline__ void load(int cg, int C, const float* mean, const float* invstd, const float* gamma,
+                                       const float* beta, const float* watt) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      sc[e] = invstd[c] * (gamma ? gamma[c] : 1.f);
+      sh[e] = (beta ? beta[c] : 0.f) - mean[c] * sc[e];
+      wx0[e] = watt[c];
+      wy0[e] = watt[C + c];
+      wx1[e] = watt[2 * C + c];
+      wy1[e] = watt[3 * C + c];
+    }
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(AT) abf_mid_fwd_kernel(const T* __restrict__ z1, const T* __restrict__ y, AbfGeom g,
+                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ watt, const float* __restrict__ batt,
+                                                         T* __restrict__ xb, float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
+  LaneConst k;
+  k.load(cg, g.C, mean, invstd, gamma, beta, watt);
+  const float b0 = batt ? batt[0] : 0.f, b1 = batt ? batt[1] : 0.f;
+  const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
+  constexpr int RQ = 2;
+  for (int64_t m0 = warp0 * rpw * RQ; m0 < g.M; m0 += nwarps * rpw * RQ) {
+    float xv[RQ][8], yv[RQ][8];
+    bool live[RQ];
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+      const int64_t m = m0 + (int64_t)q * rpw + sub;
+      live[q] = m < g.M;
+      const int64_t mm = live[q] ? m : 0;
+      ld8(z1 + mm * g.C + cg * 8, xv[q]);
+      ld8(y + yrow(g, mm) * g.C + cg * 8, yv[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xv[q][e] = fmaf(xv[q][e], k.sc[e], k.sh[e]);          // xp
+        l0 = fmaf(xv[q][e], k.wx0[e], fmaf(yv[q][e], k.wy0[e], l0));
+        l1 = fmaf(xv[q][e], k.wx1[e], fmaf(yv[q][e], k.wy1[e], l1));
+      }
+      for (int o = g.tpr >> 1; o > 0; o >>= 1) {
+        l0 += __shfl_xor_sync(0xffffffffu, l0, o);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+      }
+      l0 += b0;
+      l1 += b1;
+      const float s0 = sigm(l0), s1 = sigm(l1);
+      if (live[q]) {
+        const int64_t m = m0 + (int64_t)q * rpw + sub;
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = xv[q][e] * s0 + yv[q][e] * s1;
+        st8(xb + m * g.C + cg * 8, o8);
+        if (cg == 0) *reinterpret_cast<float2*>(logits + 2 * m) = make_float2(l0, l1);
+      }
+    }
+  }
+}
+
+// MODE 0: statistics pass (sums for BatchNorm backward, dW_att, db_att)
+// MODE 1: apply pass (dz1, dy_prev)
+// A lane group always processes the PAIR of rows (f = 2j, 2j+1) that share one y_prev row when
+// Fy = F/2 (so dy_prev is written once, without atomics); with Fy = F the pair is two plain rows.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(AT) abf_mid_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ z1,
+                                                         const T* __restrict__ y, AbfGeom g,
+                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ watt, const float* __restrict__ logits,
+                                                         double* __restrict__ sums, double* __restrict__ dwatt,
+                                                         double* __restrict__ dbatt, int training, T* __restrict__ dz1,
+                                                         T* __restrict__ dy) {
+  extern __shared__ float red[];   // MODE 0: [6][C] + 2
+  const int C = g.C;
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < 6 * C + 2; i += AT) red[i] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
+  LaneConst k;
+  k.load(cg, C, mean, invstd, gamma, beta, watt);
+  float mu[8], is[8], gi[8], k1[8], k2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    mu[e] = mean[c];
+    is[e] = invstd[c];
+    gi[e] = (gamma ? gamma[c] : 1.f) * is[e];
+    if (MODE == 1) {
+      k1[e] = training ? (float)(sums[c] / (double)g.M) : 0.f;
+      k2[e] = training ? (float)(sums[C + c] / (double)g.M) : 0.f;
+    }
+  }
+  // MODE 0 accumulators
+  float a_s0[8], a_s1[8], a_wx0[8], a_wx1[8], a_wy0[8], a_wy1[8], a_b0 = 0.f, a_b1 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a_s0[e] = a_s1[e] = a_wx0[e] = a_wx1[e] = a_wy0[e] = a_wy1[e] = 0.f;
+
+  const int64_t pairs = g.M >> 1;           // M is even (F is even)
+  const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
+  for (int64_t p0 = warp0 * rpw; p0 < pairs; p0 += nwarps * rpw) {
+    const int64_t p = p0 + sub;
+    const bool live = p < pairs;
+    const int64_t m0 = live ? 2 * p : 0;
+    float gv[2][8], xv[2][8], yv[2][8];
+    float2 lg[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int64_t m = m0 + q;
+      ld8(gout + m * C + cg * 8, gv[q]);
+      ld8(z1 + m * C + cg * 8, xv[q]);
+      lg[q] = *reinterpret_cast<const float2*>(logits + 2 * m);
+    }
+    const int64_t yr0 = yrow(g, m0);
+    ld8(y + yr0 * C + cg * 8, yv[0]);
+    if (g.Fy == g.F) ld8(y + (yr0 + 1) * C + cg * 8, yv[1]);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[1][e] = yv[0][e];
+    }
+    float dyv[2][8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float s0 = sigm(lg[q].x), s1 = sigm(lg[q].y);
+      float xh[8], t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xh[e] = (xv[q][e] - mu[e]) * is[e];
+        xv[q][e] = fmaf(xv[q][e], k.sc[e], k.sh[e]);          // xp
+        t0 = fmaf(gv[q][e], xv[q][e], t0);
+        t1 = fmaf(gv[q][e], yv[q][e], t1);
+      }
+      for (int o = g.tpr >> 1; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+      }
+      const float dl0 = live ? t0 * s0 * (1.f - s0) : 0.f;
+      const float dl1 = live ? t1 * s1 * (1.f - s1) : 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float ge = live ? gv[q][e] : 0.f;
+        const float dxp = ge * s0 + k.wx0[e] * dl0 + k.wx1[e] * dl1;
+        if (MODE == 0) {
+          a_s0[e] += dxp;
+          a_s1[e] = fmaf(dxp, xh[e], a_s1[e]);
+          a_wx0[e] = fmaf(dl0, xv[q][e], a_wx0[e]);
+          a_wx1[e] = fmaf(dl1, xv[q][e], a_wx1[e]);
+          a_wy0[e] = fmaf(dl0, yv[q][e], a_wy0[e]);
+          a_wy1[e] = fmaf(dl1, yv[q][e], a_wy1[e]);
+        } else {
+          dyv[q][e] = ge * s1 + k.wy0[e] * dl0 + k.wy1[e] * dl1;
+          xv[q][e] = gi[e] * (dxp - k1[e] - xh[e] * k2[e]);     // dz1
+        }
+      }
+      if (MODE == 0 && cg == 0) {
+        a_b0 += dl0;
+        a_b1 += dl1;
+      }
+    }
+    if (MODE == 1 && live) {
+      st8(dz1 + m0 * C + cg * 8, xv[0]);
+      st8(dz1 + (m0 + 1) * C + cg * 8, xv[1]);
+      if (g.Fy == g.F) {
+        st8(dy + yr0 * C + cg * 8, dyv[0]);
+        st8(dy + (yr0 + 1) * C + cg * 8, dyv[1]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dyv[0][e] += dyv[1][e];
+        st8(dy + yr0 * C + cg * 8, dyv[0]);
+      }
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      atomicAdd(&red[c], a_s0[e]);
+      atomicAdd(&red[C + c], a_s1[e]);
+      atomicAdd(&red[2 * C + c], a_wx0[e]);
+      atomicAdd(&red[3 * C + c], a_wy0[e]);
+      atomicAdd(&red[4 * C + c], a_wx1[e]);
+      atomicAdd(&red[5 * C + c], a_wy1[e]);
+    }
+    if (cg == 0) {
+      atomicAdd(&red[6 * C], a_b0);
+      atomicAdd(&red[6 * C + 1], a_b1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += AT) {
+      atomicAdd(sums + i, (double)red[i]);
+      atomicAdd(sums + C + i, (double)red[C + i]);
+      // dwatt layout = W_att layout [2][2C]: row k, columns [x channels | y channels]
+      atomicAdd(dwatt + i, (double)red[2 * C + i]);
+      atomicAdd(dwatt + C + i, (double)red[3 * C + i]);
+      atomicAdd(dwatt + 2 * C + i, (double)red[4 * C + i]);
+      atomicAdd(dwatt + 3 * C + i, (double)red[5 * C + i]);
+    }
+    if (threadIdx.x == 0) {
+      atomicAdd(dbatt, (double)red[6 * C]);
+      atomicAdd(dbatt + 1, (double)red[6 * C + 1]);
+    }
+  }
+}
+
+const char* abf_unsupported(int B, int T, int F, int Fy, int C, const void* a, const void* b, const void* c) {
+  if (C % 8 || C > 256 || C < 8) return "C must be a multiple of 8 in [8,256]";
+  const int tpr = C / 8;
+  if (tpr & (tpr - 1)) return "C/8 must be a power of two";
+  if (!(Fy == F || 2 * Fy == F)) return "y_prev must have F or F/2 frequency rows";
+  if (F % 2) return "F must be even";
+  if (((uintptr_t)a % 16) || ((uintptr_t)b % 16) || (c && ((uintptr_t)c % 16))) return "tensors must be 16-byte aligned";
+  return nullptr;
+}
+
+int abf_grid(int64_t warp_iters) {
+  int64_t blocks = (warp_iters + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+}  // namespace clskd
+
+using namespace clskd;
+
+extern "C" int clskd_abf_mid_supported(int B, int T, int F, int Fy, int C) {
+  return abf_unsupported(B, T, F, Fy, C, nullptr, nullptr, nullptr) == nullptr ? 1 : 0;
+}
+
+extern "C" int clskd_abf_mid_fwd(const void* z1, const void* y, int dtype, int B, int T, int F, int Fy, int C,
+                                 const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                 const float* watt, const float* batt, void* xb, float* logits, void* stream) {
+  CLSKD_CHECK_ARG(z1 && y && mean && invstd && watt && xb && logits, "clskd_abf_mid_fwd: null pointer");
+  if (const char* why = abf_unsupported(B, T, F, Fy, C, z1, y, xb)) {
+    set_error("clskd_abf_mid_fwd: unsupported: %s", why);
+    return CLSKD_ERR_UNSUPPORTED;
+  }
+  AbfGeom g;
+  g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
+  if (g.M == 0) return CLSKD_OK;
+  const int rows_per_warp_iter = (32 / g.tpr) * 2;
+  const int grid = abf_grid((g.M + rows_per_warp_iter - 1) / rows_per_warp_iter / 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_fwd_kernel<TT><<<grid, AT, 0, st>>>(
+                                      (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt, batt, (TT*)xb, logits)));
+  CLSKD_CHECK_LAUNCH("clskd_abf_mid_fwd");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y, int dtype, int B, int T, int F, int Fy,
+                                 int C, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                 const float* watt, const float* logits, int training, double* sums, double* dwatt,
+                                 double* dbatt, void* dz1, void* dy, void* stream) {
+  CLSKD_CHECK_ARG(gout && z1 && y && mean && invstd && watt && logits && sums && dwatt && dbatt && dz1 && dy,
+                  "clskd_abf_mid_bwd: null pointer");
+  if (const char* why = abf_unsupported(B, T, F, Fy, C, gout, z1, dz1)) {
+    set_error("clskd_abf_mid_bwd: unsupported: %s", why);
+    return CLSKD_ERR_UNSUPPORTED;
+  }
+  CLSKD_CHECK_ARG(((uintptr_t)y % 16) == 0 && ((uintptr_t)dy % 16) == 0, "clskd_abf_mid_bwd: y / dy must be 16-byte aligned");
+  AbfGeom g;
+  g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dwatt, 0, sizeof(double) * 4 * C, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbatt, 0, sizeof(double) * 2, st);
+  if (e != cudaSuccess) { set_error("clskd_abf_mid_bwd: memset: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+  if (g.M == 0) return CLSKD_OK;
+  const int64_t pairs = g.M / 2;
+  const int pairs_per_warp = 32 / g.tpr;
+  const int grid = abf_grid((pairs + pairs_per_warp - 1) / pairs_per_warp / 4);
+  const size_t sh = sizeof(float) * (6 * (size_t)C + 2);
+  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 0><<<grid, AT, sh, st>>>(
+                                      (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt,
+                                      logits, sums, dwatt, dbatt, training, nullptr, nullptr)));
+  CLSKD_CHECK_LAUNCH("clskd_abf_mid_bwd(stats)");
+  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 1><<<grid, AT, 0, st>>>(
+                                      (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt,
+                                      logits, sums, dwatt, dbatt, training, (TT*)dz1, (TT*)dy)));
+  CLSKD_CHECK_LAUNCH("clskd_abf_mid_bwd(apply)");
+  return CLSKD_OK;
+}

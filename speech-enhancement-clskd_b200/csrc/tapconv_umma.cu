@@ -50,10 +50,12 @@ struct UmmaParams {
   // epilogue staging for the TMA store: sub-tiles of gw_y columns, [128 rows][gw_y] each, swizzled
   int gw_y, es;                // columns per sub-tile, bytes per output element
   uint32_t y_sub_bytes;        // 128 * gw_y * es
-  uint32_t stage_region;       // bytes of the operand ring (staging buffer follows it)
+  uint32_t stage_region;       // bytes of the operand ring (staging buffers follow it)
+  uint32_t staging_bytes;      // one staging buffer: 128 rows x block_n x es
+  int nstg;                    // 1 or 2 staging buffers (double-buffered TMA stores)
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
                     const UmmaParams p) {
@@ -164,7 +166,7 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // global write is a full coalesced box; rows beyond To are clipped by the tensor map.
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;        // row of the 128-row tile
-    uint8_t* stg = ring + p.stage_region;
+    uint8_t* stg_base = ring + p.stage_region;
     const uint32_t pitch = (uint32_t)(p.gw_y * p.es);          // 128 / 64 / 32 bytes
     const uint32_t xr = pitch == 128 ? (uint32_t)(row & 7) : (pitch == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1));
     const bool issuer = (threadIdx.x == 64);                    // first epilogue thread
@@ -180,8 +182,12 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int n0 = n_tile * p.block_n;
       mbar_wait(&tmem_full_bar[as], (local >> 1) & 1);
       fence_after();
-      // the previous tile's TMA store must have finished reading the staging buffer
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      // the TMA store that last used this staging buffer must have finished reading it
+      uint8_t* stg = stg_base + (size_t)((p.nstg == 2) ? (local & 1) : 0) * p.staging_bytes;
+      if (issuer) {
+        if (p.nstg == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = 0; c < p.block_n; c += 16) {
         uint32_t v[16];
@@ -336,7 +342,13 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   p.tmem_cols = (uint32_t)cols;
   const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
   const uint32_t staging_bytes = (uint32_t)UM * p.block_n * p.es;
-  int stages = (int)((200 * 1024 - staging_bytes) / stage_bytes);
+  p.staging_bytes = staging_bytes;
+  // two CTAs per SM when the accumulators (2 x 2 x block_n TMEM columns) and ~110 KB of smem each
+  // allow it: their serial per-tile latencies (TMA -> MMA -> TMEM drain -> store) overlap
+  const bool two_ctas = 2 * cols <= 512 && staging_bytes <= 32 * 1024;
+  const uint32_t budget = two_ctas ? 108u * 1024u : 200u * 1024u;
+  p.nstg = (2 * staging_bytes + 2 * stage_bytes <= budget) ? 2 : 1;
+  int stages = (int)((budget - p.nstg * staging_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   const int num_k = p.ntaps * p.chunks_tot;
@@ -381,7 +393,7 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(y) failed: %d", (int)r); return CLSKD_ERR_CUDA; }
   }
-  size_t smem = (size_t)stages * stage_bytes + staging_bytes + 1024;
+  size_t smem = (size_t)stages * stage_bytes + (size_t)p.nstg * staging_bytes + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(tapconv_umma_kernel,
@@ -389,7 +401,8 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
     if (e != cudaSuccess) { set_error("clskd_tapconv_fwd_umma: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
     smem_set = smem;
   }
-  const unsigned grid = (unsigned)(tiles < (int64_t)sm_count() ? tiles : (int64_t)sm_count());
+  const int64_t max_ctas = (int64_t)sm_count() * (two_ctas ? 2 : 1);
+  const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
   tapconv_umma_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmY, p);
   CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd_umma");
   return CLSKD_OK;

@@ -668,6 +668,60 @@ class EmuLib:
         DZ[:, 1] = (G * Y).sum(1) * Z[:, 1] * (1 - Z[:, 1])
         return 0
 
+    # ------------------------------------------------------------------ fused ABF middle stage
+    def clskd_abf_mid_supported(self, B, T, F, Fy, C):
+        tpr = C // 8
+        return int(C % 8 == 0 and 8 <= C <= 256 and (tpr & (tpr - 1)) == 0 and (Fy == F or 2 * Fy == F) and F % 2 == 0)
+
+    @staticmethod
+    def _abf_terms(z1, y, B, T, F, Fy, C, mean, invstd, gamma, beta, watt):
+        Z = _arr(z1, B * T * F * C).reshape(B, T, F, C).astype(np.float64)
+        Y = _arr(y, B * T * Fy * C).reshape(B, T, Fy, C).astype(np.float64)
+        idx = (np.arange(F) * Fy) // F
+        yv = Y[:, :, idx]
+        mu, isd = _arr(mean, C).astype(np.float64), _arr(invstd, C).astype(np.float64)
+        g = _arr(gamma, C).astype(np.float64) if gamma else np.ones(C)
+        b = _arr(beta, C).astype(np.float64) if beta else np.zeros(C)
+        xh = (Z - mu) * isd
+        xp = xh * g + b
+        W = _arr(watt, 4 * C).reshape(2, 2 * C).astype(np.float64)
+        return xh, xp, yv, g, isd, W, idx
+
+    def clskd_abf_mid_fwd(self, z1, y, dt, B, T, F, Fy, C, mean, invstd, gamma, beta, watt, batt, xb, logits, stream):
+        _need_f32(dt)
+        xh, xp, yv, g, isd, W, idx = self._abf_terms(z1, y, B, T, F, Fy, C, mean, invstd, gamma, beta, watt)
+        lg = xp @ W[:, :C].T + yv @ W[:, C:].T + (_arr(batt, 2).astype(np.float64) if batt else 0)
+        s = 1.0 / (1.0 + np.exp(-lg))
+        _arr(xb, B * T * F * C).reshape(B, T, F, C)[...] = xp * s[..., :1] + yv * s[..., 1:]
+        _arr(logits, B * T * F * 2).reshape(B, T, F, 2)[...] = lg
+        return 0
+
+    def clskd_abf_mid_bwd(self, gout, z1, y, dt, B, T, F, Fy, C, mean, invstd, gamma, beta, watt, logits, training,
+                          sums, dwatt, dbatt, dz1, dy, stream):
+        _need_f32(dt)
+        xh, xp, yv, g, isd, W, idx = self._abf_terms(z1, y, B, T, F, Fy, C, mean, invstd, gamma, beta, watt)
+        G = _arr(gout, B * T * F * C).reshape(B, T, F, C).astype(np.float64)
+        lg = _arr(logits, B * T * F * 2).reshape(B, T, F, 2).astype(np.float64)
+        s = 1.0 / (1.0 + np.exp(-lg))
+        dl = np.stack([(G * xp).sum(-1), (G * yv).sum(-1)], -1) * s * (1 - s)
+        dxp = G * s[..., :1] + dl @ W[:, :C]
+        dyv = G * s[..., 1:] + dl @ W[:, C:]
+        M = B * T * F
+        S = _arr(sums, 2 * C, np.float64).reshape(2, C)
+        S[0], S[1] = dxp.reshape(M, C).sum(0), (dxp * xh).reshape(M, C).sum(0)
+        DW = _arr(dwatt, 4 * C, np.float64).reshape(2, 2 * C)
+        DW[:, :C] = dl.reshape(M, 2).T @ xp.reshape(M, C)
+        DW[:, C:] = dl.reshape(M, 2).T @ yv.reshape(M, C)
+        _arr(dbatt, 2, np.float64)[...] = dl.reshape(M, 2).sum(0)
+        r = dxp - (S[0] / M + xh * (S[1] / M) if training else 0)
+        _arr(dz1, M * C).reshape(B, T, F, C)[...] = g * isd * r
+        DY = _arr(dy, B * T * Fy * C).reshape(B, T, Fy, C)
+        acc = np.zeros((B, T, Fy, C))
+        for fo in range(F):
+            acc[:, :, idx[fo]] += dyv[:, :, fo]
+        DY[...] = acc
+        return 0
+
     def clskd_tapsum_fwd(self, z, zdt, B, Ti, Fi, To, Fo, sf, Zc, ntaps, dt, df, N, bias, y, ydt, stream):
         _need_f32(zdt), _need_f32(ydt)
         Z = _arr(z, B * Ti * Fi * Zc).reshape(B, Ti, Fi, Zc)

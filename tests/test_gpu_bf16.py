@@ -239,7 +239,7 @@ def test_umma_gram_fwd_bwd_vs_torch(cuda_dev, B, K):
     assert err < 1.5e-2 * gref.abs().max().item(), err          # dz is rounded to bf16 (2^-8 relative)
 
 
-@pytest.mark.parametrize("cin,cout,ks", [(128, 2, 3), (64, 1, 3), (32, 2, 5)])
+@pytest.mark.parametrize("cin,cout,ks", [(128, 2, 3), (64, 1, 3), (32, 2, 3)])
 def test_tap_in_channel_narrow_conv_vs_torch(cuda_dev, cin, cout, ks):
     """bf16 policy: k x k conv onto <= 2 channels = pointwise tcgen05 GEMM + tap gather-sum"""
     import clskd_b200

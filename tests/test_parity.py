@@ -411,7 +411,7 @@ def test_narrow_real_convs_vs_torch(dev, cin, cout, ks):
     assert torch.allclose(conv.bias.grad.cpu(), gb_ref, atol=2e-3, rtol=1e-3)
 
 
-@pytest.mark.parametrize("cin,cout,ks", [(16, 2, 3), (8, 1, 5)])
+@pytest.mark.parametrize("cin,cout,ks", [(16, 2, 3), (8, 1, 3)])
 def test_tap_in_channel_decomposition_vs_torch(dev, cin, cout, ks):
     """the narrow-conv decomposition (pointwise GEMM onto (tap, n) channels + tap gather-sum and its
     adjoint) forced on under the fp32 policy"""
