@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="write per-launch shapes/times of the profiled kernel here")
     ap.add_argument("--profile-kernel", default="auto",
                     help="C-ABI entry point timed with CUDA events for the roofline object")
     return ap.parse_args()
@@ -208,8 +209,9 @@ class KernelTimer:
         self.enabled = False
         self._orig = lib_mod.call
         self.counts = {}
+        self.shapes = []
 
-    def install(self, work_fn):
+    def install(self, work_fn, shape_fn=None):
         orig, me = self._orig, self
 
         def call(name, *a):
@@ -222,6 +224,7 @@ class KernelTimer:
                 e1.record()
                 me.pairs.append((e0, e1))
                 f, b = work_fn(a)
+                me.shapes.append(shape_fn(a) if shape_fn else None)
                 me.flops += f
                 me.bytes += b
                 return rc
@@ -245,6 +248,12 @@ def tapconv_work(a):
     flops = 2.0 * M * K * d.N
     byts = float(d.B * d.Ti * d.Fi * (d.c0 + d.c1) * xe + M * d.N * ye + K * d.N * xe)
     return flops, byts
+
+
+def tapconv_shape(a):
+    d = a[0]._obj
+    return {"M": d.B * d.To * d.Fo, "taps": d.ntaps, "C": d.c0 + d.c1, "N": d.N, "Fo": d.Fo, "sf": d.sf,
+            "out": "bf16" if d.y_dtype == 1 else "f32"}
 
 
 def run_ours(args):
@@ -282,7 +291,7 @@ def run_ours(args):
     if kname == "auto":
         kname = "clskd_tapconv_fwd_umma" if args.precision == "bf16" else "clskd_tapconv_fwd"
     kt = KernelTimer(_lib, kname)
-    kt.install(tapconv_work)
+    kt.install(tapconv_work, tapconv_shape)
 
     def barrier():
         if world > 1:
@@ -370,6 +379,14 @@ def run_ours(args):
             "max_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
         }
         print(json.dumps(line), flush=True)
+        if args.dump_launches:
+            rows = []
+            for (e_a, e_b), shp in zip(kt.pairs, kt.shapes):
+                ms_l = e_a.elapsed_time(e_b)
+                fl = 2.0 * shp["M"] * shp["taps"] * shp["C"] * shp["N"]
+                rows.append(dict(shp, ms=ms_l, tflops=fl / (ms_l / 1e3) / 1e12 if ms_l > 0 else 0.0))
+            with open(args.dump_launches, "w") as f:
+                json.dump(rows, f)
     if world > 1:
         dist.destroy_process_group()
 

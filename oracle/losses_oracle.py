@@ -127,8 +127,23 @@ def clskd_step_loss(teacher_sd, student_sd, X, y, abf_enc_sd=None, abf_dec_sd=No
     with torch.no_grad():
         t_wav = dccrn_forward(teacher_sd, X, training=teacher_training, taps=tt)[-1]
     s_wav = dccrn_forward(student_sd, X, training=student_training, taps=st)[-1]
-    terms = {'base': mr_stft_loss(s_wav, y, [512], [100], [400])[1]}
-    if mode in ('clskd', 'spkd_all'):
+    if mode == 'reviewkd':          # distill_ReviewKD.py:56 base-loss resolution
+        terms = {'base': mr_stft_loss(s_wav, y, [512], [16], [32])[1]}
+    else:
+        terms = {'base': mr_stft_loss(s_wav, y, [512], [100], [400])[1]}
+    if mode == 'reviewkd':
+        # distill_ReviewKD.py:92-125 on the local DCCRN: hcl between fused student maps and teacher maps;
+        # the LSTM taps go through hcl when their widths agree and SPKD otherwise (hcl needs equal shapes)
+        e_shapes = [m.shape[2] for m in st['encoder']][::-1]
+        d_shapes = [m.shape[2] for m in st['decoder']]
+        f_enc = review_kd_forward(st['encoder'], abf_enc_sd, e_shapes, e_shapes, 'encoder')
+        f_dec = review_kd_forward(st['decoder'], abf_dec_sd, d_shapes, d_shapes, 'decoder')
+        terms['encoder'] = hcl(f_enc, tt['encoder'])
+        terms['decoder'] = hcl(f_dec, tt['decoder'])
+        for key, i in (('clstm_real', 0), ('clstm_img', 1)):
+            a, b = st['clstm'][i].transpose(0, 1), tt['clstm'][i].transpose(0, 1)
+            terms[key] = hcl([a.unsqueeze(1)], [b.unsqueeze(1)]) if a.shape == b.shape else spkd(a, b)
+    elif mode in ('clskd', 'spkd_all'):
         if mode == 'clskd':
             e_shapes = [m.shape[2] for m in st['encoder']][::-1]
             d_shapes = [m.shape[2] for m in st['decoder']]

@@ -64,34 +64,47 @@ __device__ __forceinline__ int64_t yrow(const AbfGeom& g, int64_t m) {
   return bt * g.Fy + (f >> 1);
 }
 
-// per-lane constants: BN scale/shift and the 4 attention weight vectors of the lane's 8 channels
-struct LaneConst {
-  float sc[8], sh[8], wx0[8], wx1[8], wy0[8], wy1[8];
-  __device__ __forceinline__ void load(int cg, int C, const float* mean, const float* invstd, const float* gamma,
-                                       const float* beta, const float* watt) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = cg * 8 + e;
-      sc[e] = invstd[c] * (gamma ? gamma[c] : 1.f);
-      sh[e] = (beta ? beta[c] : 0.f) - mean[c] * sc[e];
-      wx0[e] = watt[c];
-      wy0[e] = watt[C + c];
-      wx1[e] = watt[2 * C + c];
-      wy1[e] = watt[3 * C + c];
-    }
+// per-channel constants staged in shared memory as [NCONST][C] floats (a lane reads its 8 channels
+// of one constant with two 16-byte loads; lanes of a row are contiguous -> conflict free).  Keeping
+// them out of registers is what lets two or three CTAs stay resident per SM.
+enum { K_SC = 0, K_SH, K_WX0, K_WY0, K_WX1, K_WY1, K_MU, K_IS, K_GI, K_K1, K_K2, NCONST };
+
+__device__ __forceinline__ void stage_consts(float* cs, int C, const float* mean, const float* invstd,
+                                             const float* gamma, const float* beta, const float* watt,
+                                             const double* sums, double invM, int training) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = gamma ? gamma[c] : 1.f;
+    const float sc = invstd[c] * g;
+    cs[K_SC * C + c] = sc;
+    cs[K_SH * C + c] = (beta ? beta[c] : 0.f) - mean[c] * sc;
+    cs[K_WX0 * C + c] = watt[c];
+    cs[K_WY0 * C + c] = watt[C + c];
+    cs[K_WX1 * C + c] = watt[2 * C + c];
+    cs[K_WY1 * C + c] = watt[3 * C + c];
+    cs[K_MU * C + c] = mean[c];
+    cs[K_IS * C + c] = invstd[c];
+    cs[K_GI * C + c] = g * invstd[c];
+    cs[K_K1 * C + c] = (sums && training) ? (float)(sums[c] * invM) : 0.f;
+    cs[K_K2 * C + c] = (sums && training) ? (float)(sums[C + c] * invM) : 0.f;
   }
-};
+  __syncthreads();
+}
+__device__ __forceinline__ void ldc(const float* cs, int which, int C, int cg, float* o) {
+  const float4 a = *reinterpret_cast<const float4*>(cs + which * C + cg * 8);
+  const float4 b = *reinterpret_cast<const float4*>(cs + which * C + cg * 8 + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
 
 template <typename T>
-__global__ void __launch_bounds__(AT) abf_mid_fwd_kernel(const T* __restrict__ z1, const T* __restrict__ y, AbfGeom g,
-                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         const float* __restrict__ watt, const float* __restrict__ batt,
-                                                         T* __restrict__ xb, float* __restrict__ logits) {
+__global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict__ z1, const T* __restrict__ y, AbfGeom g,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ watt, const float* __restrict__ batt,
+                                                            T* __restrict__ xb, float* __restrict__ logits) {
+  extern __shared__ float cs[];
+  stage_consts(cs, g.C, mean, invstd, gamma, beta, watt, nullptr, 0., 0);
   const int lane = threadIdx.x & 31;
   const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
-  LaneConst k;
-  k.load(cg, g.C, mean, invstd, gamma, beta, watt);
   const float b0 = batt ? batt[0] : 0.f, b1 = batt ? batt[1] : 0.f;
   const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
@@ -107,29 +120,53 @@ __global__ void __launch_bounds__(AT) abf_mid_fwd_kernel(const T* __restrict__ z
       ld8(z1 + mm * g.C + cg * 8, xv[q]);
       ld8(y + yrow(g, mm) * g.C + cg * 8, yv[q]);
     }
+    float l0[RQ], l1[RQ];
+    {
+      float sc[8], sh[8];
+      ldc(cs, K_SC, g.C, cg, sc);
+      ldc(cs, K_SH, g.C, cg, sh);
+#pragma unroll
+      for (int q = 0; q < RQ; ++q)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xv[q][e] = fmaf(xv[q][e], sc[e], sh[e]);      // xp
+    }
+    {
+      float wx[8], wy[8];
+      ldc(cs, K_WX0, g.C, cg, wx);
+      ldc(cs, K_WY0, g.C, cg, wy);
+#pragma unroll
+      for (int q = 0; q < RQ; ++q) {
+        float a = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a = fmaf(xv[q][e], wx[e], fmaf(yv[q][e], wy[e], a));
+        l0[q] = a;
+      }
+      ldc(cs, K_WX1, g.C, cg, wx);
+      ldc(cs, K_WY1, g.C, cg, wy);
+#pragma unroll
+      for (int q = 0; q < RQ; ++q) {
+        float a = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a = fmaf(xv[q][e], wx[e], fmaf(yv[q][e], wy[e], a));
+        l1[q] = a;
+      }
+    }
 #pragma unroll
     for (int q = 0; q < RQ; ++q) {
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        xv[q][e] = fmaf(xv[q][e], k.sc[e], k.sh[e]);          // xp
-        l0 = fmaf(xv[q][e], k.wx0[e], fmaf(yv[q][e], k.wy0[e], l0));
-        l1 = fmaf(xv[q][e], k.wx1[e], fmaf(yv[q][e], k.wy1[e], l1));
-      }
       for (int o = g.tpr >> 1; o > 0; o >>= 1) {
-        l0 += __shfl_xor_sync(0xffffffffu, l0, o);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+        l0[q] += __shfl_xor_sync(0xffffffffu, l0[q], o);
+        l1[q] += __shfl_xor_sync(0xffffffffu, l1[q], o);
       }
-      l0 += b0;
-      l1 += b1;
-      const float s0 = sigm(l0), s1 = sigm(l1);
+      l0[q] += b0;
+      l1[q] += b1;
+      const float s0 = sigm(l0[q]), s1 = sigm(l1[q]);
       if (live[q]) {
         const int64_t m = m0 + (int64_t)q * rpw + sub;
         float o8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o8[e] = xv[q][e] * s0 + yv[q][e] * s1;
         st8(xb + m * g.C + cg * 8, o8);
-        if (cg == 0) *reinterpret_cast<float2*>(logits + 2 * m) = make_float2(l0, l1);
+        if (cg == 0) *reinterpret_cast<float2*>(logits + 2 * m) = make_float2(l0[q], l1[q]);
       }
     }
   }
@@ -140,36 +177,22 @@ __global__ void __launch_bounds__(AT) abf_mid_fwd_kernel(const T* __restrict__ z
 // A lane group always processes the PAIR of rows (f = 2j, 2j+1) that share one y_prev row when
 // Fy = F/2 (so dy_prev is written once, without atomics); with Fy = F the pair is two plain rows.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(AT) abf_mid_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ z1,
-                                                         const T* __restrict__ y, AbfGeom g,
-                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         const float* __restrict__ watt, const float* __restrict__ logits,
-                                                         double* __restrict__ sums, double* __restrict__ dwatt,
-                                                         double* __restrict__ dbatt, int training, T* __restrict__ dz1,
-                                                         T* __restrict__ dy) {
-  extern __shared__ float red[];   // MODE 0: [6][C] + 2
+__global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ z1,
+                                                            const T* __restrict__ y, AbfGeom g,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ watt, const float* __restrict__ logits,
+                                                            double* __restrict__ sums, double* __restrict__ dwatt,
+                                                            double* __restrict__ dbatt, int training, T* __restrict__ dz1,
+                                                            T* __restrict__ dy) {
+  extern __shared__ float cs[];   // [NCONST][C] constants, then (MODE 0) [6][C] + 2 reduction slots
   const int C = g.C;
-  if (MODE == 0) {
+  float* red = cs + NCONST * C;
+  if (MODE == 0)
     for (int i = threadIdx.x; i < 6 * C + 2; i += AT) red[i] = 0.f;
-    __syncthreads();
-  }
+  stage_consts(cs, C, mean, invstd, gamma, beta, watt, MODE == 1 ? sums : nullptr, 1.0 / (double)g.M, training);
   const int lane = threadIdx.x & 31;
   const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
-  LaneConst k;
-  k.load(cg, C, mean, invstd, gamma, beta, watt);
-  float mu[8], is[8], gi[8], k1[8], k2[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = cg * 8 + e;
-    mu[e] = mean[c];
-    is[e] = invstd[c];
-    gi[e] = (gamma ? gamma[c] : 1.f) * is[e];
-    if (MODE == 1) {
-      k1[e] = training ? (float)(sums[c] / (double)g.M) : 0.f;
-      k2[e] = training ? (float)(sums[C + c] / (double)g.M) : 0.f;
-    }
-  }
   // MODE 0 accumulators
   float a_s0[8], a_s1[8], a_wx0[8], a_wx1[8], a_wy0[8], a_wy1[8], a_b0 = 0.f, a_b1 = 0.f;
 #pragma unroll
@@ -198,55 +221,103 @@ __global__ void __launch_bounds__(AT) abf_mid_bwd_kernel(const T* __restrict__ g
 #pragma unroll
       for (int e = 0; e < 8; ++e) yv[1][e] = yv[0][e];
     }
-    float dyv[2][8];
+    if (!live) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gv[q][e] = 0.f;
+    }
+    // xhat (kept in place of z1) and xp
+    float xp[2][8];
+    {
+      float mu[8], is[8], sc[8], sh[8];
+      ldc(cs, K_MU, C, cg, mu);
+      ldc(cs, K_IS, C, cg, is);
+      ldc(cs, K_SC, C, cg, sc);
+      ldc(cs, K_SH, C, cg, sh);
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xp[q][e] = fmaf(xv[q][e], sc[e], sh[e]);
+          xv[q][e] = (xv[q][e] - mu[e]) * is[e];              // xhat
+        }
+    }
+    float s0[2], s1[2], dl0[2], dl1[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const float s0 = sigm(lg[q].x), s1 = sigm(lg[q].y);
-      float xh[8], t0 = 0.f, t1 = 0.f;
+      s0[q] = sigm(lg[q].x);
+      s1[q] = sigm(lg[q].y);
+      float t0 = 0.f, t1 = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        xh[e] = (xv[q][e] - mu[e]) * is[e];
-        xv[q][e] = fmaf(xv[q][e], k.sc[e], k.sh[e]);          // xp
-        t0 = fmaf(gv[q][e], xv[q][e], t0);
+        t0 = fmaf(gv[q][e], xp[q][e], t0);
         t1 = fmaf(gv[q][e], yv[q][e], t1);
       }
       for (int o = g.tpr >> 1; o > 0; o >>= 1) {
         t0 += __shfl_xor_sync(0xffffffffu, t0, o);
         t1 += __shfl_xor_sync(0xffffffffu, t1, o);
       }
-      const float dl0 = live ? t0 * s0 * (1.f - s0) : 0.f;
-      const float dl1 = live ? t1 * s1 * (1.f - s1) : 0.f;
+      dl0[q] = t0 * s0[q] * (1.f - s0[q]);
+      dl1[q] = t1 * s1[q] * (1.f - s1[q]);
+    }
+    if (MODE == 0) {
+      float wx0[8], wx1[8];
+      ldc(cs, K_WX0, C, cg, wx0);
+      ldc(cs, K_WX1, C, cg, wx1);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float ge = live ? gv[q][e] : 0.f;
-        const float dxp = ge * s0 + k.wx0[e] * dl0 + k.wx1[e] * dl1;
-        if (MODE == 0) {
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dxp = gv[q][e] * s0[q] + wx0[e] * dl0[q] + wx1[e] * dl1[q];
           a_s0[e] += dxp;
-          a_s1[e] = fmaf(dxp, xh[e], a_s1[e]);
-          a_wx0[e] = fmaf(dl0, xv[q][e], a_wx0[e]);
-          a_wx1[e] = fmaf(dl1, xv[q][e], a_wx1[e]);
-          a_wy0[e] = fmaf(dl0, yv[q][e], a_wy0[e]);
-          a_wy1[e] = fmaf(dl1, yv[q][e], a_wy1[e]);
-        } else {
-          dyv[q][e] = ge * s1 + k.wy0[e] * dl0 + k.wy1[e] * dl1;
-          xv[q][e] = gi[e] * (dxp - k1[e] - xh[e] * k2[e]);     // dz1
+          a_s1[e] = fmaf(dxp, xv[q][e], a_s1[e]);
+          a_wx0[e] = fmaf(dl0[q], xp[q][e], a_wx0[e]);
+          a_wx1[e] = fmaf(dl1[q], xp[q][e], a_wx1[e]);
+          a_wy0[e] = fmaf(dl0[q], yv[q][e], a_wy0[e]);
+          a_wy1[e] = fmaf(dl1[q], yv[q][e], a_wy1[e]);
+        }
+        if (cg == 0) {
+          a_b0 += dl0[q];
+          a_b1 += dl1[q];
         }
       }
-      if (MODE == 0 && cg == 0) {
-        a_b0 += dl0;
-        a_b1 += dl1;
-      }
-    }
-    if (MODE == 1 && live) {
-      st8(dz1 + m0 * C + cg * 8, xv[0]);
-      st8(dz1 + (m0 + 1) * C + cg * 8, xv[1]);
-      if (g.Fy == g.F) {
-        st8(dy + yr0 * C + cg * 8, dyv[0]);
-        st8(dy + (yr0 + 1) * C + cg * 8, dyv[1]);
-      } else {
+    } else {
+      {
+        float wx0[8], wx1[8], gi[8], k1[8], k2[8];
+        ldc(cs, K_WX0, C, cg, wx0);
+        ldc(cs, K_WX1, C, cg, wx1);
+        ldc(cs, K_GI, C, cg, gi);
+        ldc(cs, K_K1, C, cg, k1);
+        ldc(cs, K_K2, C, cg, k2);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dyv[0][e] += dyv[1][e];
-        st8(dy + yr0 * C + cg * 8, dyv[0]);
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dxp = gv[q][e] * s0[q] + wx0[e] * dl0[q] + wx1[e] * dl1[q];
+            xp[q][e] = gi[e] * (dxp - k1[e] - xv[q][e] * k2[e]);      // dz1
+          }
+      }
+      {
+        float wy0[8], wy1[8];
+        ldc(cs, K_WY0, C, cg, wy0);
+        ldc(cs, K_WY1, C, cg, wy1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) yv[q][e] = gv[q][e] * s1[q] + wy0[e] * dl0[q] + wy1[e] * dl1[q];   // dyv
+      }
+      if (live) {
+        st8(dz1 + m0 * C + cg * 8, xp[0]);
+        st8(dz1 + (m0 + 1) * C + cg * 8, xp[1]);
+        if (g.Fy == g.F) {
+          st8(dy + yr0 * C + cg * 8, yv[0]);
+          st8(dy + (yr0 + 1) * C + cg * 8, yv[1]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) yv[0][e] += yv[1][e];
+          st8(dy + yr0 * C + cg * 8, yv[0]);
+        }
       }
     }
   }
@@ -323,7 +394,7 @@ extern "C" int clskd_abf_mid_fwd(const void* z1, const void* y, int dtype, int B
   const int rows_per_warp_iter = (32 / g.tpr) * 2;
   const int grid = abf_grid((g.M + rows_per_warp_iter - 1) / rows_per_warp_iter / 2);
   cudaStream_t st = (cudaStream_t)stream;
-  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_fwd_kernel<TT><<<grid, AT, 0, st>>>(
+  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_fwd_kernel<TT><<<grid, AT, sizeof(float) * NCONST * (size_t)C, st>>>(
                                       (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt, batt, (TT*)xb, logits)));
   CLSKD_CHECK_LAUNCH("clskd_abf_mid_fwd");
   return CLSKD_OK;
@@ -351,12 +422,12 @@ extern "C" int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y
   const int64_t pairs = g.M / 2;
   const int pairs_per_warp = 32 / g.tpr;
   const int grid = abf_grid((pairs + pairs_per_warp - 1) / pairs_per_warp / 4);
-  const size_t sh = sizeof(float) * (6 * (size_t)C + 2);
+  const size_t sh = sizeof(float) * ((NCONST + 6) * (size_t)C + 2);
   CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 0><<<grid, AT, sh, st>>>(
                                       (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt,
                                       logits, sums, dwatt, dbatt, training, nullptr, nullptr)));
   CLSKD_CHECK_LAUNCH("clskd_abf_mid_bwd(stats)");
-  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 1><<<grid, AT, 0, st>>>(
+  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 1><<<grid, AT, sizeof(float) * NCONST * (size_t)C, st>>>(
                                       (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt,
                                       logits, sums, dwatt, dbatt, training, (TT*)dz1, (TT*)dy)));
   CLSKD_CHECK_LAUNCH("clskd_abf_mid_bwd(apply)");

@@ -472,3 +472,35 @@ def test_mask_layer_decomposition_vs_oracle(dev):
     assert torch.allclose(sp.grad.permute(0, 3, 2, 1).cpu(), sr.grad, atol=1e-4, rtol=1e-4)
     for k, p in dec.named_parameters():
         assert torch.allclose(p.grad.cpu(), sd[k].grad, atol=1e-3, rtol=1e-3), k
+
+
+def test_reviewkd_step_vs_oracle(dev):
+    """ReviewKD recipe (distill_ReviewKD.py:69-139 on the local DCCRN, hcl on 4-D maps) against the
+    oracle with injected ABF weights: loss terms and student gradients"""
+    from clskd_b200.distill import DistillStep
+    from oracle import losses_oracle as LO
+    g, L = golden("dccrn.pt"), golden("losses.pt")
+    teacher = _build(g["teacher_cfg"], g["t_sd"], dev)
+    student = _build(g["student_cfg"], g["s_sd"], dev)
+    student.train()
+    X, y = g["X"].to(dev), g["y"].to(dev)
+    step = DistillStep(teacher, student, mode="reviewkd")
+    step.materialize(X)
+    student.load_state_dict(full_sd(g["s_sd"]))
+    _load_abf(step.abf_encoder, L["abf_enc_sd"])
+    _load_abf(step.abf_decoder, L["abf_dec_sd"])
+    loss = step(X, y)
+    loss.backward()
+    s_sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
+                and not k.startswith(("stft.", "istft.")) else v) for k, v in full_sd(g["s_sd"]).items()}
+    ref, terms = LO.clskd_step_loss(full_sd(g["t_sd"]), s_sd, g["X"], g["y"], L["abf_enc_sd"], L["abf_dec_sd"],
+                                    mode="reviewkd")
+    ref.backward()
+    for k, v in terms.items():
+        assert rel_err(step.last_terms[k].detach(), v.detach()) < 1e-4, k
+    assert rel_err(loss.detach(), ref.detach()) < 1e-4
+    for name, p in student.named_parameters():
+        if bn_shadowed_bias(name) or s_sd[name].grad is None:
+            continue
+        gr = s_sd[name].grad
+        assert torch.allclose(p.grad.cpu(), gr, rtol=5e-3, atol=2e-3 * gr.abs().max().item() + 1e-9), name
