@@ -50,6 +50,45 @@ __device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + __expf(-v))
 
 constexpr int AT = 256;
 
+// ---- cp.async software pipeline: every thread owns private 16-byte slots in shared memory
+// ([stage][slot][thread], so a warp's read-back is conflict free).  Loads for iteration i+D-1 are
+// in flight while iteration i computes: the bytes in flight per SM no longer depend on registers
+// or occupancy (these kernels are HBM-latency bound otherwise).
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp16(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp8(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 8 consecutive channels of type T = VB<T> bytes = NCP 16-byte slots
+template <typename T> struct Vec8 { static constexpr int NCP = sizeof(T) / 2; };
+template <typename T>
+__device__ __forceinline__ void cp_vec8(uint8_t* slot0, int slot_stride, const T* g) {
+#pragma unroll
+  for (int i = 0; i < Vec8<T>::NCP; ++i) cp16(slot0 + i * slot_stride, reinterpret_cast<const uint8_t*>(g) + 16 * i);
+}
+__device__ __forceinline__ void ld_vec8(const uint8_t* slot0, int slot_stride, const __nv_bfloat16*, float* o) {
+  const uint4 u = *reinterpret_cast<const uint4*>(slot0);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    o[2 * i] = f.x;
+    o[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void ld_vec8(const uint8_t* slot0, int slot_stride, const float*, float* o) {
+  const float4 a = *reinterpret_cast<const float4*>(slot0);
+  const float4 b = *reinterpret_cast<const float4*>(slot0 + slot_stride);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+constexpr int PD = 3;   // pipeline depth
+
 struct AbfGeom {
   int64_t M;      // rows B*T*F
   int F, Fy, C;   // F of this level, F of y_prev (F or F/2), channels
@@ -101,24 +140,58 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ watt, const float* __restrict__ batt,
                                                             T* __restrict__ xb, float* __restrict__ logits) {
-  extern __shared__ float cs[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* cs = reinterpret_cast<float*>(smem_raw);
+  constexpr int RQ = 2;
+  constexpr int NCP = Vec8<T>::NCP;
+  constexpr int NSLOT = 2 * RQ * NCP;                    // z1[q], y[q]
+  constexpr int SLOT_STRIDE = AT * 16;                   // bytes between consecutive slots of a thread
+  uint8_t* pipe = smem_raw + ((sizeof(float) * NCONST * g.C + 15) & ~(size_t)15) + threadIdx.x * 16;
   stage_consts(cs, g.C, mean, invstd, gamma, beta, watt, nullptr, 0., 0);
   const int lane = threadIdx.x & 31;
   const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
   const float b0 = batt ? batt[0] : 0.f, b1 = batt ? batt[1] : 0.f;
   const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
-  constexpr int RQ = 2;
-  for (int64_t m0 = warp0 * rpw * RQ; m0 < g.M; m0 += nwarps * rpw * RQ) {
+  const int64_t stride = nwarps * rpw * RQ;
+  const int64_t iters = (g.M + stride - 1) / stride;
+
+  auto issue = [&](int64_t it) {
+    if (it < iters) {
+      uint8_t* st = pipe + (size_t)(it % PD) * NSLOT * SLOT_STRIDE;
+      const int64_t m0 = (warp0 + it * nwarps) * rpw * RQ;
+#pragma unroll
+      for (int q = 0; q < RQ; ++q) {
+        const int64_t m = m0 + (int64_t)q * rpw + sub;
+        if (m < g.M) {
+          cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, z1 + m * g.C + cg * 8);
+          cp_vec8<T>(st + ((RQ + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, y + yrow(g, m) * g.C + cg * 8);
+        }
+      }
+    }
+    cp_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < PD - 1; ++i) issue(i);
+
+  for (int64_t it = 0; it < iters; ++it) {
+    issue(it + PD - 1);
+    cp_wait<PD - 1>();
+    const uint8_t* st = pipe + (size_t)(it % PD) * NSLOT * SLOT_STRIDE;
+    const int64_t m0 = (warp0 + it * nwarps) * rpw * RQ;
     float xv[RQ][8], yv[RQ][8];
     bool live[RQ];
 #pragma unroll
     for (int q = 0; q < RQ; ++q) {
       const int64_t m = m0 + (int64_t)q * rpw + sub;
       live[q] = m < g.M;
-      const int64_t mm = live[q] ? m : 0;
-      ld8(z1 + mm * g.C + cg * 8, xv[q]);
-      ld8(y + yrow(g, mm) * g.C + cg * 8, yv[q]);
+      if (live[q]) {
+        ld_vec8(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, xv[q]);
+        ld_vec8(st + ((RQ + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[q]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xv[q][e] = yv[q][e] = 0.f;
+      }
     }
     float l0[RQ], l1[RQ];
     {
@@ -185,9 +258,14 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
                                                             double* __restrict__ sums, double* __restrict__ dwatt,
                                                             double* __restrict__ dbatt, int training, T* __restrict__ dz1,
                                                             T* __restrict__ dy) {
-  extern __shared__ float cs[];   // [NCONST][C] constants, then (MODE 0) [6][C] + 2 reduction slots
+  extern __shared__ __align__(16) uint8_t smem_raw[];   // constants, (MODE 0) reduction slots, cp.async pipeline
+  float* cs = reinterpret_cast<float*>(smem_raw);
   const int C = g.C;
   float* red = cs + NCONST * C;
+  constexpr int NCP = Vec8<T>::NCP;
+  constexpr int NSLOT = 6 * NCP + 1;                     // g[2], z1[2], y[2] vectors + one slot for both logit pairs
+  constexpr int SLOT_STRIDE = AT * 16;
+  uint8_t* pipe = smem_raw + ((sizeof(float) * ((NCONST + 6) * C + 2) + 15) & ~(size_t)15) + threadIdx.x * 16;
   if (MODE == 0)
     for (int i = threadIdx.x; i < 6 * C + 2; i += AT) red[i] = 0.f;
   stage_consts(cs, C, mean, invstd, gamma, beta, watt, MODE == 1 ? sums : nullptr, 1.0 / (double)g.M, training);
@@ -201,31 +279,63 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
   const int64_t pairs = g.M >> 1;           // M is even (F is even)
   const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
-  for (int64_t p0 = warp0 * rpw; p0 < pairs; p0 += nwarps * rpw) {
-    const int64_t p = p0 + sub;
+  const int64_t stride = nwarps * rpw;
+  const int64_t iters = (pairs + stride - 1) / stride;
+
+  auto issue = [&](int64_t it) {
+    if (it < iters) {
+      uint8_t* st = pipe + (size_t)(it % PD) * NSLOT * SLOT_STRIDE;
+      const int64_t p = (warp0 + it * nwarps) * rpw + sub;
+      if (p < pairs) {
+        const int64_t m0 = 2 * p;
+        const int64_t yr0 = yrow(g, m0);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, gout + (m0 + q) * C + cg * 8);
+          cp_vec8<T>(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, z1 + (m0 + q) * C + cg * 8);
+        }
+        cp_vec8<T>(st + (4 * NCP) * SLOT_STRIDE, SLOT_STRIDE, y + yr0 * C + cg * 8);
+        if (g.Fy == g.F) cp_vec8<T>(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, y + (yr0 + 1) * C + cg * 8);
+        cp16(st + (6 * NCP) * SLOT_STRIDE, logits + 2 * m0);      // logits of rows m0 and m0+1 (16 bytes)
+      }
+    }
+    cp_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < PD - 1; ++i) issue(i);
+
+  for (int64_t it = 0; it < iters; ++it) {
+    issue(it + PD - 1);
+    cp_wait<PD - 1>();
+    const uint8_t* st = pipe + (size_t)(it % PD) * NSLOT * SLOT_STRIDE;
+    const int64_t p = (warp0 + it * nwarps) * rpw + sub;
     const bool live = p < pairs;
     const int64_t m0 = live ? 2 * p : 0;
+    const int64_t yr0 = yrow(g, m0);
     float gv[2][8], xv[2][8], yv[2][8];
     float2 lg[2];
+    if (live) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int64_t m = m0 + q;
-      ld8(gout + m * C + cg * 8, gv[q]);
-      ld8(z1 + m * C + cg * 8, xv[q]);
-      lg[q] = *reinterpret_cast<const float2*>(logits + 2 * m);
-    }
-    const int64_t yr0 = yrow(g, m0);
-    ld8(y + yr0 * C + cg * 8, yv[0]);
-    if (g.Fy == g.F) ld8(y + (yr0 + 1) * C + cg * 8, yv[1]);
-    else {
+      for (int q = 0; q < 2; ++q) {
+        ld_vec8(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, gv[q]);
+        ld_vec8(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, xv[q]);
+      }
+      ld_vec8(st + (4 * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[0]);
+      if (g.Fy == g.F) ld_vec8(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[1]);
+      else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) yv[1][e] = yv[0][e];
-    }
-    if (!live) {
+        for (int e = 0; e < 8; ++e) yv[1][e] = yv[0][e];
+      }
+      const float4 l4 = *reinterpret_cast<const float4*>(st + (6 * NCP) * SLOT_STRIDE);
+      lg[0] = make_float2(l4.x, l4.y);
+      lg[1] = make_float2(l4.z, l4.w);
+    } else {
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
+      for (int q = 0; q < 2; ++q) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) gv[q][e] = 0.f;
+        for (int e = 0; e < 8; ++e) gv[q][e] = xv[q][e] = yv[q][e] = 0.f;
+        lg[q] = make_float2(0.f, 0.f);
+      }
     }
     // xhat (kept in place of z1) and xp
     float xp[2][8];
@@ -392,10 +502,22 @@ extern "C" int clskd_abf_mid_fwd(const void* z1, const void* y, int dtype, int B
   g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
   if (g.M == 0) return CLSKD_OK;
   const int rows_per_warp_iter = (32 / g.tpr) * 2;
-  const int grid = abf_grid((g.M + rows_per_warp_iter - 1) / rows_per_warp_iter / 2);
+  const int grid = abf_grid((g.M + rows_per_warp_iter - 1) / rows_per_warp_iter / 4);
   cudaStream_t st = (cudaStream_t)stream;
-  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_fwd_kernel<TT><<<grid, AT, sizeof(float) * NCONST * (size_t)C, st>>>(
-                                      (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt, batt, (TT*)xb, logits)));
+  const size_t es = dtype == CLSKD_F32 ? 4 : 2;
+  const size_t cbytes = (sizeof(float) * NCONST * (size_t)C + 15) & ~(size_t)15;
+  const size_t sh = cbytes + (size_t)PD * (4 * (es / 2)) * AT * 16;
+  if (dtype == CLSKD_F32) {
+    static bool a0 = false;
+    if (!a0) { cudaFuncSetAttribute(abf_mid_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); a0 = true; }
+    abf_mid_fwd_kernel<float><<<grid, AT, sh, st>>>((const float*)z1, (const float*)y, g, mean, invstd, gamma, beta, watt,
+                                                    batt, (float*)xb, logits);
+  } else {
+    static bool a1 = false;
+    if (!a1) { cudaFuncSetAttribute(abf_mid_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); a1 = true; }
+    abf_mid_fwd_kernel<__nv_bfloat16><<<grid, AT, sh, st>>>((const __nv_bfloat16*)z1, (const __nv_bfloat16*)y, g, mean,
+                                                            invstd, gamma, beta, watt, batt, (__nv_bfloat16*)xb, logits);
+  }
   CLSKD_CHECK_LAUNCH("clskd_abf_mid_fwd");
   return CLSKD_OK;
 }
@@ -422,12 +544,22 @@ extern "C" int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y
   const int64_t pairs = g.M / 2;
   const int pairs_per_warp = 32 / g.tpr;
   const int grid = abf_grid((pairs + pairs_per_warp - 1) / pairs_per_warp / 4);
-  const size_t sh = sizeof(float) * ((NCONST + 6) * (size_t)C + 2);
+  const size_t es = dtype == CLSKD_F32 ? 4 : 2;
+  const size_t cbytes = (sizeof(float) * ((NCONST + 6) * (size_t)C + 2) + 15) & ~(size_t)15;
+  const size_t sh = cbytes + (size_t)PD * (6 * (es / 2) + 1) * AT * 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(abf_mid_bwd_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(abf_mid_bwd_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(abf_mid_bwd_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(abf_mid_bwd_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
   CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 0><<<grid, AT, sh, st>>>(
                                       (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt,
                                       logits, sums, dwatt, dbatt, training, nullptr, nullptr)));
   CLSKD_CHECK_LAUNCH("clskd_abf_mid_bwd(stats)");
-  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 1><<<grid, AT, sizeof(float) * NCONST * (size_t)C, st>>>(
+  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 1><<<grid, AT, sh, st>>>(
                                       (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt,
                                       logits, sums, dwatt, dbatt, training, (TT*)dz1, (TT*)dy)));
   CLSKD_CHECK_LAUNCH("clskd_abf_mid_bwd(apply)");

@@ -53,6 +53,7 @@ struct UmmaParams {
   uint32_t stage_region;       // bytes of the operand ring (staging buffers follow it)
   uint32_t staging_bytes;      // one staging buffer: 128 rows x block_n x es
   int nstg;                    // 1 or 2 staging buffers (double-buffered TMA stores)
+  int ecols;                   // columns staged per TMA-store round (<= 128): block_n / ecols rounds per tile
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -171,6 +172,7 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t xr = pitch == 128 ? (uint32_t)(row & 7) : (pitch == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1));
     const bool issuer = (threadIdx.x == 64);                    // first epilogue thread
     int local = 0;
+    int sround = 0;                                             // staging rounds issued so far
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const int n_tile = tile % p.tiles_n;
@@ -182,58 +184,65 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int n0 = n_tile * p.block_n;
       mbar_wait(&tmem_full_bar[as], (local >> 1) & 1);
       fence_after();
-      // the TMA store that last used this staging buffer must have finished reading it
-      uint8_t* stg = stg_base + (size_t)((p.nstg == 2) ? (local & 1) : 0) * p.staging_bytes;
-      if (issuer) {
-        if (p.nstg == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c), v);
-        float o[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
-        if (p.bias) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
+      const int t0 = t_blk * p.t_tile, f0 = f_blk * p.fo_tile;
+      const int rounds = p.block_n / p.ecols;
+      for (int rd = 0; rd < rounds; ++rd, ++sround) {
+        // the TMA store that last used this staging buffer must have finished reading it
+        uint8_t* stg = stg_base + (size_t)((p.nstg == 2) ? (sround & 1) : 0) * p.staging_bytes;
+        if (issuer) {
+          if (p.nstg == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        const int sub = c / p.gw_y, col = c - sub * p.gw_y;
-        uint8_t* rowp = stg + (size_t)sub * p.y_sub_bytes + (size_t)row * pitch;
-        const uint32_t ch0 = (uint32_t)(col * p.es) >> 4;          // first 16-byte chunk of these 16 columns
-        if (p.es == 2) {
-          uint32_t pk[8];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int cbeg = rd * p.ecols;
+        for (int c = cbeg; c < cbeg + p.ecols; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c), v);
+          float o[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+          if (p.bias) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
           }
-          *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ xr) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ xr) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        } else {
+          const int cl = c - cbeg;
+          const int sub = cl / p.gw_y, col = cl - sub * p.gw_y;
+          uint8_t* rowp = stg + (size_t)sub * p.y_sub_bytes + (size_t)row * pitch;
+          const uint32_t ch0 = (uint32_t)(col * p.es) >> 4;          // first 16-byte chunk of these 16 columns
+          if (p.es == 2) {
+            uint32_t pk[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            *reinterpret_cast<float4*>(rowp + (((ch0 + e) ^ xr) << 4)) =
-                make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+            for (int e = 0; e < 8; ++e) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ xr) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ xr) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              *reinterpret_cast<float4*>(rowp + (((ch0 + e) ^ xr) << 4)) =
+                  make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+          }
         }
-      }
-      // accumulator drained: hand the TMEM buffer back to the MMA warp
-      fence_before();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
-      // make the generic-proxy smem writes visible to the async proxy, then one thread stores
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (issuer) {
-        const int t0 = t_blk * p.t_tile, f0 = f_blk * p.fo_tile;
-        for (int sidx = 0; sidx < p.block_n / p.gw_y; ++sidx) {
-          asm volatile(
-              "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                  reinterpret_cast<uint64_t>(&tmY)),
-              "r"(smem_u32(stg + (size_t)sidx * p.y_sub_bytes)), "r"(n0 + sidx * p.gw_y), "r"(f0), "r"(t0), "r"(b)
-              : "memory");
+        if (rd == rounds - 1) {
+          // accumulator drained: hand the TMEM buffer back to the MMA warp
+          fence_before();
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
         }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // make the generic-proxy smem writes visible to the async proxy, then one thread stores
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          for (int sidx = 0; sidx < p.ecols / p.gw_y; ++sidx) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(&tmY)),
+                "r"(smem_u32(stg + (size_t)sidx * p.y_sub_bytes)), "r"(n0 + cbeg + sidx * p.gw_y), "r"(f0), "r"(t0), "r"(b)
+                : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
@@ -341,12 +350,14 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   while (cols < 2 * p.block_n) cols <<= 1;     // double-buffered accumulator
   p.tmem_cols = (uint32_t)cols;
   const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-  const uint32_t staging_bytes = (uint32_t)UM * p.block_n * p.es;
+  p.ecols = p.block_n > 128 ? 128 : p.block_n;     // block_n is 256 or <= 128 here... (256 = 2 rounds)
+  if (p.block_n % p.ecols) p.ecols = p.block_n;
+  const uint32_t staging_bytes = (uint32_t)UM * p.ecols * p.es;
   p.staging_bytes = staging_bytes;
   // two CTAs per SM when the accumulators (2 x 2 x block_n TMEM columns) and ~110 KB of smem each
   // allow it: their serial per-tile latencies (TMA -> MMA -> TMEM drain -> store) overlap
   const bool two_ctas = 2 * cols <= 512 && staging_bytes <= 32 * 1024;
-  const uint32_t budget = two_ctas ? 108u * 1024u : 200u * 1024u;
+  const uint32_t budget = two_ctas ? 108u * 1024u : 222u * 1024u;
   p.nstg = (2 * staging_bytes + 2 * stage_bytes <= budget) ? 2 : 1;
   int stages = (int)((budget - p.nstg * staging_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
