@@ -347,8 +347,15 @@ def run_ours(args):
         n_launch = max(1, len(kt.pairs))
         k_ms = kt.total_ms()
         achieved = kt.flops / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
+        traffic = None
+        try:      # dram bytes per launch of the same kernel from the committed `ncu --set full` capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            if tj.get("entry_point") == kname:
+                traffic = tj.get("traffic_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                    "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
                     "launches_timed": len(kt.pairs), "avg_launch_ms": k_ms / n_launch,
                     "share_of_step": k_ms / ms if ms > 0 else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF (of fallback)",

@@ -343,7 +343,7 @@ def test_distill_step_golden(dev, mode):
         if bn_shadowed_bias(name):
             continue
         assert params[name].grad is not None, name
-        check_summary(params[name].grad, gref, rtol=2e-3, atol=1e-7, what="grad " + name)
+        check_summary(params[name].grad, gref, rtol=2e-3, atol=5e-7, what="grad " + name)   # fp32 reduction-order noise
     if mode == "clskd":
         for key, rk in (("abf_enc_grads", step.abf_encoder), ("abf_dec_grads", step.abf_decoder)):
             ps = dict(rk.named_parameters())
