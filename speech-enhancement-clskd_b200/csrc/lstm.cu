@@ -16,7 +16,11 @@ constexpr int RB = 4;
 
 __device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + expf(-v)); }
 
-// WMODE 0: W^T fp32 in smem; 1: W^T bf16 in smem; 2: W^T read from global (L2)
+// One thread owns hidden unit j of RB = 4 batch rows: all four gates of its cells, so the gate
+// math needs no exchange and the only per-step traffic through shared memory is the broadcast read
+// of h (one float4 = the 4 rows of h_k per k) and the 4-gate weight vector W[k][j][0..3] (8 bytes
+// in bf16, 16 bytes in fp32): 2 shared loads per 16 FMAs.  h is double-buffered -> one barrier per
+// time step.  WMODE 0: weights fp32 in smem; 1: bf16 in smem; 2: fp32 from global / L2.
 template <int WMODE>
 __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ whh_t,
                                 int T, int R, int Bp, int H, int64_t pre_pstride,
@@ -25,7 +29,7 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
                                 float* __restrict__ gates_out, float* __restrict__ c_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int G = 4 * H;
-  const int tid = threadIdx.x;  // gate row g
+  const int j = threadIdx.x;  // hidden unit
   const int set = blockIdx.y;
   const int r0 = blockIdx.x * RB;
   const int64_t out_set_stride = (int64_t)T * R * H;
@@ -35,94 +39,110 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
   if (gates_out) gates_out += (int64_t)set * out_set_stride * 4;
   if (c_out) c_out += (int64_t)set * out_set_stride;
 
-  float* h_s = reinterpret_cast<float*>(smem_raw);          // [RB][H]
-  float* g_s = h_s + RB * H;                                  // [RB][4H]
-  float* w_f = g_s + RB * G;                                  // [H][4H] fp32 (WMODE 0)
-  __nv_bfloat16* w_b = reinterpret_cast<__nv_bfloat16*>(w_f); // [H][4H] bf16 (WMODE 1)
+  float4* h_s = reinterpret_cast<float4*>(smem_raw);                 // [2][H] : (rows 0..3 of h_k)
+  float4* w_f = h_s + 2 * H;                                          // [H][H] float4 (WMODE 0)
+  uint2* w_b = reinterpret_cast<uint2*>(h_s + 2 * H);                 // [H][H] 4 x bf16 (WMODE 1)
 
+  // W_hh^T is [k][g*H + j]; stage it as [k][j][g]
   if (WMODE == 0) {
-    for (int i = tid; i < H * G; i += blockDim.x) w_f[i] = whh_t[i];
+    for (int i = j; i < H * H; i += blockDim.x) {
+      const int k = i / H, jj = i - k * H;
+      const float* wp = whh_t + (int64_t)k * G + jj;
+      w_f[i] = make_float4(wp[0], wp[H], wp[2 * H], wp[3 * H]);
+    }
   } else if (WMODE == 1) {
-    for (int i = tid; i < H * G; i += blockDim.x) w_b[i] = __float2bfloat16_rn(whh_t[i]);
+    for (int i = j; i < H * H; i += blockDim.x) {
+      const int k = i / H, jj = i - k * H;
+      const float* wp = whh_t + (int64_t)k * G + jj;
+      __nv_bfloat162 a = __floats2bfloat162_rn(wp[0], wp[H]), b = __floats2bfloat162_rn(wp[2 * H], wp[3 * H]);
+      w_b[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
   }
-  for (int i = tid; i < RB * H; i += blockDim.x) h_s[i] = 0.f;
+  h_s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float c_state[RB] = {0.f, 0.f, 0.f, 0.f};
 
-  // cell ownership: thread tid -> (row cr, unit cj); valid because blockDim = 4H = RB*H
-  const int cr = tid / H, cj = tid - cr * H;
-  float c_state = 0.f;
-
-  // row r -> (part, batch): pre row base and output row index (without the time term)
+  // pre-activation addresses of (row r, gate g, unit j) without the time term
   int64_t prow[RB];
+  int64_t orow[RB];
 #pragma unroll
   for (int r = 0; r < RB; ++r) {
-    int rr = min(r0 + r, R - 1);
-    prow[r] = (int64_t)(rr / Bp) * pre_pstride + (int64_t)(rr % Bp) * pre_ld + tid;
+    const int rr = min(r0 + r, R - 1);
+    prow[r] = (int64_t)(rr / Bp) * pre_pstride + (int64_t)(rr % Bp) * pre_ld + j;
+    orow[r] = (int64_t)(rr / Bp) * T * Bp + (rr % Bp);                // output row ((part*T + t)*Bp + b) at t = 0
   }
-  float pcur[RB], pnext[RB];
+  float pcur[RB][4], pnext[RB][4];
 #pragma unroll
-  for (int r = 0; r < RB; ++r) {
-    pcur[r] = (r0 + r < R && T > 0) ? pre[prow[r]] : 0.f;
-    pnext[r] = 0.f;
-  }
-  // output row of this thread's cell: ((part*T + t)*Bp + b)
-  const int crow = min(r0 + cr, R - 1);
-  const int64_t orow_base = (int64_t)(crow / Bp) * T * Bp + (crow % Bp);
+  for (int r = 0; r < RB; ++r)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      pcur[r][g] = (r0 + r < R && T > 0) ? pre[prow[r] + g * H] : 0.f;
+      pnext[r][g] = 0.f;
+    }
   __syncthreads();
 
   for (int t = 0; t < T; ++t) {
     if (t + 1 < T) {
 #pragma unroll
       for (int r = 0; r < RB; ++r)
-        if (r0 + r < R) pnext[r] = pre[prow[r] + (int64_t)(t + 1) * pre_tstride];
-    }
-    float acc[RB];
+        if (r0 + r < R) {
 #pragma unroll
-    for (int r = 0; r < RB; ++r) acc[r] = pcur[r];
-    for (int k = 0; k < H; k += 4) {
+          for (int g = 0; g < 4; ++g) pnext[r][g] = pre[prow[r] + (int64_t)(t + 1) * pre_tstride + g * H];
+        }
+    }
+    float acc[RB][4];
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[r][g] = pcur[r][g];
+    const float4* hb = h_s + (t & 1) * H;
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) {
       float w[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (WMODE == 0) w[e] = w_f[(k + e) * G + tid];
-        else if (WMODE == 1) w[e] = __bfloat162float(w_b[(k + e) * G + tid]);
-        else w[e] = __ldg(whh_t + (int64_t)(k + e) * G + tid);
+      if (WMODE == 0) {
+        const float4 wv = w_f[k * H + j];
+        w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w;
+      } else if (WMODE == 1) {
+        const uint2 wv = w_b[k * H + j];
+        w[0] = __uint_as_float(wv.x << 16);
+        w[1] = __uint_as_float(wv.x & 0xffff0000u);
+        w[2] = __uint_as_float(wv.y << 16);
+        w[3] = __uint_as_float(wv.y & 0xffff0000u);
+      } else {
+        const float* wp = whh_t + (int64_t)k * G + j;
+        w[0] = __ldg(wp); w[1] = __ldg(wp + H); w[2] = __ldg(wp + 2 * H); w[3] = __ldg(wp + 3 * H);
       }
+      const float4 hv = hb[k];
+      const float hr[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        float4 hv = *reinterpret_cast<const float4*>(h_s + r * H + k);
-        acc[r] = fmaf(w[0], hv.x, acc[r]);
-        acc[r] = fmaf(w[1], hv.y, acc[r]);
-        acc[r] = fmaf(w[2], hv.z, acc[r]);
-        acc[r] = fmaf(w[3], hv.w, acc[r]);
-      }
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[r][g] = fmaf(w[g], hr[r], acc[r][g]);
     }
+    float hn[RB];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) g_s[r * G + tid] = acc[r];
-    __syncthreads();
-    // gate math: one (row, unit) per thread
-    {
-      float gi = sigm(g_s[cr * G + cj]);
-      float gf = sigm(g_s[cr * G + H + cj]);
-      float gg = tanhf(g_s[cr * G + 2 * H + cj]);
-      float go = sigm(g_s[cr * G + 3 * H + cj]);
-      c_state = gf * c_state + gi * gg;
-      float hv = go * tanhf(c_state);
-      h_s[cr * H + cj] = hv;
-      if (r0 + cr < R) {
-        int64_t row = orow_base + (int64_t)t * Bp;
-        h_out[row * H + cj] = hv;
+    for (int r = 0; r < RB; ++r) {
+      const float gi = sigm(acc[r][0]), gf = sigm(acc[r][1]), gg = tanhf(acc[r][2]), go = sigm(acc[r][3]);
+      c_state[r] = gf * c_state[r] + gi * gg;
+      hn[r] = go * tanhf(c_state[r]);
+      if (r0 + r < R) {
+        const int64_t row = orow[r] + (int64_t)t * Bp;
+        h_out[row * H + j] = hn[r];
         if (gates_out) {
           float* gp = gates_out + row * G;
-          gp[cj] = gi;
-          gp[H + cj] = gf;
-          gp[2 * H + cj] = gg;
-          gp[3 * H + cj] = go;
+          gp[j] = gi;
+          gp[H + j] = gf;
+          gp[2 * H + j] = gg;
+          gp[3 * H + j] = go;
         }
-        if (c_out) c_out[row * H + cj] = c_state;
+        if (c_out) c_out[row * H + j] = c_state[r];
       }
     }
+    h_s[((t + 1) & 1) * H + j] = make_float4(hn[0], hn[1], hn[2], hn[3]);
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RB; ++r) pcur[r] = pnext[r];
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pcur[r][g] = pnext[r][g];
   }
 }
 
@@ -231,25 +251,24 @@ extern "C" int clskd_lstm_fwd(const float* pre, const float* whh_t, int T, int R
                               int64_t pre_set_stride, int64_t whh_set_stride, int w_bf16, float* h,
                               float* gates, float* c, void* stream) {
   CLSKD_CHECK_ARG(pre && whh_t && h, "clskd_lstm_fwd: null pointer");
-  CLSKD_CHECK_ARG(H >= 4 && H % 4 == 0 && 4 * H <= 1024, "clskd_lstm_fwd: H=%d unsupported (4..256, multiple of 4)", H);
+  CLSKD_CHECK_ARG(H >= 4 && H % 4 == 0 && H <= 1024, "clskd_lstm_fwd: H=%d unsupported (4..1024, multiple of 4)", H);
   CLSKD_CHECK_ARG(T >= 0 && R >= 1 && nsets >= 1 && Bp >= 1 && R % Bp == 0, "clskd_lstm_fwd: bad extents");
   if (T == 0) return CLSKD_OK;
-  const int G = 4 * H;
-  size_t base = sizeof(float) * ((size_t)RB * H + (size_t)RB * G);
-  size_t w32 = sizeof(float) * (size_t)H * G, w16 = w32 / 2;
+  size_t base = sizeof(float4) * 2 * (size_t)H;
+  size_t w32 = sizeof(float4) * (size_t)H * H, w16 = w32 / 2;
   dim3 grid(cdiv(R, RB), nsets);
   cudaError_t e;
 #define LSTM_FWD_ARGS pre, whh_t, T, R, Bp, H, pre_pstride, pre_tstride, pre_ld, pre_set_stride, whh_set_stride, h, gates, c
   if (!w_bf16 && base + w32 <= kSmemLimit) {
     e = cudaFuncSetAttribute(lstm_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
     if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
-    lstm_fwd_kernel<0><<<grid, G, base + w32, ST>>>(LSTM_FWD_ARGS);
+    lstm_fwd_kernel<0><<<grid, H, base + w32, ST>>>(LSTM_FWD_ARGS);
   } else if (w_bf16 && base + w16 <= kSmemLimit) {
     e = cudaFuncSetAttribute(lstm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w16));
     if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
-    lstm_fwd_kernel<1><<<grid, G, base + w16, ST>>>(LSTM_FWD_ARGS);
+    lstm_fwd_kernel<1><<<grid, H, base + w16, ST>>>(LSTM_FWD_ARGS);
   } else {
-    lstm_fwd_kernel<2><<<grid, G, base, ST>>>(LSTM_FWD_ARGS);
+    lstm_fwd_kernel<2><<<grid, H, base, ST>>>(LSTM_FWD_ARGS);
   }
 #undef LSTM_FWD_ARGS
   CLSKD_CHECK_LAUNCH("clskd_lstm_fwd");
