@@ -240,6 +240,8 @@ class KernelTimer:
 
 def tapconv_work(a):
     """algorithmic FLOPs / bytes of one tapconv launch from its descriptor"""
+    if not hasattr(a[0], "_obj"):
+        return 0.0, 0.0          # not a tap-list contraction (only its time is reported)
     d = a[0]._obj
     M = d.B * d.To * d.Fo
     K = d.ntaps * (d.c0 + d.c1)
@@ -251,6 +253,8 @@ def tapconv_work(a):
 
 
 def tapconv_shape(a):
+    if not hasattr(a[0], "_obj"):
+        return {"M": 0, "taps": 0, "C": 0, "N": 0, "Fo": 0, "sf": 0, "out": "-"}
     d = a[0]._obj
     return {"M": d.B * d.To * d.Fo, "taps": d.ntaps, "C": d.c0 + d.c1, "N": d.N, "Fo": d.Fo, "sf": d.sf,
             "out": "bf16" if d.y_dtype == 1 else "f32"}

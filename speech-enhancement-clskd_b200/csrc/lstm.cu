@@ -21,7 +21,7 @@ __device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + expf(-v)); 
 // of h (one float4 = the 4 rows of h_k per k) and the 4-gate weight vector W[k][j][0..3] (8 bytes
 // in bf16, 16 bytes in fp32): 2 shared loads per 16 FMAs.  h is double-buffered -> one barrier per
 // time step.  WMODE 0: weights fp32 in smem; 1: bf16 in smem; 2: fp32 from global / L2.
-template <int WMODE>
+template <int WMODE, int RBF>
 __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ whh_t,
                                 int T, int R, int Bp, int H, int64_t pre_pstride,
                                 int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride,
@@ -31,7 +31,7 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
   const int G = 4 * H;
   const int j = threadIdx.x;  // hidden unit
   const int set = blockIdx.y;
-  const int r0 = blockIdx.x * RB;
+  const int r0 = blockIdx.x * RBF;
   const int64_t out_set_stride = (int64_t)T * R * H;
   pre += (int64_t)set * pre_set_stride;
   whh_t += (int64_t)set * whh_set_stride;
@@ -39,9 +39,9 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
   if (gates_out) gates_out += (int64_t)set * out_set_stride * 4;
   if (c_out) c_out += (int64_t)set * out_set_stride;
 
-  float4* h_s = reinterpret_cast<float4*>(smem_raw);                 // [2][H] : (rows 0..3 of h_k)
-  float4* w_f = h_s + 2 * H;                                          // [H][H] float4 (WMODE 0)
-  uint2* w_b = reinterpret_cast<uint2*>(h_s + 2 * H);                 // [H][H] 4 x bf16 (WMODE 1)
+  float* h_s = reinterpret_cast<float*>(smem_raw);                   // [2][H][RBF] : (rows of h_k)
+  float4* w_f = reinterpret_cast<float4*>(h_s + 2 * H * 4);           // [H][H] float4 (WMODE 0)
+  uint2* w_b = reinterpret_cast<uint2*>(h_s + 2 * H * 4);             // [H][H] 4 x bf16 (WMODE 1)
 
   // W_hh^T is [k][g*H + j]; stage it as [k][j][g]
   if (WMODE == 0) {
@@ -58,21 +58,24 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
       w_b[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
     }
   }
-  h_s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float c_state[RB] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < RBF; ++r) h_s[j * RBF + r] = 0.f;
+  float c_state[RBF];
+#pragma unroll
+  for (int r = 0; r < RBF; ++r) c_state[r] = 0.f;
 
   // pre-activation addresses of (row r, gate g, unit j) without the time term
-  int64_t prow[RB];
-  int64_t orow[RB];
+  int64_t prow[RBF];
+  int64_t orow[RBF];
 #pragma unroll
-  for (int r = 0; r < RB; ++r) {
+  for (int r = 0; r < RBF; ++r) {
     const int rr = min(r0 + r, R - 1);
     prow[r] = (int64_t)(rr / Bp) * pre_pstride + (int64_t)(rr % Bp) * pre_ld + j;
     orow[r] = (int64_t)(rr / Bp) * T * Bp + (rr % Bp);                // output row ((part*T + t)*Bp + b) at t = 0
   }
-  float pcur[RB][4], pnext[RB][4];
+  float pcur[RBF][4], pnext[RBF][4];
 #pragma unroll
-  for (int r = 0; r < RB; ++r)
+  for (int r = 0; r < RBF; ++r)
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       pcur[r][g] = (r0 + r < R && T > 0) ? pre[prow[r] + g * H] : 0.f;
@@ -83,18 +86,18 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
   for (int t = 0; t < T; ++t) {
     if (t + 1 < T) {
 #pragma unroll
-      for (int r = 0; r < RB; ++r)
+      for (int r = 0; r < RBF; ++r)
         if (r0 + r < R) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) pnext[r][g] = pre[prow[r] + (int64_t)(t + 1) * pre_tstride + g * H];
         }
     }
-    float acc[RB][4];
+    float acc[RBF][4];
 #pragma unroll
-    for (int r = 0; r < RB; ++r)
+    for (int r = 0; r < RBF; ++r)
 #pragma unroll
       for (int g = 0; g < 4; ++g) acc[r][g] = pcur[r][g];
-    const float4* hb = h_s + (t & 1) * H;
+    const float* hb = h_s + (t & 1) * H * RBF;
 #pragma unroll 4
     for (int k = 0; k < H; ++k) {
       float w[4];
@@ -111,16 +114,22 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
         const float* wp = whh_t + (int64_t)k * G + j;
         w[0] = __ldg(wp); w[1] = __ldg(wp + H); w[2] = __ldg(wp + 2 * H); w[3] = __ldg(wp + 3 * H);
       }
-      const float4 hv = hb[k];
-      const float hr[4] = {hv.x, hv.y, hv.z, hv.w};
+      float hr[RBF];
+      if (RBF == 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hb + k * 4);
+        hr[0] = hv.x; hr[1] = hv.y; hr[2 % RBF] = hv.z; hr[3 % RBF] = hv.w;
+      } else {
+        const float2 hv = *reinterpret_cast<const float2*>(hb + k * 2);
+        hr[0] = hv.x; hr[1] = hv.y;
+      }
 #pragma unroll
-      for (int r = 0; r < RB; ++r)
+      for (int r = 0; r < RBF; ++r)
 #pragma unroll
         for (int g = 0; g < 4; ++g) acc[r][g] = fmaf(w[g], hr[r], acc[r][g]);
     }
-    float hn[RB];
+    float hn[RBF];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
+    for (int r = 0; r < RBF; ++r) {
       const float gi = sigm(acc[r][0]), gf = sigm(acc[r][1]), gg = tanhf(acc[r][2]), go = sigm(acc[r][3]);
       c_state[r] = gf * c_state[r] + gi * gg;
       hn[r] = go * tanhf(c_state[r]);
@@ -137,10 +146,11 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
         if (c_out) c_out[row * H + j] = c_state[r];
       }
     }
-    h_s[((t + 1) & 1) * H + j] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+#pragma unroll
+    for (int r = 0; r < RBF; ++r) h_s[((t + 1) & 1) * H * RBF + j * RBF + r] = hn[r];
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RB; ++r)
+    for (int r = 0; r < RBF; ++r)
 #pragma unroll
       for (int g = 0; g < 4; ++g) pcur[r][g] = pnext[r][g];
   }
@@ -256,19 +266,27 @@ extern "C" int clskd_lstm_fwd(const float* pre, const float* whh_t, int T, int R
   if (T == 0) return CLSKD_OK;
   size_t base = sizeof(float4) * 2 * (size_t)H;
   size_t w32 = sizeof(float4) * (size_t)H * H, w16 = w32 / 2;
-  dim3 grid(cdiv(R, RB), nsets);
+  // 2 rows per CTA while that still leaves every CTA its own SM (the recurrence is FMA-issue bound
+  // per SM), 4 rows per CTA for large batches
+  const bool rb2 = (int64_t)cdiv(R, 2) * nsets <= (int64_t)sm_count();
+  dim3 grid(cdiv(R, rb2 ? 2 : 4), nsets);
   cudaError_t e;
 #define LSTM_FWD_ARGS pre, whh_t, T, R, Bp, H, pre_pstride, pre_tstride, pre_ld, pre_set_stride, whh_set_stride, h, gates, c
   if (!w_bf16 && base + w32 <= kSmemLimit) {
-    e = cudaFuncSetAttribute(lstm_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
+    e = cudaFuncSetAttribute(lstm_fwd_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
     if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
-    lstm_fwd_kernel<0><<<grid, H, base + w32, ST>>>(LSTM_FWD_ARGS);
+    if (rb2) lstm_fwd_kernel<0, 2><<<grid, H, base + w32, ST>>>(LSTM_FWD_ARGS);
+    else lstm_fwd_kernel<0, 4><<<grid, H, base + w32, ST>>>(LSTM_FWD_ARGS);
   } else if (w_bf16 && base + w16 <= kSmemLimit) {
-    e = cudaFuncSetAttribute(lstm_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w16));
+    e = cudaFuncSetAttribute(lstm_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w16));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w16));
     if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
-    lstm_fwd_kernel<1><<<grid, H, base + w16, ST>>>(LSTM_FWD_ARGS);
+    if (rb2) lstm_fwd_kernel<1, 2><<<grid, H, base + w16, ST>>>(LSTM_FWD_ARGS);
+    else lstm_fwd_kernel<1, 4><<<grid, H, base + w16, ST>>>(LSTM_FWD_ARGS);
   } else {
-    lstm_fwd_kernel<2><<<grid, H, base, ST>>>(LSTM_FWD_ARGS);
+    if (rb2) lstm_fwd_kernel<2, 2><<<grid, H, base, ST>>>(LSTM_FWD_ARGS);
+    else lstm_fwd_kernel<2, 4><<<grid, H, base, ST>>>(LSTM_FWD_ARGS);
   }
 #undef LSTM_FWD_ARGS
   CLSKD_CHECK_LAUNCH("clskd_lstm_fwd");
