@@ -124,6 +124,43 @@ def _bn_prelu(x, sd, prefix, training, eps=1e-5, momentum=0.1, update=None):
     return F.prelu(y, sd[prefix + '2.weight'])
 
 
+# ------------------------------------------------------------------ tools_for_model.py:398-508
+def complex_batch_norm(x, p, training, eps=1e-5, momentum=0.1, update=None):
+    """ComplexBatchNorm.forward (Trabelsi 2x2 whitening).  p: dict with Wrr, Wri, Wii, Br, Bi and the
+    running buffers RMr, RMi, RVrr, RVri, RVii; x: [B, 2C, ...] (real half then imag half of dim 1).
+    When training, the lerp-updated running buffers are returned in `update`."""
+    xr, xi = torch.chunk(x, 2, 1)
+    red = [d for d in range(xr.dim()) if d != 1]
+    vdim = [1] * xr.dim()
+    vdim[1] = xr.size(1)
+    if training:
+        Mr, Mi = xr.mean(red, keepdim=True), xi.mean(red, keepdim=True)          # :424-428
+    else:
+        Mr, Mi = p['RMr'].view(vdim), p['RMi'].view(vdim)
+    xr, xi = xr - Mr, xi - Mi                                                   # :435
+    if training:
+        Vrr, Vri, Vii = (xr * xr).mean(red, keepdim=True), (xr * xi).mean(red, keepdim=True), \
+            (xi * xi).mean(red, keepdim=True)                                   # :444-450
+        if update is not None:                                                  # lerp_ :433-434,455-457
+            for k, v in (('RMr', Mr), ('RMi', Mi), ('RVrr', Vrr), ('RVri', Vri), ('RVii', Vii)):
+                update[k] = p[k] + momentum * (v.reshape(-1) - p[k])
+    else:
+        Vrr, Vri, Vii = p['RVrr'].view(vdim), p['RVri'].view(vdim), p['RVii'].view(vdim)
+    Vrr, Vii = Vrr + eps, Vii + eps                                             # :462-464
+    tau = Vrr + Vii
+    delta = Vrr * Vii - Vri * Vri                                               # :472
+    s_ = delta.sqrt()
+    t = (tau + 2 * s_).sqrt()
+    rst = (s_ * t).reciprocal()                                                 # :477
+    Urr, Uii, Uri = (s_ + Vii) * rst, (s_ + Vrr) * rst, -Vri * rst
+    Wrr, Wri, Wii = p['Wrr'].view(vdim), p['Wri'].view(vdim), p['Wii'].view(vdim)
+    Zrr, Zri = Wrr * Urr + Wri * Uri, Wrr * Uri + Wri * Uii                     # :493-496
+    Zir, Zii = Wri * Urr + Wii * Uri, Wri * Uri + Wii * Uii
+    yr = Zrr * xr + Zri * xi + p['Br'].view(vdim)
+    yi = Zir * xr + Zii * xi + p['Bi'].view(vdim)
+    return torch.cat([yr, yi], 1)
+
+
 def mask_apply(real, imag, mask_real, mask_imag, mode):
     """DCCRN.py:153,159,212-230"""
     if mode == 'E':

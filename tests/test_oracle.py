@@ -174,3 +174,30 @@ def test_oracle_against_live_reference():
             out = D.dccrn_forward(sd, x, masking_mode=mode)
         for a, b in zip(out, ref):
             assert (a - b).abs().max().item() < 1e-5, mode
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("training", [True, False])
+def test_complex_batch_norm_oracle_against_live_reference(training):
+    import warnings
+    mods = ref_shim.load()
+    g = torch.Generator().manual_seed(3)
+    m = mods["tools_for_model"].ComplexBatchNorm(12)
+    for n_, b in m.named_buffers():
+        if b.is_floating_point():
+            b.copy_(0.5 + torch.rand(b.shape, generator=g) if "RV" in n_ and "ri" not in n_ else 0.1 * torch.randn(b.shape, generator=g))
+    m.Br.data.normal_(generator=g)
+    m.Bi.data.normal_(generator=g)
+    p = {k: v.detach().clone() for k, v in list(m.named_parameters()) + list(m.named_buffers())}
+    x = torch.randn(3, 12, 5, 7, generator=g)
+    m.train(training)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with torch.no_grad():
+            ref = m(x)
+    upd = {}
+    out = D.complex_batch_norm(x, p, training, update=upd)
+    assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5)
+    if training:
+        for k, v in upd.items():
+            assert torch.allclose(v, getattr(m, k), atol=1e-6), k

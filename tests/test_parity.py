@@ -504,3 +504,41 @@ def test_reviewkd_step_vs_oracle(dev):
             continue
         gr = s_sd[name].grad
         assert torch.allclose(p.grad.cpu(), gr, rtol=5e-3, atol=2e-3 * gr.abs().max().item() + 1e-9), name
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_complex_batch_norm_vs_oracle(dev, training):
+    """ComplexBatchNorm (tools_for_model.py:335-512; use_cbn=True) forward, train and eval statistics"""
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(3)
+    m = tm.ComplexBatchNorm(12)
+    for n_, b in m.named_buffers():
+        if b.is_floating_point():
+            b.copy_(0.5 + torch.rand(b.shape, generator=g) if ("RV" in n_ and "ri" not in n_)
+                    else 0.1 * torch.randn(b.shape, generator=g))
+    m.Br.data.normal_(generator=g)
+    m.Bi.data.normal_(generator=g)
+    p = {k: v.detach().clone() for k, v in list(m.named_parameters()) + list(m.named_buffers())}
+    x = torch.randn(3, 12, 6, 7, generator=g)
+    upd = {}
+    ref = D.complex_batch_norm(x, p, training, update=upd)
+    m = m.to(dev)
+    m.train(training)
+    with torch.no_grad():
+        out = m(x.to(dev))
+    assert torch.allclose(out.cpu(), ref, atol=1e-5, rtol=1e-5)
+    if training:
+        for k, v in upd.items():
+            assert torch.allclose(getattr(m, k).cpu(), v, atol=1e-6), k
+        assert int(m.num_batches_tracked) == 1
+
+
+def test_dccrn_with_complex_batch_norm_runs(dev):
+    """use_cbn=True model variant (DCCRN.py:80-81): forward under no_grad produces the reference shapes"""
+    import clskd_b200
+    m = clskd_b200.DCCRN(rnn_units=16, use_clstm=True, use_cbn=True, kernel_num=[4, 8, 8, 16, 16, 16]).to(dev).eval()
+    with torch.no_grad():
+        out = m(0.1 * torch.randn(2, 1600, generator=torch.Generator().manual_seed(0)).to(dev))
+    assert out[-1].shape == (2, 1600) and torch.isfinite(out[-1]).all()
+    assert out[0].shape == (2, 257, 19)
