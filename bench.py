@@ -367,7 +367,7 @@ def run_ours(args):
         step_gflop = B * args.seconds / 4.0 * (FWD_GFLOP["teacher"] + 3 * FWD_GFLOP[args.student] +
                                                (3 * ABF_GFLOP[args.student] if args.mode == "clskd" else 0.0))
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             step, a_s = cpu_step_fn(args.student, args.cpu_batch, args.seconds, args.mode)
             dt = time_cpu(step, 1, warm=1)
             cores = os.cpu_count() or 1

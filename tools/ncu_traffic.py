@@ -1,7 +1,7 @@
 """Summarise an `ncu --set full` report of one kernel: per-launch DRAM traffic, duration, tensor-pipe
 and memory-throughput percentages.  Writes a markdown summary and a small JSON that bench.py reads
 for the `roofline.traffic` field.
-Usage: python tools/ncu_traffic.py report.ncu-rep kernel_tag out.md out.json"""
+Usage: python tools/ncu_traffic.py report.ncu-rep|raw.csv kernel_tag out.md out.json"""
 import csv
 import io
 import json
@@ -25,7 +25,10 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us":
 
 def main():
     rep, tag, out_md, out_json = sys.argv[1:5]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):        # already exported with `ncu -i rep --page raw --csv`
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
