@@ -114,6 +114,17 @@ int clskd_pack_gather(const float* a, const float* b, const int32_t* table, int6
  * Folds the block-weight gradient back onto the reference's separate real/imag parameters. */
 int clskd_unpack_gather2(const float* src, const int32_t* table2, int64_t n, float* dst,
                          int accumulate, void* stream);
+/* Split-bf16 operand staging for fp32-accurate GEMMs on the tensor cores (replaces the TF32/fp32
+ * library GEMMs behind F.conv1d / F.conv_transpose1d of the STFT front end, tools_for_model.py:57,100,
+ * torch.stft of framework.py:27, and the fp32 nn.LSTM / nn.Linear projections, tools_for_model.py:164-172).
+ * Row m = (i0*n1 + i1)*n2 + i2 of the fp32 source is x[i0*s0 + i1*s1 + i2*s2 + k*sk], k < K.
+ * hi = bf16(x), lo = bf16(x - hi).  out is bf16 [Mp, nseg*Kp] (rows >= n0*n1*n2 and k >= K zero):
+ *   order 0 (activation operand): [hi | lo] (nseg 2) or [hi | lo | hi] (nseg 3)
+ *   order 1 (weight operand, nseg 3): [hi | hi | lo]
+ * so that one bf16 contraction over 3*Kp yields x_hi*w_hi + x_lo*w_hi + x_hi*w_lo. */
+int clskd_split_bf16x3(const float* x, int64_t s0, int64_t s1, int64_t s2, int64_t sk, int64_t n0,
+                       int n1, int n2, int K, int Kp, int64_t Mp, int order, int nseg, void* out,
+                       void* stream);
 /* zero / reflect padding of waveforms: dst[b, i] = src[b, map(i - left)], i in [0, L+left+right).
  * mode 0: zeros (ConvSTFT, tools_for_model.py:56); mode 1: reflect (torch.stft center=True,
  * framework.py:27). dst is fp32. */

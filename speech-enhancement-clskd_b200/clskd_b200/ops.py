@@ -28,6 +28,7 @@ class _Policy:
         self.name = "fp32"
         self.act_dtype = torch.float32
         self.use_umma = False
+        self.split_gemm = True   # fp32-input GEMMs (STFT/iSTFT/LSTM projections) as split-bf16 tcgen05 contractions
         self.narrow = "auto"     # tap-in-channel decomposition of narrow convs: "auto" (tensor-core policy) / "always"
 
 
@@ -422,6 +423,83 @@ def _view_of(t):
     return 0, (t.stride(0), t.stride(1), t.stride(2))
 
 
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def _split_gemm(d: TapConv, l: Launch, a, b, bias, x0, y) -> bool:
+    """fp32-input pointwise contraction (STFT / iSTFT DFT GEMMs, fp32 LSTM and Linear projections) on
+    the tcgen05 kernel with split-bf16 operands: x = hi + lo and w = hi + lo are staged as
+    [x_hi | x_lo | x_hi] x [w_hi ; w_hi ; w_lo] so that ONE bf16 contraction over 3K with fp32 TMEM
+    accumulation gives x_hi w_hi + x_lo w_hi + x_hi w_lo (~1e-5 relative; the fp32 policy keeps the
+    fp32 FMA kernel).  Returns False when the launch is not such a GEMM (caller falls through)."""
+    global umma_launches
+    if d.x_dtype != _lib.F32 or d.y_dtype != _lib.F32 or d.ntaps != 1 or d.dt[0] or d.df[0] or d.sf != 1 \
+            or d.c1 or d.accumulate or d.Ti != d.To or d.Fi != d.Fo:
+        return False
+    K, N = d.c0, d.N
+    M = d.B * d.To * d.Fo
+    if M < 1024 or K < 32 or N < 32:          # tiny / skinny problems stay on the FMA / GEMV kernels
+        return False
+    Kp = _round_up(K, 64)
+    Np = _round_up(N, 16) if N <= 128 else _round_up(N, 128)
+    dev = x0.device
+    # weights: fp32 [K][N] (per-parameter-version cache) -> bf16 [Np][3Kp] = [hi | hi | lo]
+    w32 = packed_weights(l._cache, "cn", lambda: l.t_cn, a, b, torch.float32)
+    ent = l._cache.get("split_nc")
+    if ent is not None and ent[0] is w32:
+        ws = ent[1]
+    else:
+        ws = torch.empty((Np, 3 * Kp), dtype=torch.bfloat16, device=dev)
+        call("clskd_split_bf16x3", w32.data_ptr(), 0, 0, 1, N, 1, 1, N, K, Kp, Np, 1, 3, ws.data_ptr(), _stream())
+        l._cache["split_nc"] = (w32, ws)
+    # activations: rows (b, t, f) gathered by strides -> bf16 [M][2Kp] = [hi | lo]; the third K segment
+    # re-reads the hi half through the second tensor map
+    xs = torch.empty((M, 2 * Kp), dtype=torch.bfloat16, device=dev)
+    call("clskd_split_bf16x3", d.x0, d.x0_sB, d.x0_sT, d.x0_sF, 1, d.B, d.To, d.Fo, K, Kp, M, 0, 2,
+         xs.data_ptr(), _stream())
+    # output: straight into y when its rows are uniformly strided and TMA-storable, else via scratch
+    dims = [(n, st) for n, st in ((d.B, d.y_sB), (d.To, d.y_sT), (d.Fo, d.y_sF)) if n > 1]
+    rows_uniform = all(o[1] == i[0] * i[1] for o, i in zip(dims[:-1], dims[1:]))
+    ld = dims[-1][1] if dims else N
+    direct = Np == N and rows_uniform and ld % 4 == 0 and d.y % 16 == 0
+    bias_p = bias
+    if bias is not None and Np != N:
+        bias_p = torch.zeros(Np, dtype=torch.float32, device=dev)
+        strided_copy_into(bias.view(-1)[:N], bias_p[:N])
+    if direct:
+        yt, y_ptr, y_ld = None, d.y, ld
+    else:
+        yt = torch.empty((M, Np), dtype=torch.float32, device=dev)
+        y_ptr, y_ld = yt.data_ptr(), Np
+    g = TapConv()
+    g.x0, g.x1 = xs.data_ptr(), xs.data_ptr()
+    g.x0_sB = g.x1_sB = M * 2 * Kp
+    g.x0_sT = g.x1_sT = 2 * Kp
+    g.x0_sF = g.x1_sF = 2 * Kp
+    g.c0, g.c1 = 2 * Kp, Kp
+    g.B, g.To, g.Fo, g.Ti, g.Fi = 1, M, 1, M, 1
+    g.sf, g.ntaps = 1, 1
+    g.dt[0] = g.df[0] = 0
+    g.w = ws.data_ptr()
+    g.bias = bias_p.data_ptr() if bias_p is not None else None
+    g.N = Np
+    g.y = y_ptr
+    g.y_sB, g.y_sT, g.y_sF = M * y_ld, y_ld, y_ld
+    g.x_dtype, g.y_dtype, g.accumulate = _lib.BF16, _lib.F32, 0
+    if not _lib.load().clskd_tapconv_umma_supported(ctypes.byref(g)):
+        return False
+    call("clskd_tapconv_fwd_umma", ctypes.byref(g), _stream())
+    umma_launches += 1
+    if yt is not None:
+        shape = (d.B, d.To, d.Fo, N)
+        src = yt.as_strided(shape, (d.To * d.Fo * Np, d.Fo * Np, Np, 1))
+        dst = y.as_strided(shape, (d.y_sB, d.y_sT, d.y_sF, 1),
+                           y.storage_offset() + (d.y - y.data_ptr()) // 4)
+        strided_copy_into(src, dst)
+    return True
+
+
 def run_tapconv(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, a, b, bias, y, x0_view=None, x1_view=None,
                 y_view=None, accumulate=False, allow_umma=True):
     """Run one launch.  *_view = (elem_offset, (sB, sT, sF)) override the tensors' own strides."""
@@ -435,6 +513,8 @@ def run_tapconv(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, a, b, bias, y, x0_
     d = TapConv()
     _fill_desc(d, x0, x0_off, x0_str, x1, x1_off, x1_str, c0, c1, B, To, Fo, Ti, Fi, l, x0, bias,
                l.N, y, y_off, y_str, accumulate)
+    if policy.use_umma and policy.split_gemm and _split_gemm(d, l, a, b, bias, x0, y):
+        return y
     if allow_umma and _umma_ok(d):
         w = packed_weights(l._cache, "nc", lambda: l.t_nc, a, b, torch.bfloat16)
         d.w = w.data_ptr()

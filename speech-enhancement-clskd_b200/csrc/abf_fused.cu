@@ -93,15 +93,13 @@ struct AbfGeom {
   int64_t M;      // rows B*T*F
   int F, Fy, C;   // F of this level, F of y_prev (F or F/2), channels
   int tpr;        // lanes per row = C/8 (power of two <= 32)
+  int cshift;     // log2(C)  (C = 8 * tpr is a power of two)
+  int yshift;     // 0: y_prev has F rows, 1: F/2 rows
 };
 
-// row m = (bt, f) -> flat row of y_prev
-__device__ __forceinline__ int64_t yrow(const AbfGeom& g, int64_t m) {
-  if (g.Fy == g.F) return m;
-  const int64_t bt = m / g.F;
-  const int f = (int)(m - bt * g.F);
-  return bt * g.Fy + (f >> 1);
-}
+// row m = bt*F + f -> flat row of y_prev = bt*Fy + (f >> yshift).  F is even, so with Fy = F/2 this
+// is simply m >> 1: no division on the per-row path (the kernels are instruction-issue bound).
+__device__ __forceinline__ int64_t yrow(const AbfGeom& g, int64_t m) { return m >> g.yshift; }
 
 // per-channel constants staged in shared memory as [NCONST][C] floats (a lane reads its 8 channels
 // of one constant with two 16-byte loads; lanes of a row are contiguous -> conflict free).  Keeping
@@ -154,36 +152,41 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
   const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
   const int64_t stride = nwarps * rpw * RQ;
-  const int64_t iters = (g.M + stride - 1) / stride;
+  const int cs_ = g.cshift;
+  const int coff = cg * 8;
 
-  auto issue = [&](int64_t it) {
-    if (it < iters) {
-      uint8_t* st = pipe + (size_t)(it % PD) * NSLOT * SLOT_STRIDE;
-      const int64_t m0 = (warp0 + it * nwarps) * rpw * RQ;
+  // the issue side runs PD-1 iterations ahead of the compute side; both walk rows incrementally
+  int64_t mi = warp0 * rpw * RQ + sub;      // first row of this lane group in the iteration being issued
+  int si = 0;                               // its pipeline stage
+  auto issue = [&]() {
+    uint8_t* st = pipe + (size_t)si * NSLOT * SLOT_STRIDE;
 #pragma unroll
-      for (int q = 0; q < RQ; ++q) {
-        const int64_t m = m0 + (int64_t)q * rpw + sub;
-        if (m < g.M) {
-          cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, z1 + m * g.C + cg * 8);
-          cp_vec8<T>(st + ((RQ + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, y + yrow(g, m) * g.C + cg * 8);
-        }
+    for (int q = 0; q < RQ; ++q) {
+      const int64_t m = mi + q * rpw;
+      if (m < g.M) {
+        cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, z1 + (m << cs_) + coff);
+        cp_vec8<T>(st + ((RQ + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, y + (yrow(g, m) << cs_) + coff);
       }
     }
     cp_commit();
+    mi += stride;
+    si = si + 1 == PD ? 0 : si + 1;
   };
 #pragma unroll
-  for (int i = 0; i < PD - 1; ++i) issue(i);
+  for (int i = 0; i < PD - 1; ++i) issue();
 
-  for (int64_t it = 0; it < iters; ++it) {
-    issue(it + PD - 1);
+  int sc_ = 0;
+  for (int64_t mb = warp0 * rpw * RQ; mb < g.M; mb += stride) {     // mb is warp-uniform
+    issue();
     cp_wait<PD - 1>();
-    const uint8_t* st = pipe + (size_t)(it % PD) * NSLOT * SLOT_STRIDE;
-    const int64_t m0 = (warp0 + it * nwarps) * rpw * RQ;
+    const uint8_t* st = pipe + (size_t)sc_ * NSLOT * SLOT_STRIDE;
+    sc_ = sc_ + 1 == PD ? 0 : sc_ + 1;
+    const int64_t m0 = mb + sub;
     float xv[RQ][8], yv[RQ][8];
     bool live[RQ];
 #pragma unroll
     for (int q = 0; q < RQ; ++q) {
-      const int64_t m = m0 + (int64_t)q * rpw + sub;
+      const int64_t m = m0 + q * rpw;
       live[q] = m < g.M;
       if (live[q]) {
         ld_vec8(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, xv[q]);
@@ -234,11 +237,11 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
       l1[q] += b1;
       const float s0 = sigm(l0[q]), s1 = sigm(l1[q]);
       if (live[q]) {
-        const int64_t m = m0 + (int64_t)q * rpw + sub;
+        const int64_t m = m0 + q * rpw;
         float o8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o8[e] = xv[q][e] * s0 + yv[q][e] * s1;
-        st8(xb + m * g.C + cg * 8, o8);
+        st8(xb + (m << cs_) + coff, o8);
         if (cg == 0) *reinterpret_cast<float2*>(logits + 2 * m) = make_float2(l0[q], l1[q]);
       }
     }
@@ -280,35 +283,43 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
   const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
   const int64_t stride = nwarps * rpw;
-  const int64_t iters = (pairs + stride - 1) / stride;
+  const int cs_ = g.cshift;
+  const int coff = cg * 8;
+  const bool y_full = g.yshift == 0;
 
-  auto issue = [&](int64_t it) {
-    if (it < iters) {
-      uint8_t* st = pipe + (size_t)(it % PD) * NSLOT * SLOT_STRIDE;
-      const int64_t p = (warp0 + it * nwarps) * rpw + sub;
-      if (p < pairs) {
-        const int64_t m0 = 2 * p;
-        const int64_t yr0 = yrow(g, m0);
+  int64_t pi = warp0 * rpw + sub;           // pair issued next by this lane group
+  int si = 0;
+  auto issue = [&]() {
+    if (pi < pairs) {
+      uint8_t* st = pipe + (size_t)si * NSLOT * SLOT_STRIDE;
+      const int64_t m0 = 2 * pi;
+      const int64_t yr0 = yrow(g, m0);
+      const T* gp = gout + (m0 << cs_) + coff;
+      const T* zp = z1 + (m0 << cs_) + coff;
+      const T* yp = y + (yr0 << cs_) + coff;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, gout + (m0 + q) * C + cg * 8);
-          cp_vec8<T>(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, z1 + (m0 + q) * C + cg * 8);
-        }
-        cp_vec8<T>(st + (4 * NCP) * SLOT_STRIDE, SLOT_STRIDE, y + yr0 * C + cg * 8);
-        if (g.Fy == g.F) cp_vec8<T>(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, y + (yr0 + 1) * C + cg * 8);
-        cp16(st + (6 * NCP) * SLOT_STRIDE, logits + 2 * m0);      // logits of rows m0 and m0+1 (16 bytes)
+      for (int q = 0; q < 2; ++q) {
+        cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, gp + ((int64_t)q << cs_));
+        cp_vec8<T>(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, zp + ((int64_t)q << cs_));
       }
+      cp_vec8<T>(st + (4 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp);
+      if (y_full) cp_vec8<T>(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp + ((int64_t)1 << cs_));
+      cp16(st + (6 * NCP) * SLOT_STRIDE, logits + 2 * m0);      // logits of rows m0 and m0+1 (16 bytes)
     }
     cp_commit();
+    pi += stride;
+    si = si + 1 == PD ? 0 : si + 1;
   };
 #pragma unroll
-  for (int i = 0; i < PD - 1; ++i) issue(i);
+  for (int i = 0; i < PD - 1; ++i) issue();
 
-  for (int64_t it = 0; it < iters; ++it) {
-    issue(it + PD - 1);
+  int sc_ = 0;
+  for (int64_t pb = warp0 * rpw; pb < pairs; pb += stride) {       // pb is warp-uniform
+    issue();
     cp_wait<PD - 1>();
-    const uint8_t* st = pipe + (size_t)(it % PD) * NSLOT * SLOT_STRIDE;
-    const int64_t p = (warp0 + it * nwarps) * rpw + sub;
+    const uint8_t* st = pipe + (size_t)sc_ * NSLOT * SLOT_STRIDE;
+    sc_ = sc_ + 1 == PD ? 0 : sc_ + 1;
+    const int64_t p = pb + sub;
     const bool live = p < pairs;
     const int64_t m0 = live ? 2 * p : 0;
     const int64_t yr0 = yrow(g, m0);
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
         ld_vec8(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, xv[q]);
       }
       ld_vec8(st + (4 * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[0]);
-      if (g.Fy == g.F) ld_vec8(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[1]);
+      if (y_full) ld_vec8(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[1]);
       else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) yv[1][e] = yv[0][e];
@@ -418,15 +429,17 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
           for (int e = 0; e < 8; ++e) yv[q][e] = gv[q][e] * s1[q] + wy0[e] * dl0[q] + wy1[e] * dl1[q];   // dyv
       }
       if (live) {
-        st8(dz1 + m0 * C + cg * 8, xp[0]);
-        st8(dz1 + (m0 + 1) * C + cg * 8, xp[1]);
-        if (g.Fy == g.F) {
-          st8(dy + yr0 * C + cg * 8, yv[0]);
-          st8(dy + (yr0 + 1) * C + cg * 8, yv[1]);
+        T* zo = dz1 + (m0 << cs_) + coff;
+        T* yo = dy + (yr0 << cs_) + coff;
+        st8(zo, xp[0]);
+        st8(zo + ((int64_t)1 << cs_), xp[1]);
+        if (y_full) {
+          st8(yo, yv[0]);
+          st8(yo + ((int64_t)1 << cs_), yv[1]);
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) yv[0][e] += yv[1][e];
-          st8(dy + yr0 * C + cg * 8, yv[0]);
+          st8(yo, yv[0]);
         }
       }
     }
@@ -473,6 +486,8 @@ const char* abf_unsupported(int B, int T, int F, int Fy, int C, const void* a, c
   return nullptr;
 }
 
+int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
 int abf_grid(int64_t warp_iters) {
   int64_t blocks = (warp_iters + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 8;
@@ -500,6 +515,7 @@ extern "C" int clskd_abf_mid_fwd(const void* z1, const void* y, int dtype, int B
   }
   AbfGeom g;
   g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
+  g.cshift = ilog2(C); g.yshift = Fy == F ? 0 : 1;
   if (g.M == 0) return CLSKD_OK;
   const int rows_per_warp_iter = (32 / g.tpr) * 2;
   const int grid = abf_grid((g.M + rows_per_warp_iter - 1) / rows_per_warp_iter / 4);
@@ -535,6 +551,7 @@ extern "C" int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y
   CLSKD_CHECK_ARG(((uintptr_t)y % 16) == 0 && ((uintptr_t)dy % 16) == 0, "clskd_abf_mid_bwd: y / dy must be 16-byte aligned");
   AbfGeom g;
   g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
+  g.cshift = ilog2(C); g.yshift = Fy == F ? 0 : 1;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(dwatt, 0, sizeof(double) * 4 * C, st);

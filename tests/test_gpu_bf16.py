@@ -269,3 +269,58 @@ def test_tap_in_channel_narrow_conv_vs_torch(cuda_dev, cin, cout, ks):
     assert (gx - xr.grad).abs().max().item() < 2e-2 * xr.grad.abs().max().item()
     gw = conv.weight.grad.cpu()
     assert (gw - wr.grad).abs().max().item() < 2e-2 * wr.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("B,L", [(8, 16000), (2, 64000)])
+def test_split_bf16_stft_istft_vs_oracle(cuda_dev, B, L):
+    """STFT / iSTFT DFT GEMMs of the bf16 policy run on tcgen05 with split-bf16 (hi+lo) operands:
+    spectra, round trip and the waveform gradient must stay at fp32-GEMM accuracy (1e-5 relative to
+    the largest value), far inside the bf16 policy's 1e-3 waveform budget."""
+    import clskd_b200
+    from clskd_b200 import ops
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(L)
+    x = 0.1 * torch.randn(B, L, generator=g)
+    stft, istft = tm.ConvSTFT(400, 100, 512, 'hamming', 'complex').to(cuda_dev), \
+        tm.ConviSTFT(400, 100, 512, 'hamming', 'complex').to(cuda_dev)
+    w_a, _ = D.init_kernels(400, 100, 512, 'hamming')
+    w_s, win = D.init_kernels(400, 100, 512, 'hamming', invers=True)
+    ref_spec = D.conv_stft(x, w_a, 400, 100)
+    gw = torch.randn(ref_spec.shape, generator=g)
+    xr = x.clone().requires_grad_(True)
+    spec_r = D.conv_stft(xr, w_a, 400, 100)
+    wav_r = D.conv_istft(spec_r * 0.5, w_s, win, 400, 100)
+    (wav_r * wav_r).sum().backward()
+    clskd_b200.set_precision("bf16")
+    n0 = ops.umma_launches
+    xd = x.to(cuda_dev).requires_grad_(True)
+    spec = stft(xd)
+    assert ops.umma_launches == n0 + 1, "split-bf16 tcgen05 route was not taken for the STFT GEMM"
+    wav = istft(spec * 0.5)
+    assert ops.umma_launches == n0 + 2, "split-bf16 tcgen05 route was not taken for the iSTFT GEMM"
+    (wav * wav).sum().backward()
+    assert ops.umma_launches == n0 + 4, "data gradients of the DFT GEMMs must take the split route too"
+    s = ref_spec.abs().max().item()
+    assert (spec.detach().cpu() - ref_spec).abs().max().item() < 1e-5 * s
+    assert (wav.detach().cpu() - wav_r.detach()).abs().max().item() < 1e-5 * max(wav_r.abs().max().item(), 1e-3) + 2e-7
+    gs = xr.grad.abs().max().item()
+    assert (xd.grad.cpu() - xr.grad).abs().max().item() < 2e-5 * gs
+
+
+def test_split_bf16_gemm_bias_and_padding(cuda_dev):
+    """the split route pads K to 64 and N to the tcgen05 tile (scratch + strided copy) and adds the bias"""
+    import clskd_b200
+    from clskd_b200 import ops
+    from clskd_b200.clstm import _LinearParams
+    g = torch.Generator().manual_seed(5)
+    lin = _LinearParams(72, 200)
+    x = torch.randn(5000, 72, generator=g)
+    ref = x.double() @ lin.weight.detach().double().t() + lin.bias.detach().double()
+    lin = lin.to(cuda_dev)
+    clskd_b200.set_precision("bf16")
+    n0 = ops.umma_launches
+    with torch.no_grad():
+        y = lin.forward_rows(x.to(cuda_dev))
+    assert ops.umma_launches == n0 + 1
+    assert (y.cpu().double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
