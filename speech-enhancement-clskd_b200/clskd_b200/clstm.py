@@ -132,10 +132,17 @@ class ComplexLSTMLayerFn(torch.autograd.Function):
             dX = torch.empty(X.shape, dtype=X.dtype, device=dev)
             run_tapconv(dpre.view(1, P * T, B, 2 * G), None, 2 * G, 0, 1, P * T, B, P * T, B,
                         plans.ih.dgrad[0][0], wr_ih, wi_ih, None, dX.view(1, P * T, B, D))
+        # tensor-core policy: the weight gradients contract bf16 copies of dpre / X / h on tcgen05 (fp32
+        # accumulation over the T*B rows), like every other weight gradient of that policy
+        dpre_w, X_w, h_w = dpre, X, h
+        if ops.policy.use_umma and D % 16 == 0 and H % 16 == 0 and P * T * B >= 4096:
+            dpre_w = dense(dpre, torch.bfloat16)
+            X_w = dense(X, torch.bfloat16)
+            h_w = dense(h, torch.bfloat16)
         # input-projection weight grads (both sets at once)
         dwcat = torch.empty(plans.ih.wcat, dtype=torch.float32, device=dev)
-        run_wgrad(X.view(1, P * T, B, D), None, D, 0, 1, P * T, B, P * T, B, plans.ih.fwd[0],
-                  dpre.view(1, P * T, B, 2 * G), dwcat)
+        run_wgrad(X_w.view(1, P * T, B, D), None, D, 0, 1, P * T, B, P * T, B, plans.ih.fwd[0],
+                  dpre_w.view(1, P * T, B, 2 * G), dwcat)
         dwr_ih = unpack_grads(dwcat, plans.ih.unpack_a, G * D).view(G, D)
         dwi_ih = unpack_grads(dwcat, plans.ih.unpack_b, G * D).view(G, D)
         # recurrent weight grads: dW_hh[s][g][k] = sum_{p,t>=1,b} dpre[p,t,b,s*4H+g] * h[s,p,t-1,b,k]
@@ -144,7 +151,7 @@ class ComplexLSTMLayerFn(torch.autograd.Function):
         dw_hh = []
         for s in range(2):
             tmp = torch.empty(H * G, dtype=torch.float32, device=dev)
-            run_wgrad(h[s], None, H, 0, P, T, B, T, B, l, dpre, tmp,
+            run_wgrad(h_w[s], None, H, 0, P, T, B, T, B, l, dpre_w, tmp,
                       dy_view=(s * G, (T * B * 2 * G, B * 2 * G, 2 * G)))
             dw_hh.append(unpack_grads(tmp, plans.hh_unpack, G * H).view(G, H))
         # biases: column sums of dpre
@@ -287,11 +294,14 @@ class _Project2Fn(torch.autograd.Function):
         f = ops._f32c
         dY = torch.empty_like(Y)
         grads = []
+        Y_w, g_w = Y, g
+        if ops.policy.use_umma and H % 16 == 0 and P % 16 == 0 and T * B >= 4096:
+            Y_w, g_w = dense(Y, torch.bfloat16), dense(g, torch.bfloat16)     # tcgen05 weight gradient
         for p, (w, plan) in enumerate(((wr, plan_r), (wi, plan_i))):
             run_tapconv(g[p].view(1, T, B, P), None, P, 0, 1, T, B, T, B, plan.dgrad[0][0], f(w), None, None,
                         dY[p].view(1, T, B, H))
             dw = torch.empty(plan.wcat, dtype=torch.float32, device=g.device)
-            run_wgrad(Y[p].view(1, T, B, H), None, H, 0, 1, T, B, T, B, plan.fwd[0], g[p].view(1, T, B, P), dw)
+            run_wgrad(Y_w[p].view(1, T, B, H), None, H, 0, 1, T, B, T, B, plan.fwd[0], g_w[p].view(1, T, B, P), dw)
             s, _ = colstats(g[p].view(-1, P))
             grads.append((unpack_grads(dw, plan.unpack_a, plan.na).view(P, H), f64_to_f32(s)))
         return dY, grads[0][0], grads[0][1], grads[1][0], grads[1][1], None, None

@@ -107,6 +107,9 @@ def strided_copy_into(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
 def strided_copy(src: torch.Tensor, dtype=None) -> torch.Tensor:
     """Dense copy of an arbitrary <=4-D strided view, with optional dtype conversion."""
     dst = torch.empty(src.shape, dtype=dtype or src.dtype, device=src.device)
+    if src.dim() > 4 and src.is_contiguous():          # pure dtype conversion of a dense tensor
+        strided_copy_into(src.view(-1, src.shape[-1]), dst.view(-1, src.shape[-1]))
+        return dst
     return strided_copy_into(src, dst)
 
 
@@ -434,7 +437,7 @@ def _split_gemm(d: TapConv, l: Launch, a, b, bias, x0, y) -> bool:
     accumulation gives x_hi w_hi + x_lo w_hi + x_hi w_lo (~1e-5 relative; the fp32 policy keeps the
     fp32 FMA kernel).  Returns False when the launch is not such a GEMM (caller falls through)."""
     global umma_launches
-    if d.x_dtype != _lib.F32 or d.y_dtype != _lib.F32 or d.ntaps != 1 or d.dt[0] or d.df[0] or d.sf != 1 \
+    if d.x_dtype != _lib.F32 or d.ntaps != 1 or d.dt[0] or d.df[0] or d.sf != 1 \
             or d.c1 or d.accumulate or d.Ti != d.To or d.Fi != d.Fo:
         return False
     K, N = d.c0, d.N
@@ -442,7 +445,9 @@ def _split_gemm(d: TapConv, l: Launch, a, b, bias, x0, y) -> bool:
     if M < 1024 or K < 32 or N < 32:          # tiny / skinny problems stay on the FMA / GEMV kernels
         return False
     Kp = _round_up(K, 64)
-    Np = _round_up(N, 16) if N <= 128 else _round_up(N, 128)
+    y_bf16 = d.y_dtype == _lib.BF16
+    ye = 2 if y_bf16 else 4
+    Np = _round_up(N, 16) if N <= (256 if y_bf16 else 128) else _round_up(N, 128)
     dev = x0.device
     # weights: fp32 [K][N] (per-parameter-version cache) -> bf16 [Np][3Kp] = [hi | hi | lo]
     w32 = packed_weights(l._cache, "cn", lambda: l.t_cn, a, b, torch.float32)
@@ -462,7 +467,7 @@ def _split_gemm(d: TapConv, l: Launch, a, b, bias, x0, y) -> bool:
     dims = [(n, st) for n, st in ((d.B, d.y_sB), (d.To, d.y_sT), (d.Fo, d.y_sF)) if n > 1]
     rows_uniform = all(o[1] == i[0] * i[1] for o, i in zip(dims[:-1], dims[1:]))
     ld = dims[-1][1] if dims else N
-    direct = Np == N and rows_uniform and ld % 4 == 0 and d.y % 16 == 0
+    direct = Np == N and rows_uniform and (ld * ye) % 16 == 0 and d.y % 16 == 0
     bias_p = bias
     if bias is not None and Np != N:
         bias_p = torch.zeros(Np, dtype=torch.float32, device=dev)
@@ -470,7 +475,7 @@ def _split_gemm(d: TapConv, l: Launch, a, b, bias, x0, y) -> bool:
     if direct:
         yt, y_ptr, y_ld = None, d.y, ld
     else:
-        yt = torch.empty((M, Np), dtype=torch.float32, device=dev)
+        yt = torch.empty((M, Np), dtype=y.dtype, device=dev)
         y_ptr, y_ld = yt.data_ptr(), Np
     g = TapConv()
     g.x0, g.x1 = xs.data_ptr(), xs.data_ptr()
@@ -486,7 +491,7 @@ def _split_gemm(d: TapConv, l: Launch, a, b, bias, x0, y) -> bool:
     g.N = Np
     g.y = y_ptr
     g.y_sB, g.y_sT, g.y_sF = M * y_ld, y_ld, y_ld
-    g.x_dtype, g.y_dtype, g.accumulate = _lib.BF16, _lib.F32, 0
+    g.x_dtype, g.y_dtype, g.accumulate = _lib.BF16, d.y_dtype, 0
     if not _lib.load().clskd_tapconv_umma_supported(ctypes.byref(g)):
         return False
     call("clskd_tapconv_fwd_umma", ctypes.byref(g), _stream())
@@ -495,7 +500,7 @@ def _split_gemm(d: TapConv, l: Launch, a, b, bias, x0, y) -> bool:
         shape = (d.B, d.To, d.Fo, N)
         src = yt.as_strided(shape, (d.To * d.Fo * Np, d.Fo * Np, Np, 1))
         dst = y.as_strided(shape, (d.y_sB, d.y_sT, d.y_sF, 1),
-                           y.storage_offset() + (d.y - y.data_ptr()) // 4)
+                           y.storage_offset() + (d.y - y.data_ptr()) // ye)
         strided_copy_into(src, dst)
     return True
 

@@ -56,6 +56,31 @@ __global__ void strided_copy4d_kernel(const TS* __restrict__ src, TD* __restrict
   }
 }
 
+// innermost dimension contiguous on both sides: a thread moves V consecutive elements with 8/16-byte
+// accesses and decodes its index once per vector (32-bit arithmetic whenever the count allows)
+template <typename TS, typename TD, int V, typename I>
+__global__ void __launch_bounds__(256)
+strided_copy4d_vec_kernel(const TS* __restrict__ src, TD* __restrict__ dst, I n1, I n2, I n3v, I total,
+                          int64_t s0, int64_t s1, int64_t s2, int64_t d0, int64_t d1, int64_t d2) {
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    const I i3 = i % n3v;
+    I r = i / n3v;
+    const I i2 = r % n2;
+    r /= n2;
+    const I i1 = r % n1, i0 = r / n1;
+    const TS* sp = src + (int64_t)i0 * s0 + (int64_t)i1 * s1 + (int64_t)i2 * s2 + (int64_t)i3 * V;
+    TD* dp = dst + (int64_t)i0 * d0 + (int64_t)i1 * d1 + (int64_t)i2 * d2 + (int64_t)i3 * V;
+    if (V >= 4) {
+#pragma unroll
+      for (int j = 0; j < V / 4; ++j) st4(dp + 4 * j, ld4(sp + 4 * j));
+    } else {
+      const float a = ld_f(sp), b = ld_f(sp + 1);
+      st_f(dp, a);
+      st_f(dp + 1, b);
+    }
+  }
+}
+
 template <typename TD>
 __global__ void pack_gather_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                    const int32_t* __restrict__ table, int64_t n,
@@ -833,6 +858,39 @@ extern "C" int clskd_strided_copy4d(const void* src, int src_dtype, const int64_
   CLSKD_CHECK_ARG(src && dst && ss && ds && shape, "clskd_strided_copy4d: null pointer");
   int64_t total = shape[0] * shape[1] * shape[2] * shape[3];
   if (total == 0) return CLSKD_OK;
+  if (ss[3] == 1 && ds[3] == 1 && shape[3] % 2 == 0) {
+    // vector width: largest of 8/4/2 that divides the row and keeps every access naturally aligned
+    const int se = src_dtype == CLSKD_F32 ? 4 : 2, de = dst_dtype == CLSKD_F32 ? 4 : 2;
+    auto fits = [&](int v) {
+      if (shape[3] % v) return false;
+      const int av = v > 4 ? 4 : v;            // elements per single access (ld4/st4 or scalar)
+      const int64_t sa = (int64_t)(av == 1 ? 1 : av) * se, da = (int64_t)(av == 1 ? 1 : av) * de;
+      if (v == 2) return true;                 // scalar accesses: always aligned
+      for (int k = 0; k < 3; ++k)
+        if ((ss[k] * se) % sa || (ds[k] * de) % da) return false;
+      return ((uintptr_t)src % sa) == 0 && ((uintptr_t)dst % da) == 0;
+    };
+    const int v = fits(8) ? 8 : (fits(4) ? 4 : 2);
+    const int64_t n3v = shape[3] / v;
+    const int64_t tv = shape[0] * shape[1] * shape[2] * n3v;
+    const int gridv = ew_grid(tv, 256);
+    const bool small = tv + (int64_t)gridv * 256 < 4000000000LL;
+#define LV3(TS, TD, V, I)                                                                                   \
+  strided_copy4d_vec_kernel<TS, TD, V, I><<<gridv, 256, 0, ST>>>((const TS*)src, (TD*)dst, (I)shape[1],       \
+                                                                  (I)shape[2], (I)n3v, (I)tv, ss[0], ss[1],  \
+                                                                  ss[2], ds[0], ds[1], ds[2])
+#define LV2(TS, TD, V) do { if (small) LV3(TS, TD, V, unsigned); else LV3(TS, TD, V, int64_t); } while (0)
+#define LV(TS, TD) do { if (v == 8) LV2(TS, TD, 8); else if (v == 4) LV2(TS, TD, 4); else LV2(TS, TD, 2); } while (0)
+    if (src_dtype == CLSKD_F32 && dst_dtype == CLSKD_F32) LV(float, float);
+    else if (src_dtype == CLSKD_F32) LV(float, __nv_bfloat16);
+    else if (dst_dtype == CLSKD_F32) LV(__nv_bfloat16, float);
+    else LV(__nv_bfloat16, __nv_bfloat16);
+#undef LV
+#undef LV2
+#undef LV3
+    CLSKD_CHECK_LAUNCH("clskd_strided_copy4d(vec)");
+    return CLSKD_OK;
+  }
   int grid = ew_grid(total, 256);
 #define L(TS, TD)                                                                               \
   strided_copy4d_kernel<TS, TD><<<grid, 256, 0, ST>>>((const TS*)src, (TD*)dst, shape[0], shape[1], \

@@ -614,6 +614,15 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// input element (b, ti, fi, c) of the (x0 | x1) channel concat, zero outside the map
+template <typename TX>
+__device__ __forceinline__ float smallk_at(const ClskdTapConv& d, int c, int b, int ti, int fi) {
+  if (ti < 0 || ti >= d.Ti || fi < 0 || fi >= d.Fi) return 0.f;
+  if (c < d.c0)
+    return ld_f(reinterpret_cast<const TX*>(d.x0) + (int64_t)b * d.x0_sB + (int64_t)ti * d.x0_sT + (int64_t)fi * d.x0_sF + c);
+  return ld_f(reinterpret_cast<const TX*>(d.x1) + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF + (c - d.c0));
+}
+
 template <typename TX>
 __device__ __forceinline__ float smallk_x(const ClskdTapConv& d, int k, int Ctot, int b, int t, int f) {
   const int tap = k / Ctot, c = k - tap * Ctot;
@@ -624,7 +633,11 @@ __device__ __forceinline__ float smallk_x(const ClskdTapConv& d, int k, int Ctot
   return ld_f(reinterpret_cast<const TX*>(d.x1) + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF + (c - d.c0));
 }
 
-template <typename TX, typename TY, typename I>
+// Y[m][n] for K = ntaps*C <= 32 (first encoder layer: 2 input channels, 5x2 taps; 1x1 convs on the
+// 2-channel mask map).  A thread owns 8*NV consecutive outputs of one row: the row's K inputs are
+// loaded once per thread (tap bounds and addresses hoisted out of the channel loop), the weights are
+// broadcast from shared memory, so the kernel is bound by the output store, not by instruction issue.
+template <typename TX, typename TY, typename I, int NV>
 __global__ void __launch_bounds__(256) tapconv_fwd_smallk_kernel(ClskdTapConv d, int Ktot) {
   extern __shared__ float wsm[];   // [Ktot][N] + bias[N]
   const int N = d.N, Ctot = d.c0 + d.c1;
@@ -632,29 +645,45 @@ __global__ void __launch_bounds__(256) tapconv_fwd_smallk_kernel(ClskdTapConv d,
   for (int i = threadIdx.x; i < Ktot * N; i += blockDim.x) wsm[i] = w[i];
   for (int i = threadIdx.x; i < N; i += blockDim.x) wsm[Ktot * N + i] = d.bias ? d.bias[i] : 0.f;
   __syncthreads();
-  const I tpr = N >> 3;                         // threads per row
+  const I tpr = N / (8 * NV);                   // threads per row
   const I M = (I)d.B * d.To * d.Fo;
   const I total = M * tpr;                      // I = unsigned when it fits 32 bits (cheap divisions)
   TY* y = reinterpret_cast<TY*>(d.y);
+  const TX* x0 = reinterpret_cast<const TX*>(d.x0);
+  const TX* x1 = reinterpret_cast<const TX*>(d.x1);
   for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
-    const int n0 = (int)(i % tpr) * 8;
+    const int n0 = (int)(i % tpr) * (8 * NV);
     const I m = i / tpr;
     const int f = (int)(m % (I)d.Fo);
     const I r = m / (I)d.Fo;
     const int t = (int)(r % (I)d.To), b = (int)(r / (I)d.To);
-    float acc[8];
+    float acc[NV][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = wsm[Ktot * N + n0 + e];
-    for (int k = 0; k < Ktot; ++k) {
-      const float xv = smallk_x<TX>(d, k, Ctot, b, t, f);
-      const float4 w0 = *reinterpret_cast<const float4*>(&wsm[k * N + n0]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&wsm[k * N + n0 + 4]);
-      acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-      acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-      acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-      acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[v][e] = wsm[Ktot * N + n0 + v * 8 + e];
+    const float* wk = wsm + n0;
+    for (int tap = 0; tap < d.ntaps; ++tap) {
+      const int ti = t + d.dt[tap], fi = f * d.sf + d.df[tap];
+      const bool ok = ti >= 0 && ti < d.Ti && fi >= 0 && fi < d.Fi;
+      const TX* p0 = x0 + (int64_t)b * d.x0_sB + (int64_t)ti * d.x0_sT + (int64_t)fi * d.x0_sF;
+      const TX* p1 = d.c1 ? x1 + (int64_t)b * d.x1_sB + (int64_t)ti * d.x1_sT + (int64_t)fi * d.x1_sF : p0;
+      for (int c = 0; c < Ctot; ++c, wk += N) {
+        const float xv = ok ? (c < d.c0 ? ld_f(p0 + c) : ld_f(p1 + (c - d.c0))) : 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wk + v * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wk + v * 8 + 4);
+          acc[v][0] = fmaf(xv, w0.x, acc[v][0]); acc[v][1] = fmaf(xv, w0.y, acc[v][1]);
+          acc[v][2] = fmaf(xv, w0.z, acc[v][2]); acc[v][3] = fmaf(xv, w0.w, acc[v][3]);
+          acc[v][4] = fmaf(xv, w1.x, acc[v][4]); acc[v][5] = fmaf(xv, w1.y, acc[v][5]);
+          acc[v][6] = fmaf(xv, w1.z, acc[v][6]); acc[v][7] = fmaf(xv, w1.w, acc[v][7]);
+        }
+      }
     }
-    st8(y + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF + n0, acc);
+    TY* yo = y + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + (int64_t)f * d.y_sF + n0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) st8(yo + v * 8, acc[v]);
   }
 }
 
@@ -680,6 +709,16 @@ __global__ void __launch_bounds__(256) tapconv_wgrad_smallk_kernel(ClskdTapConv 
     for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
   const int64_t M = (int64_t)d.B * d.To * d.Fo;
   const TY* dy = reinterpret_cast<const TY*>(d.y);
+  // (tap shift, channel) of the up-to-8 contraction indices this thread owns: decoded once
+  int dta[8], dfa[8], ca[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int k = k0 + a;
+    const int tap = a < kcnt ? k / Ctot : 0;
+    dta[a] = d.dt[tap];
+    dfa[a] = d.df[tap];
+    ca[a] = a < kcnt ? k - tap * Ctot : -1;
+  }
   if (sub < rows_par) {
     constexpr int RB = 2;
     for (int64_t m0 = (int64_t)blockIdx.x * rows_par * RB + sub; m0 < M; m0 += (int64_t)gridDim.x * rows_par * RB) {
@@ -697,7 +736,8 @@ __global__ void __launch_bounds__(256) tapconv_wgrad_smallk_kernel(ClskdTapConv 
           for (int e = 0; e < 8; ++e) g[q][e] = 0.f;
         }
 #pragma unroll
-        for (int a = 0; a < 8; ++a) xv[q][a] = (live && a < kcnt) ? smallk_x<TX>(d, k0 + a, Ctot, b, t, f) : 0.f;
+        for (int a = 0; a < 8; ++a)
+          xv[q][a] = (live && ca[a] >= 0) ? smallk_at<TX>(d, ca[a], b, t + dta[a], f * d.sf + dfa[a]) : 0.f;
       }
 #pragma unroll
       for (int q = 0; q < RB; ++q)
@@ -816,20 +856,28 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
   }
   int ktot_sk;
   if (smallk_ok(d, &ktot_sk)) {
-    const int64_t total = M * (d->N / 8);
+    const int nv = d->N % 32 == 0 ? 4 : (d->N % 16 == 0 ? 2 : 1);
+    const int64_t total = M * (d->N / (8 * nv));
     int64_t blocks = (total + 255) / 256;
     if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
     const size_t sh = sizeof(float) * ((size_t)ktot_sk * d->N + d->N);
-    const bool small = total + (int64_t)blocks * 256 < 4000000000LL;
-#define LAUNCH_SK(TX, TY)                                                                                \
-  do {                                                                                                   \
-    if (small) tapconv_fwd_smallk_kernel<TX, TY, unsigned><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk); \
-    else tapconv_fwd_smallk_kernel<TX, TY, int64_t><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);     \
+    const bool small = total + (int64_t)blocks * 256 < 4000000000LL && M * (d->N / 8) < 4000000000LL;
+#define LAUNCH_SK2(TX, TY, NV)                                                                               \
+  do {                                                                                                       \
+    if (small) tapconv_fwd_smallk_kernel<TX, TY, unsigned, NV><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk); \
+    else tapconv_fwd_smallk_kernel<TX, TY, int64_t, NV><<<(unsigned)blocks, 256, sh, st>>>(*d, ktot_sk);     \
+  } while (0)
+#define LAUNCH_SK(TX, TY)                  \
+  do {                                     \
+    if (nv == 4) LAUNCH_SK2(TX, TY, 4);    \
+    else if (nv == 2) LAUNCH_SK2(TX, TY, 2); \
+    else LAUNCH_SK2(TX, TY, 1);            \
   } while (0)
     if (d->x_dtype == CLSKD_F32 && d->y_dtype == CLSKD_F32) LAUNCH_SK(float, float);
     else if (d->x_dtype == CLSKD_F32) LAUNCH_SK(float, __nv_bfloat16);
     else if (d->y_dtype == CLSKD_F32) LAUNCH_SK(__nv_bfloat16, float);
     else LAUNCH_SK(__nv_bfloat16, __nv_bfloat16);
+#undef LAUNCH_SK2
 #undef LAUNCH_SK
     CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(smallk)");
     return CLSKD_OK;

@@ -77,6 +77,20 @@ def main():
             shp = "M=%d taps=%d C=%d+%d N=%d Fo=%d sf=%d x=%s y=%s" % (
                 d.B * d.To * d.Fo, d.ntaps, d.c0, d.c1, d.N, d.Fo, d.sf, "bf16" if d.x_dtype else "f32",
                 "bf16" if d.y_dtype else "f32")
+        if name == "clskd_colstats":
+            shp = "M=%d C=%d %s" % (args[2], args[3], "bf16" if args[1] else "f32")
+        elif name == "clskd_bn_act_fwd":
+            shp = "M=%d C=%d %s->%s" % (args[2], args[3], "bf16" if args[1] else "f32", "bf16" if args[10] else "f32")
+        elif name in ("clskd_bn_act_bwd_stats", "clskd_bn_act_bwd_apply"):
+            shp = "M=%d C=%d %s" % (args[4], args[5], "bf16" if args[1] else "f32")
+        elif name in ("clskd_gram_fwd_umma", "clskd_gram_bwd_umma", "clskd_gram_fwd", "clskd_gram_bwd"):
+            shp = "B=%d K=%d %s" % (args[2], args[3], "bf16" if args[1] else "f32")
+        elif name in ("clskd_abf_mid_fwd",):
+            shp = "B=%d T=%d F=%d Fy=%d C=%d" % tuple(args[3:8])
+        elif name in ("clskd_abf_mid_bwd",):
+            shp = "B=%d T=%d F=%d Fy=%d C=%d" % tuple(args[4:9])
+        elif name in ("clskd_lstm_fwd",):
+            shp = "T=%d R=%d H=%d" % (args[2], args[3], args[5])
         if name == "clskd_strided_copy4d":
             shp = "shape=%s src=%s/%s dst=%s/%s" % (list(args[6]), "bf16" if args[1] else "f32", list(args[2]),
                                                    "bf16" if args[4] else "f32", list(args[5]))
@@ -111,7 +125,7 @@ def main():
         print("%-32s %5d %9.3f ms %5.1f%%" % (k, v[0], v[1], 100 * v[1] / ssum))
     print("---- tapconv launches by time")
     for ms, name, shp in sorted(shaped, reverse=True)[:a.top]:
-        if name == "clskd_strided_copy4d":
+        if not name.startswith("clskd_tapconv"):
             print("%8.3f ms               %-26s %s" % (ms, name, shp))
             continue
         d = dict(kv.split("=") for kv in shp.split())
