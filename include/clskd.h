@@ -184,6 +184,22 @@ int clskd_cbn_finalize(const double* s, int64_t M, int Cc, float eps, float mome
                        float* RVrr, float* RVri, float* RVii, float* coef, void* stream);
 int clskd_cbn_apply(const void* x, int x_dtype, int64_t M, int Cc, const float* coef,
                     const float* Br, const float* Bi, void* y, int y_dtype, void* stream);
+/* Backward of the block (autograd of tools_for_model.py:398-508; with batch statistics the gradient
+ * flows through the mean and the 2x2 covariance, like the reference's undetached statistics):
+ *   pass 1  s6[0..5][Cc] = sum dyr, dyi, dyr*xr, dyr*xi, dyi*xr, dyi*xi        (fp64, zeroed by the call)
+ *   pass 2  per channel: dWrr/dWri/dWii/dBr/dBi (fp32 [Cc], each may be NULL) and coefb[11][Cc] such that
+ *           dx = Z^T (dy - mean dy) + G (x - mean x)   (G = 0 with running statistics, training=0);
+ *           `s` are the forward moments of clskd_cbn_moments (training=1), else the running buffers are used
+ *   pass 3  dx from x, dy and coefb (x, dy, dx share one dtype) */
+int clskd_cbn_bwd_moments(const void* x, const void* dy, int dtype, int64_t M, int Cc, double* s6,
+                          void* stream);
+int clskd_cbn_bwd_finalize(const double* s, const double* s6, int64_t M, int Cc, float eps, int training,
+                           const float* Wrr, const float* Wri, const float* Wii, const float* RMr,
+                           const float* RMi, const float* RVrr, const float* RVri, const float* RVii,
+                           float* coefb, float* dWrr, float* dWri, float* dWii, float* dBr, float* dBi,
+                           void* stream);
+int clskd_cbn_bwd_apply(const void* x, const void* dy, int dtype, int64_t M, int Cc, const float* coefb,
+                        void* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Mask / spectrum kernels (DCCRN.py:153,159,207-232)

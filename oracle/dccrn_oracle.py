@@ -112,6 +112,14 @@ def complex_lstm(real, imag, sd, prefix, project):
 def _bn_prelu(x, sd, prefix, training, eps=1e-5, momentum=0.1, update=None):
     """nn.BatchNorm2d + nn.PReLU of DCCRN.py:80-82; running stats are updated in `update` (a dict)
     when training."""
+    if (prefix + '1.Wrr') in sd:                 # use_cbn=True: ComplexBatchNorm in slot .1 (DCCRN.py:80-81)
+        keys = ('Wrr', 'Wri', 'Wii', 'Br', 'Bi', 'RMr', 'RMi', 'RVrr', 'RVri', 'RVii')
+        upd = {} if (training and update is not None) else None
+        y = complex_batch_norm(x, {k: sd[prefix + '1.' + k] for k in keys}, training, eps, momentum, update=upd)
+        if upd is not None:
+            for k, v in upd.items():
+                update[prefix + '1.' + k] = v
+        return F.prelu(y, sd[prefix + '2.weight'])
     w, b = sd[prefix + '1.weight'], sd[prefix + '1.bias']
     rm, rv = sd[prefix + '1.running_mean'], sd[prefix + '1.running_var']
     if training:
@@ -182,7 +190,8 @@ def mask_apply(real, imag, mask_real, mask_imag, mode):
 
 def dccrn_forward(sd, x, masking_mode='E', win_len=400, hop=100, fft_len=512, training=False, taps=None,
                   update=None):
-    """DCCRN.forward (DCCRN.py:149-240) for use_clstm=True, use_cbn=False.
+    """DCCRN.forward (DCCRN.py:149-240) for use_clstm=True; use_cbn is inferred from the state_dict keys
+    (`*.1.Wrr` present = ComplexBatchNorm in the norm slot).
     sd: state_dict with the reference's keys; returns (mask_real, mask_imag, real, imag, wav).
     taps (dict) collects what feature_extraction.DCCRN's hooks see (feature_extraction.py:11-13)."""
     n_layers = len([k for k in sd if k.startswith('encoder.') and k.endswith('.0.real_conv.weight')])
@@ -214,7 +223,7 @@ def dccrn_forward(sd, x, masking_mode='E', win_len=400, hop=100, fft_len=512, tr
         out = complex_cat([out, enc[-1 - idx]], 1)
         out = complex_deconv2d(out, sd[pre + '0.real_conv.weight'], sd[pre + '0.real_conv.bias'],
                                sd[pre + '0.imag_conv.weight'], sd[pre + '0.imag_conv.bias'])
-        if (pre + '1.weight') in sd:
+        if (pre + '1.weight') in sd or (pre + '1.Wrr') in sd:
             out = _bn_prelu(out, sd, pre, training, update=update)
         dec.append(out)
         out = out[..., 1:]

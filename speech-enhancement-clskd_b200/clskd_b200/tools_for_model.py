@@ -382,10 +382,66 @@ class cPReLU(nn.Module):
         return torch.cat([self.r_prelu(real), self.i_prelu(imag)], self.complex_axis)
 
 
+class _CBNFn(torch.autograd.Function):
+    """y = Z (x - mean) + B with Z = W V^{-1/2} per complex channel (tools_for_model.py:398-508) on the
+    moments / whitening kernels; backward = batch sums -> closed-form per-channel whitening derivative
+    -> one apply pass.  x: physical dense [..., 2*Cc] (real half then imag half)."""
+
+    @staticmethod
+    def forward(ctx, x, Wrr, Wri, Wii, Br, Bi, mod, training):
+        Cc = mod.num_features
+        M = x.numel() // (2 * Cc)
+        dev = x.device
+        coef = torch.empty(6, Cc, dtype=torch.float32, device=dev)
+        s = torch.empty(5, Cc, dtype=torch.float64, device=dev)
+        st = ops._stream()
+        if training:
+            call("clskd_cbn_moments", x.data_ptr(), ops._tag(x.dtype), M, Cc, s.data_ptr(), st)
+        rs = mod.track_running_stats
+        P = lambda t: t.data_ptr() if t is not None else None
+        call("clskd_cbn_finalize", s.data_ptr(), M, Cc, float(mod.eps), float(mod.momentum or 0.0),
+             1 if training else 0, P(Wrr), P(Wri), P(Wii),
+             P(mod.RMr) if rs else None, P(mod.RMi) if rs else None, P(mod.RVrr) if rs else None,
+             P(mod.RVri) if rs else None, P(mod.RVii) if rs else None, coef.data_ptr(), st)
+        y = torch.empty_like(x)
+        call("clskd_cbn_apply", x.data_ptr(), ops._tag(x.dtype), M, Cc, coef.data_ptr(), P(Br), P(Bi),
+             y.data_ptr(), ops._tag(y.dtype), st)
+        ctx.mod, ctx.training, ctx.dims = mod, training, (M, Cc)
+        ctx.save_for_backward(x, Wrr, Wri, Wii, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wrr, Wri, Wii, s = ctx.saved_tensors
+        mod, training = ctx.mod, ctx.training
+        M, Cc = ctx.dims
+        dev = x.device
+        st = ops._stream()
+        dy = dense(dy, x.dtype)
+        P = lambda t: t.data_ptr() if t is not None else None
+        s6 = torch.empty(6, Cc, dtype=torch.float64, device=dev)
+        call("clskd_cbn_bwd_moments", x.data_ptr(), dy.data_ptr(), ops._tag(x.dtype), M, Cc, s6.data_ptr(), st)
+        coefb = torch.empty(11, Cc, dtype=torch.float32, device=dev)
+        pg = torch.empty(5, Cc, dtype=torch.float32, device=dev)
+        aff = Wrr is not None
+        call("clskd_cbn_bwd_finalize", s.data_ptr(), s6.data_ptr(), M, Cc, float(mod.eps), 1 if training else 0,
+             P(Wrr), P(Wri), P(Wii), P(mod.RMr), P(mod.RMi), P(mod.RVrr), P(mod.RVri), P(mod.RVii),
+             coefb.data_ptr(), pg[0].data_ptr() if aff else None, pg[1].data_ptr() if aff else None,
+             pg[2].data_ptr() if aff else None, pg[3].data_ptr() if aff else None,
+             pg[4].data_ptr() if aff else None, st)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("clskd_cbn_bwd_apply", x.data_ptr(), dy.data_ptr(), ops._tag(x.dtype), M, Cc, coefb.data_ptr(),
+                 dx.data_ptr(), st)
+        g = [pg[i] if aff else None for i in range(5)]
+        return dx, g[0], g[1], g[2], g[3], g[4], None, None
+
+
 class ComplexBatchNorm(nn.Module):
-    """Trabelsi-style complex batch norm (reference: tools_for_model.py:335-512).  Forward
-    (training and eval statistics) runs on the moments/whitening kernels; the backward pass of this
-    optional block (use_cbn=True, off by default) is not implemented."""
+    """Trabelsi-style complex batch norm (reference: tools_for_model.py:335-512): 2x2 whitening of
+    (real, imag) per channel + complex affine, with batch (training) or running statistics; forward
+    and backward (through the batch statistics, like the reference) run on the C-ABI kernels."""
 
     def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True,
                  complex_axis=1):
@@ -416,28 +472,13 @@ class ComplexBatchNorm(nn.Module):
                 self.register_parameter(n, None)
 
     def forward_phys(self, x, slope=None):
-        if torch.is_grad_enabled() and (x.requires_grad or (self.affine and self.Wrr.requires_grad)):
-            raise NotImplementedError("ComplexBatchNorm: backward is not implemented (forward-only block)")
         Cc = self.num_features
-        M = x.numel() // (2 * Cc)
         training = self.training or not self.track_running_stats
         if self.training and self.track_running_stats:
             self.num_batches_tracked.add_(1)
         dev = x.device
-        coef = torch.empty(6, Cc, dtype=torch.float32, device=dev)
-        s = torch.empty(5, Cc, dtype=torch.float64, device=dev)
-        st = ops._stream()
-        if training:
-            call("clskd_cbn_moments", x.data_ptr(), ops._tag(x.dtype), M, Cc, s.data_ptr(), st)
-        rs = self.track_running_stats
-        P = lambda t: t.data_ptr() if t is not None else None
-        call("clskd_cbn_finalize", s.data_ptr(), M, Cc, float(self.eps), float(self.momentum or 0.0),
-             1 if training else 0, P(self.Wrr), P(self.Wri), P(self.Wii),
-             P(self.RMr) if rs else None, P(self.RMi) if rs else None, P(self.RVrr) if rs else None,
-             P(self.RVri) if rs else None, P(self.RVii) if rs else None, coef.data_ptr(), st)
-        y = torch.empty_like(x)
-        call("clskd_cbn_apply", x.data_ptr(), ops._tag(x.dtype), M, Cc, coef.data_ptr(), P(self.Br), P(self.Bi),
-             y.data_ptr(), ops._tag(y.dtype), st)
+        x = dense(x)
+        y = _CBNFn.apply(x, self.Wrr, self.Wri, self.Wii, self.Br, self.Bi, self, training)
         if slope is not None:
             C = 2 * Cc
             zero = torch.zeros(C, dtype=torch.float32, device=dev)

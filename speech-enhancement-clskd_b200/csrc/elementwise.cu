@@ -443,6 +443,125 @@ __global__ void cbn_apply_kernel(const TX* __restrict__ x, int64_t M, int Cc,
   }
 }
 
+// ---- complex BN backward (autograd of tools_for_model.py:398-508, batch statistics included)
+// pass 1: s6[0..5][Cc] = sum dyr, dyi, dyr*xr, dyr*xi, dyi*xr, dyi*xi
+template <typename T>
+__global__ void cbn_bwd_moments_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int Cc,
+                                       int rpb, double* __restrict__ s) {
+  extern __shared__ float sh[];  // [6][blockDim.x]
+  const int tid = threadIdx.x;
+  const int active = rpb * Cc;
+  const int c = tid % Cc, r0 = tid / Cc;
+  const int64_t mbeg = (int64_t)blockIdx.x * rpb * CS_ROWS_PER_THREAD;
+  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (tid < active) {
+    for (int it = 0; it < CS_ROWS_PER_THREAD; ++it) {
+      int64_t m = mbeg + r0 + (int64_t)it * rpb;
+      if (m >= M) break;
+      const float xr = ld_f(x + m * 2 * Cc + c), xi = ld_f(x + m * 2 * Cc + Cc + c);
+      const float gr = ld_f(dy + m * 2 * Cc + c), gi = ld_f(dy + m * 2 * Cc + Cc + c);
+      a[0] += gr; a[1] += gi; a[2] += gr * xr; a[3] += gr * xi; a[4] += gi * xr; a[5] += gi * xi;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) sh[k * blockDim.x + tid] = a[k];
+  __syncthreads();
+  if (tid < Cc) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double v = 0.;
+      for (int r = 0; r < rpb; ++r) v += sh[k * blockDim.x + r * Cc + tid];
+      atomicAdd(s + (int64_t)k * Cc + tid, v);
+    }
+  }
+}
+
+// per-channel closed-form backward of the 2x2 whitening (fp64): parameter gradients and the
+// coefficients of  dx = Z^T (dy - mean dy) + G (x - mean x)   (G = 0 with running statistics)
+__global__ void cbn_bwd_finalize_kernel(const double* __restrict__ s, const double* __restrict__ s6, int64_t M,
+                                        int Cc, float eps, int training, const float* __restrict__ Wrr,
+                                        const float* __restrict__ Wri, const float* __restrict__ Wii,
+                                        const float* RMr, const float* RMi, const float* RVrr, const float* RVri,
+                                        const float* RVii, float* __restrict__ coefb, float* dWrr, float* dWri,
+                                        float* dWii, float* dBr, float* dBi) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cc) return;
+  double mr, mi, a, b, d;
+  if (training) {
+    mr = s[c] / M; mi = s[Cc + c] / M;
+    a = s[2 * Cc + c] / M - mr * mr;
+    b = s[3 * Cc + c] / M - mr * mi;
+    d = s[4 * Cc + c] / M - mi * mi;
+  } else {
+    mr = RMr[c]; mi = RMi[c]; a = RVrr[c]; b = RVri[c]; d = RVii[c];
+  }
+  a += (double)eps;
+  d += (double)eps;
+  const double sq = sqrt(a * d - b * b), t = sqrt(a + d + 2. * sq), r = 1. / (sq * t);
+  const double Urr = (sq + d) * r, Uii = (sq + a) * r, Uri = -b * r;
+  const double wrr = Wrr ? Wrr[c] : 1., wri = Wri ? Wri[c] : 0., wii = Wii ? Wii[c] : 1.;
+  const double Zrr = wrr * Urr + wri * Uri, Zri = wrr * Uri + wri * Uii;
+  const double Zir = wri * Urr + wii * Uri, Zii = wri * Uri + wii * Uii;
+  const double gr = s6[c], gi = s6[Cc + c];
+  // A[i][j] = sum dy_i * (x_j - mean_j)
+  const double Arr = s6[2 * Cc + c] - mr * gr, Ari = s6[3 * Cc + c] - mi * gr;
+  const double Air = s6[4 * Cc + c] - mr * gi, Aii = s6[5 * Cc + c] - mi * gi;
+  // Z = W U  ->  dW = A U^T (U symmetric), dU = W^T A
+  if (dWrr) dWrr[c] = (float)(Arr * Urr + Ari * Uri);
+  if (dWri) dWri[c] = (float)((Arr * Uri + Ari * Uii) + (Air * Urr + Aii * Uri));
+  if (dWii) dWii[c] = (float)(Air * Uri + Aii * Uii);
+  if (dBr) dBr[c] = (float)gr;
+  if (dBi) dBi[c] = (float)gi;
+  double Grr = 0., Gri = 0., Gii = 0.;
+  if (training) {
+    const double dUrr = wrr * Arr + wri * Air;
+    const double dUri = (wrr * Ari + wri * Aii) + (wri * Arr + wii * Air);
+    const double dUii = wri * Ari + wii * Aii;
+    // derivatives of U(a, b, d)
+    const double ds[3] = {d / (2. * sq), -b / sq, a / (2. * sq)};
+    double dv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double dt = ((k == 1 ? 0. : 1.) + 2. * ds[k]) / (2. * t);
+      const double dr = -r * (ds[k] / sq + dt / t);
+      const double dUrr_k = (ds[k] + (k == 2 ? 1. : 0.)) * r + (sq + d) * dr;
+      const double dUii_k = (ds[k] + (k == 0 ? 1. : 0.)) * r + (sq + a) * dr;
+      const double dUri_k = -(k == 1 ? 1. : 0.) * r - b * dr;
+      dv[k] = dUrr * dUrr_k + dUii * dUii_k + dUri * dUri_k;
+    }
+    Grr = 2. * dv[0] / M; Gri = dv[1] / M; Gii = 2. * dv[2] / M;
+  }
+  const double mgr = training ? gr / M : 0., mgi = training ? gi / M : 0.;
+  coefb[c] = (float)mr;
+  coefb[Cc + c] = (float)mi;
+  coefb[2 * Cc + c] = (float)Zrr;   // dx_r = Zrr dyr + Zir dyi + Grr xcr + Gri xci - cr
+  coefb[3 * Cc + c] = (float)Zir;
+  coefb[4 * Cc + c] = (float)Zri;   // dx_i = Zri dyr + Zii dyi + Gri xcr + Gii xci - ci
+  coefb[5 * Cc + c] = (float)Zii;
+  coefb[6 * Cc + c] = (float)Grr;
+  coefb[7 * Cc + c] = (float)Gri;
+  coefb[8 * Cc + c] = (float)Gii;
+  coefb[9 * Cc + c] = (float)(Zrr * mgr + Zir * mgi);
+  coefb[10 * Cc + c] = (float)(Zri * mgr + Zii * mgi);
+}
+
+template <typename T>
+__global__ void cbn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, int64_t M, int Cc,
+                                     const float* __restrict__ cb, T* __restrict__ dx) {
+  const int64_t total = M * Cc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cc);
+    const int64_t m = i / Cc;
+    const float xr = ld_f(x + m * 2 * Cc + c) - cb[c], xi = ld_f(x + m * 2 * Cc + Cc + c) - cb[Cc + c];
+    const float gr = ld_f(dy + m * 2 * Cc + c), gi = ld_f(dy + m * 2 * Cc + Cc + c);
+    const float dr = cb[2 * Cc + c] * gr + cb[3 * Cc + c] * gi + cb[6 * Cc + c] * xr + cb[7 * Cc + c] * xi - cb[9 * Cc + c];
+    const float di = cb[4 * Cc + c] * gr + cb[5 * Cc + c] * gi + cb[7 * Cc + c] * xr + cb[8 * Cc + c] * xi - cb[10 * Cc + c];
+    st_f(dx + m * 2 * Cc + c, dr);
+    st_f(dx + m * 2 * Cc + Cc + c, di);
+  }
+}
+
 // ------------------------------------------------------------------------------- mask
 // One thread per (b,t,bin).  Trig-free polar mask: cos/sin of atan2 are the normalised
 // components, so est = tanh|m| * |s|_eps * (unit(s) * unit(m)) as a complex product.
@@ -1130,6 +1249,46 @@ extern "C" int clskd_cbn_apply(const void* x, int x_dtype, int64_t M, int Cc, co
                        (cbn_apply_kernel<T, T><<<ew_grid(M * Cc, 256), 256, 0, ST>>>(
                            (const T*)x, M, Cc, coef, Br, Bi, (T*)y)));
   CLSKD_CHECK_LAUNCH("clskd_cbn_apply");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_cbn_bwd_moments(const void* x, const void* dy, int dtype, int64_t M, int Cc, double* s6,
+                                     void* stream) {
+  CLSKD_CHECK_ARG(x && dy && s6, "clskd_cbn_bwd_moments: null pointer");
+  CsGeom g;
+  CLSKD_CHECK_ARG(colstats_geom(M, Cc, &g) == 0, "clskd_cbn_bwd_moments: Cc=%d unsupported", Cc);
+  cudaError_t e__ = cudaMemsetAsync(s6, 0, sizeof(double) * 6 * Cc, ST);
+  if (e__ != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e__)); return CLSKD_ERR_CUDA; }
+  if (M == 0) return CLSKD_OK;
+  size_t sh = 6 * g.threads * sizeof(float);
+  CLSKD_DISPATCH_DTYPE(dtype, T,
+                       (cbn_bwd_moments_kernel<T><<<g.grid, g.threads, sh, ST>>>((const T*)x, (const T*)dy, M, Cc,
+                                                                                  g.rpb, s6)));
+  CLSKD_CHECK_LAUNCH("clskd_cbn_bwd_moments");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_cbn_bwd_finalize(const double* s, const double* s6, int64_t M, int Cc, float eps, int training,
+                                      const float* Wrr, const float* Wri, const float* Wii, const float* RMr,
+                                      const float* RMi, const float* RVrr, const float* RVri, const float* RVii,
+                                      float* coefb, float* dWrr, float* dWri, float* dWii, float* dBr, float* dBi,
+                                      void* stream) {
+  CLSKD_CHECK_ARG(coefb && s6 && (training ? (s != nullptr && M > 0) : (RMr && RMi && RVrr && RVri && RVii)),
+                  "clskd_cbn_bwd_finalize: bad arguments");
+  cbn_bwd_finalize_kernel<<<cdiv(Cc, 128), 128, 0, ST>>>(s, s6, M, Cc, eps, training, Wrr, Wri, Wii, RMr, RMi, RVrr,
+                                                         RVri, RVii, coefb, dWrr, dWri, dWii, dBr, dBi);
+  CLSKD_CHECK_LAUNCH("clskd_cbn_bwd_finalize");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_cbn_bwd_apply(const void* x, const void* dy, int dtype, int64_t M, int Cc, const float* coefb,
+                                   void* dx, void* stream) {
+  CLSKD_CHECK_ARG(x && dy && coefb && dx, "clskd_cbn_bwd_apply: null pointer");
+  if (M * Cc == 0) return CLSKD_OK;
+  CLSKD_DISPATCH_DTYPE(dtype, T,
+                       (cbn_bwd_apply_kernel<T><<<ew_grid(M * Cc, 256), 256, 0, ST>>>((const T*)x, (const T*)dy, M, Cc,
+                                                                                       coefb, (T*)dx)));
+  CLSKD_CHECK_LAUNCH("clskd_cbn_bwd_apply");
   return CLSKD_OK;
 }
 

@@ -340,6 +340,75 @@ class EmuLib:
         Y[:, Cc:] = C[4] * xr + C[5] * xi + (_arr(Bi, Cc) if Bi else 0)
         return 0
 
+    def clskd_cbn_bwd_moments(self, x, dy, dt, M, Cc, s6, stream):
+        _need_f32(dt)
+        X = _arr(x, M * 2 * Cc).reshape(M, 2 * Cc).astype(np.float64)
+        G = _arr(dy, M * 2 * Cc).reshape(M, 2 * Cc).astype(np.float64)
+        xr, xi, gr, gi = X[:, :Cc], X[:, Cc:], G[:, :Cc], G[:, Cc:]
+        S = _arr(s6, 6 * Cc, np.float64).reshape(6, Cc)
+        S[0], S[1] = gr.sum(0), gi.sum(0)
+        S[2], S[3], S[4], S[5] = (gr * xr).sum(0), (gr * xi).sum(0), (gi * xr).sum(0), (gi * xi).sum(0)
+        return 0
+
+    def clskd_cbn_bwd_finalize(self, s, s6, M, Cc, eps, training, Wrr, Wri, Wii, RMr, RMi, RVrr, RVri, RVii,
+                               coefb, dWrr, dWri, dWii, dBr, dBi, stream):
+        if training:
+            S = _arr(s, 5 * Cc, np.float64).reshape(5, Cc)
+            mr, mi = S[0] / M, S[1] / M
+            a, b, d = S[2] / M - mr * mr, S[3] / M - mr * mi, S[4] / M - mi * mi
+        else:
+            mr, mi, a, b, d = (_arr(p, Cc).astype(np.float64) for p in (RMr, RMi, RVrr, RVri, RVii))
+        a, d = a + np.float64(np.float32(eps)), d + np.float64(np.float32(eps))
+        sq = np.sqrt(a * d - b * b)
+        t = np.sqrt(a + d + 2 * sq)
+        r = 1.0 / (sq * t)
+        Urr, Uii, Uri = (sq + d) * r, (sq + a) * r, -b * r
+        one, zero = np.ones(Cc), np.zeros(Cc)
+        wrr = _arr(Wrr, Cc).astype(np.float64) if Wrr else one
+        wri = _arr(Wri, Cc).astype(np.float64) if Wri else zero
+        wii = _arr(Wii, Cc).astype(np.float64) if Wii else one
+        Zrr, Zri = wrr * Urr + wri * Uri, wrr * Uri + wri * Uii
+        Zir, Zii = wri * Urr + wii * Uri, wri * Uri + wii * Uii
+        S6 = _arr(s6, 6 * Cc, np.float64).reshape(6, Cc)
+        gr, gi = S6[0], S6[1]
+        Arr, Ari, Air, Aii = S6[2] - mr * gr, S6[3] - mi * gr, S6[4] - mr * gi, S6[5] - mi * gi
+        for ptr, val in ((dWrr, Arr * Urr + Ari * Uri), (dWri, Arr * Uri + Ari * Uii + Air * Urr + Aii * Uri),
+                         (dWii, Air * Uri + Aii * Uii), (dBr, gr), (dBi, gi)):
+            if ptr:
+                _arr(ptr, Cc)[...] = val
+        Grr = Gri = Gii = zero
+        mgr = mgi = zero
+        if training:
+            dUrr = wrr * Arr + wri * Air
+            dUri = wrr * Ari + wri * Aii + wri * Arr + wii * Air
+            dUii = wri * Ari + wii * Aii
+            ds = [d / (2 * sq), -b / sq, a / (2 * sq)]
+            dv = []
+            for k in range(3):
+                dt_ = ((0.0 if k == 1 else 1.0) + 2 * ds[k]) / (2 * t)
+                dr = -r * (ds[k] / sq + dt_ / t)
+                dUrr_k = (ds[k] + (1.0 if k == 2 else 0.0)) * r + (sq + d) * dr
+                dUii_k = (ds[k] + (1.0 if k == 0 else 0.0)) * r + (sq + a) * dr
+                dUri_k = -(1.0 if k == 1 else 0.0) * r - b * dr
+                dv.append(dUrr * dUrr_k + dUii * dUii_k + dUri * dUri_k)
+            Grr, Gri, Gii = 2 * dv[0] / M, dv[1] / M, 2 * dv[2] / M
+            mgr, mgi = gr / M, gi / M
+        C = _arr(coefb, 11 * Cc).reshape(11, Cc)
+        for i, v in enumerate((mr, mi, Zrr, Zir, Zri, Zii, Grr, Gri, Gii, Zrr * mgr + Zir * mgi, Zri * mgr + Zii * mgi)):
+            C[i] = v
+        return 0
+
+    def clskd_cbn_bwd_apply(self, x, dy, dt, M, Cc, coefb, dx, stream):
+        _need_f32(dt)
+        X = _arr(x, M * 2 * Cc).reshape(M, 2 * Cc)
+        G = _arr(dy, M * 2 * Cc).reshape(M, 2 * Cc)
+        D = _arr(dx, M * 2 * Cc).reshape(M, 2 * Cc)
+        C = _arr(coefb, 11 * Cc).reshape(11, Cc)
+        xr, xi, gr, gi = X[:, :Cc] - C[0], X[:, Cc:] - C[1], G[:, :Cc], G[:, Cc:]
+        D[:, :Cc] = C[2] * gr + C[3] * gi + C[6] * xr + C[7] * xi - C[9]
+        D[:, Cc:] = C[4] * gr + C[5] * gi + C[7] * xr + C[8] * xi - C[10]
+        return 0
+
     # ------------------------------------------------------------------ mask
     @staticmethod
     def _mask_inputs(spec, mask, m_sB, m_sT, B, T, nb):

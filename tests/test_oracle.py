@@ -201,3 +201,55 @@ def test_complex_batch_norm_oracle_against_live_reference(training):
     if training:
         for k, v in upd.items():
             assert torch.allclose(v, getattr(m, k), atol=1e-6), k
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("training", [True, False])
+def test_complex_batch_norm_gradients_oracle_against_live_reference(training):
+    """pins the oracle's ComplexBatchNorm BACKWARD: autograd of the restatement == autograd of the
+    unmodified reference module (input and affine-parameter gradients)"""
+    import warnings
+    mods = ref_shim.load()
+    g = torch.Generator().manual_seed(9)
+    m = mods["tools_for_model"].ComplexBatchNorm(8)
+    for n_, b in m.named_buffers():
+        if b.is_floating_point():
+            b.copy_(0.5 + torch.rand(b.shape, generator=g) if "RV" in n_ and "ri" not in n_ else 0.1 * torch.randn(b.shape, generator=g))
+    m.Br.data.normal_(generator=g)
+    m.Bi.data.normal_(generator=g)
+    p = {k: v.detach().clone() for k, v in list(m.named_parameters()) + list(m.named_buffers())}
+    for k in ("Wrr", "Wri", "Wii", "Br", "Bi"):
+        p[k].requires_grad_(True)
+    x = torch.randn(3, 8, 4, 6, generator=g) + 0.2
+    gy = torch.randn(3, 8, 4, 6, generator=g)
+    m.train(training)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        (m(xa) * gy).sum().backward()
+    (D.complex_batch_norm(xb, p, training) * gy).sum().backward()
+    assert torch.allclose(xb.grad, xa.grad, atol=1e-5, rtol=1e-4)
+    for k in ("Wrr", "Wri", "Wii", "Br", "Bi"):
+        assert torch.allclose(p[k].grad, getattr(m, k).grad, atol=1e-4, rtol=1e-4), k
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_use_cbn_model_oracle_against_live_reference():
+    """DCCRN(use_cbn=True) (DCCRN.py:80-81): the oracle forward follows the live reference in eval and
+    train mode (the norm slot holds ComplexBatchNorm, inferred from the state_dict keys)"""
+    import warnings
+    mods = ref_shim.load()
+    kn, ru = [4, 8, 8, 16, 16, 16], 16
+    torch.manual_seed(21)
+    m = mods["DCCRN"].DCCRN(rnn_units=ru, masking_mode="E", use_clstm=True, use_cbn=True, kernel_num=kn)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = 0.1 * torch.randn(2, 2400, generator=torch.Generator().manual_seed(6))
+    for training in (False, True):
+        m.train(training)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with torch.no_grad():
+                ref = m(x)
+                out = D.dccrn_forward(sd, x, training=training)
+        for a, b in zip(out, ref):
+            assert (a - b).abs().max().item() < 2e-5, training

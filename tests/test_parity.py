@@ -534,6 +534,92 @@ def test_complex_batch_norm_vs_oracle(dev, training):
         assert int(m.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize("training", [True, False])
+def test_complex_batch_norm_backward_vs_oracle_autograd(dev, training):
+    """gradients of ComplexBatchNorm wrt the input (through the batch mean and 2x2 covariance when
+    training) and wrt Wrr/Wri/Wii/Br/Bi against autograd of the oracle restatement"""
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(11)
+    m = tm.ComplexBatchNorm(10)
+    for n_, b in m.named_buffers():
+        if b.is_floating_point():
+            b.copy_(0.5 + torch.rand(b.shape, generator=g) if ("RV" in n_ and "ri" not in n_)
+                    else 0.1 * torch.randn(b.shape, generator=g))
+    for prm in (m.Wrr, m.Wii):
+        prm.data.add_(0.3 * torch.randn(prm.shape, generator=g))
+    m.Br.data.normal_(generator=g)
+    m.Bi.data.normal_(generator=g)
+    p = {k: v.detach().clone() for k, v in list(m.named_parameters()) + list(m.named_buffers())}
+    names = ["Wrr", "Wri", "Wii", "Br", "Bi"]
+    for k in names:
+        p[k].requires_grad_(True)
+    x = (torch.randn(4, 10, 5, 9, generator=g) * torch.linspace(0.5, 2.0, 10).view(1, 10, 1, 1) + 0.3)
+    gy = torch.randn(4, 10, 5, 9, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = D.complex_batch_norm(xr, p, training)
+    (ref * gy).sum().backward()
+    m = m.to(dev)
+    m.train(training)
+    xd = x.to(dev).requires_grad_(True)
+    out = m(xd)
+    (out * gy.to(dev)).sum().backward()
+    assert torch.allclose(out.detach().cpu(), ref.detach(), atol=1e-5, rtol=1e-5)
+    sx = xr.grad.abs().max().item()
+    assert (xd.grad.cpu() - xr.grad).abs().max().item() < 2e-5 * max(sx, 1.0), "dx"
+    for k in names:
+        ref_g = p[k].grad
+        got = getattr(m, k).grad.cpu()
+        assert (got - ref_g).abs().max().item() < 1e-4 * max(ref_g.abs().max().item(), 1.0), k
+
+
+def test_dccrn_with_complex_batch_norm_trains(dev):
+    """use_cbn=True model variant: one SI-SNR training step runs end to end (gradients reach every
+    ComplexBatchNorm parameter and the first encoder convolution)"""
+    import clskd_b200
+    torch.manual_seed(0)
+    m = clskd_b200.DCCRN(rnn_units=16, use_clstm=True, use_cbn=True, kernel_num=[4, 8, 8, 16, 16, 16]).to(dev).train()
+    gen = torch.Generator().manual_seed(0)
+    x, y = 0.1 * torch.randn(2, 1600, generator=gen), 0.1 * torch.randn(2, 1600, generator=gen)
+    wav = m(x.to(dev))[-1]
+    loss = m.loss(wav, y.to(dev), loss_mode='SI-SNR')
+    loss.backward()
+    assert torch.isfinite(loss).all()
+    for n_, prm in m.named_parameters():
+        if n_.startswith("encoder.") and (".1." in n_ or n_.endswith("0.real_conv.weight")):
+            assert prm.grad is not None and torch.isfinite(prm.grad).all(), n_
+    assert m.encoder[0][1].Wrr.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_dccrn_with_complex_batch_norm_vs_oracle(dev, training):
+    """use_cbn=True model (DCCRN.py:80-81): enhanced waveform and SI-SNR gradients against the oracle"""
+    import clskd_b200
+    from oracle import dccrn_oracle as D
+    torch.manual_seed(4)
+    m = clskd_b200.DCCRN(rnn_units=16, use_clstm=True, use_cbn=True, kernel_num=[4, 8, 8, 16, 16, 16])
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    live = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and ".R" not in k
+                                                   and not k.startswith(("stft.", "istft."))) else v)
+            for k, v in sd.items()}
+    gen = torch.Generator().manual_seed(1)
+    x, y = 0.1 * torch.randn(3, 2400, generator=gen), 0.1 * torch.randn(3, 2400, generator=gen)
+    ref_wav = D.dccrn_forward(live, x, training=training)[-1]
+    from oracle import losses_oracle as LO
+    ref_loss = -LO.si_snr(ref_wav, y)
+    ref_loss.backward()
+    m = m.to(dev).train(training)
+    wav = m(x.to(dev))[-1]
+    loss = m.loss(wav, y.to(dev), loss_mode='SI-SNR')
+    loss.backward()
+    assert (wav.detach().cpu() - ref_wav.detach()).abs().max().item() < 2e-5
+    assert rel_err(loss, ref_loss) < 1e-4
+    for name in ("encoder.0.1.Wri", "encoder.2.1.Wrr", "decoder.1.1.Bi", "encoder.1.0.real_conv.weight",
+                 "decoder.4.1.Wii", "enhance.0.real_lstm.weight_ih_l0"):
+        got, want = dict(m.named_parameters())[name].grad.cpu(), live[name].grad
+        assert (got - want).abs().max().item() < 2e-3 * max(want.abs().max().item(), 1e-6) + 1e-6, name
+
+
 def test_dccrn_with_complex_batch_norm_runs(dev):
     """use_cbn=True model variant (DCCRN.py:80-81): forward under no_grad produces the reference shapes"""
     import clskd_b200
