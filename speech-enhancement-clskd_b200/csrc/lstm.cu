@@ -156,6 +156,145 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
   }
 }
 
+// Same recurrence with TWO threads per hidden unit (threads 2j, 2j+1): each contracts half of the k
+// range for all RBF rows, the pair swaps partial sums with one shuffle per value, and each thread then
+// finalises (gate math, state, stores) RBF/2 of the rows.  Halves the serial FMA chain per time step
+// and doubles the warps per scheduler that hide the shared-memory latency - the step time is what
+// bounds this kernel.  Weights in shared memory only (WMODE 0 fp32, 1 bf16).
+template <int WMODE, int RBF>
+__global__ void lstm_fwd_ks2_kernel(const float* __restrict__ pre, const float* __restrict__ whh_t,
+                                    int T, int R, int Bp, int H, int64_t pre_pstride,
+                                    int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride,
+                                    int64_t whh_set_stride, float* __restrict__ h_out,
+                                    float* __restrict__ gates_out, float* __restrict__ c_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int RH = RBF / 2;
+  const int G = 4 * H;
+  const int j = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int set = blockIdx.y;
+  const int r0 = blockIdx.x * RBF + half * RH;      // first row this thread finalises
+  const int64_t out_set_stride = (int64_t)T * R * H;
+  pre += (int64_t)set * pre_set_stride;
+  whh_t += (int64_t)set * whh_set_stride;
+  h_out += (int64_t)set * out_set_stride;
+  if (gates_out) gates_out += (int64_t)set * out_set_stride * 4;
+  if (c_out) c_out += (int64_t)set * out_set_stride;
+
+  float* h_s = reinterpret_cast<float*>(smem_raw);                   // [2][H][RBF]
+  float4* w_f = reinterpret_cast<float4*>(h_s + 2 * H * 4);
+  uint2* w_b = reinterpret_cast<uint2*>(h_s + 2 * H * 4);
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+    const int k = i / H, jj = i - k * H;
+    const float* wp = whh_t + (int64_t)k * G + jj;
+    if (WMODE == 0) {
+      w_f[i] = make_float4(wp[0], wp[H], wp[2 * H], wp[3 * H]);
+    } else {
+      __nv_bfloat162 a = __floats2bfloat162_rn(wp[0], wp[H]), b = __floats2bfloat162_rn(wp[2 * H], wp[3 * H]);
+      w_b[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RH; ++r) h_s[j * RBF + half * RH + r] = 0.f;
+  float c_state[RH];
+  int64_t prow[RH], orow[RH];
+#pragma unroll
+  for (int r = 0; r < RH; ++r) {
+    c_state[r] = 0.f;
+    const int rr = min(r0 + r, R - 1);
+    prow[r] = (int64_t)(rr / Bp) * pre_pstride + (int64_t)(rr % Bp) * pre_ld + j;
+    orow[r] = (int64_t)(rr / Bp) * T * Bp + (rr % Bp);
+  }
+  float pcur[RH][4], pnext[RH][4];
+#pragma unroll
+  for (int r = 0; r < RH; ++r)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      pcur[r][g] = (r0 + r < R) ? pre[prow[r] + g * H] : 0.f;
+      pnext[r][g] = 0.f;
+    }
+  const int kbeg = half * (H >> 1), kend = kbeg + (H >> 1);
+  __syncthreads();
+
+  for (int t = 0; t < T; ++t) {
+    if (t + 1 < T) {
+#pragma unroll
+      for (int r = 0; r < RH; ++r)
+        if (r0 + r < R) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) pnext[r][g] = pre[prow[r] + (int64_t)(t + 1) * pre_tstride + g * H];
+        }
+    }
+    float acc[RBF][4];
+#pragma unroll
+    for (int r = 0; r < RBF; ++r)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[r][g] = 0.f;
+    const float* hb = h_s + (t & 1) * H * RBF;
+#pragma unroll 8
+    for (int k = kbeg; k < kend; ++k) {
+      float w[4];
+      if (WMODE == 0) {
+        const float4 wv = w_f[k * H + j];
+        w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w;
+      } else {
+        const uint2 wv = w_b[k * H + j];
+        w[0] = __uint_as_float(wv.x << 16);
+        w[1] = __uint_as_float(wv.x & 0xffff0000u);
+        w[2] = __uint_as_float(wv.y << 16);
+        w[3] = __uint_as_float(wv.y & 0xffff0000u);
+      }
+      float hr[RBF];
+      if (RBF == 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hb + k * 4);
+        hr[0] = hv.x; hr[1] = hv.y; hr[2 % RBF] = hv.z; hr[3 % RBF] = hv.w;
+      } else {
+        const float2 hv = *reinterpret_cast<const float2*>(hb + k * 2);
+        hr[0] = hv.x; hr[1] = hv.y;
+      }
+#pragma unroll
+      for (int r = 0; r < RBF; ++r)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[r][g] = fmaf(w[g], hr[r], acc[r][g]);
+    }
+    // the pair swaps the partial sums of the rows the OTHER thread finalises
+    float tot[RH][4];
+#pragma unroll
+    for (int r = 0; r < RH; ++r)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float mine = half ? acc[RH + r][g] : acc[r][g];
+        const float send = half ? acc[r][g] : acc[RH + r][g];
+        tot[r][g] = pcur[r][g] + mine + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+    float hn[RH];
+#pragma unroll
+    for (int r = 0; r < RH; ++r) {
+      const float gi = sigm(tot[r][0]), gf = sigm(tot[r][1]), gg = tanhf(tot[r][2]), go = sigm(tot[r][3]);
+      c_state[r] = gf * c_state[r] + gi * gg;
+      hn[r] = go * tanhf(c_state[r]);
+      if (r0 + r < R) {
+        const int64_t row = orow[r] + (int64_t)t * Bp;
+        h_out[row * H + j] = hn[r];
+        if (gates_out) {
+          float* gp = gates_out + row * G;
+          gp[j] = gi;
+          gp[H + j] = gf;
+          gp[2 * H + j] = gg;
+          gp[3 * H + j] = go;
+        }
+        if (c_out) c_out[row * H + j] = c_state[r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RH; ++r) h_s[((t + 1) & 1) * H * RBF + j * RBF + half * RH + r] = hn[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RH; ++r)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pcur[r][g] = pnext[r][g];
+  }
+}
+
 // BPTT.  Thread tid = (q, k): phase A treats it as cell (row q, unit k); phase B as the partial
 // dot product over gate quarter q for hidden unit k.  W_hh [4H][H] in smem (WMODE 0) or global (2).
 template <int WMODE>
@@ -270,19 +409,32 @@ extern "C" int clskd_lstm_fwd(const float* pre, const float* whh_t, int T, int R
   // per SM), 4 rows per CTA for large batches
   const bool rb2 = (int64_t)cdiv(R, 2) * nsets <= (int64_t)sm_count();
   dim3 grid(cdiv(R, rb2 ? 2 : 4), nsets);
+  const bool ks2 = 2 * H <= 1024;      // two threads per hidden unit (k range split in halves)
   cudaError_t e;
 #define LSTM_FWD_ARGS pre, whh_t, T, R, Bp, H, pre_pstride, pre_tstride, pre_ld, pre_set_stride, whh_set_stride, h, gates, c
   if (!w_bf16 && base + w32 <= kSmemLimit) {
     e = cudaFuncSetAttribute(lstm_fwd_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
     if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
-    if (rb2) lstm_fwd_kernel<0, 2><<<grid, H, base + w32, ST>>>(LSTM_FWD_ARGS);
+    if (ks2) {
+      e = cudaFuncSetAttribute(lstm_fwd_ks2_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_ks2_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
+      if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+      if (rb2) lstm_fwd_ks2_kernel<0, 2><<<grid, 2 * H, base + w32, ST>>>(LSTM_FWD_ARGS);
+      else lstm_fwd_ks2_kernel<0, 4><<<grid, 2 * H, base + w32, ST>>>(LSTM_FWD_ARGS);
+    } else if (rb2) lstm_fwd_kernel<0, 2><<<grid, H, base + w32, ST>>>(LSTM_FWD_ARGS);
     else lstm_fwd_kernel<0, 4><<<grid, H, base + w32, ST>>>(LSTM_FWD_ARGS);
   } else if (w_bf16 && base + w16 <= kSmemLimit) {
     e = cudaFuncSetAttribute(lstm_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w16));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w16));
     if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
-    if (rb2) lstm_fwd_kernel<1, 2><<<grid, H, base + w16, ST>>>(LSTM_FWD_ARGS);
+    if (ks2) {
+      e = cudaFuncSetAttribute(lstm_fwd_ks2_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w16));
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_ks2_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w16));
+      if (e != cudaSuccess) { set_error("clskd_lstm_fwd: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+      if (rb2) lstm_fwd_ks2_kernel<1, 2><<<grid, 2 * H, base + w16, ST>>>(LSTM_FWD_ARGS);
+      else lstm_fwd_ks2_kernel<1, 4><<<grid, 2 * H, base + w16, ST>>>(LSTM_FWD_ARGS);
+    } else if (rb2) lstm_fwd_kernel<1, 2><<<grid, H, base + w16, ST>>>(LSTM_FWD_ARGS);
     else lstm_fwd_kernel<1, 4><<<grid, H, base + w16, ST>>>(LSTM_FWD_ARGS);
   } else {
     if (rb2) lstm_fwd_kernel<2, 2><<<grid, H, base, ST>>>(LSTM_FWD_ARGS);
