@@ -87,7 +87,7 @@ def cpu_step_fn(student_w, batch, seconds, mode):
         loss, _ = LO.clskd_step_loss(t_sd, s_live, X, y, abf_e, abf_d, mode=mode)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     return step, batch * seconds
 
 
@@ -139,14 +139,14 @@ def run_reference(args):
     dt = time_cpu(step, max(1, args.steps), warm=max(1, min(args.warmup, 1)))
     val = audio_s / dt
     cores = os.cpu_count() or 1
-    sample = "oracle (CPU port of the reference step) on %d x %.0f s utterances, %d threads" % (
-        args.cpu_batch, args.seconds, cores)
+    sample = ("oracle (CPU port of the reference step) on a bounded sample of the workload: %d x %.0f s utterances "
+              "per step instead of %d, %d threads") % (args.cpu_batch, args.seconds, args.batch, cores)
     line = {
         "impl": "reference", "metric": "audio-seconds/sec per CLSKD distill step", "value": val,
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.cpu_batch),
+        "config": workload_config(args, args.batch),       # the arm's workload; each CPU step is a bounded sample of it
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

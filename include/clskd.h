@@ -76,6 +76,18 @@ typedef struct ClskdTapConv {
   int64_t y_sB, y_sT, y_sF;
   int32_t x_dtype, y_dtype;
   int32_t accumulate;      /* 1: Y += result (fp32 outputs only) */
+  /* Fused epilogue of the tcgen05 forward kernel (all NULL = plain contraction; the other entry points
+   * reject a descriptor that sets any of them).  Applied per output element v = acc + bias[n]:
+   *   ep_scale/ep_shift [N] fp32: v = v*scale[n] + shift[n]   (eval-mode nn.BatchNorm2d folded, DCCRN.py:80-81)
+   *   ep_slope (device scalar):   v = v > 0 ? v : slope*v      (nn.PReLU, DCCRN.py:82)
+   *   stats_sum/stats_sumsq [N] fp64: += column sums of the STORED (rounded) outputs and of their squares
+   *   over the valid rows - the batch statistics of the train-mode BatchNorm that follows the conv;
+   *   the caller zeroes them; several launches (sub-pixel phases of a transposed conv) accumulate. */
+  const float* ep_scale;
+  const float* ep_shift;
+  const float* ep_slope;
+  double* stats_sum;
+  double* stats_sumsq;
 } ClskdTapConv;
 
 /* fp32 CUDA-core implicit GEMM (exact-fp32 policy, and layers too small for a UMMA tile) */
@@ -150,6 +162,10 @@ int clskd_bn_finalize(const double* sum, const double* sumsq, int64_t M, int C, 
 /* eval statistics: mean = running_mean, invstd = rsqrt(running_var + eps) */
 int clskd_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
                         float* mean, float* invstd, void* stream);
+/* eval-mode BatchNorm folded to one affine per channel for a conv epilogue:
+ * scale = gamma*rsqrt(running_var+eps), shift = beta - running_mean*scale (gamma/beta may be NULL) */
+int clskd_bn_fold(const float* running_mean, const float* running_var, const float* gamma,
+                  const float* beta, int C, float eps, float* scale, float* shift, void* stream);
 /* y = prelu((x-mean)*invstd*gamma+beta); slope is a DEVICE scalar pointer or NULL (identity). */
 int clskd_bn_act_fwd(const void* x, int x_dtype, int64_t M, int C, const float* mean,
                      const float* invstd, const float* gamma, const float* beta,

@@ -37,6 +37,8 @@ class TapConv(ctypes.Structure):
         ("y_sB", ctypes.c_int64), ("y_sT", ctypes.c_int64), ("y_sF", ctypes.c_int64),
         ("x_dtype", ctypes.c_int32), ("y_dtype", ctypes.c_int32),
         ("accumulate", ctypes.c_int32),
+        ("ep_scale", ctypes.c_void_p), ("ep_shift", ctypes.c_void_p), ("ep_slope", ctypes.c_void_p),
+        ("stats_sum", ctypes.c_void_p), ("stats_sumsq", ctypes.c_void_p),
     ]
 
 

@@ -235,6 +235,7 @@ class RealConv2d(nn.Module):
 
     def forward_phys(self, x0, x1=None, out_dtype=None):
         if self._use_narrow(x0, x1):
+            ops.request_epilogue(None)      # the pointwise stage below is not the conv output
             plan, dts, dfs = self._narrow_plan()
             z = TapConvFn.apply(plan, x0, None, self.weight, None, None, None, x0.dtype)
             return ops.TapSumFn.apply(z, dts, dfs, self.out_channels, (x0.shape[1], x0.shape[2]), 1,
@@ -262,7 +263,14 @@ class ABF(nn.Module):
 
     def forward(self, x, y=None, shape=None, out_shape=None, feature_type=None):
         if self.att_conv is not None:
+            bn1 = self.conv1[1]
+            ep = None
+            if ops.policy.use_umma and ops.policy.fuse_epilogue and (bn1.training or not bn1.track_running_stats):
+                ep = ops.Epilogue(stats=torch.zeros(2, bn1.num_features, dtype=torch.float64, device=x.device))
+                ops.request_epilogue(ep)         # batch statistics of z1 from the conv epilogue
             z1 = self.conv1[0].forward_phys(to_phys(x))                   # 1x1 conv, pre-BatchNorm
+            ops.request_epilogue(None)
+            pre = ep.stats if (ep is not None and ep.fused) else None
             yp = to_phys(y, z1.dtype, need_dense=True)
             if yp.shape[1] != z1.shape[1]:
                 raise NotImplementedError("ABF: residual and feature maps must share the time axis")
@@ -275,9 +283,9 @@ class ABF(nn.Module):
                 xp = ops.AbfMidFn.apply(z1, yp, bn.weight, bn.bias, att.weight, att.bias,
                                         bn.running_mean if bn.track_running_stats else None,
                                         bn.running_var if bn.track_running_stats else None,
-                                        not use_running, bn.momentum, bn.eps)
+                                        not use_running, bn.momentum, bn.eps, pre)
             else:
-                xp = self.conv1[1].forward_phys(z1, None)
+                xp = self.conv1[1].forward_phys(z1, None, pre)
                 if yp.shape[2] != shape:
                     yp = ResizeFFn.apply(yp, shape)          # F.interpolate(y, (shape, w), 'nearest')
                 z = self.att_conv[0].forward_phys(xp, yp, torch.float32)      # logits [B,T,F,2]

@@ -28,6 +28,7 @@ class _Policy:
         self.name = "fp32"
         self.act_dtype = torch.float32
         self.use_umma = False
+        self.fuse_epilogue = True   # BatchNorm statistics / folded eval BatchNorm + PReLU in the tcgen05 conv epilogue
         self.split_gemm = True   # fp32-input GEMMs (STFT/iSTFT/LSTM projections) as split-bf16 tcgen05 contractions
         self.narrow = "auto"     # tap-in-channel decomposition of narrow convs: "auto" (tensor-core policy) / "always"
 
@@ -419,6 +420,33 @@ umma_launches = 0
 core_launches = 0
 
 
+class Epilogue:
+    """Request for the fused epilogue of the tcgen05 forward kernel (ClskdTapConv.ep_* / stats_*):
+    `scale`/`shift` [N] fp32 (eval BatchNorm folded), `slope` (PReLU weight, 1 element) and/or
+    `stats` fp64 [2, N] (zeroed; receives column sums / sums of squares of the stored output = the
+    batch statistics of the BatchNorm that follows).  `fused` says whether the launch honoured it."""
+
+    def __init__(self, scale=None, shift=None, slope=None, stats=None):
+        self.scale, self.shift, self.slope, self.stats = scale, shift, slope, stats
+        self.fused = False
+
+
+_pending_ep = None
+fused_epilogues = 0      # number of convolutions whose BatchNorm work ran in the tcgen05 epilogue
+
+
+def request_epilogue(ep):
+    """The next TapConvFn.forward consumes this request (set by ConvBNAct right before the conv)."""
+    global _pending_ep
+    _pending_ep = ep
+
+
+def _take_epilogue():
+    global _pending_ep
+    ep, _pending_ep = _pending_ep, None
+    return ep
+
+
 def _view_of(t):
     """(elem_offset, (sB, sT, sF)) of a 4-D [B,T,F,C] tensor whose channel stride is 1."""
     if t.dim() != 4 or (t.shape[3] > 1 and t.stride(3) != 1):
@@ -506,8 +534,10 @@ def _split_gemm(d: TapConv, l: Launch, a, b, bias, x0, y) -> bool:
 
 
 def run_tapconv(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, a, b, bias, y, x0_view=None, x1_view=None,
-                y_view=None, accumulate=False, allow_umma=True):
-    """Run one launch.  *_view = (elem_offset, (sB, sT, sF)) override the tensors' own strides."""
+                y_view=None, accumulate=False, allow_umma=True, ep=None):
+    """Run one launch.  *_view = (elem_offset, (sB, sT, sF)) override the tensors' own strides.
+    ep: Epilogue request; returns None WITHOUT launching when the request cannot be fused (the caller
+    then runs the plain contraction and the separate BatchNorm kernels)."""
     global umma_launches, core_launches
     x0_off, x0_str = x0_view if x0_view is not None else _view_of(x0)
     if x1 is not None:
@@ -518,7 +548,14 @@ def run_tapconv(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, a, b, bias, y, x0_
     d = TapConv()
     _fill_desc(d, x0, x0_off, x0_str, x1, x1_off, x1_str, c0, c1, B, To, Fo, Ti, Fi, l, x0, bias,
                l.N, y, y_off, y_str, accumulate)
-    if policy.use_umma and policy.split_gemm and _split_gemm(d, l, a, b, bias, x0, y):
+    if ep is not None:
+        d.ep_scale, d.ep_shift = _ptr(ep.scale), _ptr(ep.shift)
+        d.ep_slope = _ptr(ep.slope)
+        if ep.stats is not None:
+            d.stats_sum, d.stats_sumsq = ep.stats[0].data_ptr(), ep.stats[1].data_ptr()
+        if not (allow_umma and _umma_ok(d)):
+            return None
+    if ep is None and policy.use_umma and policy.split_gemm and _split_gemm(d, l, a, b, bias, x0, y):
         return y
     if allow_umma and _umma_ok(d):
         w = packed_weights(l._cache, "nc", lambda: l.t_nc, a, b, torch.bfloat16)
@@ -581,10 +618,23 @@ class TapConvFn(torch.autograd.Function):
             bias = packed_weights(plan._cache, "bias", lambda: plan.bias_table, _f32c(bias_a),
                                   _f32c(bias_b) if bias_b is not None else None, torch.float32)
         y = torch.empty((B, To, Fo, plan.N), dtype=out_dtype, device=x0.device)
-        for l in plan.fwd:
+        ep = _take_epilogue()
+        if ep is not None and ((ep.stats is not None and ep.stats.shape[1] != plan.N) or
+                               (ep.scale is not None and ep.scale.numel() != plan.N)):
+            ep = None                # not the conv this request was made for
+        for i, l in enumerate(plan.fwd):
             Fo_l = Fo // l.osf
             yv = (l.ooff * plan.N, (To * Fo * plan.N, Fo * plan.N, l.osf * plan.N))
-            run_tapconv(x0, x1, plan.c0, plan.c1, B, To, Fo_l, Ti, Fi, l, a32, b32, bias, y, y_view=yv)
+            r = run_tapconv(x0, x1, plan.c0, plan.c1, B, To, Fo_l, Ti, Fi, l, a32, b32, bias, y, y_view=yv, ep=ep)
+            if r is None:            # epilogue not fusable: only ever refused on the first launch of a plan
+                if i:
+                    raise RuntimeError("tapconv: fused epilogue refused after the first launch of a plan")
+                ep = None
+                run_tapconv(x0, x1, plan.c0, plan.c1, B, To, Fo_l, Ti, Fi, l, a32, b32, bias, y, y_view=yv)
+        if ep is not None:
+            global fused_epilogues
+            ep.fused = True
+            fused_epilogues += 1
         ctx.plan = plan
         ctx.save_for_backward(x0, x1, a, b)
         ctx.has_bias = (bias_a is not None, bias_b is not None)
@@ -660,7 +710,7 @@ class BNActFn(torch.autograd.Function):
     Replaces nn.BatchNorm2d + nn.PReLU (DCCRN.py:80-82); slope=None -> no activation."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, slope, running_mean, running_var, training, momentum, eps):
+    def forward(ctx, x, gamma, beta, slope, running_mean, running_var, training, momentum, eps, pre_stats=None):
         _require_cuda(x)
         C = x.shape[-1]
         M = x.numel() // C
@@ -669,7 +719,8 @@ class BNActFn(torch.autograd.Function):
         mean, invstd = stats[0], stats[1]
         use_batch = training or running_mean is None
         if use_batch:
-            s, ss = colstats(x.view(M, C))
+            # pre_stats: fp64 [2, C] column sums already accumulated by the producing conv's epilogue
+            s, ss = (pre_stats[0], pre_stats[1]) if pre_stats is not None else colstats(x.view(M, C))
             call("clskd_bn_finalize", s.data_ptr(), ss.data_ptr(), M, C, float(eps),
                  float(momentum if momentum is not None else 0.0), mean.data_ptr(), invstd.data_ptr(),
                  running_mean.data_ptr() if (running_mean is not None and training) else None,
@@ -710,7 +761,7 @@ class BNActFn(torch.autograd.Function):
         dgamma = pg[:C].view_as(gamma) if gamma is not None else None
         dbeta = pg[C:2 * C].view_as(beta) if beta is not None else None
         dslope = pg[2 * C:].view_as(slope) if slope is not None else None
-        return dx, dgamma, dbeta, dslope, None, None, None, None, None
+        return dx, dgamma, dbeta, dslope, None, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------------
@@ -1027,7 +1078,8 @@ class AbfMidFn(torch.autograd.Function):
     z1: dense [B,T,F,C] (1x1-conv output), y_prev: dense [B,T,Fy,C]; returns xb [B,T,F,C]."""
 
     @staticmethod
-    def forward(ctx, z1, y_prev, gamma, beta, watt, batt, running_mean, running_var, training, momentum, eps):
+    def forward(ctx, z1, y_prev, gamma, beta, watt, batt, running_mean, running_var, training, momentum, eps,
+                pre_stats=None):
         B, T, F, C = z1.shape
         Fy = y_prev.shape[2]
         M = B * T * F
@@ -1036,7 +1088,7 @@ class AbfMidFn(torch.autograd.Function):
         mean, invstd = stats[0], stats[1]
         use_batch = training or running_mean is None
         if use_batch:
-            s, ss = colstats(z1.view(M, C))
+            s, ss = (pre_stats[0], pre_stats[1]) if pre_stats is not None else colstats(z1.view(M, C))
             call("clskd_bn_finalize", s.data_ptr(), ss.data_ptr(), M, C, float(eps),
                  float(momentum if momentum is not None else 0.0), mean.data_ptr(), invstd.data_ptr(),
                  running_mean.data_ptr() if (running_mean is not None and training) else None,
@@ -1078,7 +1130,7 @@ class AbfMidFn(torch.autograd.Function):
         dbeta, dgamma = a32[:C].view_as(beta), a32[C:2 * C].view_as(gamma)
         dw = a32[2 * C:6 * C].view_as(watt)
         db = a32[6 * C:] if ctx.has_bias else None
-        return dz1, dy, dgamma, dbeta, dw, db, None, None, None, None, None
+        return dz1, dy, dgamma, dbeta, dw, db, None, None, None, None, None, None
 
 
 def abf_mid_supported(z1, y_prev):

@@ -311,6 +311,7 @@ class ComplexConvTranspose2d(nn.Module):
     def forward_phys(self, x0, x1=None, out_dtype=None):
         ca = None if x1 is None else x0.shape[-1] // 2
         if self._use_narrow(x0, x1):
+            ops.request_epilogue(None)      # the pointwise stage below is not the conv output
             pw, dts, dfs, full = self._narrow_plan(ca)
             z = TapConvFn.apply(pw, x0, x1, self.real_conv.weight, self.imag_conv.weight, None, None, x0.dtype)
             To, Fo = full.out_size(x0.shape[1], x0.shape[2])
@@ -343,14 +344,15 @@ class BatchNorm2d(nn.BatchNorm2d):
     """nn.BatchNorm2d (same parameters/buffers) whose forward is the fused statistics + normalise
     kernel pair; `forward_phys(x, slope)` additionally fuses the following PReLU."""
 
-    def forward_phys(self, x_phys, slope=None):
+    def forward_phys(self, x_phys, slope=None, pre_stats=None):
+        """pre_stats: fp64 [2, C] column sums of x_phys already produced by the conv epilogue"""
         if self.training and self.track_running_stats and self.num_batches_tracked is not None:
             self.num_batches_tracked.add_(1)
         use_running = (not self.training) and self.track_running_stats
         return BNActFn.apply(x_phys, self.weight, self.bias, slope,
                              self.running_mean if self.track_running_stats else None,
                              self.running_var if self.track_running_stats else None,
-                             not use_running, self.momentum, self.eps)
+                             not use_running, self.momentum, self.eps, pre_stats)
 
     def forward(self, inputs):
         return to_logical(self.forward_phys(to_phys(inputs, need_dense=True)))
@@ -366,7 +368,7 @@ class PReLU(nn.PReLU):
         C = x.shape[-1]
         zero = torch.zeros(C, dtype=torch.float32, device=x.device)
         one = torch.ones(C, dtype=torch.float32, device=x.device)
-        y = BNActFn.apply(x, None, None, self.weight, zero, one, False, 0.0, 0.0)
+        y = BNActFn.apply(x, None, None, self.weight, zero, one, False, 0.0, 0.0, None)
         return to_logical(y) if inputs.dim() == 4 else y
 
 
@@ -483,7 +485,7 @@ class ComplexBatchNorm(nn.Module):
             C = 2 * Cc
             zero = torch.zeros(C, dtype=torch.float32, device=dev)
             one = torch.ones(C, dtype=torch.float32, device=dev)
-            y = BNActFn.apply(y, None, None, slope, zero, one, False, 0.0, 0.0)
+            y = BNActFn.apply(y, None, None, slope, zero, one, False, 0.0, 0.0, None)
         return y
 
     def forward(self, inputs):
@@ -496,13 +498,43 @@ class ConvBNAct(nn.Sequential):
     Forward hooks on this module (feature_extraction) see the same output the reference's
     nn.Sequential would produce."""
 
-    def forward_phys(self, x0, x1=None):
+    def _conv(self, x0, x1):
         conv = self[0]
-        z = conv.forward_phys(x0, x1) if x1 is not None else conv.forward_phys(x0)
+        return conv.forward_phys(x0, x1) if x1 is not None else conv.forward_phys(x0)
+
+    def forward_phys(self, x0, x1=None):
         if len(self) == 1:
-            return z
+            return self._conv(x0, x1)
+        bn = self[1]
         slope = self[2].weight if len(self) > 2 else None
-        return self[1].forward_phys(z, slope)
+        if ops.policy.use_umma and ops.policy.fuse_epilogue and type(bn) is BatchNorm2d and x0.dtype == torch.bfloat16:
+            C = bn.num_features
+            use_running = (not bn.training) and bn.track_running_stats
+            if use_running and not torch.is_grad_enabled():
+                # frozen / inference: BatchNorm folded to a per-channel affine and PReLU applied in the conv
+                # epilogue - the activation is written once, already normalised
+                fold = torch.empty(2, C, dtype=torch.float32, device=x0.device)
+                call("clskd_bn_fold", bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                     ops._ptr(ops._f32c(bn.weight)) if bn.weight is not None else None,
+                     ops._ptr(ops._f32c(bn.bias)) if bn.bias is not None else None, C, float(bn.eps),
+                     fold[0].data_ptr(), fold[1].data_ptr(), ops._stream())
+                ep = ops.Epilogue(scale=fold[0], shift=fold[1],
+                                  slope=ops._f32c(slope) if slope is not None else None)
+                ops.request_epilogue(ep)
+                z = self._conv(x0, x1)
+                ops.request_epilogue(None)
+                if ep.fused:
+                    return z
+                return bn.forward_phys(z, slope)
+            if not use_running:
+                # training: the conv epilogue accumulates the batch statistics of what it stores
+                ep = ops.Epilogue(stats=torch.zeros(2, C, dtype=torch.float64, device=x0.device))
+                ops.request_epilogue(ep)
+                z = self._conv(x0, x1)
+                ops.request_epilogue(None)
+                return bn.forward_phys(z, slope, ep.stats if ep.fused else None)
+        z = self._conv(x0, x1)
+        return bn.forward_phys(z, slope)
 
     def forward(self, inputs, skip=None):
         x0 = to_phys(inputs)

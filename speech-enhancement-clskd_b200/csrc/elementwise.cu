@@ -258,6 +258,16 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
   }
 }
 
+__global__ void bn_fold_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, int C, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = (gamma ? gamma[c] : 1.f) * (1.f / sqrtf(rvar[c] + eps));
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - rmean[c] * sc;
+}
+
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar,
                                      int C, float eps, float* __restrict__ mean,
                                      float* __restrict__ invstd) {
@@ -1115,6 +1125,14 @@ extern "C" int clskd_bn_eval_stats(const float* running_mean, const float* runni
   bn_eval_stats_kernel<<<cdiv(C, 128), 128, 0, ST>>>(running_mean, running_var, C, eps, mean,
                                                      invstd);
   CLSKD_CHECK_LAUNCH("clskd_bn_eval_stats");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_bn_fold(const float* running_mean, const float* running_var, const float* gamma,
+                             const float* beta, int C, float eps, float* scale, float* shift, void* stream) {
+  CLSKD_CHECK_ARG(running_mean && running_var && scale && shift, "clskd_bn_fold: null pointer");
+  bn_fold_kernel<<<cdiv(C, 128), 128, 0, ST>>>(running_mean, running_var, gamma, beta, C, eps, scale, shift);
+  CLSKD_CHECK_LAUNCH("clskd_bn_fold");
   return CLSKD_OK;
 }
 

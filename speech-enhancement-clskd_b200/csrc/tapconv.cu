@@ -805,6 +805,10 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
   if (rc) return rc;
   CLSKD_CHECK_ARG(!(d->accumulate && d->y_dtype != CLSKD_F32),
                   "clskd_tapconv_fwd: accumulate needs fp32 output");
+  if (d->ep_scale || d->ep_shift || d->ep_slope || d->stats_sum || d->stats_sumsq) {
+    set_error("clskd_tapconv_fwd: the fused epilogue (ep_*, stats_*) exists on the tcgen05 kernel only");
+    return CLSKD_ERR_UNSUPPORTED;
+  }
   int64_t M = (int64_t)d->B * d->To * d->Fo;
   if (M == 0) return CLSKD_OK;
   cudaStream_t st = (cudaStream_t)stream;

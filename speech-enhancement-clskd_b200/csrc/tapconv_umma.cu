@@ -54,6 +54,12 @@ struct UmmaParams {
   uint32_t staging_bytes;      // one staging buffer: 128 rows x block_n x es
   int nstg;                    // 1 or 2 staging buffers (double-buffered TMA stores)
   int ecols;                   // columns staged per TMA-store round (<= 128): block_n / ecols rounds per tile
+  // fused epilogue (see ClskdTapConv): folded eval BatchNorm, PReLU, batch statistics of the stored outputs
+  const float* ep_scale;
+  const float* ep_shift;
+  const float* ep_slope;
+  double* stats_sum;
+  double* stats_sumsq;
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -171,6 +177,14 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t pitch = (uint32_t)(p.gw_y * p.es);          // 128 / 64 / 32 bytes
     const uint32_t xr = pitch == 128 ? (uint32_t)(row & 7) : (pitch == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1));
     const bool issuer = (threadIdx.x == 64);                    // first epilogue thread
+    const float ep_slope = p.ep_slope ? __ldg(p.ep_slope) : 1.f;
+    // batch statistics: thread et owns column (et % ecols) of every staging round and the row slice
+    // [part*ecols, (part+1)*ecols) of the 128-row tile; partial sums stay in registers across all
+    // tiles of this persistent CTA (tiles_n == 1, <= 2 rounds) and are flushed once at the end.
+    // (A 16-byte-per-thread read-back was measured slower: 138 registers instead of 115.)
+    const int et = threadIdx.x - 64;
+    const int st_col = et % p.ecols, st_part = et / p.ecols;
+    float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f;
     int local = 0;
     int sround = 0;                                             // staging rounds issued so far
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
@@ -204,6 +218,14 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if (p.bias) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
+          }
+          if (p.ep_scale) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = fmaf(o[e], __ldg(p.ep_scale + n0 + c + e), __ldg(p.ep_shift + n0 + c + e));
+          }
+          if (p.ep_slope) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = o[e] > 0.f ? o[e] : o[e] * ep_slope;
           }
           const int cl = c - cbeg;
           const int sub = cl / p.gw_y, col = cl - sub * p.gw_y;
@@ -243,6 +265,34 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        if (p.stats_sum) {
+          // column sums of the staged (bf16-rounded) tile over its valid rows, read back from the swizzled
+          // staging buffer (consecutive threads read consecutive columns of one row: conflict free); the
+          // buffer is not rewritten before every epilogue thread has passed the next round's barriers
+          int nvalid = (p.To - t0) * p.fo_tile;
+          if (nvalid > UM) nvalid = UM;
+          const int sub = st_col / p.gw_y, cl = st_col - sub * p.gw_y;
+          const uint8_t* colp = stg + (size_t)sub * p.y_sub_bytes + ((cl * 2) & 15);
+          const uint32_t chk = (uint32_t)(cl * 2) >> 4;
+          int rend = (st_part + 1) * p.ecols;
+          if (rend > nvalid) rend = nvalid;
+          float s = 0.f, q = 0.f;
+          for (int rr = st_part * p.ecols; rr < rend; ++rr) {
+            const uint32_t x2 = pitch == 128 ? (uint32_t)(rr & 7) : (pitch == 64 ? (uint32_t)((rr >> 1) & 3) : (uint32_t)((rr >> 2) & 1));
+            const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + (size_t)rr * pitch + ((chk ^ x2) << 4)));
+            s += v;
+            q = fmaf(v, v, q);
+          }
+          if (rd == 0) { st_s0 += s; st_q0 += q; } else { st_s1 += s; st_q1 += q; }
+        }
+      }
+    }
+    if (p.stats_sum) {
+      atomicAdd(p.stats_sum + st_col, (double)st_s0);
+      atomicAdd(p.stats_sumsq + st_col, (double)st_q0);
+      if (p.block_n > p.ecols) {
+        atomicAdd(p.stats_sum + p.ecols + st_col, (double)st_s1);
+        atomicAdd(p.stats_sumsq + p.ecols + st_col, (double)st_q1);
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
@@ -264,6 +314,13 @@ const char* umma_unsupported(const ClskdTapConv* d) {
   if (d->sf != 1 && d->sf != 2) return "sf must be 1 or 2";
   if (!is_pow2(d->Fo) || (d->Fo > 128 && d->Fo % 128)) return "Fo must be a power of two";
   if (d->accumulate) return "accumulate unsupported";
+  if ((d->ep_scale == nullptr) != (d->ep_shift == nullptr)) return "ep_scale and ep_shift come together";
+  if ((d->stats_sum == nullptr) != (d->stats_sumsq == nullptr)) return "stats_sum and stats_sumsq come together";
+  if (d->stats_sum) {
+    if (d->y_dtype != CLSKD_BF16) return "fused statistics need a bf16 output";
+    if (d->N != 16 && d->N != 32 && d->N != 64 && d->N != 128 && d->N != 256)
+      return "fused statistics need N in {16,32,64,128,256}";
+  }
   if (d->Fi % d->sf) return "Fi must be a multiple of sf";
   auto chk = [&](const void* x, int64_t sB, int64_t sT, int64_t sF) -> const char* {
     if ((uintptr_t)x % 16) return "x not 16-byte aligned";
@@ -367,6 +424,8 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   p.stages = stages;
   p.y = d->y; p.y_sB = d->y_sB; p.y_sT = d->y_sT; p.y_sF = d->y_sF; p.y_dtype = d->y_dtype;
   p.bias = d->bias; p.N = d->N;
+  p.ep_scale = d->ep_scale; p.ep_shift = d->ep_shift; p.ep_slope = d->ep_slope;
+  p.stats_sum = d->stats_sum; p.stats_sumsq = d->stats_sumsq;
 
   CUtensorMap tmA0, tmA1, tmB;
   int rc = encode_act(enc, &tmA0, d->x0, d->c0, d->sf, d->Fi, d->Ti, d->B, d->x0_sB, d->x0_sT,

@@ -324,3 +324,59 @@ def test_split_bf16_gemm_bias_and_padding(cuda_dev):
         y = lin.forward_rows(x.to(cuda_dev))
     assert ops.umma_launches == n0 + 1
     assert (y.cpu().double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("kind,cin,cout,F,T,B", [("conv", 32, 64, 64, 37, 3), ("conv", 64, 256, 16, 130, 2),
+                                                  ("deconv", 64, 32, 8, 33, 2), ("deconv", 32, 16, 64, 70, 1)])
+def test_fused_conv_epilogue_batch_statistics_and_folded_eval_bn(cuda_dev, kind, cin, cout, F, T, B):
+    """tcgen05 conv epilogue: (a) train-mode BatchNorm statistics accumulated from the stored outputs
+    (sub-pixel phases of the transposed conv accumulate into one buffer, ragged last time tile masked),
+    (b) eval-mode BatchNorm folded to scale/shift + PReLU applied before the single store.  Both against
+    the separate statistics / normalise kernels on the same operands, and (a) against the fp32 oracle."""
+    import clskd_b200
+    from clskd_b200 import ops
+    from clskd_b200 import tools_for_model as tm
+    g = torch.Generator().manual_seed(cin + F + T)
+    if kind == "conv":
+        conv = tm.ComplexConv2d(cin, cout, kernel_size=(5, 2), stride=(2, 1), padding=(2, 1))
+        x1 = None
+    else:
+        conv = tm.ComplexConvTranspose2d(2 * cin, cout, kernel_size=(5, 2), stride=(2, 1), padding=(2, 0),
+                                         output_padding=(1, 0))
+        x1 = torch.randn(B, T, F, cin, generator=g).bfloat16().to(cuda_dev)
+    conv.real_conv.bias.data.normal_(generator=g)
+    conv.imag_conv.bias.data.normal_(generator=g)
+    blk = tm.ConvBNAct(conv, tm.BatchNorm2d(cout), tm.PReLU()).to(cuda_dev)
+    blk[1].weight.data.uniform_(0.5, 1.5, generator=None)
+    blk[1].bias.data.normal_()
+    blk[1].running_mean.normal_(0, 0.1)
+    blk[1].running_var.uniform_(0.5, 1.5)
+    x0 = torch.randn(B, T, F, cin, generator=g).bfloat16().to(cuda_dev)
+    clskd_b200.set_precision("bf16")
+    outs = {}
+    for fuse in (True, False):
+        ops.policy.fuse_epilogue = fuse
+        for mode in ("train", "eval"):
+            blk.train(mode == "train")
+            rm0, rv0 = blk[1].running_mean.clone(), blk[1].running_var.clone()
+            n0 = ops.fused_epilogues
+            with torch.no_grad():
+                y = blk.forward_phys(x0, x1)
+            assert (ops.fused_epilogues - n0) == (1 if fuse else 0), (fuse, mode)
+            outs[(fuse, mode)] = (y.float().cpu(), blk[1].running_mean.clone().cpu(), blk[1].running_var.clone().cpu())
+            blk[1].running_mean.copy_(rm0)
+            blk[1].running_var.copy_(rv0)
+    ops.policy.fuse_epilogue = True
+    yf, rmf, rvf = outs[(True, "train")]
+    yu, rmu, rvu = outs[(False, "train")]
+    scale = yu.abs().max().item()
+    # same stored bf16 conv output, statistics differ only by fp32-vs-fp64 partial sums
+    assert (rmf - rmu).abs().max().item() < 1e-5 * max(1.0, rmu.abs().max().item())
+    assert (rvf - rvu).abs().max().item() < 1e-4 * max(1.0, rvu.abs().max().item())
+    assert (yf - yu).abs().max().item() < 1e-2 * scale          # at most a bf16 ulp here and there
+    assert (yf - yu).abs().mean().item() < 1e-4 * scale
+    ye, yeu = outs[(True, "eval")][0], outs[(False, "eval")][0]
+    se = yeu.abs().max().item()
+    # folded: one rounding of the normalised value instead of two (conv output, then BN output)
+    assert (ye - yeu).abs().max().item() < 2e-2 * se
+    assert (ye - yeu).abs().mean().item() < 2e-3 * se
