@@ -62,6 +62,9 @@ struct UmmaParams {
   double* stats_sumsq;
 };
 
+// EP = false: plain contraction (+bias); EP = true: the fused epilogue variants (kept out of the plain
+// instantiation so that it stays at its lean register count)
+template <bool EP>
 __global__ void __launch_bounds__(kThreads, 2)
 tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
@@ -177,7 +180,7 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t pitch = (uint32_t)(p.gw_y * p.es);          // 128 / 64 / 32 bytes
     const uint32_t xr = pitch == 128 ? (uint32_t)(row & 7) : (pitch == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1));
     const bool issuer = (threadIdx.x == 64);                    // first epilogue thread
-    const float ep_slope = p.ep_slope ? __ldg(p.ep_slope) : 1.f;
+    const float ep_slope = (EP && p.ep_slope) ? __ldg(p.ep_slope) : 1.f;
     // batch statistics: thread et owns column (et % ecols) of every staging round and the row slice
     // [part*ecols, (part+1)*ecols) of the 128-row tile; partial sums stay in registers across all
     // tiles of this persistent CTA (tiles_n == 1, <= 2 rounds) and are flushed once at the end.
@@ -219,11 +222,11 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
             for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
           }
-          if (p.ep_scale) {
+          if (EP && p.ep_scale) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) o[e] = fmaf(o[e], __ldg(p.ep_scale + n0 + c + e), __ldg(p.ep_shift + n0 + c + e));
           }
-          if (p.ep_slope) {
+          if (EP && p.ep_slope) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) o[e] = o[e] > 0.f ? o[e] : o[e] * ep_slope;
           }
@@ -265,7 +268,7 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (p.stats_sum) {
+        if (EP && p.stats_sum) {
           // column sums of the staged (bf16-rounded) tile over its valid rows, read back from the swizzled
           // staging buffer (consecutive threads read consecutive columns of one row: conflict free); the
           // buffer is not rewritten before every epilogue thread has passed the next round's barriers
@@ -287,7 +290,7 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
       }
     }
-    if (p.stats_sum) {
+    if (EP && p.stats_sum) {
       atomicAdd(p.stats_sum + st_col, (double)st_s0);
       atomicAdd(p.stats_sumsq + st_col, (double)st_q0);
       if (p.block_n > p.ecols) {
@@ -464,16 +467,18 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
     if (r) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(y) failed: %d", (int)r); return CLSKD_ERR_CUDA; }
   }
   size_t smem = (size_t)stages * stage_bytes + (size_t)p.nstg * staging_bytes + 1024;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapconv_umma_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool ep = d->ep_scale || d->ep_slope || d->stats_sum;
+  static size_t smem_set[2] = {0, 0};
+  if (smem > smem_set[ep ? 1 : 0]) {
+    cudaError_t e = ep ? cudaFuncSetAttribute(tapconv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(tapconv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("clskd_tapconv_fwd_umma: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
-    smem_set = smem;
+    smem_set[ep ? 1 : 0] = smem;
   }
   const int64_t max_ctas = (int64_t)sm_count() * (two_ctas ? 2 : 1);
   const unsigned grid = (unsigned)(tiles < max_ctas ? tiles : max_ctas);
-  tapconv_umma_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmY, p);
+  if (ep) tapconv_umma_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmY, p);
+  else tapconv_umma_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmY, p);
   CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd_umma");
   return CLSKD_OK;
 }
