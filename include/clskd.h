@@ -349,6 +349,25 @@ int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y, int dtype
                       const float* beta, const float* watt, const float* logits, int training,
                       double* sums, double* dwatt, double* dbatt, void* dz1, void* dy, void* stream);
 
+/* The same block when the 1x1 conv in front of it has only TWO input channels (the mask-level map
+ * of the decoder side, framework.py:209 with in_channel = 2): z1 = W1 x is recomputed per row from
+ * x [B,T,F,2] and w1 [C][2] (fp32) instead of being stored and re-read, BatchNorm statistics of z1 come
+ * from the 2x2 moments of x (clskd_cbn_moments with Cc = 1 -> clskd_rank2_colstats -> clskd_bn_finalize),
+ * and the backward returns dx [B,T,F,2] and dw1 (fp64 [C][2], zeroed by the call) directly - replacing the
+ * conv1 forward, its statistics pass, its data- and weight-gradient launches and the dz1 round trip. */
+int clskd_abf_mid_xs_fwd(const void* x, const float* w1, const void* y, int dtype, int B, int T, int F,
+                         int Fy, int C, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, const float* watt, const float* batt, void* xb, float* logits,
+                         void* stream);
+int clskd_abf_mid_xs_bwd(const void* gout, const void* x, const float* w1, const void* y, int dtype, int B,
+                         int T, int F, int Fy, int C, const float* mean, const float* invstd,
+                         const float* gamma, const float* beta, const float* watt, const float* logits,
+                         int training, double* sums, double* dwatt, double* dbatt, double* dw1, void* dx,
+                         void* dy, void* stream);
+/* sum[c] = sum_m (W1 x_m)[c], sumsq[c] = sum_m (W1 x_m)[c]^2 from s5 = moments of the 2-channel x */
+int clskd_rank2_colstats(const double* s5, const float* w1, int C, double* sum, double* sumsq,
+                         void* stream);
+
 /* Tap-in-channel decomposition of a convolution-like layer with very few output channels (ABF's
  * 3x3 conv onto the 2-channel mask map; the last, mask-producing transposed conv of the decoder):
  * a pointwise GEMM first produces, at every INPUT position, the contribution to each (tap, n) pair

@@ -261,8 +261,30 @@ class ABF(nn.Module):
         nn.init.kaiming_uniform_(self.conv2[0].weight, a=1)
         self.fused = True     # fused BN + resize + attention + blend kernel where the shapes allow
 
+    def _rank2_ok(self, x, y, shape):
+        """fused mid stage with the 1x1 conv folded in: tensor-core policy, 2 input channels, no conv bias"""
+        c1 = self.conv1[0]
+        if not (ops.policy.use_umma and ops.policy.abf_rank2 and self.fused and c1.in_channels == 2
+                and c1.bias is None and x.is_cuda and x.shape[2] == shape and y.shape[3] == x.shape[3]):
+            return False
+        B, _, F, T = x.shape
+        C, Fy = y.shape[1], y.shape[2]
+        return C == c1.out_channels and bool(ops._lib.load().clskd_abf_mid_supported(B, T, F, Fy, C))
+
     def forward(self, x, y=None, shape=None, out_shape=None, feature_type=None):
-        if self.att_conv is not None:
+        if self.att_conv is not None and self._rank2_ok(x, y, shape):
+            # 2-channel input: z1 = W1 x never touches HBM (recomputed inside the fused mid-stage kernels)
+            bn, att = self.conv1[1], self.att_conv[0]
+            xs = ops.dense(to_phys(x))
+            yp = to_phys(y, xs.dtype, need_dense=True)
+            if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+            use_running = (not bn.training) and bn.track_running_stats
+            xp = ops.AbfMidXsFn.apply(xs, yp, self.conv1[0].weight, bn.weight, bn.bias, att.weight, att.bias,
+                                      bn.running_mean if bn.track_running_stats else None,
+                                      bn.running_var if bn.track_running_stats else None,
+                                      not use_running, bn.momentum, bn.eps)
+        elif self.att_conv is not None:
             bn1 = self.conv1[1]
             ep = None
             if ops.policy.use_umma and ops.policy.fuse_epilogue and (bn1.training or not bn1.track_running_stats):

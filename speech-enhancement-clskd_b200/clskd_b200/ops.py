@@ -28,6 +28,7 @@ class _Policy:
         self.name = "fp32"
         self.act_dtype = torch.float32
         self.use_umma = False
+        self.abf_rank2 = True       # ABF level whose 1x1 conv has 2 input channels: z1 recomputed in the mid kernels
         self.fuse_epilogue = True   # BatchNorm statistics / folded eval BatchNorm + PReLU in the tcgen05 conv epilogue
         self.split_gemm = True   # fp32-input GEMMs (STFT/iSTFT/LSTM projections) as split-bf16 tcgen05 contractions
         self.narrow = "auto"     # tap-in-channel decomposition of narrow convs: "auto" (tensor-core policy) / "always"
@@ -1131,6 +1132,76 @@ class AbfMidFn(torch.autograd.Function):
         dw = a32[2 * C:6 * C].view_as(watt)
         db = a32[6 * C:] if ctx.has_bias else None
         return dz1, dy, dgamma, dbeta, dw, db, None, None, None, None, None, None
+
+
+class AbfMidXsFn(torch.autograd.Function):
+    """AbfMidFn for a 1x1 conv with TWO input channels in front of the block (the mask-level map of the
+    decoder side): z1 = W1 x is recomputed per row inside the kernels, the BatchNorm statistics of z1
+    come from the 2x2 moments of x, and the backward returns dx and dW1 directly (clskd_abf_mid_xs_*).
+    xs: dense [B,T,F,2]; w1: conv1 weight [C,2,1,1]; y_prev: dense [B,T,Fy,C]; returns xb [B,T,F,C]."""
+
+    @staticmethod
+    def forward(ctx, xs, y_prev, w1, gamma, beta, watt, batt, running_mean, running_var, training, momentum, eps):
+        B, T, F, _ = xs.shape
+        C = w1.shape[0]
+        Fy = y_prev.shape[2]
+        M = B * T * F
+        dev = xs.device
+        st = _stream()
+        w1f = _f32c(w1).view(C, 2)
+        stats = torch.empty(2, C, dtype=torch.float32, device=dev)
+        mean, invstd = stats[0], stats[1]
+        use_batch = training or running_mean is None
+        if use_batch:
+            s5 = torch.empty(5, dtype=torch.float64, device=dev)
+            call("clskd_cbn_moments", xs.data_ptr(), _tag(xs.dtype), M, 1, s5.data_ptr(), st)
+            ss = torch.empty(2, C, dtype=torch.float64, device=dev)
+            call("clskd_rank2_colstats", s5.data_ptr(), w1f.data_ptr(), C, ss[0].data_ptr(), ss[1].data_ptr(), st)
+            call("clskd_bn_finalize", ss[0].data_ptr(), ss[1].data_ptr(), M, C, float(eps),
+                 float(momentum if momentum is not None else 0.0), mean.data_ptr(), invstd.data_ptr(),
+                 running_mean.data_ptr() if (running_mean is not None and training) else None,
+                 running_var.data_ptr() if (running_var is not None and training) else None, st)
+        else:
+            call("clskd_bn_eval_stats", running_mean.data_ptr(), running_var.data_ptr(), C, float(eps),
+                 mean.data_ptr(), invstd.data_ptr(), st)
+        g32, b32 = _f32c(gamma), _f32c(beta)
+        w32 = _f32c(watt).view(2, 2 * C)
+        ba32 = _f32c(batt) if batt is not None else None
+        xb = torch.empty((B, T, F, C), dtype=xs.dtype, device=dev)
+        logits = torch.empty((B, T, F, 2), dtype=torch.float32, device=dev)
+        call("clskd_abf_mid_xs_fwd", xs.data_ptr(), w1f.data_ptr(), y_prev.data_ptr(), _tag(xs.dtype), B, T, F, Fy, C,
+             mean.data_ptr(), invstd.data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(), _ptr(ba32),
+             xb.data_ptr(), logits.data_ptr(), st)
+        ctx.save_for_backward(xs, y_prev, stats, gamma, beta, watt, logits, w1)
+        ctx.use_batch = use_batch
+        ctx.has_bias = batt is not None
+        return xb
+
+    @staticmethod
+    def backward(ctx, g):
+        xs, y_prev, stats, gamma, beta, watt, logits, w1 = ctx.saved_tensors
+        B, T, F, _ = xs.shape
+        C = w1.shape[0]
+        Fy = y_prev.shape[2]
+        dev = xs.device
+        g = dense(g, xs.dtype)
+        acc = torch.empty(8 * C + 2, dtype=torch.float64, device=dev)
+        sums, dwatt, dbatt, dw1 = acc[:2 * C], acc[2 * C:6 * C], acc[6 * C:6 * C + 2], acc[6 * C + 2:]
+        dxs = torch.empty_like(xs)
+        dy = torch.empty_like(y_prev)
+        g32, b32 = _f32c(gamma), _f32c(beta)
+        w32 = _f32c(watt).view(2, 2 * C)
+        w1f = _f32c(w1).view(C, 2)
+        call("clskd_abf_mid_xs_bwd", g.data_ptr(), xs.data_ptr(), w1f.data_ptr(), y_prev.data_ptr(), _tag(xs.dtype),
+             B, T, F, Fy, C, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(),
+             logits.data_ptr(), 1 if ctx.use_batch else 0, sums.data_ptr(), dwatt.data_ptr(), dbatt.data_ptr(),
+             dw1.data_ptr(), dxs.data_ptr(), dy.data_ptr(), _stream())
+        a32 = f64_to_f32(acc)
+        dbeta, dgamma = a32[:C].view_as(beta), a32[C:2 * C].view_as(gamma)
+        dw = a32[2 * C:6 * C].view_as(watt)
+        db = a32[6 * C:6 * C + 2] if ctx.has_bias else None
+        dw1_ = a32[6 * C + 2:].view_as(w1)
+        return dxs, dy, dw1_, dgamma, dbeta, dw, db, None, None, None, None, None
 
 
 def abf_mid_supported(z1, y_prev):

@@ -61,6 +61,9 @@ __device__ __forceinline__ void cp16(void* sdst, const void* gsrc) {
 __device__ __forceinline__ void cp8(void* sdst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s_u32(sdst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp4(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_u32(sdst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -87,6 +90,27 @@ __device__ __forceinline__ void ld_vec8(const uint8_t* slot0, int slot_stride, c
   const float4 b = *reinterpret_cast<const float4*>(slot0 + slot_stride);
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
+// XS variants: the 1x1 conv in front of the block has only TWO input channels (the mask-level map of
+// the decoder side), so z1 = W1 x is recomputed per row from the 2-channel input instead of being
+// stored and re-read (4 or 8 bytes per row instead of 2C or 4C), and the backward produces dx and dW1
+// directly instead of writing dz1 for a separate data/weight-gradient pass.
+// n consecutive 2-channel rows of type T -> copy into a pipeline slot / decode from it
+template <typename T>
+__device__ __forceinline__ void cp_xs(uint8_t* slot, const T* g, int nrows) {
+  // bf16: 4 bytes per row, fp32: 8 bytes per row
+  if (sizeof(T) == 2) { if (nrows == 2) cp8(slot, g); else cp4(slot, g); }
+  else { cp8(slot, g); if (nrows == 2) cp8(slot + 8, g + 2); }
+}
+__device__ __forceinline__ void ld_xs(const uint8_t* slot, const __nv_bfloat16*, int row, float& x0, float& x1) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(slot + 4 * row);
+  x0 = __uint_as_float(u << 16);
+  x1 = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ void ld_xs(const uint8_t* slot, const float*, int row, float& x0, float& x1) {
+  const float2 v = *reinterpret_cast<const float2*>(slot + 8 * row);
+  x0 = v.x;
+  x1 = v.y;
+}
 constexpr int PD = 3;   // pipeline depth
 
 struct AbfGeom {
@@ -104,11 +128,12 @@ __device__ __forceinline__ int64_t yrow(const AbfGeom& g, int64_t m) { return m 
 // per-channel constants staged in shared memory as [NCONST][C] floats (a lane reads its 8 channels
 // of one constant with two 16-byte loads; lanes of a row are contiguous -> conflict free).  Keeping
 // them out of registers is what lets two or three CTAs stay resident per SM.
-enum { K_SC = 0, K_SH, K_WX0, K_WY0, K_WX1, K_WY1, K_MU, K_IS, K_GI, K_K1, K_K2, NCONST };
+enum { K_SC = 0, K_SH, K_WX0, K_WY0, K_WX1, K_WY1, K_MU, K_IS, K_GI, K_K1, K_K2, K_W10, K_W11, NCONST };
 
 __device__ __forceinline__ void stage_consts(float* cs, int C, const float* mean, const float* invstd,
                                              const float* gamma, const float* beta, const float* watt,
-                                             const double* sums, double invM, int training) {
+                                             const double* sums, double invM, int training,
+                                             const float* w1 = nullptr) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float g = gamma ? gamma[c] : 1.f;
     const float sc = invstd[c] * g;
@@ -123,6 +148,8 @@ __device__ __forceinline__ void stage_consts(float* cs, int C, const float* mean
     cs[K_GI * C + c] = g * invstd[c];
     cs[K_K1 * C + c] = (sums && training) ? (float)(sums[c] * invM) : 0.f;
     cs[K_K2 * C + c] = (sums && training) ? (float)(sums[C + c] * invM) : 0.f;
+    cs[K_W10 * C + c] = w1 ? w1[2 * c] : 0.f;          // conv1 weight [C][2] (XS variants)
+    cs[K_W11 * C + c] = w1 ? w1[2 * c + 1] : 0.f;
   }
   __syncthreads();
 }
@@ -132,11 +159,12 @@ __device__ __forceinline__ void ldc(const float* cs, int which, int C, int cg, f
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
-template <typename T>
+template <typename T, bool XS>
 __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict__ z1, const T* __restrict__ y, AbfGeom g,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ watt, const float* __restrict__ batt,
+                                                            const float* __restrict__ w1,
                                                             T* __restrict__ xb, float* __restrict__ logits) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* cs = reinterpret_cast<float*>(smem_raw);
@@ -145,7 +173,7 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
   constexpr int NSLOT = 2 * RQ * NCP;                    // z1[q], y[q]
   constexpr int SLOT_STRIDE = AT * 16;                   // bytes between consecutive slots of a thread
   uint8_t* pipe = smem_raw + ((sizeof(float) * NCONST * g.C + 15) & ~(size_t)15) + threadIdx.x * 16;
-  stage_consts(cs, g.C, mean, invstd, gamma, beta, watt, nullptr, 0., 0);
+  stage_consts(cs, g.C, mean, invstd, gamma, beta, watt, nullptr, 0., 0, XS ? w1 : nullptr);
   const int lane = threadIdx.x & 31;
   const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
   const float b0 = batt ? batt[0] : 0.f, b1 = batt ? batt[1] : 0.f;
@@ -164,7 +192,8 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
     for (int q = 0; q < RQ; ++q) {
       const int64_t m = mi + q * rpw;
       if (m < g.M) {
-        cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, z1 + (m << cs_) + coff);
+        if (XS) cp_xs<T>(st + (q * NCP) * SLOT_STRIDE, z1 + 2 * m, 1);
+        else cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, z1 + (m << cs_) + coff);
         cp_vec8<T>(st + ((RQ + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, y + (yrow(g, m) << cs_) + coff);
       }
     }
@@ -189,7 +218,16 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
       const int64_t m = m0 + q * rpw;
       live[q] = m < g.M;
       if (live[q]) {
-        ld_vec8(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, xv[q]);
+        if (XS) {
+          float x0, x1, wa[8], wb[8];
+          ld_xs(st + (q * NCP) * SLOT_STRIDE, (const T*)nullptr, 0, x0, x1);
+          ldc(cs, K_W10, g.C, cg, wa);
+          ldc(cs, K_W11, g.C, cg, wb);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xv[q][e] = fmaf(wa[e], x0, wb[e] * x1);      // z1 = W1 x
+        } else {
+          ld_vec8(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, xv[q]);
+        }
         ld_vec8(st + ((RQ + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[q]);
       } else {
 #pragma unroll
@@ -252,7 +290,7 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
 // MODE 1: apply pass (dz1, dy_prev)
 // A lane group always processes the PAIR of rows (f = 2j, 2j+1) that share one y_prev row when
 // Fy = F/2 (so dy_prev is written once, without atomics); with Fy = F the pair is two plain rows.
-template <typename T, int MODE>
+template <typename T, int MODE, bool XS>
 __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ z1,
                                                             const T* __restrict__ y, AbfGeom g,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -260,7 +298,8 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
                                                             const float* __restrict__ watt, const float* __restrict__ logits,
                                                             double* __restrict__ sums, double* __restrict__ dwatt,
                                                             double* __restrict__ dbatt, int training, T* __restrict__ dz1,
-                                                            T* __restrict__ dy) {
+                                                            T* __restrict__ dy, const float* __restrict__ w1,
+                                                            double* __restrict__ dw1) {
   extern __shared__ __align__(16) uint8_t smem_raw[];   // constants, (MODE 0) reduction slots, cp.async pipeline
   float* cs = reinterpret_cast<float*>(smem_raw);
   const int C = g.C;
@@ -269,9 +308,14 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
   constexpr int NSLOT = 6 * NCP + 1;                     // g[2], z1[2], y[2] vectors + one slot for both logit pairs
   constexpr int SLOT_STRIDE = AT * 16;
   uint8_t* pipe = smem_raw + ((sizeof(float) * ((NCONST + 6) * C + 2) + 15) & ~(size_t)15) + threadIdx.x * 16;
-  if (MODE == 0)
+  if (MODE == 0 || XS)
     for (int i = threadIdx.x; i < 6 * C + 2; i += AT) red[i] = 0.f;
-  stage_consts(cs, C, mean, invstd, gamma, beta, watt, MODE == 1 ? sums : nullptr, 1.0 / (double)g.M, training);
+  stage_consts(cs, C, mean, invstd, gamma, beta, watt, MODE == 1 ? sums : nullptr, 1.0 / (double)g.M, training,
+               XS ? w1 : nullptr);
+  // XS apply pass: dW1[c][k] partial sums of this thread's 8 channels
+  float a_w10[8], a_w11[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a_w10[e] = a_w11[e] = 0.f;
   const int lane = threadIdx.x & 31;
   const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
   // MODE 0 accumulators
@@ -295,13 +339,14 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
       const int64_t m0 = 2 * pi;
       const int64_t yr0 = yrow(g, m0);
       const T* gp = gout + (m0 << cs_) + coff;
-      const T* zp = z1 + (m0 << cs_) + coff;
+      const T* zp = XS ? z1 : z1 + (m0 << cs_) + coff;
       const T* yp = y + (yr0 << cs_) + coff;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, gp + ((int64_t)q << cs_));
-        cp_vec8<T>(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, zp + ((int64_t)q << cs_));
+        if (!XS) cp_vec8<T>(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, zp + ((int64_t)q << cs_));
       }
+      if (XS) cp_xs<T>(st + (2 * NCP) * SLOT_STRIDE, z1 + 2 * m0, 2);      // rows m0, m0+1 of the 2-channel input
       cp_vec8<T>(st + (4 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp);
       if (y_full) cp_vec8<T>(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp + ((int64_t)1 << cs_));
       cp16(st + (6 * NCP) * SLOT_STRIDE, logits + 2 * m0);      // logits of rows m0 and m0+1 (16 bytes)
@@ -325,11 +370,23 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
     const int64_t yr0 = yrow(g, m0);
     float gv[2][8], xv[2][8], yv[2][8];
     float2 lg[2];
+    float xs0[2] = {0.f, 0.f}, xs1[2] = {0.f, 0.f};
     if (live) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         ld_vec8(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, gv[q]);
-        ld_vec8(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, xv[q]);
+        if (!XS) ld_vec8(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, xv[q]);
+      }
+      if (XS) {
+        float wa[8], wb[8];
+        ldc(cs, K_W10, C, cg, wa);
+        ldc(cs, K_W11, C, cg, wb);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          ld_xs(st + (2 * NCP) * SLOT_STRIDE, (const T*)nullptr, q, xs0[q], xs1[q]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xv[q][e] = fmaf(wa[e], xs0[q], wb[e] * xs1[q]);      // z1 = W1 x
+        }
       }
       ld_vec8(st + (4 * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[0]);
       if (y_full) ld_vec8(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[1]);
@@ -428,11 +485,41 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
 #pragma unroll
           for (int e = 0; e < 8; ++e) yv[q][e] = gv[q][e] * s1[q] + wy0[e] * dl0[q] + wy1[e] * dl1[q];   // dyv
       }
+      if (XS) {
+        // conv1 backward in place: dx[k] = sum_c W1[c][k] dz1[c] (row-wise), dW1[c][k] += dz1[c] x[k]
+        float wa[8], wb[8];
+        ldc(cs, K_W10, C, cg, wa);
+        ldc(cs, K_W11, C, cg, wb);
+        float p[2][2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            p0 = fmaf(wa[e], xp[q][e], p0);
+            p1 = fmaf(wb[e], xp[q][e], p1);
+            a_w10[e] = fmaf(xp[q][e], xs0[q], a_w10[e]);
+            a_w11[e] = fmaf(xp[q][e], xs1[q], a_w11[e]);
+          }
+          for (int o = g.tpr >> 1; o > 0; o >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+          }
+          p[q][0] = p0;
+          p[q][1] = p1;
+        }
+        if (live && cg == 0) {
+          T* xo = dz1 + 2 * m0;                       // dx rows m0, m0+1 of the 2-channel input
+          st_f(xo, p[0][0]); st_f(xo + 1, p[0][1]); st_f(xo + 2, p[1][0]); st_f(xo + 3, p[1][1]);
+        }
+      }
       if (live) {
         T* zo = dz1 + (m0 << cs_) + coff;
         T* yo = dy + (yr0 << cs_) + coff;
-        st8(zo, xp[0]);
-        st8(zo + ((int64_t)1 << cs_), xp[1]);
+        if (!XS) {
+          st8(zo, xp[0]);
+          st8(zo + ((int64_t)1 << cs_), xp[1]);
+        }
         if (y_full) {
           st8(yo, yv[0]);
           st8(yo + ((int64_t)1 << cs_), yv[1]);
@@ -442,6 +529,19 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
           st8(yo, yv[0]);
         }
       }
+    }
+  }
+  if (MODE == 1 && XS) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      atomicAdd(&red[c], a_w10[e]);
+      atomicAdd(&red[C + c], a_w11[e]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += AT) {
+      atomicAdd(dw1 + 2 * i, (double)red[i]);
+      atomicAdd(dw1 + 2 * i + 1, (double)red[C + i]);
     }
   }
   if (MODE == 0) {
@@ -505,14 +605,18 @@ extern "C" int clskd_abf_mid_supported(int B, int T, int F, int Fy, int C) {
   return abf_unsupported(B, T, F, Fy, C, nullptr, nullptr, nullptr) == nullptr ? 1 : 0;
 }
 
-extern "C" int clskd_abf_mid_fwd(const void* z1, const void* y, int dtype, int B, int T, int F, int Fy, int C,
-                                 const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                 const float* watt, const float* batt, void* xb, float* logits, void* stream) {
-  CLSKD_CHECK_ARG(z1 && y && mean && invstd && watt && xb && logits, "clskd_abf_mid_fwd: null pointer");
-  if (const char* why = abf_unsupported(B, T, F, Fy, C, z1, y, xb)) {
-    set_error("clskd_abf_mid_fwd: unsupported: %s", why);
+// shared launchers: xs == false: `z1` is the stored conv1 output [M, C]; xs == true: `z1` is the 2-channel
+// conv1 INPUT [M, 2] and w1 its weight [C][2]
+static int abf_fwd_launch(const char* who, bool xs, const void* z1, const void* y, int dtype, int B, int T, int F,
+                          int Fy, int C, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, const float* watt, const float* batt, const float* w1, void* xb,
+                          float* logits, void* stream) {
+  CLSKD_CHECK_ARG(z1 && y && mean && invstd && watt && xb && logits && (!xs || w1), "%s: null pointer", who);
+  if (const char* why = abf_unsupported(B, T, F, Fy, C, xs ? y : z1, y, xb)) {
+    set_error("%s: unsupported: %s", who, why);
     return CLSKD_ERR_UNSUPPORTED;
   }
+  CLSKD_CHECK_ARG(!xs || ((uintptr_t)z1 % 16) == 0, "%s: x must be 16-byte aligned", who);
   AbfGeom g;
   g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
   g.cshift = ilog2(C); g.yshift = Fy == F ? 0 : 1;
@@ -523,32 +627,39 @@ extern "C" int clskd_abf_mid_fwd(const void* z1, const void* y, int dtype, int B
   const size_t es = dtype == CLSKD_F32 ? 4 : 2;
   const size_t cbytes = (sizeof(float) * NCONST * (size_t)C + 15) & ~(size_t)15;
   const size_t sh = cbytes + (size_t)PD * (4 * (es / 2)) * AT * 16;
-  if (dtype == CLSKD_F32) {
-    static bool a0 = false;
-    if (!a0) { cudaFuncSetAttribute(abf_mid_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); a0 = true; }
-    abf_mid_fwd_kernel<float><<<grid, AT, sh, st>>>((const float*)z1, (const float*)y, g, mean, invstd, gamma, beta, watt,
-                                                    batt, (float*)xb, logits);
-  } else {
-    static bool a1 = false;
-    if (!a1) { cudaFuncSetAttribute(abf_mid_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); a1 = true; }
-    abf_mid_fwd_kernel<__nv_bfloat16><<<grid, AT, sh, st>>>((const __nv_bfloat16*)z1, (const __nv_bfloat16*)y, g, mean,
-                                                            invstd, gamma, beta, watt, batt, (__nv_bfloat16*)xb, logits);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(abf_mid_fwd_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(abf_mid_fwd_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(abf_mid_fwd_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(abf_mid_fwd_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
   }
-  CLSKD_CHECK_LAUNCH("clskd_abf_mid_fwd");
+  if (xs)
+    CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_fwd_kernel<TT, true><<<grid, AT, sh, st>>>(
+                                        (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt, batt, w1,
+                                        (TT*)xb, logits)));
+  else
+    CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_fwd_kernel<TT, false><<<grid, AT, sh, st>>>(
+                                        (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt, batt, nullptr,
+                                        (TT*)xb, logits)));
+  CLSKD_CHECK_LAUNCH(who);
   return CLSKD_OK;
 }
 
-extern "C" int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y, int dtype, int B, int T, int F, int Fy,
-                                 int C, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                 const float* watt, const float* logits, int training, double* sums, double* dwatt,
-                                 double* dbatt, void* dz1, void* dy, void* stream) {
-  CLSKD_CHECK_ARG(gout && z1 && y && mean && invstd && watt && logits && sums && dwatt && dbatt && dz1 && dy,
-                  "clskd_abf_mid_bwd: null pointer");
-  if (const char* why = abf_unsupported(B, T, F, Fy, C, gout, z1, dz1)) {
-    set_error("clskd_abf_mid_bwd: unsupported: %s", why);
+static int abf_bwd_launch(const char* who, bool xs, const void* gout, const void* z1, const void* y, int dtype, int B,
+                          int T, int F, int Fy, int C, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, const float* watt, const float* logits, int training, double* sums,
+                          double* dwatt, double* dbatt, void* dz1, void* dy, const float* w1, double* dw1,
+                          void* stream) {
+  CLSKD_CHECK_ARG(gout && z1 && y && mean && invstd && watt && logits && sums && dwatt && dbatt && dz1 && dy &&
+                      (!xs || (w1 && dw1)), "%s: null pointer", who);
+  if (const char* why = abf_unsupported(B, T, F, Fy, C, gout, xs ? gout : z1, xs ? nullptr : dz1)) {
+    set_error("%s: unsupported: %s", who, why);
     return CLSKD_ERR_UNSUPPORTED;
   }
-  CLSKD_CHECK_ARG(((uintptr_t)y % 16) == 0 && ((uintptr_t)dy % 16) == 0, "clskd_abf_mid_bwd: y / dy must be 16-byte aligned");
+  CLSKD_CHECK_ARG(((uintptr_t)y % 16) == 0 && ((uintptr_t)dy % 16) == 0, "%s: y / dy must be 16-byte aligned", who);
+  CLSKD_CHECK_ARG(!xs || (((uintptr_t)z1 % 16) == 0 && ((uintptr_t)dz1 % 16) == 0), "%s: x / dx must be 16-byte aligned", who);
   AbfGeom g;
   g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
   g.cshift = ilog2(C); g.yshift = Fy == F ? 0 : 1;
@@ -556,7 +667,8 @@ extern "C" int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y
   cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(dwatt, 0, sizeof(double) * 4 * C, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(dbatt, 0, sizeof(double) * 2, st);
-  if (e != cudaSuccess) { set_error("clskd_abf_mid_bwd: memset: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+  if (e == cudaSuccess && xs) e = cudaMemsetAsync(dw1, 0, sizeof(double) * 2 * C, st);
+  if (e != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
   if (g.M == 0) return CLSKD_OK;
   const int64_t pairs = g.M / 2;
   const int pairs_per_warp = 32 / g.tpr;
@@ -566,19 +678,71 @@ extern "C" int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y
   const size_t sh = cbytes + (size_t)PD * (6 * (es / 2) + 1) * AT * 16;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(abf_mid_bwd_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(abf_mid_bwd_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(abf_mid_bwd_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(abf_mid_bwd_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+#define ABF_ATTR(TT, MD, XX) cudaFuncSetAttribute(abf_mid_bwd_kernel<TT, MD, XX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+    ABF_ATTR(float, 0, false); ABF_ATTR(float, 1, false); ABF_ATTR(__nv_bfloat16, 0, false); ABF_ATTR(__nv_bfloat16, 1, false);
+    ABF_ATTR(float, 0, true); ABF_ATTR(float, 1, true); ABF_ATTR(__nv_bfloat16, 0, true); ABF_ATTR(__nv_bfloat16, 1, true);
+#undef ABF_ATTR
     attr = true;
   }
-  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 0><<<grid, AT, sh, st>>>(
-                                      (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt,
-                                      logits, sums, dwatt, dbatt, training, nullptr, nullptr)));
-  CLSKD_CHECK_LAUNCH("clskd_abf_mid_bwd(stats)");
-  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 1><<<grid, AT, sh, st>>>(
-                                      (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt,
-                                      logits, sums, dwatt, dbatt, training, (TT*)dz1, (TT*)dy)));
-  CLSKD_CHECK_LAUNCH("clskd_abf_mid_bwd(apply)");
+#define ABF_BWD(MD, XX, DZ, DY)                                                                                     \
+  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, MD, XX><<<grid, AT, sh, st>>>(                            \
+                                      (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta,   \
+                                      watt, logits, sums, dwatt, dbatt, training, (TT*)(DZ), (TT*)(DY), w1, dw1)))
+  if (xs) ABF_BWD(0, true, nullptr, nullptr); else ABF_BWD(0, false, nullptr, nullptr);
+  CLSKD_CHECK_LAUNCH(who);
+  if (xs) ABF_BWD(1, true, dz1, dy); else ABF_BWD(1, false, dz1, dy);
+#undef ABF_BWD
+  CLSKD_CHECK_LAUNCH(who);
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_abf_mid_fwd(const void* z1, const void* y, int dtype, int B, int T, int F, int Fy, int C,
+                                 const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                 const float* watt, const float* batt, void* xb, float* logits, void* stream) {
+  return abf_fwd_launch("clskd_abf_mid_fwd", false, z1, y, dtype, B, T, F, Fy, C, mean, invstd, gamma, beta, watt, batt,
+                        nullptr, xb, logits, stream);
+}
+
+extern "C" int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y, int dtype, int B, int T, int F, int Fy,
+                                 int C, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                 const float* watt, const float* logits, int training, double* sums, double* dwatt,
+                                 double* dbatt, void* dz1, void* dy, void* stream) {
+  return abf_bwd_launch("clskd_abf_mid_bwd", false, gout, z1, y, dtype, B, T, F, Fy, C, mean, invstd, gamma, beta, watt,
+                        logits, training, sums, dwatt, dbatt, dz1, dy, nullptr, nullptr, stream);
+}
+
+extern "C" int clskd_abf_mid_xs_fwd(const void* x, const float* w1, const void* y, int dtype, int B, int T, int F, int Fy,
+                                    int C, const float* mean, const float* invstd, const float* gamma,
+                                    const float* beta, const float* watt, const float* batt, void* xb, float* logits,
+                                    void* stream) {
+  return abf_fwd_launch("clskd_abf_mid_xs_fwd", true, x, y, dtype, B, T, F, Fy, C, mean, invstd, gamma, beta, watt, batt,
+                        w1, xb, logits, stream);
+}
+
+extern "C" int clskd_abf_mid_xs_bwd(const void* gout, const void* x, const float* w1, const void* y, int dtype, int B,
+                                    int T, int F, int Fy, int C, const float* mean, const float* invstd,
+                                    const float* gamma, const float* beta, const float* watt, const float* logits,
+                                    int training, double* sums, double* dwatt, double* dbatt, double* dw1, void* dx,
+                                    void* dy, void* stream) {
+  return abf_bwd_launch("clskd_abf_mid_xs_bwd", true, gout, x, y, dtype, B, T, F, Fy, C, mean, invstd, gamma, beta, watt,
+                        logits, training, sums, dwatt, dbatt, dx, dy, w1, dw1, stream);
+}
+
+// column sums of z = W1 x for a 2-channel x from the moments of x: sum_c = w0 S0 + w1 S1,
+// sumsq_c = w0^2 S00 + 2 w0 w1 S01 + w1^2 S11   (s5 = clskd_cbn_moments of x viewed as one complex channel)
+__global__ void rank2_colstats_kernel(const double* __restrict__ s5, const float* __restrict__ w1, int C,
+                                      double* __restrict__ sum, double* __restrict__ sumsq) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double a = w1[2 * c], b = w1[2 * c + 1];
+  sum[c] = a * s5[0] + b * s5[1];
+  sumsq[c] = a * a * s5[2] + 2. * a * b * s5[3] + b * b * s5[4];
+}
+
+extern "C" int clskd_rank2_colstats(const double* s5, const float* w1, int C, double* sum, double* sumsq,
+                                    void* stream) {
+  CLSKD_CHECK_ARG(s5 && w1 && sum && sumsq && C >= 1, "clskd_rank2_colstats: bad arguments");
+  rank2_colstats_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(s5, w1, C, sum, sumsq);
+  CLSKD_CHECK_LAUNCH("clskd_rank2_colstats");
   return CLSKD_OK;
 }

@@ -380,3 +380,49 @@ def test_fused_conv_epilogue_batch_statistics_and_folded_eval_bn(cuda_dev, kind,
     # folded: one rounding of the normalised value instead of two (conv output, then BN output)
     assert (ye - yeu).abs().max().item() < 2e-2 * se
     assert (ye - yeu).abs().mean().item() < 2e-3 * se
+
+
+@pytest.mark.parametrize("mid,F,T,B,up", [(64, 32, 21, 2, True), (128, 16, 40, 3, False)])
+def test_abf_rank2_mid_stage_vs_stored_z1_path(cuda_dev, mid, F, T, B, up):
+    """ABF level whose 1x1 conv has 2 input channels (mask-level decoder map): the kernels that recompute
+    z1 = W1 x per row (and return dx, dW1 directly) against the path that stores z1 and runs the conv's own
+    forward / data-gradient / weight-gradient launches.  Differences are bf16 roundings of z1 only."""
+    import clskd_b200
+    from clskd_b200 import framework as fw
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(mid + F)
+    torch.manual_seed(mid)
+    abf = fw.ABF(2, mid, 2, True).to(cuda_dev).train()
+    abf.conv1[1].weight.data.uniform_(0.5, 1.5)
+    abf.conv1[1].bias.data.normal_(0, 0.2)
+    abf.att_conv[0].bias.data.normal_(0, 0.2)
+    Fy = F // 2 if up else F
+    x0 = torch.randn(B, 2, F, T, generator=g)
+    y0 = torch.randn(B, mid, Fy, T, generator=g)
+    gw = torch.randn(B, mid, F, T, generator=g).to(cuda_dev)
+    clskd_b200.set_precision("bf16")
+    res = {}
+    for rank2 in (True, False):
+        ops.policy.abf_rank2 = rank2
+        for p in abf.parameters():
+            p.grad = None
+        rm = abf.conv1[1].running_mean.clone()
+        x = x0.to(cuda_dev).bfloat16().requires_grad_(True)
+        y = y0.to(cuda_dev).bfloat16().requires_grad_(True)
+        out, fused = abf(x, y, F, None, "decoder")
+        (fused.float() * gw).sum().backward()
+        res[rank2] = dict(fused=fused.detach().float().cpu(), dx=x.grad.float().cpu(), dy=y.grad.float().cpu(),
+                          dw1=abf.conv1[0].weight.grad.float().cpu().reshape(-1),
+                          dgamma=abf.conv1[1].weight.grad.float().cpu(), dbeta=abf.conv1[1].bias.grad.float().cpu(),
+                          dwatt=abf.att_conv[0].weight.grad.float().cpu().reshape(-1),
+                          rmean=abf.conv1[1].running_mean.clone().cpu())
+        abf.conv1[1].running_mean.copy_(rm)
+    ops.policy.abf_rank2 = True
+    a, b = res[True], res[False]
+    for k in ("fused", "dy", "dx"):
+        s = b[k].abs().max().item()
+        assert (a[k] - b[k]).abs().max().item() < 4e-2 * s, k
+        assert (a[k] - b[k]).abs().mean().item() < 4e-3 * s, k
+    for k in ("dw1", "dgamma", "dbeta", "dwatt", "rmean"):
+        s = max(b[k].abs().max().item(), 1e-6)
+        assert (a[k] - b[k]).abs().max().item() < 2e-2 * s, k

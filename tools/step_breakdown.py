@@ -89,6 +89,12 @@ def main():
             shp = "B=%d T=%d F=%d Fy=%d C=%d" % tuple(args[3:8])
         elif name in ("clskd_abf_mid_bwd",):
             shp = "B=%d T=%d F=%d Fy=%d C=%d" % tuple(args[4:9])
+        elif name == "clskd_abf_mid_xs_fwd":
+            shp = "B=%d T=%d F=%d Fy=%d C=%d" % tuple(args[4:9])
+        elif name == "clskd_abf_mid_xs_bwd":
+            shp = "B=%d T=%d F=%d Fy=%d C=%d" % tuple(args[5:10])
+        elif name == "clskd_cbn_moments":
+            shp = "M=%d Cc=%d" % (args[2], args[3])
         elif name in ("clskd_lstm_fwd",):
             shp = "T=%d R=%d H=%d" % (args[2], args[3], args[5])
         if name == "clskd_strided_copy4d":
