@@ -210,13 +210,24 @@ def dccrn_forward(sd, x, masking_mode='E', win_len=400, hop=100, fft_len=512, tr
     o = out.permute(3, 0, 1, 2)
     r = o[:, :, :C // 2].reshape(T, B, C // 2 * D)
     i_ = o[:, :, C // 2:].reshape(T, B, C // 2 * D)
-    n_rnn = len([k for k in sd if k.startswith('enhance.') and k.endswith('.real_lstm.weight_ih_l0')])
-    for l in range(n_rnn):                                                        # :186
-        r, i_ = complex_lstm(r, i_, sd, 'enhance.%d.' % l, ('enhance.%d.r_trans.weight' % l) in sd)
-    lstm_tap = [r, i_]
-    r = r.reshape(T, B, C // 2, D)
-    i_ = i_.reshape(T, B, C // 2, D)
-    out = torch.cat([r, i_], 2).permute(1, 2, 3, 0)                               # :188-199
+    if 'enhance.weight_ih_l0' in sd:        # use_clstm=False: 2-layer nn.LSTM + Linear "tranform" (:100-110, :193-199)
+        y = o.reshape(T, B, C * D)
+        l = 0
+        while ('enhance.weight_ih_l%d' % l) in sd:
+            y = _lstm(y, sd['enhance.weight_ih_l%d' % l], sd['enhance.weight_hh_l%d' % l],
+                      sd['enhance.bias_ih_l%d' % l], sd['enhance.bias_hh_l%d' % l])
+            l += 1
+        lstm_tap = [y]
+        y = F.linear(y, sd['tranform.weight'], sd['tranform.bias'])
+        out = y.reshape(T, B, C, D).permute(1, 2, 3, 0)
+    else:
+        n_rnn = len([k for k in sd if k.startswith('enhance.') and k.endswith('.real_lstm.weight_ih_l0')])
+        for l in range(n_rnn):                                                    # :186
+            r, i_ = complex_lstm(r, i_, sd, 'enhance.%d.' % l, ('enhance.%d.r_trans.weight' % l) in sd)
+        lstm_tap = [r, i_]
+        r = r.reshape(T, B, C // 2, D)
+        i_ = i_.reshape(T, B, C // 2, D)
+        out = torch.cat([r, i_], 2).permute(1, 2, 3, 0)                           # :188-199
     dec = []
     for idx in range(n_layers):                                                   # :201-205
         pre = 'decoder.%d.' % idx

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import config as cfg
 from . import ops
-from .clstm import NavieComplexLSTM
+from .clstm import LSTM, NavieComplexLSTM, _LinearParams
 from .ops import MaskFn, dense, strided_copy_into, to_logical, to_phys
 from .tools_for_loss import mse, sdr, si_sdr, si_snr
 from .tools_for_model import (BatchNorm2d, ComplexBatchNorm, ComplexConv2d, ComplexConvTranspose2d, ConvBNAct,
@@ -73,6 +73,26 @@ class _FromLstmFn(torch.autograd.Function):
         return outs[0], outs[1], None, None
 
 
+class _Cat2Fn(torch.autograd.Function):
+    """X [2, T, B, D] -> [T, B, 2D] (part 0 features, then part 1 features)."""
+
+    @staticmethod
+    def forward(ctx, X):
+        _, T, B, D = X.shape
+        out = torch.empty((T, B, 2 * D), dtype=X.dtype, device=X.device)
+        strided_copy_into(X[0], out[..., :D])
+        strided_copy_into(X[1], out[..., D:])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        D = g.shape[-1] // 2
+        dX = torch.empty((2,) + tuple(g.shape[:2]) + (D,), dtype=g.dtype, device=g.device)
+        strided_copy_into(g[..., :D], dX[0])
+        strided_copy_into(g[..., D:], dX[1])
+        return dX
+
+
 class _TrimFirstFn(torch.autograd.Function):
     """physical [B,T+1,F,C] -> view [B,T,F,C] without column 0 (DCCRN.py:205)."""
 
@@ -105,9 +125,6 @@ class DCCRN(nn.Module):
         self.kernel_num = [2] + list(kernel_num)
         self.masking_mode = masking_mode
         self.use_clstm = use_clstm
-        if not use_clstm:
-            raise NotImplementedError("DCCRN: only the complex-LSTM bottleneck (use_clstm=True, 'DCCRN-CL') is "
-                                      "implemented on this path")
         self.fix = True
         self.stft = ConvSTFT(win_len, win_inc, fft_len, win_type, 'complex', fix=True)
         self.istft = ConviSTFT(win_len, win_inc, fft_len, win_type, 'complex', fix=True)
@@ -123,13 +140,17 @@ class DCCRN(nn.Module):
                 ComplexConv2d(kn[idx], kn[idx + 1], kernel_size=(kernel_size, 2), stride=(2, 1), padding=(2, 1)),
                 norm(kn[idx + 1]), PReLU()))
         hidden_dim = fft_len // (2 ** len(kn))
-        rnns = []
-        for idx in range(rnn_layers):
-            rnns.append(NavieComplexLSTM(
-                input_size=hidden_dim * kn[-1] if idx == 0 else rnn_units, hidden_size=rnn_units,
-                bidirectional=False, batch_first=False,
-                projection_dim=hidden_dim * kn[-1] if idx == rnn_layers - 1 else None))
-        self.enhance = nn.Sequential(*rnns)
+        if use_clstm:
+            rnns = []
+            for idx in range(rnn_layers):
+                rnns.append(NavieComplexLSTM(
+                    input_size=hidden_dim * kn[-1] if idx == 0 else rnn_units, hidden_size=rnn_units,
+                    bidirectional=False, batch_first=False,
+                    projection_dim=hidden_dim * kn[-1] if idx == rnn_layers - 1 else None))
+            self.enhance = nn.Sequential(*rnns)
+        else:       # plain 2-layer nn.LSTM + Linear "tranform" (DCCRN.py:100-110; the typo is the reference's key)
+            self.enhance = LSTM(input_size=hidden_dim * kn[-1], hidden_size=rnn_units, num_layers=2)
+            self.tranform = _LinearParams(rnn_units, hidden_dim * kn[-1])
         for idx in range(len(kn) - 1, 0, -1):
             conv = ComplexConvTranspose2d(kn[idx] * 2, kn[idx - 1], kernel_size=(kernel_size, 2), stride=(2, 1),
                                           padding=(2, 0), output_padding=(1, 0))
@@ -152,9 +173,18 @@ class DCCRN(nn.Module):
         # ---- complex LSTM bottleneck
         x = to_phys(out, need_dense=True)
         F = x.shape[2]
-        X = _ToLstmFn.apply(x, act)
-        r, i = self.enhance([X[0], X[1]])
-        out = to_logical(_FromLstmFn.apply(r, i, F, act))
+        if self.use_clstm:
+            X = _ToLstmFn.apply(x, act)
+            r, i = self.enhance([X[0], X[1]])
+            out = to_logical(_FromLstmFn.apply(r, i, F, act))
+        else:       # DCCRN.py:193-199: [T, B, C*D] -> LSTM -> Linear -> [T, B, C, D]
+            Bb, Tt, _, C = x.shape
+            X = _ToLstmFn.apply(x, act)                               # [2, T, B, Cc*F]: feature c*F+f per half
+            seq = _Cat2Fn.apply(X)                                    # [T, B, C*F] (real-half features, then imag-half)
+            y, _ = self.enhance(seq)
+            y = self.tranform(y)                                      # [T, B, C*F] fp32
+            half = y.shape[-1] // 2
+            out = to_logical(_FromLstmFn.apply(y[..., :half], y[..., half:], F, act))
         # ---- decoder: skip connections are the second K segment of each transposed conv
         for idx in range(len(self.decoder)):
             out = self.decoder[idx](out, encoder_out[-1 - idx])

@@ -310,3 +310,128 @@ class _Project2Fn(torch.autograd.Function):
 def _project2(mod, Y):
     return _Project2Fn.apply(Y, mod.r_trans.weight, mod.r_trans.bias, mod.i_trans.weight, mod.i_trans.bias,
                              mod.r_trans.plan(), mod.i_trans.plan())
+
+
+# ---------------------------------------------------------------------------------------------
+# plain (real) LSTM bottleneck of DCCRN(use_clstm=False)  (reference: DCCRN.py:100-110, 193-199)
+# ---------------------------------------------------------------------------------------------
+
+class _LstmPlans:
+    """Static tables of one real LSTM layer (one weight set, one 'part')."""
+
+    def __init__(self, D, H, device):
+        G = 4 * H
+        self.D, self.H = D, H
+        self.ih = ConvPlan("conv", _codes((G, D), 0).T[None, None], 1, 0, 0, D, 0, None, G * D, 0, device)
+        hr = _codes((G, H), 0)
+        self.whh_t = torch.from_numpy(ops._pairs(hr.T.reshape(-1))).to(device)     # [H][4H]
+        self.whh = torch.from_numpy(ops._pairs(hr.reshape(-1))).to(device)         # [4H][H]
+        j = np.arange(G)
+        self.bias = torch.from_numpy(np.stack([j * 4, j * 4 + 1], 1).astype(np.int32)).to(device)
+        t = np.full((G * H, 2), -1, dtype=np.int32)
+        gg, kk = np.meshgrid(np.arange(G), np.arange(H), indexing="ij")
+        t[:, 0] = ((kk * G + gg) * 2).reshape(-1)
+        self.hh_unpack = torch.from_numpy(t).to(device)
+        self.cache = {}
+
+
+class LSTMLayerFn(torch.autograd.Function):
+    """One unidirectional nn.LSTM layer, zero initial state: X [T, B, D] -> Y [T, B, H] (fp32).
+    Same kernels as the complex LSTM with one weight set: batched input projection (tapconv / split-bf16
+    tcgen05), persistent recurrence (clskd_lstm_fwd), BPTT (clskd_lstm_bwd), tapconv weight gradients."""
+
+    @staticmethod
+    def forward(ctx, plans: _LstmPlans, X, w_ih, w_hh, b_ih, b_hh, w_bf16):
+        T, B, D = X.shape
+        H, G = plans.H, 4 * plans.H
+        dev = X.device
+        st = ops._stream()
+        f = ops._f32c
+        w_ih, w_hh, b_ih, b_hh = f(w_ih), f(w_hh), f(b_ih), f(b_hh)
+        bias = torch.empty(G, dtype=torch.float32, device=dev)
+        call("clskd_pack_gather", b_ih.data_ptr(), b_hh.data_ptr(), plans.bias.data_ptr(), G, bias.data_ptr(), 0, st)
+        pre = torch.empty((T, B, G), dtype=torch.float32, device=dev)
+        run_tapconv(X.view(1, T, B, D), None, D, 0, 1, T, B, T, B, plans.ih.fwd[0], w_ih, None, bias,
+                    pre.view(1, T, B, G))
+        whh_t = ops.packed_weights(plans.cache, "whh_t", lambda: plans.whh_t, w_hh, None, torch.float32)
+        train = any(ctx.needs_input_grad)
+        h = torch.empty((T, B, H), dtype=torch.float32, device=dev)
+        gates = torch.empty((T, B, G), dtype=torch.float32, device=dev) if train else None
+        c = torch.empty((T, B, H), dtype=torch.float32, device=dev) if train else None
+        call("clskd_lstm_fwd", pre.data_ptr(), whh_t.data_ptr(), T, B, B, H, 1, T * B * G, B * G, G, 0, H * G,
+             1 if w_bf16 else 0, h.data_ptr(), ops._ptr(gates), ops._ptr(c), st)
+        ctx.plans = plans
+        ctx.save_for_backward(X, w_ih, w_hh, h, gates, c)
+        return h
+
+    @staticmethod
+    def backward(ctx, dY):
+        plans = ctx.plans
+        X, w_ih, w_hh, h, gates, c = ctx.saved_tensors
+        if gates is None:
+            raise RuntimeError("LSTM: backward requested but the forward did not save its gates")
+        T, B, D = X.shape
+        H, G = plans.H, 4 * plans.H
+        dev = dY.device
+        st = ops._stream()
+        dh = dense(dY, torch.float32)
+        whh = pack_weights(plans.whh, w_hh, None, torch.float32)
+        dpre = torch.empty((T, B, G), dtype=torch.float32, device=dev)
+        call("clskd_lstm_bwd", dh.data_ptr(), whh.data_ptr(), gates.data_ptr(), c.data_ptr(), T, B, B, H, 1,
+             G * H, T * B * G, B * G, G, 0, dpre.data_ptr(), st)
+        dX = None
+        if ctx.needs_input_grad[1]:
+            dX = torch.empty(X.shape, dtype=X.dtype, device=dev)
+            run_tapconv(dpre.view(1, T, B, G), None, G, 0, 1, T, B, T, B, plans.ih.dgrad[0][0], w_ih, None, None,
+                        dX.view(1, T, B, D))
+        dpre_w, X_w, h_w = dpre, X, h
+        if ops.policy.use_umma and D % 16 == 0 and H % 16 == 0 and T * B >= 4096:
+            dpre_w, X_w, h_w = dense(dpre, torch.bfloat16), dense(X, torch.bfloat16), dense(h, torch.bfloat16)
+        dwcat = torch.empty(plans.ih.wcat, dtype=torch.float32, device=dev)
+        run_wgrad(X_w.view(1, T, B, D), None, D, 0, 1, T, B, T, B, plans.ih.fwd[0], dpre_w.view(1, T, B, G), dwcat)
+        dw_ih = unpack_grads(dwcat, plans.ih.unpack_a, G * D).view(G, D)
+        # dW_hh[g][k] = sum_{t>=1,b} dpre[t,b,g] * h[t-1,b,k]
+        l = Launch(dt=[-1], df=[0], K=H, N=G)
+        tmp = torch.empty(H * G, dtype=torch.float32, device=dev)
+        run_wgrad(h_w.view(1, T, B, H), None, H, 0, 1, T, B, T, B, l, dpre_w.view(1, T, B, G), tmp)
+        dw_hh = unpack_grads(tmp, plans.hh_unpack, G * H).view(G, H)
+        sb, _ = colstats(dpre.view(-1, G))
+        db = f64_to_f32(sb)
+        return None, dX, dw_ih, dw_hh, db, db, None
+
+
+class LSTM(nn.Module):
+    """nn.LSTM(input_size, hidden_size, num_layers, bidirectional=False, batch_first=False) with the same
+    parameter names (`weight_ih_l{k}`, `weight_hh_l{k}`, `bias_ih_l{k}`, `bias_hh_l{k}`); forward(x [T,B,D])
+    returns (output [T,B,H], (h_n, c_n)) with c_n = None (the path never consumes it)."""
+
+    def __init__(self, input_size, hidden_size, num_layers=1, dropout=0.0, bidirectional=False, batch_first=False):
+        super().__init__()
+        if bidirectional or batch_first or dropout:
+            raise NotImplementedError("LSTM: bidirectional / batch_first / dropout are not implemented")
+        self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
+        k = 1.0 / math.sqrt(hidden_size)
+        for l in range(num_layers):
+            d = input_size if l == 0 else hidden_size
+            setattr(self, "weight_ih_l%d" % l, nn.Parameter(torch.empty(4 * hidden_size, d).uniform_(-k, k)))
+            setattr(self, "weight_hh_l%d" % l, nn.Parameter(torch.empty(4 * hidden_size, hidden_size).uniform_(-k, k)))
+            setattr(self, "bias_ih_l%d" % l, nn.Parameter(torch.empty(4 * hidden_size).uniform_(-k, k)))
+            setattr(self, "bias_hh_l%d" % l, nn.Parameter(torch.empty(4 * hidden_size).uniform_(-k, k)))
+        self._plans = {}
+
+    def flatten_parameters(self):
+        pass
+
+    def forward(self, x, hx=None):
+        if hx is not None:
+            raise NotImplementedError("LSTM: only the zero initial state is implemented")
+        ops._require_cuda(x)
+        y = dense(x, ops.policy.act_dtype)
+        for l in range(self.num_layers):
+            key = (l, y.device)
+            if key not in self._plans:
+                self._plans[key] = _LstmPlans(y.shape[-1], self.hidden_size, y.device)
+            y = LSTMLayerFn.apply(self._plans[key], y, getattr(self, "weight_ih_l%d" % l),
+                                  getattr(self, "weight_hh_l%d" % l), getattr(self, "bias_ih_l%d" % l),
+                                  getattr(self, "bias_hh_l%d" % l), ops.policy.name == "bf16")
+        return y, (y[-1:], None)

@@ -253,3 +253,19 @@ def test_use_cbn_model_oracle_against_live_reference():
                 out = D.dccrn_forward(sd, x, training=training)
         for a, b in zip(out, ref):
             assert (a - b).abs().max().item() < 2e-5, training
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_plain_lstm_model_oracle_against_live_reference():
+    """DCCRN(use_clstm=False) (DCCRN.py:100-110, 193-199): oracle forward == live reference"""
+    mods = ref_shim.load()
+    kn, ru = [4, 8, 8, 16, 16, 16], 24
+    torch.manual_seed(33)
+    m = mods["DCCRN"].DCCRN(rnn_units=ru, masking_mode="E", use_clstm=False, kernel_num=kn).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = 0.1 * torch.randn(2, 2400, generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        ref = m(x)
+        out = D.dccrn_forward(sd, x)
+    for a, b in zip(out, ref):
+        assert (a - b).abs().max().item() < 1e-5

@@ -620,6 +620,40 @@ def test_dccrn_with_complex_batch_norm_vs_oracle(dev, training):
         assert (got - want).abs().max().item() < 2e-3 * max(want.abs().max().item(), 1e-6) + 1e-6, name
 
 
+@pytest.mark.parametrize("training", [False, True])
+def test_dccrn_plain_lstm_bottleneck_vs_oracle(dev, training):
+    """DCCRN(use_clstm=False) - the reference constructor's default: 2-layer nn.LSTM + Linear `tranform`
+    (DCCRN.py:100-110, 193-199): state_dict keys, enhanced waveform and SI-SNR gradients vs the oracle"""
+    import clskd_b200
+    from oracle import dccrn_oracle as D
+    from oracle import losses_oracle as LO
+    torch.manual_seed(8)
+    m = clskd_b200.DCCRN(rnn_units=24, use_clstm=False, kernel_num=[4, 8, 8, 16, 16, 16])
+    keys = set(m.state_dict())
+    for k in ("enhance.weight_ih_l0", "enhance.weight_hh_l1", "enhance.bias_ih_l1", "tranform.weight", "tranform.bias"):
+        assert k in keys, k
+    assert tuple(m.enhance.weight_ih_l0.shape) == (96, 64) and tuple(m.tranform.weight.shape) == (64, 24)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    live = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k
+                                                   and not k.startswith(("stft.", "istft."))) else v)
+            for k, v in sd.items()}
+    gen = torch.Generator().manual_seed(2)
+    x, y = 0.1 * torch.randn(3, 2400, generator=gen), 0.1 * torch.randn(3, 2400, generator=gen)
+    ref_wav = D.dccrn_forward(live, x, training=training)[-1]
+    ref_loss = -LO.si_snr(ref_wav, y)
+    ref_loss.backward()
+    m = m.to(dev).train(training)
+    wav = m(x.to(dev))[-1]
+    loss = m.loss(wav, y.to(dev), loss_mode='SI-SNR')
+    loss.backward()
+    assert (wav.detach().cpu() - ref_wav.detach()).abs().max().item() < 2e-5
+    assert rel_err(loss, ref_loss) < 1e-4
+    for name in ("enhance.weight_ih_l0", "enhance.weight_hh_l0", "enhance.bias_hh_l1", "enhance.weight_ih_l1",
+                 "tranform.weight", "tranform.bias", "encoder.1.0.real_conv.weight", "decoder.0.0.imag_conv.weight"):
+        got, want = dict(m.named_parameters())[name].grad.cpu(), live[name].grad
+        assert (got - want).abs().max().item() < 2e-3 * max(want.abs().max().item(), 1e-6) + 1e-6, name
+
+
 def test_dccrn_with_complex_batch_norm_runs(dev):
     """use_cbn=True model variant (DCCRN.py:80-81): forward under no_grad produces the reference shapes"""
     import clskd_b200

@@ -45,15 +45,19 @@ def check_summary(t, ref, rtol=1e-4, atol=1e-5, what=""):
         "%s: sum %.6e vs %.6e" % (what, float(t.sum()), ref["sum"])
 
 
+def _f(v):
+    return float(v.detach()) if torch.is_tensor(v) else float(v)
+
+
 def rel_err(a, b):
-    a, b = float(a), float(b)
+    a, b = _f(a), _f(b)
     return abs(a - b) / max(abs(b), 1e-12)
 
 
 
 def close(a, b, rtol=1e-5, atol=1e-5):
     """scalar comparison for values that may sit near zero (dB-valued objectives)"""
-    a, b = float(a), float(b)
+    a, b = _f(a), _f(b)
     return abs(a - b) <= atol + rtol * abs(b)
 
 
