@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap-abf", type=int, default=None, help="1/0: encoder-side ABF chain on a second stream")
     ap.add_argument("--dump-launches", default=None, help="write per-launch shapes/times of the profiled kernel here")
     ap.add_argument("--profile-kernel", default="auto",
                     help="C-ABI entry point timed with CUDA events for the roofline object")
@@ -291,6 +292,8 @@ def run_ours(args):
     torch.manual_seed(3)                       # identical ABF init on every rank
     tr = DistillTrainer(teacher, student, mode=args.mode, example_input=X[:2])
 
+    if args.overlap_abf is not None:
+        tr.step_fn.overlap_abf = bool(args.overlap_abf)
     kname = args.profile_kernel
     if kname == "auto":
         kname = "clskd_tapconv_fwd_umma" if args.precision == "bf16" else "clskd_tapconv_fwd"

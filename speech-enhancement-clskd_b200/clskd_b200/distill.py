@@ -55,7 +55,18 @@ class DistillStep(nn.Module):
         self.abf_decoder = None
         self.last_terms = {}
         self.overlap_teacher = True
+        self.overlap_abf = True
         self._side = None
+        self._side2 = None
+
+    def join_streams(self):
+        """make the current stream wait for everything queued on the side streams (the backward of a
+        branch that ran on a side stream runs there too)"""
+        if torch.cuda.is_available():
+            cur = torch.cuda.current_stream()
+            for s_ in (self._side, self._side2):
+                if s_ is not None:
+                    cur.wait_stream(s_)
 
     # ---- ABF management
     def _abfs(self, s_enc, s_dec, t_enc, t_dec):
@@ -124,6 +135,30 @@ class DistillStep(nn.Module):
                 f_enc, f_dec = s_enc, s_dec
             else:
                 abf_e, abf_d = self._abfs(s_enc, s_dec, t_enc, t_dec)
+                if X.is_cuda and self.overlap_abf and self.mode == 'clskd':
+                    # the encoder-side and decoder-side fusion chains (and their SPKD terms) are independent:
+                    # the encoder side runs on a second stream (its backward follows it there), which fills
+                    # the launch gaps and the tails of the small deep-level kernels of the other side
+                    main = torch.cuda.current_stream()
+                    if self._side2 is None:
+                        self._side2 = torch.cuda.Stream(device=X.device)
+                    self._side2.wait_stream(main)
+                    with torch.cuda.stream(self._side2):
+                        f_enc = abf_e(X)
+                        terms['encoder'] = sum(SPKDLoss(sf, tf, 'batchmean')() for sf, tf in zip(f_enc, t_enc))
+                    f_dec = abf_d(X)
+                    terms['decoder'] = sum(SPKDLoss(sf, tf, 'batchmean')() for sf, tf in zip(f_dec, t_dec))
+                    main.wait_stream(self._side2)
+                    for t in list(s_enc) + list(t_enc):
+                        t.record_stream(self._side2)
+                    terms['encoder'].record_stream(main)
+                    terms['clstm_real'] = SPKDLoss(s_re, t_re, reduction='batchmean')()
+                    terms['clstm_img'] = SPKDLoss(s_im, t_im, reduction='batchmean')()
+                    self.last_terms = terms
+                    loss = None
+                    for v in terms.values():
+                        loss = v if loss is None else loss + v
+                    return loss
                 f_enc, f_dec = abf_e(X), abf_d(X)
             if self.mode == 'reviewkd':
                 terms['encoder'] = hcl(f_enc, t_enc)
@@ -182,7 +217,6 @@ class FlatAdam:
         self.m = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
-        self._ptr_host = torch.empty(len(sizes), dtype=torch.int64, pin_memory=dev.type == 'cuda')
         self._ptr_dev = torch.empty(len(sizes), dtype=torch.int64, device=dev)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0
@@ -192,13 +226,20 @@ class FlatAdam:
             p.grad = None
 
     def pack_grads(self):
+        ptrs = []
         for i, p in enumerate(self.params):
             g = p.grad
             if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
                 g = ops.dense(g, torch.float32)
                 p.grad = g
-            self._ptr_host[i] = g.data_ptr() if g is not None else 0
-        self._ptr_dev.copy_(self._ptr_host, non_blocking=True)
+            ptrs.append(g.data_ptr() if g is not None else 0)
+        # a FRESH pinned staging block per step (the pinned caching allocator only recycles it after the async
+        # copy has run): the host may be more than a step ahead of the GPU, so one reused host buffer could be
+        # overwritten with the next step's gradient addresses before this step's copy has executed
+        host = torch.tensor(ptrs, dtype=torch.int64)
+        if self._ptr_dev.is_cuda:
+            host = host.pin_memory()
+        self._ptr_dev.copy_(host, non_blocking=True)
         call("clskd_multi_pack_f32", self._ptr_dev.data_ptr(), self.offsets.data_ptr(), len(self.params),
              self.total, self.flat_g.data_ptr(), ops._stream())
         return self.flat_g
@@ -237,6 +278,7 @@ class DistillTrainer:
         self.opt.zero_grad()
         loss = self.step_fn(X, y)
         loss.backward()
+        self.step_fn.join_streams()          # backward kernels of side-stream branches finish before the grads are packed
         g = self.opt.pack_grads()
         world = 1
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -45,6 +45,7 @@ def main():
     tr = DistillTrainer(teacher, student, mode=a.mode, example_input=X[:2])
     if a.no_overlap:
         tr.step_fn.overlap_teacher = False
+        tr.step_fn.overlap_abf = False
     for _ in range(3):
         tr.train_step(X, y)
     torch.cuda.synchronize()
