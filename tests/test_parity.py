@@ -194,12 +194,15 @@ def test_conv_block_gradients_vs_autograd(dev):
             assert torch.allclose(p.grad.cpu(), ref, rtol=2e-3, atol=2e-4 * ref.abs().max().item() + 1e-6), pre + n
 
 
-def test_complex_lstm(dev):
+@pytest.mark.parametrize("B", [3, 83])
+def test_complex_lstm(dev, B):
+    """B = 3: two batch rows per CTA; B = 83: 2*B*2 row/set pairs exceed the SM count, so the recurrence
+    kernel switches to four rows per CTA (the large-batch / inference configuration); ragged last CTA."""
     from clskd_b200.clstm import NavieComplexLSTM
     from oracle import dccrn_oracle as D
     g = torch.Generator().manual_seed(1)
     lstm = NavieComplexLSTM(input_size=24, hidden_size=16, projection_dim=24)
-    r, i = torch.randn(7, 3, 12, generator=g), torch.randn(7, 3, 12, generator=g)
+    r, i = torch.randn(7, B, 12, generator=g), torch.randn(7, B, 12, generator=g)
     sd = {"x." + k: v.clone() for k, v in lstm.state_dict().items()}
     rr, ri = D.complex_lstm(r, i, sd, "x.", True)
     lstm = lstm.to(dev)
