@@ -269,3 +269,44 @@ def test_plain_lstm_model_oracle_against_live_reference():
         out = D.dccrn_forward(sd, x)
     for a, b in zip(out, ref):
         assert (a - b).abs().max().item() < 1e-5
+
+
+# ---------------------------------------------------------------- golden fixtures of the model variants
+# (tests/golden/variants.pt, generated from the UNMODIFIED reference by tests/golden/make_golden_variants.py;
+#  these run everywhere, also where /root/reference does not exist)
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_complex_batch_norm_oracle_vs_golden(mode):
+    V = golden("variants.pt")["cbn"]
+    p = {k: v.clone() for k, v in V["state"].items()}
+    for k in ("Wrr", "Wri", "Wii", "Br", "Bi"):
+        p[k].requires_grad_(True)
+    x = V["x"].clone().requires_grad_(True)
+    upd = {}
+    y = D.complex_batch_norm(x, p, mode == "train", update=upd)
+    (y * V["gy"]).sum().backward()
+    ref = V[mode]
+    assert torch.allclose(y.detach(), ref["y"], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(x.grad, ref["dx"], atol=1e-5, rtol=1e-4)
+    for k, g in ref["grads"].items():
+        assert torch.allclose(p[k].grad, g, atol=1e-4, rtol=1e-4), k
+    if mode == "train":
+        for k, v in upd.items():
+            assert torch.allclose(v, ref["running"][k], atol=1e-6), k
+
+
+@pytest.mark.parametrize("name", ["cbn_model", "lstm_model"])
+def test_model_variants_oracle_vs_golden(name):
+    """DCCRN(use_cbn=True) and DCCRN(use_clstm=False): waveform (eval, train), -SI-SNR and gradients"""
+    from oracle import losses_oracle as LO
+    V = golden("variants.pt")[name]
+    sd = full_sd(V["sd"])
+    with torch.no_grad():
+        assert (D.dccrn_forward(sd, V["x"])[-1] - V["wav_eval"]).abs().max().item() < 2e-5
+    live = {k: (v.clone().requires_grad_(True) if k in V["grads"] else v) for k, v in sd.items()}
+    wav = D.dccrn_forward(live, V["x"], training=True)[-1]
+    assert (wav.detach() - V["wav_train"]).abs().max().item() < 2e-5
+    loss = -LO.si_snr(wav, V["y"])
+    assert rel_err(loss, V["loss_train"]) < 1e-4
+    loss.backward()
+    for k, g in V["grads"].items():
+        assert (live[k].grad - g).abs().max().item() < 2e-3 * max(g.abs().max().item(), 1e-6) + 1e-6, k

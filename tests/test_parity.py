@@ -657,6 +657,32 @@ def test_dccrn_plain_lstm_bottleneck_vs_oracle(dev, training):
         assert (got - want).abs().max().item() < 2e-3 * max(want.abs().max().item(), 1e-6) + 1e-6, name
 
 
+@pytest.mark.parametrize("name", ["cbn_model", "lstm_model"])
+def test_model_variants_golden(dev, name):
+    """product vs fixtures generated from the unmodified reference (tests/golden/variants.pt):
+    DCCRN(use_cbn=True) and DCCRN(use_clstm=False) - waveform in eval and train mode, -SI-SNR, gradients"""
+    import clskd_b200
+    V = golden("variants.pt")[name]
+    m = clskd_b200.DCCRN(masking_mode="E", kernel_num=V["kernel_num"], **V["kw"])
+    m.load_state_dict(full_sd(V["sd"]))
+    m = m.to(dev)
+    x, y = V["x"].to(dev), V["y"].to(dev)
+    m.eval()
+    with torch.no_grad():
+        assert (m(x)[-1].cpu() - V["wav_eval"]).abs().max().item() < 2e-5
+    m.load_state_dict(full_sd(V["sd"]))          # eval left the running statistics untouched; be explicit anyway
+    m.train()
+    wav = m(x)[-1]
+    assert (wav.detach().cpu() - V["wav_train"]).abs().max().item() < 2e-5
+    loss = m.loss(wav, y, loss_mode='SI-SNR')
+    assert rel_err(loss, V["loss_train"]) < 1e-4
+    loss.backward()
+    params = dict(m.named_parameters())
+    for k, g in V["grads"].items():
+        got = params[k].grad.cpu()
+        assert (got - g).abs().max().item() < 2e-3 * max(g.abs().max().item(), 1e-6) + 1e-6, k
+
+
 def test_dccrn_with_complex_batch_norm_runs(dev):
     """use_cbn=True model variant (DCCRN.py:80-81): forward under no_grad produces the reference shapes"""
     import clskd_b200
