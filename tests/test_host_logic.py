@@ -44,3 +44,27 @@ def test_no_cpu_fallback():
         clskd_b200.tools_for_loss.si_snr(torch.zeros(1, 100), torch.zeros(1, 100))
 
 
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints ONE JSON line with the
+    contract keys: same metric / unit / config as our arm, impl=reference, cpu_baseline and a zero-copy e2e."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1", "--cpu-batch", "1", "--seconds", "0.5"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "audio-s/s" and d["higher_is_better"] is True
+    assert d["metric"] == "audio-seconds/sec per CLSKD distill step" and d["value"] > 0
+    assert d["config"]["workload"].startswith("DCCRN-CL teacher") and d["config"]["per_gpu_batch"] == 64
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    for k in ("n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data"):
+        assert k in d, k
