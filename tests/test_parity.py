@@ -354,6 +354,64 @@ def test_distill_step_golden(dev, mode):
                 check_summary(ps[name].grad, gref, rtol=2e-3, atol=1e-7, what=key + " " + name)
 
 
+def test_faithful_step_matches_oracle_with_train_mode_teacher(emu):
+    """DistillStep(faithful=True): teacher BatchNorm in train mode with autograd enabled and the student
+    forward run twice, as distill.py:49-50,77,85,100 does (host logic; CPU model of the C ABI)."""
+    import clskd_b200
+    from clskd_b200.distill import DistillStep
+    from oracle import losses_oracle as LO
+    clskd_b200.set_precision("fp32")
+    dev = torch.device("cpu")
+    g, L = golden("dccrn.pt"), golden("losses.pt")
+    teacher = _build(g["teacher_cfg"], g["t_sd"], dev)
+    student = _build(g["student_cfg"], g["s_sd"], dev)
+    teacher.train()
+    student.train()
+    X, y = g["X"][:, :3200], g["y"][:, :3200]
+    step = DistillStep(teacher, student, mode="spkd_all", faithful=True)
+    rm0 = student.encoder[0][1].running_mean.clone()
+    loss = step(X, y)
+    ref, terms = LO.clskd_step_loss(full_sd(g["t_sd"]), full_sd(g["s_sd"]), X, y, mode="spkd_all",
+                                    teacher_training=True)
+    assert rel_err(loss, ref) < 1e-4
+    for k, v in terms.items():
+        assert rel_err(step.last_terms[k], v) < 1e-4, k
+    assert teacher.training and int(teacher.encoder[0][1].num_batches_tracked) == 1     # train-mode teacher BN
+    assert int(student.encoder[0][1].num_batches_tracked) == 2                           # two student forwards
+    assert not torch.equal(student.encoder[0][1].running_mean, rm0)
+    loss.backward()
+    assert student.encoder[0][0].real_conv.weight.grad is not None
+    assert all(p.grad is None for p in teacher.parameters())
+
+
+def test_fresh_abf_step_rebuilds_untrained_fusion_blocks(emu):
+    """DistillStep(fresh_abf=True): new random ABF weights on every step, never trainable
+    (distill.py:92-96: build_review_kd inside training_step); the student still receives gradients."""
+    import clskd_b200
+    from clskd_b200.distill import DistillStep
+    clskd_b200.set_precision("fp32")
+    dev = torch.device("cpu")
+    g = golden("dccrn.pt")
+    teacher = _build(g["teacher_cfg"], g["t_sd"], dev)
+    student = _build(g["student_cfg"], g["s_sd"], dev)
+    student.train()
+    X, y = g["X"][:, :3200], g["y"][:, :3200]
+    step = DistillStep(teacher, student, mode="clskd", fresh_abf=True)
+    torch.manual_seed(0)
+    l1 = step(X, y)
+    l1.backward()
+    assert step.abf_encoder is None and step.abf_decoder is None           # nothing persistent
+    assert student.encoder[2][0].real_conv.weight.grad.abs().sum() > 0
+    n_train = len(step.trainable_parameters())
+    assert n_train == sum(1 for p in student.parameters() if p.requires_grad)
+    student.load_state_dict(full_sd(g["s_sd"]))
+    torch.manual_seed(1)
+    l2 = step(X, y)
+    assert abs(float(l1.detach()) - float(l2.detach())) > 0                 # different random projections
+    assert rel_err(step.last_terms["base"], float(l2.detach()) - sum(
+        float(v.detach()) for k, v in step.last_terms.items() if k != "base")) < 1e-4
+
+
 def test_flat_adam_matches_torch_adam(dev):
     from clskd_b200.distill import FlatAdam
     g = torch.Generator().manual_seed(0)
