@@ -164,3 +164,42 @@ def clskd_step_loss(teacher_sd, student_sd, X, y, abf_enc_sd=None, abf_dec_sd=No
     else:
         raise ValueError(mode)
     return sum(terms.values()), terms
+
+
+# ------------------------------------------------------------------ framework.py:176-202, 226-242
+def make_abf_state_dict(in_channels, out_channels, seed=0, randomize_bn=True):
+    """Deterministic ReviewKD weights ('abfs.{i}.…', i = 0 deepest) with the reference constructor's
+    distributions: conv1 / conv2 kaiming_uniform(a=1) (framework.py:194-195), att_conv torch default
+    (kaiming_uniform(a=sqrt(5)) + uniform bias).  in_channels / out_channels are listed shallow -> deep
+    like ReviewKD's arguments; mid = min(512, in_channels[-1]) (framework.py:238).  Lets a parity test
+    inject identical fusion weights into the reference, this oracle and the CUDA implementation without
+    shipping megabytes of weights in a fixture."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    mid = min(512, in_channels[-1])
+    last = len(in_channels) - 1
+    sd = {}
+
+    def ku(shape, a):
+        fan_in = shape[1] * shape[2] * shape[3]
+        bound = math.sqrt(2.0 / (1 + a * a)) * math.sqrt(3.0 / fan_in)
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+    def bn(p, ch):
+        sd[p + 'weight'] = 1 + 0.2 * torch.randn(ch, generator=g) if randomize_bn else torch.ones(ch)
+        sd[p + 'bias'] = 0.1 * torch.randn(ch, generator=g) if randomize_bn else torch.zeros(ch)
+        sd[p + 'running_mean'] = torch.zeros(ch)
+        sd[p + 'running_var'] = torch.ones(ch)
+        sd[p + 'num_batches_tracked'] = torch.tensor(0)
+
+    for idx in range(last, -1, -1):                       # abfs = blocks[::-1]: deepest first
+        p = 'abfs.%d.' % (last - idx)
+        sd[p + 'conv1.0.weight'] = ku((mid, in_channels[idx], 1, 1), 1.0)
+        bn(p + 'conv1.1.', mid)
+        sd[p + 'conv2.0.weight'] = ku((out_channels[idx], mid, 3, 3), 1.0)
+        bn(p + 'conv2.1.', out_channels[idx])
+        if idx < last:
+            sd[p + 'att_conv.0.weight'] = ku((2, 2 * mid, 1, 1), math.sqrt(5))
+            b = 1.0 / math.sqrt(2 * mid)
+            sd[p + 'att_conv.0.bias'] = (torch.rand(2, generator=g) * 2 - 1) * b
+    return sd

@@ -403,7 +403,8 @@ class LSTMLayerFn(torch.autograd.Function):
 class LSTM(nn.Module):
     """nn.LSTM(input_size, hidden_size, num_layers, bidirectional=False, batch_first=False) with the same
     parameter names (`weight_ih_l{k}`, `weight_hh_l{k}`, `bias_ih_l{k}`, `bias_hh_l{k}`); forward(x [T,B,D])
-    returns (output [T,B,H], (h_n, c_n)) with c_n = None (the path never consumes it)."""
+    returns (output [T,B,H], (h_n, c_n)): h_n [num_layers,B,H] like nn.LSTM; c_n = None (the recurrence kernel
+    keeps the cell state in registers and only stores it for training; no caller of the path consumes it)."""
 
     def __init__(self, input_size, hidden_size, num_layers=1, dropout=0.0, bidirectional=False, batch_first=False):
         super().__init__()
@@ -427,6 +428,7 @@ class LSTM(nn.Module):
             raise NotImplementedError("LSTM: only the zero initial state is implemented")
         ops._require_cuda(x)
         y = dense(x, ops.policy.act_dtype)
+        last = []
         for l in range(self.num_layers):
             key = (l, y.device)
             if key not in self._plans:
@@ -434,4 +436,5 @@ class LSTM(nn.Module):
             y = LSTMLayerFn.apply(self._plans[key], y, getattr(self, "weight_ih_l%d" % l),
                                   getattr(self, "weight_hh_l%d" % l), getattr(self, "bias_ih_l%d" % l),
                                   getattr(self, "bias_hh_l%d" % l), ops.policy.name == "bf16")
-        return y, (y[-1:], None)
+            last.append(y[-1])
+        return y, (torch.stack(last, 0), None)

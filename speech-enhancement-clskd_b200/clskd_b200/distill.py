@@ -32,7 +32,15 @@ def _taps(model, X, grad):
     finally:
         ext.remove_hook()
     fm = ext.feature_maps
-    real, imag = fm["clstm"][0]
+    tap = fm["clstm"][0]
+    if getattr(model, "use_clstm", True):
+        real, imag = tap                       # NavieComplexLSTM stack: [real, imag], each [T,B,D]
+    else:
+        # plain nn.LSTM bottleneck (DCCRN.py:101-109): the hook sees (y [T,B,H], (h_n, c_n)); the real / imaginary
+        # SPKD terms of distill.py:128-135 are taken on the two halves of the feature axis
+        y = tap[0]
+        half = y.shape[-1] // 2
+        real, imag = y[..., :half], y[..., half:]
     # the local LSTM is time-major; SPKD flattens from dim 1, so make the taps batch-first
     return wav, fm["encoder"], fm["decoder"], real.transpose(0, 1), imag.transpose(0, 1)
 
@@ -220,6 +228,33 @@ class FlatAdam:
         self._ptr_dev = torch.empty(len(sizes), dtype=torch.int64, device=dev)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0
+        self._sizes, self._offs = sizes, offs
+        self._active = None          # per-parameter "has a gradient" flags of the last pack_grads()
+        self._steps = [0] * len(sizes)   # per-parameter step counters (torch.optim.Adam state['step'])
+
+    def check_views(self):
+        """the parameters must still be views of the flat bucket (a later model.to() / .half() would silently
+        detach them from the optimizer)"""
+        base = self.flat_p.data_ptr()
+        for p, o in zip(self.params, self._offs[:-1]):
+            if p.data_ptr() != base + 4 * o or p.dtype != torch.float32:
+                raise RuntimeError("FlatAdam: a parameter no longer aliases the flat bucket (was the model moved or "
+                                   "cast after the optimizer was built?)")
+
+    def state_dict(self):
+        """checkpoint of the optimizer state (moments, step count, hyper-parameters, bucket layout)"""
+        return {"step_count": self.step_count, "steps": list(self._steps), "m": self.m.clone(), "v": self.v.clone(),
+                "sizes": list(self._sizes),
+                "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        if list(sd["sizes"]) != list(self._sizes):
+            raise ValueError("FlatAdam.load_state_dict: parameter layout differs from the checkpoint's")
+        self.m.copy_(sd["m"])
+        self.v.copy_(sd["v"])
+        self.step_count = int(sd["step_count"])
+        self._steps = list(sd.get("steps", [self.step_count] * len(self._sizes)))
+        self.lr, self.betas, self.eps, self.weight_decay = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
 
     def zero_grad(self):
         for p in self.params:
@@ -233,6 +268,7 @@ class FlatAdam:
                 g = ops.dense(g, torch.float32)
                 p.grad = g
             ptrs.append(g.data_ptr() if g is not None else 0)
+        self._active = [q != 0 for q in ptrs]
         # a FRESH pinned staging block per step (the pinned caching allocator only recycles it after the async
         # copy has run): the host may be more than a step ahead of the GPU, so one reused host buffer could be
         # overwritten with the next step's gradient addresses before this step's copy has executed
@@ -247,9 +283,28 @@ class FlatAdam:
     def step(self, world_size=1):
         """flat_g must hold the (summed over ranks) gradient; it is divided by world_size."""
         self.step_count += 1
-        call("clskd_adam_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(),
-             self.v.data_ptr(), self.total, float(self.lr), float(self.betas[0]), float(self.betas[1]),
-             float(self.eps), float(self.weight_decay), self.step_count, 1.0 / world_size, ops._stream())
+        if self.step_count % 64 == 1:
+            self.check_views()
+        # torch.optim.Adam skips parameters whose .grad is None (no moment decay, no weight decay, no update, and
+        # their own step counter does not advance): update contiguous ranges of the bucket that received a
+        # gradient in the last pack_grads() and share a step count - one launch in the usual all-active case
+        act = self._active if self._active is not None else [True] * len(self.params)
+        ranges = []          # (lo, hi, step)
+        for i, a in enumerate(act):
+            if not a:
+                continue
+            self._steps[i] += 1
+            lo, hi, k = self._offs[i], self._offs[i + 1], self._steps[i]
+            if ranges and ranges[-1][1] == lo and ranges[-1][2] == k:
+                ranges[-1] = (ranges[-1][0], hi, k)
+            else:
+                ranges.append((lo, hi, k))
+        for lo, hi, k in ranges:
+            if hi > lo:
+                call("clskd_adam_step", self.flat_p.data_ptr() + 4 * lo, self.flat_g.data_ptr() + 4 * lo,
+                     self.m.data_ptr() + 4 * lo, self.v.data_ptr() + 4 * lo, hi - lo, float(self.lr),
+                     float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                     k, 1.0 / world_size, ops._stream())
         ops.invalidate_weight_cache()      # the kernel rewrote the parameters in place
 
 
@@ -271,6 +326,36 @@ class DistillTrainer:
         if self.opt is None:
             self.step_fn.materialize(X)
             self.opt = FlatAdam(self.step_fn.trainable_parameters(), lr=self.lr, weight_decay=self.weight_decay)
+            self._sync_initial_state()
+
+    def _sync_initial_state(self):
+        """Data-parallel start: every rank must train the SAME weights.  Rank 0's flat parameter bucket (student +
+        the lazily created, randomly initialised ABF blocks) and all BatchNorm buffers are broadcast once, like
+        DDP does at construction; ranks with a different parameter layout are an error."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        n = torch.tensor([self.opt.total, -self.opt.total], dtype=torch.int64, device=self.opt.flat_p.device)
+        dist.all_reduce(n, op=dist.ReduceOp.MAX)
+        if int(n[0]) != self.opt.total or int(-n[1]) != self.opt.total:
+            raise RuntimeError("DistillTrainer: ranks disagree on the number of trainable parameters")
+        dist.broadcast(self.opt.flat_p, src=0)
+        ops.invalidate_weight_cache()
+        self.broadcast_buffers()
+
+    def broadcast_buffers(self):
+        """rank 0's BatchNorm running statistics / counters to every rank (DDP's broadcast_buffers); statistics
+        stay rank-local during training as in the reference (no SyncBN) - call this before evaluation / checkpoints"""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        mods = [self.student, self.step_fn.abf_encoder, self.step_fn.abf_decoder]
+        for m in mods:
+            if m is None:
+                continue
+            for b in m.buffers():
+                if b.numel() and b.is_floating_point() or b.dtype == torch.int64:
+                    dist.broadcast(b, src=0)
 
     def train_step(self, X, y):
         import torch.distributed as dist

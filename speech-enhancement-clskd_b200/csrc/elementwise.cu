@@ -1488,15 +1488,16 @@ extern "C" int clskd_sqdiff_bwd(const void* a, int a_dtype, const void* b, int b
   return CLSKD_OK;
 }
 
-extern "C" int clskd_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
-                               float beta1, float beta2, float eps, float weight_decay, int step,
-                               float grad_scale, void* stream) {
+extern "C" int clskd_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr,
+                               double beta1, double beta2, double eps, double weight_decay, int step,
+                               double grad_scale, void* stream) {
   CLSKD_CHECK_ARG(p && g && m && v && step >= 1, "clskd_adam_step: bad arguments");
   if (n == 0) return CLSKD_OK;
-  float bc1 = 1.f - powf(beta1, (float)step);
-  float bc2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<ew_grid(n, 256), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
-                                               bc1, sqrtf(bc2), grad_scale);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  adam_kernel<<<ew_grid(n, 256), 256, 0, ST>>>(p, g, m, v, n, (float)lr, (float)beta1, (float)beta2,
+                                               (float)eps, (float)weight_decay, (float)bc1,
+                                               (float)sqrt(bc2), (float)grad_scale);
   CLSKD_CHECK_LAUNCH("clskd_adam_step");
   return CLSKD_OK;
 }

@@ -39,7 +39,7 @@ def _batch():
     return 0.1 * torch.randn(4, 1500, generator=g), 0.1 * torch.randn(4, 1500, generator=g)
 
 
-def _worker(rank, world, port, mode, out_dir):
+def _worker(rank, world, port, mode, out_dir, unsynced=False):
     _setup_paths()
     torch.set_num_threads(1)
     import cabi_emu
@@ -51,7 +51,12 @@ def _worker(rank, world, port, mode, out_dir):
     X, y = _batch()
     n = X.shape[0] // world
     Xs, ys = X[rank * n:(rank + 1) * n], y[rank * n:(rank + 1) * n]
-    torch.manual_seed(3)                        # identical ABF init on every rank
+    torch.manual_seed(3 + (rank if unsynced else 0))      # unsynced: every rank draws its own ABF weights ...
+    if unsynced and rank > 0:                             # ... and starts from a different student
+        with torch.no_grad():
+            for p in student.parameters():
+                p.add_(0.01 * torch.randn(p.shape))
+        torch.manual_seed(3 + rank)
     tr = DistillTrainer(teacher, student, mode=mode, lr=1e-3, example_input=Xs)
     losses = [float(tr.train_step(Xs, ys)) for _ in range(2)]
     torch.save({"flat_p": tr.opt.flat_p.clone(), "losses": losses}, os.path.join(out_dir, "rank%d.pt" % rank))
@@ -66,10 +71,12 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("mode", ["spkd_all", "clskd"])
-def test_two_rank_step_equals_averaged_gradients(tmp_path, mode, monkeypatch):
+@pytest.mark.parametrize("mode,unsynced", [("spkd_all", False), ("clskd", False), ("clskd", True)])
+def test_two_rank_step_equals_averaged_gradients(tmp_path, mode, unsynced, monkeypatch):
+    """unsynced = True: the ranks construct different students / ABF blocks; the trainer's initial broadcast of
+    rank 0's parameter bucket must make the run identical to the synchronised one."""
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), mode, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), mode, str(tmp_path), unsynced), nprocs=world, join=True)
     r0 = torch.load(tmp_path / "rank0.pt")
     r1 = torch.load(tmp_path / "rank1.pt")
     assert torch.equal(r0["flat_p"], r1["flat_p"]), "ranks diverged"

@@ -1,0 +1,374 @@
+"""GPU parity of the BENCHMARKED configuration against fixtures generated from the unmodified reference
+(tests/golden/make_golden_real.py): teacher [32,64,128,256,256,256]/256, half-width and quarter-width
+students, B = 4 utterances of 4 s (T = 643 frames), both precision policies.
+
+north_star tolerances: enhanced-waveform max-abs error <= 1e-3 (bf16 policy) / <= 1e-5 (fp32 policy),
+distillation-loss relative error <= 1e-3.  Gradients are compared per tensor by relative L2 error on the
+fixture's strided samples; the bounds are stated next to each assertion and every measured value is
+written to gpurun_out/parity_r02.json (committed under profiles/)."""
+import pytest
+import torch
+
+from util import ParityLog, bn_shadowed_bias, golden, rel_err, sample_rel_l2
+
+pytestmark = pytest.mark.gpu
+LOG = ParityLog()
+
+
+@pytest.fixture(scope="module")
+def G():
+    return golden("real_width.pt")
+
+
+@pytest.fixture
+def cuda_dev():
+    import clskd_b200
+    assert torch.cuda.is_available()
+    clskd_b200._lib.load()
+    yield torch.device("cuda:0")
+    clskd_b200.set_precision("fp32")
+
+
+def _inputs(G):
+    g = torch.Generator().manual_seed(G["seeds"]["data"])
+    X = 0.1 * torch.randn(G["B"], G["L"], generator=g)
+    y = 0.1 * torch.randn(G["B"], G["L"], generator=g)
+    assert abs(float(X.double().sum()) - G["X_sum"]["sum"]) < 1e-6 * G["X_sum"]["asum"]
+    return X, y
+
+
+def _model(cfg, seed, dev, check=None):
+    import clskd_b200
+    from oracle.dccrn_oracle import make_state_dict
+    sd = make_state_dict(cfg["kernel_num"], cfg["rnn_units"], seed=seed)
+    if check:
+        for k, ref in check.items():          # the regenerated weights are the ones the reference ran with
+            assert abs(float(sd[k].double().sum()) - ref["sum"]) <= 1e-6 * ref["asum"], k
+    m = clskd_b200.DCCRN(rnn_units=cfg["rnn_units"], masking_mode="E", use_clstm=True, kernel_num=cfg["kernel_num"])
+    m.load_state_dict(sd)
+    return m.to(dev)
+
+
+def _tap_errors(fm, ref):
+    errs = {}
+    for kind in ("encoder", "decoder"):
+        for i, t in enumerate(fm[kind]):
+            errs["%s%d" % (kind[:3], i)] = sample_rel_l2(t, ref[kind][i])
+    re, im = fm["clstm"][0]
+    errs["lstm_re"] = sample_rel_l2(re.transpose(0, 1), ref["clstm"][0])
+    errs["lstm_im"] = sample_rel_l2(im.transpose(0, 1), ref["clstm"][1])
+    return errs
+
+
+@pytest.mark.parametrize("policy,wav_tol,tap_tol", [("fp32", 1e-5, 1e-4), ("bf16", 1e-3, 3e-2)])
+@pytest.mark.parametrize("which", ["teacher_eval", "teacher_train", "half_train", "quarter_train"])
+def test_real_width_forward(cuda_dev, G, which, policy, wav_tol, tap_tol):
+    """enhanced waveform (first two of the four utterances are stored in full) and every feature tap"""
+    import clskd_b200
+    X, _ = _inputs(G)
+    if which.startswith("teacher"):
+        m = _model(G["teacher_cfg"], G["seeds"]["teacher"], cuda_dev, G["t_sd_sum"])
+        ref = G[which]
+    else:
+        name = which.split("_")[0]
+        m = _model(G["student_cfgs"][name], G["seeds"]["student"], cuda_dev, G[name]["s_sd_sum"])
+        ref = G[name]["student_train"]
+    m.train(which.endswith("train"))
+    clskd_b200.set_precision(policy)
+    ext = clskd_b200.feature_extraction.DCCRN(m)
+    with torch.no_grad():
+        wav = m(X.to(cuda_dev), is_feat=True)
+    ext.remove_hook()
+    err = (wav[:2].float().cpu() - ref["wav"]).abs().max().item()
+    taps = _tap_errors(ext.feature_maps, ref)
+    LOG.add("forward/%s/%s" % (which, policy), wav_max_abs=err, wav_peak=float(ref["wav"].abs().max()), taps=taps)
+    assert err <= wav_tol, "waveform max-abs error %.3e" % err
+    assert sample_rel_l2(wav, ref["wav_sum"]) <= 50 * wav_tol
+    # feature taps: relative L2 (bf16 taps carry one bf16 rounding per layer: 2^-9 rms per stage)
+    assert max(taps.values()) <= tap_tol, taps
+
+
+def _load_abf(rk, sd):
+    own = rk.state_dict()
+    assert set(own) == set(sd), sorted(set(own) ^ set(sd))
+    rk.load_state_dict(sd)
+
+
+def _step(G, dev, student_name, mode, tmode, policy):
+    import clskd_b200
+    from clskd_b200.distill import DistillStep
+    from oracle.losses_oracle import make_abf_state_dict
+    X, y = _inputs(G)
+    clskd_b200.set_precision(policy)
+    rec = G[student_name]
+    teacher = _model(G["teacher_cfg"], G["seeds"]["teacher"], dev)
+    student = _model(G["student_cfgs"][student_name], G["seeds"]["student"], dev)
+    student.train()
+    faithful = tmode == "train"
+    if faithful:
+        teacher.train()
+    step = DistillStep(teacher, student, mode=mode, faithful=faithful)
+    Xd, yd = X.to(dev), y.to(dev)
+    if mode == "clskd":
+        step.materialize(Xd)
+        a = rec["abf_args"]
+        _load_abf(step.abf_encoder, make_abf_state_dict(a["enc_in"], a["enc_out"], G["seeds"]["abf_enc"]))
+        _load_abf(step.abf_decoder, make_abf_state_dict(a["dec_in"], a["dec_out"], G["seeds"]["abf_dec"]))
+        # materialize ran forwards that moved BatchNorm running statistics; they do not enter a train-mode loss
+    loss = step(Xd, yd)
+    loss.backward()
+    step.join_streams()
+    torch.cuda.synchronize()
+    return step, student, loss, rec["%s_%s" % (mode, tmode)]
+
+
+STEP_CASES = [("half", "clskd", "eval"), ("half", "clskd", "train"), ("half", "spkd_all", "eval"),
+              ("quarter", "clskd", "eval")]
+
+
+@pytest.mark.parametrize("policy", ["fp32", "bf16"])
+@pytest.mark.parametrize("student_name,mode,tmode", STEP_CASES)
+def test_real_width_distill_step(cuda_dev, G, student_name, mode, tmode, policy):
+    """CLSKD / SPKD-all step at the benchmarked widths: total loss and each of its 5 terms against the
+    reference, student and ABF gradients against the reference's autograd.  tmode = 'train' is the
+    reference-faithful step (train-mode teacher BatchNorm with autograd on, student forward twice)."""
+    step, student, loss, ref = _step(G, cuda_dev, student_name, mode, tmode, policy)
+    tag = "step/%s/%s/%s/%s" % (student_name, mode, tmode, policy)
+    terms = {k: rel_err(step.last_terms[k].detach(), v) for k, v in ref["terms"].items()}
+    # a term's error relative to the TOTAL loss (the two LSTM terms are 1e-4 of the total)
+    terms_vs_total = {k: abs(float(step.last_terms[k].detach()) - v) / abs(ref["loss"]) for k, v in ref["terms"].items()}
+    lerr = rel_err(loss.detach(), ref["loss"])
+    params = dict(student.named_parameters())
+    gerr = {}
+    for name, gref in ref["grads"].items():
+        if bn_shadowed_bias(name):
+            continue
+        assert params[name].grad is not None, name
+        gerr[name] = sample_rel_l2(params[name].grad, gref)
+    aerr = {}
+    if mode == "clskd":
+        for key, rk in (("abf_enc_grads", step.abf_encoder), ("abf_dec_grads", step.abf_decoder)):
+            ps = dict(rk.named_parameters())
+            for name, gref in ref[key].items():
+                if gref["l2"] < 1e-12:
+                    continue
+                aerr[key[4:7] + "." + name] = sample_rel_l2(ps[name].grad, gref)
+    worst = sorted(gerr.items(), key=lambda kv: -kv[1])[:5]
+    LOG.add(tag, loss_rel=lerr, terms_rel=terms, terms_vs_total=terms_vs_total, grad_rel_l2_max=max(gerr.values()),
+            grad_rel_l2_median=sorted(gerr.values())[len(gerr) // 2], grad_worst=dict(worst),
+            abf_grad_rel_l2_max=max(aerr.values()) if aerr else None,
+            abf_grad_rel_l2_median=sorted(aerr.values())[len(aerr) // 2] if aerr else None,
+            abf_grad_worst=dict(sorted(aerr.items(), key=lambda kv: -kv[1])[:5]))
+    if policy == "fp32":
+        assert lerr < 1e-4 and max(terms.values()) < 1e-3, (lerr, terms)
+        assert max(gerr.values()) < 1e-2, worst              # fp32 reduction-order noise through 643 BPTT steps
+        assert not aerr or max(aerr.values()) < 1e-2
+    else:
+        assert lerr < 1e-3, lerr                                              # north_star
+        assert max(terms_vs_total.values()) < 1e-3, terms_vs_total            # every term, against the total
+        assert max(terms.values()) < 2e-2, terms                              # every term, against itself
+        assert sorted(gerr.values())[len(gerr) // 2] < 5e-2, worst            # median per-tensor gradient error
+        assert max(gerr.values()) < 0.25, worst
+        assert not aerr or max(aerr.values()) < 0.25
+    assert all(torch.isfinite(p.grad).all() for p in student.parameters() if p.grad is not None)
+
+
+def test_faithful_step_runs_student_twice_and_moves_teacher_bn(cuda_dev, G):
+    """DistillStep(faithful=True) on the GPU kernels (distill.py:49-50,77,85,100)"""
+    import clskd_b200
+    clskd_b200.set_precision("fp32")
+    from clskd_b200.distill import DistillStep
+    X, y = _inputs(G)
+    teacher = _model(G["teacher_cfg"], G["seeds"]["teacher"], cuda_dev)
+    student = _model(G["student_cfgs"]["half"], G["seeds"]["student"], cuda_dev)
+    teacher.train()
+    student.train()
+    rm0 = teacher.encoder[0][1].running_mean.clone()
+    st = DistillStep(teacher, student, mode="spkd_all", faithful=True)
+    l2 = st(X[:2].to(cuda_dev), y[:2].to(cuda_dev))
+    l2.backward()
+    assert teacher.training and int(teacher.encoder[0][1].num_batches_tracked) == 1
+    assert not torch.equal(teacher.encoder[0][1].running_mean, rm0)
+    assert int(student.encoder[0][1].num_batches_tracked) == 2
+    assert all(p.grad is None for p in teacher.parameters())
+    assert student.encoder[0][0].real_conv.weight.grad is not None
+
+
+@pytest.mark.parametrize("policy", ["fp32", "bf16"])
+def test_fresh_abf_step_on_gpu(cuda_dev, G, policy):
+    """DistillStep(fresh_abf=True): new random, untrained fusion blocks every step (distill.py:92-96) on the
+    CUDA kernels; with the same seed the step is reproducible and equals the oracle run with those weights."""
+    import clskd_b200
+    from clskd_b200.distill import DistillStep
+    from oracle import losses_oracle as LO
+    from oracle.dccrn_oracle import make_state_dict
+    clskd_b200.set_precision(policy)
+    cfg_t = dict(kernel_num=[32, 64, 64, 64, 64, 64], rnn_units=64)
+    cfg_s = dict(kernel_num=[16, 32, 32, 32, 32, 32], rnn_units=32)
+    teacher, student = _model(cfg_t, 1, cuda_dev), _model(cfg_s, 2, cuda_dev)
+    student.train()
+    g = torch.Generator().manual_seed(0)
+    X, y = 0.1 * torch.randn(4, 8000, generator=g), 0.1 * torch.randn(4, 8000, generator=g)
+    step = DistillStep(teacher, student, mode="clskd", fresh_abf=True)
+    captured = {}
+    orig = step._abfs
+
+    def spy(*a):
+        enc, dec = orig(*a)
+        captured["enc"] = {k: v.detach().float().cpu().clone() for k, v in enc.state_dict().items()}
+        captured["dec"] = {k: v.detach().float().cpu().clone() for k, v in dec.state_dict().items()}
+        return enc, dec
+    step._abfs = spy
+    torch.manual_seed(0)
+    l1 = step(X.to(cuda_dev), y.to(cuda_dev))
+    l1.backward()
+    assert step.abf_encoder is None and step.abf_decoder is None
+    assert len(step.trainable_parameters()) == sum(1 for p in student.parameters() if p.requires_grad)
+    ref, _ = LO.clskd_step_loss(make_state_dict(cfg_t["kernel_num"], cfg_t["rnn_units"], seed=1),
+                                make_state_dict(cfg_s["kernel_num"], cfg_s["rnn_units"], seed=2), X, y,
+                                abf_enc_sd=captured["enc"], abf_dec_sd=captured["dec"], mode="clskd")
+    err = rel_err(l1.detach(), ref.detach())
+    LOG.add("fresh_abf/" + policy, loss_rel=err)
+    assert err < (1e-4 if policy == "fp32" else 1e-3)
+    w1 = captured["enc"]["abfs.0.conv1.0.weight"].clone()
+    torch.manual_seed(1)
+    step(X.to(cuda_dev), y.to(cuda_dev))
+    assert not torch.equal(w1, captured["enc"]["abfs.0.conv1.0.weight"])      # re-randomised every step
+
+
+@pytest.mark.parametrize("policy", ["fp32", "bf16"])
+def test_complex_lstm_teacher_width_bptt(cuda_dev, policy):
+    """Teacher-width complex LSTM (D = 512, H = 128, projection back to 512) over T = 643 steps and B = 4:
+    2 parts x T x B = 5144 rows >= 4096, so the bf16 policy takes the tcgen05 weight-gradient route and keeps
+    bf16 W_hh in shared memory.  Forward and BPTT against the oracle's autograd."""
+    import clskd_b200
+    from clskd_b200 import ops
+    from clskd_b200.clstm import NavieComplexLSTM
+    from oracle import dccrn_oracle as D
+    T, B, Din, H = 643, 4, 512, 128
+    g = torch.Generator().manual_seed(3)
+    torch.manual_seed(3)
+    l0 = NavieComplexLSTM(input_size=2 * Din, hidden_size=2 * H, projection_dim=None)
+    l1 = NavieComplexLSTM(input_size=2 * H, hidden_size=2 * H, projection_dim=2 * Din)
+    r, i = 0.5 * torch.randn(T, B, Din, generator=g), 0.5 * torch.randn(T, B, Din, generator=g)
+    gr, gi = torch.randn(T, B, Din, generator=g), torch.randn(T, B, Din, generator=g)
+    sd = {"a." + k: v.clone() for k, v in l0.state_dict().items()}
+    sd.update({"b." + k: v.clone() for k, v in l1.state_dict().items()})
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    r2 = r.clone().requires_grad_(True)
+    h = D.complex_lstm(r2, i, params, "a.", False)
+    o2 = D.complex_lstm(h[0], h[1], params, "b.", True)
+    ((o2[0] * gr).sum() + (o2[1] * gi).sum()).backward()
+    clskd_b200.set_precision(policy)
+    l0, l1 = l0.to(cuda_dev), l1.to(cuda_dev)
+    rd = r.to(cuda_dev).requires_grad_(True)
+    n0 = ops.umma_launches
+    out = l1(l0([rd, i.to(cuda_dev)]))
+    ((out[0].float() * gr.to(cuda_dev)).sum() + (out[1].float() * gi.to(cuda_dev)).sum()).backward()
+    if policy == "bf16":
+        assert ops.umma_launches - n0 >= 6, "tcgen05 projection / weight-gradient launches expected"
+    rl2 = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    errs = {"out_re": rl2(out[0].detach().float(), o2[0].detach()), "out_im": rl2(out[1].detach().float(), o2[1].detach()),
+            "dx": rl2(rd.grad.float(), r2.grad)}
+    for mod, pre in ((l0, "a."), (l1, "b.")):
+        for k, p in mod.named_parameters():
+            errs[pre + k] = rl2(p.grad.float(), params[pre + k].grad)
+    LOG.add("clstm_teacher_width/" + policy, **errs)
+    tol = 1e-3 if policy == "fp32" else 3e-2
+    assert max(errs.values()) < tol, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+
+
+@pytest.mark.parametrize("mid,cin,F,T,B,up", [(128, 64, 32, 41, 3, True), (128, 16, 128, 23, 2, True), (64, 32, 16, 40, 3, False)])
+def test_bf16_abf_block_vs_oracle(cuda_dev, mid, cin, F, T, B, up):
+    """One ABF level under the bf16 policy (fused BN + resize + attention + blend kernels, tcgen05 1x1 and 3x3
+    convs with the fused-statistics epilogue) against oracle.losses_oracle.abf_forward and its autograd."""
+    import clskd_b200
+    from clskd_b200 import framework as fw
+    from oracle import losses_oracle as LO
+    g = torch.Generator().manual_seed(mid + F)
+    torch.manual_seed(mid + cin)
+    cout = 32
+    abf = fw.ABF(cin, mid, cout, True)
+    for seq in (abf.conv1, abf.conv2):
+        seq[1].weight.data.uniform_(0.5, 1.5)
+        seq[1].bias.data.normal_(0, 0.2)
+    abf.att_conv[0].bias.data.normal_(0, 0.2)
+    sd = {"p." + k: v.detach().clone() for k, v in abf.state_dict().items()}
+    Fy = F // 2 if up else F
+    x0 = torch.randn(B, cin, F, T, generator=g).bfloat16().float()
+    y0 = torch.randn(B, mid, Fy, T, generator=g).bfloat16().float()
+    g_out = torch.randn(B, cout, F, T, generator=g)
+    g_fus = torch.randn(B, mid, F, T, generator=g)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    full = dict(sd)
+    full.update(params)
+    xr, yr = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+    ro, rf = LO.abf_forward(xr, yr, full, "p.", F, F, training=True)
+    ((ro * g_out).sum() + (rf * g_fus).sum()).backward()
+    clskd_b200.set_precision("bf16")
+    abf = abf.to(cuda_dev).train()
+    x = x0.to(cuda_dev).bfloat16().requires_grad_(True)
+    y = y0.to(cuda_dev).bfloat16().requires_grad_(True)
+    out, fused = abf(x, y, F, F, "decoder")
+    ((out.float() * g_out.to(cuda_dev)).sum() + (fused.float() * g_fus.to(cuda_dev)).sum()).backward()
+    rl2 = lambda a, b: float((a.detach().double().cpu() - b.detach().double()).norm() / max(float(b.detach().double().norm()), 1e-30))
+    errs = {"out": rl2(out.float(), ro), "fused": rl2(fused.float(), rf), "dx": rl2(x.grad.float(), xr.grad),
+            "dy": rl2(y.grad.float(), yr.grad)}
+    for k, p in abf.named_parameters():
+        errs["d." + k] = rl2(p.grad.float(), params["p." + k].grad)
+    LOG.add("abf_block_bf16/mid%d_cin%d_F%d" % (mid, cin, F), **errs)
+    assert errs["out"] < 1e-2 and errs["fused"] < 1e-2, errs         # one bf16 rounding per stored stage (2^-9 rms)
+    assert max(errs.values()) < 3e-2, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+
+
+@pytest.mark.parametrize("kind,cin,cout,F,T,B", [("conv", 32, 64, 64, 37, 3), ("deconv", 64, 32, 8, 33, 2)])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_bf16_fused_conv_epilogue_vs_oracle(cuda_dev, kind, cin, cout, F, T, B, mode):
+    """conv / transposed conv + BatchNorm + PReLU block with the fused tcgen05 epilogue (batch statistics in
+    train mode, folded affine + PReLU in eval mode) against the oracle's complex conv + F.batch_norm + PReLU."""
+    import clskd_b200
+    from clskd_b200 import ops
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    import torch.nn.functional as Fnn
+    g = torch.Generator().manual_seed(cin + F + T)
+    if kind == "conv":
+        conv = tm.ComplexConv2d(cin, cout, kernel_size=(5, 2), stride=(2, 1), padding=(2, 1))
+    else:
+        conv = tm.ComplexConvTranspose2d(2 * cin, cout, kernel_size=(5, 2), stride=(2, 1), padding=(2, 0),
+                                         output_padding=(1, 0))
+    conv.real_conv.bias.data.normal_(generator=g)
+    conv.imag_conv.bias.data.normal_(generator=g)
+    for p in conv.parameters():
+        p.data = p.data.bfloat16().float()
+    bn = tm.BatchNorm2d(cout)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_(0, 0.3)
+    bn.running_mean.normal_(0, 0.1)
+    bn.running_var.uniform_(0.5, 1.5)
+    blk = tm.ConvBNAct(conv, bn, tm.PReLU())
+    x0 = torch.randn(B, cin, F, T, generator=g).bfloat16().float()
+    x1 = torch.randn(B, cin, F, T, generator=g).bfloat16().float() if kind == "deconv" else None
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    if kind == "conv":
+        z = D.complex_conv2d(x0, conv.real_conv.weight, conv.real_conv.bias, conv.imag_conv.weight, conv.imag_conv.bias)
+    else:
+        z = D.complex_deconv2d(D.complex_cat([x0, x1], 1), conv.real_conv.weight, conv.real_conv.bias,
+                               conv.imag_conv.weight, conv.imag_conv.bias)
+    ref = Fnn.prelu(Fnn.batch_norm(z, rm, rv, bn.weight, bn.bias, mode == "train", 0.1, 1e-5), blk[2].weight).detach()
+    blk = blk.to(cuda_dev)
+    blk.train(mode == "train")
+    clskd_b200.set_precision("bf16")
+    ph = lambda t: t.permute(0, 3, 2, 1).contiguous().to(cuda_dev).bfloat16()
+    n0 = ops.fused_epilogues
+    with torch.no_grad():
+        yv = blk.forward_phys(ph(x0), ph(x1) if x1 is not None else None)
+    assert ops.fused_epilogues == n0 + 1, "fused epilogue not taken"
+    yv = yv.float().permute(0, 3, 2, 1).cpu()
+    err = float((yv - ref).norm() / ref.norm())
+    mx = float((yv - ref).abs().max() / ref.abs().max())
+    LOG.add("fused_epilogue_bf16/%s_%s" % (kind, mode), rel_l2=err, max_rel=mx)
+    assert err < 6e-3 and mx < 2e-2, (err, mx)         # bf16 storage of z (train) / of the output (eval)
+    if mode == "train":
+        assert torch.allclose(blk[1].running_mean.cpu(), rm, rtol=2e-3, atol=2e-4)
+        assert torch.allclose(blk[1].running_var.cpu(), rv, rtol=4e-3, atol=1e-4)

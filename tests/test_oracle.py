@@ -310,3 +310,37 @@ def test_model_variants_oracle_vs_golden(name):
     loss.backward()
     for k, g in V["grads"].items():
         assert (live[k].grad - g).abs().max().item() < 2e-3 * max(g.abs().max().item(), 1e-6) + 1e-6, k
+
+
+def test_oracle_step_at_benchmarked_widths_vs_reference_fixture():
+    """tests/golden/real_width.pt (unmodified reference, teacher [32..256]/256 -> half student, B = 4 x 4 s,
+    T = 643): the oracle's CLSKD step loss, its 5 terms and the student / ABF gradients at the benchmarked widths."""
+    from oracle import dccrn_oracle as D
+    from oracle import losses_oracle as LO
+    from util import sample_rel_l2
+    G = golden("real_width.pt")
+    g = torch.Generator().manual_seed(G["seeds"]["data"])
+    X, y = 0.1 * torch.randn(G["B"], G["L"], generator=g), 0.1 * torch.randn(G["B"], G["L"], generator=g)
+    tc, sc, rec = G["teacher_cfg"], G["student_cfgs"]["half"], G["half"]
+    t_sd = D.make_state_dict(tc["kernel_num"], tc["rnn_units"], seed=G["seeds"]["teacher"])
+    s_sd = D.make_state_dict(sc["kernel_num"], sc["rnn_units"], seed=G["seeds"]["student"])
+    a = rec["abf_args"]
+    e_sd = LO.make_abf_state_dict(a["enc_in"], a["enc_out"], G["seeds"]["abf_enc"])
+    d_sd = LO.make_abf_state_dict(a["dec_in"], a["dec_out"], G["seeds"]["abf_dec"])
+    leaf = lambda sd: {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
+                           and not k.startswith(("stft.", "istft.")) else v) for k, v in sd.items()}
+    s_sd, e_sd, d_sd = leaf(s_sd), leaf(e_sd), leaf(d_sd)
+    loss, terms = LO.clskd_step_loss(t_sd, s_sd, X, y, abf_enc_sd=e_sd, abf_dec_sd=d_sd, mode="clskd")
+    ref = rec["clskd_eval"]
+    assert rel_err(loss.detach(), ref["loss"]) < 1e-5
+    for k, v in ref["terms"].items():
+        assert rel_err(terms[k].detach(), v) < 1e-4, k
+    loss.backward()
+    for name, gref in ref["grads"].items():
+        if bn_shadowed_bias(name):
+            continue
+        assert sample_rel_l2(s_sd[name].grad, gref) < 2e-3, name
+    for key, sd in (("abf_enc_grads", e_sd), ("abf_dec_grads", d_sd)):
+        for name, gref in ref[key].items():
+            if gref["l2"] > 1e-12:
+                assert sample_rel_l2(sd[name].grad, gref) < 2e-3, (key, name)

@@ -424,14 +424,76 @@ def test_flat_adam_matches_torch_adam(dev):
         for p, q in zip(ps, qs):
             gr = torch.randn(p.shape, generator=g)
             p.grad, q.grad = gr.clone().to(dev), gr.clone()
-        if it == 1:                                     # a parameter without a gradient packs as zeros
+        if it == 1:                                     # a parameter without a gradient is skipped like torch does
             ps[2].grad = None
-            qs[2].grad = torch.zeros_like(qs[2])
+            qs[2].grad = None
         ours.pack_grads()
         ours.step()
         ref.step()
         for p, q in zip(ps, qs):
             assert torch.allclose(p.detach().cpu(), q.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_flat_adam_state_dict_round_trip(dev):
+    from clskd_b200.distill import FlatAdam
+    g = torch.Generator().manual_seed(1)
+    mk = lambda: [torch.nn.Parameter(torch.randn(s, generator=torch.Generator().manual_seed(4)).to(dev)) for s in [(6, 2), (3,)]]
+    grads = [[torch.randn(p.shape, generator=g) for p in mk()] for _ in range(4)]
+    a_params, b_params = mk(), mk()
+    a, b = FlatAdam(a_params, lr=1e-3, weight_decay=1e-2), FlatAdam(b_params, lr=1e-3, weight_decay=1e-2)
+
+    def run(opt, params, its):
+        for it in its:
+            for p, gr in zip(params, grads[it]):
+                p.grad = gr.clone().to(dev)
+            opt.pack_grads()
+            opt.step()
+    run(a, a_params, range(4))
+    run(b, b_params, range(2))
+    sd = b.state_dict()
+    c_params = mk()
+    c = FlatAdam(c_params, lr=5.0)
+    c.flat_p.copy_(b.flat_p)
+    c.load_state_dict(sd)
+    run(c, c_params, range(2, 4))
+    assert torch.allclose(c.flat_p, a.flat_p, rtol=1e-6, atol=1e-7)
+    c_params[0].data = c_params[0].data.clone()           # detached from the bucket (what model.to() would do)
+    with pytest.raises(RuntimeError):
+        c.check_views()
+
+
+def test_distill_step_with_plain_lstm_bottleneck(dev):
+    """use_clstm=False (the DCCRN constructor default, DCCRN.py:101-109): the feature modes tap the plain LSTM's
+    output; the step loss equals the oracle's with the LSTM output split into halves."""
+    import clskd_b200
+    from clskd_b200.distill import DistillStep
+    from oracle import losses_oracle as LO
+    torch.manual_seed(0)
+    kw_t, kw_s = dict(kernel_num=[4, 8, 8, 16, 16, 16], rnn_units=16), dict(kernel_num=[2, 4, 4, 8, 8, 8], rnn_units=8)
+    teacher = clskd_b200.DCCRN(masking_mode="E", use_clstm=False, **kw_t)
+    student = clskd_b200.DCCRN(masking_mode="E", use_clstm=False, **kw_s)
+    t_sd = {k: v.detach().clone() for k, v in teacher.state_dict().items()}
+    s_sd = {k: v.detach().clone() for k, v in student.state_dict().items()}
+    teacher, student = teacher.to(dev), student.to(dev)
+    student.train()
+    g = torch.Generator().manual_seed(0)
+    X, y = 0.1 * torch.randn(3, 2000, generator=g), 0.1 * torch.randn(3, 2000, generator=g)
+    step = DistillStep(teacher, student, mode="spkd_all")
+    loss = step(X.to(dev), y.to(dev))
+    loss.backward()
+    assert student.enhance.weight_hh_l0.grad is not None
+    tt, st = {}, {}
+    from oracle.dccrn_oracle import dccrn_forward
+    with torch.no_grad():
+        dccrn_forward(t_sd, X, training=False, taps=tt)
+        s_wav = dccrn_forward(s_sd, X, training=True, taps=st)[-1]
+        ref = LO.mr_stft_loss(s_wav, y, [512], [100], [400])[1]
+        ref = ref + sum(LO.spkd(a, b) for a, b in zip(st["encoder"], tt["encoder"]))
+        ref = ref + sum(LO.spkd(a, b) for a, b in zip(st["decoder"], tt["decoder"]))
+        ys, yt = st["clstm"][0].transpose(0, 1), tt["clstm"][0].transpose(0, 1)
+        hs, ht = ys.shape[-1] // 2, yt.shape[-1] // 2
+        ref = ref + LO.spkd(ys[..., :hs], yt[..., :ht]) + LO.spkd(ys[..., hs:], yt[..., ht:])
+    assert rel_err(loss.detach(), ref) < 1e-4
 
 
 def test_trainer_step_decreases_loss(dev):

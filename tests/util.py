@@ -65,3 +65,36 @@ def bn_shadowed_bias(name):
     """conv biases that feed a train-mode BatchNorm have a mathematically zero gradient (the batch
     mean is subtracted): the reference's autograd value is rounding noise and is not compared."""
     return name.endswith("_conv.bias") and not name.startswith("decoder.5.")
+
+
+def sample_rel_l2(t, ref):
+    """relative L2 error of a tensor against a golden summary, evaluated on the stored strided sample
+    (ref = {"sample", "step", "numel", ...} from make_golden_real.summ)"""
+    n = ref["sample"].numel()
+    t = t.detach().double().cpu().reshape(-1)
+    assert t.numel() == ref["numel"], "numel %d vs %d" % (t.numel(), ref["numel"])
+    s = t[::ref["step"]][:n]
+    r = ref["sample"].double()
+    return float((s - r).norm() / max(float(r.norm()), 1e-30))
+
+
+class ParityLog:
+    """Collects measured parity errors of the GPU tests into gpurun_out/parity_<tag>.json (merged over
+    tests) so that the stated bounds can be read next to what was measured."""
+
+    def __init__(self, tag="r02"):
+        root = os.path.dirname(HERE)
+        self.path = os.path.join(root, "gpurun_out", "parity_%s.json" % tag)
+
+    def add(self, test, **vals):
+        import json
+        os.makedirs(os.path.dirname(self.path), exist_ok=True)
+        data = {}
+        if os.path.exists(self.path):
+            try:
+                data = json.load(open(self.path))
+            except Exception:
+                data = {}
+        data.setdefault(test, {}).update(vals)
+        with open(self.path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
