@@ -309,6 +309,15 @@ int clskd_lstm_fwd(const float* pre, const float* whh_t, int T, int R, int Bp, i
                    int64_t pre_pstride, int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride,
                    int64_t whh_set_stride, int w_bf16, float* h, float* gates, float* c,
                    void* stream);
+/* The same recurrence with a carried state (time-chunked streaming inference, eval.py:42-60 on long
+ * utterances): h0 / c0 [nsets][R][H] initialise the state (NULL = zeros, the reference's default), hN / cN
+ * receive the state after the last step (NULL to skip; may alias h0 / c0 for an in-place carry).
+ * With T == 0 nothing is launched and hN / cN are left untouched. */
+int clskd_lstm_fwd_state(const float* pre, const float* whh_t, int T, int R, int Bp, int H, int nsets,
+                         int64_t pre_pstride, int64_t pre_tstride, int64_t pre_ld,
+                         int64_t pre_set_stride, int64_t whh_set_stride, int w_bf16, float* h,
+                         float* gates, float* c, const float* h0, const float* c0, float* hN,
+                         float* cN, void* stream);
 /* BPTT: given dh_out (gradient wrt every h_t, layout of h) produces dpre (gradient wrt the
  * pre-activations, addressed like `pre`).  gates/c are the saved forward tensors; `whh` is
  * W_hh [nsets][4H][H] fp32. */

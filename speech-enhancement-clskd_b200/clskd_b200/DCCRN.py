@@ -14,7 +14,7 @@ import torch.nn as nn
 from . import config as cfg
 from . import ops
 from .clstm import LSTM, NavieComplexLSTM, _LinearParams
-from .ops import MaskFn, dense, strided_copy_into, to_logical, to_phys
+from .ops import MaskFn, dense, strided_copy, strided_copy_into, to_logical, to_phys
 from .tools_for_loss import mse, sdr, si_sdr, si_snr
 from .tools_for_model import (BatchNorm2d, ComplexBatchNorm, ComplexConv2d, ComplexConvTranspose2d, ConvBNAct,
                               ConviSTFT, ConvSTFT, PReLU)
@@ -201,6 +201,121 @@ class DCCRN(nn.Module):
         mask_real, mask_imag = mp[..., 0].permute(0, 2, 1), mp[..., 1].permute(0, 2, 1)
         real, imag = out_spec[..., 0].permute(0, 2, 1), out_spec[..., 1].permute(0, 2, 1)
         return mask_real, mask_imag, real, imag, out_wav
+
+    # ------------------------------------------------------------------------------------------
+    # time-chunked streaming inference (the reference's eval path eval.py:42-60 runs whole
+    # utterances one at a time).  Exact, not approximate: apart from the LSTM the model has a bounded temporal
+    # footprint - every encoder conv looks back ONE frame (time kernel 2, causal left pad 1,
+    # tools_for_model.py:237-238), the LSTM is unidirectional (state carried in (h, c)), every transposed conv
+    # followed by the drop of column 0 (DCCRN.py:205) looks AHEAD one frame (6 frames = 37.5 ms in total), eval
+    # BatchNorm / PReLU / mask are pointwise, and the iSTFT overlap-add spans 4 frames.  So activation memory is
+    # bounded by the chunk length instead of the utterance length.
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _tcat(parts):
+        """concatenate logical [B, C, F, t] maps along time (physical [B, t, F, C]) with the library's copy kernel"""
+        ps = [to_phys(p) for p in parts]
+        if len(ps) == 1 and ps[0].is_contiguous():
+            return to_logical(strided_copy(ps[0]))
+        B, _, F, C = ps[0].shape
+        T = sum(p.shape[1] for p in ps)
+        out = torch.empty((B, T, F, C), dtype=ps[0].dtype, device=ps[0].device)
+        o = 0
+        for p in ps:
+            strided_copy_into(p, out[:, o:o + p.shape[1]])
+            o += p.shape[1]
+        return to_logical(out)
+
+    def enhance_streaming(self, inputs, chunk_frames=400):
+        """Enhanced waveform [B, L'] of `inputs` [B, L], identical (to fp32 rounding) to
+        `forward(inputs, is_feat=True)` in eval mode, computed in time chunks of `chunk_frames` STFT frames."""
+        if self.training:
+            raise RuntimeError("enhance_streaming: eval mode only (train-mode BatchNorm couples all frames)")
+        if not self.use_clstm:
+            raise NotImplementedError("enhance_streaming: implemented for the complex-LSTM bottleneck (DCCRN-CL)")
+        ops._require_cuda(inputs)
+        if inputs.dim() == 3:
+            inputs = inputs.squeeze(1)
+        act = ops.policy.act_dtype
+        B, L = inputs.shape
+        hop, win = self.win_inc, self.win_len
+        pad = win - hop
+        nlay = len(self.decoder)
+        T = (L + 2 * pad - win) // hop + 1
+        if T <= chunk_frames + 2 * nlay + 8:
+            return self.forward(inputs, is_feat=True)
+        from .ops import Pad1dFn
+        with torch.no_grad():
+            xpad = Pad1dFn.apply(inputs, pad, pad, 0)                       # [B, L + 600]
+            bounds = list(range(0, T, chunk_frames)) + [T]
+            if bounds[-1] - bounds[-2] < 2 * nlay + 8:                      # fold a short tail into the last chunk
+                bounds.pop(-2)
+            enc_prev = [None] * len(self.encoder)       # last input frame of every encoder layer
+            states = [m.new_state(B, inputs.device) for m in self.enhance]
+            tail_in, tail_skip, tail_spec = None, [None] * len(self.encoder), None   # last `nlay` frames
+            tail_est = None                                                  # last 3 estimated-spectrum frames
+            pieces = []
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                last = b == T
+                seg = dense(xpad[:, a * hop:(b - 1) * hop + win])
+                spec = self.stft.spectrum_padded(seg)                        # fp32 [B, b-a, 257, 2]
+                out = to_logical(dense(spec[:, :, 1:, :]))
+                enc_out = []
+                for li, layer in enumerate(self.encoder):
+                    if enc_prev[li] is None:
+                        nxt = layer(out)
+                    else:
+                        nxt = layer(self._tcat([enc_prev[li], out]))[..., 1:]
+                    enc_prev[li] = self._tcat([out[..., -1:]])
+                    out = nxt
+                    enc_out.append(out)
+                x = to_phys(out, need_dense=True)
+                Fd = x.shape[2]
+                X = _ToLstmFn.apply(x, act)
+                for m, stt in zip(self.enhance, states):
+                    X = m.forward_stacked_state(dense(X, act), stt)
+                out = to_logical(_FromLstmFn.apply(X[0], X[1], Fd, act))
+                # decoder on the window [a - nlay, b): its outputs are final for frames [a - nlay, b - nlay)
+                if tail_in is not None:
+                    out = self._tcat([tail_in, out])
+                    enc_out = [self._tcat([t_, e_]) for t_, e_ in zip(tail_skip, enc_out)]
+                    spec = self._cat_rows(tail_spec, spec)
+                f0 = a - nlay if tail_in is not None else a
+                if not last:
+                    tail_in = self._tcat([out[..., -nlay:]])
+                    tail_skip = [self._tcat([e_[..., -nlay:]]) for e_ in enc_out]
+                    tail_spec = strided_copy(spec[:, -nlay:])
+                for idx in range(nlay):
+                    out = self.decoder[idx](out, enc_out[-1 - idx])
+                    out = to_logical(_TrimFirstFn.apply(to_phys(out)))
+                nvalid = out.shape[-1] if last else out.shape[-1] - nlay
+                mask = to_phys(out)[:, :nvalid]
+                if mask.stride(3) != 1 or mask.stride(2) != 2 or mask.stride(1) != mask.shape[2] * 2:
+                    mask = dense(mask)
+                est, _ = MaskFn.apply(dense(spec[:, :nvalid]), mask, self.masking_mode, False)
+                f1 = f0 + nvalid
+                rows = est.view(B, nvalid, -1)
+                if tail_est is not None:
+                    rows = self._cat_rows(tail_est, rows)
+                tail_est = strided_copy(rows[:, -3:])
+                pieces.append(self.istft.synthesize(rows, interleaved=True, clamp=True))
+                del out, enc_out, spec, est, rows, X, x
+            wav = torch.empty((B, sum(p_.shape[1] for p_ in pieces)), dtype=torch.float32, device=inputs.device)
+            o = 0
+            for p_ in pieces:
+                strided_copy_into(p_.view(B, 1, 1, -1), wav[:, o:o + p_.shape[1]].unsqueeze(1).unsqueeze(1))
+                o += p_.shape[1]
+        return wav
+
+    @staticmethod
+    def _cat_rows(a, b):
+        """concatenate [B, ta, ...] and [B, tb, ...] along dim 1 with the library's copy kernel"""
+        B = a.shape[0]
+        out = torch.empty((B, a.shape[1] + b.shape[1]) + tuple(a.shape[2:]), dtype=a.dtype, device=a.device)
+        n = a[0, 0].numel()
+        strided_copy_into(a.reshape(B, 1, a.shape[1], n), out[:, :a.shape[1]].reshape(B, 1, a.shape[1], n))
+        strided_copy_into(b.reshape(B, 1, b.shape[1], n), out[:, a.shape[1]:].reshape(B, 1, b.shape[1], n))
+        return out
 
     def get_params(self, weight_decay=0.0):
         weights = [p for n, p in self.named_parameters() if 'bias' not in n]

@@ -59,47 +59,65 @@ class _ClstmPlans:
         self.cache = {}
 
 
+def _clstm_forward(plans, X, wr_ih, wr_hh, br_ih, br_hh, wi_ih, wi_hh, bi_ih, bi_hh, w_bf16, train, state):
+    """One complex LSTM layer on X [2, T, B, D] (fp32 contiguous weights) -> (Y [2,T,B,H], h, gates, c).
+    state: None (zero initial state, the reference's default) or a dict with 'h' / 'c' tensors
+    [2 sets][2*B rows][H] that initialise the recurrence and are UPDATED IN PLACE with the state after the last
+    step (time-chunked streaming inference)."""
+    P, T, B, D = X.shape
+    H, G = plans.H, 4 * plans.H
+    dev = X.device
+    st = ops._stream()
+    # biases of both sets -> [8H]
+    bkey = (ops._wkey(br_ih, br_hh), ops._wkey(bi_ih, bi_hh))
+    ent = plans.cache.get("bias8")
+    if ent is not None and ent[0] == bkey:
+        bias8 = ent[1]
+    else:
+        bias8 = torch.empty(2 * G, dtype=torch.float32, device=dev)
+        call("clskd_pack_gather", br_ih.data_ptr(), br_hh.data_ptr(), plans.bias.data_ptr(), G,
+             bias8.data_ptr(), 0, st)
+        call("clskd_pack_gather", bi_ih.data_ptr(), bi_hh.data_ptr(), plans.bias.data_ptr(), G,
+             bias8.data_ptr() + 4 * G, 0, st)
+        plans.cache["bias8"] = (bkey, bias8)
+    # input projections for both sets: rows (p,t,b) -> pre [2, T, B, 8H]
+    pre = torch.empty((P, T, B, 2 * G), dtype=torch.float32, device=dev)
+    run_tapconv(X.view(1, P * T, B, D), None, D, 0, 1, P * T, B, P * T, B, plans.ih.fwd[0], wr_ih, wi_ih,
+                bias8, pre.view(1, P * T, B, 2 * G))
+    whh_t = ops.packed_weights(plans.cache, "whh_t", lambda: plans.whh_t, wr_hh, wi_hh, torch.float32)
+    h = torch.empty((2, P, T, B, H), dtype=torch.float32, device=dev)
+    gates = torch.empty((2, P, T, B, G), dtype=torch.float32, device=dev) if train else None
+    c = torch.empty((2, P, T, B, H), dtype=torch.float32, device=dev) if train else None
+    if state is None:
+        call("clskd_lstm_fwd", pre.data_ptr(), whh_t.data_ptr(), T, P * B, B, H, 2,
+             T * B * 2 * G, B * 2 * G, 2 * G, G, H * G, 1 if w_bf16 else 0,
+             h.data_ptr(), ops._ptr(gates), ops._ptr(c), st)
+    else:
+        hs, cs = state["h"], state["c"]
+        assert hs.shape == (2, P * B, H) and cs.shape == (2, P * B, H) and hs.is_contiguous() and cs.is_contiguous()
+        call("clskd_lstm_fwd_state", pre.data_ptr(), whh_t.data_ptr(), T, P * B, B, H, 2,
+             T * B * 2 * G, B * 2 * G, 2 * G, G, H * G, 1 if w_bf16 else 0,
+             h.data_ptr(), ops._ptr(gates), ops._ptr(c), hs.data_ptr(), cs.data_ptr(), hs.data_ptr(), cs.data_ptr(), st)
+    # combine: real = rr - ii = h[set0, part0] - h[set1, part1]; imag = ir + ri = h[0,1] + h[1,0]
+    Y = torch.empty((2, T, B, H), dtype=torch.float32, device=dev)
+    n = T * B * H
+    call("clskd_axpby_f32", h[0, 0].data_ptr(), h[1, 1].data_ptr(), 1.0, -1.0, Y[0].data_ptr(), n, st)
+    call("clskd_axpby_f32", h[0, 1].data_ptr(), h[1, 0].data_ptr(), 1.0, 1.0, Y[1].data_ptr(), n, st)
+    return Y, h, gates, c
+
+
 class ComplexLSTMLayerFn(torch.autograd.Function):
     """X [2, T, B, D] -> Y [2, T, B, H] (Y[0] = rr - ii, Y[1] = ir + ri)."""
 
     @staticmethod
     def forward(ctx, plans: _ClstmPlans, X, wr_ih, wr_hh, br_ih, br_hh, wi_ih, wi_hh, bi_ih, bi_hh, w_bf16):
-        P, T, B, D = X.shape
-        H, G = plans.H, 4 * plans.H
-        dev = X.device
-        st = ops._stream()
         f = ops._f32c
         wr_ih, wr_hh, br_ih, br_hh = f(wr_ih), f(wr_hh), f(br_ih), f(br_hh)
         wi_ih, wi_hh, bi_ih, bi_hh = f(wi_ih), f(wi_hh), f(bi_ih), f(bi_hh)
-        # biases of both sets -> [8H]
-        bkey = (ops._wkey(br_ih, br_hh), ops._wkey(bi_ih, bi_hh))
-        ent = plans.cache.get("bias8")
-        if ent is not None and ent[0] == bkey:
-            bias8 = ent[1]
-        else:
-            bias8 = torch.empty(2 * G, dtype=torch.float32, device=dev)
-            call("clskd_pack_gather", br_ih.data_ptr(), br_hh.data_ptr(), plans.bias.data_ptr(), G,
-                 bias8.data_ptr(), 0, st)
-            call("clskd_pack_gather", bi_ih.data_ptr(), bi_hh.data_ptr(), plans.bias.data_ptr(), G,
-                 bias8.data_ptr() + 4 * G, 0, st)
-            plans.cache["bias8"] = (bkey, bias8)
-        # input projections for both sets: rows (p,t,b) -> pre [2, T, B, 8H]
-        pre = torch.empty((P, T, B, 2 * G), dtype=torch.float32, device=dev)
-        run_tapconv(X.view(1, P * T, B, D), None, D, 0, 1, P * T, B, P * T, B, plans.ih.fwd[0], wr_ih, wi_ih,
-                    bias8, pre.view(1, P * T, B, 2 * G))
-        whh_t = ops.packed_weights(plans.cache, "whh_t", lambda: plans.whh_t, wr_hh, wi_hh, torch.float32)
         train = any(ctx.needs_input_grad)   # False under torch.no_grad()
-        h = torch.empty((2, P, T, B, H), dtype=torch.float32, device=dev)
-        gates = torch.empty((2, P, T, B, G), dtype=torch.float32, device=dev) if train else None
-        c = torch.empty((2, P, T, B, H), dtype=torch.float32, device=dev) if train else None
-        call("clskd_lstm_fwd", pre.data_ptr(), whh_t.data_ptr(), T, P * B, B, H, 2,
-             T * B * 2 * G, B * 2 * G, 2 * G, G, H * G, 1 if w_bf16 else 0,
-             h.data_ptr(), ops._ptr(gates), ops._ptr(c), st)
-        # combine: real = rr - ii = h[set0, part0] - h[set1, part1]; imag = ir + ri = h[0,1] + h[1,0]
-        Y = torch.empty((2, T, B, H), dtype=torch.float32, device=dev)
-        n = T * B * H
-        call("clskd_axpby_f32", h[0, 0].data_ptr(), h[1, 1].data_ptr(), 1.0, -1.0, Y[0].data_ptr(), n, st)
-        call("clskd_axpby_f32", h[0, 1].data_ptr(), h[1, 0].data_ptr(), 1.0, 1.0, Y[1].data_ptr(), n, st)
+        Y, h, gates, c = _clstm_forward(plans, X, wr_ih, wr_hh, br_ih, br_hh, wi_ih, wi_hh, bi_ih, bi_hh, w_bf16,
+                                        train, None)
+        P, T, B, D = X.shape
         ctx.plans = plans
         ctx.save_for_backward(X, wr_ih, wi_ih, wr_hh, wi_hh, h, gates, c)
         ctx.dims = (P, T, B, D)
@@ -254,6 +272,24 @@ class NavieComplexLSTM(nn.Module):
                                      ops.policy.name == "bf16")
         if self.projection_dim is not None:
             Y = _project2(self, Y)
+        return Y
+
+    def new_state(self, batch, device):
+        """zero (h, c) of the four LSTM passes for `batch` utterances: [2 weight sets][2 parts * batch][H]"""
+        z = lambda: torch.zeros((2, 2 * batch, self.rnn_units), dtype=torch.float32, device=device)
+        return {"h": z(), "c": z()}
+
+    def forward_stacked_state(self, X, state):
+        """Inference with a carried recurrent state (no autograd): X dense [2, T, B, D] -> Y like forward_stacked;
+        `state` (new_state) is advanced in place, so consecutive time chunks reproduce the whole-sequence output."""
+        f = ops._f32c
+        r, i = self.real_lstm, self.imag_lstm
+        with torch.no_grad():
+            Y, _, _, _ = _clstm_forward(self._get_plans(X.device), X, f(r.weight_ih_l0), f(r.weight_hh_l0),
+                                        f(r.bias_ih_l0), f(r.bias_hh_l0), f(i.weight_ih_l0), f(i.weight_hh_l0),
+                                        f(i.bias_ih_l0), f(i.bias_hh_l0), ops.policy.name == "bf16", False, state)
+            if self.projection_dim is not None:
+                Y = _project2(self, Y)
         return Y
 
     def forward(self, inputs):

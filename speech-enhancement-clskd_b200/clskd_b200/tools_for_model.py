@@ -83,6 +83,14 @@ class ConvSTFT(nn.Module):
             return spec.view(spec.shape[0], spec.shape[1], -1, 2)
         return spec
 
+    def spectrum_padded(self, xpad, interleaved=True):
+        """spectrum of an ALREADY padded signal [B, n]: frames start at 0, win_inc, ... (streaming inference cuts
+        frame ranges out of one padded utterance instead of padding every chunk)"""
+        spec = FramedGemmFn.apply(self._plan(interleaved), self.weight.view(-1), xpad, self.win_len, self.stride)
+        if interleaved:
+            return spec.view(spec.shape[0], spec.shape[1], -1, 2)
+        return spec
+
     def forward(self, inputs):
         outputs = self.spectrum(inputs, interleaved=False).permute(0, 2, 1)
         if self.feature_type == 'complex':

@@ -26,7 +26,8 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
                                 int T, int R, int Bp, int H, int64_t pre_pstride,
                                 int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride,
                                 int64_t whh_set_stride, float* __restrict__ h_out,
-                                float* __restrict__ gates_out, float* __restrict__ c_out) {
+                                float* __restrict__ gates_out, float* __restrict__ c_out,
+                                const float* h0, const float* c0, float* hN, float* cN) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int G = 4 * H;
   const int j = threadIdx.x;  // hidden unit
@@ -58,11 +59,15 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
       w_b[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
     }
   }
-#pragma unroll
-  for (int r = 0; r < RBF; ++r) h_s[j * RBF + r] = 0.f;
+  // initial state [nsets][R][H] (streaming inference carries it across time chunks); zero when NULL
+  const int64_t st_set = (int64_t)set * R * H;
   float c_state[RBF];
 #pragma unroll
-  for (int r = 0; r < RBF; ++r) c_state[r] = 0.f;
+  for (int r = 0; r < RBF; ++r) {
+    const bool ok = r0 + r < R;
+    h_s[j * RBF + r] = (h0 && ok) ? h0[st_set + (int64_t)(r0 + r) * H + j] : 0.f;
+    c_state[r] = (c0 && ok) ? c0[st_set + (int64_t)(r0 + r) * H + j] : 0.f;
+  }
 
   // pre-activation addresses of (row r, gate g, unit j) without the time term
   int64_t prow[RBF];
@@ -154,6 +159,12 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ pre, const float* __re
 #pragma unroll
       for (int g = 0; g < 4; ++g) pcur[r][g] = pnext[r][g];
   }
+#pragma unroll
+  for (int r = 0; r < RBF; ++r)
+    if (r0 + r < R) {
+      if (hN) hN[st_set + (int64_t)(r0 + r) * H + j] = h_s[(T & 1) * H * RBF + j * RBF + r];
+      if (cN) cN[st_set + (int64_t)(r0 + r) * H + j] = c_state[r];
+    }
 }
 
 // Same recurrence with TWO threads per hidden unit (threads 2j, 2j+1): each contracts half of the k
@@ -166,7 +177,8 @@ __global__ void lstm_fwd_ks2_kernel(const float* __restrict__ pre, const float* 
                                     int T, int R, int Bp, int H, int64_t pre_pstride,
                                     int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride,
                                     int64_t whh_set_stride, float* __restrict__ h_out,
-                                    float* __restrict__ gates_out, float* __restrict__ c_out) {
+                                    float* __restrict__ gates_out, float* __restrict__ c_out,
+                                    const float* h0, const float* c0, float* hN, float* cN) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int RH = RBF / 2;
   const int G = 4 * H;
@@ -193,13 +205,14 @@ __global__ void lstm_fwd_ks2_kernel(const float* __restrict__ pre, const float* 
       w_b[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
     }
   }
-#pragma unroll
-  for (int r = 0; r < RH; ++r) h_s[j * RBF + half * RH + r] = 0.f;
+  const int64_t st_set = (int64_t)set * R * H;
   float c_state[RH];
   int64_t prow[RH], orow[RH];
 #pragma unroll
   for (int r = 0; r < RH; ++r) {
-    c_state[r] = 0.f;
+    const bool ok = r0 + r < R;
+    h_s[j * RBF + half * RH + r] = (h0 && ok) ? h0[st_set + (int64_t)(r0 + r) * H + j] : 0.f;
+    c_state[r] = (c0 && ok) ? c0[st_set + (int64_t)(r0 + r) * H + j] : 0.f;
     const int rr = min(r0 + r, R - 1);
     prow[r] = (int64_t)(rr / Bp) * pre_pstride + (int64_t)(rr % Bp) * pre_ld + j;
     orow[r] = (int64_t)(rr / Bp) * T * Bp + (rr % Bp);
@@ -293,6 +306,12 @@ __global__ void lstm_fwd_ks2_kernel(const float* __restrict__ pre, const float* 
 #pragma unroll
       for (int g = 0; g < 4; ++g) pcur[r][g] = pnext[r][g];
   }
+#pragma unroll
+  for (int r = 0; r < RH; ++r)
+    if (r0 + r < R) {
+      if (hN) hN[st_set + (int64_t)(r0 + r) * H + j] = h_s[(T & 1) * H * RBF + j * RBF + half * RH + r];
+      if (cN) cN[st_set + (int64_t)(r0 + r) * H + j] = c_state[r];
+    }
 }
 
 // BPTT.  Thread tid = (q, k): phase A treats it as cell (row q, unit k); phase B as the partial
@@ -399,6 +418,15 @@ extern "C" int clskd_lstm_fwd(const float* pre, const float* whh_t, int T, int R
                               int nsets, int64_t pre_pstride, int64_t pre_tstride, int64_t pre_ld,
                               int64_t pre_set_stride, int64_t whh_set_stride, int w_bf16, float* h,
                               float* gates, float* c, void* stream) {
+  return clskd_lstm_fwd_state(pre, whh_t, T, R, Bp, H, nsets, pre_pstride, pre_tstride, pre_ld, pre_set_stride,
+                              whh_set_stride, w_bf16, h, gates, c, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int clskd_lstm_fwd_state(const float* pre, const float* whh_t, int T, int R, int Bp, int H,
+                                    int nsets, int64_t pre_pstride, int64_t pre_tstride, int64_t pre_ld,
+                                    int64_t pre_set_stride, int64_t whh_set_stride, int w_bf16, float* h,
+                                    float* gates, float* c, const float* h0, const float* c0, float* hN,
+                                    float* cN, void* stream) {
   CLSKD_CHECK_ARG(pre && whh_t && h, "clskd_lstm_fwd: null pointer");
   CLSKD_CHECK_ARG(H >= 4 && H % 4 == 0 && H <= 1024, "clskd_lstm_fwd: H=%d unsupported (4..1024, multiple of 4)", H);
   CLSKD_CHECK_ARG(T >= 0 && R >= 1 && nsets >= 1 && Bp >= 1 && R % Bp == 0, "clskd_lstm_fwd: bad extents");
@@ -411,7 +439,7 @@ extern "C" int clskd_lstm_fwd(const float* pre, const float* whh_t, int T, int R
   dim3 grid(cdiv(R, rb2 ? 2 : 4), nsets);
   const bool ks2 = 2 * H <= 1024;      // two threads per hidden unit (k range split in halves)
   cudaError_t e;
-#define LSTM_FWD_ARGS pre, whh_t, T, R, Bp, H, pre_pstride, pre_tstride, pre_ld, pre_set_stride, whh_set_stride, h, gates, c
+#define LSTM_FWD_ARGS pre, whh_t, T, R, Bp, H, pre_pstride, pre_tstride, pre_ld, pre_set_stride, whh_set_stride, h, gates, c, h0, c0, hN, cN
   if (!w_bf16 && base + w32 <= kSmemLimit) {
     e = cudaFuncSetAttribute(lstm_fwd_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + w32));

@@ -647,6 +647,13 @@ class EmuLib:
 
     # ------------------------------------------------------------------ LSTM
     def clskd_lstm_fwd(self, pre, whh_t, T, R, Bp, H, nsets, pps, pts, pld, pss, wss, w_bf16, h, gates, c, stream):
+        return self.clskd_lstm_fwd_state(pre, whh_t, T, R, Bp, H, nsets, pps, pts, pld, pss, wss, w_bf16, h, gates, c,
+                                         None, None, None, None, stream)
+
+    def clskd_lstm_fwd_state(self, pre, whh_t, T, R, Bp, H, nsets, pps, pts, pld, pss, wss, w_bf16, h, gates, c,
+                             h0, c0, hN, cN, stream):
+        if T == 0:
+            return 0
         G = 4 * H
         P = R // Bp
         sig = lambda v: 1.0 / (1.0 + np.exp(-v))
@@ -657,8 +664,8 @@ class EmuLib:
             W = _arr(whh_t + 4 * s * wss, H * G).reshape(H, G).astype(np.float64)
             for p in range(P):
                 Pre = _strided(pre + 4 * (s * pss + p * pps), (T, Bp, G), (pts, pld, 1)).astype(np.float64)
-                hh = np.zeros((Bp, H))
-                cc = np.zeros((Bp, H))
+                hh = _arr(h0, nsets * R * H).reshape(nsets, P, Bp, H)[s, p].astype(np.float64) if h0 else np.zeros((Bp, H))
+                cc = _arr(c0, nsets * R * H).reshape(nsets, P, Bp, H)[s, p].astype(np.float64) if c0 else np.zeros((Bp, H))
                 for t in range(T):
                     g_ = Pre[t] + hh @ W
                     i_, f_, gg, o_ = sig(g_[:, :H]), sig(g_[:, H:2 * H]), np.tanh(g_[:, 2 * H:3 * H]), sig(g_[:, 3 * H:])
@@ -669,6 +676,10 @@ class EmuLib:
                         Gt[s, p, t] = np.concatenate([i_, f_, gg, o_], 1)
                     if Ct is not None:
                         Ct[s, p, t] = cc
+                if hN:
+                    _arr(hN, nsets * R * H).reshape(nsets, P, Bp, H)[s, p] = hh
+                if cN:
+                    _arr(cN, nsets * R * H).reshape(nsets, P, Bp, H)[s, p] = cc
         return 0
 
     def clskd_lstm_bwd(self, dh_out, whh, gates, c, T, R, Bp, H, nsets, wss, pps, pts, pld, pss, dpre, stream):

@@ -102,6 +102,23 @@ def main():
         out["teacher_" + tmode] = tap_rec(*t_taps[tmode])
         print("teacher", tmode, float(t_taps[tmode][0].abs().max()))
 
+    # eval-mode teacher whose BatchNorm running statistics MATCH the data (what a trained teacher has): one
+    # train-mode pass with momentum 1 sets running_mean / running_var to the batch statistics; stored so that
+    # the tests load exactly these buffers
+    teacher.load_state_dict(t_sd)
+    bns = [m for m in teacher.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for m in bns:
+        m.momentum = 1.0
+    teacher.train()
+    with torch.no_grad():
+        teacher(X)
+    for m in bns:
+        m.momentum = 0.1
+    out["teacher_cal_running"] = {k: v.clone() for k, v in teacher.state_dict().items() if "running_" in k}
+    teacher.eval()
+    out["teacher_eval_cal"] = tap_rec(*taps(teacher, False))
+    print("teacher eval (calibrated running stats)", float(out["teacher_eval_cal"]["wav"].abs().max()))
+
     for sname, scfg in STUDENTS.items():
         student, s_sd = build(scfg, SEEDS["student"])
         rec = {"s_sd_sum": {k: summ(s_sd[k], 16) for k in ("encoder.3.0.real_conv.weight", "decoder.1.0.imag_conv.weight")}}

@@ -811,3 +811,25 @@ def test_dccrn_with_complex_batch_norm_runs(dev):
         out = m(0.1 * torch.randn(2, 1600, generator=torch.Generator().manual_seed(0)).to(dev))
     assert out[-1].shape == (2, 1600) and torch.isfinite(out[-1]).all()
     assert out[0].shape == (2, 257, 19)
+
+
+@pytest.mark.parametrize("L,chunk", [(6000, 16), (9037, 23), (4100, 30)])
+def test_streaming_inference_equals_whole_utterance(dev, L, chunk):
+    """Time-chunked streaming inference (carried LSTM state, 1-frame encoder halo, 6-frame decoder look-ahead,
+    3-frame overlap-add halo) reproduces the whole-utterance forward and the oracle (fp32: <= 1e-5)."""
+    from oracle import dccrn_oracle as D
+    kn, ru = [4, 8, 8, 16, 16, 16], 16
+    sd = D.make_state_dict(kn, ru, seed=21)
+    m = _build(dict(kernel_num=kn, rnn_units=ru), sd, dev)
+    m.eval()
+    x = 0.1 * torch.randn(3, L, generator=torch.Generator().manual_seed(L))
+    with torch.no_grad():
+        ref = D.dccrn_forward(sd, x)[-1]
+        whole = m(x.to(dev), is_feat=True)
+        stream = m.enhance_streaming(x.to(dev), chunk_frames=chunk)
+    assert stream.shape == whole.shape == ref.shape
+    assert (stream.cpu() - whole.cpu()).abs().max().item() < 1e-5
+    assert (stream.cpu() - ref).abs().max().item() < 1e-5
+    m.train()
+    with pytest.raises(RuntimeError):
+        m.enhance_streaming(x.to(dev), chunk_frames=chunk)
