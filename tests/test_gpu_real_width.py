@@ -387,3 +387,32 @@ def test_bf16_fused_conv_epilogue_vs_oracle(cuda_dev, kind, cin, cout, F, T, B, 
     if mode == "train":
         assert torch.allclose(blk[1].running_mean.cpu(), rm, rtol=2e-3, atol=2e-4)
         assert torch.allclose(blk[1].running_var.cpu(), rv, rtol=4e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("policy,tol", [("fp32", 1e-5), ("bf16", 1e-3)])
+def test_streaming_inference_60s_equals_whole_utterance(cuda_dev, policy, tol):
+    """BASELINE configs[4] path: 60 s utterances (T = 9603 frames) enhanced in 400-frame chunks with carried LSTM
+    state and halo frames equal the whole-utterance forward; activation memory is bounded by the chunk."""
+    import clskd_b200
+    clskd_b200.set_precision(policy)
+    cfg = dict(kernel_num=[16, 32, 64, 128, 128, 128], rnn_units=128)
+    m = _model(cfg, 5, cuda_dev).eval()
+    x = (0.1 * torch.randn(2, 960000, generator=torch.Generator().manual_seed(9))).to(cuda_dev)
+    with torch.no_grad():
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        whole = m(x, is_feat=True)
+        mem_whole = torch.cuda.max_memory_allocated() - base
+        torch.cuda.synchronize()
+        del_whole = whole.float().cpu()
+        del whole
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        stream = m.enhance_streaming(x, chunk_frames=400)
+        mem_stream = torch.cuda.max_memory_allocated() - base
+    err = (stream.float().cpu() - del_whole).abs().max().item()
+    LOG.add("streaming_60s/" + policy, max_abs=err, mem_whole_gb=mem_whole / 2 ** 30, mem_stream_gb=mem_stream / 2 ** 30)
+    assert stream.shape == del_whole.shape == (2, 960000)
+    assert err <= tol, err
+    assert mem_stream < 0.25 * mem_whole, (mem_stream, mem_whole)
