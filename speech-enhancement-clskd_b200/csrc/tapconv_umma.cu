@@ -4,19 +4,33 @@
 //   Y[b,to,fo,n] = bias[n] + sum_j sum_c X[b, to+dt[j], fo*sf+df[j], c] * W[j][n][c]
 //
 // One CTA computes a 128 x BLOCK_N output tile: the 128 rows are a (t_tile x fo_tile) patch of one
-// utterance, so that for every tap the A operand is ONE TMA box of the channels-last activation
-// tensor viewed as the 5-D tensor (C, f-parity, F/sf, T, B); the tap only shifts the box
-// coordinates, and frequency/time zero padding (and the ragged last time tile) come for free from
-// TMA out-of-bounds zero fill.  The skip connection of the decoder is a second tensor map that
-// supplies the upper K range (no materialised concat).  B is the packed block weight
-// [tap][n][c] (K-major).  Both operands land in 128/64/32-byte swizzled K-major shared memory and
-// are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16 per instruction) issued by one thread.
+// utterance, so that the A operand of a tap is a box of the channels-last activation tensor viewed as the
+// 5-D tensor (C, f-parity, F/sf, T, B); frequency/time zero padding (and the ragged last time tile) come
+// for free from TMA out-of-bounds zero fill.  The skip connection of the decoder is a second tensor map
+// that supplies the upper K range (no materialised concat).  B is the packed block weight
+// [tap][n][c] (K-major).  Both operands land in 128/64/32-byte swizzled K-major shared memory and are
+// consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16 per instruction) issued by one thread.
 //
-// Persistent: one CTA per SM loops over its tiles.  Warp roles (192 threads): warp 0 = TMA
-// producer (runs ahead across tiles through the shared-memory ring), warp 1 = TMEM allocator + MMA
-// issuer, warps 2-5 = epilogue (tcgen05.ld -> bias -> bf16/fp32 -> global).  The accumulator is
-// double-buffered in TMEM (2 x BLOCK_N <= 512 columns), so the epilogue of tile i overlaps the main
-// loop of tile i+1, and barrier/TMEM set-up is paid once per CTA instead of once per tile.
+// Operand reuse (the kernel is bound by the L2 -> shared-memory fill rate, not by the tensor pipe):
+//   * HALO PATCHES.  Taps are grouped; a group loads ONE activation patch per K chunk and every tap of the
+//     group is issued from a shifted shared-memory descriptor instead of its own TMA box.  tcgen05 applies
+//     the swizzle XOR to the absolute shared-memory address, so a descriptor start that is shifted by whole
+//     rows (not a multiple of the 1024-byte pattern) reads exactly the shifted rows of a canonically
+//     swizzled patch with matrix-base-offset 0 (measured: profiles/r02_hw_desc_shift.log).
+//       - full mode (fo_tile = 128, stride 1): one (t_tile+tspan) x (128+fspan) patch serves all taps
+//         (3x3: 390 rows instead of 9 x 128);
+//       - time mode (any tile): taps that differ only in dt share a (t_tile+tspan) x fo_tile patch; the
+//         shift is a multiple of fo_tile rows;
+//       - legacy mode: one box per tap.
+//   * RESIDENT WEIGHTS.  When the whole packed weight of the launch fits next to the pipeline it is loaded
+//     once per persistent CTA and the ring carries activation patches only.
+//
+// Persistent: one CTA per SM (two when TMEM / shared memory allow) loops over its tiles.  Warp roles
+// (192 threads): warp 0 = TMA producer (runs ahead across tiles through the shared-memory ring), warp 1 =
+// TMEM allocator + MMA issuer, warps 2-5 = epilogue (tcgen05.ld -> bias / folded BatchNorm / PReLU ->
+// bf16/fp32 -> swizzled staging -> TMA store, batch statistics from the staged tile).  The accumulator is
+// double-buffered in TMEM (2 x BLOCK_N <= 512 columns), so the epilogue of tile i overlaps the main loop of
+// tile i+1.
 #include "umma.cuh"
 
 namespace clskd {
@@ -25,6 +39,12 @@ using namespace umma;
 
 constexpr int UM = 128;       // UMMA M
 constexpr int kThreads = 192;
+constexpr int kMaxEpN = 256;  // epilogue constants staged in shared memory up to this N
+
+// tuning overrides (clskd_set_tuning): 0 = automatic
+int g_tune_mode = 0;       // 1 legacy (one box per tap), 2 time-grouped patches, 3 full halo patch where possible
+int g_tune_resident = 0;   // 1 never keep the weights resident, 2 always when they fit
+int g_tune_two_cta = 0;    // 1 force one CTA per SM, 2 force two when possible
 
 struct UmmaParams {
   int B, To, Fo;
@@ -32,12 +52,19 @@ struct UmmaParams {
   int block_n, block_k;
   int chunks0, chunks_tot;  // K chunks of source 0 / total per tap
   int ntaps;
-  int tap_t[CLSKD_MAX_TAPS];   // time offset
-  int tap_p[CLSKD_MAX_TAPS];   // parity coordinate (df mod sf)
-  int tap_f[CLSKD_MAX_TAPS];   // floor(df / sf)
+  // tap groups: taps [grp_beg[g], grp_beg[g+1]) (group order) share the patch whose box origin is shifted by
+  // (grp_p, grp_f, grp_t) from the tile origin; tap_aoff = byte offset of the tap's 128-row A tile in the patch
+  int ngroups, maxg;
+  int grp_beg[CLSKD_MAX_TAPS + 1];
+  int grp_p[CLSKD_MAX_TAPS], grp_f[CLSKD_MAX_TAPS], grp_t[CLSKD_MAX_TAPS];
+  uint32_t tap_aoff[CLSKD_MAX_TAPS];
+  int tap_w[CLSKD_MAX_TAPS];   // tap coordinate in the weight tensor map
   int stages;
-  uint32_t a_bytes, b_bytes;   // per stage, padded to 1024
-  uint32_t tx_bytes;           // bytes actually delivered per stage
+  uint32_t a_bytes, b_bytes;   // patch / weight tile, padded to 1024
+  uint32_t a_tx, b_tx;         // bytes actually delivered
+  uint32_t stage_bytes;        // a_bytes + maxg * b_bytes (resident: a_bytes)
+  int resident;                // whole weight resident in shared memory
+  uint32_t bres_off;           // its offset from the ring base
   uint32_t sbo;                // stride byte offset >> 4
   uint32_t layout_type;        // UMMA smem layout type (2 = SW128, 4 = SW64, 6 = SW32)
   uint32_t tmem_cols;
@@ -50,8 +77,8 @@ struct UmmaParams {
   // epilogue staging for the TMA store: sub-tiles of gw_y columns, [128 rows][gw_y] each, swizzled
   int gw_y, es;                // columns per sub-tile, bytes per output element
   uint32_t y_sub_bytes;        // 128 * gw_y * es
-  uint32_t stage_region;       // bytes of the operand ring (staging buffers follow it)
-  uint32_t staging_bytes;      // one staging buffer: 128 rows x block_n x es
+  uint32_t stg_off;            // offset of the staging buffers from the ring base
+  uint32_t staging_bytes;      // one staging buffer: 128 rows x ecols x es
   int nstg;                    // 1 or 2 staging buffers (double-buffered TMA stores)
   int ecols;                   // columns staged per TMA-store round (<= 128): block_n / ecols rounds per tile
   // fused epilogue (see ClskdTapConv): folded eval BatchNorm, PReLU, batch statistics of the stored outputs
@@ -61,6 +88,27 @@ struct UmmaParams {
   double* stats_sum;
   double* stats_sumsq;
 };
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // EP = false: plain contraction (+bias); EP = true: the fused epilogue variants (kept out of the plain
 // instantiation so that it stays at its lean register count)
@@ -74,13 +122,15 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __shared__ __align__(8) uint64_t empty_bar[8];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float ep_c[3][kMaxEpN];   // bias, scale, shift of the (single) n tile
 
   // 1024-byte aligned operand ring
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~(uintptr_t)1023);
-  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool ep_smem = p.N <= kMaxEpN;       // then tiles_n == 1 or n0 + c < N <= kMaxEpN anyway
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -91,20 +141,34 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 128);     // every epilogue thread arrives
     }
+    mbar_init(&bres_bar, 1);
     fence_barrier_init();
+  }
+  if (ep_smem) {
+    for (int i = threadIdx.x; i < p.N; i += kThreads) {
+      ep_c[0][i] = p.bias ? __ldg(p.bias + i) : 0.f;
+      ep_c[1][i] = (EP && p.ep_scale) ? __ldg(p.ep_scale + i) : 1.f;
+      ep_c[2][i] = (EP && p.ep_shift) ? __ldg(p.ep_shift + i) : 0.f;
+    }
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int num_k = p.ntaps * p.chunks_tot;
 
   // persistent: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (n tile fastest, so
   // consecutive CTAs share the activation patch in L2)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (p.resident) {
+        mbar_expect_tx(&bres_bar, (uint32_t)(p.ntaps * p.chunks_tot) * p.b_tx);
+        uint8_t* dst = ring + p.bres_off;
+        for (int j = 0; j < p.ntaps; ++j)
+          for (int ch = 0; ch < p.chunks_tot; ++ch)
+            tma_load_3d(dst + (size_t)(j * p.chunks_tot + ch) * p.b_bytes, &tmB, &bres_bar, ch * p.block_k, 0, p.tap_w[j]);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -115,21 +179,25 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int t_blk = r % p.t_tiles;
         const int b = r / p.t_tiles;
         const int t0 = t_blk * p.t_tile, f0 = f_blk * p.fo_tile, n0 = n_tile * p.block_n;
-        for (int it = 0; it < num_k; ++it) {
-          const int tap = it / p.chunks_tot;
-          const int ch = it - tap * p.chunks_tot;
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], p.tx_bytes);
-          uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
-          uint8_t* b_dst = a_dst + p.a_bytes;
+        for (int ch = 0; ch < p.chunks_tot; ++ch) {
           const bool src0 = ch < p.chunks0;
           const int cc = (src0 ? ch : ch - p.chunks0) * p.block_k;
-          tma_load_5d(a_dst, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.tap_p[tap],
-                      f0 + p.tap_f[tap], t0 + p.tap_t[tap], b);
-          tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * p.block_k, n0, tap);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
+          for (int g = 0; g < p.ngroups; ++g) {
+            const int jb = p.grp_beg[g], je = p.grp_beg[g + 1];
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_expect_tx(&full_bar[stage], p.a_tx + (p.resident ? 0u : (uint32_t)(je - jb) * p.b_tx));
+            uint8_t* a_dst = ring + (size_t)stage * p.stage_bytes;
+            tma_load_5d(a_dst, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.grp_p[g], f0 + p.grp_f[g],
+                        t0 + p.grp_t[g], b);
+            if (!p.resident) {
+              uint8_t* b_dst = a_dst + p.a_bytes;
+              for (int j = jb; j < je; ++j)
+                tma_load_3d(b_dst + (size_t)(j - jb) * p.b_bytes, &tmB, &full_bar[stage], ch * p.block_k, n0, p.tap_w[j]);
+            }
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
       }
@@ -143,28 +211,42 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       const int ksteps = p.block_k / 16;
+      const uint32_t ring_addr = smem_u32(ring);
+      if (p.resident) {
+        mbar_wait(&bres_bar, 0);
+        fence_after();
+      }
       int local = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
         const int as = local & 1;
         mbar_wait(&tmem_empty_bar[as], ((local >> 1) & 1) ^ 1u);   // epilogue drained this accumulator
         fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)(as * p.block_n);
-        for (int it = 0; it < num_k; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          fence_after();
-          const uint32_t a_addr = smem_u32(ring + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_bytes;
-          const uint64_t adesc = make_smem_desc(a_addr, p.sbo, p.layout_type);
-          const uint64_t bdesc = make_smem_desc(b_addr, p.sbo, p.layout_type);
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
-            umma_bf16(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                      (it | k) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
+        uint32_t first = 0;
+        for (int ch = 0; ch < p.chunks_tot; ++ch) {
+          for (int g = 0; g < p.ngroups; ++g) {
+            mbar_wait(&full_bar[stage], phase);
+            fence_after();
+            const uint32_t a_addr = ring_addr + (uint32_t)stage * p.stage_bytes;
+            for (int j = p.grp_beg[g]; j < p.grp_beg[g + 1]; ++j) {
+              // the tap's A tile: the patch rows shifted by tap_aoff (matrix base offset stays 0: the swizzle
+              // XOR is a function of the absolute shared-memory address)
+              const uint64_t adesc = make_smem_desc(a_addr + p.tap_aoff[j], p.sbo, p.layout_type);
+              const uint32_t b_addr = p.resident
+                                          ? ring_addr + p.bres_off + (uint32_t)(j * p.chunks_tot + ch) * p.b_bytes
+                                          : a_addr + p.a_bytes + (uint32_t)(j - p.grp_beg[g]) * p.b_bytes;
+              const uint64_t bdesc = make_smem_desc(b_addr, p.sbo, p.layout_type);
+              for (int k = 0; k < ksteps; ++k) {
+                // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
+                umma_bf16(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first);
+                first = 1u;
+              }
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
         umma_commit(&tmem_full_bar[as]);
@@ -176,20 +258,23 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // global write is a full coalesced box; rows beyond To are clipped by the tensor map.
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;        // row of the 128-row tile
-    uint8_t* stg_base = ring + p.stage_region;
+    uint8_t* stg_base = ring + p.stg_off;
     const uint32_t pitch = (uint32_t)(p.gw_y * p.es);          // 128 / 64 / 32 bytes
     const uint32_t xr = pitch == 128 ? (uint32_t)(row & 7) : (pitch == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1));
     const bool issuer = (threadIdx.x == 64);                    // first epilogue thread
     const float ep_slope = (EP && p.ep_slope) ? __ldg(p.ep_slope) : 1.f;
-    // batch statistics: thread et owns column (et % ecols) of every staging round and the row slice
-    // [part*ecols, (part+1)*ecols) of the 128-row tile; partial sums stay in registers across all
-    // tiles of this persistent CTA (tiles_n == 1, <= 2 rounds) and are flushed once at the end.
-    // (A 16-byte-per-thread read-back was measured slower: 138 registers instead of 115.)
+    const bool has_bias = p.bias != nullptr, has_aff = EP && p.ep_scale != nullptr, has_slope = EP && p.ep_slope != nullptr;
+    // batch statistics: thread et owns the column PAIR (2*st_pr, 2*st_pr+1) of every staging round and the rows
+    // st_part, st_part + nparts, ... of the 128-row tile (32-bit reads of the staged bf16 tile: consecutive lanes
+    // read consecutive words of one row); partial sums stay in registers across all tiles of this persistent CTA
+    // (tiles_n == 1, <= 2 rounds) and are flushed once at the end.
     const int et = threadIdx.x - 64;
-    const int st_col = et % p.ecols, st_part = et / p.ecols;
-    float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f;
+    const int npairs = p.ecols >> 1, nparts = 128 / npairs;
+    const int st_pr = et % npairs, st_part = et / npairs;
+    float st_s[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, st_q[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     int local = 0;
     int sround = 0;                                             // staging rounds issued so far
+    const int cw = (p.ecols % 32 == 0) ? 32 : 16;               // accumulator columns per tcgen05.ld
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const int n_tile = tile % p.tiles_n;
@@ -212,42 +297,72 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int cbeg = rd * p.ecols;
-        for (int c = cbeg; c < cbeg + p.ecols; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c), v);
-          float o[16];
+        for (int c = cbeg; c < cbeg + p.ecols; c += cw) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c);
+          if (cw == 32) tmem_ld32_nowait(taddr, v);
+          else tmem_ld16_nowait(taddr, v);
+          tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
-          if (p.bias) {
+          for (int h = 0; h < 2; ++h) {
+            if (h * 16 < cw) {
+              float o[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
-          }
-          if (EP && p.ep_scale) {
+              for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[h * 16 + e]);
+              const int cc = c + h * 16;              // first of these 16 columns inside the n tile
+              if (ep_smem) {
+                const float4* cb = reinterpret_cast<const float4*>(&ep_c[0][n0 + cc]);
+                const float4* cs = reinterpret_cast<const float4*>(&ep_c[1][n0 + cc]);
+                const float4* ch = reinterpret_cast<const float4*>(&ep_c[2][n0 + cc]);
+                if (has_bias) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] = fmaf(o[e], __ldg(p.ep_scale + n0 + c + e), __ldg(p.ep_shift + n0 + c + e));
-          }
-          if (EP && p.ep_slope) {
+                  for (int e4 = 0; e4 < 4; ++e4) {
+                    const float4 bb = cb[e4];
+                    o[4 * e4] += bb.x; o[4 * e4 + 1] += bb.y; o[4 * e4 + 2] += bb.z; o[4 * e4 + 3] += bb.w;
+                  }
+                }
+                if (has_aff) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] = o[e] > 0.f ? o[e] : o[e] * ep_slope;
-          }
-          const int cl = c - cbeg;
-          const int sub = cl / p.gw_y, col = cl - sub * p.gw_y;
-          uint8_t* rowp = stg + (size_t)sub * p.y_sub_bytes + (size_t)row * pitch;
-          const uint32_t ch0 = (uint32_t)(col * p.es) >> 4;          // first 16-byte chunk of these 16 columns
-          if (p.es == 2) {
-            uint32_t pk[8];
+                  for (int e4 = 0; e4 < 4; ++e4) {
+                    const float4 s4 = cs[e4], h4 = ch[e4];
+                    o[4 * e4] = fmaf(o[4 * e4], s4.x, h4.x); o[4 * e4 + 1] = fmaf(o[4 * e4 + 1], s4.y, h4.y);
+                    o[4 * e4 + 2] = fmaf(o[4 * e4 + 2], s4.z, h4.z); o[4 * e4 + 3] = fmaf(o[4 * e4 + 3], s4.w, h4.w);
+                  }
+                }
+              } else {
+                if (has_bias) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                  for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + cc + e);
+                }
+                if (has_aff) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) o[e] = fmaf(o[e], __ldg(p.ep_scale + n0 + cc + e), __ldg(p.ep_shift + n0 + cc + e));
+                }
+              }
+              if (has_slope) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o[e] = o[e] > 0.f ? o[e] : o[e] * ep_slope;
+              }
+              const int cl = cc - cbeg;
+              const int sub = cl / p.gw_y, col = cl - sub * p.gw_y;
+              uint8_t* rowp = stg + (size_t)sub * p.y_sub_bytes + (size_t)row * pitch;
+              const uint32_t ch0 = (uint32_t)(col * p.es) >> 4;          // first 16-byte chunk of these 16 columns
+              if (p.es == 2) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ xr) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ xr) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  *reinterpret_cast<float4*>(rowp + (((ch0 + e) ^ xr) << 4)) =
+                      make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+              }
             }
-            *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ xr) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ xr) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              *reinterpret_cast<float4*>(rowp + (((ch0 + e) ^ xr) << 4)) =
-                  make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
           }
         }
         if (rd == rounds - 1) {
@@ -270,32 +385,37 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         if (EP && p.stats_sum) {
           // column sums of the staged (bf16-rounded) tile over its valid rows, read back from the swizzled
-          // staging buffer (consecutive threads read consecutive columns of one row: conflict free); the
-          // buffer is not rewritten before every epilogue thread has passed the next round's barriers
+          // staging buffer while the TMA store is in flight; the buffer is not rewritten before every epilogue
+          // thread has passed the next round's barriers
           int nvalid = (p.To - t0) * p.fo_tile;
           if (nvalid > UM) nvalid = UM;
-          const int sub = st_col / p.gw_y, cl = st_col - sub * p.gw_y;
-          const uint8_t* colp = stg + (size_t)sub * p.y_sub_bytes + ((cl * 2) & 15);
-          const uint32_t chk = (uint32_t)(cl * 2) >> 4;
-          int rend = (st_part + 1) * p.ecols;
-          if (rend > nvalid) rend = nvalid;
-          float s = 0.f, q = 0.f;
-          for (int rr = st_part * p.ecols; rr < rend; ++rr) {
+          const int cl = 2 * st_pr;
+          const int sub = cl / p.gw_y, col = cl - sub * p.gw_y;
+          const uint8_t* colp = stg + (size_t)sub * p.y_sub_bytes + ((col * 2) & 15);
+          const uint32_t chk = (uint32_t)(col * 2) >> 4;
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+          for (int rr = st_part; rr < nvalid; rr += nparts) {
             const uint32_t x2 = pitch == 128 ? (uint32_t)(rr & 7) : (pitch == 64 ? (uint32_t)((rr >> 1) & 3) : (uint32_t)((rr >> 2) & 1));
-            const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + (size_t)rr * pitch + ((chk ^ x2) << 4)));
-            s += v;
-            q = fmaf(v, v, q);
+            const uint32_t w2 = *reinterpret_cast<const uint32_t*>(colp + (size_t)rr * pitch + ((chk ^ x2) << 4));
+            const float va = __uint_as_float(w2 << 16), vb = __uint_as_float(w2 & 0xffff0000u);
+            s0 += va;
+            q0 = fmaf(va, va, q0);
+            s1 += vb;
+            q1 = fmaf(vb, vb, q1);
           }
-          if (rd == 0) { st_s0 += s; st_q0 += q; } else { st_s1 += s; st_q1 += q; }
+          st_s[rd & 1][0] += s0; st_q[rd & 1][0] += q0;
+          st_s[rd & 1][1] += s1; st_q[rd & 1][1] += q1;
         }
       }
     }
     if (EP && p.stats_sum) {
-      atomicAdd(p.stats_sum + st_col, (double)st_s0);
-      atomicAdd(p.stats_sumsq + st_col, (double)st_q0);
-      if (p.block_n > p.ecols) {
-        atomicAdd(p.stats_sum + p.ecols + st_col, (double)st_s1);
-        atomicAdd(p.stats_sumsq + p.ecols + st_col, (double)st_q1);
+      const int rounds = p.block_n / p.ecols;
+      for (int rd = 0; rd < rounds; ++rd) {
+        const int c0 = rd * p.ecols + 2 * st_pr;
+        atomicAdd(p.stats_sum + c0, (double)st_s[rd][0]);
+        atomicAdd(p.stats_sumsq + c0, (double)st_q[rd][0]);
+        atomicAdd(p.stats_sum + c0 + 1, (double)st_s[rd][1]);
+        atomicAdd(p.stats_sumsq + c0 + 1, (double)st_q[rd][1]);
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
@@ -341,12 +461,32 @@ const char* umma_unsupported(const ClskdTapConv* d) {
   return nullptr;
 }
 
+// channels-last activation as the 5-D tensor (C, f-parity, Fi/sf, Ti, B) with an arbitrary (fp x tp) patch box
+int encode_act_patch(EncodeTiledFn enc, CUtensorMap* tm, const void* x, int C, int sf, int Fi, int Ti, int B, int64_t sB,
+                     int64_t sT, int64_t sF, int block_k, int fp, int tp, CUtensorMapSwizzle sw) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)sf, (cuuint64_t)(Fi / sf), (cuuint64_t)Ti, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)sF * 2, (cuuint64_t)sF * 2 * sf, (cuuint64_t)sT * 2, (cuuint64_t)sB * 2};
+  cuuint32_t box[5] = {(cuuint32_t)block_k, 1, (cuuint32_t)fp, (cuuint32_t)tp, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return (int)enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 }  // namespace
 }  // namespace clskd
 
 using namespace clskd;
 
 extern "C" int clskd_has_tcgen05(void) { return 1; }
+
+extern "C" int clskd_set_tuning(int key, int value) {
+  switch (key) {
+    case 0: g_tune_mode = value; return CLSKD_OK;
+    case 1: g_tune_resident = value; return CLSKD_OK;
+    case 2: g_tune_two_cta = value; return CLSKD_OK;
+    default: set_error("clskd_set_tuning: unknown key %d", key); return CLSKD_ERR_ARG;
+  }
+}
 
 extern "C" int clskd_tapconv_umma_supported(const ClskdTapConv* d) {
   if (!d) return 0;
@@ -383,17 +523,82 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   p.chunks0 = d->c0 / bk;
   p.chunks_tot = Ctot / bk;
   p.ntaps = d->ntaps;
+  const uint32_t pitch_a = (uint32_t)bk * 2;                 // bytes per patch row (= swizzle span)
+
+  // ---- tap geometry: (time offset, parity, floor(df / sf))
+  int tt[CLSKD_MAX_TAPS], tp_[CLSKD_MAX_TAPS], tf[CLSKD_MAX_TAPS];
+  int tmin = 1 << 30, tmax = -(1 << 30), fmin = 1 << 30, fmax = -(1 << 30);
   for (int j = 0; j < d->ntaps; ++j) {
     int df = d->df[j];
     int fl = df >= 0 ? df / d->sf : -((-df + d->sf - 1) / d->sf);  // floor division
-    p.tap_t[j] = d->dt[j];
-    p.tap_f[j] = fl;
-    p.tap_p[j] = df - fl * d->sf;
+    tt[j] = d->dt[j];
+    tf[j] = fl;
+    tp_[j] = df - fl * d->sf;
+    tmin = tt[j] < tmin ? tt[j] : tmin; tmax = tt[j] > tmax ? tt[j] : tmax;
+    fmin = fl < fmin ? fl : fmin; fmax = fl > fmax ? fl : fmax;
   }
+  // ---- grouping mode
+  int mode = 1;
+  const bool full_ok = d->sf == 1 && p.fo_tile == UM && d->ntaps > 1 && (UM + (fmax - fmin)) <= 256 &&
+                       (p.t_tile + (tmax - tmin)) <= 16;
+  const bool time_ok = d->ntaps > 1 && (p.fo_tile % 8 == 0) && (p.t_tile + (tmax - tmin)) * p.fo_tile <= 1024;
+  if (full_ok) mode = 3;
+  else if (time_ok && p.t_tile > 1 && tmax > tmin) mode = 2;
+  if (g_tune_mode == 1) mode = 1;
+  if (g_tune_mode == 2) mode = time_ok ? 2 : 1;
+  if (g_tune_mode == 3) mode = full_ok ? 3 : (time_ok && p.t_tile > 1 && tmax > tmin ? 2 : 1);
+  int box_f = p.fo_tile, box_t = p.t_tile;
+  auto build_groups = [&](int md) {
+    box_f = p.fo_tile;
+    box_t = p.t_tile;
+    if (md == 3) {
+      box_f = UM + (fmax - fmin);
+      box_t = p.t_tile + (tmax - tmin);
+      p.ngroups = 1;
+      p.grp_beg[0] = 0; p.grp_beg[1] = d->ntaps;
+      p.grp_p[0] = 0; p.grp_f[0] = fmin; p.grp_t[0] = tmin;
+      for (int j = 0; j < d->ntaps; ++j) {
+        p.tap_w[j] = j;
+        p.tap_aoff[j] = (uint32_t)((tt[j] - tmin) * box_f + (tf[j] - fmin)) * pitch_a;
+      }
+    } else if (md == 2) {
+      box_t = p.t_tile + (tmax - tmin);
+      bool used[CLSKD_MAX_TAPS] = {false};
+      int n = 0;
+      p.ngroups = 0;
+      for (int j = 0; j < d->ntaps; ++j) {
+        if (used[j]) continue;
+        const int g = p.ngroups++;
+        p.grp_beg[g] = n;
+        p.grp_p[g] = tp_[j]; p.grp_f[g] = tf[j]; p.grp_t[g] = tmin;
+        for (int i = j; i < d->ntaps; ++i)
+          if (!used[i] && tp_[i] == tp_[j] && tf[i] == tf[j]) {
+            used[i] = true;
+            p.tap_w[n] = i;
+            p.tap_aoff[n] = (uint32_t)((tt[i] - tmin) * box_f) * pitch_a;
+            ++n;
+          }
+      }
+      p.grp_beg[p.ngroups] = n;
+    } else {
+      p.ngroups = d->ntaps;
+      for (int j = 0; j < d->ntaps; ++j) {
+        p.grp_beg[j] = j;
+        p.grp_p[j] = tp_[j]; p.grp_f[j] = tf[j]; p.grp_t[j] = tt[j];
+        p.tap_w[j] = j;
+        p.tap_aoff[j] = 0;
+      }
+      p.grp_beg[d->ntaps] = d->ntaps;
+    }
+    p.maxg = 0;
+    for (int g = 0; g < p.ngroups; ++g) {
+      const int n = p.grp_beg[g + 1] - p.grp_beg[g];
+      p.maxg = n > p.maxg ? n : p.maxg;
+    }
+  };
   auto pad1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
-  p.a_bytes = pad1k((uint32_t)UM * bk * 2);
-  p.b_bytes = pad1k((uint32_t)p.block_n * bk * 2);
-  p.tx_bytes = (uint32_t)UM * bk * 2 + (uint32_t)p.block_n * bk * 2;
+  p.b_tx = (uint32_t)p.block_n * pitch_a;
+  p.b_bytes = pad1k(p.b_tx);
   p.sbo = (uint32_t)(8 * bk * 2) >> 4;
   CUtensorMapSwizzle sw;
   if (bk == 64) { p.layout_type = 2; sw = CU_TENSOR_MAP_SWIZZLE_128B; }
@@ -409,34 +614,57 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   int cols = 32;
   while (cols < 2 * p.block_n) cols <<= 1;     // double-buffered accumulator
   p.tmem_cols = (uint32_t)cols;
-  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-  p.ecols = p.block_n > 128 ? 128 : p.block_n;     // block_n is 256 or <= 128 here... (256 = 2 rounds)
+  p.ecols = p.block_n > 128 ? 128 : p.block_n;     // block_n is 256 or <= 128 here (256 = 2 rounds)
   if (p.block_n % p.ecols) p.ecols = p.block_n;
   const uint32_t staging_bytes = (uint32_t)UM * p.ecols * p.es;
   p.staging_bytes = staging_bytes;
-  // two CTAs per SM when the accumulators (2 x 2 x block_n TMEM columns) and ~110 KB of smem each
-  // allow it: their serial per-tile latencies (TMA -> MMA -> TMEM drain -> store) overlap
-  const bool two_ctas = 2 * cols <= 512 && staging_bytes <= 32 * 1024;
-  const uint32_t budget = two_ctas ? 108u * 1024u : 222u * 1024u;
-  p.nstg = (2 * staging_bytes + 2 * stage_bytes <= budget) ? 2 : 1;
-  int stages = (int)((budget - p.nstg * staging_bytes) / stage_bytes);
-  if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
-  const int num_k = p.ntaps * p.chunks_tot;
-  // (the ring runs ahead across tiles of the persistent loop, so it is not limited by num_k)
+  const uint32_t w_bytes = (uint32_t)(d->ntaps * p.chunks_tot) * p.b_bytes;
+  const uint32_t kSmemMax = 226u * 1024u;
+  bool resident = false, two_ctas = false;
+  uint32_t fixed = 0;
+  int stages = 0;
+  for (;;) {
+    build_groups(mode);
+    p.a_tx = (uint32_t)box_f * box_t * pitch_a;
+    p.a_bytes = pad1k(p.a_tx);
+    // resident weights: the whole packed weight next to the pipeline (single n tile), leaving room for two
+    // patch stages and one staging buffer
+    resident = p.tiles_n == 1 && w_bytes <= 100u * 1024u && w_bytes + 2 * p.a_bytes + staging_bytes + 2048 <= kSmemMax;
+    if (g_tune_resident == 1) resident = false;
+    p.resident = resident ? 1 : 0;
+    p.stage_bytes = p.a_bytes + (resident ? 0u : (uint32_t)p.maxg * p.b_bytes);
+    fixed = resident ? w_bytes : 0u;
+    // two CTAs per SM when the accumulators (2 x 2 x block_n TMEM columns) and ~110 KB of smem each
+    // allow it: their serial per-tile latencies (TMA -> MMA -> TMEM drain -> store) overlap
+    two_ctas = 2 * cols <= 512 && staging_bytes <= 32 * 1024 &&
+               fixed + 2 * p.stage_bytes + staging_bytes + 1024 <= 108u * 1024u;
+    if (g_tune_two_cta == 1) two_ctas = false;
+    const uint32_t budget = two_ctas ? 108u * 1024u : kSmemMax;
+    p.nstg = (fixed + 2 * staging_bytes + 2 * p.stage_bytes + 1024 <= budget) ? 2 : 1;
+    stages = (int)((budget - 1024 - fixed - p.nstg * staging_bytes) / p.stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages >= 2) break;
+    if (mode == 1) {
+      set_error("clskd_tapconv_fwd_umma: tile does not fit shared memory (stage %u B, weights %u B)", p.stage_bytes, fixed);
+      return CLSKD_ERR_UNSUPPORTED;
+    }
+    mode = 1;        // patches do not fit: one box per tap
+  }
   p.stages = stages;
+  p.bres_off = (uint32_t)stages * p.stage_bytes;
+  p.stg_off = p.bres_off + fixed;
   p.y = d->y; p.y_sB = d->y_sB; p.y_sT = d->y_sT; p.y_sF = d->y_sF; p.y_dtype = d->y_dtype;
   p.bias = d->bias; p.N = d->N;
   p.ep_scale = d->ep_scale; p.ep_shift = d->ep_shift; p.ep_slope = d->ep_slope;
   p.stats_sum = d->stats_sum; p.stats_sumsq = d->stats_sumsq;
 
   CUtensorMap tmA0, tmA1, tmB;
-  int rc = encode_act(enc, &tmA0, d->x0, d->c0, d->sf, d->Fi, d->Ti, d->B, d->x0_sB, d->x0_sT,
-                      d->x0_sF, bk, p.fo_tile, p.t_tile, sw);
+  int rc = encode_act_patch(enc, &tmA0, d->x0, d->c0, d->sf, d->Fi, d->Ti, d->B, d->x0_sB, d->x0_sT,
+                            d->x0_sF, bk, box_f, box_t, sw);
   if (rc) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(x0) failed: %d", rc); return CLSKD_ERR_CUDA; }
   if (d->c1) {
-    rc = encode_act(enc, &tmA1, d->x1, d->c1, d->sf, d->Fi, d->Ti, d->B, d->x1_sB, d->x1_sT,
-                    d->x1_sF, bk, p.fo_tile, p.t_tile, sw);
+    rc = encode_act_patch(enc, &tmA1, d->x1, d->c1, d->sf, d->Fi, d->Ti, d->B, d->x1_sB, d->x1_sT,
+                          d->x1_sF, bk, box_f, box_t, sw);
     if (rc) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(x1) failed: %d", rc); return CLSKD_ERR_CUDA; }
   } else {
     tmA1 = tmA0;
@@ -454,7 +682,6 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   const int64_t tiles = (int64_t)d->B * p.t_tiles * p.f_tiles * p.tiles_n;
   CLSKD_CHECK_ARG(tiles <= 2147483647LL, "clskd_tapconv_fwd_umma: too many tiles");
   p.num_tiles = (int)tiles;
-  p.stage_region = (uint32_t)stages * stage_bytes;
   CUtensorMap tmY;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->Fo, (cuuint64_t)d->To, (cuuint64_t)d->B};
@@ -466,7 +693,7 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(y) failed: %d", (int)r); return CLSKD_ERR_CUDA; }
   }
-  size_t smem = (size_t)stages * stage_bytes + (size_t)p.nstg * staging_bytes + 1024;
+  size_t smem = (size_t)p.stg_off + (size_t)p.nstg * staging_bytes + 1024;
   const bool ep = d->ep_scale || d->ep_slope || d->stats_sum;
   static size_t smem_set[2] = {0, 0};
   if (smem > smem_set[ep ? 1 : 0]) {

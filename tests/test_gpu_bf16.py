@@ -426,3 +426,36 @@ def test_abf_rank2_mid_stage_vs_stored_z1_path(cuda_dev, mid, F, T, B, up):
     for k in ("dw1", "dgamma", "dbeta", "dwatt", "rmean"):
         s = max(b[k].abs().max().item(), 1e-6)
         assert (a[k] - b[k]).abs().max().item() < 2e-2 * s, k
+
+
+@pytest.mark.parametrize("cin,cout,F,T,B,ks", [(32, 64, 128, 9, 2, 3), (128, 32, 256, 5, 1, 3), (16, 128, 128, 7, 2, 1),
+                                              (64, 48, 128, 6, 1, 3), (64, 128, 32, 21, 2, 3), (128, 256, 8, 70, 2, 3)])
+@pytest.mark.parametrize("tune", [(0, 0), (1, 1), (2, 1), (3, 1), (3, 0)])
+def test_umma_operand_reuse_modes_vs_torch(cuda_dev, cin, cout, F, T, B, ks, tune):
+    """halo-patch / time-grouped / per-tap operand loading and resident weights of the tcgen05 forward kernel
+    (clskd_set_tuning) against torch's conv2d on bf16-representable operands, fp32 output (fp32 accumulation only)"""
+    import clskd_b200
+    from clskd_b200 import _lib
+    from clskd_b200 import framework as fw
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(cin + F + ks)
+    conv = fw.RealConv2d(cin, cout, ks, padding=ks // 2, bias=True)
+    _round_params(conv)
+    x = torch.randn(B, cin, F, T, generator=g).bfloat16().float()
+    ref = torch.nn.functional.conv2d(x, conv.weight, conv.bias, padding=ks // 2)
+    conv = conv.to(cuda_dev)
+    xp = x.permute(0, 3, 2, 1).contiguous().to(cuda_dev).bfloat16()
+    lib = _lib.load()
+    try:
+        lib.clskd_set_tuning(0, tune[0])
+        lib.clskd_set_tuning(1, tune[1])
+        with torch.no_grad():
+            clskd_b200.set_precision("bf16")
+            n0 = ops.umma_launches
+            y = conv.forward_phys(xp, out_dtype=torch.float32)
+            assert ops.umma_launches == n0 + 1
+    finally:
+        lib.clskd_set_tuning(0, 0)
+        lib.clskd_set_tuning(1, 0)
+    y = y.permute(0, 3, 2, 1).cpu()
+    assert (y - ref).abs().max().item() < 2e-5 * max(ref.abs().max().item(), 1.0)
