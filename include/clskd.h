@@ -99,8 +99,11 @@ int clskd_tapconv_umma_supported(const ClskdTapConv* d);
 /* Tuning overrides of the tcgen05 forward kernel for A/B measurements (tools/kbench.py); value 0 = automatic.
  *   key 0: operand-reuse mode (1 one TMA box per tap, 2 time-grouped patches, 3 full halo patch where possible)
  *   key 1: 1 = never keep the packed weight resident in shared memory
- *   key 2: 1 = one CTA per SM */
+ *   key 2: 1 = one CTA per SM
+ *   key 3: 1 = route clskd_tapconv_fwd_umma to the round-1 kernel (clskd_tapconv_fwd_umma_v1) */
 int clskd_set_tuning(int key, int value);
+/* the round-1 forward kernel (one TMA box per tap, weights through the ring): A/B baseline only */
+int clskd_tapconv_fwd_umma_v1(const ClskdTapConv* d, void* stream);
 
 /* weight gradient of the same contraction:
  *   dW[j][c][n] = sum_{b,to,fo} X[b,to+dt[j],fo*sf+df[j],c] * dY[b,to,fo,n]     (fp32 out)

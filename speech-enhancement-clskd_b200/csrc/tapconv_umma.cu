@@ -45,6 +45,7 @@ constexpr int kMaxEpN = 256;  // epilogue constants staged in shared memory up t
 int g_tune_mode = 0;       // 1 legacy (one box per tap), 2 time-grouped patches, 3 full halo patch where possible
 int g_tune_resident = 0;   // 1 never keep the weights resident, 2 always when they fit
 int g_tune_two_cta = 0;    // 1 force one CTA per SM, 2 force two when possible
+int g_tune_v1 = 0;         // 1 route to the round-1 kernel
 
 struct UmmaParams {
   int B, To, Fo;
@@ -484,6 +485,7 @@ extern "C" int clskd_set_tuning(int key, int value) {
     case 0: g_tune_mode = value; return CLSKD_OK;
     case 1: g_tune_resident = value; return CLSKD_OK;
     case 2: g_tune_two_cta = value; return CLSKD_OK;
+    case 3: g_tune_v1 = value; return CLSKD_OK;
     default: set_error("clskd_set_tuning: unknown key %d", key); return CLSKD_ERR_ARG;
   }
 }
@@ -502,6 +504,7 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   }
   const int64_t M = (int64_t)d->B * d->To * d->Fo;
   if (M == 0) return CLSKD_OK;
+  if (g_tune_v1) return clskd_tapconv_fwd_umma_v1(d, stream);
   EncodeTiledFn enc = get_encode();
   const int Ctot = d->c0 + d->c1;
 
@@ -619,7 +622,7 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   const uint32_t staging_bytes = (uint32_t)UM * p.ecols * p.es;
   p.staging_bytes = staging_bytes;
   const uint32_t w_bytes = (uint32_t)(d->ntaps * p.chunks_tot) * p.b_bytes;
-  const uint32_t kSmemMax = 226u * 1024u;
+  const uint32_t kSmemMax = 222u * 1024u;     // 227 KB per CTA minus the static shared memory (epilogue constants, barriers)
   bool resident = false, two_ctas = false;
   uint32_t fixed = 0;
   int stages = 0;
@@ -637,9 +640,9 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
     // two CTAs per SM when the accumulators (2 x 2 x block_n TMEM columns) and ~110 KB of smem each
     // allow it: their serial per-tile latencies (TMA -> MMA -> TMEM drain -> store) overlap
     two_ctas = 2 * cols <= 512 && staging_bytes <= 32 * 1024 &&
-               fixed + 2 * p.stage_bytes + staging_bytes + 1024 <= 108u * 1024u;
+               fixed + 2 * p.stage_bytes + staging_bytes + 1024 <= 106u * 1024u;
     if (g_tune_two_cta == 1) two_ctas = false;
-    const uint32_t budget = two_ctas ? 108u * 1024u : kSmemMax;
+    const uint32_t budget = two_ctas ? 106u * 1024u : kSmemMax;
     p.nstg = (fixed + 2 * staging_bytes + 2 * p.stage_bytes + 1024 <= budget) ? 2 : 1;
     stages = (int)((budget - 1024 - fixed - p.nstg * staging_bytes) / p.stage_bytes);
     if (stages > 8) stages = 8;

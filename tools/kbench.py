@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--variants", default=None, help="comma-separated subset of variant names")
+    ap.add_argument("--shapes", default=None, help="comma-separated shape indices")
     a = ap.parse_args()
     from clskd_b200 import _lib
     lib = _lib.load()
@@ -63,11 +65,16 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    variants = [("legacy", (1, 1)), ("legacy+resident", (1, 0)), ("time", (2, 1)), ("time+resident", (2, 0)),
+    variants = [("v1", (0, 0, 0, 1)), ("legacy", (1, 1)), ("legacy+res", (1, 0)), ("time", (2, 1)), ("time+res", (2, 0)),
                 ("full", (3, 1)), ("auto", (0, 0)), ("auto 1cta", (0, 0, 1))]
+    if a.variants:
+        variants = [v for v in variants if v[0] in a.variants.split(",")]
     results = []
     st = torch.cuda.current_stream().cuda_stream
-    for name, B, T, F, C, N, kind, stats in (SHAPES[:4] if a.quick else SHAPES):
+    shapes = SHAPES[:4] if a.quick else SHAPES
+    if a.shapes:
+        shapes = [SHAPES[int(i)] for i in a.shapes.split(",")]
+    for name, B, T, F, C, N, kind, stats in shapes:
         taps, sf = taps_of(kind)
         Fo = F // sf
         g = torch.Generator(device="cpu").manual_seed(1)
@@ -101,6 +108,7 @@ def main():
             lib.clskd_set_tuning(0, tune[0])
             lib.clskd_set_tuning(1, tune[1])
             lib.clskd_set_tuning(2, tune[2] if len(tune) > 2 else 0)
+            lib.clskd_set_tuning(3, tune[3] if len(tune) > 3 else 0)
             try:
                 for i in range(3):
                     d.x0 = xs[i % 3].data_ptr()
@@ -129,7 +137,8 @@ def main():
                                           "max_rel_diff_vs_legacy": err, "stats_rel_diff": serr}
             except RuntimeError as e:
                 row["variants"][vname] = {"error": str(e)[:200]}
-        lib.clskd_set_tuning(0, 0); lib.clskd_set_tuning(1, 0); lib.clskd_set_tuning(2, 0)
+        for k in range(4):
+            lib.clskd_set_tuning(k, 0)
         results.append(row)
         print("%-38s floor %.3f ms | " % (name, row["floor_ms"]) + " | ".join(
             "%s %.3f%s" % (k, v.get("ms", -1), "" if v.get("max_rel_diff_vs_legacy", 0) < 2e-2 else " !!DIFF %.2g" % v["max_rel_diff_vs_legacy"])
