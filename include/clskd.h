@@ -100,10 +100,17 @@ int clskd_tapconv_umma_supported(const ClskdTapConv* d);
  *   key 0: operand-reuse mode (1 one TMA box per tap, 2 time-grouped patches, 3 full halo patch where possible)
  *   key 1: 1 = never keep the packed weight resident in shared memory
  *   key 2: 1 = one CTA per SM
- *   key 3: 1 = route clskd_tapconv_fwd_umma to the round-1 kernel (clskd_tapconv_fwd_umma_v1) */
+ *   key 3: 1 = route clskd_tapconv_fwd_umma to the round-1 kernel (clskd_tapconv_fwd_umma_v1)
+ *   key 4: 1 = one TMA box per patch, 2 = one TMA box per time row of the patch
+ *   key 5: 1 = disable the per-shape autotuner.  Without a forced configuration the first call for a shape
+ *          signature (>= 65536 rows) times a handful of candidate configurations on the caller's tensors
+ *          (device-wide synchronisation, once per shape and process) and caches the fastest; also disabled by
+ *          the environment variable CLSKD_AUTOTUNE=0. */
 int clskd_set_tuning(int key, int value);
 /* the round-1 forward kernel (one TMA box per tap, weights through the ring): A/B baseline only */
 int clskd_tapconv_fwd_umma_v1(const ClskdTapConv* d, void* stream);
+/* diagnostics: shapes tuned so far / how many of them kept the round-1 kernel */
+int clskd_tuning_stats(int* n_shapes, int* n_v1);
 
 /* weight gradient of the same contraction:
  *   dW[j][c][n] = sum_{b,to,fo} X[b,to+dt[j],fo*sf+df[j],c] * dY[b,to,fo,n]     (fp32 out)

@@ -31,6 +31,11 @@
 // bf16/fp32 -> swizzled staging -> TMA store, batch statistics from the staged tile).  The accumulator is
 // double-buffered in TMEM (2 x BLOCK_N <= 512 columns), so the epilogue of tile i overlaps the main loop of
 // tile i+1.
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace clskd {
@@ -46,6 +51,18 @@ int g_tune_mode = 0;       // 1 legacy (one box per tap), 2 time-grouped patches
 int g_tune_resident = 0;   // 1 never keep the weights resident, 2 always when they fit
 int g_tune_two_cta = 0;    // 1 force one CTA per SM, 2 force two when possible
 int g_tune_v1 = 0;         // 1 route to the round-1 kernel
+int g_tune_split = 0;      // 1 one TMA box per patch, 2 one box per time row of the patch (more loads in flight)
+int g_tune_noauto = 0;     // 1 disable the per-shape autotuner (first-call timing of the candidate configurations)
+
+// one launch configuration of the forward kernel (0 = automatic for every field)
+struct FwdCfg {
+  int v1;        // round-1 kernel
+  int mode;      // 1 one box per tap, 2 time-grouped patches, 3 full halo patch where possible
+  int resident;  // 1 never keep the weights resident
+  int two_cta;   // 1 one CTA per SM
+  int split;     // 1 one TMA box per patch, 2 one per time row
+  int bk_cap;    // cap of the K chunk (32: smaller stages, two CTAs per SM fit more often)
+};
 
 struct UmmaParams {
   int B, To, Fo;
@@ -63,6 +80,9 @@ struct UmmaParams {
   int stages;
   uint32_t a_bytes, b_bytes;   // patch / weight tile, padded to 1024
   uint32_t a_tx, b_tx;         // bytes actually delivered
+  int a_nbox;                  // the patch is loaded as a_nbox boxes of a_box_t time rows each (a_box_bytes apart)
+  int a_box_t;
+  uint32_t a_box_bytes;
   uint32_t stage_bytes;        // a_bytes + maxg * b_bytes (resident: a_bytes)
   int resident;                // whole weight resident in shared memory
   uint32_t bres_off;           // its offset from the ring base
@@ -125,14 +145,11 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float ep_c[3][kMaxEpN];   // bias, scale, shift of the (single) n tile
 
   // 1024-byte aligned operand ring
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                              ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool ep_smem = p.N <= kMaxEpN;       // then tiles_n == 1 or n0 + c < N <= kMaxEpN anyway
-
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -144,13 +161,6 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     mbar_init(&bres_bar, 1);
     fence_barrier_init();
-  }
-  if (ep_smem) {
-    for (int i = threadIdx.x; i < p.N; i += kThreads) {
-      ep_c[0][i] = p.bias ? __ldg(p.bias + i) : 0.f;
-      ep_c[1][i] = (EP && p.ep_scale) ? __ldg(p.ep_scale + i) : 1.f;
-      ep_c[2][i] = (EP && p.ep_shift) ? __ldg(p.ep_shift + i) : 0.f;
-    }
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
   fence_before();
@@ -188,8 +198,9 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_expect_tx(&full_bar[stage], p.a_tx + (p.resident ? 0u : (uint32_t)(je - jb) * p.b_tx));
             uint8_t* a_dst = ring + (size_t)stage * p.stage_bytes;
-            tma_load_5d(a_dst, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.grp_p[g], f0 + p.grp_f[g],
-                        t0 + p.grp_t[g], b);
+            for (int bx = 0; bx < p.a_nbox; ++bx)
+              tma_load_5d(a_dst + (size_t)bx * p.a_box_bytes, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.grp_p[g],
+                          f0 + p.grp_f[g], t0 + p.grp_t[g] + bx * p.a_box_t, b);
             if (!p.resident) {
               uint8_t* b_dst = a_dst + p.a_bytes;
               for (int j = jb; j < je; ++j)
@@ -264,18 +275,15 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t xr = pitch == 128 ? (uint32_t)(row & 7) : (pitch == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1));
     const bool issuer = (threadIdx.x == 64);                    // first epilogue thread
     const float ep_slope = (EP && p.ep_slope) ? __ldg(p.ep_slope) : 1.f;
-    const bool has_bias = p.bias != nullptr, has_aff = EP && p.ep_scale != nullptr, has_slope = EP && p.ep_slope != nullptr;
-    // batch statistics: thread et owns the column PAIR (2*st_pr, 2*st_pr+1) of every staging round and the rows
-    // st_part, st_part + nparts, ... of the 128-row tile (32-bit reads of the staged bf16 tile: consecutive lanes
-    // read consecutive words of one row); partial sums stay in registers across all tiles of this persistent CTA
-    // (tiles_n == 1, <= 2 rounds) and are flushed once at the end.
+    // batch statistics: thread et owns column (et % ecols) of every staging round and the row slice
+    // [part*ecols, (part+1)*ecols) of the 128-row tile; partial sums stay in registers across all
+    // tiles of this persistent CTA (tiles_n == 1, <= 2 rounds) and are flushed once at the end.
+    // (A 16-byte-per-thread read-back was measured slower: 138 registers instead of 115.)
     const int et = threadIdx.x - 64;
-    const int npairs = p.ecols >> 1, nparts = 128 / npairs;
-    const int st_pr = et % npairs, st_part = et / npairs;
-    float st_s[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, st_q[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    const int st_col = et % p.ecols, st_part = et / p.ecols;
+    float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f;
     int local = 0;
     int sround = 0;                                             // staging rounds issued so far
-    const int cw = (p.ecols % 32 == 0) ? 32 : 16;               // accumulator columns per tcgen05.ld
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const int n_tile = tile % p.tiles_n;
@@ -298,72 +306,42 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int cbeg = rd * p.ecols;
-        for (int c = cbeg; c < cbeg + p.ecols; c += cw) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c);
-          if (cw == 32) tmem_ld32_nowait(taddr, v);
-          else tmem_ld16_nowait(taddr, v);
-          tmem_wait_ld();
+        for (int c = cbeg; c < cbeg + p.ecols; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c), v);
+          float o[16];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h * 16 < cw) {
-              float o[16];
+          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+          if (p.bias) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[h * 16 + e]);
-              const int cc = c + h * 16;              // first of these 16 columns inside the n tile
-              if (ep_smem) {
-                const float4* cb = reinterpret_cast<const float4*>(&ep_c[0][n0 + cc]);
-                const float4* cs = reinterpret_cast<const float4*>(&ep_c[1][n0 + cc]);
-                const float4* ch = reinterpret_cast<const float4*>(&ep_c[2][n0 + cc]);
-                if (has_bias) {
+            for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
+          }
+          if (EP && p.ep_scale) {
 #pragma unroll
-                  for (int e4 = 0; e4 < 4; ++e4) {
-                    const float4 bb = cb[e4];
-                    o[4 * e4] += bb.x; o[4 * e4 + 1] += bb.y; o[4 * e4 + 2] += bb.z; o[4 * e4 + 3] += bb.w;
-                  }
-                }
-                if (has_aff) {
+            for (int e = 0; e < 16; ++e) o[e] = fmaf(o[e], __ldg(p.ep_scale + n0 + c + e), __ldg(p.ep_shift + n0 + c + e));
+          }
+          if (EP && p.ep_slope) {
 #pragma unroll
-                  for (int e4 = 0; e4 < 4; ++e4) {
-                    const float4 s4 = cs[e4], h4 = ch[e4];
-                    o[4 * e4] = fmaf(o[4 * e4], s4.x, h4.x); o[4 * e4 + 1] = fmaf(o[4 * e4 + 1], s4.y, h4.y);
-                    o[4 * e4 + 2] = fmaf(o[4 * e4 + 2], s4.z, h4.z); o[4 * e4 + 3] = fmaf(o[4 * e4 + 3], s4.w, h4.w);
-                  }
-                }
-              } else {
-                if (has_bias) {
+            for (int e = 0; e < 16; ++e) o[e] = o[e] > 0.f ? o[e] : o[e] * ep_slope;
+          }
+          const int cl = c - cbeg;
+          const int sub = cl / p.gw_y, col = cl - sub * p.gw_y;
+          uint8_t* rowp = stg + (size_t)sub * p.y_sub_bytes + (size_t)row * pitch;
+          const uint32_t ch0 = (uint32_t)(col * p.es) >> 4;          // first 16-byte chunk of these 16 columns
+          if (p.es == 2) {
+            uint32_t pk[8];
 #pragma unroll
-                  for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + cc + e);
-                }
-                if (has_aff) {
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) o[e] = fmaf(o[e], __ldg(p.ep_scale + n0 + cc + e), __ldg(p.ep_shift + n0 + cc + e));
-                }
-              }
-              if (has_slope) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) o[e] = o[e] > 0.f ? o[e] : o[e] * ep_slope;
-              }
-              const int cl = cc - cbeg;
-              const int sub = cl / p.gw_y, col = cl - sub * p.gw_y;
-              uint8_t* rowp = stg + (size_t)sub * p.y_sub_bytes + (size_t)row * pitch;
-              const uint32_t ch0 = (uint32_t)(col * p.es) >> 4;          // first 16-byte chunk of these 16 columns
-              if (p.es == 2) {
-                uint32_t pk[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-                }
-                *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ xr) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ xr) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  *reinterpret_cast<float4*>(rowp + (((ch0 + e) ^ xr) << 4)) =
-                      make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
-              }
+            for (int e = 0; e < 8; ++e) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
             }
+            *reinterpret_cast<uint4*>(rowp + (((ch0 + 0) ^ xr) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ xr) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              *reinterpret_cast<float4*>(rowp + (((ch0 + e) ^ xr) << 4)) =
+                  make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
           }
         }
         if (rd == rounds - 1) {
@@ -386,37 +364,32 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         if (EP && p.stats_sum) {
           // column sums of the staged (bf16-rounded) tile over its valid rows, read back from the swizzled
-          // staging buffer while the TMA store is in flight; the buffer is not rewritten before every epilogue
-          // thread has passed the next round's barriers
+          // staging buffer (consecutive threads read consecutive columns of one row: conflict free); the
+          // buffer is not rewritten before every epilogue thread has passed the next round's barriers
           int nvalid = (p.To - t0) * p.fo_tile;
           if (nvalid > UM) nvalid = UM;
-          const int cl = 2 * st_pr;
-          const int sub = cl / p.gw_y, col = cl - sub * p.gw_y;
-          const uint8_t* colp = stg + (size_t)sub * p.y_sub_bytes + ((col * 2) & 15);
-          const uint32_t chk = (uint32_t)(col * 2) >> 4;
-          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-          for (int rr = st_part; rr < nvalid; rr += nparts) {
+          const int sub = st_col / p.gw_y, cl = st_col - sub * p.gw_y;
+          const uint8_t* colp = stg + (size_t)sub * p.y_sub_bytes + ((cl * 2) & 15);
+          const uint32_t chk = (uint32_t)(cl * 2) >> 4;
+          int rend = (st_part + 1) * p.ecols;
+          if (rend > nvalid) rend = nvalid;
+          float s = 0.f, q = 0.f;
+          for (int rr = st_part * p.ecols; rr < rend; ++rr) {
             const uint32_t x2 = pitch == 128 ? (uint32_t)(rr & 7) : (pitch == 64 ? (uint32_t)((rr >> 1) & 3) : (uint32_t)((rr >> 2) & 1));
-            const uint32_t w2 = *reinterpret_cast<const uint32_t*>(colp + (size_t)rr * pitch + ((chk ^ x2) << 4));
-            const float va = __uint_as_float(w2 << 16), vb = __uint_as_float(w2 & 0xffff0000u);
-            s0 += va;
-            q0 = fmaf(va, va, q0);
-            s1 += vb;
-            q1 = fmaf(vb, vb, q1);
+            const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + (size_t)rr * pitch + ((chk ^ x2) << 4)));
+            s += v;
+            q = fmaf(v, v, q);
           }
-          st_s[rd & 1][0] += s0; st_q[rd & 1][0] += q0;
-          st_s[rd & 1][1] += s1; st_q[rd & 1][1] += q1;
+          if (rd == 0) { st_s0 += s; st_q0 += q; } else { st_s1 += s; st_q1 += q; }
         }
       }
     }
     if (EP && p.stats_sum) {
-      const int rounds = p.block_n / p.ecols;
-      for (int rd = 0; rd < rounds; ++rd) {
-        const int c0 = rd * p.ecols + 2 * st_pr;
-        atomicAdd(p.stats_sum + c0, (double)st_s[rd][0]);
-        atomicAdd(p.stats_sumsq + c0, (double)st_q[rd][0]);
-        atomicAdd(p.stats_sum + c0 + 1, (double)st_s[rd][1]);
-        atomicAdd(p.stats_sumsq + c0 + 1, (double)st_q[rd][1]);
+      atomicAdd(p.stats_sum + st_col, (double)st_s0);
+      atomicAdd(p.stats_sumsq + st_col, (double)st_q0);
+      if (p.block_n > p.ecols) {
+        atomicAdd(p.stats_sum + p.ecols + st_col, (double)st_s1);
+        atomicAdd(p.stats_sumsq + p.ecols + st_col, (double)st_q1);
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
@@ -486,6 +459,8 @@ extern "C" int clskd_set_tuning(int key, int value) {
     case 1: g_tune_resident = value; return CLSKD_OK;
     case 2: g_tune_two_cta = value; return CLSKD_OK;
     case 3: g_tune_v1 = value; return CLSKD_OK;
+    case 4: g_tune_split = value; return CLSKD_OK;
+    case 5: g_tune_noauto = value; return CLSKD_OK;
     default: set_error("clskd_set_tuning: unknown key %d", key); return CLSKD_ERR_ARG;
   }
 }
@@ -495,16 +470,8 @@ extern "C" int clskd_tapconv_umma_supported(const ClskdTapConv* d) {
   return umma_unsupported(d) == nullptr ? 1 : 0;
 }
 
-extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
-  CLSKD_CHECK_ARG(d && d->x0 && d->w && d->y, "clskd_tapconv_fwd_umma: null pointer");
-  CLSKD_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= CLSKD_MAX_TAPS, "clskd_tapconv_fwd_umma: ntaps");
-  if (const char* why = umma_unsupported(d)) {
-    set_error("clskd_tapconv_fwd_umma: unsupported: %s", why);
-    return CLSKD_ERR_UNSUPPORTED;
-  }
-  const int64_t M = (int64_t)d->B * d->To * d->Fo;
-  if (M == 0) return CLSKD_OK;
-  if (g_tune_v1) return clskd_tapconv_fwd_umma_v1(d, stream);
+static int launch_cfg(const ClskdTapConv* d, const FwdCfg& cfg, void* stream) {
+  if (cfg.v1) return clskd_tapconv_fwd_umma_v1(d, stream);
   EncodeTiledFn enc = get_encode();
   const int Ctot = d->c0 + d->c1;
 
@@ -522,6 +489,7 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   // largest K chunk that divides both sources
   int bk = 64;
   while (bk > 16 && (d->c0 % bk || (d->c1 % bk))) bk >>= 1;
+  if (cfg.bk_cap >= 16 && bk > cfg.bk_cap) bk = cfg.bk_cap;
   p.block_k = bk;
   p.chunks0 = d->c0 / bk;
   p.chunks_tot = Ctot / bk;
@@ -547,16 +515,16 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   const bool time_ok = d->ntaps > 1 && (p.fo_tile % 8 == 0) && (p.t_tile + (tmax - tmin)) * p.fo_tile <= 1024;
   if (full_ok) mode = 3;
   else if (time_ok && p.t_tile > 1 && tmax > tmin) mode = 2;
-  if (g_tune_mode == 1) mode = 1;
-  if (g_tune_mode == 2) mode = time_ok ? 2 : 1;
-  if (g_tune_mode == 3) mode = full_ok ? 3 : (time_ok && p.t_tile > 1 && tmax > tmin ? 2 : 1);
+  if (cfg.mode == 1) mode = 1;
+  if (cfg.mode == 2) mode = time_ok ? 2 : 1;
+  if (cfg.mode == 3) mode = full_ok ? 3 : (time_ok && p.t_tile > 1 && tmax > tmin ? 2 : 1);
   int box_f = p.fo_tile, box_t = p.t_tile;
   auto build_groups = [&](int md) {
     box_f = p.fo_tile;
     box_t = p.t_tile;
     if (md == 3) {
-      box_f = UM + (fmax - fmin);
-      box_t = p.t_tile + (tmax - tmin);
+      box_f = (UM + (fmax - fmin) + 7) & ~7;     // whole 8-row swizzle atoms per time row: every per-row TMA box
+      box_t = p.t_tile + (tmax - tmin);          // of the patch then starts on a pattern boundary
       p.ngroups = 1;
       p.grp_beg[0] = 0; p.grp_beg[1] = d->ntaps;
       p.grp_p[0] = 0; p.grp_f[0] = fmin; p.grp_t[0] = tmin;
@@ -630,10 +598,16 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
     build_groups(mode);
     p.a_tx = (uint32_t)box_f * box_t * pitch_a;
     p.a_bytes = pad1k(p.a_tx);
+    // several TMA boxes per patch: the TMA unit keeps more row requests in flight across boxes than inside one
+    int split = (mode != 1 && box_t > 1) ? 2 : 1;
+    if (cfg.split) split = cfg.split;
+    if (split == 2 && box_t > 1) { p.a_nbox = box_t; p.a_box_t = 1; }
+    else { p.a_nbox = 1; p.a_box_t = box_t; }
+    p.a_box_bytes = (uint32_t)box_f * p.a_box_t * pitch_a;
     // resident weights: the whole packed weight next to the pipeline (single n tile), leaving room for two
     // patch stages and one staging buffer
     resident = p.tiles_n == 1 && w_bytes <= 100u * 1024u && w_bytes + 2 * p.a_bytes + staging_bytes + 2048 <= kSmemMax;
-    if (g_tune_resident == 1) resident = false;
+    if (cfg.resident == 1) resident = false;
     p.resident = resident ? 1 : 0;
     p.stage_bytes = p.a_bytes + (resident ? 0u : (uint32_t)p.maxg * p.b_bytes);
     fixed = resident ? w_bytes : 0u;
@@ -641,7 +615,7 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
     // allow it: their serial per-tile latencies (TMA -> MMA -> TMEM drain -> store) overlap
     two_ctas = 2 * cols <= 512 && staging_bytes <= 32 * 1024 &&
                fixed + 2 * p.stage_bytes + staging_bytes + 1024 <= 106u * 1024u;
-    if (g_tune_two_cta == 1) two_ctas = false;
+    if (cfg.two_cta == 1) two_ctas = false;
     const uint32_t budget = two_ctas ? 106u * 1024u : kSmemMax;
     p.nstg = (fixed + 2 * staging_bytes + 2 * p.stage_bytes + 1024 <= budget) ? 2 : 1;
     stages = (int)((budget - 1024 - fixed - p.nstg * staging_bytes) / p.stage_bytes);
@@ -663,11 +637,11 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
 
   CUtensorMap tmA0, tmA1, tmB;
   int rc = encode_act_patch(enc, &tmA0, d->x0, d->c0, d->sf, d->Fi, d->Ti, d->B, d->x0_sB, d->x0_sT,
-                            d->x0_sF, bk, box_f, box_t, sw);
+                            d->x0_sF, bk, box_f, p.a_box_t, sw);
   if (rc) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(x0) failed: %d", rc); return CLSKD_ERR_CUDA; }
   if (d->c1) {
     rc = encode_act_patch(enc, &tmA1, d->x1, d->c1, d->sf, d->Fi, d->Ti, d->B, d->x1_sB, d->x1_sT,
-                          d->x1_sF, bk, box_f, box_t, sw);
+                          d->x1_sF, bk, box_f, p.a_box_t, sw);
     if (rc) { set_error("clskd_tapconv_fwd_umma: cuTensorMapEncodeTiled(x1) failed: %d", rc); return CLSKD_ERR_CUDA; }
   } else {
     tmA1 = tmA0;
@@ -710,5 +684,106 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
   if (ep) tapconv_umma_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmY, p);
   else tapconv_umma_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmY, p);
   CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd_umma");
+  return CLSKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-shape autotuner.  Which configuration wins depends on what bounds the shape (L2 -> shared-memory fill
+// rate, shared-memory operand reads of narrow-N MMAs, resident CTAs per SM, epilogue latency): the first call
+// for a shape signature times a handful of candidates on the caller's own tensors and caches the winner
+// (like cuDNN's find mode).  Candidate runs write the same outputs; their batch statistics go to a scratch
+// buffer.  clskd_set_tuning keys 0-4 force a configuration instead, key 5 = 1 disables the tuner.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_tune_mu;
+std::unordered_map<std::string, FwdCfg> g_tune_cache;
+double* g_tune_scratch = nullptr;      // [2][256] fp64 statistics sink for candidate runs
+
+std::string shape_key(const ClskdTapConv* d) {
+  char buf[512];
+  int n = snprintf(buf, sizeof(buf), "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d%d%d%d|", d->B, d->To, d->Fo, d->Ti, d->Fi, d->sf,
+                   d->ntaps, d->c0, d->c1, d->N, d->y_dtype, d->bias ? 1 : 0, d->ep_scale ? 1 : 0, d->ep_slope ? 1 : 0,
+                   d->stats_sum ? 1 : 0);
+  for (int j = 0; j < d->ntaps && n < (int)sizeof(buf) - 16; ++j) n += snprintf(buf + n, sizeof(buf) - n, "%d:%d;", d->dt[j], d->df[j]);
+  return std::string(buf);
+}
+
+FwdCfg autotune(const ClskdTapConv* d, cudaStream_t st) {
+  const FwdCfg cands[] = {
+      {1, 0, 0, 0, 0, 0},    // round-1 kernel
+      {0, 0, 0, 0, 0, 0},    // automatic grouping, resident weights when they fit
+      {0, 0, 1, 0, 0, 0},    // ... weights through the ring
+      {0, 1, 0, 0, 0, 0},    // one box per tap, resident weights
+      {0, 0, 0, 0, 0, 32},   // K chunk 32 (smaller stages)
+      {0, 0, 1, 0, 0, 32},
+      {0, 2, 1, 0, 0, 0},    // time-grouped patches
+      {0, 2, 1, 0, 0, 32},
+  };
+  if (!g_tune_scratch && cudaMalloc(&g_tune_scratch, sizeof(double) * 512) != cudaSuccess) {
+    cudaGetLastError();
+    return cands[0];
+  }
+  ClskdTapConv t = *d;
+  if (t.stats_sum) {
+    t.stats_sum = g_tune_scratch;
+    t.stats_sumsq = g_tune_scratch + 256;
+  }
+  cudaDeviceSynchronize();           // nothing else may share the SMs while the candidates are timed
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int best = 0;
+  float best_ms = 1e30f;
+  for (int i = 0; i < (int)(sizeof(cands) / sizeof(cands[0])); ++i) {
+    if (launch_cfg(&t, cands[i], st) != CLSKD_OK) { cudaGetLastError(); continue; }
+    cudaEventRecord(e0, st);
+    bool ok = true;
+    for (int r = 0; r < 2 && ok; ++r) ok = launch_cfg(&t, cands[i], st) == CLSKD_OK;
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess || !ok) { cudaGetLastError(); continue; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best_ms) { best_ms = ms; best = i; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return cands[best];
+}
+}  // namespace
+
+extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
+  CLSKD_CHECK_ARG(d && d->x0 && d->w && d->y, "clskd_tapconv_fwd_umma: null pointer");
+  CLSKD_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= CLSKD_MAX_TAPS, "clskd_tapconv_fwd_umma: ntaps");
+  if (const char* why = umma_unsupported(d)) {
+    set_error("clskd_tapconv_fwd_umma: unsupported: %s", why);
+    return CLSKD_ERR_UNSUPPORTED;
+  }
+  const int64_t M = (int64_t)d->B * d->To * d->Fo;
+  if (M == 0) return CLSKD_OK;
+  const bool forced = g_tune_v1 || g_tune_mode || g_tune_resident || g_tune_two_cta || g_tune_split;
+  static const bool env_off = getenv("CLSKD_AUTOTUNE") && atoi(getenv("CLSKD_AUTOTUNE")) == 0;
+  if (forced || g_tune_noauto || env_off || M < 65536) {
+    // forced configuration, or a launch too small to be worth tuning (automatic configuration)
+    const FwdCfg cfg = {g_tune_v1, g_tune_mode, g_tune_resident, g_tune_two_cta, g_tune_split, 0};
+    return launch_cfg(d, cfg, stream);
+  }
+  FwdCfg cfg;
+  {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    const std::string key = shape_key(d);
+    auto it = g_tune_cache.find(key);
+    if (it == g_tune_cache.end()) it = g_tune_cache.emplace(key, autotune(d, (cudaStream_t)stream)).first;
+    cfg = it->second;
+  }
+  return launch_cfg(d, cfg, stream);
+}
+
+// number of shapes tuned so far and how many chose the round-1 kernel (diagnostics for tools/kbench.py, bench.py)
+extern "C" int clskd_tuning_stats(int* n_shapes, int* n_v1) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  int v = 0;
+  for (auto& kv : g_tune_cache) v += kv.second.v1 ? 1 : 0;
+  if (n_shapes) *n_shapes = (int)g_tune_cache.size();
+  if (n_v1) *n_v1 = v;
   return CLSKD_OK;
 }

@@ -65,8 +65,10 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    variants = [("v1", (0, 0, 0, 1)), ("legacy", (1, 1)), ("legacy+res", (1, 0)), ("time", (2, 1)), ("time+res", (2, 0)),
-                ("full", (3, 1)), ("auto", (0, 0)), ("auto 1cta", (0, 0, 1))]
+    # (mode, resident-off, one-cta, v1, split, no-autotune)
+    variants = [("v1", (0, 0, 0, 1, 0, 1)), ("legacy", (1, 1, 0, 0, 0, 1)), ("legacy+res", (1, 0, 0, 0, 0, 1)),
+                ("time", (2, 1, 0, 0, 0, 1)), ("full", (3, 1, 0, 0, 0, 1)), ("full 1box", (3, 1, 0, 0, 1, 1)),
+                ("full+res", (3, 0, 0, 0, 0, 1)), ("auto", (0, 0, 0, 0, 0, 1)), ("tuned", (0, 0, 0, 0, 0, 0))]
     if a.variants:
         variants = [v for v in variants if v[0] in a.variants.split(",")]
     results = []
@@ -109,6 +111,8 @@ def main():
             lib.clskd_set_tuning(1, tune[1])
             lib.clskd_set_tuning(2, tune[2] if len(tune) > 2 else 0)
             lib.clskd_set_tuning(3, tune[3] if len(tune) > 3 else 0)
+            lib.clskd_set_tuning(4, tune[4] if len(tune) > 4 else 0)
+            lib.clskd_set_tuning(5, tune[5] if len(tune) > 5 else 0)
             try:
                 for i in range(3):
                     d.x0 = xs[i % 3].data_ptr()
@@ -137,7 +141,7 @@ def main():
                                           "max_rel_diff_vs_legacy": err, "stats_rel_diff": serr}
             except RuntimeError as e:
                 row["variants"][vname] = {"error": str(e)[:200]}
-        for k in range(4):
+        for k in range(6):
             lib.clskd_set_tuning(k, 0)
         results.append(row)
         print("%-38s floor %.3f ms | " % (name, row["floor_ms"]) + " | ".join(
