@@ -388,6 +388,21 @@ int clskd_abf_mid_xs_bwd(const void* gout, const void* x, const float* w1, const
                          const float* gamma, const float* beta, const float* watt, const float* logits,
                          int training, double* sums, double* dwatt, double* dbatt, double* dw1, void* dx,
                          void* dy, void* stream);
+/* The same 2-channel middle stage with the rank-2 structure of z1 = W1 x folded through every reduction
+ * (the x half of the logits is two scalars per row; the BatchNorm-backward batch sums, dW_att and dW1 follow from
+ * three per-channel sums, six scalar sums and the 2x2 moments of x; dx needs two dot products per row): the
+ * backward is ONE pass over gout / y_prev + a one-block finalisation + a 24-byte-per-row pass for dx.
+ * Same arguments / outputs as clskd_abf_mid_xs_fwd / _bwd; the backward takes a caller-allocated workspace of
+ * clskd_abf_xs2_bwd_workspace(B, T, F, C, &bytes) bytes (16-byte aligned). */
+int clskd_abf_xs2_fwd(const void* x, const float* w1, const void* y, int dtype, int B, int T, int F, int Fy,
+                      int C, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      const float* watt, const float* batt, void* xb, float* logits, void* stream);
+int clskd_abf_xs2_bwd_workspace(int B, int T, int F, int C, int64_t* bytes);
+int clskd_abf_xs2_bwd(const void* gout, const void* x, const float* w1, const void* y, int dtype, int B, int T,
+                      int F, int Fy, int C, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, const float* watt, const float* logits, int training, double* sums,
+                      double* dwatt, double* dbatt, double* dw1, void* dx, void* dy, void* workspace,
+                      int64_t ws_bytes, void* stream);
 /* sum[c] = sum_m (W1 x_m)[c], sumsq[c] = sum_m (W1 x_m)[c]^2 from s5 = moments of the 2-channel x */
 int clskd_rank2_colstats(const double* s5, const float* w1, int C, double* sum, double* sumsq,
                          void* stream);

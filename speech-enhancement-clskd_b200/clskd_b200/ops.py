@@ -30,6 +30,7 @@ class _Policy:
         self.use_umma = False
         self.abf_rank2 = True       # ABF level whose 1x1 conv has 2 input channels: z1 recomputed in the mid kernels
         self.fuse_epilogue = True   # BatchNorm statistics / folded eval BatchNorm + PReLU in the tcgen05 conv epilogue
+        self.abf_xs2 = True      # rank-2 folded kernels for the 2-channel ABF level (clskd_abf_xs2_*)
         self.split_gemm = True   # fp32-input GEMMs (STFT/iSTFT/LSTM projections) as split-bf16 tcgen05 contractions
         self.narrow = "auto"     # tap-in-channel decomposition of narrow convs: "auto" (tensor-core policy) / "always"
 
@@ -1169,9 +1170,11 @@ class AbfMidXsFn(torch.autograd.Function):
         ba32 = _f32c(batt) if batt is not None else None
         xb = torch.empty((B, T, F, C), dtype=xs.dtype, device=dev)
         logits = torch.empty((B, T, F, 2), dtype=torch.float32, device=dev)
-        call("clskd_abf_mid_xs_fwd", xs.data_ptr(), w1f.data_ptr(), y_prev.data_ptr(), _tag(xs.dtype), B, T, F, Fy, C,
-             mean.data_ptr(), invstd.data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(), _ptr(ba32),
-             xb.data_ptr(), logits.data_ptr(), st)
+        # rank-2 folded kernels (clskd_abf_xs2_*); policy.abf_xs2 = False keeps the round-1 kernels (A/B, tests)
+        ctx.xs2 = bool(policy.abf_xs2) and C >= 16
+        call("clskd_abf_xs2_fwd" if ctx.xs2 else "clskd_abf_mid_xs_fwd", xs.data_ptr(), w1f.data_ptr(), y_prev.data_ptr(),
+             _tag(xs.dtype), B, T, F, Fy, C, mean.data_ptr(), invstd.data_ptr(), g32.data_ptr(), b32.data_ptr(),
+             w32.data_ptr(), _ptr(ba32), xb.data_ptr(), logits.data_ptr(), st)
         ctx.save_for_backward(xs, y_prev, stats, gamma, beta, watt, logits, w1)
         ctx.use_batch = use_batch
         ctx.has_bias = batt is not None
@@ -1192,10 +1195,19 @@ class AbfMidXsFn(torch.autograd.Function):
         g32, b32 = _f32c(gamma), _f32c(beta)
         w32 = _f32c(watt).view(2, 2 * C)
         w1f = _f32c(w1).view(C, 2)
-        call("clskd_abf_mid_xs_bwd", g.data_ptr(), xs.data_ptr(), w1f.data_ptr(), y_prev.data_ptr(), _tag(xs.dtype),
-             B, T, F, Fy, C, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(),
-             logits.data_ptr(), 1 if ctx.use_batch else 0, sums.data_ptr(), dwatt.data_ptr(), dbatt.data_ptr(),
-             dw1.data_ptr(), dxs.data_ptr(), dy.data_ptr(), _stream())
+        if ctx.xs2:
+            nb = ctypes.c_int64(0)
+            call("clskd_abf_xs2_bwd_workspace", B, T, F, C, ctypes.byref(nb))
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+            call("clskd_abf_xs2_bwd", g.data_ptr(), xs.data_ptr(), w1f.data_ptr(), y_prev.data_ptr(), _tag(xs.dtype),
+                 B, T, F, Fy, C, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(),
+                 logits.data_ptr(), 1 if ctx.use_batch else 0, sums.data_ptr(), dwatt.data_ptr(), dbatt.data_ptr(),
+                 dw1.data_ptr(), dxs.data_ptr(), dy.data_ptr(), ws.data_ptr(), nb.value, _stream())
+        else:
+            call("clskd_abf_mid_xs_bwd", g.data_ptr(), xs.data_ptr(), w1f.data_ptr(), y_prev.data_ptr(), _tag(xs.dtype),
+                 B, T, F, Fy, C, stats[0].data_ptr(), stats[1].data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(),
+                 logits.data_ptr(), 1 if ctx.use_batch else 0, sums.data_ptr(), dwatt.data_ptr(), dbatt.data_ptr(),
+                 dw1.data_ptr(), dxs.data_ptr(), dy.data_ptr(), _stream())
         a32 = f64_to_f32(acc)
         dbeta, dgamma = a32[:C].view_as(beta), a32[C:2 * C].view_as(gamma)
         dw = a32[2 * C:6 * C].view_as(watt)

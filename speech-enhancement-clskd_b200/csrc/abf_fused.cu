@@ -576,6 +576,435 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
   }
 }
 
+
+// =====================================================================================================
+// XS2: the 2-channel ("mask level") ABF middle stage with the rank-2 structure of z1 = W1 x folded through
+// every reduction (framework.py:209-219 with a 2-channel conv1 input).  With
+//     xp_c   = P_c x0 + Q_c x1 + sh_c              (P = sc w10, Q = sc w11, sc = invstd gamma, sh = beta - mean sc)
+//     xhat_c = al_c x0 + be_c x1 + ga_c            (al = w10 invstd, be = w11 invstd, ga = -mean invstd)
+// the x half of the attention logits is a pair of scalars per row, the BatchNorm-backward batch sums
+//     sum_rows dxp_c,  sum_rows dxp_c x0,  sum_rows dxp_c x1        (dxp = g s0 + wx0 dl0 + wx1 dl1)
+// need only  G0_c = sum g_c s0,  G1_c = sum g_c s0 x0,  G2_c = sum g_c s0 x1  per channel plus six scalar sums, dW_att's
+// x half and dW1 follow from those sums and the 2x2 moments of x, and
+//     dx_k = sum_c w1k_c dz1_c = s0 <g, U_k> + dl0 c_ka + dl1 c_kb - c_kc - x0 c_kd - x1 c_ke      (U_k = w1k gamma invstd)
+// needs only the two per-row dot products <g, U_k>.  So the backward is ONE pass over g / y_prev (it writes dy_prev and 16
+// bytes per row: s0<g,U0>, s0<g,U1>, dl0, dl1), a one-block finalisation, and a pass over 24 bytes per row that emits dx -
+// instead of two full passes that recompute z1, xp and xhat per element.
+// Thread mapping as above: C/8 adjacent lanes own a PAIR of rows (f = 2j, 2j+1: they share the y_prev row when Fy = F/2).
+// =====================================================================================================
+enum { X_P = 0, X_Q, X_SH, X_WY0, X_WY1, X_U0, X_U1, X_NCONST };
+// scalar slots behind the per-channel constants
+enum { XS_A0 = 0, XS_B0, XS_K0, XS_A1, XS_B1, XS_K1, XS_NSCAL };
+
+__device__ __forceinline__ void xs2_stage_consts(float* cs, int C, const float* mean, const float* invstd, const float* gamma,
+                                                 const float* beta, const float* watt, const float* batt, const float* w1) {
+  // per-channel vectors
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = gamma ? gamma[c] : 1.f;
+    const float is = invstd[c], sc = is * g, sh = (beta ? beta[c] : 0.f) - mean[c] * sc;
+    const float a = w1[2 * c], b = w1[2 * c + 1];
+    cs[X_P * C + c] = sc * a;
+    cs[X_Q * C + c] = sc * b;
+    cs[X_SH * C + c] = sh;
+    cs[X_WY0 * C + c] = watt[C + c];
+    cs[X_WY1 * C + c] = watt[3 * C + c];
+    cs[X_U0 * C + c] = a * g * is;
+    cs[X_U1 * C + c] = b * g * is;
+  }
+  __syncthreads();
+  // scalars of the x half of the logits: l_k = x0 A_k + x1 B_k + K_k + <yv, wy_k>  (K_k includes the bias)
+  float* sc_ = cs + X_NCONST * C;
+  if (threadIdx.x < 32) {
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = threadIdx.x; c < C; c += 32) {
+      const float p = cs[X_P * C + c], q = cs[X_Q * C + c], sh = cs[X_SH * C + c];
+      const float wx0 = watt[c], wx1 = watt[2 * C + c];
+      v[0] = fmaf(p, wx0, v[0]); v[1] = fmaf(q, wx0, v[1]); v[2] = fmaf(sh, wx0, v[2]);
+      v[3] = fmaf(p, wx1, v[3]); v[4] = fmaf(q, wx1, v[4]); v[5] = fmaf(sh, wx1, v[5]);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = warp_sum(v[i]);
+    if (threadIdx.x == 0) {
+      sc_[XS_A0] = v[0]; sc_[XS_B0] = v[1]; sc_[XS_K0] = v[2] + (batt ? batt[0] : 0.f);
+      sc_[XS_A1] = v[3]; sc_[XS_B1] = v[4]; sc_[XS_K1] = v[5] + (batt ? batt[1] : 0.f);
+    }
+  }
+  __syncthreads();
+}
+
+// n partial sums per lane -> totals over the tpr lanes of a row group (butterfly); tpr is a power of two
+template <int N>
+__device__ __forceinline__ void group_sum(float* v, int tpr) {
+  for (int o = tpr >> 1; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(AT, 2) abf_xs2_fwd_kernel(const T* __restrict__ x, const T* __restrict__ y, AbfGeom g,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ watt, const float* __restrict__ batt,
+                                                            const float* __restrict__ w1, T* __restrict__ xb,
+                                                            float* __restrict__ logits) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* cs = reinterpret_cast<float*>(smem_raw);
+  const int C = g.C;
+  constexpr int NCP = Vec8<T>::NCP;
+  constexpr int NSLOT = 2 * NCP + 1;                      // y rows (1 or 2) + one slot for the two 2-channel rows
+  constexpr int SLOT_STRIDE = AT * 16;
+  uint8_t* pipe = smem_raw + ((sizeof(float) * (X_NCONST * C + XS_NSCAL) + 15) & ~(size_t)15) + threadIdx.x * 16;
+  xs2_stage_consts(cs, C, mean, invstd, gamma, beta, watt, batt, w1);
+  const float* sc_ = cs + X_NCONST * C;
+  const float A0 = sc_[XS_A0], B0 = sc_[XS_B0], K0 = sc_[XS_K0], A1 = sc_[XS_A1], B1 = sc_[XS_B1], K1 = sc_[XS_K1];
+  const int lane = threadIdx.x & 31;
+  const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
+  const int64_t pairs = g.M >> 1;
+  const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
+  const int64_t stride = nwarps * rpw;
+  const int cs_ = g.cshift, coff = cg * 8;
+  const bool y_full = g.yshift == 0;
+
+  int64_t pi = warp0 * rpw + sub;
+  int si = 0;
+  auto issue = [&]() {
+    if (pi < pairs) {
+      uint8_t* st = pipe + (size_t)si * NSLOT * SLOT_STRIDE;
+      const int64_t m0 = 2 * pi;
+      const T* yp = y + (yrow(g, m0) << cs_) + coff;
+      cp_vec8<T>(st, SLOT_STRIDE, yp);
+      if (y_full) cp_vec8<T>(st + NCP * SLOT_STRIDE, SLOT_STRIDE, yp + ((int64_t)1 << cs_));
+      cp_xs<T>(st + (2 * NCP) * SLOT_STRIDE, x + 2 * m0, 2);
+    }
+    cp_commit();
+    pi += stride;
+    si = si + 1 == PD ? 0 : si + 1;
+  };
+#pragma unroll
+  for (int i = 0; i < PD - 1; ++i) issue();
+
+  int sc2 = 0;
+  for (int64_t pb = warp0 * rpw; pb < pairs; pb += stride) {     // warp-uniform
+    issue();
+    cp_wait<PD - 1>();
+    const uint8_t* st = pipe + (size_t)sc2 * NSLOT * SLOT_STRIDE;
+    sc2 = sc2 + 1 == PD ? 0 : sc2 + 1;
+    const int64_t p = pb + sub;
+    const bool live = p < pairs;
+    const int64_t m0 = live ? 2 * p : 0;
+    float yv[2][8], x0[2] = {0.f, 0.f}, x1[2] = {0.f, 0.f};
+    if (live) {
+      ld_vec8(st, SLOT_STRIDE, (const T*)nullptr, yv[0]);
+      if (y_full) ld_vec8(st + NCP * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[1]);
+      ld_xs(st + (2 * NCP) * SLOT_STRIDE, (const T*)nullptr, 0, x0[0], x1[0]);
+      ld_xs(st + (2 * NCP) * SLOT_STRIDE, (const T*)nullptr, 1, x0[1], x1[1]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[0][e] = yv[1][e] = 0.f;
+    }
+    // y half of the logits (once per y row)
+    float ly[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      float w0[8], w1v[8];
+      ldc(cs, X_WY0, C, cg, w0);
+      ldc(cs, X_WY1, C, cg, w1v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        ly[0] = fmaf(yv[0][e], w0[e], ly[0]);
+        ly[1] = fmaf(yv[0][e], w1v[e], ly[1]);
+      }
+      if (y_full) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          ly[2] = fmaf(yv[1][e], w0[e], ly[2]);
+          ly[3] = fmaf(yv[1][e], w1v[e], ly[3]);
+        }
+      }
+    }
+    if (y_full) {
+      group_sum<4>(ly, g.tpr);
+    } else {
+      group_sum<2>(ly, g.tpr);
+      ly[2] = ly[0];
+      ly[3] = ly[1];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[1][e] = yv[0][e];
+    }
+    float P[8], Q[8], SH[8];
+    ldc(cs, X_P, C, cg, P);
+    ldc(cs, X_Q, C, cg, Q);
+    ldc(cs, X_SH, C, cg, SH);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float l0 = fmaf(x0[q], A0, fmaf(x1[q], B0, K0)) + ly[2 * q];
+      const float l1 = fmaf(x0[q], A1, fmaf(x1[q], B1, K1)) + ly[2 * q + 1];
+      const float s0 = sigm(l0), s1 = sigm(l1);
+      if (live) {
+        const float a = x0[q] * s0, b = x1[q] * s0;
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = fmaf(P[e], a, fmaf(Q[e], b, fmaf(SH[e], s0, yv[q][e] * s1)));
+        st8(xb + ((m0 + q) << cs_) + coff, o8);
+        if (cg == 0) *reinterpret_cast<float2*>(logits + 2 * (m0 + q)) = make_float2(l0, l1);
+      }
+    }
+  }
+}
+
+// per-CTA scalar sums of the backward pass
+enum { R_D0 = 0, R_D1, R_D0X0, R_D0X1, R_D1X0, R_D1X1, R_X0, R_X1, R_X00, R_X01, R_X11, R_NSCAL };
+
+// acc layout (fp64, zeroed by the launcher): G0[C] G1[C] G2[C] WY0[C] WY1[C] scal[R_NSCAL]
+template <typename T>
+__global__ void __launch_bounds__(AT, 2) abf_xs2_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ x,
+                                                            const T* __restrict__ y, AbfGeom g,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ watt, const float* __restrict__ w1,
+                                                            const float* __restrict__ logits, double* __restrict__ acc,
+                                                            float4* __restrict__ rows, T* __restrict__ dy) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* cs = reinterpret_cast<float*>(smem_raw);
+  const int C = g.C;
+  float* red = cs + X_NCONST * C + XS_NSCAL;              // [5*C + R_NSCAL]
+  constexpr int NCP = Vec8<T>::NCP;
+  constexpr int NSLOT = 4 * NCP + 2;                      // g[2], y[1..2] vectors, x pair, logits pair
+  constexpr int SLOT_STRIDE = AT * 16;
+  uint8_t* pipe = smem_raw + ((sizeof(float) * (X_NCONST * C + XS_NSCAL + 5 * C + R_NSCAL) + 15) & ~(size_t)15) + threadIdx.x * 16;
+  for (int i = threadIdx.x; i < 5 * C + R_NSCAL; i += AT) red[i] = 0.f;
+  xs2_stage_consts(cs, C, mean, invstd, gamma, beta, watt, nullptr, w1);
+  const int lane = threadIdx.x & 31;
+  const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
+  const int64_t pairs = g.M >> 1;
+  const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
+  const int64_t stride = nwarps * rpw;
+  const int cs_ = g.cshift, coff = cg * 8;
+  const bool y_full = g.yshift == 0;
+  float aG0[8], aG1[8], aG2[8], aW0[8], aW1[8], aS[R_NSCAL];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) aG0[e] = aG1[e] = aG2[e] = aW0[e] = aW1[e] = 0.f;
+#pragma unroll
+  for (int e = 0; e < R_NSCAL; ++e) aS[e] = 0.f;
+
+  int64_t pi = warp0 * rpw + sub;
+  int si = 0;
+  auto issue = [&]() {
+    if (pi < pairs) {
+      uint8_t* st = pipe + (size_t)si * NSLOT * SLOT_STRIDE;
+      const int64_t m0 = 2 * pi;
+      const T* gp = gout + (m0 << cs_) + coff;
+      const T* yp = y + (yrow(g, m0) << cs_) + coff;
+      cp_vec8<T>(st, SLOT_STRIDE, gp);
+      cp_vec8<T>(st + NCP * SLOT_STRIDE, SLOT_STRIDE, gp + ((int64_t)1 << cs_));
+      cp_vec8<T>(st + (2 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp);
+      if (y_full) cp_vec8<T>(st + (3 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp + ((int64_t)1 << cs_));
+      cp_xs<T>(st + (4 * NCP) * SLOT_STRIDE, x + 2 * m0, 2);
+      cp16(st + (4 * NCP + 1) * SLOT_STRIDE, logits + 2 * m0);
+    }
+    cp_commit();
+    pi += stride;
+    si = si + 1 == PD ? 0 : si + 1;
+  };
+#pragma unroll
+  for (int i = 0; i < PD - 1; ++i) issue();
+
+  int sc2 = 0;
+  for (int64_t pb = warp0 * rpw; pb < pairs; pb += stride) {
+    issue();
+    cp_wait<PD - 1>();
+    const uint8_t* st = pipe + (size_t)sc2 * NSLOT * SLOT_STRIDE;
+    sc2 = sc2 + 1 == PD ? 0 : sc2 + 1;
+    const int64_t p = pb + sub;
+    const bool live = p < pairs;
+    const int64_t m0 = live ? 2 * p : 0;
+    float gv[2][8], yv[2][8], x0[2] = {0.f, 0.f}, x1[2] = {0.f, 0.f};
+    float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      ld_vec8(st, SLOT_STRIDE, (const T*)nullptr, gv[0]);
+      ld_vec8(st + NCP * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, gv[1]);
+      ld_vec8(st + (2 * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[0]);
+      if (y_full) ld_vec8(st + (3 * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[1]);
+      ld_xs(st + (4 * NCP) * SLOT_STRIDE, (const T*)nullptr, 0, x0[0], x1[0]);
+      ld_xs(st + (4 * NCP) * SLOT_STRIDE, (const T*)nullptr, 1, x0[1], x1[1]);
+      l4 = *reinterpret_cast<const float4*>(st + (4 * NCP + 1) * SLOT_STRIDE);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gv[0][e] = gv[1][e] = yv[0][e] = yv[1][e] = 0.f;
+    }
+    if (!y_full) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[1][e] = yv[0][e];
+    }
+    // six dot products per row: <g,P>, <g,Q>, <g,sh>, <g,yv>, <g,U0>, <g,U1>
+    float d[12];
+    {
+      float P[8], Q[8], SH[8], U0[8], U1[8];
+      ldc(cs, X_P, C, cg, P);
+      ldc(cs, X_Q, C, cg, Q);
+      ldc(cs, X_SH, C, cg, SH);
+      ldc(cs, X_U0, C, cg, U0);
+      ldc(cs, X_U1, C, cg, U1);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float a = 0.f, b = 0.f, c = 0.f, dd = 0.f, u0 = 0.f, u1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float ge = gv[q][e];
+          a = fmaf(ge, P[e], a);
+          b = fmaf(ge, Q[e], b);
+          c = fmaf(ge, SH[e], c);
+          dd = fmaf(ge, yv[q][e], dd);
+          u0 = fmaf(ge, U0[e], u0);
+          u1 = fmaf(ge, U1[e], u1);
+        }
+        d[6 * q] = a; d[6 * q + 1] = b; d[6 * q + 2] = c; d[6 * q + 3] = dd; d[6 * q + 4] = u0; d[6 * q + 5] = u1;
+      }
+    }
+    group_sum<12>(d, g.tpr);
+    float s0[2], s1[2], dl0[2], dl1[2];
+    const float lg[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      s0[q] = sigm(lg[2 * q]);
+      s1[q] = sigm(lg[2 * q + 1]);
+      const float t0 = fmaf(x0[q], d[6 * q], fmaf(x1[q], d[6 * q + 1], d[6 * q + 2]));
+      const float t1 = d[6 * q + 3];
+      dl0[q] = live ? t0 * s0[q] * (1.f - s0[q]) : 0.f;
+      dl1[q] = live ? t1 * s1[q] * (1.f - s1[q]) : 0.f;
+    }
+    if (live && cg == 0) {
+      rows[m0] = make_float4(s0[0] * d[4], s0[0] * d[5], dl0[0], dl1[0]);
+      rows[m0 + 1] = make_float4(s0[1] * d[10], s0[1] * d[11], dl0[1], dl1[1]);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        aS[R_D0] += dl0[q]; aS[R_D1] += dl1[q];
+        aS[R_D0X0] = fmaf(dl0[q], x0[q], aS[R_D0X0]); aS[R_D0X1] = fmaf(dl0[q], x1[q], aS[R_D0X1]);
+        aS[R_D1X0] = fmaf(dl1[q], x0[q], aS[R_D1X0]); aS[R_D1X1] = fmaf(dl1[q], x1[q], aS[R_D1X1]);
+        aS[R_X0] += x0[q]; aS[R_X1] += x1[q];
+        aS[R_X00] = fmaf(x0[q], x0[q], aS[R_X00]); aS[R_X01] = fmaf(x0[q], x1[q], aS[R_X01]);
+        aS[R_X11] = fmaf(x1[q], x1[q], aS[R_X11]);
+      }
+    }
+    // per-channel sums and dy_prev
+    {
+      float wy0[8], wy1[8];
+      ldc(cs, X_WY0, C, cg, wy0);
+      ldc(cs, X_WY1, C, cg, wy1);
+      float dyv[2][8];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float gs = live ? s0[q] : 0.f;
+        const float gx0 = gs * x0[q], gx1 = gs * x1[q];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float ge = gv[q][e];
+          aG0[e] = fmaf(ge, gs, aG0[e]);
+          aG1[e] = fmaf(ge, gx0, aG1[e]);
+          aG2[e] = fmaf(ge, gx1, aG2[e]);
+          aW0[e] = fmaf(dl0[q], yv[q][e], aW0[e]);
+          aW1[e] = fmaf(dl1[q], yv[q][e], aW1[e]);
+          dyv[q][e] = fmaf(ge, s1[q], fmaf(wy0[e], dl0[q], wy1[e] * dl1[q]));
+        }
+      }
+      if (live) {
+        T* yo = dy + (yrow(g, m0) << cs_) + coff;
+        if (y_full) {
+          st8(yo, dyv[0]);
+          st8(yo + ((int64_t)1 << cs_), dyv[1]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dyv[0][e] += dyv[1][e];
+          st8(yo, dyv[0]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    atomicAdd(&red[c], aG0[e]);
+    atomicAdd(&red[C + c], aG1[e]);
+    atomicAdd(&red[2 * C + c], aG2[e]);
+    atomicAdd(&red[3 * C + c], aW0[e]);
+    atomicAdd(&red[4 * C + c], aW1[e]);
+  }
+  if (cg == 0) {
+#pragma unroll
+    for (int e = 0; e < R_NSCAL; ++e) atomicAdd(&red[5 * C + e], aS[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 5 * C + R_NSCAL; i += AT) atomicAdd(acc + i, (double)red[i]);
+}
+
+// one block: batch sums -> dgamma / dbeta (sums), dW_att, db_att, dW1 and the 10 constants of the dx pass
+__global__ void abf_xs2_finalize_kernel(const double* __restrict__ acc, int C, double invM, int training,
+                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        const float* __restrict__ watt, const float* __restrict__ w1,
+                                        double* __restrict__ sums, double* __restrict__ dwatt, double* __restrict__ dbatt,
+                                        double* __restrict__ dw1, float* __restrict__ dxc) {
+  __shared__ double sh[10][32];
+  const double* S = acc + 5 * C;
+  double part[10];
+  for (int i = 0; i < 10; ++i) part[i] = 0.;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double g = gamma ? gamma[c] : 1.f, is = invstd[c], mu = mean[c];
+    const double a = w1[2 * c], b = w1[2 * c + 1];
+    const double sc = is * g, shv = (beta ? (double)beta[c] : 0.) - mu * sc;
+    const double P = sc * a, Q = sc * b, al = a * is, be = b * is, ga = -mu * is, gi = g * is;
+    const double wx0 = watt[c], wx1 = watt[2 * C + c];
+    const double S1 = acc[c] + wx0 * S[R_D0] + wx1 * S[R_D1];
+    const double SX0 = acc[C + c] + wx0 * S[R_D0X0] + wx1 * S[R_D1X0];
+    const double SX1 = acc[2 * C + c] + wx0 * S[R_D0X1] + wx1 * S[R_D1X1];
+    const double S2 = al * SX0 + be * SX1 + ga * S1;
+    sums[c] = S1;                 // dbeta
+    sums[C + c] = S2;             // dgamma
+    dwatt[c] = P * S[R_D0X0] + Q * S[R_D0X1] + shv * S[R_D0];
+    dwatt[C + c] = acc[3 * C + c];
+    dwatt[2 * C + c] = P * S[R_D1X0] + Q * S[R_D1X1] + shv * S[R_D1];
+    dwatt[3 * C + c] = acc[4 * C + c];
+    const double k1 = training ? S1 * invM : 0., k2 = training ? S2 * invM : 0.;
+    dw1[2 * c] = gi * (SX0 - k1 * S[R_X0] - k2 * (al * S[R_X00] + be * S[R_X01] + ga * S[R_X0]));
+    dw1[2 * c + 1] = gi * (SX1 - k1 * S[R_X1] - k2 * (al * S[R_X01] + be * S[R_X11] + ga * S[R_X1]));
+    const double U0 = a * gi, U1 = b * gi;
+    part[0] += U0 * wx0; part[1] += U0 * wx1; part[2] += U0 * (k1 + ga * k2); part[3] += U0 * al * k2; part[4] += U0 * be * k2;
+    part[5] += U1 * wx0; part[6] += U1 * wx1; part[7] += U1 * (k1 + ga * k2); part[8] += U1 * al * k2; part[9] += U1 * be * k2;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = 0; i < 10; ++i) {
+    part[i] = warp_sum(part[i]);
+    if (lane == 0) sh[i][w] = part[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    double t = 0.;
+    for (int k = 0; k < (int)((blockDim.x + 31) >> 5); ++k) t += sh[threadIdx.x][k];
+    dxc[threadIdx.x] = (float)t;
+  }
+  if (threadIdx.x == 0) {
+    dbatt[0] = S[R_D0];
+    dbatt[1] = S[R_D1];
+  }
+}
+
+// dx_k = e_k + dl0 c_ka + dl1 c_kb - c_kc - x0 c_kd - x1 c_ke   (24 bytes per row in, 4 or 8 out)
+template <typename T>
+__global__ void abf_xs2_dx_kernel(const float4* __restrict__ rows, const T* __restrict__ x, int64_t M,
+                                  const float* __restrict__ dxc, T* __restrict__ dx) {
+  float c[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) c[i] = __ldg(dxc + i);
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    const float4 r = rows[m];
+    const float x0 = ld_f(x + 2 * m), x1 = ld_f(x + 2 * m + 1);
+    st_f(dx + 2 * m, r.x + r.z * c[0] + r.w * c[1] - c[2] - x0 * c[3] - x1 * c[4]);
+    st_f(dx + 2 * m + 1, r.y + r.z * c[5] + r.w * c[6] - c[7] - x0 * c[8] - x1 * c[9]);
+  }
+}
+
 const char* abf_unsupported(int B, int T, int F, int Fy, int C, const void* a, const void* b, const void* c) {
   if (C % 8 || C > 256 || C < 8) return "C must be a multiple of 8 in [8,256]";
   const int tpr = C / 8;
@@ -587,6 +1016,12 @@ const char* abf_unsupported(int B, int T, int F, int Fy, int C, const void* a, c
 }
 
 int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+int ew_grid_abf(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
 
 int abf_grid(int64_t warp_iters) {
   int64_t blocks = (warp_iters + 7) / 8;
@@ -726,6 +1161,104 @@ extern "C" int clskd_abf_mid_xs_bwd(const void* gout, const void* x, const float
                                     void* dy, void* stream) {
   return abf_bwd_launch("clskd_abf_mid_xs_bwd", true, gout, x, y, dtype, B, T, F, Fy, C, mean, invstd, gamma, beta, watt,
                         logits, training, sums, dwatt, dbatt, dx, dy, w1, dw1, stream);
+}
+
+
+// ---- XS2 launchers (rank-2 folded kernels above)
+extern "C" int clskd_abf_xs2_fwd(const void* x, const float* w1, const void* y, int dtype, int B, int T, int F, int Fy,
+                                 int C, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                 const float* watt, const float* batt, void* xb, float* logits, void* stream) {
+  const char* who = "clskd_abf_xs2_fwd";
+  CLSKD_CHECK_ARG(x && w1 && y && mean && invstd && watt && xb && logits, "%s: null pointer", who);
+  if (const char* why = abf_unsupported(B, T, F, Fy, C, y, y, xb)) {
+    set_error("%s: unsupported: %s", who, why);
+    return CLSKD_ERR_UNSUPPORTED;
+  }
+  CLSKD_CHECK_ARG(((uintptr_t)x % 16) == 0 && C >= 16, "%s: x must be 16-byte aligned and C >= 16", who);
+  AbfGeom g;
+  g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
+  g.cshift = ilog2(C); g.yshift = Fy == F ? 0 : 1;
+  if (g.M == 0) return CLSKD_OK;
+  const int64_t pairs = g.M / 2;
+  const int ppw = 32 / g.tpr;
+  const int grid = abf_grid((pairs + ppw - 1) / ppw / 4);
+  const size_t es = dtype == CLSKD_F32 ? 4 : 2;
+  const size_t cbytes = (sizeof(float) * (X_NCONST * (size_t)C + XS_NSCAL) + 15) & ~(size_t)15;
+  const size_t sh = cbytes + (size_t)PD * (2 * (es / 2) + 1) * AT * 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(abf_xs2_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(abf_xs2_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_xs2_fwd_kernel<TT><<<grid, AT, sh, (cudaStream_t)stream>>>(
+                                      (const TT*)x, (const TT*)y, g, mean, invstd, gamma, beta, watt, batt, w1, (TT*)xb, logits)));
+  CLSKD_CHECK_LAUNCH(who);
+  return CLSKD_OK;
+}
+
+// workspace of clskd_abf_xs2_bwd: 16 bytes per row + the fp64 sums + the dx constants
+static int64_t xs2_ws_bytes(int B, int T, int F, int C) {
+  const int64_t M = (int64_t)B * T * F;
+  return M * 16 + (int64_t)sizeof(double) * (5 * (int64_t)C + R_NSCAL) + 64 + 256;
+}
+extern "C" int clskd_abf_xs2_bwd_workspace(int B, int T, int F, int C, int64_t* bytes) {
+  CLSKD_CHECK_ARG(bytes, "clskd_abf_xs2_bwd_workspace: null pointer");
+  *bytes = xs2_ws_bytes(B, T, F, C);
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_abf_xs2_bwd(const void* gout, const void* x, const float* w1, const void* y, int dtype, int B, int T,
+                                 int F, int Fy, int C, const float* mean, const float* invstd, const float* gamma,
+                                 const float* beta, const float* watt, const float* logits, int training, double* sums,
+                                 double* dwatt, double* dbatt, double* dw1, void* dx, void* dy, void* workspace,
+                                 int64_t ws_bytes, void* stream) {
+  const char* who = "clskd_abf_xs2_bwd";
+  CLSKD_CHECK_ARG(gout && x && w1 && y && mean && invstd && watt && logits && sums && dwatt && dbatt && dw1 && dx && dy &&
+                      workspace, "%s: null pointer", who);
+  if (const char* why = abf_unsupported(B, T, F, Fy, C, gout, y, dy)) {
+    set_error("%s: unsupported: %s", who, why);
+    return CLSKD_ERR_UNSUPPORTED;
+  }
+  CLSKD_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)workspace % 16) == 0 && C >= 16 && C <= 1024,
+                  "%s: x / workspace must be 16-byte aligned, 16 <= C <= 1024", who);
+  CLSKD_CHECK_ARG(ws_bytes >= xs2_ws_bytes(B, T, F, C), "%s: workspace too small", who);
+  AbfGeom g;
+  g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
+  g.cshift = ilog2(C); g.yshift = Fy == F ? 0 : 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  float4* rows = reinterpret_cast<float4*>(workspace);
+  double* acc = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(workspace) + g.M * 16);
+  float* dxc = reinterpret_cast<float*>(acc + 5 * (size_t)C + R_NSCAL);
+  cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * (5 * (size_t)C + R_NSCAL), st);
+  if (e != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+  const size_t es = dtype == CLSKD_F32 ? 4 : 2;
+  if (g.M > 0) {
+    const int64_t pairs = g.M / 2;
+    const int ppw = 32 / g.tpr;
+    const int grid = abf_grid((pairs + ppw - 1) / ppw / 4);
+    const size_t cbytes = (sizeof(float) * (X_NCONST * (size_t)C + XS_NSCAL + 5 * (size_t)C + R_NSCAL) + 15) & ~(size_t)15;
+    const size_t sh = cbytes + (size_t)PD * (4 * (es / 2) + 2) * AT * 16;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(abf_xs2_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(abf_xs2_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_xs2_bwd_kernel<TT><<<grid, AT, sh, st>>>(
+                                        (const TT*)gout, (const TT*)x, (const TT*)y, g, mean, invstd, gamma, beta, watt, w1,
+                                        logits, acc, rows, (TT*)dy)));
+    CLSKD_CHECK_LAUNCH(who);
+  }
+  abf_xs2_finalize_kernel<<<1, 256, 0, st>>>(acc, C, g.M > 0 ? 1.0 / (double)g.M : 0.0, training, mean, invstd, gamma, beta,
+                                            watt, w1, sums, dwatt, dbatt, dw1, dxc);
+  CLSKD_CHECK_LAUNCH(who);
+  if (g.M > 0) {
+    const int grid = ew_grid_abf(g.M);
+    CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_xs2_dx_kernel<TT><<<grid, 256, 0, st>>>(rows, (const TT*)x, g.M, dxc, (TT*)dx)));
+    CLSKD_CHECK_LAUNCH(who);
+  }
+  return CLSKD_OK;
 }
 
 // column sums of z = W1 x for a 2-channel x from the moments of x: sum_c = w0 S0 + w1 S1,

@@ -599,7 +599,7 @@ static int launch_cfg(const ClskdTapConv* d, const FwdCfg& cfg, void* stream) {
     p.a_tx = (uint32_t)box_f * box_t * pitch_a;
     p.a_bytes = pad1k(p.a_tx);
     // several TMA boxes per patch: the TMA unit keeps more row requests in flight across boxes than inside one
-    int split = (mode != 1 && box_t > 1) ? 2 : 1;
+    int split = 1;       // measured: one box per patch is at least as fast as one per time row (tools/kbench.py)
     if (cfg.split) split = cfg.split;
     if (split == 2 && box_t > 1) { p.a_nbox = box_t; p.a_box_t = 1; }
     else { p.a_nbox = 1; p.a_box_t = box_t; }

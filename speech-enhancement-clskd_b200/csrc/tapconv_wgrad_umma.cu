@@ -9,6 +9,11 @@
 // 64/32/16-channel swizzle group, the tap only shifts the box coordinates (zero fill outside the
 // tensor = conv padding), the skip connection is a second tensor map (no materialised concat).
 //
+// Operand reuse: taps are grouped and a group loads ONE activation patch per row tile; each tap's A tile is that
+// patch read through a shared-memory descriptor shifted by whole rows (the swizzle XOR is a function of the absolute
+// address: profiles/r02_hw_desc_shift.log) - "full" halo patch for 128-wide frequency tiles at stride 1, time-grouped
+// patches otherwise, one box per tap as the fallback.
+//
 // One CTA owns (tap group g, 128-channel tile, n tile) and a contiguous range of row patches: the
 // accumulators D_j of the G = 512/n_tile taps of its group live in TMEM for the whole range (the
 // dY patch is loaded once per row patch and shared by the G taps), and are added to dW with fp32
@@ -31,7 +36,11 @@ struct WgradParams {
   int t_tile, fo_tile, f_tiles, t_tiles;
   int n_row_tiles, tiles_per_cta;
   int ntaps, G, ngroups, c_tiles, n_tiles, n_tile;
-  int tap_t[CLSKD_MAX_TAPS], tap_p[CLSKD_MAX_TAPS], tap_f[CLSKD_MAX_TAPS];
+  // taps in patch-group order: tap_w = tap index in dW, tap_pg = patch group, tap_roff = first row of the tap's
+  // 128-row tile inside the patch; patch group coordinates (parity, f shift, t shift) relative to the tile origin
+  int tap_w[CLSKD_MAX_TAPS], tap_pg[CLSKD_MAX_TAPS], tap_roff[CLSKD_MAX_TAPS];
+  int pg_p[CLSKD_MAX_TAPS], pg_f[CLSKD_MAX_TAPS], pg_t[CLSKD_MAX_TAPS];
+  uint32_t a_stage_bytes;              // one patch: nsub_a sub-blocks of a_sub_bytes
   int gw_a, gw_b;                      // swizzle group widths in elements (64 / 32 / 16)
   int c0, Ctot, N;
   uint32_t a_sub_bytes, b_sub_bytes, b_stage_bytes;
@@ -110,15 +119,16 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
           tma_load_4d(b_buf + (size_t)bs * p.b_stage_bytes + (size_t)s * p.b_sub_bytes, &tmDY, &b_full[bs],
                       n0 + s * p.gw_b, f0, t0, b);
         for (int g = 0; g < gcur; ++g) {
-          const int tap = tap0 + g;
+          const int j = tap0 + g;
+          if (g > 0 && p.tap_pg[j] == p.tap_pg[j - 1]) continue;        // same patch as the previous tap
+          const int pg = p.tap_pg[j];
           mbar_wait(&a_empty[stage], phase ^ 1u);
           mbar_expect_tx(&a_full[stage], (uint32_t)nsub_a * p.a_sub_bytes);
           for (int s = 0; s < nsub_a; ++s) {
             const int cc = cbase + s * p.gw_a;
             const bool src0 = cc < p.c0;
-            tma_load_5d(a_buf + (size_t)stage * A_STAGE + (size_t)s * p.a_sub_bytes, src0 ? &tmA0 : &tmA1,
-                        &a_full[stage], src0 ? cc : cc - p.c0, p.tap_p[tap], f0 + p.tap_f[tap],
-                        t0 + p.tap_t[tap], b);
+            tma_load_5d(a_buf + (size_t)stage * p.a_stage_bytes + (size_t)s * p.a_sub_bytes, src0 ? &tmA0 : &tmA1,
+                        &a_full[stage], src0 ? cc : cc - p.c0, p.pg_p[pg], f0 + p.pg_f[pg], t0 + p.pg_t[pg], b);
           }
           if (++stage == p.a_stages) {
             stage = 0;
@@ -141,9 +151,12 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
         mbar_wait(&b_full[bs], (it >> 1) & 1);
         const uint32_t b_addr = smem_u32(b_buf + (size_t)bs * p.b_stage_bytes);
         for (int g = 0; g < gcur; ++g) {
-          mbar_wait(&a_full[stage], phase);
-          fence_after();
-          const uint32_t a_addr = smem_u32(a_buf + (size_t)stage * A_STAGE);
+          const int j = tap0 + g;
+          if (g == 0 || p.tap_pg[j] != p.tap_pg[j - 1]) {               // first tap of a patch: wait for it
+            mbar_wait(&a_full[stage], phase);
+            fence_after();
+          }
+          const uint32_t a_addr = smem_u32(a_buf + (size_t)stage * p.a_stage_bytes) + (uint32_t)p.tap_roff[j] * pitch_a;
 #pragma unroll
           for (int k = 0; k < ROWS / 16; ++k) {
             const uint64_t adesc = make_smem_desc_lbo(a_addr + (uint32_t)k * 16u * pitch_a, p.a_sub_bytes >> 4,
@@ -152,10 +165,12 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
                                                       (8u * pitch_b) >> 4, p.layout_b);
             umma_bf16(tmem_base + (uint32_t)(g * p.n_tile), adesc, bdesc, idesc, (it | k) ? 1u : 0u);
           }
-          umma_commit(&a_empty[stage]);
-          if (++stage == p.a_stages) {
-            stage = 0;
-            phase ^= 1u;
+          if (g == gcur - 1 || p.tap_pg[j + 1] != p.tap_pg[j]) {        // last tap of the patch: release the stage
+            umma_commit(&a_empty[stage]);
+            if (++stage == p.a_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
         umma_commit(&b_empty[bs]);
@@ -170,7 +185,7 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
     mbar_wait(&tmem_full_bar, 0);
     fence_after();
     for (int g = 0; g < gcur; ++g) {
-      float* dst = p.dw + ((int64_t)(tap0 + g) * p.Ctot + c_glob) * p.N + n0;
+      float* dst = p.dw + ((int64_t)p.tap_w[tap0 + g] * p.Ctot + c_glob) * p.N + n0;
       for (int c = 0; c < p.n_tile; c += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile + c), v);

@@ -459,3 +459,34 @@ def test_umma_operand_reuse_modes_vs_torch(cuda_dev, cin, cout, F, T, B, ks, tun
         lib.clskd_set_tuning(1, 0)
     y = y.permute(0, 3, 2, 1).cpu()
     assert (y - ref).abs().max().item() < 2e-5 * max(ref.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("C,F,T,B,up,training", [(128, 32, 21, 2, True, True), (64, 16, 40, 3, False, True), (128, 64, 9, 1, True, False),
+                                                 (256, 8, 30, 2, True, True)])
+def test_abf_xs2_kernels_vs_round1_xs_kernels_fp32(cuda_dev, C, F, T, B, up, training):
+    """rank-2 folded 2-channel ABF middle stage (clskd_abf_xs2_fwd / _bwd: one backward pass + finalisation + dx pass)
+    against the round-1 kernels that recompute z1 per element in two passes, on fp32 tensors (same math, different
+    association): outputs and every gradient to fp32 rounding."""
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(C + F)
+    Fy = F // 2 if up else F
+    xs = torch.randn(B, T, F, 2, generator=g)
+    yp = torch.randn(B, T, Fy, C, generator=g)
+    w1 = 0.5 * torch.randn(C, 2, 1, 1, generator=g)
+    gamma, beta = 0.5 + torch.rand(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    watt, batt = 0.1 * torch.randn(2, 2 * C, 1, 1, generator=g), 0.2 * torch.randn(2, generator=g)
+    rm, rv = 0.1 * torch.randn(C, generator=g), 0.5 + torch.rand(C, generator=g)
+    up_g = torch.randn(B, T, F, C, generator=g)
+    res = {}
+    for xs2 in (True, False):
+        ops.policy.abf_xs2 = xs2
+        leaves = [t.clone().to(cuda_dev).requires_grad_(True) for t in (xs, yp, w1, gamma, beta, watt, batt)]
+        out = ops.AbfMidXsFn.apply(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[5], leaves[6],
+                                   rm.clone().to(cuda_dev), rv.clone().to(cuda_dev), training, 0.1, 1e-5)
+        (out * up_g.to(cuda_dev)).sum().backward()
+        res[xs2] = [out.detach().cpu()] + [t.grad.detach().cpu() for t in leaves]
+    ops.policy.abf_xs2 = True
+    names = ["xb", "dx", "dy", "dw1", "dgamma", "dbeta", "dwatt", "dbatt"]
+    for n, a, b in zip(names, res[True], res[False]):
+        s = max(b.abs().max().item(), 1e-6)
+        assert (a - b).abs().max().item() < 2e-4 * s, n

@@ -293,10 +293,12 @@ def test_complex_lstm_teacher_width_bptt(cuda_dev, policy):
     assert max(errs.values()) < tol, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
 
 
-@pytest.mark.parametrize("mid,cin,F,T,B,up", [(128, 64, 32, 41, 3, True), (128, 16, 128, 23, 2, True), (64, 32, 16, 40, 3, False)])
+@pytest.mark.parametrize("mid,cin,F,T,B,up", [(128, 64, 32, 41, 3, True), (128, 16, 128, 23, 2, True), (64, 32, 16, 40, 3, False),
+                                              (128, 2, 64, 21, 2, True), (64, 2, 32, 33, 3, False)])
 def test_bf16_abf_block_vs_oracle(cuda_dev, mid, cin, F, T, B, up):
     """One ABF level under the bf16 policy (fused BN + resize + attention + blend kernels, tcgen05 1x1 and 3x3
-    convs with the fused-statistics epilogue) against oracle.losses_oracle.abf_forward and its autograd."""
+    convs with the fused-statistics epilogue; cin = 2: the rank-2 folded clskd_abf_xs2_* kernels of the mask-level
+    map) against oracle.losses_oracle.abf_forward and its autograd."""
     import clskd_b200
     from clskd_b200 import framework as fw
     from oracle import losses_oracle as LO
