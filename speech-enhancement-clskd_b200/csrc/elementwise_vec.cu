@@ -71,43 +71,26 @@ __global__ void __launch_bounds__(VT) colstats_vec_kernel(const T* __restrict__ 
     sl = slope ? slope[0] : 1.f;
   }
   if (rs < rows_par) {
-    // UN independent 16-byte loads per operand in flight per thread (the kernel is HBM-latency bound otherwise)
-    constexpr int UN = MODE == 0 ? 4 : 2;
-    const int64_t stride = (int64_t)gridDim.x * rows_par;
-    for (int64_t m0 = (int64_t)blockIdx.x * rows_par + rs; m0 < M; m0 += UN * stride) {
-      float v[UN][8], d[UN][8];
+    for (int64_t m = (int64_t)blockIdx.x * rows_par + rs; m < M; m += (int64_t)gridDim.x * rows_par) {
+      float v[8];
+      ld8(x + m * C + cg * 8, v);
+      if (MODE == 0) {
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int64_t m = m0 + u * stride;
-        if (m < M) {
-          ld8(x + m * C + cg * 8, v[u]);
-          if (MODE == 1) ld8(dy + m * C + cg * 8, d[u]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            v[u][e] = MODE == 1 ? mu[e] : 0.f;      // contributes exactly zero below
-            d[u][e] = 0.f;
-          }
+        for (int e = 0; e < 8; ++e) {
+          a0[e] += v[e];
+          a1[e] = fmaf(v[e], v[e], a1[e]);
         }
-      }
+      } else {
+        float d[8];
+        ld8(dy + m * C + cg * 8, d);
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        if (MODE == 0) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            a0[e] += v[u][e];
-            a1[e] = fmaf(v[u][e], v[u][e], a1[e]);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float xh = (v[u][e] - mu[e]) * is[e];
-            const float uu = fmaf(xh, g[e], bt[e]);
-            const float dz = uu > 0.f ? d[u][e] : d[u][e] * sl;
-            a0[e] += dz;
-            a1[e] = fmaf(dz, xh, a1[e]);
-            a2 += uu > 0.f ? 0.f : d[u][e] * uu;
-          }
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (v[e] - mu[e]) * is[e];
+          const float u = fmaf(xh, g[e], bt[e]);
+          const float dz = u > 0.f ? d[e] : d[e] * sl;
+          a0[e] += dz;
+          a1[e] = fmaf(dz, xh, a1[e]);
+          a2 += u > 0.f ? 0.f : d[e] * u;
         }
       }
     }

@@ -39,6 +39,7 @@
 #include "umma.cuh"
 
 namespace clskd {
+extern int g_wgrad_mode;               // tapconv_wgrad_umma.cu
 namespace {
 using namespace umma;
 
@@ -461,6 +462,7 @@ extern "C" int clskd_set_tuning(int key, int value) {
     case 3: g_tune_v1 = value; return CLSKD_OK;
     case 4: g_tune_split = value; return CLSKD_OK;
     case 5: g_tune_noauto = value; return CLSKD_OK;
+    case 6: g_wgrad_mode = value; return CLSKD_OK;
     default: set_error("clskd_set_tuning: unknown key %d", key); return CLSKD_ERR_ARG;
   }
 }

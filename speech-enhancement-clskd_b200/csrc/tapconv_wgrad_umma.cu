@@ -23,12 +23,12 @@
 #include "umma.cuh"
 
 namespace clskd {
+int g_wgrad_mode = 0;                  // clskd_set_tuning key 6: 1 one box per tap, 2 time-grouped patches at most
 namespace {
 using namespace umma;
 
 constexpr int kThreads = 192;
 constexpr int ROWS = 128;              // rows (GEMM K) per smem patch
-constexpr uint32_t A_STAGE = 32768;    // 128 rows x 128 channels x bf16
 constexpr int MAX_A_STAGES = 4;
 
 struct WgradParams {
@@ -265,31 +265,93 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
   CLSKD_CHECK_ARG(nrt <= 2147483647LL, "clskd_tapconv_wgrad_umma: too many row patches");
   p.n_row_tiles = (int)nrt;
   p.ntaps = d->ntaps;
+  int tt[CLSKD_MAX_TAPS], tpar[CLSKD_MAX_TAPS], tf[CLSKD_MAX_TAPS];
+  int tmin = 1 << 30, tmax = -(1 << 30), fmin = 1 << 30, fmax = -(1 << 30);
   for (int j = 0; j < d->ntaps; ++j) {
     int df = d->df[j];
     int fl = df >= 0 ? df / d->sf : -((-df + d->sf - 1) / d->sf);
-    p.tap_t[j] = d->dt[j];
-    p.tap_f[j] = fl;
-    p.tap_p[j] = df - fl * d->sf;
+    tt[j] = d->dt[j];
+    tf[j] = fl;
+    tpar[j] = df - fl * d->sf;
+    tmin = tt[j] < tmin ? tt[j] : tmin; tmax = tt[j] > tmax ? tt[j] : tmax;
+    fmin = fl < fmin ? fl : fmin; fmax = fl > fmax ? fl : fmax;
   }
   p.n_tile = d->N <= 256 ? d->N : (d->N % 256 == 0 ? 256 : 128);
   p.n_tiles = d->N / p.n_tile;
   p.G = 512 / p.n_tile;
   if (p.G > d->ntaps) p.G = d->ntaps;
-  p.ngroups = cdiv(d->ntaps, p.G);
   p.c_tiles = cdiv(Ctot, 128);
   p.gw_a = pick_gw(d->c0, d->c1);
   p.gw_b = pick_gw(p.n_tile, 0);
   p.c0 = d->c0; p.Ctot = Ctot; p.N = d->N;
-  p.a_sub_bytes = (uint32_t)ROWS * p.gw_a * 2;
   p.b_sub_bytes = (uint32_t)ROWS * p.gw_b * 2;
   p.b_stage_bytes = ((uint32_t)ROWS * p.n_tile * 2 + 1023u) & ~1023u;
   p.layout_a = layout_for_bytes(p.gw_a * 2);
   p.layout_b = layout_for_bytes(p.gw_b * 2);
-  int stages = (int)((200u * 1024u - 2u * p.b_stage_bytes) / A_STAGE);
-  if (stages > MAX_A_STAGES) stages = MAX_A_STAGES;
+  const int nsub_max = (Ctot < 128 ? Ctot : 128) / p.gw_a;
+  const uint32_t kBudget = 222u * 1024u;
+  // ---- patch grouping: 3 full halo patch (all taps in one CTA), 2 time-grouped patches, 1 one box per tap
+  const bool full_ok = d->sf == 1 && p.fo_tile == ROWS && d->ntaps > 1 && p.G >= d->ntaps &&
+                       ((ROWS + (fmax - fmin) + 7) & ~7) <= 256 && (p.t_tile + (tmax - tmin)) <= 16;
+  const bool time_ok = d->ntaps > 1 && p.fo_tile % 8 == 0 && p.t_tile > 1 && tmax > tmin && (p.t_tile + (tmax - tmin)) <= 256;
+  int mode = full_ok ? 3 : (time_ok ? 2 : 1);
+  if (g_wgrad_mode == 1) mode = 1;
+  if (g_wgrad_mode == 2) mode = time_ok ? 2 : 1;
+  int box_f = p.fo_tile, box_t = p.t_tile;
+  int stages = 0;
+  for (;;) {
+    box_f = p.fo_tile;
+    box_t = p.t_tile;
+    int npg = 0;
+    if (mode == 3) {
+      box_f = (ROWS + (fmax - fmin) + 7) & ~7;
+      box_t = p.t_tile + (tmax - tmin);
+      npg = 1;
+      p.pg_p[0] = 0; p.pg_f[0] = fmin; p.pg_t[0] = tmin;
+      for (int j = 0; j < d->ntaps; ++j) {
+        p.tap_w[j] = j;
+        p.tap_pg[j] = 0;
+        p.tap_roff[j] = (tt[j] - tmin) * box_f + (tf[j] - fmin);
+      }
+    } else if (mode == 2) {
+      box_t = p.t_tile + (tmax - tmin);
+      bool used[CLSKD_MAX_TAPS] = {false};
+      int n = 0;
+      for (int j = 0; j < d->ntaps; ++j) {
+        if (used[j]) continue;
+        p.pg_p[npg] = tpar[j]; p.pg_f[npg] = tf[j]; p.pg_t[npg] = tmin;
+        for (int i = j; i < d->ntaps; ++i)
+          if (!used[i] && tpar[i] == tpar[j] && tf[i] == tf[j]) {
+            used[i] = true;
+            p.tap_w[n] = i;
+            p.tap_pg[n] = npg;
+            p.tap_roff[n] = (tt[i] - tmin) * box_f;
+            ++n;
+          }
+        ++npg;
+      }
+      // taps per CTA: whole patch groups where possible (a group cut by the CTA boundary is loaded twice)
+      const int gsz = tmax - tmin + 1;
+      if (p.G < d->ntaps && p.G > gsz && d->ntaps % gsz == 0) p.G = p.G / gsz * gsz;
+    } else {
+      npg = d->ntaps;
+      for (int j = 0; j < d->ntaps; ++j) {
+        p.tap_w[j] = j;
+        p.tap_pg[j] = j;
+        p.tap_roff[j] = 0;
+        p.pg_p[j] = tpar[j]; p.pg_f[j] = tf[j]; p.pg_t[j] = tt[j];
+      }
+    }
+    p.a_sub_bytes = (uint32_t)box_f * box_t * p.gw_a * 2;
+    p.a_stage_bytes = ((uint32_t)nsub_max * p.a_sub_bytes + 1023u) & ~1023u;
+    stages = (int)((kBudget - 1024u - 2u * p.b_stage_bytes) / p.a_stage_bytes);
+    if (stages > MAX_A_STAGES) stages = MAX_A_STAGES;
+    if (stages >= 2 || mode == 1) break;
+    mode = mode == 3 && time_ok ? 2 : 1;          // the patch does not fit twice: smaller patches
+  }
   if (stages < 2) stages = 2;
   p.a_stages = stages;
+  p.ngroups = cdiv(d->ntaps, p.G);
   int cols = 32;
   while (cols < p.G * p.n_tile) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
@@ -305,11 +367,11 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
   CUtensorMap tmA0, tmA1, tmDY;
   CUtensorMapSwizzle swa = swizzle_for_bytes(p.gw_a * 2), swb = swizzle_for_bytes(p.gw_b * 2);
   int rc = encode_act(enc, &tmA0, d->x0, d->c0, d->sf, d->Fi, d->Ti, d->B, d->x0_sB, d->x0_sT, d->x0_sF, p.gw_a,
-                      p.fo_tile, p.t_tile, swa);
+                      box_f, box_t, swa);
   if (rc) { set_error("clskd_tapconv_wgrad_umma: cuTensorMapEncodeTiled(x0) failed: %d", rc); return CLSKD_ERR_CUDA; }
   if (d->c1) {
     rc = encode_act(enc, &tmA1, d->x1, d->c1, d->sf, d->Fi, d->Ti, d->B, d->x1_sB, d->x1_sT, d->x1_sF, p.gw_a,
-                    p.fo_tile, p.t_tile, swa);
+                    box_f, box_t, swa);
     if (rc) { set_error("clskd_tapconv_wgrad_umma: cuTensorMapEncodeTiled(x1) failed: %d", rc); return CLSKD_ERR_CUDA; }
   } else {
     tmA1 = tmA0;
@@ -324,7 +386,7 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r) { set_error("clskd_tapconv_wgrad_umma: cuTensorMapEncodeTiled(dy) failed: %d", (int)r); return CLSKD_ERR_CUDA; }
   }
-  size_t smem = 2 * (size_t)p.b_stage_bytes + (size_t)p.a_stages * A_STAGE + 1024;
+  size_t smem = 2 * (size_t)p.b_stage_bytes + (size_t)p.a_stages * p.a_stage_bytes + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(tapconv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

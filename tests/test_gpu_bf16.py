@@ -175,9 +175,12 @@ def _wgrad_both_policies(cuda_dev, mod, inputs, ops):
     return res
 
 
+@pytest.mark.parametrize("wmode", [0, 1])
 @pytest.mark.parametrize("case", ["conv_64_128", "conv_32_64", "conv_16_32", "deconv_skip_128", "deconv_skip_64",
-                                  "abf3x3_128_256", "abf3x3_128_32", "abf1x1_32_128"])
-def test_umma_wgrad_vs_cuda_core(cuda_dev, case):
+                                  "abf3x3_128_256", "abf3x3_128_32", "abf1x1_32_128", "abf3x3F128_128_32",
+                                  "abf3x3F128_32_128", "abf3x3F256_64_48", "abf3x3F64_128_64"])
+def test_umma_wgrad_vs_cuda_core(cuda_dev, case, wmode):
+    """wmode 0: automatic operand reuse (full halo patch at F >= 128, time-grouped patches below); 1: one box per tap"""
     from clskd_b200 import framework as fw
     from clskd_b200 import ops
     from clskd_b200 import tools_for_model as tm
@@ -194,6 +197,11 @@ def test_umma_wgrad_vs_cuda_core(cuda_dev, case):
         mod = tm.ComplexConvTranspose2d(2 * c, c // 2, kernel_size=(5, 2), stride=(2, 1), padding=(2, 0),
                                         output_padding=(1, 0))
         inputs = (act(2, 33, 16, c), act(2, 33, 16, c))
+    elif case.startswith("abf3x3F"):
+        F_ = int(case.split("_")[0][7:])
+        cin, cout = (int(v) for v in case.split("_")[1:])
+        mod = fw.RealConv2d(cin, cout, 3, padding=1, bias=False)
+        inputs = (act(2, 9, F_, cin),)
     elif case.startswith("abf3x3_"):
         cin, cout = (int(v) for v in case.split("_")[1:])
         mod = fw.RealConv2d(cin, cout, 3, padding=1, bias=False)
@@ -204,7 +212,12 @@ def test_umma_wgrad_vs_cuda_core(cuda_dev, case):
         inputs = (act(2, 41, 64, cin),)
     _round_params(mod)
     mod = mod.to(cuda_dev)
-    res = _wgrad_both_policies(cuda_dev, mod, inputs, ops)
+    from clskd_b200 import _lib
+    _lib.load().clskd_set_tuning(6, wmode)
+    try:
+        res = _wgrad_both_policies(cuda_dev, mod, inputs, ops)
+    finally:
+        _lib.load().clskd_set_tuning(6, 0)
     assert res["bf16"][1] >= 2 and res["fp32"][1] == 0, "tcgen05 forward + wgrad launches expected"
     for k, gref in res["fp32"][0].items():
         gu = res["bf16"][0][k]
