@@ -19,7 +19,7 @@ namespace {
 using namespace umma;
 
 constexpr int kThreads = 192;
-constexpr int GF_STAGES = 8;
+constexpr int GF_STAGES = 6;                     // 6 x 16 KB per CTA: two CTAs per SM = 12 boxes in flight (was 8 with one CTA)
 constexpr uint32_t GF_STAGE_BYTES = 128 * 128;   // 128 rows x 64 bf16
 
 struct GramFwdParams {
@@ -28,7 +28,7 @@ struct GramFwdParams {
   float* G;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[GF_STAGES], empty_bar[GF_STAGES];

@@ -288,7 +288,9 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
   p.b_stage_bytes = ((uint32_t)ROWS * p.n_tile * 2 + 1023u) & ~1023u;
   p.layout_a = layout_for_bytes(p.gw_a * 2);
   p.layout_b = layout_for_bytes(p.gw_b * 2);
-  const int nsub_max = (Ctot < 128 ? Ctot : 128) / p.gw_a;
+  // the MMA always reads M = 128 channels = 128 / gw_a sub-blocks (rows of absent channels are discarded by the
+  // epilogue), so a stage must span all of them even when fewer are loaded
+  const int nsub_max = 128 / p.gw_a;
   const uint32_t kBudget = 222u * 1024u;
   // ---- patch grouping: 3 full halo patch (all taps in one CTA), 2 time-grouped patches, 1 one box per tap
   const bool full_ok = d->sf == 1 && p.fo_tile == ROWS && d->ntaps > 1 && p.G >= d->ntaps &&
