@@ -73,6 +73,8 @@ def parse():
     ap.add_argument("--only", default=None, choices=list(EXTRAS), help="child mode: measure one extra object")
     ap.add_argument("--overlap-abf", type=int, default=None, help="1/0: encoder-side ABF chain on a second stream")
     ap.add_argument("--dump-launches", default=None, help="write per-launch shapes/times of the profiled kernel here")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     ap.add_argument("--profile-kernel", default="auto",
                     help="C-ABI entry point timed with CUDA events for the roofline object")
     return ap.parse_args()
@@ -319,6 +321,17 @@ def _load_traffic(kname):
     return None, None
 
 
+def _tuning_stats(_lib):
+    """shapes the forward kernel's per-shape autotuner timed in this process / how many kept the round-1 configuration"""
+    import ctypes
+    try:
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.load().clskd_tuning_stats(ctypes.byref(a), ctypes.byref(b))
+        return {"shapes_tuned": a.value, "kept_round1_config": b.value}
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     import clskd_b200
@@ -380,6 +393,16 @@ def run_ours(args):
     for _ in range(args.warmup):
         tr.train_step(X, y)
     barrier()
+    if args.profile_step:
+        tr.step_fn.overlap_teacher = tr.step_fn.overlap_abf = False      # ncu serialises kernels anyway
+        tr.train_step(X, y)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        tr.train_step(X, y)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"profiled": "one %s step, %d x %.0f s" % (args.mode, B, args.seconds)}), flush=True)
+        return
     # ---------------- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
     if rank == 0:
@@ -485,7 +508,7 @@ def run_ours(args):
             "step_tflops": step_gflop / 1e3 / (ms / args.steps / 1e3) if ms > 0 else None,
             "loss": float(loss), "loss_e2e": loss_host,
             "umma_launches": clskd_b200.ops.umma_launches, "core_launches": clskd_b200.ops.core_launches,
-            "max_mem_gb": max_mem,
+            "max_mem_gb": max_mem, "autotune": _tuning_stats(_lib),
         }
         if args.dump_launches:
             rows = []

@@ -107,7 +107,7 @@ int clskd_tapconv_umma_supported(const ClskdTapConv* d);
  *          (device-wide synchronisation, once per shape and process) and caches the fastest; also disabled by
  *          the environment variable CLSKD_AUTOTUNE=0.
  *   key 6: weight-gradient kernel (clskd_tapconv_wgrad_umma): 1 = one TMA box per tap, 2 = time-grouped patches
- *          at most (no full halo patch) */
+ *          at most (no full halo patch), 3 = patches wherever the geometry allows (automatic: only for N >= 128) */
 int clskd_set_tuning(int key, int value);
 /* the round-1 forward kernel (one TMA box per tap, weights through the ring): A/B baseline only */
 int clskd_tapconv_fwd_umma_v1(const ClskdTapConv* d, void* stream);

@@ -297,6 +297,10 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
                        ((ROWS + (fmax - fmin) + 7) & ~7) <= 256 && (p.t_tile + (tmax - tmin)) <= 16;
   const bool time_ok = d->ntaps > 1 && p.fo_tile % 8 == 0 && p.t_tile > 1 && tmax > tmin && (p.t_tile + (tmax - tmin)) <= 256;
   int mode = full_ok ? 3 : (time_ok ? 2 : 1);
+  // measured (profiles/r02_step_breakdown_d/e.json): patches pay for wide tiles (N >= 128 with >= 64 channels: -12 %);
+  // narrow-N launches are bound by the shared-memory operand reads of their MMAs and by stage depth, where the larger
+  // patch stages lose (+4 .. +15 %): those keep one box per tap.  g_wgrad_mode = 3 forces patches for tests.
+  if (g_wgrad_mode == 0 && !(p.n_tile >= 128 && Ctot >= 64)) mode = 1;
   if (g_wgrad_mode == 1) mode = 1;
   if (g_wgrad_mode == 2) mode = time_ok ? 2 : 1;
   int box_f = p.fo_tile, box_t = p.t_tile;
