@@ -757,6 +757,90 @@ __global__ void __launch_bounds__(256) tapconv_wgrad_smallk_kernel(ClskdTapConv 
   for (int i = threadIdx.x; i < Ktot * N; i += blockDim.x) atomicAdd(dw + i, red[i]);
 }
 
+
+// Weight gradient of a convolution with TWO input channels (first encoder layer: the interleaved spectrum, 5x2 taps,
+// frequency stride 2).  One block walks (b, t) lines: the <= 2 input time rows a line's taps touch are staged in shared
+// memory (zero padded in f, zero for t outside the map), thread (slot, n) owns output channel n of the output
+// frequencies slot, slot + S, ...: one coalesced dY read and NT broadcast float2 reads per (fo, n) feed 2*NT register
+// accumulators - no per-element bounds checks or address arithmetic (the generic small-K kernel spent its time there:
+// 184 GB/s).  Cross-slot and cross-block reductions in shared / global fp32 atomics.
+template <typename TY, int NT>
+__global__ void __launch_bounds__(256) tapconv_wgrad_c2_kernel(ClskdTapConv d, int tmin, int tspan, int fmin, int fspan) {
+  extern __shared__ float xs[];                  // [tspan][Fi + fspan][2] then red[NT*2][N]
+  const int N = d.N;
+  const int FW = d.Fi + fspan;                   // padded input line
+  float* red = xs + (size_t)tspan * FW * 2;
+  for (int i = threadIdx.x; i < NT * 2 * N; i += blockDim.x) red[i] = 0.f;
+  const int slots = blockDim.x / N;
+  const int n = threadIdx.x % N, slot = threadIdx.x / N;
+  int off[NT];                                    // float2 index of tap j for output frequency 0
+#pragma unroll
+  for (int j = 0; j < NT; ++j) off[j] = (d.dt[j] - tmin) * FW + (d.df[j] - fmin);
+  float2 acc[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j] = make_float2(0.f, 0.f);
+  const float* x = reinterpret_cast<const float*>(d.x0);
+  const TY* dy = reinterpret_cast<const TY*>(d.y);
+  const int64_t lines = (int64_t)d.B * d.To;
+  for (int64_t ln = blockIdx.x; ln < lines; ln += gridDim.x) {
+    const int b = (int)(ln / d.To), t = (int)(ln - (int64_t)b * d.To);
+    __syncthreads();
+    for (int i = threadIdx.x; i < tspan * FW; i += blockDim.x) {
+      const int tr = i / FW, fp = i - tr * FW;
+      const int ti = t + tmin + tr, fi = fp + fmin;
+      float2 v = make_float2(0.f, 0.f);
+      if (ti >= 0 && ti < d.Ti && fi >= 0 && fi < d.Fi)
+        v = *reinterpret_cast<const float2*>(x + (int64_t)b * d.x0_sB + (int64_t)ti * d.x0_sT + (int64_t)fi * d.x0_sF);
+      reinterpret_cast<float2*>(xs)[i] = v;
+    }
+    __syncthreads();
+    if (slot < slots) {
+      const TY* dyl = dy + (int64_t)b * d.y_sB + (int64_t)t * d.y_sT + n;
+      const float2* xl = reinterpret_cast<const float2*>(xs);
+      for (int fo = slot; fo < d.Fo; fo += slots) {
+        const float g = ld_f(dyl + (int64_t)fo * d.y_sF);
+        const int base = fo * d.sf;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float2 xv = xl[base + off[j]];
+          acc[j].x = fmaf(xv.x, g, acc[j].x);
+          acc[j].y = fmaf(xv.y, g, acc[j].y);
+        }
+      }
+    }
+  }
+  if (slot < slots) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      atomicAdd(&red[(j * 2) * N + n], acc[j].x);
+      atomicAdd(&red[(j * 2 + 1) * N + n], acc[j].y);
+    }
+  }
+  __syncthreads();
+  float* dw = reinterpret_cast<float*>(const_cast<void*>(d.w));
+  for (int i = threadIdx.x; i < NT * 2 * N; i += blockDim.x) atomicAdd(dw + i, red[i]);
+}
+
+// fp32 2-channel source with channel pairs 8-byte aligned, <= 2..3 time rows per line, N a power of two <= 256
+bool wgrad_c2_ok(const ClskdTapConv* d, int* tmin, int* tspan, int* fmin, int* fspan) {
+  if (d->c0 != 2 || d->c1 != 0 || d->x_dtype != CLSKD_F32 || d->accumulate) return false;
+  if (d->ntaps != 10 && d->ntaps != 9 && d->ntaps != 1) return false;
+  if (d->N < 8 || d->N > 256 || (d->N & (d->N - 1))) return false;
+  if (((uintptr_t)d->x0 % 8) || (d->x0_sB % 2) || (d->x0_sT % 2) || (d->x0_sF % 2)) return false;
+  int t0 = 1 << 30, t1 = -(1 << 30), f0 = 1 << 30, f1 = -(1 << 30);
+  for (int j = 0; j < d->ntaps; ++j) {
+    t0 = d->dt[j] < t0 ? d->dt[j] : t0; t1 = d->dt[j] > t1 ? d->dt[j] : t1;
+    f0 = d->df[j] < f0 ? d->df[j] : f0; f1 = d->df[j] > f1 ? d->df[j] : f1;
+  }
+  *tmin = t0; *tspan = t1 - t0 + 1; *fmin = f0;
+  // the last output frequency reads input (Fo-1)*sf + f1: pad the staged line so that index stays inside it
+  const int need = (d->Fo - 1) * d->sf + f1 - f0 + 1;
+  *fspan = need > d->Fi ? need - d->Fi : 0;
+  if (*fspan < f1 - f0) *fspan = f1 - f0;
+  const size_t sh = sizeof(float) * ((size_t)(*tspan) * (d->Fi + *fspan) * 2 + (size_t)d->ntaps * 2 * d->N);
+  return *tspan <= 3 && sh <= 96 * 1024;
+}
+
 bool smallk_ok(const ClskdTapConv* d, int* Ktot) {
   *Ktot = d->ntaps * (d->c0 + d->c1);
   if (*Ktot > SK_MAXK || d->N % 8 || d->N < 8 || d->N > 512 || d->accumulate) return false;
@@ -956,6 +1040,28 @@ extern "C" int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream) {
 #undef LAUNCH_W2
     CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad(n2)");
     return CLSKD_OK;
+  }
+  {
+    int tmin, tspan, fmin, fspan;
+    if (M >= 4096 && wgrad_c2_ok(d, &tmin, &tspan, &fmin, &fspan)) {
+      const size_t sh = sizeof(float) * ((size_t)tspan * (d->Fi + fspan) * 2 + (size_t)d->ntaps * 2 * d->N);
+      int64_t lines = (int64_t)d->B * d->To;
+      int blocks = sm_count() * 4;
+      if (blocks > lines) blocks = (int)lines;
+#define LAUNCH_C2(TY, NT)                                                                                       \
+  do {                                                                                                          \
+    cudaFuncSetAttribute(tapconv_wgrad_c2_kernel<TY, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+    tapconv_wgrad_c2_kernel<TY, NT><<<blocks, 256, sh, st>>>(*d, tmin, tspan, fmin, fspan);                     \
+  } while (0)
+      if (d->y_dtype == CLSKD_F32) {
+        if (d->ntaps == 10) LAUNCH_C2(float, 10); else if (d->ntaps == 9) LAUNCH_C2(float, 9); else LAUNCH_C2(float, 1);
+      } else {
+        if (d->ntaps == 10) LAUNCH_C2(__nv_bfloat16, 10); else if (d->ntaps == 9) LAUNCH_C2(__nv_bfloat16, 9); else LAUNCH_C2(__nv_bfloat16, 1);
+      }
+#undef LAUNCH_C2
+      CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad(c2)");
+      return CLSKD_OK;
+    }
   }
   int ktot_sk;
   if (smallk_ok(d, &ktot_sk) && M >= 1024 && d->N <= 256) {
