@@ -107,7 +107,8 @@ int clskd_tapconv_umma_supported(const ClskdTapConv* d);
  *          (device-wide synchronisation, once per shape and process) and caches the fastest; also disabled by
  *          the environment variable CLSKD_AUTOTUNE=0.
  *   key 6: weight-gradient kernel (clskd_tapconv_wgrad_umma): 1 = one TMA box per tap, 2 = time-grouped patches
- *          at most (no full halo patch), 3 = patches wherever the geometry allows (automatic: only for N >= 128) */
+ *          at most (no full halo patch), 3 = patches wherever the geometry allows (automatic: only for N >= 128),
+ *          4 = one box per tap inside the patch kernel instead of the round-1 kernel (tests) */
 int clskd_set_tuning(int key, int value);
 /* the round-1 forward kernel (one TMA box per tap, weights through the ring): A/B baseline only */
 int clskd_tapconv_fwd_umma_v1(const ClskdTapConv* d, void* stream);
@@ -124,6 +125,8 @@ int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream);
  * tensors/strides (see clskd_tapconv_wgrad_umma_supported). */
 int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream);
 int clskd_tapconv_wgrad_umma_supported(const ClskdTapConv* d);
+/* the round-1 weight-gradient kernel (one TMA box per tap); clskd_tapconv_wgrad_umma routes its narrow-N launches here */
+int clskd_tapconv_wgrad_umma_v1(const ClskdTapConv* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout / packing helpers
@@ -465,6 +468,12 @@ int clskd_axpby_f32(const float* x, const float* y, float a, float b, float* out
                     void* stream);
 /* out[0] = sum_i w[i]*in[i] over n fp32 scalars given as an array of device pointers is not
  * needed: losses are combined by the autograd graph on the host side. */
+
+/* out = in0 + in1 (+ in2 + in3), k in 2..4 dense same-dtype tensors of n elements, fp32 accumulation: the gradient
+ * accumulation of a tensor with several consumers (skip connection + next layer + feature tap), which autograd
+ * would otherwise do with its own add kernels.  16-byte aligned tensors. */
+int clskd_sum_n(const void* in0, const void* in1, const void* in2, const void* in3, int k, int dtype,
+                int64_t n, void* out, void* stream);
 
 /* fp64 -> fp32 scalar conversion with scaling: out[i] = (float)(in[i]*scale) */
 int clskd_f64_to_f32(const double* in, int n, double scale, float* out, void* stream);

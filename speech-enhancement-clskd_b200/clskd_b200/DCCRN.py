@@ -169,7 +169,8 @@ class DCCRN(nn.Module):
         encoder_out = []
         for layer in self.encoder:
             out = layer(out)
-            encoder_out.append(out)
+            skip, out = ops.fanout(out, 2)       # skip connection + next layer: gradients summed by one library kernel
+            encoder_out.append(skip)
         # ---- complex LSTM bottleneck
         x = to_phys(out, need_dense=True)
         F = x.shape[2]

@@ -6,6 +6,11 @@ alike, because the B200 model keeps the same submodule tree."""
 class DCCRN:
     def __init__(self, model):
         self.model = model
+        try:        # clskd_b200 models: sum the gradients of tapped tensors in the library
+            from .ops import fanout
+            self._fanout = fanout if type(model).__module__.startswith("clskd_b200") else None
+        except Exception:      # used on a reference model
+            self._fanout = None
         self.feature_maps = {"encoder": [], "decoder": [], "clstm": []}
         self._handles = []
         for blk in model.encoder:
@@ -21,7 +26,19 @@ class DCCRN:
 
     def _tap(self, key):
         def hook(module, inputs, output):
-            self.feature_maps[key].append(output)
+            # a tapped tensor has two consumers (the distillation loss and the rest of the model): hand out two
+            # aliases whose gradients the library sums with one kernel (ops.fanout; identity outside autograd)
+            fan = getattr(self, "_fanout", None)
+            if fan is None:
+                self.feature_maps[key].append(output)
+                return None
+            if isinstance(output, (list, tuple)):
+                pairs = [fan(o, 2) if hasattr(o, "requires_grad") else (o, o) for o in output]
+                self.feature_maps[key].append(type(output)(p[0] for p in pairs))
+                return type(output)(p[1] for p in pairs)
+            a, b = fan(output, 2)
+            self.feature_maps[key].append(a)
+            return b
         return hook
 
     # reference method names

@@ -316,8 +316,9 @@ class ABF(nn.Module):
             xp = self.conv1.forward_phys(to_phys(x))
         if out_shape is not None and xp.shape[2] != out_shape:
             xp = ResizeFFn.apply(xp, out_shape)
+        xp, res = ops.fanout(xp, 2)              # conv2 + residual of the next level
         out = self.conv2.forward_phys(xp)
-        return to_logical(out), to_logical(xp)
+        return to_logical(out), to_logical(res)
 
 
 class ReviewKD(nn.Module):

@@ -138,6 +138,79 @@ def dense(x: torch.Tensor, dtype=None) -> torch.Tensor:
     return strided_copy(x, dtype)
 
 
+class FanoutFn(torch.autograd.Function):
+    """k aliases of a tensor that has k consumers (skip connection + next layer + feature tap ...): the
+    gradients of the aliases are summed by ONE library kernel (clskd_sum_n, fp32 accumulation) instead of
+    autograd's chain of add kernels."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        ctx.set_materialize_grads(False)
+        return tuple(x.view_as(x) for _ in range(k))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gs = [g for g in gs if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        dt = gs[0].dtype
+        base = gs[0]
+        # sum in the memory order of the first gradient (they are all gradients of the same tensor, so they
+        # normally share it); anything else is made dense in that order first
+        ds = []
+        for g in gs:
+            if g.dtype != dt or g.stride() != base.stride() or not _is_dense(g):
+                g = _dense_like(g, base, dt)
+            ds.append(g)
+        if not _is_dense(base):
+            ds = [_dense_like(g, None, dt) for g in gs]
+        out = torch.empty_like(ds[0])
+        while len(ds) > 4:                     # more than four consumers: fold four at a time
+            part = torch.empty_like(ds[0])
+            call("clskd_sum_n", ds[0].data_ptr(), ds[1].data_ptr(), ds[2].data_ptr(), ds[3].data_ptr(), 4, _tag(dt),
+                 ds[0].numel(), part.data_ptr(), _stream())
+            ds = [part] + ds[4:]
+        p = [d_.data_ptr() for d_ in ds] + [None] * (4 - len(ds))
+        call("clskd_sum_n", p[0], p[1], p[2], p[3], len(ds), _tag(dt), ds[0].numel(), out.data_ptr(), _stream())
+        return out, None
+
+
+def _is_dense(t):
+    """occupies numel contiguous elements in SOME dimension order (e.g. a permuted view of a contiguous tensor)"""
+    if t.is_contiguous():
+        return True
+    if t.numel() == 0:
+        return True
+    order = sorted(range(t.dim()), key=lambda i: (-t.stride(i), -t.shape[i]))
+    exp = 1
+    for i in reversed(order):
+        if t.shape[i] != 1 and t.stride(i) != exp:
+            return False
+        exp *= t.shape[i]
+    return True
+
+
+def _dense_like(g, base, dtype):
+    """g re-laid out with base's strides (or contiguous when base is None / not dense) in `dtype`"""
+    if base is None or not _is_dense(base):
+        return dense(g, dtype)
+    out = torch.empty_strided(base.shape, base.stride(), dtype=dtype, device=g.device)
+    if g.dim() <= 4:
+        strided_copy_into(g, out)
+    else:
+        out.copy_(g)
+    return out
+
+
+def fanout(x, k=2):
+    """k aliases of x whose gradients are summed by the library (no-op outside autograd)"""
+    if k < 2 or not (torch.is_grad_enabled() and x.requires_grad):
+        return (x,) * k
+    return FanoutFn.apply(x, k)
+
+
 def to_phys(x_logical: torch.Tensor, dtype=None, need_dense=False) -> torch.Tensor:
     """logical [B, C, F, T] -> physical [B, T, F, C] with unit channel stride (a view whenever the
     logical tensor is itself a view of a physical one; copied by the layout kernel otherwise)."""

@@ -917,6 +917,40 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+
+// out = in0 + in1 (+ in2 + in3): gradient accumulation of a tensor with several consumers (what autograd's own
+// at::add would do), fp32 accumulation, 16-byte vectors with a scalar tail
+template <typename T, int K>
+__global__ void sum_n_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
+                             const T* __restrict__ d, int64_t n, T* __restrict__ out) {
+  constexpr int V = 16 / sizeof(T);
+  const int64_t nv = n / V;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc[V];
+    const T* src[4] = {a, b, c, d};
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src[k] + i * V);
+      const T* h = reinterpret_cast<const T*>(&u);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += ld_f(h + e);
+    }
+    uint4 o;
+    T* ho = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int e = 0; e < V; ++e) st_f(ho + e, acc[e]);
+    *reinterpret_cast<uint4*>(out + i * V) = o;
+  }
+  for (int64_t i = nv * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = ld_f(a + i) + ld_f(b + i);
+    if (K > 2) v += ld_f(c + i);
+    if (K > 3) v += ld_f(d + i);
+    st_f(out + i, v);
+  }
+}
+
 __global__ void fill_kernel(float* p, int64_t n, float v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
@@ -1542,5 +1576,20 @@ extern "C" int clskd_f64_to_f32(const double* in, int n, double scale, float* ou
   if (n == 0) return CLSKD_OK;
   f64_to_f32_kernel<<<cdiv(n, 128), 128, 0, ST>>>(in, n, scale, out);
   CLSKD_CHECK_LAUNCH("clskd_f64_to_f32");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_sum_n(const void* in0, const void* in1, const void* in2, const void* in3, int k, int dtype,
+                           int64_t n, void* out, void* stream) {
+  CLSKD_CHECK_ARG(in0 && in1 && out && k >= 2 && k <= 4 && (k < 3 || in2) && (k < 4 || in3), "clskd_sum_n: bad arguments");
+  CLSKD_CHECK_ARG(!(((uintptr_t)in0 | (uintptr_t)in1 | (uintptr_t)in2 | (uintptr_t)in3 | (uintptr_t)out) & 15),
+                  "clskd_sum_n: tensors must be 16-byte aligned");
+  if (n == 0) return CLSKD_OK;
+  const int grid = ew_grid(n / 4 + 1, 256);
+#define L(T, K) sum_n_kernel<T, K><<<grid, 256, 0, ST>>>((const T*)in0, (const T*)in1, (const T*)in2, (const T*)in3, n, (T*)out)
+  if (dtype == CLSKD_F32) { if (k == 2) L(float, 2); else if (k == 3) L(float, 3); else L(float, 4); }
+  else { if (k == 2) L(__nv_bfloat16, 2); else if (k == 3) L(__nv_bfloat16, 3); else L(__nv_bfloat16, 4); }
+#undef L
+  CLSKD_CHECK_LAUNCH("clskd_sum_n");
   return CLSKD_OK;
 }

@@ -320,6 +320,112 @@ __global__ void __launch_bounds__(PT) tapsum_fwd_kernel(const TZ* __restrict__ z
   }
 }
 
+
+// ---- tiled tap sum (stride 1, Ti == To, Fi == Fo): one block owns a TT x TF patch of output positions of one utterance.
+// Forward: the (TT + tspan) x (TF + fspan) patch of z rows is staged in shared memory with 16-byte loads (every z row is
+// read once per block instead of once per tap), then thread (t, f) gathers its <= 16 tap values; zero outside the map.
+// Backward: the patch of dy rows (N values each) is staged, thread (t, f) assembles and stores the whole dz row.
+constexpr int TS_TT = 4, TS_TF = 64;        // 256 output positions per block
+
+template <typename TZ, typename TY>
+__global__ void __launch_bounds__(256) tapsum_fwd_tiled_kernel(const TZ* __restrict__ z, int B, int T, int F, int Zc,
+                                                              TapList taps, int N, int tmin, int tspan, int fmin, int fspan,
+                                                              const float* __restrict__ bias, TY* __restrict__ y) {
+  extern __shared__ __align__(16) uint8_t ts_smem[];
+  const int PW = TS_TF + fspan, PH = TS_TT + tspan;
+  const int pitch = Zc * (int)sizeof(TZ) + 8;                       // +8 bytes: rows of consecutive f spread over the banks
+  const int f_tiles = (F + TS_TF - 1) / TS_TF, t_tiles = (T + TS_TT - 1) / TS_TT;
+  const int chunks = Zc * (int)sizeof(TZ) / 8;                       // 8-byte pieces per z row
+  for (int tile = blockIdx.x; tile < B * t_tiles * f_tiles; tile += gridDim.x) {
+    const int ft = tile % f_tiles;
+    int r = tile / f_tiles;
+    const int tt = r % t_tiles, b = r / t_tiles;
+    const int t0 = tt * TS_TT, f0 = ft * TS_TF;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PH * PW * chunks; i += 256) {
+      const int c = i % chunks;
+      int rr = i / chunks;
+      const int pf = rr % PW, pt = rr / PW;
+      const int ti = t0 + tmin + pt, fi = f0 + fmin + pf;
+      uint2 v = make_uint2(0u, 0u);
+      if (ti >= 0 && ti < T && fi >= 0 && fi < F)
+        v = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(z + (((int64_t)b * T + ti) * F + fi) * Zc) + 8 * c);
+      *reinterpret_cast<uint2*>(ts_smem + (size_t)rr * pitch + 8 * c) = v;
+    }
+    __syncthreads();
+    const int lt = threadIdx.x / TS_TF, lf = threadIdx.x % TS_TF;
+    const int t = t0 + lt, f = f0 + lf;
+    if (t < T && f < F) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < taps.n; ++j) {
+        const int pr = (lt + taps.dt[j] - tmin) * PW + (lf + taps.df[j] - fmin);
+        const TZ* zp = reinterpret_cast<const TZ*>(ts_smem + (size_t)pr * pitch) + j * N;
+        for (int n = 0; n < N; ++n) acc[n] += ld_f(zp + n);
+      }
+      TY* yo = y + (((int64_t)b * T + t) * F + f) * N;
+      for (int n = 0; n < N; ++n) st_f(yo + n, acc[n] + (bias ? bias[n] : 0.f));
+    }
+  }
+}
+
+template <typename TD, typename TZ>
+__global__ void __launch_bounds__(256) tapsum_bwd_tiled_kernel(const TD* __restrict__ dy, int B, int T, int F, int Zc,
+                                                              TapList taps, int N, int tmin, int tspan, int fmin, int fspan,
+                                                              TZ* __restrict__ dz) {
+  extern __shared__ __align__(16) uint8_t ts_smem[];
+  float* ps = reinterpret_cast<float*>(ts_smem);                     // [(TT + tspan) x (TF + fspan)][N] fp32
+  const int PW = TS_TF + fspan, PH = TS_TT + tspan;
+  const int f_tiles = (F + TS_TF - 1) / TS_TF, t_tiles = (T + TS_TT - 1) / TS_TT;
+  for (int tile = blockIdx.x; tile < B * t_tiles * f_tiles; tile += gridDim.x) {
+    const int ft = tile % f_tiles;
+    int r = tile / f_tiles;
+    const int tt = r % t_tiles, b = r / t_tiles;
+    const int t0 = tt * TS_TT, f0 = ft * TS_TF;
+    __syncthreads();
+    // dz[(t,f)][j] = dy[(t - dt_j, f - df_j)]: the patch spans t0 - tmax .. t0 + TT - 1 - tmin (same extents, mirrored)
+    for (int i = threadIdx.x; i < PH * PW * N; i += 256) {
+      const int n = i % N;
+      int rr = i / N;
+      const int pf = rr % PW, pt = rr / PW;
+      const int ti = t0 - (tmin + tspan) + pt, fi = f0 - (fmin + fspan) + pf;
+      float v = 0.f;
+      if (ti >= 0 && ti < T && fi >= 0 && fi < F) v = ld_f(dy + (((int64_t)b * T + ti) * F + fi) * N + n);
+      ps[i] = v;
+    }
+    __syncthreads();
+    const int lt = threadIdx.x / TS_TF, lf = threadIdx.x % TS_TF;
+    const int t = t0 + lt, f = f0 + lf;
+    if (t < T && f < F) {
+      TZ* zo = dz + (((int64_t)b * T + t) * F + f) * Zc;
+      for (int c0 = 0; c0 < Zc; c0 += 8) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = c0 + e;
+          const int j = c / N, n = c - j * N;
+          float v = 0.f;
+          if (j < taps.n) {
+            const int pr = (lt - taps.dt[j] + tmin + tspan) * PW + (lf - taps.df[j] + fmin + fspan);
+            v = ps[pr * N + n];
+          }
+          o[e] = v;
+        }
+        st8(zo + c0, o);
+      }
+    }
+  }
+}
+
+struct TapExt { int tmin, tspan, fmin, fspan; };
+static TapExt tap_extents(const TapList& tl) {
+  int t0 = 1 << 30, t1 = -(1 << 30), f0 = 1 << 30, f1 = -(1 << 30);
+  for (int j = 0; j < tl.n; ++j) {
+    t0 = tl.dt[j] < t0 ? tl.dt[j] : t0; t1 = tl.dt[j] > t1 ? tl.dt[j] : t1;
+    f0 = tl.df[j] < f0 ? tl.df[j] : f0; f1 = tl.df[j] > f1 ? tl.df[j] : f1;
+  }
+  return TapExt{t0, t1 - t0, f0, f1 - f0};
+}
+
 // one thread per (input position, 8-channel group) of dz
 template <typename TD, typename TZ>
 __global__ void __launch_bounds__(PT) tapsum_bwd_kernel(const TD* __restrict__ dy, int B, int Ti, int Fi, int To,
@@ -473,6 +579,29 @@ extern "C" int clskd_tapsum_fwd(const void* z, int z_dtype, int B, int Ti, int F
   for (int j = 0; j < ntaps; ++j) { tl.dt[j] = dt_host[j]; tl.df[j] = df_host[j]; }
   const int grid = pw_grid(M);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const TapExt te = tap_extents(tl);
+    const int zes = z_dtype == CLSKD_F32 ? 4 : 2;
+    const size_t sh = (size_t)(TS_TT + te.tspan) * (TS_TF + te.fspan) * (Zc * zes + 8);
+    if (sf == 1 && Ti == To && Fi == Fo && M >= 65536 && (Zc * zes) % 8 == 0 && ((uintptr_t)z % 8) == 0 && te.tspan <= 4 &&
+        te.fspan <= 8 && sh <= 96 * 1024) {
+      const int64_t tiles = (int64_t)B * cdiv(To, TS_TT) * cdiv(Fo, TS_TF);
+      const int g2 = (int)(tiles < (int64_t)sm_count() * 8 ? tiles : (int64_t)sm_count() * 8);
+#define LT(TZ, TY)                                                                                                   \
+  do {                                                                                                               \
+    cudaFuncSetAttribute(tapsum_fwd_tiled_kernel<TZ, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);   \
+    tapsum_fwd_tiled_kernel<TZ, TY><<<g2, 256, sh, st>>>((const TZ*)z, B, To, Fo, Zc, tl, N, te.tmin, te.tspan, te.fmin, \
+                                                        te.fspan, bias, (TY*)y);                                     \
+  } while (0)
+      if (z_dtype == CLSKD_F32 && y_dtype == CLSKD_F32) LT(float, float);
+      else if (z_dtype == CLSKD_F32) LT(float, __nv_bfloat16);
+      else if (y_dtype == CLSKD_F32) LT(__nv_bfloat16, float);
+      else LT(__nv_bfloat16, __nv_bfloat16);
+#undef LT
+      CLSKD_CHECK_LAUNCH("clskd_tapsum_fwd(tiled)");
+      return CLSKD_OK;
+    }
+  }
 #define L(TZ, TY) tapsum_fwd_kernel<TZ, TY><<<grid, PT, 0, st>>>((const TZ*)z, B, Ti, Fi, To, Fo, sf, Zc, tl, N, bias, (TY*)y)
   if (z_dtype == CLSKD_F32 && y_dtype == CLSKD_F32) L(float, float);
   else if (z_dtype == CLSKD_F32) L(float, __nv_bfloat16);
@@ -498,6 +627,23 @@ extern "C" int clskd_tapsum_bwd(const void* dy, int dy_dtype, int B, int Ti, int
   for (int j = 0; j < ntaps; ++j) { tl.dt[j] = dt_host[j]; tl.df[j] = df_host[j]; }
   const int grid = pw_grid(M * (Zc / 8));
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const TapExt te = tap_extents(tl);
+    const size_t sh = sizeof(float) * (size_t)(TS_TT + te.tspan) * (TS_TF + te.fspan) * N;
+    if (sf == 1 && Ti == To && Fi == Fo && M >= 65536 && te.tspan <= 4 && te.fspan <= 8) {
+      const int64_t tiles = (int64_t)B * cdiv(To, TS_TT) * cdiv(Fo, TS_TF);
+      const int g2 = (int)(tiles < (int64_t)sm_count() * 8 ? tiles : (int64_t)sm_count() * 8);
+#define LT(TD, TZ) tapsum_bwd_tiled_kernel<TD, TZ><<<g2, 256, sh, st>>>((const TD*)dy, B, To, Fo, Zc, tl, N, te.tmin, te.tspan, \
+                                                                       te.fmin, te.fspan, (TZ*)dz)
+      if (dy_dtype == CLSKD_F32 && dz_dtype == CLSKD_F32) LT(float, float);
+      else if (dy_dtype == CLSKD_F32) LT(float, __nv_bfloat16);
+      else if (dz_dtype == CLSKD_F32) LT(__nv_bfloat16, float);
+      else LT(__nv_bfloat16, __nv_bfloat16);
+#undef LT
+      CLSKD_CHECK_LAUNCH("clskd_tapsum_bwd(tiled)");
+      return CLSKD_OK;
+    }
+  }
 #define L(TD, TZ) tapsum_bwd_kernel<TD, TZ><<<grid, PT, 0, st>>>((const TD*)dy, B, Ti, Fi, To, Fo, sf, Zc, tl, N, (TZ*)dz)
   if (dy_dtype == CLSKD_F32 && dz_dtype == CLSKD_F32) L(float, float);
   else if (dy_dtype == CLSKD_F32) L(float, __nv_bfloat16);

@@ -9,11 +9,6 @@
 // 64/32/16-channel swizzle group, the tap only shifts the box coordinates (zero fill outside the
 // tensor = conv padding), the skip connection is a second tensor map (no materialised concat).
 //
-// Operand reuse: taps are grouped and a group loads ONE activation patch per row tile; each tap's A tile is that
-// patch read through a shared-memory descriptor shifted by whole rows (the swizzle XOR is a function of the absolute
-// address: profiles/r02_hw_desc_shift.log) - "full" halo patch for 128-wide frequency tiles at stride 1, time-grouped
-// patches otherwise, one box per tap as the fallback.
-//
 // One CTA owns (tap group g, 128-channel tile, n tile) and a contiguous range of row patches: the
 // accumulators D_j of the G = 512/n_tile taps of its group live in TMEM for the whole range (the
 // dY patch is loaded once per row patch and shared by the G taps), and are added to dW with fp32
@@ -23,24 +18,20 @@
 #include "umma.cuh"
 
 namespace clskd {
-int g_wgrad_mode = 0;                  // clskd_set_tuning key 6: 1 one box per tap, 2 time-grouped patches at most
 namespace {
 using namespace umma;
 
 constexpr int kThreads = 192;
 constexpr int ROWS = 128;              // rows (GEMM K) per smem patch
+constexpr uint32_t A_STAGE = 32768;    // 128 rows x 128 channels x bf16
 constexpr int MAX_A_STAGES = 4;
 
-struct WgradParams {
+struct WgradParamsV1 {
   int B, To, Fo;
   int t_tile, fo_tile, f_tiles, t_tiles;
   int n_row_tiles, tiles_per_cta;
   int ntaps, G, ngroups, c_tiles, n_tiles, n_tile;
-  // taps in patch-group order: tap_w = tap index in dW, tap_pg = patch group, tap_roff = first row of the tap's
-  // 128-row tile inside the patch; patch group coordinates (parity, f shift, t shift) relative to the tile origin
-  int tap_w[CLSKD_MAX_TAPS], tap_pg[CLSKD_MAX_TAPS], tap_roff[CLSKD_MAX_TAPS];
-  int pg_p[CLSKD_MAX_TAPS], pg_f[CLSKD_MAX_TAPS], pg_t[CLSKD_MAX_TAPS];
-  uint32_t a_stage_bytes;              // one patch: nsub_a sub-blocks of a_sub_bytes
+  int tap_t[CLSKD_MAX_TAPS], tap_p[CLSKD_MAX_TAPS], tap_f[CLSKD_MAX_TAPS];
   int gw_a, gw_b;                      // swizzle group widths in elements (64 / 32 / 16)
   int c0, Ctot, N;
   uint32_t a_sub_bytes, b_sub_bytes, b_stage_bytes;
@@ -51,8 +42,8 @@ struct WgradParams {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                          const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
+tapconv_wgrad_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                          const __grid_constant__ CUtensorMap tmDY, const WgradParamsV1 p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t a_full[MAX_A_STAGES], a_empty[MAX_A_STAGES];
   __shared__ __align__(8) uint64_t b_full[2], b_empty[2];
@@ -119,16 +110,15 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
           tma_load_4d(b_buf + (size_t)bs * p.b_stage_bytes + (size_t)s * p.b_sub_bytes, &tmDY, &b_full[bs],
                       n0 + s * p.gw_b, f0, t0, b);
         for (int g = 0; g < gcur; ++g) {
-          const int j = tap0 + g;
-          if (g > 0 && p.tap_pg[j] == p.tap_pg[j - 1]) continue;        // same patch as the previous tap
-          const int pg = p.tap_pg[j];
+          const int tap = tap0 + g;
           mbar_wait(&a_empty[stage], phase ^ 1u);
           mbar_expect_tx(&a_full[stage], (uint32_t)nsub_a * p.a_sub_bytes);
           for (int s = 0; s < nsub_a; ++s) {
             const int cc = cbase + s * p.gw_a;
             const bool src0 = cc < p.c0;
-            tma_load_5d(a_buf + (size_t)stage * p.a_stage_bytes + (size_t)s * p.a_sub_bytes, src0 ? &tmA0 : &tmA1,
-                        &a_full[stage], src0 ? cc : cc - p.c0, p.pg_p[pg], f0 + p.pg_f[pg], t0 + p.pg_t[pg], b);
+            tma_load_5d(a_buf + (size_t)stage * A_STAGE + (size_t)s * p.a_sub_bytes, src0 ? &tmA0 : &tmA1,
+                        &a_full[stage], src0 ? cc : cc - p.c0, p.tap_p[tap], f0 + p.tap_f[tap],
+                        t0 + p.tap_t[tap], b);
           }
           if (++stage == p.a_stages) {
             stage = 0;
@@ -151,12 +141,9 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
         mbar_wait(&b_full[bs], (it >> 1) & 1);
         const uint32_t b_addr = smem_u32(b_buf + (size_t)bs * p.b_stage_bytes);
         for (int g = 0; g < gcur; ++g) {
-          const int j = tap0 + g;
-          if (g == 0 || p.tap_pg[j] != p.tap_pg[j - 1]) {               // first tap of a patch: wait for it
-            mbar_wait(&a_full[stage], phase);
-            fence_after();
-          }
-          const uint32_t a_addr = smem_u32(a_buf + (size_t)stage * p.a_stage_bytes) + (uint32_t)p.tap_roff[j] * pitch_a;
+          mbar_wait(&a_full[stage], phase);
+          fence_after();
+          const uint32_t a_addr = smem_u32(a_buf + (size_t)stage * A_STAGE);
 #pragma unroll
           for (int k = 0; k < ROWS / 16; ++k) {
             const uint64_t adesc = make_smem_desc_lbo(a_addr + (uint32_t)k * 16u * pitch_a, p.a_sub_bytes >> 4,
@@ -165,12 +152,10 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
                                                       (8u * pitch_b) >> 4, p.layout_b);
             umma_bf16(tmem_base + (uint32_t)(g * p.n_tile), adesc, bdesc, idesc, (it | k) ? 1u : 0u);
           }
-          if (g == gcur - 1 || p.tap_pg[j + 1] != p.tap_pg[j]) {        // last tap of the patch: release the stage
-            umma_commit(&a_empty[stage]);
-            if (++stage == p.a_stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          umma_commit(&a_empty[stage]);
+          if (++stage == p.a_stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
         umma_commit(&b_empty[bs]);
@@ -185,7 +170,7 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
     mbar_wait(&tmem_full_bar, 0);
     fence_after();
     for (int g = 0; g < gcur; ++g) {
-      float* dst = p.dw + ((int64_t)p.tap_w[tap0 + g] * p.Ctot + c_glob) * p.N + n0;
+      float* dst = p.dw + ((int64_t)(tap0 + g) * p.Ctot + c_glob) * p.N + n0;
       for (int c = 0; c < p.n_tile; c += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile + c), v);
@@ -202,13 +187,13 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-int pick_gw(int a, int b) {
+int pick_gw_v1(int a, int b) {
   if (a % 64 == 0 && b % 64 == 0) return 64;
   if (a % 32 == 0 && b % 32 == 0) return 32;
   return 16;
 }
 
-const char* wgrad_unsupported(const ClskdTapConv* d) {
+const char* wgrad_unsupported_v1(const ClskdTapConv* d) {
   if (d->x_dtype != CLSKD_BF16 || d->y_dtype != CLSKD_BF16) return "x and dy must be bf16";
   if (d->c0 % 16 || d->c1 % 16) return "channels must be multiples of 16";
   if (d->N % 16) return "N must be a multiple of 16";
@@ -235,26 +220,23 @@ const char* wgrad_unsupported(const ClskdTapConv* d) {
 
 using namespace clskd;
 
-extern "C" int clskd_tapconv_wgrad_umma_supported(const ClskdTapConv* d) {
-  if (!d || !d->x0 || !d->y || !d->w) return 0;
-  return wgrad_unsupported(d) == nullptr ? 1 : 0;
-}
-
-extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
-  CLSKD_CHECK_ARG(d && d->x0 && d->w && d->y, "clskd_tapconv_wgrad_umma: null pointer");
-  CLSKD_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= CLSKD_MAX_TAPS, "clskd_tapconv_wgrad_umma: ntaps");
-  if (const char* why = wgrad_unsupported(d)) {
-    set_error("clskd_tapconv_wgrad_umma: unsupported: %s", why);
+// round-1 weight-gradient kernel (one TMA box per tap): used for the narrow-N launches, where it is faster than the
+// patch kernel (profiles/r02_step_breakdown_g.json), and as its A/B baseline
+extern "C" int clskd_tapconv_wgrad_umma_v1(const ClskdTapConv* d, void* stream) {
+  CLSKD_CHECK_ARG(d && d->x0 && d->w && d->y, "clskd_tapconv_wgrad_umma_v1: null pointer");
+  CLSKD_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= CLSKD_MAX_TAPS, "clskd_tapconv_wgrad_umma_v1: ntaps");
+  if (const char* why = wgrad_unsupported_v1(d)) {
+    set_error("clskd_tapconv_wgrad_umma_v1: unsupported: %s", why);
     return CLSKD_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int Ctot = d->c0 + d->c1;
   if (!d->accumulate) {
     cudaError_t e = cudaMemsetAsync(const_cast<void*>(d->w), 0, sizeof(float) * (size_t)d->ntaps * Ctot * d->N, st);
-    if (e != cudaSuccess) { set_error("clskd_tapconv_wgrad_umma: memset: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+    if (e != cudaSuccess) { set_error("clskd_tapconv_wgrad_umma_v1: memset: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
   }
   EncodeTiledFn enc = get_encode();
-  WgradParams p;
+  WgradParamsV1 p;
   memset(&p, 0, sizeof(p));
   p.B = d->B; p.To = d->To; p.Fo = d->Fo;
   p.fo_tile = d->Fo < ROWS ? d->Fo : ROWS;
@@ -262,103 +244,34 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
   p.f_tiles = d->Fo / p.fo_tile;
   p.t_tiles = cdiv(d->To, p.t_tile);
   const int64_t nrt = (int64_t)d->B * p.t_tiles * p.f_tiles;
-  CLSKD_CHECK_ARG(nrt <= 2147483647LL, "clskd_tapconv_wgrad_umma: too many row patches");
+  CLSKD_CHECK_ARG(nrt <= 2147483647LL, "clskd_tapconv_wgrad_umma_v1: too many row patches");
   p.n_row_tiles = (int)nrt;
   p.ntaps = d->ntaps;
-  int tt[CLSKD_MAX_TAPS], tpar[CLSKD_MAX_TAPS], tf[CLSKD_MAX_TAPS];
-  int tmin = 1 << 30, tmax = -(1 << 30), fmin = 1 << 30, fmax = -(1 << 30);
   for (int j = 0; j < d->ntaps; ++j) {
     int df = d->df[j];
     int fl = df >= 0 ? df / d->sf : -((-df + d->sf - 1) / d->sf);
-    tt[j] = d->dt[j];
-    tf[j] = fl;
-    tpar[j] = df - fl * d->sf;
-    tmin = tt[j] < tmin ? tt[j] : tmin; tmax = tt[j] > tmax ? tt[j] : tmax;
-    fmin = fl < fmin ? fl : fmin; fmax = fl > fmax ? fl : fmax;
+    p.tap_t[j] = d->dt[j];
+    p.tap_f[j] = fl;
+    p.tap_p[j] = df - fl * d->sf;
   }
   p.n_tile = d->N <= 256 ? d->N : (d->N % 256 == 0 ? 256 : 128);
   p.n_tiles = d->N / p.n_tile;
   p.G = 512 / p.n_tile;
   if (p.G > d->ntaps) p.G = d->ntaps;
+  p.ngroups = cdiv(d->ntaps, p.G);
   p.c_tiles = cdiv(Ctot, 128);
-  p.gw_a = pick_gw(d->c0, d->c1);
-  p.gw_b = pick_gw(p.n_tile, 0);
+  p.gw_a = pick_gw_v1(d->c0, d->c1);
+  p.gw_b = pick_gw_v1(p.n_tile, 0);
   p.c0 = d->c0; p.Ctot = Ctot; p.N = d->N;
+  p.a_sub_bytes = (uint32_t)ROWS * p.gw_a * 2;
   p.b_sub_bytes = (uint32_t)ROWS * p.gw_b * 2;
   p.b_stage_bytes = ((uint32_t)ROWS * p.n_tile * 2 + 1023u) & ~1023u;
   p.layout_a = layout_for_bytes(p.gw_a * 2);
   p.layout_b = layout_for_bytes(p.gw_b * 2);
-  // the MMA always reads M = 128 channels = 128 / gw_a sub-blocks (rows of absent channels are discarded by the
-  // epilogue), so a stage must span all of them even when fewer are loaded
-  const int nsub_max = 128 / p.gw_a;
-  const uint32_t kBudget = 222u * 1024u;
-  // ---- patch grouping: 3 full halo patch (all taps in one CTA), 2 time-grouped patches, 1 one box per tap
-  const bool full_ok = d->sf == 1 && p.fo_tile == ROWS && d->ntaps > 1 && p.G >= d->ntaps &&
-                       ((ROWS + (fmax - fmin) + 7) & ~7) <= 256 && (p.t_tile + (tmax - tmin)) <= 16;
-  const bool time_ok = d->ntaps > 1 && p.fo_tile % 8 == 0 && p.t_tile > 1 && tmax > tmin && (p.t_tile + (tmax - tmin)) <= 256;
-  int mode = full_ok ? 3 : (time_ok ? 2 : 1);
-  // measured (profiles/r02_step_breakdown_d/e.json): patches pay for wide tiles (N >= 128 with >= 64 channels: -12 %);
-  // narrow-N launches are bound by the shared-memory operand reads of their MMAs and by stage depth, where the larger
-  // patch stages lose (+4 .. +15 %): those keep one box per tap.  g_wgrad_mode = 3 forces patches for tests.
-  if (g_wgrad_mode == 0 && !(p.n_tile >= 128 && Ctot >= 64)) mode = 1;
-  if (g_wgrad_mode == 1) mode = 1;
-  if (mode == 1 && g_wgrad_mode != 4) return clskd_tapconv_wgrad_umma_v1(d, stream);     // (dW already zeroed: harmless)
-  if (g_wgrad_mode == 2) mode = time_ok ? 2 : 1;
-  int box_f = p.fo_tile, box_t = p.t_tile;
-  int stages = 0;
-  for (;;) {
-    box_f = p.fo_tile;
-    box_t = p.t_tile;
-    int npg = 0;
-    if (mode == 3) {
-      box_f = (ROWS + (fmax - fmin) + 7) & ~7;
-      box_t = p.t_tile + (tmax - tmin);
-      npg = 1;
-      p.pg_p[0] = 0; p.pg_f[0] = fmin; p.pg_t[0] = tmin;
-      for (int j = 0; j < d->ntaps; ++j) {
-        p.tap_w[j] = j;
-        p.tap_pg[j] = 0;
-        p.tap_roff[j] = (tt[j] - tmin) * box_f + (tf[j] - fmin);
-      }
-    } else if (mode == 2) {
-      box_t = p.t_tile + (tmax - tmin);
-      bool used[CLSKD_MAX_TAPS] = {false};
-      int n = 0;
-      for (int j = 0; j < d->ntaps; ++j) {
-        if (used[j]) continue;
-        p.pg_p[npg] = tpar[j]; p.pg_f[npg] = tf[j]; p.pg_t[npg] = tmin;
-        for (int i = j; i < d->ntaps; ++i)
-          if (!used[i] && tpar[i] == tpar[j] && tf[i] == tf[j]) {
-            used[i] = true;
-            p.tap_w[n] = i;
-            p.tap_pg[n] = npg;
-            p.tap_roff[n] = (tt[i] - tmin) * box_f;
-            ++n;
-          }
-        ++npg;
-      }
-      // taps per CTA: whole patch groups where possible (a group cut by the CTA boundary is loaded twice)
-      const int gsz = tmax - tmin + 1;
-      if (p.G < d->ntaps && p.G > gsz && d->ntaps % gsz == 0) p.G = p.G / gsz * gsz;
-    } else {
-      npg = d->ntaps;
-      for (int j = 0; j < d->ntaps; ++j) {
-        p.tap_w[j] = j;
-        p.tap_pg[j] = j;
-        p.tap_roff[j] = 0;
-        p.pg_p[j] = tpar[j]; p.pg_f[j] = tf[j]; p.pg_t[j] = tt[j];
-      }
-    }
-    p.a_sub_bytes = (uint32_t)box_f * box_t * p.gw_a * 2;
-    p.a_stage_bytes = ((uint32_t)nsub_max * p.a_sub_bytes + 1023u) & ~1023u;
-    stages = (int)((kBudget - 1024u - 2u * p.b_stage_bytes) / p.a_stage_bytes);
-    if (stages > MAX_A_STAGES) stages = MAX_A_STAGES;
-    if (stages >= 2 || mode == 1) break;
-    mode = mode == 3 && time_ok ? 2 : 1;          // the patch does not fit twice: smaller patches
-  }
+  int stages = (int)((200u * 1024u - 2u * p.b_stage_bytes) / A_STAGE);
+  if (stages > MAX_A_STAGES) stages = MAX_A_STAGES;
   if (stages < 2) stages = 2;
   p.a_stages = stages;
-  p.ngroups = cdiv(d->ntaps, p.G);
   int cols = 32;
   while (cols < p.G * p.n_tile) cols <<= 1;
   p.tmem_cols = (uint32_t)cols;
@@ -374,12 +287,12 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
   CUtensorMap tmA0, tmA1, tmDY;
   CUtensorMapSwizzle swa = swizzle_for_bytes(p.gw_a * 2), swb = swizzle_for_bytes(p.gw_b * 2);
   int rc = encode_act(enc, &tmA0, d->x0, d->c0, d->sf, d->Fi, d->Ti, d->B, d->x0_sB, d->x0_sT, d->x0_sF, p.gw_a,
-                      box_f, box_t, swa);
-  if (rc) { set_error("clskd_tapconv_wgrad_umma: cuTensorMapEncodeTiled(x0) failed: %d", rc); return CLSKD_ERR_CUDA; }
+                      p.fo_tile, p.t_tile, swa);
+  if (rc) { set_error("clskd_tapconv_wgrad_umma_v1: cuTensorMapEncodeTiled(x0) failed: %d", rc); return CLSKD_ERR_CUDA; }
   if (d->c1) {
     rc = encode_act(enc, &tmA1, d->x1, d->c1, d->sf, d->Fi, d->Ti, d->B, d->x1_sB, d->x1_sT, d->x1_sF, p.gw_a,
-                    box_f, box_t, swa);
-    if (rc) { set_error("clskd_tapconv_wgrad_umma: cuTensorMapEncodeTiled(x1) failed: %d", rc); return CLSKD_ERR_CUDA; }
+                    p.fo_tile, p.t_tile, swa);
+    if (rc) { set_error("clskd_tapconv_wgrad_umma_v1: cuTensorMapEncodeTiled(x1) failed: %d", rc); return CLSKD_ERR_CUDA; }
   } else {
     tmA1 = tmA0;
   }
@@ -391,17 +304,17 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
     CUresult r = enc(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->y), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r) { set_error("clskd_tapconv_wgrad_umma: cuTensorMapEncodeTiled(dy) failed: %d", (int)r); return CLSKD_ERR_CUDA; }
+    if (r) { set_error("clskd_tapconv_wgrad_umma_v1: cuTensorMapEncodeTiled(dy) failed: %d", (int)r); return CLSKD_ERR_CUDA; }
   }
-  size_t smem = 2 * (size_t)p.b_stage_bytes + (size_t)p.a_stages * p.a_stage_bytes + 1024;
+  size_t smem = 2 * (size_t)p.b_stage_bytes + (size_t)p.a_stages * A_STAGE + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapconv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("clskd_tapconv_wgrad_umma: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+    cudaError_t e = cudaFuncSetAttribute(tapconv_wgrad_umma_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("clskd_tapconv_wgrad_umma_v1: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
     smem_set = smem;
   }
   dim3 grid((unsigned)nsplit, (unsigned)ycount);
-  tapconv_wgrad_umma_kernel<<<grid, kThreads, smem, st>>>(tmA0, tmA1, tmDY, p);
-  CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad_umma");
+  tapconv_wgrad_umma_v1_kernel<<<grid, kThreads, smem, st>>>(tmA0, tmA1, tmDY, p);
+  CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad_umma_v1");
   return CLSKD_OK;
 }

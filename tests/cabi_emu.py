@@ -913,6 +913,16 @@ class EmuLib:
         _arr(out, n)[...] = r
         return 0
 
+    def clskd_sum_n(self, in0, in1, in2, in3, k, dtype, n, out, stream):
+        _need_f32(dtype)
+        r = _arr(in0, n) + _arr(in1, n)
+        if k > 2:
+            r = r + _arr(in2, n)
+        if k > 3:
+            r = r + _arr(in3, n)
+        _arr(out, n)[...] = r
+        return 0
+
     def clskd_f64_to_f32(self, inp, n, scale, out, stream):
         _arr(out, n)[...] = _arr(inp, n, np.float64) * scale
         return 0

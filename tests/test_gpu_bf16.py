@@ -175,7 +175,7 @@ def _wgrad_both_policies(cuda_dev, mod, inputs, ops):
     return res
 
 
-@pytest.mark.parametrize("wmode", [3, 1])
+@pytest.mark.parametrize("wmode", [3, 4, 0])
 @pytest.mark.parametrize("case", ["conv_64_128", "conv_32_64", "conv_16_32", "deconv_skip_128", "deconv_skip_64",
                                   "abf3x3_128_256", "abf3x3_128_32", "abf1x1_32_128", "abf3x3F128_128_32",
                                   "abf3x3F128_32_128", "abf3x3F256_64_48", "abf3x3F64_128_64"])
@@ -252,17 +252,19 @@ def test_umma_gram_fwd_bwd_vs_torch(cuda_dev, B, K):
     assert err < 1.5e-2 * gref.abs().max().item(), err          # dz is rounded to bf16 (2^-8 relative)
 
 
-@pytest.mark.parametrize("cin,cout,ks", [(128, 2, 3), (64, 1, 3), (32, 2, 3)])
-def test_tap_in_channel_narrow_conv_vs_torch(cuda_dev, cin, cout, ks):
-    """bf16 policy: k x k conv onto <= 2 channels = pointwise tcgen05 GEMM + tap gather-sum"""
+@pytest.mark.parametrize("cin,cout,ks,F,T", [(128, 2, 3, 32, 45), (64, 1, 3, 32, 45), (32, 2, 3, 32, 45), (32, 2, 3, 128, 301),
+                                             (64, 2, 3, 256, 131)])
+def test_tap_in_channel_narrow_conv_vs_torch(cuda_dev, cin, cout, ks, F, T):
+    """bf16 policy: k x k conv onto <= 2 channels = pointwise tcgen05 GEMM + tap gather-sum (the last two sizes take
+    the shared-memory tiled gather-sum kernels, >= 65536 positions)"""
     import clskd_b200
     from clskd_b200 import framework as fw
     from clskd_b200 import ops
     g = torch.Generator().manual_seed(cin + ks)
     conv = fw.RealConv2d(cin, cout, ks, padding=ks // 2, bias=False)
     _round_params(conv)
-    x = torch.randn(2, cin, 32, 45, generator=g).bfloat16().float()
-    up = torch.randn(2, cout, 32, 45, generator=g).bfloat16().float()
+    x = torch.randn(2, cin, F, T, generator=g).bfloat16().float()
+    up = torch.randn(2, cout, F, T, generator=g).bfloat16().float()
     xr = x.clone().requires_grad_(True)
     wr = conv.weight.detach().clone().requires_grad_(True)
     ref = torch.nn.functional.conv2d(xr, wr, padding=ks // 2)
