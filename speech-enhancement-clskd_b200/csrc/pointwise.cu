@@ -321,52 +321,11 @@ __global__ void __launch_bounds__(PT) tapsum_fwd_kernel(const TZ* __restrict__ z
 }
 
 
-// ---- tiled tap sum (stride 1, Ti == To, Fi == Fo): one block owns a TT x TF patch of output positions of one utterance.
-// Forward: the (TT + tspan) x (TF + fspan) patch of z rows is staged in shared memory with 16-byte loads (every z row is
-// read once per block instead of once per tap), then thread (t, f) gathers its <= 16 tap values; zero outside the map.
-// Backward: the patch of dy rows (N values each) is staged, thread (t, f) assembles and stores the whole dz row.
+// ---- tiled tap-sum gradient (stride 1, Ti == To, Fi == Fo): one block owns a TT x TF patch of positions of one
+// utterance; the patch of dy rows (N values each) is staged in shared memory, thread (t, f) assembles and stores its
+// whole dz row (measured 0.61 -> 0.48 ms per launch; the same tiling of the FORWARD gather was slower than the direct
+// kernel - its z rows are re-read from L1, not from HBM - and was dropped).
 constexpr int TS_TT = 4, TS_TF = 64;        // 256 output positions per block
-
-template <typename TZ, typename TY>
-__global__ void __launch_bounds__(256) tapsum_fwd_tiled_kernel(const TZ* __restrict__ z, int B, int T, int F, int Zc,
-                                                              TapList taps, int N, int tmin, int tspan, int fmin, int fspan,
-                                                              const float* __restrict__ bias, TY* __restrict__ y) {
-  extern __shared__ __align__(16) uint8_t ts_smem[];
-  const int PW = TS_TF + fspan, PH = TS_TT + tspan;
-  const int pitch = Zc * (int)sizeof(TZ) + 8;                       // +8 bytes: rows of consecutive f spread over the banks
-  const int f_tiles = (F + TS_TF - 1) / TS_TF, t_tiles = (T + TS_TT - 1) / TS_TT;
-  const int chunks = Zc * (int)sizeof(TZ) / 8;                       // 8-byte pieces per z row
-  for (int tile = blockIdx.x; tile < B * t_tiles * f_tiles; tile += gridDim.x) {
-    const int ft = tile % f_tiles;
-    int r = tile / f_tiles;
-    const int tt = r % t_tiles, b = r / t_tiles;
-    const int t0 = tt * TS_TT, f0 = ft * TS_TF;
-    __syncthreads();
-    for (int i = threadIdx.x; i < PH * PW * chunks; i += 256) {
-      const int c = i % chunks;
-      int rr = i / chunks;
-      const int pf = rr % PW, pt = rr / PW;
-      const int ti = t0 + tmin + pt, fi = f0 + fmin + pf;
-      uint2 v = make_uint2(0u, 0u);
-      if (ti >= 0 && ti < T && fi >= 0 && fi < F)
-        v = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(z + (((int64_t)b * T + ti) * F + fi) * Zc) + 8 * c);
-      *reinterpret_cast<uint2*>(ts_smem + (size_t)rr * pitch + 8 * c) = v;
-    }
-    __syncthreads();
-    const int lt = threadIdx.x / TS_TF, lf = threadIdx.x % TS_TF;
-    const int t = t0 + lt, f = f0 + lf;
-    if (t < T && f < F) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int j = 0; j < taps.n; ++j) {
-        const int pr = (lt + taps.dt[j] - tmin) * PW + (lf + taps.df[j] - fmin);
-        const TZ* zp = reinterpret_cast<const TZ*>(ts_smem + (size_t)pr * pitch) + j * N;
-        for (int n = 0; n < N; ++n) acc[n] += ld_f(zp + n);
-      }
-      TY* yo = y + (((int64_t)b * T + t) * F + f) * N;
-      for (int n = 0; n < N; ++n) st_f(yo + n, acc[n] + (bias ? bias[n] : 0.f));
-    }
-  }
-}
 
 template <typename TD, typename TZ>
 __global__ void __launch_bounds__(256) tapsum_bwd_tiled_kernel(const TD* __restrict__ dy, int B, int T, int F, int Zc,
@@ -579,29 +538,6 @@ extern "C" int clskd_tapsum_fwd(const void* z, int z_dtype, int B, int Ti, int F
   for (int j = 0; j < ntaps; ++j) { tl.dt[j] = dt_host[j]; tl.df[j] = df_host[j]; }
   const int grid = pw_grid(M);
   cudaStream_t st = (cudaStream_t)stream;
-  {
-    const TapExt te = tap_extents(tl);
-    const int zes = z_dtype == CLSKD_F32 ? 4 : 2;
-    const size_t sh = (size_t)(TS_TT + te.tspan) * (TS_TF + te.fspan) * (Zc * zes + 8);
-    if (sf == 1 && Ti == To && Fi == Fo && M >= 65536 && (Zc * zes) % 8 == 0 && ((uintptr_t)z % 8) == 0 && te.tspan <= 4 &&
-        te.fspan <= 8 && sh <= 96 * 1024) {
-      const int64_t tiles = (int64_t)B * cdiv(To, TS_TT) * cdiv(Fo, TS_TF);
-      const int g2 = (int)(tiles < (int64_t)sm_count() * 8 ? tiles : (int64_t)sm_count() * 8);
-#define LT(TZ, TY)                                                                                                   \
-  do {                                                                                                               \
-    cudaFuncSetAttribute(tapsum_fwd_tiled_kernel<TZ, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);   \
-    tapsum_fwd_tiled_kernel<TZ, TY><<<g2, 256, sh, st>>>((const TZ*)z, B, To, Fo, Zc, tl, N, te.tmin, te.tspan, te.fmin, \
-                                                        te.fspan, bias, (TY*)y);                                     \
-  } while (0)
-      if (z_dtype == CLSKD_F32 && y_dtype == CLSKD_F32) LT(float, float);
-      else if (z_dtype == CLSKD_F32) LT(float, __nv_bfloat16);
-      else if (y_dtype == CLSKD_F32) LT(__nv_bfloat16, float);
-      else LT(__nv_bfloat16, __nv_bfloat16);
-#undef LT
-      CLSKD_CHECK_LAUNCH("clskd_tapsum_fwd(tiled)");
-      return CLSKD_OK;
-    }
-  }
 #define L(TZ, TY) tapsum_fwd_kernel<TZ, TY><<<grid, PT, 0, st>>>((const TZ*)z, B, Ti, Fi, To, Fo, sf, Zc, tl, N, bias, (TY*)y)
   if (z_dtype == CLSKD_F32 && y_dtype == CLSKD_F32) L(float, float);
   else if (z_dtype == CLSKD_F32) L(float, __nv_bfloat16);
