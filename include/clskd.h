@@ -469,6 +469,13 @@ int clskd_axpby_f32(const float* x, const float* y, float a, float b, float* out
 /* out[0] = sum_i w[i]*in[i] over n fp32 scalars given as an array of device pointers is not
  * needed: losses are combined by the autograd graph on the host side. */
 
+/* Per-utterance second moments of two fp32 waveform batches a, b [B, L] (row strides in elements):
+ * out[b*5 .. b*5+4] = (sum a, sum b, sum a*a, sum a*b, sum b*b) in fp64.  One pass gives every batched validation
+ * metric of the training loop (SI-SDR with mean removal, SNR and their improvements over the mixture), which the
+ * reference computes one utterance at a time on the CPU (distill.py:150-200, asteroid get_metrics). */
+int clskd_pair_moments(const float* a, const float* b, int B, int L, int64_t a_sB, int64_t b_sB, double* out,
+                       void* stream);
+
 /* out = in0 + in1 (+ in2 + in3), k in 2..4 dense same-dtype tensors of n elements, fp32 accumulation: the gradient
  * accumulation of a tensor with several consumers (skip connection + next layer + feature tap), which autograd
  * would otherwise do with its own add kernels.  16-byte aligned tensors. */

@@ -7,8 +7,8 @@ All compute goes through libclskd_sm100.so (include/clskd.h); there is no CPU fa
 """
 from . import _lib
 from .ops import get_precision, set_precision
-from . import config, tools_for_loss, tools_for_model, feature_extraction, framework, distill
+from . import config, tools_for_loss, tools_for_model, feature_extraction, framework, distill, metrics, lightning
 from .DCCRN import DCCRN
 
 __all__ = ["DCCRN", "config", "tools_for_loss", "tools_for_model", "feature_extraction", "framework",
-           "distill", "set_precision", "get_precision"]
+           "distill", "metrics", "lightning", "set_precision", "get_precision"]

@@ -502,3 +502,46 @@ extern "C" int clskd_gram_bwd(const void* z, int dtype, int B, int64_t K, int64_
   CLSKD_CHECK_LAUNCH("clskd_gram_bwd");
   return CLSKD_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-utterance second moments of a pair of waveforms (fp64): out[b] = (sum a, sum b, sum a*a, sum a*b, sum b*b).
+// Everything the batched validation metrics need (SI-SDR with mean removal, SNR, improvements: distill.py:150-200
+// computes them one utterance at a time on the CPU through asteroid's get_metrics) in one pass over the batch.
+// ---------------------------------------------------------------------------------------------------------
+namespace clskd {
+namespace {
+__global__ void __launch_bounds__(256) pair_moments_kernel(const float* __restrict__ a, const float* __restrict__ b, int L,
+                                                           int64_t a_sB, int64_t b_sB, double* __restrict__ out) {
+  __shared__ double sh[32];
+  const int bi = blockIdx.y;
+  const float* ap = a + (int64_t)bi * a_sB;
+  const float* bp = b + (int64_t)bi * b_sB;
+  double s[5] = {0., 0., 0., 0., 0.};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+    const double x = ap[i], y = bp[i];
+    s[0] += x; s[1] += y; s[2] += x * x; s[3] += x * y; s[4] += y * y;
+  }
+  for (int k = 0; k < 5; ++k) {
+    const double t = block_sum<double>(s[k], sh);
+    if (threadIdx.x == 0) atomicAdd(out + (int64_t)bi * 5 + k, t);
+    __syncthreads();
+  }
+}
+}  // namespace
+}  // namespace clskd
+
+extern "C" int clskd_pair_moments(const float* a, const float* b, int B, int L, int64_t a_sB, int64_t b_sB, double* out,
+                                  void* stream) {
+  CLSKD_CHECK_ARG(a && b && out && B >= 0 && L >= 0, "clskd_pair_moments: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return CLSKD_OK;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * 5 * (size_t)B, st);
+  if (e != cudaSuccess) { clskd::set_error("clskd_pair_moments: memset: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+  if (L == 0) return CLSKD_OK;
+  int bx = (L + 256 * 8 - 1) / (256 * 8);
+  if (bx > 64) bx = 64;
+  clskd::pair_moments_kernel<<<dim3(bx, B), 256, 0, st>>>(a, b, L, a_sB, b_sB, out);
+  CLSKD_CHECK_LAUNCH("clskd_pair_moments");
+  return CLSKD_OK;
+}

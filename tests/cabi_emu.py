@@ -913,6 +913,14 @@ class EmuLib:
         _arr(out, n)[...] = r
         return 0
 
+    def clskd_pair_moments(self, a, b, B, L, a_sB, b_sB, out, stream):
+        O = _arr(out, B * 5, np.float64).reshape(B, 5)
+        for i in range(B):
+            x = _arr(a + 4 * i * a_sB, L).astype(np.float64)
+            y = _arr(b + 4 * i * b_sB, L).astype(np.float64)
+            O[i] = [x.sum(), y.sum(), (x * x).sum(), (x * y).sum(), (y * y).sum()]
+        return 0
+
     def clskd_sum_n(self, in0, in1, in2, in3, k, dtype, n, out, stream):
         _need_f32(dtype)
         r = _arr(in0, n) + _arr(in1, n)

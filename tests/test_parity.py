@@ -833,3 +833,41 @@ def test_streaming_inference_equals_whole_utterance(dev, L, chunk):
     m.train()
     with pytest.raises(RuntimeError):
         m.enhance_streaming(x.to(dev), chunk_frames=chunk)
+
+
+# ------------------------------------------------------------------------------------ training module / metrics
+def test_batched_validation_metrics_vs_oracle(dev):
+    """SI-SDR (mean-removed, pb_bss_eval definition) / SNR and their improvements over the mixture for a whole batch
+    from one library pass, against the numpy restatement"""
+    from clskd_b200 import metrics
+    from oracle import metrics_oracle as MO
+    g = torch.Generator().manual_seed(3)
+    clean = 0.1 * torch.randn(5, 4001, generator=g) + 0.01
+    mix = clean + 0.05 * torch.randn(5, 4001, generator=g)
+    est = 0.7 * clean + 0.01 * torch.randn(5, 4001, generator=g) - 0.02
+    means, per = metrics.batch_metrics(mix.to(dev), clean.to(dev), est.to(dev))
+    ref = MO.batch_metrics(mix.numpy(), clean.numpy(), est.numpy())
+    for k, v in ref.items():
+        assert torch.allclose(per[k].cpu(), torch.from_numpy(v), rtol=1e-6, atol=1e-6), k
+        assert abs(means[k] - float(v.mean())) < 1e-5, k
+
+
+def test_knowledge_distillation_module_hooks(dev):
+    """the reference's LightningModule hook names over the fused step: training_step lowers the loss, validation_step
+    returns batched metrics, configure_optimizers returns an optimizer; `fit` drives them without Lightning"""
+    from clskd_b200.lightning import KnowledgeDistillation
+    from oracle import dccrn_oracle as D
+    cfg_t, cfg_s = dict(kernel_num=[4, 8, 8, 16, 16, 16], rnn_units=16), dict(kernel_num=[2, 4, 4, 8, 8, 8], rnn_units=8)
+    teacher = _build(cfg_t, D.make_state_dict(cfg_t["kernel_num"], cfg_t["rnn_units"], seed=1), dev)
+    student = _build(cfg_s, D.make_state_dict(cfg_s["kernel_num"], cfg_s["rnn_units"], seed=2), dev)
+    g = torch.Generator().manual_seed(0)
+    y = (0.1 * torch.randn(3, 2000, generator=g)).to(dev)
+    X = y + (0.05 * torch.randn(3, 2000, generator=g)).to(dev)
+    kd = KnowledgeDistillation(teacher, student, mode="spkd_all", lr=1e-3)
+    hist = kd.fit([(X.unsqueeze(1), y.unsqueeze(1))] * 3, [(X, y)], epochs=2)
+    assert hist[1]["train_loss"] < hist[0]["train_loss"]
+    for k in ("si_sdr", "input_si_sdr", "si_sdr_imp", "snr", "snr_imp"):
+        assert k in hist[1] and hist[1][k] == hist[1][k]
+    assert abs(hist[1]["si_sdr_imp"] - (hist[1]["si_sdr"] - hist[1]["input_si_sdr"])) < 1e-6
+    assert isinstance(kd.configure_optimizers(), torch.optim.Adam)
+    assert "train_base" in kd.logged and student.training
