@@ -92,8 +92,10 @@ typedef struct ClskdTapConv {
 
 /* fp32 CUDA-core implicit GEMM (exact-fp32 policy, and layers too small for a UMMA tile) */
 int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream);
-/* bf16 tcgen05/TMA implicit GEMM; requires (c0+c1)%16==0, c0%16==0, N%16==0, bf16 x/w,
- * dense [B,Ti,Fi,C] sources (see clskd_tapconv_umma_supported). */
+/* bf16 tcgen05/TMA implicit GEMM; requires c0%8==0, c1%8==0, N%8==0, bf16 x/w, dense [B,Ti,Fi,C] sources
+ * (see clskd_tapconv_umma_supported).  Packed weight `w`: bf16 [ntaps][Np][c0p + c1p] with every extent rounded up to
+ * a multiple of 16 (c0p = ceil16(c0) ...) and zeros in the padding: channel counts that are multiples of 8 but not of
+ * 16 (the reference's quarter-width student) run with 16-wide TMA boxes over the 8 channels that exist. */
 int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream);
 int clskd_tapconv_umma_supported(const ClskdTapConv* d);
 /* Tuning overrides of the tcgen05 forward kernel for A/B measurements (tools/kbench.py); value 0 = automatic.
@@ -121,7 +123,7 @@ int clskd_tuning_stats(int* n_shapes, int* n_v1);
  * unless d->accumulate. */
 int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream);
 /* the same weight gradient on the tcgen05 tensor cores (bf16 x and dY, fp32 dW, split-K over CTAs
- * with fp32 reductions): requires c0%16==0, c1%16==0, N%16==0, power-of-two Fo, 16-byte aligned
+ * with fp32 reductions): requires c0%8==0, c1%8==0, N%8==0 (multiples of 8 run padded to 16), power-of-two Fo, 16-byte aligned
  * tensors/strides (see clskd_tapconv_wgrad_umma_supported). */
 int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream);
 int clskd_tapconv_wgrad_umma_supported(const ClskdTapConv* d);

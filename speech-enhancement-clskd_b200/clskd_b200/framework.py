@@ -231,7 +231,7 @@ class RealConv2d(nn.Module):
                     and KT == 2 * self.padding[1] + 1)
         if ops.policy.narrow == "always":
             return shape_ok
-        return (shape_ok and ops.policy.use_umma and self.in_channels % 16 == 0 and x0.dtype == torch.bfloat16)
+        return (shape_ok and ops.policy.use_umma and self.in_channels % 8 == 0 and x0.dtype == torch.bfloat16)
 
     def forward_phys(self, x0, x1=None, out_dtype=None):
         if self._use_narrow(x0, x1):

@@ -261,6 +261,22 @@ class Launch:
             self._t_nc = torch.from_numpy(_pairs(self.blk.transpose(0, 2, 1).reshape(-1))).to(self.device)
         return self._t_nc
 
+    def t_nc_padded(self, c0, c1):
+        """[tap][Np][c0p + c1p] table for the tcgen05 kernel when a channel count is a multiple of 8 but not of 16
+        (quarter-width student): each source's K range and N are padded to 16 with skipped (= zero) entries; the
+        kernel's TMA boxes are 16 channels wide over the 8 that exist (clskd_tapconv_fwd_umma)."""
+        key = ("t_nc_pad", c0, c1)
+        if key not in self._cache:
+            p16 = lambda v: (v + 15) // 16 * 16
+            nt, K, N = self.blk.shape
+            assert K == c0 + c1
+            out = np.full((nt, p16(c0) + p16(c1), p16(N)), -1, dtype=np.int64)
+            out[:, :c0, :N] = self.blk[:, :c0, :]
+            if c1:
+                out[:, p16(c0):p16(c0) + c1, :N] = self.blk[:, c0:, :]
+            self._cache[key] = torch.from_numpy(_pairs(out.transpose(0, 2, 1).reshape(-1))).to(self.device)
+        return self._cache[key]
+
 
 def _codes(shape, sel):
     n = int(np.prod(shape))
@@ -633,7 +649,10 @@ def run_tapconv(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, a, b, bias, y, x0_
     if ep is None and policy.use_umma and policy.split_gemm and _split_gemm(d, l, a, b, bias, x0, y):
         return y
     if allow_umma and _umma_ok(d):
-        w = packed_weights(l._cache, "nc", lambda: l.t_nc, a, b, torch.bfloat16)
+        if c0 % 16 or c1 % 16 or l.N % 16:
+            w = packed_weights(l._cache, "nc_pad%d_%d" % (c0, c1), lambda: l.t_nc_padded(c0, c1), a, b, torch.bfloat16)
+        else:
+            w = packed_weights(l._cache, "nc", lambda: l.t_nc, a, b, torch.bfloat16)
         d.w = w.data_ptr()
         call("clskd_tapconv_fwd_umma", ctypes.byref(d), _stream())
         umma_launches += 1

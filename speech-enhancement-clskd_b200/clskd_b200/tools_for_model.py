@@ -313,8 +313,8 @@ class ComplexConvTranspose2d(nn.Module):
         ok = self.out_channels == 1 and self.kernel_size[0] * self.kernel_size[1] <= 16
         if ops.policy.narrow == "always":
             return ok
-        return (ok and ops.policy.use_umma and x0.dtype == torch.bfloat16 and x0.shape[-1] % 16 == 0
-                and (x1 is None or (x1.dtype == torch.bfloat16 and x1.shape[-1] % 16 == 0)))
+        return (ok and ops.policy.use_umma and x0.dtype == torch.bfloat16 and x0.shape[-1] % 8 == 0
+                and (x1 is None or (x1.dtype == torch.bfloat16 and x1.shape[-1] % 8 == 0)))
 
     def forward_phys(self, x0, x1=None, out_dtype=None):
         ca = None if x1 is None else x0.shape[-1] // 2

@@ -313,13 +313,17 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           float o[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+          // columns >= N exist only as padding of an N that is not a multiple of 16 (zero weights; clipped by the
+          // TMA store): their per-channel constants are not read
+          const int nlive = p.N - (n0 + c);
           if (p.bias) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] += __ldg(p.bias + n0 + c + e);
+            for (int e = 0; e < 16; ++e) o[e] += e < nlive ? __ldg(p.bias + n0 + c + e) : 0.f;
           }
           if (EP && p.ep_scale) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] = fmaf(o[e], __ldg(p.ep_scale + n0 + c + e), __ldg(p.ep_shift + n0 + c + e));
+            for (int e = 0; e < 16; ++e)
+              if (e < nlive) o[e] = fmaf(o[e], __ldg(p.ep_scale + n0 + c + e), __ldg(p.ep_shift + n0 + c + e));
           }
           if (EP && p.ep_slope) {
 #pragma unroll
@@ -385,7 +389,7 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
       }
     }
-    if (EP && p.stats_sum) {
+    if (EP && p.stats_sum && st_col < p.N) {
       atomicAdd(p.stats_sum + st_col, (double)st_s0);
       atomicAdd(p.stats_sumsq + st_col, (double)st_q0);
       if (p.block_n > p.ecols) {
@@ -404,9 +408,11 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 // dense source check + geometry; returns nullptr if supported, else a reason
 const char* umma_unsupported(const ClskdTapConv* d) {
   if (d->x_dtype != CLSKD_BF16) return "x must be bf16";
-  const int Ctot = d->c0 + d->c1;
-  if (Ctot % 16 || d->c0 % 16) return "channels must be multiples of 16";
-  if (d->N % 16) return "N must be a multiple of 16";
+  // channel counts that are multiples of 8 but not of 16 (the reference's quarter-width student: 8-channel maps) run
+  // padded: the TMA box is 16 channels wide over the 8 that exist (zero fill / clipped store) and the packed weight
+  // carries zero rows / columns - see clskd_tapconv_umma_padded
+  if (d->c0 % 8 || d->c1 % 8 || d->c0 < 8) return "channels must be multiples of 8";
+  if (d->N % 8 || d->N < 8) return "N must be a multiple of 8";
   if (d->N > 256 && d->N % 128) return "N > 256 must be a multiple of 128";
   if (d->y_dtype != CLSKD_BF16 && d->N > 128 && d->N % 128) return "fp32 output: N > 128 must be a multiple of 128";
   if (d->sf != 1 && d->sf != 2) return "sf must be 1 or 2";
@@ -416,8 +422,8 @@ const char* umma_unsupported(const ClskdTapConv* d) {
   if ((d->stats_sum == nullptr) != (d->stats_sumsq == nullptr)) return "stats_sum and stats_sumsq come together";
   if (d->stats_sum) {
     if (d->y_dtype != CLSKD_BF16) return "fused statistics need a bf16 output";
-    if (d->N != 16 && d->N != 32 && d->N != 64 && d->N != 128 && d->N != 256)
-      return "fused statistics need N in {16,32,64,128,256}";
+    if (d->N != 8 && d->N != 16 && d->N != 32 && d->N != 64 && d->N != 128 && d->N != 256)
+      return "fused statistics need N in {8,16,32,64,128,256}";
   }
   if (d->Fi % d->sf) return "Fi must be a multiple of sf";
   auto chk = [&](const void* x, int64_t sB, int64_t sT, int64_t sF) -> const char* {
@@ -472,10 +478,18 @@ extern "C" int clskd_tapconv_umma_supported(const ClskdTapConv* d) {
   return umma_unsupported(d) == nullptr ? 1 : 0;
 }
 
+static inline int pad16(int v) { return (v + 15) & ~15; }
+
 static int launch_cfg(const ClskdTapConv* d, const FwdCfg& cfg, void* stream) {
-  if (cfg.v1) return clskd_tapconv_fwd_umma_v1(d, stream);
+  const bool padded = (d->c0 % 16) || (d->c1 % 16) || (d->N % 16);
+  if (cfg.v1) {
+    if (padded) { set_error("clskd_tapconv_fwd_umma: the round-1 kernel needs multiples of 16 channels"); return CLSKD_ERR_UNSUPPORTED; }
+    return clskd_tapconv_fwd_umma_v1(d, stream);
+  }
   EncodeTiledFn enc = get_encode();
-  const int Ctot = d->c0 + d->c1;
+  // padded extents: what the kernel contracts / produces (the packed weight is [ntaps][Np][c0p + c1p])
+  const int c0p = pad16(d->c0), c1p = pad16(d->c1), Np = pad16(d->N);
+  const int Ctot = c0p + c1p;
 
   UmmaParams p;
   memset(&p, 0, sizeof(p));
@@ -484,16 +498,16 @@ static int launch_cfg(const ClskdTapConv* d, const FwdCfg& cfg, void* stream) {
   p.t_tile = UM / p.fo_tile;
   p.f_tiles = d->Fo / p.fo_tile;
   p.t_tiles = cdiv(d->To, p.t_tile);
-  p.block_n = d->N <= 256 ? d->N : (d->N % 256 == 0 ? 256 : 128);
+  p.block_n = Np <= 256 ? Np : (Np % 256 == 0 ? 256 : 128);
   p.es = d->y_dtype == CLSKD_BF16 ? 2 : 4;
-  if (p.es == 4 && p.block_n > 128 && d->N % 128 == 0) p.block_n = 128;   // keep the fp32 staging tile <= 64 KB
-  p.tiles_n = d->N / p.block_n;
+  if (p.es == 4 && p.block_n > 128 && Np % 128 == 0) p.block_n = 128;   // keep the fp32 staging tile <= 64 KB
+  p.tiles_n = Np / p.block_n;
   // largest K chunk that divides both sources
   int bk = 64;
-  while (bk > 16 && (d->c0 % bk || (d->c1 % bk))) bk >>= 1;
+  while (bk > 16 && (c0p % bk || (c1p % bk))) bk >>= 1;
   if (cfg.bk_cap >= 16 && bk > cfg.bk_cap) bk = cfg.bk_cap;
   p.block_k = bk;
-  p.chunks0 = d->c0 / bk;
+  p.chunks0 = c0p / bk;
   p.chunks_tot = Ctot / bk;
   p.ntaps = d->ntaps;
   const uint32_t pitch_a = (uint32_t)bk * 2;                 // bytes per patch row (= swizzle span)
@@ -649,8 +663,8 @@ static int launch_cfg(const ClskdTapConv* d, const FwdCfg& cfg, void* stream) {
     tmA1 = tmA0;
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)Ctot, (cuuint64_t)d->N, (cuuint64_t)d->ntaps};
-    cuuint64_t strides[2] = {(cuuint64_t)Ctot * 2, (cuuint64_t)Ctot * 2 * d->N};
+    cuuint64_t dims[3] = {(cuuint64_t)Ctot, (cuuint64_t)Np, (cuuint64_t)d->ntaps};
+    cuuint64_t strides[2] = {(cuuint64_t)Ctot * 2, (cuuint64_t)Ctot * 2 * Np};
     cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.block_n, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), dims,

@@ -210,8 +210,8 @@ int pick_gw(int a, int b) {
 
 const char* wgrad_unsupported(const ClskdTapConv* d) {
   if (d->x_dtype != CLSKD_BF16 || d->y_dtype != CLSKD_BF16) return "x and dy must be bf16";
-  if (d->c0 % 16 || d->c1 % 16) return "channels must be multiples of 16";
-  if (d->N % 16) return "N must be a multiple of 16";
+  if (d->c0 % 8 || d->c1 % 8 || d->c0 < 8) return "channels must be multiples of 8";      // padded to 16 by the round-1 kernel
+  if (d->N % 8 || d->N < 8) return "N must be a multiple of 8";
   if (d->N > 256 && d->N % 128) return "N > 256 must be a multiple of 128";
   if (d->sf != 1 && d->sf != 2) return "sf must be 1 or 2";
   if (!is_pow2(d->Fo) || (d->Fo > 128 && d->Fo % 128)) return "Fo must be a power of two";
@@ -302,7 +302,10 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
   // patch stages lose (+4 .. +15 %): those keep one box per tap.  g_wgrad_mode = 3 forces patches for tests.
   if (g_wgrad_mode == 0 && !(p.n_tile >= 128 && Ctot >= 64)) mode = 1;
   if (g_wgrad_mode == 1) mode = 1;
-  if (mode == 1 && g_wgrad_mode != 4) return clskd_tapconv_wgrad_umma_v1(d, stream);     // (dW already zeroed: harmless)
+  const bool padded = (d->c0 % 16) || (d->c1 % 16) || (d->N % 16);
+  if (padded) mode = 1;
+  if ((mode == 1 && g_wgrad_mode != 4) || padded)
+    return clskd_tapconv_wgrad_umma_v1(d, stream);     // (dW already zeroed: harmless)
   if (g_wgrad_mode == 2) mode = time_ok ? 2 : 1;
   int box_f = p.fo_tile, box_t = p.t_tile;
   int stages = 0;

@@ -33,7 +33,8 @@ struct WgradParamsV1 {
   int ntaps, G, ngroups, c_tiles, n_tiles, n_tile;
   int tap_t[CLSKD_MAX_TAPS], tap_p[CLSKD_MAX_TAPS], tap_f[CLSKD_MAX_TAPS];
   int gw_a, gw_b;                      // swizzle group widths in elements (64 / 32 / 16)
-  int c0, Ctot, N;
+  int c0, Ctot, N;                     // REAL extents (dW layout)
+  int c0p, c1r, Ctot_p;                // source 0 padded to 16 channels, real channels of source 1, padded total
   uint32_t a_sub_bytes, b_sub_bytes, b_stage_bytes;
   uint32_t layout_a, layout_b;
   int a_stages;
@@ -66,7 +67,7 @@ tapconv_wgrad_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
   const int gcur = min(p.G, p.ntaps - tap0);
   const int n0 = n_t * p.n_tile;
   const int cbase = c_t * 128;
-  const int cvalid = min(128, p.Ctot - cbase);
+  const int cvalid = min(128, p.Ctot_p - cbase);      // padded channel axis: [c0 -> c0p | c1 -> c1p]
   const int nsub_a = cvalid / p.gw_a;
   const int nsub_b = p.n_tile / p.gw_b;
   const int tile_beg = blockIdx.x * p.tiles_per_cta;
@@ -115,9 +116,9 @@ tapconv_wgrad_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
           mbar_expect_tx(&a_full[stage], (uint32_t)nsub_a * p.a_sub_bytes);
           for (int s = 0; s < nsub_a; ++s) {
             const int cc = cbase + s * p.gw_a;
-            const bool src0 = cc < p.c0;
+            const bool src0 = cc < p.c0p;      // channels beyond a source's real extent are zero-filled by TMA
             tma_load_5d(a_buf + (size_t)stage * A_STAGE + (size_t)s * p.a_sub_bytes, src0 ? &tmA0 : &tmA1,
-                        &a_full[stage], src0 ? cc : cc - p.c0, p.tap_p[tap], f0 + p.tap_f[tap],
+                        &a_full[stage], src0 ? cc : cc - p.c0p, p.tap_p[tap], f0 + p.tap_f[tap],
                         t0 + p.tap_t[tap], b);
           }
           if (++stage == p.a_stages) {
@@ -165,8 +166,9 @@ tapconv_wgrad_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
   } else if (ntile_cta > 0) {
     // ===================== epilogue (warps 2..5): TMEM -> fp32 reductions into dW =====================
     const int q = warp & 3;
-    const int c_glob = cbase + q * 32 + lane;
-    const bool valid = (q * 32 + lane) < cvalid;
+    const int c_pad = cbase + q * 32 + lane;                 // index on the padded channel axis
+    const int c_glob = c_pad < p.c0p ? c_pad : p.c0 + (c_pad - p.c0p);
+    const bool valid = (q * 32 + lane) < cvalid && (c_pad < p.c0p ? c_pad < p.c0 : (c_pad - p.c0p) < p.c1r);
     mbar_wait(&tmem_full_bar, 0);
     fence_after();
     for (int g = 0; g < gcur; ++g) {
@@ -176,7 +178,8 @@ tapconv_wgrad_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile + c), v);
         if (valid) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) atomicAdd(dst + c + e, __uint_as_float(v[e]));
+          for (int e = 0; e < 16; ++e)
+            if (n0 + c + e < p.N) atomicAdd(dst + c + e, __uint_as_float(v[e]));      // N padded to 16: columns >= N are zero
         }
       }
     }
@@ -195,8 +198,9 @@ int pick_gw_v1(int a, int b) {
 
 const char* wgrad_unsupported_v1(const ClskdTapConv* d) {
   if (d->x_dtype != CLSKD_BF16 || d->y_dtype != CLSKD_BF16) return "x and dy must be bf16";
-  if (d->c0 % 16 || d->c1 % 16) return "channels must be multiples of 16";
-  if (d->N % 16) return "N must be a multiple of 16";
+  // multiples of 8 run padded to 16 (TMA zero fill of the absent channels, gradients of the padding discarded)
+  if (d->c0 % 8 || d->c1 % 8 || d->c0 < 8) return "channels must be multiples of 8";
+  if (d->N % 8 || d->N < 8) return "N must be a multiple of 8";
   if (d->N > 256 && d->N % 128) return "N > 256 must be a multiple of 128";
   if (d->sf != 1 && d->sf != 2) return "sf must be 1 or 2";
   if (!is_pow2(d->Fo) || (d->Fo > 128 && d->Fo % 128)) return "Fo must be a power of two";
@@ -254,15 +258,17 @@ extern "C" int clskd_tapconv_wgrad_umma_v1(const ClskdTapConv* d, void* stream) 
     p.tap_f[j] = fl;
     p.tap_p[j] = df - fl * d->sf;
   }
-  p.n_tile = d->N <= 256 ? d->N : (d->N % 256 == 0 ? 256 : 128);
-  p.n_tiles = d->N / p.n_tile;
+  const int c0p = (d->c0 + 15) & ~15, c1p = (d->c1 + 15) & ~15, Np = (d->N + 15) & ~15;
+  p.n_tile = Np <= 256 ? Np : (Np % 256 == 0 ? 256 : 128);
+  p.n_tiles = Np / p.n_tile;
   p.G = 512 / p.n_tile;
   if (p.G > d->ntaps) p.G = d->ntaps;
   p.ngroups = cdiv(d->ntaps, p.G);
-  p.c_tiles = cdiv(Ctot, 128);
-  p.gw_a = pick_gw_v1(d->c0, d->c1);
+  p.c_tiles = cdiv(c0p + c1p, 128);
+  p.gw_a = pick_gw_v1(c0p, c1p);
   p.gw_b = pick_gw_v1(p.n_tile, 0);
   p.c0 = d->c0; p.Ctot = Ctot; p.N = d->N;
+  p.c0p = c0p; p.c1r = d->c1; p.Ctot_p = c0p + c1p;
   p.a_sub_bytes = (uint32_t)ROWS * p.gw_a * 2;
   p.b_sub_bytes = (uint32_t)ROWS * p.gw_b * 2;
   p.b_stage_bytes = ((uint32_t)ROWS * p.n_tile * 2 + 1023u) & ~1023u;

@@ -178,7 +178,8 @@ def _wgrad_both_policies(cuda_dev, mod, inputs, ops):
 @pytest.mark.parametrize("wmode", [3, 4, 0])
 @pytest.mark.parametrize("case", ["conv_64_128", "conv_32_64", "conv_16_32", "deconv_skip_128", "deconv_skip_64",
                                   "abf3x3_128_256", "abf3x3_128_32", "abf1x1_32_128", "abf3x3F128_128_32",
-                                  "abf3x3F128_32_128", "abf3x3F256_64_48", "abf3x3F64_128_64"])
+                                  "abf3x3F128_32_128", "abf3x3F256_64_48", "abf3x3F64_128_64",
+                                  "conv_8_16", "conv_16_8", "deconv_skip_16", "abf1x1_8_64", "abf3x3_24_40"])
 def test_umma_wgrad_vs_cuda_core(cuda_dev, case, wmode):
     """wmode 3: operand reuse wherever possible (full halo patch at F >= 128, time-grouped patches below); 1: one box per tap"""
     from clskd_b200 import framework as fw
