@@ -300,7 +300,8 @@ int clskd_stftmag_loss_bwd(const float* xs, const float* ys, int64_t n, const do
 /* G[B,B] (fp32) = Z Z^T (+= when accumulate); Z is [B, K] with row stride ldz (elements). */
 int clskd_gram_fwd(const void* z, int dtype, int B, int64_t K, int64_t ldz, float* G,
                    int accumulate, void* stream);
-/* the same Gram product / gradient on the tcgen05 tensor cores (bf16 z, B <= 128, 16-byte aligned
+/* the same Gram product / gradient on the tcgen05 tensor cores (bf16 z, B <= 512 - batches above 128 rows run as
+ * 128-row blocks: cross blocks read both row blocks and write the mirrored result too - 16-byte aligned
  * rows, K >= 4096): each feature element is read from HBM once, partial Grams stay in TMEM.
  * clskd_gram_bwd_umma always overwrites dz. */
 int clskd_gram_umma_supported(const void* z, int dtype, int B, int64_t K, int64_t ldz);

@@ -19,17 +19,22 @@ namespace {
 using namespace umma;
 
 constexpr int kThreads = 192;
-constexpr int GF_STAGES = 6;                     // 6 x 16 KB per CTA: two CTAs per SM = 12 boxes in flight (was 8 with one CTA)
-constexpr uint32_t GF_STAGE_BYTES = 128 * 128;   // 128 rows x 64 bf16
+constexpr int GF_STAGES = 3;                     // 3 x 32 KB per CTA, two CTAs per SM
+constexpr uint32_t GF_STAGE_BYTES = 2 * 128 * 128;   // two 128-row x 64-bf16 boxes (A block, B block; one used when they coincide)
 
 struct GramFwdParams {
-  int B, npad;
+  int B, npad;                      // rows of the A block (M side) / padded rows of the B block (UMMA N)
+  int Bb;                           // rows of the B block
+  int cross;                        // 1: the B operand is a DIFFERENT row block (second tensor map); the result is
+                                    // also written mirrored (G[j][i]) - blocked Gram for batches > 128
+  int ldg, ro_a, ro_b;              // leading dimension of G and the row offsets of the two blocks in it
   int64_t chunks, chunks_per_cta;   // 64-element K chunks
   float* G;
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
-gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramFwdParams p) {
+gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmZb,
+                     const GramFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[GF_STAGES], empty_bar[GF_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
@@ -61,8 +66,11 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramFwdParam
       uint32_t phase = 0;
       for (int it = 0; it < nch; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], GF_STAGE_BYTES);
+        mbar_expect_tx(&full_bar[stage], p.cross ? GF_STAGE_BYTES : GF_STAGE_BYTES / 2);
         tma_load_2d(ring + (size_t)stage * GF_STAGE_BYTES, &tmZ, &full_bar[stage], (int)((c_beg + it) * 64), 0);
+        if (p.cross)
+          tma_load_2d(ring + (size_t)stage * GF_STAGE_BYTES + GF_STAGE_BYTES / 2, &tmZb, &full_bar[stage],
+                      (int)((c_beg + it) * 64), 0);
         if (++stage == GF_STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -80,9 +88,10 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramFwdParam
         fence_after();
         const uint32_t addr = smem_u32(ring + (size_t)stage * GF_STAGE_BYTES);
         const uint64_t desc = make_smem_desc(addr, 1024u >> 4, 2u);   // K-major, 128-byte swizzle
+        const uint64_t descb = p.cross ? make_smem_desc(addr + GF_STAGE_BYTES / 2, 1024u >> 4, 2u) : desc;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base, desc + (uint64_t)(k * 2), desc + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
+          umma_bf16(tmem_base, desc + (uint64_t)(k * 2), descb + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         if (++stage == GF_STAGES) {
           stage = 0;
@@ -103,7 +112,10 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramFwdParam
         if (i < p.B) {
 #pragma unroll
           for (int e = 0; e < 16; ++e)
-            if (c + e < p.B) atomicAdd(p.G + (int64_t)i * p.B + c + e, __uint_as_float(v[e]));
+            if (c + e < p.Bb) {
+              atomicAdd(p.G + (int64_t)(p.ro_a + i) * p.ldg + p.ro_b + c + e, __uint_as_float(v[e]));
+              if (p.cross) atomicAdd(p.G + (int64_t)(p.ro_b + c + e) * p.ldg + p.ro_a + i, __uint_as_float(v[e]));
+            }
         }
       }
     }
@@ -126,6 +138,9 @@ struct GramBwdParams {
   int64_t lddz;
   uint32_t sub_bytes;         // jb * 128 : one 64-k sub-tile of Z^T
   uint32_t s_bytes;           // npad * 128 : one 64-j chunk of S (hi or lo)
+  int ldg, i0, j0, Bj;        // blocked Gram: dG leading dimension, row offsets of the output (i) / contraction (j) blocks,
+                              // rows of the contraction block
+  int accumulate;             // dz += (second contraction block of a batch > 128)
 };
 
 __device__ __forceinline__ uint32_t sw128_offset(int row, int col_elem) {
@@ -167,7 +182,8 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParam
   for (int idx = threadIdx.x; idx < p.npad * p.jb; idx += blockDim.x) {
     const int i = idx / p.jb, j = idx - i * p.jb;
     float s = 0.f;
-    if (i < p.B && j < p.B) s = p.dG[(int64_t)i * p.B + j] + p.dG[(int64_t)j * p.B + i];
+    if (i < p.B && j < p.Bj)
+      s = p.dG[(int64_t)(p.i0 + i) * p.ldg + p.j0 + j] + p.dG[(int64_t)(p.j0 + j) * p.ldg + p.i0 + i];
     const __nv_bfloat16 hi = __float2bfloat16_rn(s);
     const __nv_bfloat16 lo = __float2bfloat16_rn(s - __bfloat162float(hi));
     const uint32_t off = (uint32_t)(j >> 6) * p.s_bytes + sw128_offset(i, j & 63);
@@ -250,11 +266,16 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParam
           for (int e = 0; e < 16; ++e) {
             const int i = c + e;
             if (i < p.B) {
-              const float val = g * __uint_as_float(v[e]);
-              if (p.dz_dtype == CLSKD_BF16)
-                reinterpret_cast<__nv_bfloat16*>(p.dz)[(int64_t)i * p.lddz + k] = __float2bfloat16_rn(val);
-              else
-                reinterpret_cast<float*>(p.dz)[(int64_t)i * p.lddz + k] = val;
+              float val = g * __uint_as_float(v[e]);
+              if (p.dz_dtype == CLSKD_BF16) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dz) + (int64_t)i * p.lddz + k;
+                if (p.accumulate) val += __bfloat162float(*o);
+                *o = __float2bfloat16_rn(val);
+              } else {
+                float* o = reinterpret_cast<float*>(p.dz) + (int64_t)i * p.lddz + k;
+                if (p.accumulate) val += *o;
+                *o = val;
+              }
             }
           }
         }
@@ -270,7 +291,7 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParam
 
 const char* gram_unsupported(const void* z, int dtype, int B, int64_t K, int64_t ldz) {
   if (dtype != CLSKD_BF16) return "z must be bf16";
-  if (B < 1 || B > 128) return "B must be <= 128";
+  if (B < 1 || B > 512) return "B must be <= 512";      // > 128: blocked into 128-row blocks
   if ((uintptr_t)z % 16 || (ldz * 2) % 16) return "z not 16-byte aligned";
   if (K < 64 * 64) return "K too small";
   if (K >= 2147483647LL) return "K too large for a TMA coordinate";
@@ -309,19 +330,6 @@ extern "C" int clskd_gram_fwd_umma(const void* z, int dtype, int B, int64_t K, i
     cudaError_t e = cudaMemsetAsync(G, 0, sizeof(float) * (size_t)B * B, st);
     if (e != cudaSuccess) { set_error("clskd_gram_fwd_umma: memset: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
   }
-  CUtensorMap tmZ;
-  int rc = encode_z(&tmZ, z, B, K, ldz, 128);
-  if (rc) { set_error("clskd_gram_fwd_umma: cuTensorMapEncodeTiled failed: %d", rc); return CLSKD_ERR_CUDA; }
-  GramFwdParams p;
-  p.B = B;
-  p.npad = (B + 15) / 16 * 16;
-  p.chunks = (K + 63) / 64;
-  int64_t ctas = 2 * (int64_t)sm_count();
-  if (ctas > p.chunks / 16) ctas = p.chunks / 16;
-  if (ctas < 1) ctas = 1;
-  p.chunks_per_cta = (p.chunks + ctas - 1) / ctas;
-  ctas = (p.chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
-  p.G = G;
   const size_t smem = (size_t)GF_STAGES * GF_STAGE_BYTES + 1024;
   static bool attr = false;
   if (!attr) {
@@ -329,8 +337,32 @@ extern "C" int clskd_gram_fwd_umma(const void* z, int dtype, int B, int64_t K, i
     if (e != cudaSuccess) { set_error("clskd_gram_fwd_umma: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
     attr = true;
   }
-  gram_fwd_umma_kernel<<<(unsigned)ctas, kThreads, smem, st>>>(tmZ, p);
-  CLSKD_CHECK_LAUNCH("clskd_gram_fwd_umma");
+  // batches > 128 rows: 128-row blocks; block pair (a, b >= a) is one launch (the cross blocks read both row blocks and
+  // write the result and its mirror image)
+  const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z);
+  for (int ra = 0; ra < B; ra += 128)
+    for (int rb = ra; rb < B; rb += 128) {
+      const int Ba = B - ra < 128 ? B - ra : 128, Bb = B - rb < 128 ? B - rb : 128;
+      CUtensorMap tmZ, tmZb;
+      int rc = encode_z(&tmZ, zb + (int64_t)ra * ldz, Ba, K, ldz, 128);
+      if (!rc) rc = encode_z(&tmZb, zb + (int64_t)rb * ldz, Bb, K, ldz, 128);
+      if (rc) { set_error("clskd_gram_fwd_umma: cuTensorMapEncodeTiled failed: %d", rc); return CLSKD_ERR_CUDA; }
+      GramFwdParams p;
+      p.B = Ba;
+      p.Bb = Bb;
+      p.npad = (Bb + 15) / 16 * 16;
+      p.cross = rb != ra ? 1 : 0;
+      p.ldg = B; p.ro_a = ra; p.ro_b = rb;
+      p.chunks = (K + 63) / 64;
+      int64_t ctas = 2 * (int64_t)sm_count();
+      if (ctas > p.chunks / 16) ctas = p.chunks / 16;
+      if (ctas < 1) ctas = 1;
+      p.chunks_per_cta = (p.chunks + ctas - 1) / ctas;
+      ctas = (p.chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;
+      p.G = G;
+      gram_fwd_umma_kernel<<<(unsigned)ctas, kThreads, smem, st>>>(tmZ, tmZb, p);
+      CLSKD_CHECK_LAUNCH("clskd_gram_fwd_umma");
+    }
   return CLSKD_OK;
 }
 
@@ -342,30 +374,43 @@ extern "C" int clskd_gram_bwd_umma(const void* z, int dtype, int B, int64_t K, i
     return CLSKD_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  GramBwdParams p;
-  p.B = B;
-  p.jb = B <= 64 ? 64 : 128;
-  p.npad = (B + 15) / 16 * 16;
-  p.K = K;
-  p.tiles = (K + 127) / 128;
-  int64_t ctas = 2 * (int64_t)sm_count();
-  if (ctas > p.tiles) ctas = p.tiles;
-  p.tiles_per_cta = (p.tiles + ctas - 1) / ctas;
-  ctas = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  p.dG = dG; p.gout = gout; p.dz = dz; p.dz_dtype = dz_dtype; p.lddz = lddz;
-  p.sub_bytes = (uint32_t)p.jb * 128u;
-  p.s_bytes = ((uint32_t)p.npad * 128u + 1023u) & ~1023u;
-  CUtensorMap tmZ;
-  int rc = encode_z(&tmZ, z, B, K, ldz, p.jb);
-  if (rc) { set_error("clskd_gram_bwd_umma: cuTensorMapEncodeTiled failed: %d", rc); return CLSKD_ERR_CUDA; }
-  const size_t smem = 2 * (size_t)(p.jb / 64) * p.s_bytes + (size_t)GB_STAGES * 2 * p.sub_bytes + 1024;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(gram_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("clskd_gram_bwd_umma: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
-    smem_set = smem;
-  }
-  gram_bwd_umma_kernel<<<(unsigned)ctas, kThreads, smem, st>>>(tmZ, p);
-  CLSKD_CHECK_LAUNCH("clskd_gram_bwd_umma");
+  const __nv_bfloat16* zb = reinterpret_cast<const __nv_bfloat16*>(z);
+  const size_t dze = dz_dtype == CLSKD_BF16 ? 2 : 4;
+  // batches > 128 rows: output block i (128 rows of dZ) = sum over contraction blocks j of S[i, j] Z_j: one launch per
+  // (i, j), the second and later j accumulate into dz
+  for (int i0 = 0; i0 < B; i0 += 128)
+    for (int j0 = 0; j0 < B; j0 += 128) {
+      const int Bi = B - i0 < 128 ? B - i0 : 128, Bj = B - j0 < 128 ? B - j0 : 128;
+      GramBwdParams p;
+      p.B = Bi;
+      p.Bj = Bj;
+      p.jb = Bj <= 64 ? 64 : 128;
+      p.npad = (Bi + 15) / 16 * 16;
+      p.K = K;
+      p.tiles = (K + 127) / 128;
+      int64_t ctas = 2 * (int64_t)sm_count();
+      if (ctas > p.tiles) ctas = p.tiles;
+      p.tiles_per_cta = (p.tiles + ctas - 1) / ctas;
+      ctas = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+      p.dG = dG; p.gout = gout;
+      p.dz = reinterpret_cast<uint8_t*>(dz) + (size_t)i0 * lddz * dze;
+      p.dz_dtype = dz_dtype; p.lddz = lddz;
+      p.ldg = B; p.i0 = i0; p.j0 = j0;
+      p.accumulate = j0 > 0 ? 1 : 0;
+      p.sub_bytes = (uint32_t)p.jb * 128u;
+      p.s_bytes = ((uint32_t)p.npad * 128u + 1023u) & ~1023u;
+      CUtensorMap tmZ;
+      int rc = encode_z(&tmZ, zb + (int64_t)j0 * ldz, Bj, K, ldz, p.jb);
+      if (rc) { set_error("clskd_gram_bwd_umma: cuTensorMapEncodeTiled failed: %d", rc); return CLSKD_ERR_CUDA; }
+      const size_t smem = 2 * (size_t)(p.jb / 64) * p.s_bytes + (size_t)GB_STAGES * 2 * p.sub_bytes + 1024;
+      static size_t smem_set = 0;
+      if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(gram_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("clskd_gram_bwd_umma: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
+        smem_set = smem;
+      }
+      gram_bwd_umma_kernel<<<(unsigned)ctas, kThreads, smem, st>>>(tmZ, p);
+      CLSKD_CHECK_LAUNCH("clskd_gram_bwd_umma");
+    }
   return CLSKD_OK;
 }

@@ -226,7 +226,8 @@ def test_umma_wgrad_vs_cuda_core(cuda_dev, case, wmode):
         assert (gu - gref).abs().max().item() < 1e-4 * max(scale, 1.0), (case, k)
 
 
-@pytest.mark.parametrize("B,K", [(64, 128 * 643), (5, 40008), (128, 8192 + 64), (16, 4096)])
+@pytest.mark.parametrize("B,K", [(64, 128 * 643), (5, 40008), (128, 8192 + 64), (16, 4096), (256, 16384 + 64), (192, 8192),
+                                 (130, 4096 + 128)])
 def test_umma_gram_fwd_bwd_vs_torch(cuda_dev, B, K):
     import clskd_b200
     from clskd_b200 import ops
