@@ -141,6 +141,8 @@ struct GramBwdParams {
   int ldg, i0, j0, Bj;        // blocked Gram: dG leading dimension, row offsets of the output (i) / contraction (j) blocks,
                               // rows of the contraction block
   int accumulate;             // dz += (second contraction block of a batch > 128)
+  int stages;                 // ring depth (<= GB_STAGES)
+  uint32_t stg_bytes;         // TMA-store staging: one [npad rows][64 k] bf16 box (two per tile, two tiles buffered)
 };
 
 __device__ __forceinline__ uint32_t sw128_offset(int row, int col_elem) {
@@ -149,8 +151,12 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col_elem) {
   return (uint32_t)(row * 128 + (((chunk ^ (row & 7)) & 7) << 4) + ((col_elem & 7) << 1));
 }
 
+// TMAO: the bf16 dZ tile goes out through shared memory and a TMA store (reduce-add when ACC).  A thread of the direct
+// epilogue walks down the rows of dZ, one 2 MB page per store instruction; at 128 rows that pattern measured 146 GB/s.
+template <bool ACC, bool TMAO>
 __global__ void __launch_bounds__(kThreads, 1)
-gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParams p) {
+gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmDZ,
+                     const GramBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[GB_STAGES], empty_bar[GB_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
@@ -159,8 +165,9 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParam
   const int jchunks = p.jb / 64;
   uint8_t* s_hi = base;                                     // [jchunks][npad rows][128 B]
   uint8_t* s_lo = base + (size_t)jchunks * p.s_bytes;
-  uint8_t* ring = base + 2 * (size_t)jchunks * p.s_bytes;   // GB_STAGES x (2 sub-tiles)
+  uint8_t* ring = base + 2 * (size_t)jchunks * p.s_bytes;   // p.stages x (2 sub-tiles)
   const uint32_t stage_bytes = 2 * p.sub_bytes;
+  uint8_t* stg_base = ring + (size_t)p.stages * stage_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t t_beg = (int64_t)blockIdx.x * p.tiles_per_cta;
   const int64_t t_end = min(p.tiles, t_beg + p.tiles_per_cta);
@@ -208,7 +215,7 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParam
         uint8_t* dst = ring + (size_t)stage * stage_bytes;
         tma_load_2d(dst, &tmZ, &full_bar[stage], (int)k0, 0);
         tma_load_2d(dst + p.sub_bytes, &tmZ, &full_bar[stage], (int)(k0 + 64), 0);
-        if (++stage == GB_STAGES) {
+        if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -243,7 +250,7 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParam
         }
         umma_commit(&empty_bar[stage]);
         umma_commit(&acc_full[as]);
-        if (++stage == GB_STAGES) {
+        if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -252,10 +259,50 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParam
   } else {
     const int q = warp & 3;
     const float g = p.gout ? p.gout[0] : 1.f;
+    const bool issuer = threadIdx.x == 64;
     for (int it = 0; it < nt; ++it) {
       const int as = it & 1;
       mbar_wait(&acc_full[as], (it >> 1) & 1);
       fence_after();
+      if (TMAO) {
+        // the store that last read this staging buffer (two tiles ago) must be done with it
+        uint8_t* stg = stg_base + (size_t)(it & 1) * 2 * p.stg_bytes;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int kl = q * 32 + lane, kk = kl & 63;
+        uint8_t* colp = stg + (size_t)(kl >> 6) * p.stg_bytes + ((kk & 7) << 1);
+        const int chunk = kk >> 3;
+        for (int c = 0; c < p.npad; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.npad + c), v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int i = c + e;
+            *reinterpret_cast<__nv_bfloat16*>(colp + i * 128 + (((chunk ^ (i & 7)) & 7) << 4)) =
+                __float2bfloat16_rn(g * __uint_as_float(v[e]));
+          }
+        }
+        fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          const int64_t k0 = (t_beg + it) * 128;
+          for (int h = 0; h < 2; ++h) {
+            if (k0 + 64 * h >= p.K) break;
+            if (ACC)
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::
+                               "l"(&tmDZ), "r"((int)(k0 + 64 * h)), "r"(0), "r"(smem_u32(stg + (size_t)h * p.stg_bytes))
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::
+                               "l"(&tmDZ), "r"((int)(k0 + 64 * h)), "r"(0), "r"(smem_u32(stg + (size_t)h * p.stg_bytes))
+                           : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        continue;
+      }
       const int64_t k = (t_beg + it) * 128 + q * 32 + lane;
       const bool kv = k < p.K;
       for (int c = 0; c < p.npad; c += 16) {
@@ -269,11 +316,11 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParam
               float val = g * __uint_as_float(v[e]);
               if (p.dz_dtype == CLSKD_BF16) {
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.dz) + (int64_t)i * p.lddz + k;
-                if (p.accumulate) val += __bfloat162float(*o);
+                if (ACC) val += __bfloat162float(*o);
                 *o = __float2bfloat16_rn(val);
               } else {
                 float* o = reinterpret_cast<float*>(p.dz) + (int64_t)i * p.lddz + k;
-                if (p.accumulate) val += *o;
+                if (ACC) val += *o;
                 *o = val;
               }
             }
@@ -283,6 +330,7 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const GramBwdParam
       fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
     }
+    if (TMAO && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
   }
   fence_before();
   __syncthreads();
@@ -399,17 +447,40 @@ extern "C" int clskd_gram_bwd_umma(const void* z, int dtype, int B, int64_t K, i
       p.accumulate = j0 > 0 ? 1 : 0;
       p.sub_bytes = (uint32_t)p.jb * 128u;
       p.s_bytes = ((uint32_t)p.npad * 128u + 1023u) & ~1023u;
-      CUtensorMap tmZ;
+      CUtensorMap tmZ, tmDZ;
       int rc = encode_z(&tmZ, zb + (int64_t)j0 * ldz, Bj, K, ldz, p.jb);
       if (rc) { set_error("clskd_gram_bwd_umma: cuTensorMapEncodeTiled failed: %d", rc); return CLSKD_ERR_CUDA; }
-      const size_t smem = 2 * (size_t)(p.jb / 64) * p.s_bytes + (size_t)GB_STAGES * 2 * p.sub_bytes + 1024;
+      const bool tmao = dz_dtype == CLSKD_BF16 && (uintptr_t)p.dz % 16 == 0 && (lddz * 2) % 16 == 0;
+      p.stg_bytes = tmao ? (((uint32_t)p.npad * 128u + 1023u) & ~1023u) : 0u;
+      if (tmao) {
+        rc = encode_z(&tmDZ, p.dz, Bi, K, lddz, p.npad);
+        if (rc) { set_error("clskd_gram_bwd_umma: cuTensorMapEncodeTiled (dz) failed: %d", rc); return CLSKD_ERR_CUDA; }
+      } else {
+        tmDZ = tmZ;
+      }
+      // two CTAs per SM while the tile is small (64 contraction rows), one at 128
+      const size_t fixed = 2 * (size_t)(p.jb / 64) * p.s_bytes + 4 * (size_t)p.stg_bytes + 1024;
+      const size_t budget = p.jb == 64 ? 110u * 1024u : 226u * 1024u;
+      p.stages = GB_STAGES;
+      while (p.stages > 2 && fixed + (size_t)p.stages * 2 * p.sub_bytes > budget) --p.stages;
+      const size_t smem = fixed + (size_t)p.stages * 2 * p.sub_bytes;
       static size_t smem_set = 0;
       if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(gram_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gram_bwd_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gram_bwd_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gram_bwd_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gram_bwd_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("clskd_gram_bwd_umma: smem attr: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
         smem_set = smem;
       }
-      gram_bwd_umma_kernel<<<(unsigned)ctas, kThreads, smem, st>>>(tmZ, p);
+      const unsigned grid = (unsigned)ctas;
+      if (tmao) {
+        if (p.accumulate) gram_bwd_umma_kernel<true, true><<<grid, kThreads, smem, st>>>(tmZ, tmDZ, p);
+        else gram_bwd_umma_kernel<false, true><<<grid, kThreads, smem, st>>>(tmZ, tmDZ, p);
+      } else {
+        if (p.accumulate) gram_bwd_umma_kernel<true, false><<<grid, kThreads, smem, st>>>(tmZ, tmDZ, p);
+        else gram_bwd_umma_kernel<false, false><<<grid, kThreads, smem, st>>>(tmZ, tmDZ, p);
+      }
       CLSKD_CHECK_LAUNCH("clskd_gram_bwd_umma");
     }
   return CLSKD_OK;
