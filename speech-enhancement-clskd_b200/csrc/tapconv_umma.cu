@@ -276,13 +276,18 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t xr = pitch == 128 ? (uint32_t)(row & 7) : (pitch == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1));
     const bool issuer = (threadIdx.x == 64);                    // first epilogue thread
     const float ep_slope = (EP && p.ep_slope) ? __ldg(p.ep_slope) : 1.f;
-    // batch statistics: thread et owns column (et % ecols) of every staging round and the row slice
-    // [part*ecols, (part+1)*ecols) of the 128-row tile; partial sums stay in registers across all
-    // tiles of this persistent CTA (tiles_n == 1, <= 2 rounds) and are flushed once at the end.
-    // (A 16-byte-per-thread read-back was measured slower: 138 registers instead of 115.)
+    // batch statistics: thread et owns four adjacent columns (one 8-byte word of a staged row) of every staging round and
+    // the row slice [part*st_rows, (part+1)*st_rows) of the 128-row tile; partial sums stay in registers across all tiles
+    // of this persistent CTA (tiles_n == 1, <= 2 rounds) and are flushed once at the end.  (One column per thread and a
+    // 128-row serial loop of 2-byte loads cost 1.4 us per tile - 0.69 ms instead of 0.29 ms on the 1x1 16->128 conv.)
     const int et = threadIdx.x - 64;
-    const int st_col = et % p.ecols, st_part = et / p.ecols;
-    float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f;
+    const int st_nvec = p.ecols >> 2;
+    const int st_parts = UM / st_nvec;
+    const int st_rows = (UM + st_parts - 1) / st_parts;
+    const int st_v = et % st_nvec, st_part = et / st_nvec;
+    const bool st_on = st_part < st_parts;
+    float st_s0[4] = {0.f, 0.f, 0.f, 0.f}, st_q0[4] = {0.f, 0.f, 0.f, 0.f};
+    float st_s1[4] = {0.f, 0.f, 0.f, 0.f}, st_q1[4] = {0.f, 0.f, 0.f, 0.f};
     int local = 0;
     int sround = 0;                                             // staging rounds issued so far
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
@@ -373,28 +378,81 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           // buffer is not rewritten before every epilogue thread has passed the next round's barriers
           int nvalid = (p.To - t0) * p.fo_tile;
           if (nvalid > UM) nvalid = UM;
-          const int sub = st_col / p.gw_y, cl = st_col - sub * p.gw_y;
-          const uint8_t* colp = stg + (size_t)sub * p.y_sub_bytes + ((cl * 2) & 15);
+          const int c4 = st_v * 4;
+          const int sub = c4 / p.gw_y, cl = c4 - sub * p.gw_y;
+          // 32-bit shared-space addresses (LDS.64, four rows in flight); the swizzle term of row rr is
+          // ((chunk ^ ((rr >> xs) & xm)) << 4) with (xs, xm) = (0, 7) / (1, 3) / (2, 1) for 128 / 64 / 32-byte rows
+          const uint32_t colb = smem_u32(stg) + (uint32_t)sub * p.y_sub_bytes + (uint32_t)((cl * 2) & 15);
           const uint32_t chk = (uint32_t)(cl * 2) >> 4;
-          int rend = (st_part + 1) * p.ecols;
+          const uint32_t xs = pitch == 128 ? 0u : (pitch == 64 ? 1u : 2u), xm = 7u >> xs;
+          int rend = (st_part + 1) * st_rows;
           if (rend > nvalid) rend = nvalid;
-          float s = 0.f, q = 0.f;
-          for (int rr = st_part * p.ecols; rr < rend; ++rr) {
-            const uint32_t x2 = pitch == 128 ? (uint32_t)(rr & 7) : (pitch == 64 ? (uint32_t)((rr >> 1) & 3) : (uint32_t)((rr >> 2) & 1));
-            const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + (size_t)rr * pitch + ((chk ^ x2) << 4)));
-            s += v;
-            q = fmaf(v, v, q);
+          if (!st_on) rend = 0;
+          float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int r4 = st_part * st_rows; r4 < rend; r4 += 4) {
+            uint32_t wx[4], wy[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t rr = (uint32_t)(r4 + u);
+              wx[u] = 0u;
+              wy[u] = 0u;
+              if ((int)rr < rend)
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(wx[u]), "=r"(wy[u])
+                             : "r"(colb + rr * pitch + ((chk ^ ((rr >> xs) & xm)) << 4)));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float v0 = __uint_as_float(wx[u] << 16), v1 = __uint_as_float(wx[u] & 0xffff0000u);
+              const float v2 = __uint_as_float(wy[u] << 16), v3 = __uint_as_float(wy[u] & 0xffff0000u);
+              s[0] += v0; q[0] = fmaf(v0, v0, q[0]);
+              s[1] += v1; q[1] = fmaf(v1, v1, q[1]);
+              s[2] += v2; q[2] = fmaf(v2, v2, q[2]);
+              s[3] += v3; q[3] = fmaf(v3, v3, q[3]);
+            }
           }
-          if (rd == 0) { st_s0 += s; st_q0 += q; } else { st_s1 += s; st_q1 += q; }
+          if (rd == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { st_s0[j] += s[j]; st_q0[j] += q[j]; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { st_s1[j] += s[j]; st_q1[j] += q[j]; }
+          }
         }
       }
     }
-    if (EP && p.stats_sum && st_col < p.N) {
-      atomicAdd(p.stats_sum + st_col, (double)st_s0);
-      atomicAdd(p.stats_sumsq + st_col, (double)st_q0);
-      if (p.block_n > p.ecols) {
-        atomicAdd(p.stats_sum + p.ecols + st_col, (double)st_s1);
-        atomicAdd(p.stats_sumsq + p.ecols + st_col, (double)st_q1);
+    if (EP && p.stats_sum) {
+      // one atomic per column and CTA: same-address fp64 atomics retire at about 20 ns each, so per-thread flushes
+      // (parts x CTAs per address) were a 25-100 us tail.  The partial sums meet in the (now idle) staging buffer.
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* scr = reinterpret_cast<float*>(stg_base);           // [round][s|q][part][ecols]
+      const int nrd = p.block_n > p.ecols ? 2 : 1;
+      const int pstride = st_parts * p.ecols;
+      if (st_on) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = st_part * p.ecols + st_v * 4 + j;
+          scr[o] = st_s0[j];
+          scr[pstride + o] = st_q0[j];
+          if (nrd == 2) {
+            scr[2 * pstride + o] = st_s1[j];
+            scr[3 * pstride + o] = st_q1[j];
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = et; c < nrd * p.ecols; c += 128) {
+        const int rd = c / p.ecols, col = c - rd * p.ecols;
+        if (rd * p.ecols + col < p.N) {
+          float s = 0.f, q = 0.f;
+          for (int pt = 0; pt < st_parts; ++pt) {
+            s += scr[(2 * rd) * pstride + pt * p.ecols + col];
+            q += scr[(2 * rd + 1) * pstride + pt * p.ecols + col];
+          }
+          atomicAdd(p.stats_sum + rd * p.ecols + col, (double)s);
+          atomicAdd(p.stats_sumsq + rd * p.ecols + col, (double)q);
+        }
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit

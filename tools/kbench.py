@@ -34,6 +34,8 @@ SHAPES = [
     ("teacher enc4 F16->8 256->256", 64, 643, 16, 256, 256, "5x2s2", False),
     ("teacher dec phase F8 512->256 t2x3", 64, 643, 8, 512, 256, "dec6", False),
     ("teacher dec phase F16 512->128 t2x3", 64, 643, 16, 512, 128, "dec6", False),
+    ("abf_conv1 F256 32->128", 64, 644, 256, 32, 128, "1x1", True),
+    ("abf_conv1 F32 64->128", 64, 643, 32, 64, 128, "1x1", True),
 ]
 
 
@@ -56,6 +58,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--variants", default=None, help="comma-separated subset of variant names")
     ap.add_argument("--shapes", default=None, help="comma-separated shape indices")
+    ap.add_argument("--nostats", action="store_true", help="time every shape without the batch-statistics epilogue")
     a = ap.parse_args()
     from clskd_b200 import _lib
     lib = _lib.load()
@@ -78,6 +81,7 @@ def main():
         shapes = [SHAPES[int(i)] for i in a.shapes.split(",")]
     for name, B, T, F, C, N, kind, stats in shapes:
         taps, sf = taps_of(kind)
+        stats = stats and not a.nostats
         Fo = F // sf
         g = torch.Generator(device="cpu").manual_seed(1)
         xs = [(0.5 * torch.randn(B, T, F, C, generator=g, dtype=torch.float32)).to(dev).bfloat16() for _ in range(1)]
