@@ -110,7 +110,9 @@ int clskd_tapconv_umma_supported(const ClskdTapConv* d);
  *          the environment variable CLSKD_AUTOTUNE=0.
  *   key 6: weight-gradient kernel (clskd_tapconv_wgrad_umma): 1 = one TMA box per tap, 2 = time-grouped patches
  *          at most (no full halo patch), 3 = patches wherever the geometry allows (automatic: only for N >= 128),
- *          4 = one box per tap inside the patch kernel instead of the round-1 kernel (tests) */
+ *          4 = one box per tap inside the patch kernel instead of the round-1 kernel (tests)
+ *   key 7: 1 = LSTM recurrence on the CUDA-core kernels only (the bf16 policy otherwise runs H = 32/64/128 on
+ *          mma.sync tensor-core kernels with W_hh held in registers) */
 int clskd_set_tuning(int key, int value);
 /* the round-1 forward kernel (one TMA box per tap, weights through the ring): A/B baseline only */
 int clskd_tapconv_fwd_umma_v1(const ClskdTapConv* d, void* stream);
@@ -348,6 +350,13 @@ int clskd_lstm_bwd(const float* dh_out, const float* whh, const float* gates, co
                    int R, int Bp, int H, int nsets, int64_t whh_set_stride, int64_t pre_pstride,
                    int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride, float* dpre,
                    void* stream);
+/* Same, with the recurrence precision of the forward pass: w_bf16 != 0 (the bf16 policy) contracts bf16-rounded
+ * W_hh with the gate gradients as a bf16 hi + lo pair on mma.sync tensor cores (H = 32 / 64 / 128; other sizes and
+ * w_bf16 == 0 run the fp32 CUDA-core kernel of clskd_lstm_bwd). */
+int clskd_lstm_bwd_policy(const float* dh_out, const float* whh, const float* gates, const float* c, int T,
+                          int R, int Bp, int H, int nsets, int64_t whh_set_stride, int64_t pre_pstride,
+                          int64_t pre_tstride, int64_t pre_ld, int64_t pre_set_stride, float* dpre,
+                          int w_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * ABF helpers (framework.py:206-224)

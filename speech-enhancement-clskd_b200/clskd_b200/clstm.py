@@ -121,6 +121,7 @@ class ComplexLSTMLayerFn(torch.autograd.Function):
         ctx.plans = plans
         ctx.save_for_backward(X, wr_ih, wi_ih, wr_hh, wi_hh, h, gates, c)
         ctx.dims = (P, T, B, D)
+        ctx.w_bf16 = bool(w_bf16)
         return Y
 
     @staticmethod
@@ -142,8 +143,8 @@ class ComplexLSTMLayerFn(torch.autograd.Function):
         call("clskd_axpby_f32", dY[1].data_ptr(), None, 1.0, 0.0, dh[1, 0].data_ptr(), n, st)
         whh = pack_weights(plans.whh, wr_hh, wi_hh, torch.float32)
         dpre = torch.empty((P, T, B, 2 * G), dtype=torch.float32, device=dev)
-        call("clskd_lstm_bwd", dh.data_ptr(), whh.data_ptr(), gates.data_ptr(), c.data_ptr(), T, P * B, B, H, 2,
-             G * H, T * B * 2 * G, B * 2 * G, 2 * G, G, dpre.data_ptr(), st)
+        call("clskd_lstm_bwd_policy", dh.data_ptr(), whh.data_ptr(), gates.data_ptr(), c.data_ptr(), T, P * B, B, H, 2,
+             G * H, T * B * 2 * G, B * 2 * G, 2 * G, G, dpre.data_ptr(), 1 if ctx.w_bf16 else 0, st)
         need = ctx.needs_input_grad
         dX = None
         if need[1]:
@@ -397,6 +398,7 @@ class LSTMLayerFn(torch.autograd.Function):
         call("clskd_lstm_fwd", pre.data_ptr(), whh_t.data_ptr(), T, B, B, H, 1, T * B * G, B * G, G, 0, H * G,
              1 if w_bf16 else 0, h.data_ptr(), ops._ptr(gates), ops._ptr(c), st)
         ctx.plans = plans
+        ctx.w_bf16 = bool(w_bf16)
         ctx.save_for_backward(X, w_ih, w_hh, h, gates, c)
         return h
 
@@ -413,8 +415,8 @@ class LSTMLayerFn(torch.autograd.Function):
         dh = dense(dY, torch.float32)
         whh = pack_weights(plans.whh, w_hh, None, torch.float32)
         dpre = torch.empty((T, B, G), dtype=torch.float32, device=dev)
-        call("clskd_lstm_bwd", dh.data_ptr(), whh.data_ptr(), gates.data_ptr(), c.data_ptr(), T, B, B, H, 1,
-             G * H, T * B * G, B * G, G, 0, dpre.data_ptr(), st)
+        call("clskd_lstm_bwd_policy", dh.data_ptr(), whh.data_ptr(), gates.data_ptr(), c.data_ptr(), T, B, B, H, 1,
+             G * H, T * B * G, B * G, G, 0, dpre.data_ptr(), 1 if ctx.w_bf16 else 0, st)
         dX = None
         if ctx.needs_input_grad[1]:
             dX = torch.empty(X.shape, dtype=X.dtype, device=dev)

@@ -40,6 +40,7 @@
 
 namespace clskd {
 extern int g_wgrad_mode;               // tapconv_wgrad_umma.cu
+extern int g_lstm_legacy;              // lstm.cu
 namespace {
 using namespace umma;
 
@@ -527,6 +528,7 @@ extern "C" int clskd_set_tuning(int key, int value) {
     case 4: g_tune_split = value; return CLSKD_OK;
     case 5: g_tune_noauto = value; return CLSKD_OK;
     case 6: g_wgrad_mode = value; return CLSKD_OK;
+    case 7: g_lstm_legacy = value; return CLSKD_OK;
     default: set_error("clskd_set_tuning: unknown key %d", key); return CLSKD_ERR_ARG;
   }
 }

@@ -682,6 +682,10 @@ class EmuLib:
                     _arr(cN, nsets * R * H).reshape(nsets, P, Bp, H)[s, p] = cc
         return 0
 
+    def clskd_lstm_bwd_policy(self, dh_out, whh, gates, c, T, R, Bp, H, nsets, wss, pps, pts, pld, pss, dpre, w_bf16,
+                              stream):
+        return self.clskd_lstm_bwd(dh_out, whh, gates, c, T, R, Bp, H, nsets, wss, pps, pts, pld, pss, dpre, stream)
+
     def clskd_lstm_bwd(self, dh_out, whh, gates, c, T, R, Bp, H, nsets, wss, pps, pts, pld, pss, dpre, stream):
         G = 4 * H
         P = R // Bp

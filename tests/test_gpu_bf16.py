@@ -507,3 +507,117 @@ def test_abf_xs2_kernels_vs_round1_xs_kernels_fp32(cuda_dev, C, F, T, B, up, tra
     for n, a, b in zip(names, res[True], res[False]):
         s = max(b.abs().max().item(), 1e-6)
         assert (a - b).abs().max().item() < 2e-4 * s, n
+
+
+def _lstm_reference(pre, whh_t, h0, c0):
+    """float64 recurrence on pre [nsets, P, T, Bp, 4H] with W_hh^T [nsets, H, 4H] (tools_for_model.py:138-178's
+    nn.LSTM cell: gates i, f, g, o)."""
+    nsets, P, T, Bp, G = pre.shape
+    H = G // 4
+    h = torch.zeros(nsets, P, T, Bp, H, dtype=torch.float64)
+    gates = torch.zeros(nsets, P, T, Bp, G, dtype=torch.float64)
+    c = torch.zeros(nsets, P, T, Bp, H, dtype=torch.float64)
+    hh, cc = h0.double().clone(), c0.double().clone()          # [nsets, P, Bp, H]
+    W = whh_t.double()
+    for t in range(T):
+        g_ = pre[:, :, t].double() + torch.einsum("spbk,skg->spbg", hh, W)
+        i_, f_, gg, o_ = (torch.sigmoid(g_[..., :H]), torch.sigmoid(g_[..., H:2 * H]), torch.tanh(g_[..., 2 * H:3 * H]),
+                          torch.sigmoid(g_[..., 3 * H:]))
+        cc = f_ * cc + i_ * gg
+        hh = o_ * torch.tanh(cc)
+        h[:, :, t], c[:, :, t] = hh, cc
+        gates[:, :, t] = torch.cat([i_, f_, gg, o_], -1)
+    return h, gates, c, hh, cc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,P,Bp,T,nsets,state", [(128, 2, 12, 40, 2, False), (64, 2, 5, 33, 2, True),
+                                                  (32, 1, 7, 25, 1, True), (64, 2, 300, 6, 2, False),
+                                                  (128, 2, 301, 5, 2, True)])
+def test_lstm_tensor_core_recurrence_vs_float64_and_cuda_core_kernel(cuda_dev, H, P, Bp, T, nsets, state):
+    """bf16 policy: the mma.sync recurrence (W_hh fragments in registers, h as a bf16 hi+lo pair) against a float64
+    recurrence with the same bf16-rounded W_hh, and against the CUDA-core kernel (tuning key 7) on the same operands.
+    Ragged row counts (rows not a multiple of 8), carried state, and the 16-rows-per-CTA variant (large R)."""
+    from clskd_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(H + Bp + T)
+    G, R = 4 * H, P * Bp
+    pre = torch.randn(P, T, Bp, nsets * G, generator=g)
+    whh_t = (torch.randn(nsets, H, G, generator=g) / H ** 0.5)
+    h0 = 0.5 * torch.randn(nsets, R, H, generator=g) if state else torch.zeros(nsets, R, H)
+    c0 = 0.5 * torch.randn(nsets, R, H, generator=g) if state else torch.zeros(nsets, R, H)
+    pre_sets = torch.stack([pre[..., s * G:(s + 1) * G] for s in range(nsets)])        # [nsets, P, T, Bp, G]
+    ref = _lstm_reference(pre_sets, whh_t.bfloat16().float(), h0.view(nsets, P, Bp, H), c0.view(nsets, P, Bp, H))
+    st = torch.cuda.current_stream().cuda_stream
+    pre_d, w_d = pre.to(cuda_dev), whh_t.to(cuda_dev).contiguous()
+    outs = {}
+    for legacy in (0, 1):
+        lib.clskd_set_tuning(7, legacy)
+        try:
+            h = torch.full((nsets, P, T, Bp, H), float("nan"), device=cuda_dev)
+            gates = torch.full((nsets, P, T, Bp, G), float("nan"), device=cuda_dev)
+            c = torch.full((nsets, P, T, Bp, H), float("nan"), device=cuda_dev)
+            hs, cs = h0.to(cuda_dev).clone(), c0.to(cuda_dev).clone()
+            _lib.call("clskd_lstm_fwd_state", pre_d.data_ptr(), w_d.data_ptr(), T, R, Bp, H, nsets,
+                      T * Bp * nsets * G, Bp * nsets * G, nsets * G, G, H * G, 1, h.data_ptr(), gates.data_ptr(),
+                      c.data_ptr(), hs.data_ptr() if state else None, cs.data_ptr() if state else None,
+                      hs.data_ptr(), cs.data_ptr(), st)
+            torch.cuda.synchronize()
+        finally:
+            lib.clskd_set_tuning(7, 0)
+        outs[legacy] = [x.cpu().double() for x in (h, gates, c, hs.view(nsets, P, Bp, H), cs.view(nsets, P, Bp, H))]
+    for name, a, b, r in zip(("h", "gates", "c", "hN", "cN"), outs[0], outs[1], ref):
+        assert torch.isfinite(a).all(), name
+        assert (a - r).abs().max().item() < 2e-5 * max(1.0, r.abs().max().item()), (name, "vs float64")
+        assert (a - b).abs().max().item() < 2e-5 * max(1.0, r.abs().max().item()), (name, "vs CUDA-core kernel")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,P,Bp,T,nsets", [(128, 2, 12, 30, 2), (64, 2, 5, 33, 2), (32, 1, 7, 25, 1),
+                                            (64, 2, 300, 6, 2), (128, 2, 301, 4, 2)])
+def test_lstm_tensor_core_bptt_vs_float64_and_cuda_core_kernel(cuda_dev, H, P, Bp, T, nsets):
+    """bf16 policy BPTT on mma.sync (W_hh^T fragments in registers, gate gradients as a bf16 hi+lo pair) against a
+    float64 BPTT with the same bf16-rounded W_hh, and against the fp32 CUDA-core kernel (fp32 W_hh: the difference is
+    the weight rounding, bounded by 2^-8 of the gradient scale)."""
+    from clskd_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3 * H + Bp + T)
+    G, R = 4 * H, P * Bp
+    pre = torch.randn(P, T, Bp, nsets * G, generator=g)
+    whh = torch.randn(nsets, G, H, generator=g) / H ** 0.5                 # W_hh [4H][H]
+    pre_sets = torch.stack([pre[..., s * G:(s + 1) * G] for s in range(nsets)])
+    z = torch.zeros(nsets, P, Bp, H)
+    h, gates, c, _, _ = _lstm_reference(pre_sets, whh.bfloat16().float().transpose(1, 2).contiguous(), z, z)
+    dh = torch.randn(nsets, P, T, Bp, H, generator=g)
+    # float64 BPTT (cabi_emu.clskd_lstm_bwd's recurrence) with the bf16-rounded weight
+    Wb = whh.bfloat16().double()
+    ref = torch.zeros(nsets, P, T, Bp, G, dtype=torch.float64)
+    dh_rec = torch.zeros(nsets, P, Bp, H, dtype=torch.float64)
+    dc_next = torch.zeros_like(dh_rec)
+    for t in range(T - 1, -1, -1):
+        gi, gf, gg, go = (gates[:, :, t][..., k * H:(k + 1) * H] for k in range(4))
+        ct = c[:, :, t]
+        cprev = c[:, :, t - 1] if t > 0 else torch.zeros_like(ct)
+        d = dh[:, :, t].double() + dh_rec
+        tc = torch.tanh(ct)
+        do = d * tc * go * (1 - go)
+        dc = d * go * (1 - tc * tc) + dc_next
+        di, df, dg = dc * gg * gi * (1 - gi), dc * cprev * gf * (1 - gf), dc * gi * (1 - gg * gg)
+        dc_next = dc * gf
+        dp = torch.cat([di, df, dg, do], -1)
+        ref[:, :, t] = dp
+        dh_rec = torch.einsum("spbg,sgk->spbk", dp, Wb)
+    st = torch.cuda.current_stream().cuda_stream
+    dev = cuda_dev
+    args = [x.float().contiguous().to(dev) for x in (dh, whh, gates, c)]
+    outs = {}
+    for w_bf16 in (1, 0):
+        dpre = torch.full((P, T, Bp, nsets * G), float("nan"), device=dev)
+        _lib.call("clskd_lstm_bwd_policy", args[0].data_ptr(), args[1].data_ptr(), args[2].data_ptr(), args[3].data_ptr(),
+                  T, R, Bp, H, nsets, G * H, T * Bp * nsets * G, Bp * nsets * G, nsets * G, G, dpre.data_ptr(), w_bf16, st)
+        torch.cuda.synchronize()
+        outs[w_bf16] = torch.stack([dpre[..., s * G:(s + 1) * G] for s in range(nsets)]).cpu().double()
+    scale = ref.abs().max().item()
+    assert torch.isfinite(outs[1]).all()
+    assert (outs[1] - ref).abs().max().item() < 3e-5 * scale
+    assert (outs[1] - outs[0]).abs().max().item() < 2e-2 * scale
