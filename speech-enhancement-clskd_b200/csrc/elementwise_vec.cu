@@ -57,40 +57,71 @@ __global__ void __launch_bounds__(VT) colstats_vec_kernel(const T* __restrict__ 
   float a0[8], a1[8], a2 = 0.f;
 #pragma unroll
   for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.f;
-  float mu[8], is[8], g[8], bt[8];
+  float nmi[8], is[8], g[8], bt[8];          // nmi = -mean * invstd: xhat = x * invstd + nmi
   float sl = 1.f;
+  float2 a2v = make_float2(0.f, 0.f);
   if (MODE == 1) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = cg * 8 + e;
-      mu[e] = mean[c];
       is[e] = invstd[c];
+      nmi[e] = -mean[c] * is[e];
       g[e] = gamma ? gamma[c] : 1.f;
       bt[e] = beta ? beta[c] : 0.f;
     }
     sl = slope ? slope[0] : 1.f;
   }
   if (rs < rows_par) {
-    for (int64_t m = (int64_t)blockIdx.x * rows_par + rs; m < M; m += (int64_t)gridDim.x * rows_par) {
-      float v[8];
-      ld8(x + m * C + cg * 8, v);
-      if (MODE == 0) {
+    // four rows in flight per thread (raw 16-byte loads first): the grid is two CTAs per SM, so that the per-column
+    // fp64 atomics at the end - about 20 ns each on one address - stay a few microseconds
+    constexpr int UR = 4;
+    constexpr int NV = sizeof(T) == 2 ? 1 : 2;                 // 16-byte vectors per 8 channels
+    const int64_t step = (int64_t)gridDim.x * rows_par;
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t m0 = (int64_t)blockIdx.x * rows_par + rs; m0 < M; m0 += UR * step) {
+      uint4 rx[UR][NV], rd[UR][NV];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          a0[e] += v[e];
-          a1[e] = fmaf(v[e], v[e], a1[e]);
+      for (int u = 0; u < UR; ++u) {
+        const int64_t m = m0 + u * step;
+        const bool ok = m < M;
+        const uint4* px = reinterpret_cast<const uint4*>(x + (ok ? m : 0) * C + cg * 8);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) rx[u][q] = ok ? px[q] : z4;
+        if (MODE == 1) {
+          const uint4* pd = reinterpret_cast<const uint4*>(dy + (ok ? m : 0) * C + cg * 8);
+#pragma unroll
+          for (int q = 0; q < NV; ++q) rd[u][q] = ok ? pd[q] : z4;
         }
-      } else {
-        float d[8];
-        ld8(dy + m * C + cg * 8, d);
+      }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xh = (v[e] - mu[e]) * is[e];
-          const float u = fmaf(xh, g[e], bt[e]);
-          const float dz = u > 0.f ? d[e] : d[e] * sl;
-          a0[e] += dz;
-          a1[e] = fmaf(dz, xh, a1[e]);
-          a2 += u > 0.f ? 0.f : d[e] * u;
+      for (int u = 0; u < UR; ++u) {
+        float v[8];
+        ld8(reinterpret_cast<const T*>(&rx[u][0]), v);
+        if (MODE == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            a0[e] += v[e];
+            a1[e] = fmaf(v[e], v[e], a1[e]);
+          }
+        } else {
+          float d[8];
+          ld8(reinterpret_cast<const T*>(&rd[u][0]), d);
+          // packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot per two channels); the PReLU branch is the
+          // 0/1 step st = (u > 0):  dz = d (sl + (1 - sl) st),  dslope += d (u - u st)
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const float2 v2 = make_float2(v[e], v[e + 1]), d2 = make_float2(d[e], d[e + 1]);
+            const float2 xh = __ffma2_rn(v2, make_float2(is[e], is[e + 1]), make_float2(nmi[e], nmi[e + 1]));
+            const float2 uu = __ffma2_rn(xh, make_float2(g[e], g[e + 1]), make_float2(bt[e], bt[e + 1]));
+            const float2 st = make_float2(uu.x > 0.f ? 1.f : 0.f, uu.y > 0.f ? 1.f : 0.f);
+            const float2 dz = __fmul2_rn(d2, __ffma2_rn(st, make_float2(1.f - sl, 1.f - sl), make_float2(sl, sl)));
+            const float2 s0 = __fadd2_rn(make_float2(a0[e], a0[e + 1]), dz);
+            const float2 s1 = __ffma2_rn(dz, xh, make_float2(a1[e], a1[e + 1]));
+            a0[e] = s0.x; a0[e + 1] = s0.y;
+            a1[e] = s1.x; a1[e + 1] = s1.y;
+            const float2 ng = __ffma2_rn(make_float2(-uu.x, -uu.y), st, uu);      // min(u, 0)
+            a2v = __ffma2_rn(d2, ng, a2v);
+          }
         }
       }
     }
@@ -99,7 +130,7 @@ __global__ void __launch_bounds__(VT) colstats_vec_kernel(const T* __restrict__ 
       atomicAdd(&red[cg * 8 + e], a0[e]);
       atomicAdd(&red[C + cg * 8 + e], a1[e]);
     }
-    if (MODE == 1) atomicAdd(&red[2 * C], a2);
+    if (MODE == 1) atomicAdd(&red[2 * C], a2 + a2v.x + a2v.y);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += VT) {
@@ -317,7 +348,8 @@ bool colstats(const void* x, const void* dy, int dtype, int mode, int64_t M, int
               double* o1, double* o2, cudaStream_t st) {
   if (C % 8 || C > 2048 || !al16(x) || (dy && !al16(dy)) || M < 1) return false;
   const int rows_par = VT / (C / 8);
-  const int grid = row_grid(M, rows_par * 4);
+  int grid = row_grid(M, rows_par * 4);
+  if (grid > 2 * sm_count()) grid = 2 * sm_count();
   const size_t sh = sizeof(float) * (2 * (size_t)C + 1);
   if (mode == 0) {
     CLSKD_DISPATCH_DTYPE(dtype, T, (colstats_vec_kernel<T, 0><<<grid, VT, sh, st>>>(
