@@ -313,12 +313,22 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int cbeg = rd * p.ecols;
-        for (int c = cbeg; c < cbeg + p.ecols; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c), v);
+        // two 16-column TMEM loads in flight per wait (the epilogue is a serial chain per tile: this halves the
+        // exposed TMEM round trips)
+        const bool pair = (p.ecols & 31) == 0;
+        for (int c2 = cbeg; c2 < cbeg + p.ecols; c2 += pair ? 32 : 16) {
+          uint32_t va[16], vb[16];
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n + c2);
+          tmem_ld16_async(tcol, va);
+          if (pair) tmem_ld16_async(tcol + 16u, vb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+          if (hh && !pair) break;
+          const int c = c2 + 16 * hh;
           float o[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(v[e]);
+          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(hh ? vb[e] : va[e]);
           // columns >= N exist only as padding of an N that is not a multiple of 16 (zero weights; clipped by the
           // TMA store): their per-channel constants are not read
           const int nlive = p.N - (n0 + c);
@@ -354,6 +364,7 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               *reinterpret_cast<float4*>(rowp + (((ch0 + e) ^ xr) << 4)) =
                   make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
           }
+        }
         }
         if (rd == rounds - 1) {
           // accumulator drained: hand the TMEM buffer back to the MMA warp
