@@ -321,6 +321,83 @@ __global__ void __launch_bounds__(PT) tapsum_fwd_kernel(const TZ* __restrict__ z
 }
 
 
+// ---- N == 2 (the mask-level maps: the only users on the training path) without per-element index arithmetic: one
+// block row per (b, t) line (no divisions per thread), a (tap, 2-channel) pair is one 4-byte (bf16) / 8-byte (fp32)
+// load, the taps are unrolled with all loads issued before the sum.  The generic kernels above spend ~15 instructions
+// per 2-byte load (0.43 ms per launch at 10.5 M outputs against a 0.06 ms HBM floor).
+template <typename T>
+__device__ __forceinline__ float2 ld_pair(const T* p);
+template <>
+__device__ __forceinline__ float2 ld_pair<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <>
+__device__ __forceinline__ float2 ld_pair<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ void st_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st_pair(__nv_bfloat16* p, float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename TZ, typename TY, int NT>
+__global__ void __launch_bounds__(PT) tapsum_fwd_n2_kernel(const TZ* __restrict__ z, int Ti, int Fi, int To, int Fo,
+                                                           int sf, int Zc, TapList taps, const float* __restrict__ bias,
+                                                           TY* __restrict__ y) {
+  const int row = blockIdx.x;                       // b * To + t
+  const int b = row / To, t = row - b * To;
+  const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f;
+  const TZ* zb = z + (int64_t)b * Ti * Fi * Zc;
+  for (int f = blockIdx.y * PT + threadIdx.x; f < Fo; f += gridDim.y * PT) {
+    float2 v[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int tt = t + taps.dt[j];
+      int ff = f + taps.df[j];
+      bool ok = j < taps.n && tt >= 0 && tt < Ti && ff >= 0;
+      if (sf == 2) {
+        ok = ok && !(ff & 1);
+        ff >>= 1;
+      }
+      ok = ok && ff < Fi;
+      v[j] = ok ? ld_pair(zb + ((int64_t)tt * Fi + ff) * Zc + 2 * j) : make_float2(0.f, 0.f);
+    }
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      a0 += v[j].x;
+      a1 += v[j].y;
+    }
+    st_pair(y + ((int64_t)row * Fo + f) * 2, a0 + b0, a1 + b1);
+  }
+}
+
+// one thread per (input position, 8-channel group = 4 taps) of dz
+template <typename TD, typename TZ>
+__global__ void __launch_bounds__(PT) tapsum_bwd_n2_kernel(const TD* __restrict__ dy, int Ti, int Fi, int To, int Fo,
+                                                           int sf, int Zc, TapList taps, TZ* __restrict__ dz) {
+  const int row = blockIdx.x;                       // b * Ti + t
+  const int b = row / Ti, t = row - b * Ti;
+  const int gpr = Zc >> 3;
+  const TD* db = dy + (int64_t)b * To * Fo * 2;
+  for (int i = blockIdx.y * PT + threadIdx.x; i < Fi * gpr; i += gridDim.y * PT) {
+    const int f = i / gpr, g = i - f * gpr;
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = g * 4 + e;
+      float2 v = make_float2(0.f, 0.f);
+      if (j < taps.n) {
+        const int tt = t - taps.dt[j], ff = f * sf - taps.df[j];
+        if (tt >= 0 && tt < To && ff >= 0 && ff < Fo) v = ld_pair(db + ((int64_t)tt * Fo + ff) * 2);
+      }
+      o[2 * e] = v.x;
+      o[2 * e + 1] = v.y;
+    }
+    st8(dz + ((int64_t)row * Fi + f) * Zc + g * 8, o);
+  }
+}
+
 // ---- tiled tap-sum gradient (stride 1, Ti == To, Fi == Fo): one block owns a TT x TF patch of positions of one
 // utterance; the patch of dy rows (N values each) is staged in shared memory, thread (t, f) assembles and stores its
 // whole dz row (measured 0.61 -> 0.48 ms per launch; the same tiling of the FORWARD gather was slower than the direct
@@ -538,6 +615,22 @@ extern "C" int clskd_tapsum_fwd(const void* z, int z_dtype, int B, int Ti, int F
   for (int j = 0; j < ntaps; ++j) { tl.dt[j] = dt_host[j]; tl.df[j] = df_host[j]; }
   const int grid = pw_grid(M);
   cudaStream_t st = (cudaStream_t)stream;
+  if (N == 2 && (sf == 1 || sf == 2) && Zc % 2 == 0 && (uintptr_t)z % 8 == 0 && (uintptr_t)y % 8 == 0 &&
+      (int64_t)B * To < 2147483647LL && ntaps <= 10) {
+    dim3 g2(B * To, cdiv(Fo, PT));
+#define LN(TZ, TY)                                                                                                   \
+  do {                                                                                                               \
+    if (ntaps <= 6) tapsum_fwd_n2_kernel<TZ, TY, 6><<<g2, PT, 0, st>>>((const TZ*)z, Ti, Fi, To, Fo, sf, Zc, tl, bias, (TY*)y); \
+    else tapsum_fwd_n2_kernel<TZ, TY, 10><<<g2, PT, 0, st>>>((const TZ*)z, Ti, Fi, To, Fo, sf, Zc, tl, bias, (TY*)y);  \
+  } while (0)
+    if (z_dtype == CLSKD_F32 && y_dtype == CLSKD_F32) LN(float, float);
+    else if (z_dtype == CLSKD_F32) LN(float, __nv_bfloat16);
+    else if (y_dtype == CLSKD_F32) LN(__nv_bfloat16, float);
+    else LN(__nv_bfloat16, __nv_bfloat16);
+#undef LN
+    CLSKD_CHECK_LAUNCH("clskd_tapsum_fwd(n2)");
+    return CLSKD_OK;
+  }
 #define L(TZ, TY) tapsum_fwd_kernel<TZ, TY><<<grid, PT, 0, st>>>((const TZ*)z, B, Ti, Fi, To, Fo, sf, Zc, tl, N, bias, (TY*)y)
   if (z_dtype == CLSKD_F32 && y_dtype == CLSKD_F32) L(float, float);
   else if (z_dtype == CLSKD_F32) L(float, __nv_bfloat16);
@@ -563,6 +656,17 @@ extern "C" int clskd_tapsum_bwd(const void* dy, int dy_dtype, int B, int Ti, int
   for (int j = 0; j < ntaps; ++j) { tl.dt[j] = dt_host[j]; tl.df[j] = df_host[j]; }
   const int grid = pw_grid(M * (Zc / 8));
   cudaStream_t st = (cudaStream_t)stream;
+  if (N == 2 && (uintptr_t)dy % 8 == 0 && (int64_t)B * Ti < 2147483647LL) {
+    dim3 g2(B * Ti, cdiv((int64_t)Fi * (Zc / 8), PT));
+#define LN(TD, TZ) tapsum_bwd_n2_kernel<TD, TZ><<<g2, PT, 0, st>>>((const TD*)dy, Ti, Fi, To, Fo, sf, Zc, tl, (TZ*)dz)
+    if (dy_dtype == CLSKD_F32 && dz_dtype == CLSKD_F32) LN(float, float);
+    else if (dy_dtype == CLSKD_F32) LN(float, __nv_bfloat16);
+    else if (dz_dtype == CLSKD_F32) LN(__nv_bfloat16, float);
+    else LN(__nv_bfloat16, __nv_bfloat16);
+#undef LN
+    CLSKD_CHECK_LAUNCH("clskd_tapsum_bwd(n2)");
+    return CLSKD_OK;
+  }
   {
     const TapExt te = tap_extents(tl);
     const size_t sh = sizeof(float) * (size_t)(TS_TT + te.tspan) * (TS_TF + te.fspan) * N;

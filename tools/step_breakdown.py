@@ -98,6 +98,10 @@ def main():
             shp = "M=%d Cc=%d" % (args[2], args[3])
         elif name in ("clskd_lstm_fwd",):
             shp = "T=%d R=%d H=%d" % (args[2], args[3], args[5])
+        if name == "clskd_sum_n":
+            shp = "k=%d n=%d %s" % (args[4], args[6], "bf16" if args[5] else "f32")
+        elif name in ("clskd_tapsum_fwd", "clskd_tapsum_bwd"):
+            shp = "B=%d Ti=%d Fi=%d To=%d Fo=%d sf=%d Zc=%d %s" % (tuple(args[2:9]) + ("bf16" if args[1] else "f32",))
         if name == "clskd_strided_copy4d":
             shp = "shape=%s src=%s/%s dst=%s/%s" % (list(args[6]), "bf16" if args[1] else "f32", list(args[2]),
                                                    "bf16" if args[4] else "f32", list(args[5]))
