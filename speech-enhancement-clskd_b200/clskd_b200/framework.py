@@ -243,6 +243,15 @@ class RealConv2d(nn.Module):
         plan = self.plan(x0.shape[-1] if x1 is not None else None)
         return TapConvFn.apply(plan, x0, x1, self.weight, None, self.bias, None, out_dtype or x0.dtype)
 
+    def forward_phys_res(self, x0):
+        """(conv(x0), alias of x0 for a second consumer): the convolution's data gradient is accumulated into the
+        alias' gradient by the kernel epilogue (ops.TapConvResFn) where the tcgen05 path runs, else a plain fan-out"""
+        if (self.bias is None and not self._use_narrow(x0, None) and ops.policy.use_umma and x0.is_cuda
+                and x0.dtype == torch.bfloat16 and torch.is_grad_enabled() and x0.requires_grad):
+            return ops.TapConvResFn.apply(self.plan(None), x0, self.weight, x0.dtype)
+        x0, res = ops.fanout(x0, 2)
+        return self.forward_phys(x0), res
+
     def forward(self, inputs):
         return to_logical(self.forward_phys(to_phys(inputs)))
 
@@ -316,8 +325,7 @@ class ABF(nn.Module):
             xp = self.conv1.forward_phys(to_phys(x))
         if out_shape is not None and xp.shape[2] != out_shape:
             xp = ResizeFFn.apply(xp, out_shape)
-        xp, res = ops.fanout(xp, 2)              # conv2 + residual of the next level
-        out = self.conv2.forward_phys(xp)
+        out, res = self.conv2.forward_phys_res(xp)       # conv2 + residual of the next level
         return to_logical(out), to_logical(res)
 
 

@@ -781,6 +781,88 @@ class TapConvFn(torch.autograd.Function):
         return None, dx0, dx1, da, db, dba, dbb, None
 
 
+class TapConvResFn(torch.autograd.Function):
+    """conv(x) together with an alias of x for a second consumer (the ABF residual, framework.py:221-224):
+    forward(plan, x0, a, out_dtype) -> (y, x0 alias).  The backward receives both gradients at once, so the data
+    gradient of the convolution is ACCUMULATED into the residual's gradient by the tcgen05 epilogue (TMA reduce-add)
+    instead of being written out and summed by a separate pass over three tensors (clskd_sum_n)."""
+
+    @staticmethod
+    def forward(ctx, plan: ConvPlan, x0, a, out_dtype):
+        _require_cuda(x0, None, a)
+        ctx.set_materialize_grads(False)
+        if not _chan_ok(x0):
+            x0 = strided_copy(x0)
+        B, Ti, Fi, _ = x0.shape
+        To, Fo = plan.out_size(Ti, Fi)
+        a32 = _f32c(a)
+        y = torch.empty((B, To, Fo, plan.N), dtype=out_dtype, device=x0.device)
+        ep = _take_epilogue()
+        if ep is not None and ((ep.stats is not None and ep.stats.shape[1] != plan.N) or
+                               (ep.scale is not None and ep.scale.numel() != plan.N)):
+            ep = None
+        for i, l in enumerate(plan.fwd):
+            Fo_l = Fo // l.osf
+            yv = (l.ooff * plan.N, (To * Fo * plan.N, Fo * plan.N, l.osf * plan.N))
+            r = run_tapconv(x0, None, plan.c0, plan.c1, B, To, Fo_l, Ti, Fi, l, a32, None, None, y, y_view=yv, ep=ep)
+            if r is None:
+                if i:
+                    raise RuntimeError("tapconv: fused epilogue refused after the first launch of a plan")
+                ep = None
+                run_tapconv(x0, None, plan.c0, plan.c1, B, To, Fo_l, Ti, Fi, l, a32, None, None, y, y_view=yv)
+        if ep is not None:
+            global fused_epilogues
+            ep.fused = True
+            fused_epilogues += 1
+        ctx.plan = plan
+        ctx.save_for_backward(x0, a)
+        ctx.dims = (B, Ti, Fi, To, Fo)
+        return y, x0.detach().view(x0.shape)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        plan: ConvPlan = ctx.plan
+        x0, a = ctx.saved_tensors
+        B, Ti, Fi, To, Fo = ctx.dims
+        a32 = _f32c(a)
+        need = ctx.needs_input_grad
+        dx0 = da = None
+        cn = plan.c0
+        if dy is None:
+            return None, dres, None, None
+        dy = dense(dy, dy.dtype)
+        if need[1]:
+            acc = (policy.use_umma and dres is not None and dres.dtype == x0.dtype and dres.shape == x0.shape
+                   and dres.is_contiguous())
+            if acc and not getattr(plan, "_res_tuned", False):
+                # an accumulating launch cannot be autotuned on its own output: tune the shape once with a plain launch
+                tmp = torch.empty(x0.shape, dtype=x0.dtype, device=x0.device)
+                for l in plan.dgrad[0]:
+                    yv = (l.ooff * cn, (Ti * Fi * cn, Fi * cn, l.osf * cn))
+                    run_tapconv(dy, None, plan.N, 0, B, Ti, Fi // l.osf, To, Fo, l, a32, None, None, tmp, y_view=yv)
+                plan._res_tuned = True
+                del tmp
+            dx = dres if acc else torch.empty(x0.shape, dtype=x0.dtype, device=x0.device)
+            for l in plan.dgrad[0]:
+                yv = (l.ooff * cn, (Ti * Fi * cn, Fi * cn, l.osf * cn))
+                run_tapconv(dy, None, plan.N, 0, B, Ti, Fi // l.osf, To, Fo, l, a32, None, None, dx, y_view=yv,
+                            accumulate=acc)
+            if not acc and dres is not None:
+                dx = FanoutFn.backward(None, dx, dres)[0]
+            dx0 = dx
+        elif dres is not None:
+            dx0 = dres
+        if need[2]:
+            dwcat = torch.empty(plan.wcat, dtype=torch.float32, device=dy.device)
+            for l in plan.fwd:
+                Fo_l = Fo // l.osf
+                dyv = (l.ooff * plan.N, (To * Fo * plan.N, Fo * plan.N, l.osf * plan.N))
+                dw_view = dwcat[l.woff:l.woff + len(l.dt) * plan.Ctot * plan.N]
+                run_wgrad(x0, None, plan.c0, plan.c1, B, To, Fo_l, Ti, Fi, l, dy, dw_view, dy_view=dyv)
+            da = unpack_grads(dwcat, plan.unpack_a, plan.na).view_as(a)
+        return None, dx0, da, None
+
+
 # --------------------------------------------------------------------------------------------
 # small wrappers
 # --------------------------------------------------------------------------------------------

@@ -506,9 +506,28 @@ class ConvBNAct(nn.Sequential):
     Forward hooks on this module (feature_extraction) see the same output the reference's
     nn.Sequential would produce."""
 
+    _res_holder = None
+
     def _conv(self, x0, x1):
         conv = self[0]
+        if self._res_holder is not None and x1 is None:
+            y, res = conv.forward_phys_res(x0)
+            self._res_holder.append(res)
+            return y
         return conv.forward_phys(x0, x1) if x1 is not None else conv.forward_phys(x0)
+
+    def forward_phys_res(self, x0):
+        """forward_phys(x0) plus an alias of x0 for a second consumer (see RealConv2d.forward_phys_res)"""
+        if not hasattr(self[0], "forward_phys_res"):
+            x0, res = ops.fanout(x0, 2)
+            return self.forward_phys(x0), res
+        self._res_holder = []
+        try:
+            out = self.forward_phys(x0)
+            res = self._res_holder[0]
+        finally:
+            self._res_holder = None
+        return out, res
 
     def forward_phys(self, x0, x1=None):
         if len(self) == 1:

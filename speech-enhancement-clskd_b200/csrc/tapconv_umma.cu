@@ -103,6 +103,7 @@ struct UmmaParams {
   uint32_t stg_off;            // offset of the staging buffers from the ring base
   uint32_t staging_bytes;      // one staging buffer: 128 rows x ecols x es
   int nstg;                    // 1 or 2 staging buffers (double-buffered TMA stores)
+  int accum;                   // 1: TMA reduce-add instead of store (y += tile)
   int ecols;                   // columns staged per TMA-store round (<= 128): block_n / ecols rounds per tile
   // fused epilogue (see ClskdTapConv): folded eval BatchNorm, PReLU, batch statistics of the stored outputs
   const float* ep_scale;
@@ -376,11 +377,18 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (issuer) {
           for (int sidx = 0; sidx < p.ecols / p.gw_y; ++sidx) {
-            asm volatile(
-                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                    reinterpret_cast<uint64_t>(&tmY)),
-                "r"(smem_u32(stg + (size_t)sidx * p.y_sub_bytes)), "r"(n0 + cbeg + sidx * p.gw_y), "r"(f0), "r"(t0), "r"(b)
-                : "memory");
+            if (p.accum)
+              asm volatile(
+                  "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(&tmY)),
+                  "r"(smem_u32(stg + (size_t)sidx * p.y_sub_bytes)), "r"(n0 + cbeg + sidx * p.gw_y), "r"(f0), "r"(t0), "r"(b)
+                  : "memory");
+            else
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(&tmY)),
+                  "r"(smem_u32(stg + (size_t)sidx * p.y_sub_bytes)), "r"(n0 + cbeg + sidx * p.gw_y), "r"(f0), "r"(t0), "r"(b)
+                  : "memory");
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -487,7 +495,9 @@ const char* umma_unsupported(const ClskdTapConv* d) {
   if (d->y_dtype != CLSKD_BF16 && d->N > 128 && d->N % 128) return "fp32 output: N > 128 must be a multiple of 128";
   if (d->sf != 1 && d->sf != 2) return "sf must be 1 or 2";
   if (!is_pow2(d->Fo) || (d->Fo > 128 && d->Fo % 128)) return "Fo must be a power of two";
-  if (d->accumulate) return "accumulate unsupported";
+  // y += result: the epilogue's TMA stores become TMA reduce-adds (performed in L2 in the output type); no fused
+  // epilogue on such a launch
+  if (d->accumulate && (d->stats_sum || d->ep_scale || d->ep_slope)) return "accumulate with a fused epilogue unsupported";
   if ((d->ep_scale == nullptr) != (d->ep_shift == nullptr)) return "ep_scale and ep_shift come together";
   if ((d->stats_sum == nullptr) != (d->stats_sumsq == nullptr)) return "stats_sum and stats_sumsq come together";
   if (d->stats_sum) {
@@ -553,7 +563,7 @@ static inline int pad16(int v) { return (v + 15) & ~15; }
 
 static int launch_cfg(const ClskdTapConv* d, const FwdCfg& cfg, void* stream) {
   const bool padded = (d->c0 % 16) || (d->c1 % 16) || (d->N % 16);
-  if (cfg.v1) {
+  if (cfg.v1 && !d->accumulate) {        // (the round-1 kernel has no reduce-add epilogue)
     if (padded) { set_error("clskd_tapconv_fwd_umma: the round-1 kernel needs multiples of 16 channels"); return CLSKD_ERR_UNSUPPORTED; }
     return clskd_tapconv_fwd_umma_v1(d, stream);
   }
@@ -721,6 +731,7 @@ static int launch_cfg(const ClskdTapConv* d, const FwdCfg& cfg, void* stream) {
   p.bias = d->bias; p.N = d->N;
   p.ep_scale = d->ep_scale; p.ep_shift = d->ep_shift; p.ep_slope = d->ep_slope;
   p.stats_sum = d->stats_sum; p.stats_sumsq = d->stats_sumsq;
+  p.accum = d->accumulate ? 1 : 0;
 
   CUtensorMap tmA0, tmA1, tmB;
   int rc = encode_act_patch(enc, &tmA0, d->x0, d->c0, d->sf, d->Fi, d->Ti, d->B, d->x0_sB, d->x0_sT,
@@ -859,7 +870,12 @@ extern "C" int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream) {
     std::lock_guard<std::mutex> lk(g_tune_mu);
     const std::string key = shape_key(d);
     auto it = g_tune_cache.find(key);
-    if (it == g_tune_cache.end()) it = g_tune_cache.emplace(key, autotune(d, (cudaStream_t)stream)).first;
+    if (it == g_tune_cache.end()) {
+      // an accumulating launch cannot be timed on the caller's tensors (every candidate would add to y): it uses the
+      // configuration a plain launch of the same shape tuned earlier, else the automatic one
+      if (d->accumulate) return launch_cfg(d, FwdCfg{0, 0, 0, 0, 0, 0}, stream);
+      it = g_tune_cache.emplace(key, autotune(d, (cudaStream_t)stream)).first;
+    }
     cfg = it->second;
   }
   return launch_cfg(d, cfg, stream);

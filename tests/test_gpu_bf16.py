@@ -621,3 +621,47 @@ def test_lstm_tensor_core_bptt_vs_float64_and_cuda_core_kernel(cuda_dev, H, P, B
     assert torch.isfinite(outs[1]).all()
     assert (outs[1] - ref).abs().max().item() < 3e-5 * scale
     assert (outs[1] - outs[0]).abs().max().item() < 2e-2 * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout,F,T,B", [(128, 32, 128, 70, 2), (64, 64, 32, 33, 3), (256, 128, 16, 600, 8)])
+def test_conv_with_residual_alias_accumulates_data_gradient(cuda_dev, cin, cout, F, T, B):
+    """RealConv2d.forward_phys_res (ABF conv2 + residual of the next level, framework.py:221-224): the convolution's
+    data gradient is added to the residual's gradient by the tcgen05 epilogue (TMA reduce-add) - against the plain
+    fan-out (separate data gradient + clskd_sum_n) on the same operands, and against torch autograd in fp32."""
+    import clskd_b200
+    from clskd_b200 import framework as fw
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(cin + F + T)
+    conv = fw.RealConv2d(cin, cout, 3, padding=1, bias=False)
+    _round_params(conv)
+    x = (0.5 * torch.randn(B, T, F, cin, generator=g)).bfloat16()
+    gy = torch.randn(B, T, F, cout, generator=g).bfloat16()
+    gres = torch.randn(B, T, F, cin, generator=g).bfloat16()
+    # fp32 reference
+    xr = x.float().permute(0, 3, 2, 1).contiguous().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, conv.weight.detach(), None, padding=1)
+    (yr * gy.float().permute(0, 3, 2, 1)).sum().backward()
+    ref_dx = xr.grad.permute(0, 3, 2, 1) + gres.float()
+    conv = conv.to(cuda_dev)
+    clskd_b200.set_precision("bf16")
+    outs = []
+    for mode in ("res", "fanout"):
+        xd = x.to(cuda_dev).requires_grad_(True)
+        conv.weight.grad = None
+        n0 = ops.umma_launches
+        if mode == "res":
+            y, res = conv.forward_phys_res(xd)
+        else:
+            x0, res = ops.fanout(xd, 2)
+            y = conv.forward_phys(x0)
+        torch.autograd.backward([y, res], [gy.to(cuda_dev), gres.to(cuda_dev).clone()])
+        assert ops.umma_launches > n0
+        outs.append((xd.grad.float().cpu(), conv.weight.grad.float().cpu(), y.detach().float().cpu()))
+    s = ref_dx.abs().max().item()
+    assert (outs[0][2] - outs[1][2]).abs().max().item() == 0.0
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-6 * outs[1][1].abs().max().item()
+    # both round the sum to bf16 once or twice: within two bf16 ulps of the fp32 result
+    assert (outs[0][0] - ref_dx).abs().max().item() < 2.0 ** -7 * s
+    assert (outs[1][0] - ref_dx).abs().max().item() < 2.0 ** -7 * s
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 2.0 ** -7 * s
