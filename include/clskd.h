@@ -146,6 +146,11 @@ int clskd_strided_copy4d(const void* src, int src_dtype, const int64_t* src_stri
  * (tools_for_model.py:252-259, :320-327) in whatever order a kernel wants. */
 int clskd_pack_gather(const float* a, const float* b, const int32_t* table, int64_t n, void* out,
                       int out_dtype, void* stream);
+/* clskd_pack_gather for many weights in one launch (after the optimizer step rewrote the parameters, every packed
+ * kernel-side weight of the step is rebuilt at once instead of lazily, one launch each).  desc: device array of
+ * n_entries x 6 int64 {a, b (or a), table, out, start, n*2 + (out_dtype == CLSKD_BF16)}; `start` = offset of the entry
+ * in the concatenated index space, ascending from 0; total = sum of n. */
+int clskd_multi_pack_gather(const int64_t* desc, int n_entries, int64_t total, void* stream);
 /* dst[j] = s0*src[i0] + s1*src[i1], table entry pair (e0,e1) with e = idx*2 + neg, e<0 -> skipped.
  * Folds the block-weight gradient back onto the reference's separate real/imag parameters. */
 int clskd_unpack_gather2(const float* src, const int32_t* table2, int64_t n, float* dst,

@@ -306,6 +306,7 @@ class FlatAdam:
                      float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
                      k, 1.0 / world_size, ops._stream())
         ops.invalidate_weight_cache()      # the kernel rewrote the parameters in place
+        ops.repack_registered()            # ... and the packed weights the step used are rebuilt in one launch
 
 
 class DistillTrainer:

@@ -452,15 +452,73 @@ def _wkey(a, b):
     return (pa, a._version, pb, b._version if b is not None else 0, weights_epoch if vol else -1)
 
 
+# Packed weights of parameters that live in a volatile range (FlatAdam's bucket) are registered here, so that after
+# the optimizer step ONE launch (clskd_multi_pack_gather) rebuilds all of those the step actually used, in place,
+# instead of one clskd_pack_gather launch per weight at its first use in the next step.
+_pack_registry = {}          # (id(cache), name, dtype) -> _PackEntry
+_pack_desc = None            # (signature, device descriptor tensor, total)
+
+
+class _PackEntry:
+    __slots__ = ("cache", "ckey", "table", "a", "b", "dtype", "out", "used")
+
+    def __init__(self, cache, ckey, table, a, b, dtype, out):
+        import weakref
+        self.cache, self.ckey, self.table, self.dtype, self.out = cache, ckey, table, dtype, out
+        self.a = weakref.ref(a)
+        self.b = weakref.ref(b) if b is not None else None
+        self.used = True
+
+
 def packed_weights(cache, name, table_fn, a, b, dtype):
     """pack_weights(table, a, b, dtype), memoised in `cache` until a / b change."""
     key = _wkey(a, b)
     ent = cache.get((name, dtype))
     if ent is not None and ent[0] == key:
+        reg = _pack_registry.get((id(cache), name, dtype))
+        if reg is not None:
+            reg.used = True
         return ent[1]
-    w = pack_weights(table_fn(), a, b, dtype)
+    table = table_fn()
+    w = pack_weights(table, a, b, dtype)
     cache[(name, dtype)] = (key, w)
+    if key[4] >= 0 and a.is_cuda:          # volatile parameters: candidate for the batched re-pack
+        _pack_registry[(id(cache), name, dtype)] = _PackEntry(cache, (name, dtype), table, a, b, dtype, w)
     return w
+
+
+def repack_registered():
+    """Rebuild, in ONE launch, every registered packed weight that was used since the last call (FlatAdam calls this
+    right after its kernel rewrote the parameters).  Entries whose parameters died, moved or were re-created drop out."""
+    global _pack_desc
+    live = []
+    for rk in list(_pack_registry.keys()):
+        e = _pack_registry[rk]
+        a = e.a()
+        b = e.b() if e.b is not None else None
+        cur = e.cache.get(e.ckey)
+        if a is None or (e.b is not None and b is None) or cur is None or cur[1] is not e.out or not e.used:
+            del _pack_registry[rk]
+            continue
+        live.append((e, a, b))
+    if not live:
+        _pack_desc = None
+        return 0
+    sig = tuple((a.data_ptr(), b.data_ptr() if b is not None else 0, e.table.data_ptr(), e.out.data_ptr())
+                for e, a, b in live)
+    if _pack_desc is None or _pack_desc[0] != sig:
+        rows, start = [], 0
+        for e, a, b in live:
+            n = e.table.shape[0]
+            rows.append([a.data_ptr(), b.data_ptr() if b is not None else a.data_ptr(), e.table.data_ptr(),
+                         e.out.data_ptr(), start, 2 * n + (1 if e.dtype == torch.bfloat16 else 0)])
+            start += n
+        _pack_desc = (sig, torch.tensor(rows, dtype=torch.int64).to(live[0][0].out.device), start)
+    call("clskd_multi_pack_gather", _pack_desc[1].data_ptr(), len(live), _pack_desc[2], _stream())
+    for e, a, b in live:
+        e.cache[e.ckey] = (_wkey(a, b), e.out)
+        e.used = False
+    return len(live)
 
 
 def pack_weights(table, a, b, dtype):

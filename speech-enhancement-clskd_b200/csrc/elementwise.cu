@@ -101,6 +101,35 @@ __global__ void pack_gather_kernel(const float* __restrict__ a, const float* __r
   }
 }
 
+// every registered packed weight in ONE launch: desc[e] = {a, b, table, out, start, n*2 + (out is bf16)} (6 x int64);
+// `start` is the entry's offset in the concatenated index space (ascending), `total` its end
+__global__ void multi_pack_gather_kernel(const int64_t* __restrict__ desc, int n_entries, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_entries - 1;
+    while (lo < hi) {                       // last entry with start <= i
+      const int mid = (lo + hi + 1) >> 1;
+      if (desc[6 * mid + 4] <= i) lo = mid; else hi = mid - 1;
+    }
+    const int64_t* de = desc + 6 * lo;
+    const float* a = reinterpret_cast<const float*>(de[0]);
+    const float* b = reinterpret_cast<const float*>(de[1]);
+    const int32_t* table = reinterpret_cast<const int32_t*>(de[2]);
+    const int64_t j = i - de[4];
+    if (j >= (de[5] >> 1)) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int32_t e = table[2 * j + k];
+      if (e >= 0) {
+        const float t = ((e & 1) ? b : a)[e >> 2];
+        v += (e & 2) ? -t : t;
+      }
+    }
+    if (de[5] & 1) reinterpret_cast<__nv_bfloat16*>(de[3])[j] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(de[3])[j] = v;
+  }
+}
+
 __global__ void unpack_gather2_kernel(const float* __restrict__ src,
                                       const int32_t* __restrict__ table2, int64_t n,
                                       float* __restrict__ dst, int accumulate) {
@@ -1079,6 +1108,14 @@ extern "C" int clskd_pack_gather(const float* a, const float* b, const int32_t* 
     pack_gather_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>(a, b ? b : a, table, n,
                                                            (__nv_bfloat16*)out);
   CLSKD_CHECK_LAUNCH("clskd_pack_gather");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_multi_pack_gather(const int64_t* desc, int n_entries, int64_t total, void* stream) {
+  CLSKD_CHECK_ARG(desc || n_entries == 0, "clskd_multi_pack_gather: null pointer");
+  if (n_entries <= 0 || total <= 0) return CLSKD_OK;
+  multi_pack_gather_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(desc, n_entries, total);
+  CLSKD_CHECK_LAUNCH("clskd_multi_pack_gather");
   return CLSKD_OK;
 }
 

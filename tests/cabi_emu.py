@@ -151,6 +151,14 @@ class EmuLib:
         D[...] = S.copy()
         return 0
 
+    def clskd_multi_pack_gather(self, desc, n_entries, total, stream):
+        d = _arr(desc, 6 * int(n_entries), np.int64).reshape(int(n_entries), 6)
+        for a, b, table, out, start, nn in d:
+            if nn & 1:
+                raise NotImplementedError("cabi_emu: bf16 packed weights")
+            self.clskd_pack_gather(int(a), int(b), int(table), int(nn >> 1), int(out), 0, stream)
+        return 0
+
     def clskd_pack_gather(self, a, b, table, n, out, out_dtype, stream):
         _need_f32(out_dtype)
         n = int(n)

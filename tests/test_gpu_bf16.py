@@ -665,3 +665,54 @@ def test_conv_with_residual_alias_accumulates_data_gradient(cuda_dev, cin, cout,
     assert (outs[0][0] - ref_dx).abs().max().item() < 2.0 ** -7 * s
     assert (outs[1][0] - ref_dx).abs().max().item() < 2.0 ** -7 * s
     assert (outs[0][0] - outs[1][0]).abs().max().item() < 2.0 ** -7 * s
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["clskd", "spkd_all"])
+def test_batched_repack_after_optimizer_step_equals_lazy_pack(cuda_dev, mode):
+    """FlatAdam rewrites the parameters behind autograd's back and then rebuilds every packed kernel-side weight of
+    the step in one launch (ops.repack_registered -> clskd_multi_pack_gather).  After two training steps every
+    registered packed weight must be bit-identical to a fresh clskd_pack_gather of the current parameters, the cache
+    must serve it without a re-pack, and the losses must follow a trainer that packs every weight lazily."""
+    import copy
+    import clskd_b200
+    from clskd_b200 import ops
+    from clskd_b200.distill import DistillTrainer
+    from oracle import dccrn_oracle as D
+    cfg_t = dict(kernel_num=[32, 64, 64, 64, 64, 64], rnn_units=64)
+    cfg_s = dict(kernel_num=[16, 32, 32, 32, 32, 32], rnn_units=32)
+    t_sd = D.make_state_dict(cfg_t["kernel_num"], cfg_t["rnn_units"], seed=1)
+    s_sd = D.make_state_dict(cfg_s["kernel_num"], cfg_s["rnn_units"], seed=2)
+
+    def mk(cfg, sd):
+        m = clskd_b200.DCCRN(rnn_units=cfg["rnn_units"], masking_mode="E", use_clstm=True, kernel_num=cfg["kernel_num"])
+        m.load_state_dict(sd)
+        return m.to(cuda_dev)
+    g = torch.Generator().manual_seed(0)
+    X = (0.1 * torch.randn(4, 8000, generator=g)).to(cuda_dev)
+    y = (0.1 * torch.randn(4, 8000, generator=g)).to(cuda_dev)
+    clskd_b200.set_precision("bf16")
+    losses = {}
+    for lazy in (False, True):
+        torch.manual_seed(11)                        # the ABF blocks are created (randomly initialised) by the trainer
+        tr = DistillTrainer(mk(cfg_t, t_sd), mk(cfg_s, s_sd), mode=mode, lr=1e-3, example_input=X)
+        out = []
+        for it in range(3):
+            if lazy:
+                ops._pack_registry.clear()           # every weight is packed lazily at its first use
+            out.append(float(tr.train_step(X, y)))
+            if not lazy and it == 1:
+                torch.cuda.synchronize()
+                live = [e for e in ops._pack_registry.values() if e.a() is not None]
+                assert len(live) > 20
+                for e in live:
+                    a, b = e.a(), (e.b() if e.b is not None else None)
+                    key, w = e.cache[e.ckey]
+                    assert w is e.out and key == ops._wkey(a, b)
+                    fresh = ops.pack_weights(e.table, a, b, e.dtype)
+                    assert torch.equal(fresh.view(torch.int16 if e.dtype == torch.bfloat16 else torch.int32),
+                                       w.view(torch.int16 if e.dtype == torch.bfloat16 else torch.int32))
+        losses[lazy] = out
+    # (atomic accumulation orders differ run to run: the two trainers agree to rounding, not bitwise)
+    for la, lb in zip(losses[False], losses[True]):
+        assert abs(la - lb) < 5e-4 * abs(lb), losses
