@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(VT) colstats_vec_kernel(const T* __restrict__ 
   if (rs < rows_par) {
     // four rows in flight per thread (raw 16-byte loads first): the grid is two CTAs per SM, so that the per-column
     // fp64 atomics at the end - about 20 ns each on one address - stay a few microseconds
-    constexpr int UR = 4;
+    constexpr int UR = MODE == 0 ? 8 : 4;       // one input tensor in MODE 0: twice the rows for the same bytes in flight
     constexpr int NV = sizeof(T) == 2 ? 1 : 2;                 // 16-byte vectors per 8 channels
     const int64_t step = (int64_t)gridDim.x * rows_par;
     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
