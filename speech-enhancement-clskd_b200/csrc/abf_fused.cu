@@ -130,6 +130,9 @@ __device__ __forceinline__ int64_t yrow(const AbfGeom& g, int64_t m) { return m 
 // them out of registers is what lets two or three CTAs stay resident per SM.
 enum { K_SC = 0, K_SH, K_WX0, K_WY0, K_WX1, K_WY1, K_MU, K_IS, K_GI, K_K1, K_K2, K_W10, K_W11, NCONST };
 
+// channel c = 8*cg + e of a constant vector lives at [e >= 4][cg][e & 3]
+__device__ __forceinline__ int cpos(int c, int C) { return ((c >> 2) & 1) * (C >> 1) + (c >> 3) * 4 + (c & 3); }
+
 __device__ __forceinline__ void stage_consts(float* cs, int C, const float* mean, const float* invstd,
                                              const float* gamma, const float* beta, const float* watt,
                                              const double* sums, double invM, int training,
@@ -137,25 +140,28 @@ __device__ __forceinline__ void stage_consts(float* cs, int C, const float* mean
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float g = gamma ? gamma[c] : 1.f;
     const float sc = invstd[c] * g;
-    cs[K_SC * C + c] = sc;
-    cs[K_SH * C + c] = (beta ? beta[c] : 0.f) - mean[c] * sc;
-    cs[K_WX0 * C + c] = watt[c];
-    cs[K_WY0 * C + c] = watt[C + c];
-    cs[K_WX1 * C + c] = watt[2 * C + c];
-    cs[K_WY1 * C + c] = watt[3 * C + c];
-    cs[K_MU * C + c] = mean[c];
-    cs[K_IS * C + c] = invstd[c];
-    cs[K_GI * C + c] = g * invstd[c];
-    cs[K_K1 * C + c] = (sums && training) ? (float)(sums[c] * invM) : 0.f;
-    cs[K_K2 * C + c] = (sums && training) ? (float)(sums[C + c] * invM) : 0.f;
-    cs[K_W10 * C + c] = w1 ? w1[2 * c] : 0.f;          // conv1 weight [C][2] (XS variants)
-    cs[K_W11 * C + c] = w1 ? w1[2 * c + 1] : 0.f;
+    cs[K_SC * C + cpos(c, C)] = sc;
+    cs[K_SH * C + cpos(c, C)] = (beta ? beta[c] : 0.f) - mean[c] * sc;
+    cs[K_WX0 * C + cpos(c, C)] = watt[c];
+    cs[K_WY0 * C + cpos(c, C)] = watt[C + c];
+    cs[K_WX1 * C + cpos(c, C)] = watt[2 * C + c];
+    cs[K_WY1 * C + cpos(c, C)] = watt[3 * C + c];
+    cs[K_MU * C + cpos(c, C)] = mean[c];
+    cs[K_IS * C + cpos(c, C)] = invstd[c];
+    cs[K_GI * C + cpos(c, C)] = g * invstd[c];
+    cs[K_K1 * C + cpos(c, C)] = (sums && training) ? (float)(sums[c] * invM) : 0.f;
+    cs[K_K2 * C + cpos(c, C)] = (sums && training) ? (float)(sums[C + c] * invM) : 0.f;
+    cs[K_W10 * C + cpos(c, C)] = w1 ? w1[2 * c] : 0.f;          // conv1 weight [C][2] (XS variants)
+    cs[K_W11 * C + cpos(c, C)] = w1 ? w1[2 * c + 1] : 0.f;
   }
   __syncthreads();
 }
 __device__ __forceinline__ void ldc(const float* cs, int which, int C, int cg, float* o) {
-  const float4 a = *reinterpret_cast<const float4*>(cs + which * C + cg * 8);
-  const float4 b = *reinterpret_cast<const float4*>(cs + which * C + cg * 8 + 4);
+  // planar halves (cpos): the 16 lanes of a row read 16 consecutive float4 per load - conflict free.  (With the 8
+  // channels of a lane contiguous the two float4 loads strode 32 bytes: 2-way bank conflicts on every constant load,
+  // 36 % of the kernels' shared-memory wavefronts in ncu.)
+  const float4 a = *reinterpret_cast<const float4*>(cs + which * C + cg * 4);
+  const float4 b = *reinterpret_cast<const float4*>(cs + which * C + (C >> 1) + cg * 4);
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
@@ -603,13 +609,13 @@ __device__ __forceinline__ void xs2_stage_consts(float* cs, int C, const float* 
     const float g = gamma ? gamma[c] : 1.f;
     const float is = invstd[c], sc = is * g, sh = (beta ? beta[c] : 0.f) - mean[c] * sc;
     const float a = w1[2 * c], b = w1[2 * c + 1];
-    cs[X_P * C + c] = sc * a;
-    cs[X_Q * C + c] = sc * b;
-    cs[X_SH * C + c] = sh;
-    cs[X_WY0 * C + c] = watt[C + c];
-    cs[X_WY1 * C + c] = watt[3 * C + c];
-    cs[X_U0 * C + c] = a * g * is;
-    cs[X_U1 * C + c] = b * g * is;
+    cs[X_P * C + cpos(c, C)] = sc * a;
+    cs[X_Q * C + cpos(c, C)] = sc * b;
+    cs[X_SH * C + cpos(c, C)] = sh;
+    cs[X_WY0 * C + cpos(c, C)] = watt[C + c];
+    cs[X_WY1 * C + cpos(c, C)] = watt[3 * C + c];
+    cs[X_U0 * C + cpos(c, C)] = a * g * is;
+    cs[X_U1 * C + cpos(c, C)] = b * g * is;
   }
   __syncthreads();
   // scalars of the x half of the logits: l_k = x0 A_k + x1 B_k + K_k + <yv, wy_k>  (K_k includes the bias)
@@ -617,7 +623,7 @@ __device__ __forceinline__ void xs2_stage_consts(float* cs, int C, const float* 
   if (threadIdx.x < 32) {
     float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int c = threadIdx.x; c < C; c += 32) {
-      const float p = cs[X_P * C + c], q = cs[X_Q * C + c], sh = cs[X_SH * C + c];
+      const float p = cs[X_P * C + cpos(c, C)], q = cs[X_Q * C + cpos(c, C)], sh = cs[X_SH * C + cpos(c, C)];
       const float wx0 = watt[c], wx1 = watt[2 * C + c];
       v[0] = fmaf(p, wx0, v[0]); v[1] = fmaf(q, wx0, v[1]); v[2] = fmaf(sh, wx0, v[2]);
       v[3] = fmaf(p, wx1, v[3]); v[4] = fmaf(q, wx1, v[4]); v[5] = fmaf(sh, wx1, v[5]);

@@ -19,8 +19,10 @@ namespace {
 using namespace umma;
 
 constexpr int kThreads = 192;
-constexpr int GF_STAGES = 3;                     // 3 x 32 KB per CTA, two CTAs per SM
-constexpr uint32_t GF_STAGE_BYTES = 2 * 128 * 128;   // two 128-row x 64-bf16 boxes (A block, B block; one used when they coincide)
+constexpr int GF_STAGES = 6;                     // 96 KB of ring per CTA, two CTAs per SM: 6 one-box stages (one row block:
+                                                 // 12 x 8-16 KB in flight per SM - the kernel is HBM-latency bound) or
+                                                 // 3 two-box stages (cross blocks of a batch > 128)
+constexpr uint32_t GF_STAGE_BYTES = 2 * 128 * 128;   // two 128-row x 64-bf16 boxes (A block, B block)
 
 struct GramFwdParams {
   int B, npad;                      // rows of the A block (M side) / padded rows of the B block (UMMA N)
@@ -45,6 +47,8 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
   const int64_t c_end = min(p.chunks, c_beg + p.chunks_per_cta);
   const int nch = (int)(c_end - c_beg);
   const uint32_t cols = p.npad < 32 ? 32u : (p.npad <= 64 ? 64u : 128u);
+  const int nstages = p.cross ? GF_STAGES / 2 : GF_STAGES;
+  const uint32_t stage_bytes = p.cross ? GF_STAGE_BYTES : GF_STAGE_BYTES / 2;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GF_STAGES; ++s) {
@@ -66,12 +70,12 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       uint32_t phase = 0;
       for (int it = 0; it < nch; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], p.cross ? GF_STAGE_BYTES : GF_STAGE_BYTES / 2);
-        tma_load_2d(ring + (size_t)stage * GF_STAGE_BYTES, &tmZ, &full_bar[stage], (int)((c_beg + it) * 64), 0);
+        mbar_expect_tx(&full_bar[stage], stage_bytes);
+        tma_load_2d(ring + (size_t)stage * stage_bytes, &tmZ, &full_bar[stage], (int)((c_beg + it) * 64), 0);
         if (p.cross)
-          tma_load_2d(ring + (size_t)stage * GF_STAGE_BYTES + GF_STAGE_BYTES / 2, &tmZb, &full_bar[stage],
+          tma_load_2d(ring + (size_t)stage * stage_bytes + GF_STAGE_BYTES / 2, &tmZb, &full_bar[stage],
                       (int)((c_beg + it) * 64), 0);
-        if (++stage == GF_STAGES) {
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -86,14 +90,14 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       for (int it = 0; it < nch; ++it) {
         mbar_wait(&full_bar[stage], phase);
         fence_after();
-        const uint32_t addr = smem_u32(ring + (size_t)stage * GF_STAGE_BYTES);
+        const uint32_t addr = smem_u32(ring + (size_t)stage * stage_bytes);
         const uint64_t desc = make_smem_desc(addr, 1024u >> 4, 2u);   // K-major, 128-byte swizzle
         const uint64_t descb = p.cross ? make_smem_desc(addr + GF_STAGE_BYTES / 2, 1024u >> 4, 2u) : desc;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem_base, desc + (uint64_t)(k * 2), descb + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
-        if (++stage == GF_STAGES) {
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -378,7 +382,7 @@ extern "C" int clskd_gram_fwd_umma(const void* z, int dtype, int B, int64_t K, i
     cudaError_t e = cudaMemsetAsync(G, 0, sizeof(float) * (size_t)B * B, st);
     if (e != cudaSuccess) { set_error("clskd_gram_fwd_umma: memset: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
   }
-  const size_t smem = (size_t)GF_STAGES * GF_STAGE_BYTES + 1024;
+  const size_t smem = (size_t)(GF_STAGES / 2) * GF_STAGE_BYTES + 1024;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gram_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
