@@ -1031,7 +1031,10 @@ int ew_grid_abf(int64_t n) {
 
 int abf_grid(int64_t warp_iters) {
   int64_t blocks = (warp_iters + 7) / 8;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  // the kernels hold two CTAs per SM (launch bounds): a grid of exactly that is one wave - the constants are staged
+  // once per SM slot and the per-column fp64 atomics of the statistics pass (about 20 ns each on one address) come from
+  // 296 CTAs instead of 1184
+  const int64_t cap = (int64_t)sm_count() * 2;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
