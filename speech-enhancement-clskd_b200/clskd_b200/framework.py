@@ -299,8 +299,10 @@ class ABF(nn.Module):
             if ops.policy.use_umma and ops.policy.fuse_epilogue and (bn1.training or not bn1.track_running_stats):
                 ep = ops.Epilogue(stats=torch.zeros(2, bn1.num_features, dtype=torch.float64, device=x.device))
                 ops.request_epilogue(ep)         # batch statistics of z1 from the conv epilogue
-            z1 = self.conv1[0].forward_phys(to_phys(x))                   # 1x1 conv, pre-BatchNorm
-            ops.request_epilogue(None)
+            try:
+                z1 = self.conv1[0].forward_phys(to_phys(x))               # 1x1 conv, pre-BatchNorm
+            finally:
+                ops.request_epilogue(None)
             pre = ep.stats if (ep is not None and ep.fused) else None
             yp = to_phys(y, z1.dtype, need_dense=True)
             if yp.shape[1] != z1.shape[1]:

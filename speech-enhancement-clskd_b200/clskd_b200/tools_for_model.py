@@ -548,8 +548,10 @@ class ConvBNAct(nn.Sequential):
                 ep = ops.Epilogue(scale=fold[0], shift=fold[1],
                                   slope=ops._f32c(slope) if slope is not None else None)
                 ops.request_epilogue(ep)
-                z = self._conv(x0, x1)
-                ops.request_epilogue(None)
+                try:
+                    z = self._conv(x0, x1)
+                finally:
+                    ops.request_epilogue(None)     # never left dangling for an unrelated conv after an exception
                 if ep.fused:
                     return z
                 return bn.forward_phys(z, slope)
@@ -557,8 +559,10 @@ class ConvBNAct(nn.Sequential):
                 # training: the conv epilogue accumulates the batch statistics of what it stores
                 ep = ops.Epilogue(stats=torch.zeros(2, C, dtype=torch.float64, device=x0.device))
                 ops.request_epilogue(ep)
-                z = self._conv(x0, x1)
-                ops.request_epilogue(None)
+                try:
+                    z = self._conv(x0, x1)
+                finally:
+                    ops.request_epilogue(None)
                 return bn.forward_phys(z, slope, ep.stats if ep.fused else None)
         z = self._conv(x0, x1)
         return bn.forward_phys(z, slope)
