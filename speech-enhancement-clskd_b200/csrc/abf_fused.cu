@@ -411,21 +411,27 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
         lg[q] = make_float2(0.f, 0.f);
       }
     }
-    // xhat (kept in place of z1) and xp
+    // xp, and (apply pass) xhat kept in place of z1.  The statistics pass keeps the raw z1: it accumulates
+    // sum dxp z1 and converts to sum dxp xhat = invstd (sum dxp z1 - mean sum dxp) once per CTA - two constant
+    // vectors and two instructions per element less in the pass that is instruction-issue bound
     float xp[2][8];
     {
-      float mu[8], is[8], sc[8], sh[8];
-      ldc(cs, K_MU, C, cg, mu);
-      ldc(cs, K_IS, C, cg, is);
+      float sc[8], sh[8];
       ldc(cs, K_SC, C, cg, sc);
       ldc(cs, K_SH, C, cg, sh);
 #pragma unroll
       for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          xp[q][e] = fmaf(xv[q][e], sc[e], sh[e]);
-          xv[q][e] = (xv[q][e] - mu[e]) * is[e];              // xhat
-        }
+        for (int e = 0; e < 8; ++e) xp[q][e] = fmaf(xv[q][e], sc[e], sh[e]);
+      if (MODE == 1) {
+        float mu[8], is[8];
+        ldc(cs, K_MU, C, cg, mu);
+        ldc(cs, K_IS, C, cg, is);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xv[q][e] = (xv[q][e] - mu[e]) * is[e];              // xhat
+      }
     }
     float s0[2], s1[2], dl0[2], dl1[2];
 #pragma unroll
@@ -568,7 +574,8 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += AT) {
       atomicAdd(sums + i, (double)red[i]);
-      atomicAdd(sums + C + i, (double)red[C + i]);
+      // red[C + i] is this CTA's sum dxp z1 (raw z1): -> sum dxp xhat
+      atomicAdd(sums + C + i, (double)invstd[i] * ((double)red[C + i] - (double)mean[i] * (double)red[i]));
       // dwatt layout = W_att layout [2][2C]: row k, columns [x channels | y channels]
       atomicAdd(dwatt + i, (double)red[2 * C + i]);
       atomicAdd(dwatt + C + i, (double)red[3 * C + i]);
