@@ -197,18 +197,41 @@ __global__ void __launch_bounds__(VT) bn_act_bwd_apply_vec_kernel(const T* __res
     k2[e] = training ? (float)sum_dz_xhat[c] * invM : 0.f;
   }
   const float sl = slope ? slope[0] : 1.f;
-  for (int64_t m = (int64_t)blockIdx.x * rows_par + rs; m < M; m += (int64_t)gridDim.x * rows_par) {
-    float v[8], d[8];
-    ld8(x + m * C + cg * 8, v);
-    ld8(dy + m * C + cg * 8, d);
+  // two rows in flight per thread (raw 16-byte loads first)
+  constexpr int NV = sizeof(T) == 2 ? 1 : 2;
+  const int64_t step = (int64_t)gridDim.x * rows_par;
+  for (int64_t m0 = (int64_t)blockIdx.x * rows_par + rs; m0 < M; m0 += 2 * step) {
+    uint4 rx[2][NV], rd[2][NV];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xh = (v[e] - mu[e]) * is[e];
-      const float u = fmaf(xh, g[e], bt[e]);
-      const float dz = u > 0.f ? d[e] : d[e] * sl;
-      v[e] = g[e] * is[e] * (dz - k1[e] - xh * k2[e]);
+    for (int u = 0; u < 2; ++u) {
+      const int64_t m = m0 + u * step;
+      if (m < M) {
+        const uint4* px = reinterpret_cast<const uint4*>(x + m * C + cg * 8);
+        const uint4* pd = reinterpret_cast<const uint4*>(dy + m * C + cg * 8);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          rx[u][q] = px[q];
+          rd[u][q] = pd[q];
+        }
+      }
     }
-    st8(dx + m * C + cg * 8, v);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t m = m0 + u * step;
+      if (m < M) {
+        float v[8], d[8];
+        ld8(reinterpret_cast<const T*>(&rx[u][0]), v);
+        ld8(reinterpret_cast<const T*>(&rd[u][0]), d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (v[e] - mu[e]) * is[e];
+          const float uu = fmaf(xh, g[e], bt[e]);
+          const float dz = uu > 0.f ? d[e] : d[e] * sl;
+          v[e] = g[e] * is[e] * (dz - k1[e] - xh * k2[e]);
+        }
+        st8(dx + m * C + cg * 8, v);
+      }
+    }
   }
 }
 
