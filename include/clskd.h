@@ -110,7 +110,8 @@ int clskd_tapconv_umma_supported(const ClskdTapConv* d);
  *          the environment variable CLSKD_AUTOTUNE=0.
  *   key 6: weight-gradient kernel (clskd_tapconv_wgrad_umma): 1 = one TMA box per tap, 2 = time-grouped patches
  *          at most (no full halo patch), 3 = patches wherever the geometry allows (automatic: only for N >= 128),
- *          4 = one box per tap inside the patch kernel instead of the round-1 kernel (tests)
+ *          4 = one box per tap inside the patch kernel instead of the round-1 kernel (tests), 5 = never the
+ *          tap-stacked kernel (clskd_tapconv_wgrad_umma_stacked)
  *   key 7: 1 = LSTM recurrence on the CUDA-core kernels only (the bf16 policy otherwise runs H = 32/64/128 on
  *          mma.sync tensor-core kernels with W_hh held in registers) */
 int clskd_set_tuning(int key, int value);
@@ -129,6 +130,11 @@ int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream);
  * tensors/strides (see clskd_tapconv_wgrad_umma_supported). */
 int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream);
 int clskd_tapconv_wgrad_umma_supported(const ClskdTapConv* d);
+/* stride-1 same-size convolutions with N <= 64 and a full (time x frequency) tap grid: the frequency taps are stacked
+ * along the MMA's N dimension (one dY patch per time tap, sub-blocks one patch row apart), the X tile is read once per
+ * time tap instead of once per tap.  clskd_tapconv_wgrad_umma routes eligible launches here (tuning key 6 = 5: never). */
+int clskd_tapconv_wgrad_umma_stacked(const ClskdTapConv* d, void* stream);
+int clskd_tapconv_wgrad_umma_stacked_supported(const ClskdTapConv* d);
 /* the round-1 weight-gradient kernel (one TMA box per tap); clskd_tapconv_wgrad_umma routes its narrow-N launches here */
 int clskd_tapconv_wgrad_umma_v1(const ClskdTapConv* d, void* stream);
 

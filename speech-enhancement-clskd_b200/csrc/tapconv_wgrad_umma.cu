@@ -247,6 +247,8 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
     set_error("clskd_tapconv_wgrad_umma: unsupported: %s", why);
     return CLSKD_ERR_UNSUPPORTED;
   }
+  // narrow-N stride-1 grids of taps: frequency taps stacked along the MMA's N (tapconv_wgrad_stack.cu)
+  if (g_wgrad_mode == 0 && clskd_tapconv_wgrad_umma_stacked_supported(d)) return clskd_tapconv_wgrad_umma_stacked(d, stream);
   cudaStream_t st = (cudaStream_t)stream;
   const int Ctot = d->c0 + d->c1;
   if (!d->accumulate) {
@@ -300,7 +302,7 @@ extern "C" int clskd_tapconv_wgrad_umma(const ClskdTapConv* d, void* stream) {
   // measured (profiles/r02_step_breakdown_d/e.json): patches pay for wide tiles (N >= 128 with >= 64 channels: -12 %);
   // narrow-N launches are bound by the shared-memory operand reads of their MMAs and by stage depth, where the larger
   // patch stages lose (+4 .. +15 %): those keep one box per tap.  g_wgrad_mode = 3 forces patches for tests.
-  if (g_wgrad_mode == 0 && !(p.n_tile >= 128 && Ctot >= 64)) mode = 1;
+  if ((g_wgrad_mode == 0 || g_wgrad_mode == 5) && !(p.n_tile >= 128 && Ctot >= 64)) mode = 1;
   if (g_wgrad_mode == 1) mode = 1;
   const bool padded = (d->c0 % 16) || (d->c1 % 16) || (d->N % 16);
   if (padded) mode = 1;

@@ -716,3 +716,56 @@ def test_batched_repack_after_optimizer_step_equals_lazy_pack(cuda_dev, mode):
     # (atomic accumulation orders differ run to run: the two trainers agree to rounding, not bitwise)
     for la, lb in zip(losses[False], losses[True]):
         assert abs(la - lb) < 5e-4 * abs(lb), losses
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,N,F,T,B", [(128, 32, 128, 70, 8), (128, 64, 64, 131, 8), (64, 16, 32, 261, 8), (192, 24, 128, 35, 16),
+                                       (128, 32, 256, 33, 8)])
+def test_tap_stacked_weight_gradient_vs_torch(cuda_dev, C, N, F, T, B):
+    """clskd_tapconv_wgrad_umma_stacked (frequency taps as sub-blocks of the MMA's N dimension, one patch row apart)
+    against torch's conv2d weight gradient on the same bf16-representable operands; also checks that
+    clskd_tapconv_wgrad_umma routes such a launch there and that tuning key 6 = 5 gives the per-tap kernel's result."""
+    import ctypes
+    from clskd_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(C + N + F)
+    taps = [(dt, df) for df in (-1, 0, 1) for dt in (-1, 0, 1)]
+    x = (0.5 * torch.randn(B, T, F, C, generator=g)).bfloat16()
+    dy = (0.5 * torch.randn(B, T, F, N, generator=g)).bfloat16()
+    # reference: weight gradient of a 3x3 same convolution, fp64 on the CPU
+    xl = x.double().permute(0, 3, 2, 1).contiguous()                 # [B, C, F, T]
+    w = torch.zeros(N, C, 3, 3, dtype=torch.float64, requires_grad=True)
+    yl = torch.nn.functional.conv2d(xl, w, None, padding=1)
+    (yl * dy.double().permute(0, 3, 2, 1)).sum().backward()
+    ref = torch.stack([w.grad[:, :, df + 1, dt + 1].t() for dt, df in taps])          # [taps][C][N]
+    xd, dyd = x.to(cuda_dev), dy.to(cuda_dev)
+    st = torch.cuda.current_stream().cuda_stream
+    d = _lib.TapConv()
+    d.x0, d.x1 = xd.data_ptr(), None
+    d.x0_sB, d.x0_sT, d.x0_sF = T * F * C, F * C, C
+    d.c0, d.c1 = C, 0
+    d.B, d.To, d.Fo, d.Ti, d.Fi = B, T, F, T, F
+    d.sf, d.ntaps = 1, len(taps)
+    for j, (dt, df) in enumerate(taps):
+        d.dt[j], d.df[j] = dt, df
+    d.bias, d.N = None, N
+    d.y = dyd.data_ptr()
+    d.y_sB, d.y_sT, d.y_sF = T * F * N, F * N, N
+    d.x_dtype, d.y_dtype, d.accumulate = _lib.BF16, _lib.BF16, 0
+    assert lib.clskd_tapconv_wgrad_umma_stacked_supported(ctypes.byref(d)) == 1
+    outs = {}
+    for name, entry, mode in (("stacked", "clskd_tapconv_wgrad_umma_stacked", 0), ("routed", "clskd_tapconv_wgrad_umma", 0),
+                              ("per_tap", "clskd_tapconv_wgrad_umma", 5)):
+        dw = torch.full((len(taps), C, N), float("nan"), dtype=torch.float32, device=cuda_dev)
+        d.w = dw.data_ptr()
+        lib.clskd_set_tuning(6, mode)
+        try:
+            _lib.call(entry, ctypes.byref(d), st)
+            torch.cuda.synchronize()
+        finally:
+            lib.clskd_set_tuning(6, 0)
+        outs[name] = dw.cpu().double()
+    scale = ref.abs().max().item()
+    for name, o in outs.items():
+        assert torch.isfinite(o).all(), name
+        assert (o - ref).abs().max().item() < 2e-5 * scale, name          # fp32 accumulation of exact bf16 products
