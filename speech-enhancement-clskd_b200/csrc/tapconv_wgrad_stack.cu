@@ -36,7 +36,10 @@ struct StackParams {
   int a_rows;                    // K rows of one tile (multiple of 16)
   int a_fbox_start;              // frequency coordinate of the X box relative to f0 (0 or -1)
   int b_fbox_start;              // ... of the dY box: a_fbox_start - df_max
-  int ndt, nf, Np, N, Ctot;      // time taps, stacked frequency taps, padded / real N, channels
+  int ndt, nf, Np, N, Ctot;      // time taps, stacked frequency taps, padded / real N, real channels (c0 + c1)
+  int c0, c0p, c1r, Ctot_p;      // source 0 real / padded to 16, real channels of source 1, padded total
+  int gw_a;                      // channels per swizzle group of the X tile (64 / 32 / 16)
+  uint32_t pitch_a, layout_a;
   int gd, ngd;                   // time taps per CTA, number of such chunks
   int c_tiles;
   int dts[MAX_DT];
@@ -51,8 +54,8 @@ struct StackParams {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
-                           const StackParams p) {
+tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX1,
+                           const __grid_constant__ CUtensorMap tmDY, const StackParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
@@ -66,6 +69,8 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   const int g0 = gchunk * p.gd;
   const int gcur = min(p.gd, p.ndt - g0);
   const int cbase = c_t * 128;
+  const int cvalid = min(128, p.Ctot_p - cbase);      // padded channel axis: [c0 -> c0p | c1 -> c1p]
+  const int nsub_a = cvalid / p.gw_a;
   const int tile_beg = blockIdx.x * p.tiles_per_cta;
   const int tile_end = min(p.n_row_tiles, tile_beg + p.tiles_per_cta);
   const int ntile_cta = tile_end - tile_beg;
@@ -107,10 +112,14 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         const int b = r / p.t_tiles;
         const int t0 = t_blk * p.t_tile, f0 = f_blk * 128;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], p.a_stage_bytes + (uint32_t)gcur * p.b_tx);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)nsub_a * p.a_sub_bytes + (uint32_t)gcur * p.b_tx);
         uint8_t* a_dst = ring + (size_t)stage * p.stage_bytes;
-        for (int s = 0; s < 2; ++s)
-          tma_load_4d(a_dst + (size_t)s * p.a_sub_bytes, &tmX, &full_bar[stage], cbase + s * 64, f0 + p.a_fbox_start, t0, b);
+        for (int s = 0; s < nsub_a; ++s) {
+          const int cc = cbase + s * p.gw_a;
+          const bool src0 = cc < p.c0p;        // channels beyond a source's real extent are zero-filled by TMA
+          tma_load_4d(a_dst + (size_t)s * p.a_sub_bytes, src0 ? &tmX : &tmX1, &full_bar[stage], src0 ? cc : cc - p.c0p,
+                      f0 + p.a_fbox_start, t0, b);
+        }
         for (int g = 0; g < gcur; ++g)
           tma_load_4d(a_dst + p.a_stage_bytes + (size_t)g * p.b_patch_bytes, &tmDY, &full_bar[stage], 0,
                       f0 + p.b_fbox_start, t0 - p.dts[g0 + g], b);
@@ -136,8 +145,10 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         for (int g = 0; g < gcur; ++g) {
           const uint32_t b_addr = a_addr + p.a_stage_bytes + (uint32_t)g * p.b_patch_bytes;
           for (int k = 0; k < ksteps; ++k) {
-            // X: 64-channel groups at LBO = a_sub_bytes, 8-row groups at SBO = 1024 (128-byte swizzle)
-            const uint64_t adesc = make_smem_desc_lbo(a_addr + (uint32_t)k * 16u * 128u, p.a_sub_bytes >> 4, 1024u >> 4, 2u);
+            // X: channel groups at LBO = a_sub_bytes, 8-row groups at SBO = 8 rows (sub-blocks past the tile's channels
+            // read stale shared memory: their accumulator rows are never stored)
+            const uint64_t adesc = make_smem_desc_lbo(a_addr + (uint32_t)k * 16u * p.pitch_a, p.a_sub_bytes >> 4,
+                                                      (8u * p.pitch_a) >> 4, p.layout_a);
             // dY: frequency taps at LBO = ONE ROW of the patch
             const uint64_t bdesc = make_smem_desc_lbo(b_addr + (uint32_t)k * 16u * p.pitch_b, p.pitch_b >> 4,
                                                       (8u * p.pitch_b) >> 4, p.layout_b);
@@ -155,8 +166,9 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   } else if (ntile_cta > 0) {
     // ===================== epilogue (warps 2..5): TMEM -> fp32 reductions into dW =====================
     const int q = warp & 3;
-    const int c = cbase + q * 32 + lane;
-    const bool valid = c < p.Ctot;
+    const int c_pad = cbase + q * 32 + lane;                 // index on the padded channel axis
+    const int c = c_pad < p.c0p ? c_pad : p.c0 + (c_pad - p.c0p);
+    const bool valid = (q * 32 + lane) < cvalid && (c_pad < p.c0p ? c_pad < p.c0 : (c_pad - p.c0p) < p.c1r);
     mbar_wait(&tmem_full_bar, 0);
     fence_after();
     for (int g = 0; g < gcur; ++g)
@@ -182,9 +194,9 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
 // geometry the stacked kernel covers; fills the tap grid.  nullptr = supported
 const char* stack_unsupported(const ClskdTapConv* d, StackParams* out) {
   if (d->x_dtype != CLSKD_BF16 || d->y_dtype != CLSKD_BF16) return "x and dy must be bf16";
-  if (d->sf != 1 || d->c1 != 0) return "stride 1, one source only";
+  if (d->sf != 1) return "stride 1 only";
   if (d->Ti != d->To || d->Fi != d->Fo) return "same-size convolution only";
-  if (d->c0 % 64) return "channels must be a multiple of 64";
+  if (d->c0 % 8 || d->c1 % 8 || d->c0 < 8) return "channels must be multiples of 8";
   const int Np = (d->N + 15) & ~15;
   if (Np != 16 && Np != 32 && Np != 64) return "N must pad to 16, 32 or 64";
   if (d->N % 8) return "N must be a multiple of 8";
@@ -221,10 +233,15 @@ const char* stack_unsupported(const ClskdTapConv* d, StackParams* out) {
     return (uintptr_t)x % 16 == 0 && (sB * 2) % 16 == 0 && (sT * 2) % 16 == 0 && (sF * 2) % 16 == 0;
   };
   if (!chk(d->x0, d->x0_sB, d->x0_sT, d->x0_sF) || !chk(d->y, d->y_sB, d->y_sT, d->y_sF)) return "alignment";
+  if (d->c1 && !chk(d->x1, d->x1_sB, d->x1_sT, d->x1_sF)) return "alignment";
   if ((int64_t)d->B * d->To * d->Fo < 65536) return "too few rows";
   if (!get_encode()) return "cuTensorMapEncodeTiled unavailable";
   p.B = d->B; p.T = d->To; p.F = d->Fo;
-  p.ndt = ndt; p.nf = nf; p.Np = Np; p.N = d->N; p.Ctot = d->c0;
+  p.ndt = ndt; p.nf = nf; p.Np = Np; p.N = d->N; p.Ctot = d->c0 + d->c1;
+  p.c0 = d->c0; p.c0p = (d->c0 + 15) & ~15; p.c1r = d->c1; p.Ctot_p = p.c0p + ((d->c1 + 15) & ~15);
+  p.gw_a = (p.c0p % 64 == 0 && (p.Ctot_p - p.c0p) % 64 == 0) ? 64 : ((p.c0p % 32 == 0 && (p.Ctot_p - p.c0p) % 32 == 0) ? 32 : 16);
+  p.pitch_a = (uint32_t)p.gw_a * 2u;
+  p.layout_a = layout_for_bytes((int)p.pitch_a);
   if (d->Fo >= 128) {
     p.t_tile = 1;
     p.f_tiles = d->Fo / 128;
@@ -245,11 +262,11 @@ const char* stack_unsupported(const ClskdTapConv* d, StackParams* out) {
   p.gd = 512 / (nf * Np);
   if (p.gd > ndt) p.gd = ndt;
   p.ngd = cdiv(ndt, p.gd);
-  p.c_tiles = d->c0 / 128 + ((d->c0 % 128) ? 1 : 0);
+  p.c_tiles = cdiv(p.Ctot_p, 128);
   p.pitch_b = (uint32_t)Np * 2u;
   p.layout_b = layout_for_bytes((int)p.pitch_b);
-  p.a_sub_bytes = (uint32_t)p.a_rows * 128u;
-  p.a_stage_bytes = 2u * p.a_sub_bytes;                                  // 128 channels
+  p.a_sub_bytes = (uint32_t)p.a_rows * p.pitch_a;
+  p.a_stage_bytes = (uint32_t)(128 / p.gw_a) * p.a_sub_bytes;            // 128 channel rows of the MMA
   p.b_tx = (uint32_t)(p.a_rows + (p.t_tile == 1 ? nf - 1 : 0)) * p.pitch_b;
   p.b_patch_bytes = (p.b_tx + (uint32_t)(nf - 1) * p.pitch_b + 1023u) & ~1023u;           // shifted reads stay inside
   p.stage_bytes = p.a_stage_bytes + (uint32_t)p.gd * p.b_patch_bytes;
@@ -283,7 +300,7 @@ extern "C" int clskd_tapconv_wgrad_umma_stacked(const ClskdTapConv* d, void* str
     return CLSKD_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(const_cast<void*>(d->w), 0, sizeof(float) * (size_t)d->ntaps * d->c0 * d->N, st);
+  cudaError_t e = cudaMemsetAsync(const_cast<void*>(d->w), 0, sizeof(float) * (size_t)d->ntaps * (d->c0 + d->c1) * d->N, st);
   if (e != cudaSuccess) { set_error("clskd_tapconv_wgrad_umma_stacked: memset: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
   p.dw = reinterpret_cast<float*>(const_cast<void*>(d->w));
   const int ycount = p.ngd * p.c_tiles;
@@ -294,18 +311,21 @@ extern "C" int clskd_tapconv_wgrad_umma_stacked(const ClskdTapConv* d, void* str
   nsplit = cdiv(p.n_row_tiles, p.tiles_per_cta);
 
   EncodeTiledFn enc = get_encode();
-  CUtensorMap tmX, tmDY;
+  CUtensorMap tmX, tmX1, tmDY;
   const int frows = p.t_tile == 1 ? 128 : d->Fo + 8;          // box rows along f per time line (X)
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)d->c0, (cuuint64_t)d->Fi, (cuuint64_t)d->Ti, (cuuint64_t)d->B};
-    cuuint64_t strides[3] = {(cuuint64_t)d->x0_sF * 2, (cuuint64_t)d->x0_sT * 2, (cuuint64_t)d->x0_sB * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)frows, (cuuint32_t)p.t_tile, 1};
+  auto enc_x = [&](CUtensorMap* tm, const void* x, int C, int64_t sB, int64_t sT, int64_t sF) -> int {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)d->Fi, (cuuint64_t)d->Ti, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)sF * 2, (cuuint64_t)sT * 2, (cuuint64_t)sB * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.gw_a, (cuuint32_t)frows, (cuuint32_t)p.t_tile, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x0), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r) { set_error("clskd_tapconv_wgrad_umma_stacked: cuTensorMapEncodeTiled(x) failed: %d", (int)r); return CLSKD_ERR_CUDA; }
-  }
+    return (int)enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes((int)p.pitch_a), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  int rc = enc_x(&tmX, d->x0, d->c0, d->x0_sB, d->x0_sT, d->x0_sF);
+  if (!rc && d->c1) rc = enc_x(&tmX1, d->x1, d->c1, d->x1_sB, d->x1_sT, d->x1_sF);
+  if (rc) { set_error("clskd_tapconv_wgrad_umma_stacked: cuTensorMapEncodeTiled(x) failed: %d", rc); return CLSKD_ERR_CUDA; }
+  if (!d->c1) tmX1 = tmX;
   {
     const int brows = p.t_tile == 1 ? 128 + p.nf - 1 : d->Fo + 8;
     cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->Fo, (cuuint64_t)d->To, (cuuint64_t)d->B};
@@ -325,7 +345,7 @@ extern "C" int clskd_tapconv_wgrad_umma_stacked(const ClskdTapConv* d, void* str
     smem_set = smem;
   }
   dim3 grid((unsigned)nsplit, (unsigned)ycount);
-  tapconv_wgrad_stack_kernel<<<grid, kThreads, smem, st>>>(tmX, tmDY, p);
+  tapconv_wgrad_stack_kernel<<<grid, kThreads, smem, st>>>(tmX, tmX1, tmDY, p);
   CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad_umma_stacked");
   return CLSKD_OK;
 }

@@ -718,32 +718,50 @@ def test_batched_repack_after_optimizer_step_equals_lazy_pack(cuda_dev, mode):
         assert abs(la - lb) < 5e-4 * abs(lb), losses
 
 
+def _shift_tf(x, dt, df):
+    """x[b, t + dt, f + df, :] with zeros outside"""
+    B, T, F, C = x.shape
+    out = torch.zeros_like(x)
+    t0, t1 = max(0, -dt), min(T, T - dt)
+    f0, f1 = max(0, -df), min(F, F - df)
+    if t1 > t0 and f1 > f0:
+        out[:, t0:t1, f0:f1] = x[:, t0 + dt:t1 + dt, f0 + df:f1 + df]
+    return out
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("C,N,F,T,B", [(128, 32, 128, 70, 8), (128, 64, 64, 131, 8), (64, 16, 32, 261, 8), (192, 24, 128, 35, 16),
-                                       (128, 32, 256, 33, 8)])
-def test_tap_stacked_weight_gradient_vs_torch(cuda_dev, C, N, F, T, B):
-    """clskd_tapconv_wgrad_umma_stacked (frequency taps as sub-blocks of the MMA's N dimension, one patch row apart)
-    against torch's conv2d weight gradient on the same bf16-representable operands; also checks that
-    clskd_tapconv_wgrad_umma routes such a launch there and that tuning key 6 = 5 gives the per-tap kernel's result."""
+@pytest.mark.parametrize("c0,c1,N,F,T,B,dts,dfs", [
+    (128, 0, 32, 128, 70, 8, (-1, 0, 1), (-1, 0, 1)), (128, 0, 64, 64, 131, 8, (-1, 0, 1), (-1, 0, 1)),
+    (64, 0, 16, 32, 261, 8, (-1, 0, 1), (-1, 0, 1)), (192, 0, 24, 128, 35, 16, (-1, 0, 1), (-1, 0, 1)),
+    (128, 0, 32, 256, 33, 8, (-1, 0, 1), (-1, 0, 1)),
+    (32, 32, 16, 64, 130, 8, (-1, 0), (-1, 0, 1)), (64, 64, 32, 32, 261, 8, (-1, 0), (0, 1)),
+    (128, 128, 64, 16, 520, 8, (-1, 0), (-1, 0, 1)), (16, 16, 32, 128, 66, 8, (-1, 0), (-1, 0)), (24, 8, 16, 64, 130, 8, (0, 1), (-1, 0, 1))])
+def test_tap_stacked_weight_gradient_vs_torch(cuda_dev, c0, c1, N, F, T, B, dts, dfs):
+    """clskd_tapconv_wgrad_umma_stacked (frequency taps as sub-blocks of the MMA's N dimension, one patch row apart;
+    one or two sources, 64 / 32 / 16-channel swizzle groups) against shifted einsums on the same bf16-representable
+    operands; also checks that clskd_tapconv_wgrad_umma routes such a launch there and that tuning key 6 = 5 gives the
+    per-tap kernel's result."""
     import ctypes
     from clskd_b200 import _lib
     lib = _lib.load()
-    g = torch.Generator().manual_seed(C + N + F)
-    taps = [(dt, df) for df in (-1, 0, 1) for dt in (-1, 0, 1)]
+    g = torch.Generator().manual_seed(c0 + N + F)
+    taps = [(dt, df) for df in dfs for dt in dts]
+    C = c0 + c1
     x = (0.5 * torch.randn(B, T, F, C, generator=g)).bfloat16()
     dy = (0.5 * torch.randn(B, T, F, N, generator=g)).bfloat16()
-    # reference: weight gradient of a 3x3 same convolution, fp64 on the CPU
-    xl = x.double().permute(0, 3, 2, 1).contiguous()                 # [B, C, F, T]
-    w = torch.zeros(N, C, 3, 3, dtype=torch.float64, requires_grad=True)
-    yl = torch.nn.functional.conv2d(xl, w, None, padding=1)
-    (yl * dy.double().permute(0, 3, 2, 1)).sum().backward()
-    ref = torch.stack([w.grad[:, :, df + 1, dt + 1].t() for dt, df in taps])          # [taps][C][N]
-    xd, dyd = x.to(cuda_dev), dy.to(cuda_dev)
+    xd_, dyd_ = x.double(), dy.double()
+    ref = torch.stack([torch.einsum("btfc,btfn->cn", _shift_tf(xd_, dt, df), dyd_) for dt, df in taps])     # [taps][C][N]
+    x0d = x[..., :c0].contiguous().to(cuda_dev)
+    x1d = x[..., c0:].contiguous().to(cuda_dev) if c1 else None
+    dyd = dy.to(cuda_dev)
     st = torch.cuda.current_stream().cuda_stream
     d = _lib.TapConv()
-    d.x0, d.x1 = xd.data_ptr(), None
-    d.x0_sB, d.x0_sT, d.x0_sF = T * F * C, F * C, C
-    d.c0, d.c1 = C, 0
+    d.x0 = x0d.data_ptr()
+    d.x0_sB, d.x0_sT, d.x0_sF = T * F * c0, F * c0, c0
+    d.x1 = x1d.data_ptr() if c1 else None
+    if c1:
+        d.x1_sB, d.x1_sT, d.x1_sF = T * F * c1, F * c1, c1
+    d.c0, d.c1 = c0, c1
     d.B, d.To, d.Fo, d.Ti, d.Fi = B, T, F, T, F
     d.sf, d.ntaps = 1, len(taps)
     for j, (dt, df) in enumerate(taps):

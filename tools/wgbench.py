@@ -21,6 +21,8 @@ SHAPES = [
     ("abf conv2 wgrad F128 128->32 3x3", 64, 643, 128, 128, 32, "3x3"),
     ("abf conv1 wgrad F128 16->128 1x1", 64, 643, 128, 16, 128, "1x1"),
     ("dec phase wgrad F64 64->16 t2x3", 64, 643, 64, 64, 16, "dec6"),
+    ("dec phase wgrad F16 256->64 t2x3", 64, 643, 16, 256, 64, "dec6"),
+    ("abf conv2 wgrad F64 128->64 3x3", 64, 643, 64, 128, 64, "3x3"),
 ]
 
 
