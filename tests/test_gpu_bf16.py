@@ -735,7 +735,9 @@ def _shift_tf(x, dt, df):
     (64, 0, 16, 32, 261, 8, (-1, 0, 1), (-1, 0, 1)), (192, 0, 24, 128, 35, 16, (-1, 0, 1), (-1, 0, 1)),
     (128, 0, 32, 256, 33, 8, (-1, 0, 1), (-1, 0, 1)),
     (32, 32, 16, 64, 130, 8, (-1, 0), (-1, 0, 1)), (64, 64, 32, 32, 261, 8, (-1, 0), (0, 1)),
-    (128, 128, 64, 16, 520, 8, (-1, 0), (-1, 0, 1)), (16, 16, 32, 128, 66, 8, (-1, 0), (-1, 0)), (24, 8, 16, 64, 130, 8, (0, 1), (-1, 0, 1))])
+    (128, 128, 64, 16, 520, 8, (-1, 0), (-1, 0, 1)), (16, 16, 32, 128, 66, 8, (-1, 0), (-1, 0)), (24, 8, 16, 64, 130, 8, (0, 1), (-1, 0, 1)),
+    (16, 0, 32, -64, 130, 8, (-1, 0), (-2, -1, 0, 1, 2)), (32, 0, 64, -32, 261, 8, (-1, 0), (-2, -1, 0, 1, 2)),
+    (64, 0, 16, -128, 66, 8, (-1, 0), (-2, -1, 0, 1, 2)), (8, 0, 24, -64, 131, 8, (-1, 0), (-2, -1, 0, 1, 2))])
 def test_tap_stacked_weight_gradient_vs_torch(cuda_dev, c0, c1, N, F, T, B, dts, dfs):
     """clskd_tapconv_wgrad_umma_stacked (frequency taps as sub-blocks of the MMA's N dimension, one patch row apart;
     one or two sources, 64 / 32 / 16-channel swizzle groups) against shifted einsums on the same bf16-representable
@@ -744,26 +746,30 @@ def test_tap_stacked_weight_gradient_vs_torch(cuda_dev, c0, c1, N, F, T, B, dts,
     import ctypes
     from clskd_b200 import _lib
     lib = _lib.load()
+    sf = 1
+    if F < 0:                  # negative F: stride 2 along f (the encoder layers), -F output frequencies
+        sf, F = 2, -F
+    Fi = F * sf
     g = torch.Generator().manual_seed(c0 + N + F)
     taps = [(dt, df) for df in dfs for dt in dts]
     C = c0 + c1
-    x = (0.5 * torch.randn(B, T, F, C, generator=g)).bfloat16()
+    x = (0.5 * torch.randn(B, T, Fi, C, generator=g)).bfloat16()
     dy = (0.5 * torch.randn(B, T, F, N, generator=g)).bfloat16()
     xd_, dyd_ = x.double(), dy.double()
-    ref = torch.stack([torch.einsum("btfc,btfn->cn", _shift_tf(xd_, dt, df), dyd_) for dt, df in taps])     # [taps][C][N]
+    ref = torch.stack([torch.einsum("btfc,btfn->cn", _shift_tf(xd_, dt, df)[:, :, ::sf], dyd_) for dt, df in taps])     # [taps][C][N]
     x0d = x[..., :c0].contiguous().to(cuda_dev)
     x1d = x[..., c0:].contiguous().to(cuda_dev) if c1 else None
     dyd = dy.to(cuda_dev)
     st = torch.cuda.current_stream().cuda_stream
     d = _lib.TapConv()
     d.x0 = x0d.data_ptr()
-    d.x0_sB, d.x0_sT, d.x0_sF = T * F * c0, F * c0, c0
+    d.x0_sB, d.x0_sT, d.x0_sF = T * Fi * c0, Fi * c0, c0
     d.x1 = x1d.data_ptr() if c1 else None
     if c1:
-        d.x1_sB, d.x1_sT, d.x1_sF = T * F * c1, F * c1, c1
+        d.x1_sB, d.x1_sT, d.x1_sF = T * Fi * c1, Fi * c1, c1
     d.c0, d.c1 = c0, c1
-    d.B, d.To, d.Fo, d.Ti, d.Fi = B, T, F, T, F
-    d.sf, d.ntaps = 1, len(taps)
+    d.B, d.To, d.Fo, d.Ti, d.Fi = B, T, F, T, Fi
+    d.sf, d.ntaps = sf, len(taps)
     for j, (dt, df) in enumerate(taps):
         d.dt[j], d.df[j] = dt, df
     d.bias, d.N = None, N
