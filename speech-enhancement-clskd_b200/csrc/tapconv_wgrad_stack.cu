@@ -144,8 +144,8 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && ntile_cta > 0) {
+    // ===================== MMA issuer (all lanes run the loops; one elected lane issues) =====================
+    if (ntile_cta > 0) {
       int stage = 0;
       uint32_t phase = 0;
       const int ksteps = p.a_rows / 16;
@@ -179,17 +179,17 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
               const uint64_t adesc = make_smem_desc_lbo(a_addr + (uint32_t)k * a_kstep, a_lbo, a_sbo, p.layout_a);
               // dY: frequency taps at LBO = ONE ROW of the patch
               const uint64_t bdesc = make_smem_desc_lbo(b_addr + (uint32_t)k * b_kstep, b_lbo, b_sbo, p.layout_b);
-              umma_bf16(tmem_base + g_col[u], adesc, bdesc, g_idesc[u], (it | k) ? 1u : 0u);
+              umma_bf16_warp(tmem_base + g_col[u], adesc, bdesc, g_idesc[u], (it | k) ? 1u : 0u);
             }
           }
         }
-        umma_commit(&empty_bar[stage]);
+        umma_commit_warp(&empty_bar[stage]);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(&tmem_full_bar);
+      umma_commit_warp(&tmem_full_bar);
     }
   } else if (ntile_cta > 0) {
     // ===================== epilogue (warps 2..5): TMEM -> fp32 reductions into dW =====================

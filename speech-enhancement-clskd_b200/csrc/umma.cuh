@@ -61,6 +61,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// warp-convergent forms: executed by ALL lanes of the issuing warp, one elected lane issues (election and the
+// predicated instruction in one asm block, no divergent branch around them)
+__device__ __forceinline__ void umma_bf16_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
@@ -95,6 +118,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo,
   return ((uint64_t)hi << 32) | lo;
 }
 
+
+// One elected lane of a fully active warp.  The MMA-issuing warp runs its loops on all 32 lanes (warp-uniform control
+// flow and operands) and guards only the tcgen05 instructions with this: inside an `if (lane == 0)` region the compiler
+// cannot prove the uniform-register operands of UTCHMMA uniform and wraps EVERY issue in an ELECT / BRA.U.ANY retry
+// loop (about 50 cycles per MMA - more than a narrow-N instruction takes to execute).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 
 // shared-memory matrix descriptor with an explicit leading-dimension byte offset (MN-major operands)
 __device__ __forceinline__ uint64_t make_smem_desc_lbo(uint32_t saddr, uint32_t lbo, uint32_t sbo,
