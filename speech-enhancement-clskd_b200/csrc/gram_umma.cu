@@ -82,7 +82,7 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nch > 0) {
+    if (nch > 0) {     // all lanes run the loop, one elected lane issues
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       int stage = 0;
@@ -95,14 +95,14 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
         const uint64_t descb = p.cross ? make_smem_desc(addr + GF_STAGE_BYTES / 2, 1024u >> 4, 2u) : desc;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base, desc + (uint64_t)(k * 2), descb + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);
+          umma_bf16_warp(tmem_base, desc + (uint64_t)(k * 2), descb + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
+        umma_commit_warp(&empty_bar[stage]);
         if (++stage == nstages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(&tmem_full_bar);
+      umma_commit_warp(&tmem_full_bar);
     }
   } else if (nch > 0) {
     const int q = warp & 3;
@@ -226,7 +226,7 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                  // all lanes run the loop, one elected lane issues
       // A = Z^T tile, MN-major (bit 15); B = S, K-major; N = npad, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) |
                              ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -248,12 +248,12 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
             // B: K-major S chunk (64 j per 128-byte row); +32 B per 16 j inside a chunk
             const uint32_t sb = s_addr + (uint32_t)(k >> 2) * p.s_bytes + (uint32_t)(k & 3) * 32u;
             const uint64_t bdesc = make_smem_desc(sb, 1024u >> 4, 2u);
-            umma_bf16(d_addr, adesc, bdesc, idesc, first ? 0u : 1u);
+            umma_bf16_warp(d_addr, adesc, bdesc, idesc, first ? 0u : 1u);
             first = 0;
           }
         }
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&acc_full[as]);
+        umma_commit_warp(&empty_bar[stage]);
+        umma_commit_warp(&acc_full[as]);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;

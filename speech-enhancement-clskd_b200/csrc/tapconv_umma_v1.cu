@@ -135,8 +135,8 @@ tapconv_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (all lanes run the loops, one elected lane issues) =====================
+    {
       // instruction descriptor: D=f32, A=B=bf16, K-major both, N, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
                              ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
@@ -158,16 +158,16 @@ tapconv_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           const uint64_t bdesc = make_smem_desc(b_addr, p.sbo, p.layout_type);
           for (int k = 0; k < ksteps; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
-            umma_bf16(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+            umma_bf16_warp(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                       (it | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+          umma_commit_warp(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tmem_full_bar[as]);
+        umma_commit_warp(&tmem_full_bar[as]);
       }
     }
   } else {

@@ -129,8 +129,8 @@ tapconv_wgrad_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && ntile_cta > 0) {
+    // ===================== MMA issuer (all lanes run the loops, one elected lane issues) =====================
+    if (ntile_cta > 0) {
       // D=f32, A=B=bf16, both operands MN-major (bits 15/16), N = n_tile, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -151,17 +151,17 @@ tapconv_wgrad_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
                                                       (8u * pitch_a) >> 4, p.layout_a);
             const uint64_t bdesc = make_smem_desc_lbo(b_addr + (uint32_t)k * 16u * pitch_b, p.b_sub_bytes >> 4,
                                                       (8u * pitch_b) >> 4, p.layout_b);
-            umma_bf16(tmem_base + (uint32_t)(g * p.n_tile), adesc, bdesc, idesc, (it | k) ? 1u : 0u);
+            umma_bf16_warp(tmem_base + (uint32_t)(g * p.n_tile), adesc, bdesc, idesc, (it | k) ? 1u : 0u);
           }
-          umma_commit(&a_empty[stage]);
+          umma_commit_warp(&a_empty[stage]);
           if (++stage == p.a_stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&b_empty[bs]);
+        umma_commit_warp(&b_empty[bs]);
       }
-      umma_commit(&tmem_full_bar);
+      umma_commit_warp(&tmem_full_bar);
     }
   } else if (ntile_cta > 0) {
     // ===================== epilogue (warps 2..5): TMEM -> fp32 reductions into dW =====================
