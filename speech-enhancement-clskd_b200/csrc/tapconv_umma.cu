@@ -174,14 +174,14 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   // persistent: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (n tile fastest, so
   // consecutive CTAs share the activation patch in L2)
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (all lanes run the loops, one elected lane issues) =====================
+    {
       if (p.resident) {
-        mbar_expect_tx(&bres_bar, (uint32_t)(p.ntaps * p.chunks_tot) * p.b_tx);
+        mbar_expect_tx_warp(&bres_bar, (uint32_t)(p.ntaps * p.chunks_tot) * p.b_tx);
         uint8_t* dst = ring + p.bres_off;
         for (int j = 0; j < p.ntaps; ++j)
           for (int ch = 0; ch < p.chunks_tot; ++ch)
-            tma_load_3d(dst + (size_t)(j * p.chunks_tot + ch) * p.b_bytes, &tmB, &bres_bar, ch * p.block_k, 0, p.tap_w[j]);
+            tma_load_3d_warp(dst + (size_t)(j * p.chunks_tot + ch) * p.b_bytes, &tmB, &bres_bar, ch * p.block_k, 0, p.tap_w[j]);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -199,15 +199,15 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           for (int g = 0; g < p.ngroups; ++g) {
             const int jb = p.grp_beg[g], je = p.grp_beg[g + 1];
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_expect_tx(&full_bar[stage], p.a_tx + (p.resident ? 0u : (uint32_t)(je - jb) * p.b_tx));
+            mbar_expect_tx_warp(&full_bar[stage], p.a_tx + (p.resident ? 0u : (uint32_t)(je - jb) * p.b_tx));
             uint8_t* a_dst = ring + (size_t)stage * p.stage_bytes;
             for (int bx = 0; bx < p.a_nbox; ++bx)
-              tma_load_5d(a_dst + (size_t)bx * p.a_box_bytes, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.grp_p[g],
+              tma_load_5d_warp(a_dst + (size_t)bx * p.a_box_bytes, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.grp_p[g],
                           f0 + p.grp_f[g], t0 + p.grp_t[g] + bx * p.a_box_t, b);
             if (!p.resident) {
               uint8_t* b_dst = a_dst + p.a_bytes;
               for (int j = jb; j < je; ++j)
-                tma_load_3d(b_dst + (size_t)(j - jb) * p.b_bytes, &tmB, &full_bar[stage], ch * p.block_k, n0, p.tap_w[j]);
+                tma_load_3d_warp(b_dst + (size_t)(j - jb) * p.b_bytes, &tmB, &full_bar[stage], ch * p.block_k, n0, p.tap_w[j]);
             }
             if (++stage == p.stages) {
               stage = 0;

@@ -110,8 +110,8 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0 && ntile_cta > 0) {
+    // ===================== TMA producer (all lanes run the loops, one elected lane issues) =====================
+    if (ntile_cta > 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < ntile_cta; ++it) {
@@ -122,7 +122,7 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         const int b = r / p.t_tiles;
         const int t0 = t_blk * p.t_tile, f0 = f_blk * 128;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], (uint32_t)(p.npar * nsub_a) * p.a_sub_bytes + (uint32_t)gcur * p.b_tx);
+        mbar_expect_tx_warp(&full_bar[stage], (uint32_t)(p.npar * nsub_a) * p.a_sub_bytes + (uint32_t)gcur * p.b_tx);
         uint8_t* a_dst = ring + (size_t)stage * p.stage_bytes;
         for (int par = 0; par < p.npar; ++par)
           for (int s = 0; s < nsub_a; ++s) {
@@ -130,12 +130,12 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
             const bool src0 = cc < p.c0p;        // channels beyond a source's real extent are zero-filled by TMA
             uint8_t* dst = a_dst + (size_t)par * p.a_tile_bytes + (size_t)s * p.a_sub_bytes;
             if (p.npar == 1)       // 4-d map at stride 1 (the 5-d form with a unit parity axis measured 20 % slower)
-              tma_load_4d(dst, src0 ? &tmX : &tmX1, &full_bar[stage], src0 ? cc : cc - p.c0p, f0 + p.a_fbox_start, t0, b);
+              tma_load_4d_warp(dst, src0 ? &tmX : &tmX1, &full_bar[stage], src0 ? cc : cc - p.c0p, f0 + p.a_fbox_start, t0, b);
             else
-              tma_load_5d(dst, src0 ? &tmX : &tmX1, &full_bar[stage], src0 ? cc : cc - p.c0p, par, f0 + p.a_fbox_start, t0, b);
+              tma_load_5d_warp(dst, src0 ? &tmX : &tmX1, &full_bar[stage], src0 ? cc : cc - p.c0p, par, f0 + p.a_fbox_start, t0, b);
           }
         for (int g = 0; g < gcur; ++g)
-          tma_load_4d(a_dst + b_off + (size_t)g * p.b_patch_bytes, &tmDY, &full_bar[stage], 0, f0 + p.b_fbox_start,
+          tma_load_4d_warp(a_dst + b_off + (size_t)g * p.b_patch_bytes, &tmDY, &full_bar[stage], 0, f0 + p.b_fbox_start,
                       t0 - p.dts[g0 + g], b);
         if (++stage == p.stages) {
           stage = 0;

@@ -101,8 +101,8 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0 && ntile_cta > 0) {
+    // ===================== TMA producer (all lanes run the loops, one elected lane issues) =====================
+    if (ntile_cta > 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < ntile_cta; ++it) {
@@ -114,20 +114,20 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
         const int t0 = t_blk * p.t_tile, f0 = f_blk * p.fo_tile;
         const int bs = it & 1;
         mbar_wait(&b_empty[bs], ((it >> 1) & 1) ^ 1u);
-        mbar_expect_tx(&b_full[bs], (uint32_t)nsub_b * p.b_sub_bytes);
+        mbar_expect_tx_warp(&b_full[bs], (uint32_t)nsub_b * p.b_sub_bytes);
         for (int s = 0; s < nsub_b; ++s)
-          tma_load_4d(b_buf + (size_t)bs * p.b_stage_bytes + (size_t)s * p.b_sub_bytes, &tmDY, &b_full[bs],
+          tma_load_4d_warp(b_buf + (size_t)bs * p.b_stage_bytes + (size_t)s * p.b_sub_bytes, &tmDY, &b_full[bs],
                       n0 + s * p.gw_b, f0, t0, b);
         for (int g = 0; g < gcur; ++g) {
           const int j = tap0 + g;
           if (g > 0 && p.tap_pg[j] == p.tap_pg[j - 1]) continue;        // same patch as the previous tap
           const int pg = p.tap_pg[j];
           mbar_wait(&a_empty[stage], phase ^ 1u);
-          mbar_expect_tx(&a_full[stage], (uint32_t)nsub_a * p.a_sub_bytes);
+          mbar_expect_tx_warp(&a_full[stage], (uint32_t)nsub_a * p.a_sub_bytes);
           for (int s = 0; s < nsub_a; ++s) {
             const int cc = cbase + s * p.gw_a;
             const bool src0 = cc < p.c0;
-            tma_load_5d(a_buf + (size_t)stage * p.a_stage_bytes + (size_t)s * p.a_sub_bytes, src0 ? &tmA0 : &tmA1,
+            tma_load_5d_warp(a_buf + (size_t)stage * p.a_stage_bytes + (size_t)s * p.a_sub_bytes, src0 ? &tmA0 : &tmA1,
                         &a_full[stage], src0 ? cc : cc - p.c0, p.pg_p[pg], f0 + p.pg_f[pg], t0 + p.pg_t[pg], b);
           }
           if (++stage == p.a_stages) {

@@ -93,8 +93,8 @@ tapconv_wgrad_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0 && ntile_cta > 0) {
+    // ===================== TMA producer (all lanes run the loops, one elected lane issues) =====================
+    if (ntile_cta > 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < ntile_cta; ++it) {
@@ -106,18 +106,18 @@ tapconv_wgrad_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
         const int t0 = t_blk * p.t_tile, f0 = f_blk * p.fo_tile;
         const int bs = it & 1;
         mbar_wait(&b_empty[bs], ((it >> 1) & 1) ^ 1u);
-        mbar_expect_tx(&b_full[bs], (uint32_t)nsub_b * p.b_sub_bytes);
+        mbar_expect_tx_warp(&b_full[bs], (uint32_t)nsub_b * p.b_sub_bytes);
         for (int s = 0; s < nsub_b; ++s)
-          tma_load_4d(b_buf + (size_t)bs * p.b_stage_bytes + (size_t)s * p.b_sub_bytes, &tmDY, &b_full[bs],
+          tma_load_4d_warp(b_buf + (size_t)bs * p.b_stage_bytes + (size_t)s * p.b_sub_bytes, &tmDY, &b_full[bs],
                       n0 + s * p.gw_b, f0, t0, b);
         for (int g = 0; g < gcur; ++g) {
           const int tap = tap0 + g;
           mbar_wait(&a_empty[stage], phase ^ 1u);
-          mbar_expect_tx(&a_full[stage], (uint32_t)nsub_a * p.a_sub_bytes);
+          mbar_expect_tx_warp(&a_full[stage], (uint32_t)nsub_a * p.a_sub_bytes);
           for (int s = 0; s < nsub_a; ++s) {
             const int cc = cbase + s * p.gw_a;
             const bool src0 = cc < p.c0p;      // channels beyond a source's real extent are zero-filled by TMA
-            tma_load_5d(a_buf + (size_t)stage * A_STAGE + (size_t)s * p.a_sub_bytes, src0 ? &tmA0 : &tmA1,
+            tma_load_5d_warp(a_buf + (size_t)stage * A_STAGE + (size_t)s * p.a_sub_bytes, src0 ? &tmA0 : &tmA1,
                         &a_full[stage], src0 ? cc : cc - p.c0p, p.tap_p[tap], f0 + p.tap_f[tap],
                         t0 + p.tap_t[tap], b);
           }
