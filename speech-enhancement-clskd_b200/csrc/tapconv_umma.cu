@@ -227,6 +227,7 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       uint32_t phase = 0;
       const int ksteps = p.block_k / 16;
       const uint32_t ring_addr = smem_u32(ring);
+      const uint64_t desc_fixed = ((uint64_t)((p.sbo & 0x3FFFu) | (1u << 14) | (p.layout_type << 29)) << 32) | (1u << 16);
       if (p.resident) {
         mbar_wait(&bres_bar, 0);
         fence_after();
@@ -243,14 +244,25 @@ tapconv_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_wait(&full_bar[stage], phase);
             fence_after();
             const uint32_t a_addr = ring_addr + (uint32_t)stage * p.stage_bytes;
-            for (int j = p.grp_beg[g]; j < p.grp_beg[g + 1]; ++j) {
+            // descriptors: hi word (SBO, version, layout) | lo word (start address >> 4, LBO = 1 (unused)); all offsets
+            // are multiples of 16 bytes below 2^18, so the 14-bit address field adds up exactly.  The next tap's patch
+            // offset is fetched BEFORE this tap's instructions are issued (the asm volatile MMAs are ordering points the
+            // compiler does not move loads across: a parameter-table round trip per tap otherwise sits in front of
+            // every tap's first instruction, and this warp's instruction stream paces narrow / short-K launches).
+            const int jb = p.grp_beg[g], je = p.grp_beg[g + 1];
+            const uint32_t a16 = a_addr >> 4;
+            uint32_t b16 = p.resident ? (ring_addr + p.bres_off + (uint32_t)(jb * p.chunks_tot + ch) * p.b_bytes) >> 4
+                                      : (a_addr + p.a_bytes) >> 4;
+            const uint32_t bstep16 = (p.resident ? (uint32_t)p.chunks_tot * p.b_bytes : p.b_bytes) >> 4;
+            uint32_t aoff_next = p.tap_aoff[jb] >> 4;
+            for (int j = jb; j < je; ++j) {
+              const uint32_t aoff = aoff_next;
+              if (j + 1 < je) aoff_next = p.tap_aoff[j + 1] >> 4;
               // the tap's A tile: the patch rows shifted by tap_aoff (matrix base offset stays 0: the swizzle
               // XOR is a function of the absolute shared-memory address)
-              const uint64_t adesc = make_smem_desc(a_addr + p.tap_aoff[j], p.sbo, p.layout_type);
-              const uint32_t b_addr = p.resident
-                                          ? ring_addr + p.bres_off + (uint32_t)(j * p.chunks_tot + ch) * p.b_bytes
-                                          : a_addr + p.a_bytes + (uint32_t)(j - p.grp_beg[g]) * p.b_bytes;
-              const uint64_t bdesc = make_smem_desc(b_addr, p.sbo, p.layout_type);
+              const uint64_t adesc = desc_fixed | (uint64_t)(a16 + aoff);
+              const uint64_t bdesc = desc_fixed | (uint64_t)b16;
+              b16 += bstep16;
               for (int k = 0; k < ksteps; ++k) {
                 // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
                 umma_bf16_warp(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first);
