@@ -223,7 +223,10 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
 const char* stack_unsupported(const ClskdTapConv* d, StackParams* out) {
   if (d->x_dtype != CLSKD_BF16 || d->y_dtype != CLSKD_BF16) return "x and dy must be bf16";
   if (d->sf != 1 && d->sf != 2) return "stride 1 or 2 only";
-  if (d->Ti != d->To || d->Fi != d->Fo * d->sf) return "time-preserving convolution with Fi = sf * Fo only";
+  // (To may differ from Ti - the decoder's sub-pixel phases produce Ti + 1 rows: the tiles walk the INPUT rows, and dY
+  // rows outside [0, To) are zero-filled by its tensor map)
+  if (d->Fi != d->Fo * d->sf) return "Fi = sf * Fo only";
+  if (d->To < d->Ti - 4 || d->To > d->Ti + 4) return "To too far from Ti";
   if (d->c0 % 8 || d->c1 % 8 || d->c0 < 8) return "channels must be multiples of 8";
   const int Np = (d->N + 15) & ~15;
   if (Np != 16 && Np != 32 && Np != 64) return "N must pad to 16, 32 or 64";
@@ -288,9 +291,9 @@ const char* stack_unsupported(const ClskdTapConv* d, StackParams* out) {
   };
   if (!chk(d->x0, d->x0_sB, d->x0_sT, d->x0_sF) || !chk(d->y, d->y_sB, d->y_sT, d->y_sF)) return "alignment";
   if (d->c1 && !chk(d->x1, d->x1_sB, d->x1_sT, d->x1_sF)) return "alignment";
-  if ((int64_t)d->B * d->To * d->Fo < 65536) return "too few rows";
+  if ((int64_t)d->B * d->Ti * d->Fo < 65536) return "too few rows";
   if (!get_encode()) return "cuTensorMapEncodeTiled unavailable";
-  p.B = d->B; p.T = d->To; p.F = d->Fo;
+  p.B = d->B; p.T = d->Ti; p.F = d->Fo;
   p.npar = sf;
   p.ndt = ndt; p.Np = Np; p.N = d->N; p.Ctot = d->c0 + d->c1;
   p.c0 = d->c0; p.c0p = (d->c0 + 15) & ~15; p.c1r = d->c1; p.Ctot_p = p.c0p + ((d->c1 + 15) & ~15);
@@ -310,7 +313,7 @@ const char* stack_unsupported(const ClskdTapConv* d, StackParams* out) {
     if (p.a_rows % 16) return "padded tile is not a multiple of 16 rows";
   }
   p.b_fbox_start = p.a_fbox_start - flmax;
-  p.t_tiles = cdiv(d->To, p.t_tile);
+  p.t_tiles = cdiv(d->Ti, p.t_tile);
   const int64_t nrt = (int64_t)d->B * p.t_tiles * p.f_tiles;
   if (nrt > 2147483647LL) return "too many row tiles";
   p.n_row_tiles = (int)nrt;

@@ -737,7 +737,8 @@ def _shift_tf(x, dt, df):
     (32, 32, 16, 64, 130, 8, (-1, 0), (-1, 0, 1)), (64, 64, 32, 32, 261, 8, (-1, 0), (0, 1)),
     (128, 128, 64, 16, 520, 8, (-1, 0), (-1, 0, 1)), (16, 16, 32, 128, 66, 8, (-1, 0), (-1, 0)), (24, 8, 16, 64, 130, 8, (0, 1), (-1, 0, 1)),
     (16, 0, 32, -64, 130, 8, (-1, 0), (-2, -1, 0, 1, 2)), (32, 0, 64, -32, 261, 8, (-1, 0), (-2, -1, 0, 1, 2)),
-    (64, 0, 16, -128, 66, 8, (-1, 0), (-2, -1, 0, 1, 2)), (8, 0, 24, -64, 131, 8, (-1, 0), (-2, -1, 0, 1, 2))])
+    (64, 0, 16, -128, 66, 8, (-1, 0), (-2, -1, 0, 1, 2)), (8, 0, 24, -64, 131, 8, (-1, 0), (-2, -1, 0, 1, 2)),
+    (32, 32, 16, 64, 1130, 8, (-1, 0), (-1, 0, 1)), (64, 64, 32, 32, 1261, 8, (-1, 0), (0, 1))])
 def test_tap_stacked_weight_gradient_vs_torch(cuda_dev, c0, c1, N, F, T, B, dts, dfs):
     """clskd_tapconv_wgrad_umma_stacked (frequency taps as sub-blocks of the MMA's N dimension, one patch row apart;
     one or two sources, 64 / 32 / 16-channel swizzle groups) against shifted einsums on the same bf16-representable
@@ -750,12 +751,18 @@ def test_tap_stacked_weight_gradient_vs_torch(cuda_dev, c0, c1, N, F, T, B, dts,
     if F < 0:                  # negative F: stride 2 along f (the encoder layers), -F output frequencies
         sf, F = 2, -F
     Fi = F * sf
+    To = T
+    if T >= 1000:              # T + 1000: one more output row than input rows (decoder sub-pixel phases)
+        T -= 1000
+        To = T + 1
     g = torch.Generator().manual_seed(c0 + N + F)
     taps = [(dt, df) for df in dfs for dt in dts]
     C = c0 + c1
     x = (0.5 * torch.randn(B, T, Fi, C, generator=g)).bfloat16()
-    dy = (0.5 * torch.randn(B, T, F, N, generator=g)).bfloat16()
+    dy = (0.5 * torch.randn(B, To, F, N, generator=g)).bfloat16()
     xd_, dyd_ = x.double(), dy.double()
+    if To != T:                # zero rows appended to x so that both have To rows
+        xd_ = torch.cat([xd_, torch.zeros(B, To - T, Fi, C, dtype=torch.float64)], 1)
     ref = torch.stack([torch.einsum("btfc,btfn->cn", _shift_tf(xd_, dt, df)[:, :, ::sf], dyd_) for dt, df in taps])     # [taps][C][N]
     x0d = x[..., :c0].contiguous().to(cuda_dev)
     x1d = x[..., c0:].contiguous().to(cuda_dev) if c1 else None
@@ -768,13 +775,13 @@ def test_tap_stacked_weight_gradient_vs_torch(cuda_dev, c0, c1, N, F, T, B, dts,
     if c1:
         d.x1_sB, d.x1_sT, d.x1_sF = T * Fi * c1, Fi * c1, c1
     d.c0, d.c1 = c0, c1
-    d.B, d.To, d.Fo, d.Ti, d.Fi = B, T, F, T, Fi
+    d.B, d.To, d.Fo, d.Ti, d.Fi = B, To, F, T, Fi
     d.sf, d.ntaps = sf, len(taps)
     for j, (dt, df) in enumerate(taps):
         d.dt[j], d.df[j] = dt, df
     d.bias, d.N = None, N
     d.y = dyd.data_ptr()
-    d.y_sB, d.y_sT, d.y_sF = T * F * N, F * N, N
+    d.y_sB, d.y_sT, d.y_sF = To * F * N, F * N, N
     d.x_dtype, d.y_dtype, d.accumulate = _lib.BF16, _lib.BF16, 0
     assert lib.clskd_tapconv_wgrad_umma_stacked_supported(ctypes.byref(d)) == 1
     outs = {}
