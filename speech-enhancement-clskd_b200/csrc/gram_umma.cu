@@ -65,15 +65,15 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {                  // all lanes run the loop, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nch; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], stage_bytes);
-        tma_load_2d(ring + (size_t)stage * stage_bytes, &tmZ, &full_bar[stage], (int)((c_beg + it) * 64), 0);
+        mbar_expect_tx_warp(&full_bar[stage], stage_bytes);
+        tma_load_2d_warp(ring + (size_t)stage * stage_bytes, &tmZ, &full_bar[stage], (int)((c_beg + it) * 64), 0);
         if (p.cross)
-          tma_load_2d(ring + (size_t)stage * stage_bytes + GF_STAGE_BYTES / 2, &tmZb, &full_bar[stage],
+          tma_load_2d_warp(ring + (size_t)stage * stage_bytes + GF_STAGE_BYTES / 2, &tmZb, &full_bar[stage],
                       (int)((c_beg + it) * 64), 0);
         if (++stage == nstages) {
           stage = 0;
@@ -209,16 +209,16 @@ gram_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {                  // all lanes run the loop, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nt; ++it) {
         const int64_t k0 = (t_beg + it) * 128;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], stage_bytes);
+        mbar_expect_tx_warp(&full_bar[stage], stage_bytes);
         uint8_t* dst = ring + (size_t)stage * stage_bytes;
-        tma_load_2d(dst, &tmZ, &full_bar[stage], (int)k0, 0);
-        tma_load_2d(dst + p.sub_bytes, &tmZ, &full_bar[stage], (int)(k0 + 64), 0);
+        tma_load_2d_warp(dst, &tmZ, &full_bar[stage], (int)k0, 0);
+        tma_load_2d_warp(dst + p.sub_bytes, &tmZ, &full_bar[stage], (int)(k0 + 64), 0);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;

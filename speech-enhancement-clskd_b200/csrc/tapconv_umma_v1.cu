@@ -103,8 +103,8 @@ tapconv_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   // persistent: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (n tile fastest, so
   // consecutive CTAs share the activation patch in L2)
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (all lanes run the loops, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -119,14 +119,14 @@ tapconv_umma_v1_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           const int tap = it / p.chunks_tot;
           const int ch = it - tap * p.chunks_tot;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+          mbar_expect_tx_warp(&full_bar[stage], p.tx_bytes);
           uint8_t* a_dst = ring + (size_t)stage * stage_bytes;
           uint8_t* b_dst = a_dst + p.a_bytes;
           const bool src0 = ch < p.chunks0;
           const int cc = (src0 ? ch : ch - p.chunks0) * p.block_k;
-          tma_load_5d(a_dst, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.tap_p[tap],
+          tma_load_5d_warp(a_dst, src0 ? &tmA0 : &tmA1, &full_bar[stage], cc, p.tap_p[tap],
                       f0 + p.tap_f[tap], t0 + p.tap_t[tap], b);
-          tma_load_3d(b_dst, &tmB, &full_bar[stage], ch * p.block_k, n0, tap);
+          tma_load_3d_warp(b_dst, &tmB, &full_bar[stage], ch * p.block_k, n0, tap);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
