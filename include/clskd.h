@@ -98,6 +98,10 @@ int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream);
  * 16 (the reference's quarter-width student) run with 16-wide TMA boxes over the 8 channels that exist. */
 int clskd_tapconv_fwd_umma(const ClskdTapConv* d, void* stream);
 int clskd_tapconv_umma_supported(const ClskdTapConv* d);
+/* padded channel extent of source 1 in the packed weight of clskd_tapconv_fwd_umma: ceil16(c1), and - when source 1 is
+ * narrower than the K chunk source 0 runs with (64 / 32 / 16: the largest that divides ceil16(c0)) - that chunk: the
+ * narrow source is one zero-filled TMA box, the contraction keeps source 0's chunk size */
+int clskd_tapconv_umma_c1p(int c0, int c1);
 /* Tuning overrides of the tcgen05 forward kernel for A/B measurements (tools/kbench.py); value 0 = automatic.
  *   key 0: operand-reuse mode (1 one TMA box per tap, 2 time-grouped patches, 3 full halo patch where possible)
  *   key 1: 1 = never keep the packed weight resident in shared memory
@@ -400,6 +404,33 @@ int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y, int dtype
                       int Fy, int C, const float* mean, const float* invstd, const float* gamma,
                       const float* beta, const float* watt, const float* logits, int training,
                       double* sums, double* dwatt, double* dbatt, void* dz1, void* dy, void* stream);
+
+/* One-pass backward of the middle stage with the BatchNorm backward of conv1 (framework.py:209, nn.BatchNorm2d after
+ * the 1x1 nn.Conv2d(in, mid, bias=False)) FOLDED into conv1's own gradients - the batch-mean terms of
+ *   dz1 = gi (dxp - mean dxp - xhat mean(dxp xhat)),   gi = gamma invstd,   xhat = (W1 x - mu) invstd
+ * are linear in x, so dz1 is never materialised and gout / z1 / y_prev are read once instead of twice:
+ *   clskd_abf_mid_bwd_fold: sums / dwatt / dbatt as clskd_abf_mid_bwd, dy, and dxp [B,T,F,C] = the gradient of the
+ *     BatchNorm OUTPUT (row-local).
+ *   clskd_abf_fold_dgrad: packed weight weff bf16 [Cin][C + c1p] and bias fp32 [Cin] of the two-source 1x1 contraction
+ *     dx = [dxp | x] weff^T + bias (clskd_tapconv_fwd_umma with x0 = dxp, x1 = x, c1p = clskd_tapconv_umma_c1p(C, Cin));
+ *     w1: fp32 [C][Cin]; sums from the call above; M = B*T*F rows; training = 0: running statistics (no mean terms).
+ *   clskd_abf_fold_dw1: dW1 fp32 [C][Cin] from P = x^T dxp (fp32 [Cin][C], clskd_tapconv_wgrad* on dxp),
+ *     G = x^T x (fp64 [Cin][Cin]) and sx = column sums of x (fp64 [Cin]) - both from clskd_colgram;
+ *     G and sx may be NULL when training = 0.
+ *   clskd_colgram: G and sx of a dense bf16 map x [M][C], C in {16, 32, 64, 128}, in one pass over x (mma.sync on
+ *     ldmatrix.trans tiles; outputs zeroed by the call). */
+int clskd_abf_mid_bwd_fold(const void* gout, const void* z1, const void* y, int dtype, int B, int T, int F,
+                           int Fy, int C, const float* mean, const float* invstd, const float* gamma,
+                           const float* beta, const float* watt, const float* logits, double* sums,
+                           double* dwatt, double* dbatt, void* dxp, void* dy, void* stream);
+int clskd_abf_fold_dgrad(const float* w1, const float* gamma, const float* mean, const float* invstd,
+                         const double* sums, int64_t M, int training, int C, int Cin, int c1p, void* weff,
+                         float* bias, void* stream);
+int clskd_colgram_supported(int dtype, int C);
+int clskd_colgram(const void* x, int dtype, int64_t M, int C, double* G, double* sx, void* stream);
+int clskd_abf_fold_dw1(const float* P, const double* G, const double* sx, const float* w1, const float* gamma,
+                       const float* mean, const float* invstd, const double* sums, int64_t M, int training,
+                       int C, int Cin, float* dw1, void* stream);
 
 /* The same block when the 1x1 conv in front of it has only TWO input channels (the mask-level map
  * of the decoder side, framework.py:209 with in_channel = 2): z1 = W1 x is recomputed per row from

@@ -280,6 +280,16 @@ class ABF(nn.Module):
         C, Fy = y.shape[1], y.shape[2]
         return C == c1.out_channels and bool(ops._lib.load().clskd_abf_mid_supported(B, T, F, Fy, C))
 
+    def _fold_ok(self, x, y, shape):
+        """conv1 + middle stage as ops.AbfFoldFn (one-pass backward): tensor-core policy, bf16 maps, no conv bias,
+        affine BatchNorm, training graph"""
+        c1, bn = self.conv1[0], self.conv1[1]
+        if not (self.fused and c1.bias is None and bn.weight is not None and torch.is_grad_enabled()
+                and x.shape[2] == shape and y.shape[3] == x.shape[3] and y.shape[1] == c1.out_channels
+                and c1.kernel_size == (1, 1)):
+            return False
+        return ops.abf_fold_supported(x.permute(0, 3, 2, 1), y.permute(0, 3, 2, 1), c1.weight)
+
     def forward(self, x, y=None, shape=None, out_shape=None, feature_type=None):
         if self.att_conv is not None and self._rank2_ok(x, y, shape):
             # 2-channel input: z1 = W1 x never touches HBM (recomputed inside the fused mid-stage kernels)
@@ -293,6 +303,18 @@ class ABF(nn.Module):
                                       bn.running_mean if bn.track_running_stats else None,
                                       bn.running_var if bn.track_running_stats else None,
                                       not use_running, bn.momentum, bn.eps)
+        elif self.att_conv is not None and self._fold_ok(x, y, shape):
+            # conv1 + BatchNorm + middle stage as one node; BatchNorm backward folded into conv1's gradients
+            c1, bn, att = self.conv1[0], self.conv1[1], self.att_conv[0]
+            xs = to_phys(x)
+            yp = to_phys(y, xs.dtype, need_dense=True)
+            if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+            use_running = (not bn.training) and bn.track_running_stats
+            xp = ops.AbfFoldFn.apply(c1.plan(None), xs, yp, c1.weight, bn.weight, bn.bias, att.weight, att.bias,
+                                     bn.running_mean if bn.track_running_stats else None,
+                                     bn.running_var if bn.track_running_stats else None,
+                                     not use_running, bn.momentum, bn.eps)
         elif self.att_conv is not None:
             bn1 = self.conv1[1]
             ep = None

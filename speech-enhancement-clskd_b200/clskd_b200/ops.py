@@ -5,6 +5,7 @@ Internal ("physical") activation layout is channels-last [B, T, F, C]; the refer
 NCHW tensors [B, C, F, T] are exposed as `.permute(0, 3, 2, 1)` views of it (no copies).
 """
 import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -31,6 +32,8 @@ class _Policy:
         self.abf_rank2 = True       # ABF level whose 1x1 conv has 2 input channels: z1 recomputed in the mid kernels
         self.fuse_epilogue = True   # BatchNorm statistics / folded eval BatchNorm + PReLU in the tcgen05 conv epilogue
         self.abf_xs2 = True      # rank-2 folded kernels for the 2-channel ABF level (clskd_abf_xs2_*)
+        # ABF conv1 + middle stage as one node, BatchNorm backward folded into conv1's gradients (CLSKD_ABF_FOLD=0: A/B)
+        self.abf_fold = os.environ.get("CLSKD_ABF_FOLD", "1") != "0"
         self.split_gemm = True   # fp32-input GEMMs (STFT/iSTFT/LSTM projections) as split-bf16 tcgen05 contractions
         self.narrow = "auto"     # tap-in-channel decomposition of narrow convs: "auto" (tensor-core policy) / "always"
 
@@ -261,16 +264,17 @@ class Launch:
             self._t_nc = torch.from_numpy(_pairs(self.blk.transpose(0, 2, 1).reshape(-1))).to(self.device)
         return self._t_nc
 
-    def t_nc_padded(self, c0, c1):
+    def t_nc_padded(self, c0, c1, c1p=None):
         """[tap][Np][c0p + c1p] table for the tcgen05 kernel when a channel count is a multiple of 8 but not of 16
         (quarter-width student): each source's K range and N are padded to 16 with skipped (= zero) entries; the
         kernel's TMA boxes are 16 channels wide over the 8 that exist (clskd_tapconv_fwd_umma)."""
-        key = ("t_nc_pad", c0, c1)
+        p16 = lambda v: (v + 15) // 16 * 16
+        c1p = p16(c1) if c1p is None else c1p      # clskd_tapconv_umma_c1p: a narrow second source fills one K chunk
+        key = ("t_nc_pad", c0, c1, c1p)
         if key not in self._cache:
-            p16 = lambda v: (v + 15) // 16 * 16
             nt, K, N = self.blk.shape
             assert K == c0 + c1
-            out = np.full((nt, p16(c0) + p16(c1), p16(N)), -1, dtype=np.int64)
+            out = np.full((nt, p16(c0) + c1p, p16(N)), -1, dtype=np.int64)
             out[:, :c0, :N] = self.blk[:, :c0, :]
             if c1:
                 out[:, p16(c0):p16(c0) + c1, :N] = self.blk[:, c0:, :]
@@ -707,8 +711,9 @@ def run_tapconv(x0, x1, c0, c1, B, To, Fo, Ti, Fi, l: Launch, a, b, bias, y, x0_
     if ep is None and policy.use_umma and policy.split_gemm and _split_gemm(d, l, a, b, bias, x0, y):
         return y
     if allow_umma and _umma_ok(d):
-        if c0 % 16 or c1 % 16 or l.N % 16:
-            w = packed_weights(l._cache, "nc_pad%d_%d" % (c0, c1), lambda: l.t_nc_padded(c0, c1), a, b, torch.bfloat16)
+        c1p = int(_lib.load().clskd_tapconv_umma_c1p(c0, c1)) if c1 else 0
+        if c0 % 16 or c1p != c1 or l.N % 16:
+            w = packed_weights(l._cache, "nc_pad%d_%d" % (c0, c1), lambda: l.t_nc_padded(c0, c1, c1p), a, b, torch.bfloat16)
         else:
             w = packed_weights(l._cache, "nc", lambda: l.t_nc, a, b, torch.bfloat16)
         d.w = w.data_ptr()
@@ -1306,6 +1311,36 @@ class AttBlendFn(torch.autograd.Function):
         return dx, dy, dz
 
 
+def _abf_mid_forward(z1, y_prev, gamma, beta, watt, batt, running_mean, running_var, training, momentum, eps, pre_stats):
+    """BatchNorm statistics of z1 (batch or running) + clskd_abf_mid_fwd -> (xb, stats [2,C] = mean / invstd, logits,
+    use_batch)"""
+    B, T, F, C = z1.shape
+    Fy = y_prev.shape[2]
+    M = B * T * F
+    dev = z1.device
+    stats = torch.empty(2, C, dtype=torch.float32, device=dev)
+    mean, invstd = stats[0], stats[1]
+    use_batch = training or running_mean is None
+    if use_batch:
+        s, ss = (pre_stats[0], pre_stats[1]) if pre_stats is not None else colstats(z1.view(M, C))
+        call("clskd_bn_finalize", s.data_ptr(), ss.data_ptr(), M, C, float(eps),
+             float(momentum if momentum is not None else 0.0), mean.data_ptr(), invstd.data_ptr(),
+             running_mean.data_ptr() if (running_mean is not None and training) else None,
+             running_var.data_ptr() if (running_var is not None and training) else None, _stream())
+    else:
+        call("clskd_bn_eval_stats", running_mean.data_ptr(), running_var.data_ptr(), C, float(eps),
+             mean.data_ptr(), invstd.data_ptr(), _stream())
+    g32, b32 = _f32c(gamma), _f32c(beta)
+    w32 = _f32c(watt).view(2, 2 * C)
+    ba32 = _f32c(batt) if batt is not None else None
+    xb = torch.empty_like(z1)
+    logits = torch.empty((B, T, F, 2), dtype=torch.float32, device=dev)
+    call("clskd_abf_mid_fwd", z1.data_ptr(), y_prev.data_ptr(), _tag(z1.dtype), B, T, F, Fy, C, mean.data_ptr(),
+         invstd.data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(), _ptr(ba32), xb.data_ptr(),
+         logits.data_ptr(), _stream())
+    return xb, stats, logits, use_batch
+
+
 class AbfMidFn(torch.autograd.Function):
     """Fused ABF middle stage: BatchNorm(z1) -> nearest-resize(y_prev) -> 2-logit attention conv ->
     sigmoid blend, one pass forward and two passes backward (clskd_abf_mid_* in clskd.h).
@@ -1314,30 +1349,8 @@ class AbfMidFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z1, y_prev, gamma, beta, watt, batt, running_mean, running_var, training, momentum, eps,
                 pre_stats=None):
-        B, T, F, C = z1.shape
-        Fy = y_prev.shape[2]
-        M = B * T * F
-        dev = z1.device
-        stats = torch.empty(2, C, dtype=torch.float32, device=dev)
-        mean, invstd = stats[0], stats[1]
-        use_batch = training or running_mean is None
-        if use_batch:
-            s, ss = (pre_stats[0], pre_stats[1]) if pre_stats is not None else colstats(z1.view(M, C))
-            call("clskd_bn_finalize", s.data_ptr(), ss.data_ptr(), M, C, float(eps),
-                 float(momentum if momentum is not None else 0.0), mean.data_ptr(), invstd.data_ptr(),
-                 running_mean.data_ptr() if (running_mean is not None and training) else None,
-                 running_var.data_ptr() if (running_var is not None and training) else None, _stream())
-        else:
-            call("clskd_bn_eval_stats", running_mean.data_ptr(), running_var.data_ptr(), C, float(eps),
-                 mean.data_ptr(), invstd.data_ptr(), _stream())
-        g32, b32 = _f32c(gamma), _f32c(beta)
-        w32 = _f32c(watt).view(2, 2 * C)
-        ba32 = _f32c(batt) if batt is not None else None
-        xb = torch.empty_like(z1)
-        logits = torch.empty((B, T, F, 2), dtype=torch.float32, device=dev)
-        call("clskd_abf_mid_fwd", z1.data_ptr(), y_prev.data_ptr(), _tag(z1.dtype), B, T, F, Fy, C, mean.data_ptr(),
-             invstd.data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(), _ptr(ba32), xb.data_ptr(),
-             logits.data_ptr(), _stream())
+        xb, stats, logits, use_batch = _abf_mid_forward(z1, y_prev, gamma, beta, watt, batt, running_mean, running_var,
+                                                        training, momentum, eps, pre_stats)
         ctx.save_for_backward(z1, y_prev, stats, gamma, beta, watt, logits)
         ctx.use_batch = use_batch
         ctx.has_bias = batt is not None
@@ -1365,6 +1378,122 @@ class AbfMidFn(torch.autograd.Function):
         dw = a32[2 * C:6 * C].view_as(watt)
         db = a32[6 * C:] if ctx.has_bias else None
         return dz1, dy, dgamma, dbeta, dw, db, None, None, None, None, None, None
+
+
+_gram_launches = {}
+
+
+def _pointwise_launch(K, N, device):
+    """descriptor-only Launch of a 1x1 contraction [K -> N] (weight-gradient launches on ad-hoc operands)"""
+    key = (K, N, device)
+    if key not in _gram_launches:
+        _gram_launches[key] = Launch(dt=[0], df=[0], K=K, N=N, device=device)
+    return _gram_launches[key]
+
+
+def abf_fold_supported(x, y_prev, w1):
+    """conv1 + middle stage as one autograd node with the BatchNorm backward folded into conv1's gradients
+    (AbfFoldFn): tensor-core policy, bf16 maps, 16 | Cin, 16 | C"""
+    if not (policy.use_umma and policy.abf_fold and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    C, Cin = w1.shape[0], w1.shape[1]
+    if Cin % 16 or C % 16 or Cin > 256 or C > 256 or x.shape[3] != Cin:
+        return False
+    B, T, F, _ = x.shape
+    if y_prev.shape[0] != B or y_prev.shape[1] != T or y_prev.shape[3] != C:
+        return False
+    lib = _lib.load()
+    return bool(lib.clskd_colgram_supported(_tag(x.dtype), Cin)) and bool(lib.clskd_abf_mid_supported(B, T, F, y_prev.shape[2], C))
+
+
+class AbfFoldFn(torch.autograd.Function):
+    """ABF conv1 (1x1, no bias) + BatchNorm + fused middle stage as ONE autograd node (framework.py:209-219).
+    Forward: the usual launches (tcgen05 1x1 conv with the batch statistics in its epilogue, clskd_abf_mid_fwd).
+    Backward: ONE pass over gout / z1 / y_prev (clskd_abf_mid_bwd_fold: batch sums, dW_att, dy_prev and dxp = the
+    gradient of the BatchNorm output); the BatchNorm-backward affine is folded into conv1's gradients
+    (clskd_abf_fold_dgrad / _dw1 in clskd.h): dx is one two-source 1x1 contraction over [dxp | x], dW1 follows from
+    x^T dxp, x^T x and the column sums of x (clskd_colgram: one pass over x).  dz1 is never written and the second pass over the three big maps of
+    AbfMidFn.backward is gone.
+    x: [B,T,F,Cin] bf16; y_prev: dense [B,T,Fy,C]; w1: conv1 weight [C,Cin,1,1]; returns xb [B,T,F,C]."""
+
+    @staticmethod
+    def forward(ctx, plan, x, y_prev, w1, gamma, beta, watt, batt, running_mean, running_var, training, momentum, eps):
+        if not (_chan_ok(x) and x.is_contiguous()):
+            x = strided_copy(x)
+        C = w1.shape[0]
+        use_batch = training or running_mean is None
+        ep = None
+        if policy.fuse_epilogue and use_batch:
+            ep = Epilogue(stats=torch.zeros(2, C, dtype=torch.float64, device=x.device))
+            request_epilogue(ep)
+        try:
+            z1 = TapConvFn.apply(plan, x, None, w1, None, None, None, x.dtype)      # (no graph inside forward)
+        finally:
+            request_epilogue(None)
+        pre = ep.stats if (ep is not None and ep.fused) else None
+        xb, stats, logits, use_batch = _abf_mid_forward(z1, y_prev, gamma, beta, watt, batt, running_mean, running_var,
+                                                        training, momentum, eps, pre)
+        ctx.save_for_backward(x, z1, y_prev, stats, gamma, beta, watt, logits, w1)
+        ctx.use_batch = use_batch
+        ctx.has_bias = batt is not None
+        ctx.plan = plan
+        return xb
+
+    @staticmethod
+    def backward(ctx, g):
+        global umma_launches
+        x, z1, y_prev, stats, gamma, beta, watt, logits, w1 = ctx.saved_tensors
+        B, T, F, C = z1.shape
+        Cin = x.shape[3]
+        Fy = y_prev.shape[2]
+        M = B * T * F
+        dev = z1.device
+        st = _stream()
+        g = dense(g, z1.dtype)
+        acc = torch.empty(2 * C + 4 * C + 2, dtype=torch.float64, device=dev)
+        sums, dwatt, dbatt = acc[:2 * C], acc[2 * C:6 * C], acc[6 * C:]
+        dxp = torch.empty_like(z1)
+        dy = torch.empty_like(y_prev)
+        g32, b32 = _f32c(gamma), _f32c(beta)
+        w32 = _f32c(watt).view(2, 2 * C)
+        w1f = _f32c(w1).view(C, Cin)
+        mean, invstd = stats[0], stats[1]
+        call("clskd_abf_mid_bwd_fold", g.data_ptr(), z1.data_ptr(), y_prev.data_ptr(), _tag(z1.dtype), B, T, F, Fy, C,
+             mean.data_ptr(), invstd.data_ptr(), g32.data_ptr(), b32.data_ptr(), w32.data_ptr(), logits.data_ptr(),
+             sums.data_ptr(), dwatt.data_ptr(), dbatt.data_ptr(), dxp.data_ptr(), dy.data_ptr(), st)
+        training = 1 if ctx.use_batch else 0
+        need = ctx.needs_input_grad
+        dx = dw1 = None
+        if need[1]:
+            c1p = int(_lib.load().clskd_tapconv_umma_c1p(C, Cin))
+            weff = torch.empty((Cin, C + c1p), dtype=torch.bfloat16, device=dev)
+            bias = torch.empty(Cin, dtype=torch.float32, device=dev)
+            call("clskd_abf_fold_dgrad", w1f.data_ptr(), g32.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                 sums.data_ptr(), M, training, C, Cin, c1p, weff.data_ptr(), bias.data_ptr(), st)
+            dx = torch.empty_like(x)
+            d = TapConv()
+            l = _pointwise_launch(C + Cin, Cin, dev)
+            _fill_desc(d, dxp, 0, _view_of(dxp)[1], x, 0, _view_of(x)[1], C, Cin, B, T, F, T, F, l, weff, bias, Cin,
+                       dx, 0, _view_of(dx)[1])
+            call("clskd_tapconv_fwd_umma", ctypes.byref(d), st)
+            umma_launches += 1
+        if need[3]:
+            P = torch.empty(Cin * C, dtype=torch.float32, device=dev)
+            run_wgrad(x, None, Cin, 0, B, T, F, T, F, _pointwise_launch(Cin, C, dev), dxp, P)
+            Gm = sx = None
+            if training:
+                gs = torch.empty(Cin * Cin + Cin, dtype=torch.float64, device=dev)
+                Gm, sx = gs[:Cin * Cin], gs[Cin * Cin:]
+                call("clskd_colgram", x.data_ptr(), _tag(x.dtype), M, Cin, Gm.data_ptr(), sx.data_ptr(), st)
+            dw1 = torch.empty((C, Cin), dtype=torch.float32, device=dev)
+            call("clskd_abf_fold_dw1", P.data_ptr(), _ptr(Gm), _ptr(sx), w1f.data_ptr(), g32.data_ptr(), mean.data_ptr(),
+                 invstd.data_ptr(), sums.data_ptr(), M, training, C, Cin, dw1.data_ptr(), st)
+            dw1 = dw1.view_as(w1)
+        a32 = f64_to_f32(acc)
+        dbeta, dgamma = a32[:C].view_as(beta), a32[C:2 * C].view_as(gamma)
+        dw = a32[2 * C:6 * C].view_as(watt)
+        db = a32[6 * C:] if ctx.has_bias else None
+        return None, dx, dy, dw1, dgamma, dbeta, dw, db, None, None, None, None, None
 
 
 class AbfMidXsFn(torch.autograd.Function):

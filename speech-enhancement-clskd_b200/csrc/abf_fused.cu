@@ -294,10 +294,18 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
 
 // MODE 0: statistics pass (sums for BatchNorm backward, dW_att, db_att)
 // MODE 1: apply pass (dz1, dy_prev)
+// MODE 2: ONE pass (clskd_abf_mid_bwd_fold): the statistics of MODE 0 and, to `dz1`, the gradient dxp of the BatchNorm
+//         OUTPUT (row-local), plus dy_prev.  The BatchNorm-backward affine dz1 = gi (dxp - k1 - k2 xhat) is then folded
+//         into the weights of conv1's data / weight gradients (abf_fold_* kernels below): dz1 is never materialised and
+//         z1 / gout / y_prev are read once instead of twice.
 // A lane group always processes the PAIR of rows (f = 2j, 2j+1) that share one y_prev row when
 // Fy = F/2 (so dy_prev is written once, without atomics); with Fy = F the pair is two plain rows.
-template <typename T, int MODE, bool XS>
-__global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ z1,
+// NT threads per CTA: 256 (two CTAs per SM, 128 registers) for the two-pass kernels; the one-pass kernel (MODE 2) keeps the
+// accumulators of MODE 0 AND the output rows of MODE 1 live - at 128 registers it spilled inside the row loop and its
+// global stores evicted the spill lines from L1 (1.83 ms at F = 128 where MODE 0 + MODE 1 took 2.17): it runs as three
+// 128-thread CTAs per SM (168 registers)
+template <typename T, int MODE, bool XS, int NT = AT>
+__global__ void __launch_bounds__(NT, NT == AT ? 2 : 3) abf_mid_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ z1,
                                                             const T* __restrict__ y, AbfGeom g,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -312,10 +320,10 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
   float* red = cs + NCONST * C;
   constexpr int NCP = Vec8<T>::NCP;
   constexpr int NSLOT = 6 * NCP + 1;                     // g[2], z1[2], y[2] vectors + one slot for both logit pairs
-  constexpr int SLOT_STRIDE = AT * 16;
+  constexpr int SLOT_STRIDE = NT * 16;
   uint8_t* pipe = smem_raw + ((sizeof(float) * ((NCONST + 6) * C + 2) + 15) & ~(size_t)15) + threadIdx.x * 16;
-  if (MODE == 0 || XS)
-    for (int i = threadIdx.x; i < 6 * C + 2; i += AT) red[i] = 0.f;
+  if (MODE != 1 || XS)
+    for (int i = threadIdx.x; i < 6 * C + 2; i += NT) red[i] = 0.f;
   stage_consts(cs, C, mean, invstd, gamma, beta, watt, MODE == 1 ? sums : nullptr, 1.0 / (double)g.M, training,
                XS ? w1 : nullptr);
   // XS apply pass: dW1[c][k] partial sums of this thread's 8 channels
@@ -330,8 +338,8 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
   for (int e = 0; e < 8; ++e) a_s0[e] = a_s1[e] = a_wx0[e] = a_wx1[e] = a_wy0[e] = a_wy1[e] = 0.f;
 
   const int64_t pairs = g.M >> 1;           // M is even (F is even)
-  const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * NT + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * NT) >> 5;
   const int64_t stride = nwarps * rpw;
   const int cs_ = g.cshift;
   const int coff = cg * 8;
@@ -451,15 +459,17 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
       dl0[q] = t0 * s0[q] * (1.f - s0[q]);
       dl1[q] = t1 * s1[q] * (1.f - s1[q]);
     }
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 2) {
       float wx0[8], wx1[8];
       ldc(cs, K_WX0, C, cg, wx0);
       ldc(cs, K_WX1, C, cg, wx1);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
+        float dx8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float dxp = gv[q][e] * s0[q] + wx0[e] * dl0[q] + wx1[e] * dl1[q];
+          dx8[e] = dxp;
           a_s0[e] += dxp;
           a_s1[e] = fmaf(dxp, xv[q][e], a_s1[e]);
           a_wx0[e] = fmaf(dl0[q], xp[q][e], a_wx0[e]);
@@ -470,6 +480,27 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
         if (cg == 0) {
           a_b0 += dl0[q];
           a_b1 += dl1[q];
+        }
+        if (MODE == 2 && live) st8(dz1 + ((m0 + q) << cs_) + coff, dx8);       // dxp (gradient of the BatchNorm output)
+      }
+      if (MODE == 2) {
+        float wy0[8], wy1[8];
+        ldc(cs, K_WY0, C, cg, wy0);
+        ldc(cs, K_WY1, C, cg, wy1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) yv[q][e] = gv[q][e] * s1[q] + wy0[e] * dl0[q] + wy1[e] * dl1[q];   // dyv
+        if (live) {
+          T* yo = dy + (yr0 << cs_) + coff;
+          if (y_full) {
+            st8(yo, yv[0]);
+            st8(yo + ((int64_t)1 << cs_), yv[1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) yv[0][e] += yv[1][e];
+            st8(yo, yv[0]);
+          }
         }
       }
     } else {
@@ -551,12 +582,12 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
       atomicAdd(&red[C + c], a_w11[e]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += AT) {
+    for (int i = threadIdx.x; i < C; i += NT) {
       atomicAdd(dw1 + 2 * i, (double)red[i]);
       atomicAdd(dw1 + 2 * i + 1, (double)red[C + i]);
     }
   }
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 2) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = cg * 8 + e;
@@ -572,7 +603,7 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_bwd_kernel(const T* __restrict_
       atomicAdd(&red[6 * C + 1], a_b1);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += AT) {
+    for (int i = threadIdx.x; i < C; i += NT) {
       atomicAdd(sums + i, (double)red[i]);
       // red[C + i] is this CTA's sum dxp z1 (raw z1): -> sum dxp xhat
       atomicAdd(sums + C + i, (double)invstd[i] * ((double)red[C + i] - (double)mean[i] * (double)red[i]));
@@ -1018,6 +1049,78 @@ __global__ void abf_xs2_dx_kernel(const float4* __restrict__ rows, const T* __re
   }
 }
 
+// =====================================================================================================
+// BatchNorm backward of the ABF's conv1 (framework.py:209) folded into conv1's own gradients.  With z1 = W1 x (1x1 conv,
+// no bias), xhat = (z1 - mu) is, gi = gamma is, k1 = mean dxp, k2 = mean dxp xhat (batch statistics; 0 in eval mode):
+//     dz1 = gi (dxp - k1 - k2 xhat)
+//     dx  = dz1 W1   = dxp (diag(gi) W1)  -  x (W1^T diag(gi k2 is) W1)  +  sum_c (gi (k2 is mu - k1))_c W1[c,:]
+//     dW1 = dz1^T x  = diag(gi) ( dxp^T x  -  k1 (sum x)^T  -  diag(k2 is) ( W1 (x^T x) - mu (sum x)^T ) )
+// so the data gradient is ONE two-source 1x1 contraction [dxp | x] with the weights below (+ a bias), and the weight
+// gradient needs dxp^T x (the usual weight-gradient launch on dxp), the Cin x Cin Gram matrix of x and its column sums.
+// =====================================================================================================
+// weff: bf16 [Cin][C + c1p] (row n = output channel of the data gradient; columns: dxp channels, then x channels,
+// zero padded to c1p);  bias: fp32 [Cin]
+__global__ void abf_fold_dgrad_kernel(const float* __restrict__ w1, const float* __restrict__ gamma,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                      const double* __restrict__ sums, double invM, int training, int C, int Cin, int c1p,
+                                      __nv_bfloat16* __restrict__ weff, float* __restrict__ bias) {
+  __shared__ float s_gi[256], s_q[256], s_r[256], s_wn[256];
+  __shared__ float s_red[8];
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float gi = (gamma ? gamma[c] : 1.f) * invstd[c];
+    const float k1 = training ? (float)(sums[c] * invM) : 0.f;
+    const float k2 = training ? (float)(sums[C + c] * invM) : 0.f;
+    s_gi[c] = gi;
+    s_q[c] = gi * k2 * invstd[c];
+    s_r[c] = gi * (k2 * invstd[c] * mean[c] - k1);
+    s_wn[c] = w1[(size_t)c * Cin + n];
+  }
+  __syncthreads();
+  const int Kt = C + c1p;
+  for (int k = threadIdx.x; k < Kt; k += blockDim.x) {
+    float v = 0.f;
+    if (k < C) v = s_gi[k] * s_wn[k];
+    else if (k - C < Cin) {
+      const int j = k - C;
+      float a = 0.f;
+      for (int c = 0; c < C; ++c) a = fmaf(s_wn[c] * s_q[c], w1[(size_t)c * Cin + j], a);
+      v = -a;
+    }
+    weff[(size_t)n * Kt + k] = __float2bfloat16(v);
+  }
+  float b = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) b = fmaf(s_r[c], s_wn[c], b);
+  for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+    bias[n] = t;
+  }
+}
+
+// P: fp32 [Cin][C] = x^T dxp;  G: fp64 [Cin][Cin] = x^T x;  sx: fp64 [Cin] column sums of x;  dw1: fp32 [C][Cin]
+__global__ void abf_fold_dw1_kernel(const float* __restrict__ P, const double* __restrict__ G, const double* __restrict__ sx,
+                                    const float* __restrict__ w1, const float* __restrict__ gamma,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const double* __restrict__ sums, double invM, int training, int C, int Cin,
+                                    float* __restrict__ dw1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * Cin) return;
+  const int c = i / Cin, k = i - c * Cin;
+  const double gi = (double)(gamma ? gamma[c] : 1.f) * (double)invstd[c];
+  double v = (double)P[(size_t)k * C + c];
+  if (training) {
+    const double k1 = sums[c] * invM, k2 = sums[C + c] * invM;
+    double t = 0.0;
+    for (int j = 0; j < Cin; ++j) t += (double)w1[(size_t)c * Cin + j] * G[(size_t)j * Cin + k];
+    v -= k1 * sx[k] + k2 * (double)invstd[c] * (t - (double)mean[c] * sx[k]);
+  }
+  dw1[i] = (float)(gi * v);
+}
+
 const char* abf_unsupported(int B, int T, int F, int Fy, int C, const void* a, const void* b, const void* c) {
   if (C % 8 || C > 256 || C < 8) return "C must be a multiple of 8 in [8,256]";
   const int tpr = C / 8;
@@ -1102,7 +1205,7 @@ static int abf_bwd_launch(const char* who, bool xs, const void* gout, const void
                           int T, int F, int Fy, int C, const float* mean, const float* invstd, const float* gamma,
                           const float* beta, const float* watt, const float* logits, int training, double* sums,
                           double* dwatt, double* dbatt, void* dz1, void* dy, const float* w1, double* dw1,
-                          void* stream) {
+                          void* stream, bool fold = false) {
   CLSKD_CHECK_ARG(gout && z1 && y && mean && invstd && watt && logits && sums && dwatt && dbatt && dz1 && dy &&
                       (!xs || (w1 && dw1)), "%s: null pointer", who);
   if (const char* why = abf_unsupported(B, T, F, Fy, C, gout, xs ? gout : z1, xs ? nullptr : dz1)) {
@@ -1133,12 +1236,27 @@ static int abf_bwd_launch(const char* who, bool xs, const void* gout, const void
     ABF_ATTR(float, 0, false); ABF_ATTR(float, 1, false); ABF_ATTR(__nv_bfloat16, 0, false); ABF_ATTR(__nv_bfloat16, 1, false);
     ABF_ATTR(float, 0, true); ABF_ATTR(float, 1, true); ABF_ATTR(__nv_bfloat16, 0, true); ABF_ATTR(__nv_bfloat16, 1, true);
 #undef ABF_ATTR
+    cudaFuncSetAttribute(abf_mid_bwd_kernel<float, 2, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(abf_mid_bwd_kernel<__nv_bfloat16, 2, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
 #define ABF_BWD(MD, XX, DZ, DY)                                                                                     \
   CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, MD, XX><<<grid, AT, sh, st>>>(                            \
                                       (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta,   \
                                       watt, logits, sums, dwatt, dbatt, training, (TT*)(DZ), (TT*)(DY), w1, dw1)))
+  if (fold) {
+    // one pass: statistics + dxp + dy_prev; 128-thread CTAs, three per SM (one wave)
+    constexpr int FT = 128;
+    int64_t blocks = ((pairs + pairs_per_warp - 1) / pairs_per_warp / 4 + FT / 32 - 1) / (FT / 32);
+    const int64_t cap = (int64_t)sm_count() * 3;
+    const int fgrid = (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+    const size_t fsh = cbytes + (size_t)PD * (6 * (es / 2) + 1) * FT * 16;
+    CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_mid_bwd_kernel<TT, 2, false, FT><<<fgrid, FT, fsh, st>>>(
+                                        (const TT*)gout, (const TT*)z1, (const TT*)y, g, mean, invstd, gamma, beta, watt,
+                                        logits, sums, dwatt, dbatt, training, (TT*)dz1, (TT*)dy, w1, dw1)));
+    CLSKD_CHECK_LAUNCH(who);
+    return CLSKD_OK;
+  }
   if (xs) ABF_BWD(0, true, nullptr, nullptr); else ABF_BWD(0, false, nullptr, nullptr);
   CLSKD_CHECK_LAUNCH(who);
   if (xs) ABF_BWD(1, true, dz1, dy); else ABF_BWD(1, false, dz1, dy);
@@ -1160,6 +1278,37 @@ extern "C" int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y
                                  double* dbatt, void* dz1, void* dy, void* stream) {
   return abf_bwd_launch("clskd_abf_mid_bwd", false, gout, z1, y, dtype, B, T, F, Fy, C, mean, invstd, gamma, beta, watt,
                         logits, training, sums, dwatt, dbatt, dz1, dy, nullptr, nullptr, stream);
+}
+
+extern "C" int clskd_abf_mid_bwd_fold(const void* gout, const void* z1, const void* y, int dtype, int B, int T, int F,
+                                      int Fy, int C, const float* mean, const float* invstd, const float* gamma,
+                                      const float* beta, const float* watt, const float* logits, double* sums,
+                                      double* dwatt, double* dbatt, void* dxp, void* dy, void* stream) {
+  return abf_bwd_launch("clskd_abf_mid_bwd_fold", false, gout, z1, y, dtype, B, T, F, Fy, C, mean, invstd, gamma, beta,
+                        watt, logits, 1, sums, dwatt, dbatt, dxp, dy, nullptr, nullptr, stream, true);
+}
+
+extern "C" int clskd_abf_fold_dgrad(const float* w1, const float* gamma, const float* mean, const float* invstd,
+                                    const double* sums, int64_t M, int training, int C, int Cin, int c1p, void* weff,
+                                    float* bias, void* stream) {
+  CLSKD_CHECK_ARG(w1 && mean && invstd && sums && weff && bias, "clskd_abf_fold_dgrad: null pointer");
+  CLSKD_CHECK_ARG(C >= 1 && C <= 256 && Cin >= 1 && Cin <= 256 && c1p >= Cin && M >= 1, "clskd_abf_fold_dgrad: extents");
+  abf_fold_dgrad_kernel<<<Cin, 256, 0, (cudaStream_t)stream>>>(w1, gamma, mean, invstd, sums, 1.0 / (double)M, training, C,
+                                                               Cin, c1p, (__nv_bfloat16*)weff, bias);
+  CLSKD_CHECK_LAUNCH("clskd_abf_fold_dgrad");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_abf_fold_dw1(const float* P, const double* G, const double* sx, const float* w1, const float* gamma,
+                                  const float* mean, const float* invstd, const double* sums, int64_t M, int training,
+                                  int C, int Cin, float* dw1, void* stream) {
+  CLSKD_CHECK_ARG(P && w1 && mean && invstd && sums && dw1 && (!training || (G && sx)), "clskd_abf_fold_dw1: null pointer");
+  CLSKD_CHECK_ARG(C >= 1 && C <= 256 && Cin >= 1 && Cin <= 256 && M >= 1, "clskd_abf_fold_dw1: extents");
+  const int n = C * Cin;
+  abf_fold_dw1_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, G, sx, w1, gamma, mean, invstd, sums,
+                                                                         1.0 / (double)M, training, C, Cin, dw1);
+  CLSKD_CHECK_LAUNCH("clskd_abf_fold_dw1");
+  return CLSKD_OK;
 }
 
 extern "C" int clskd_abf_mid_xs_fwd(const void* x, const float* w1, const void* y, int dtype, int B, int T, int F, int Fy,

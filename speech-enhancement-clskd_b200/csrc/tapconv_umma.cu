@@ -573,15 +573,29 @@ extern "C" int clskd_tapconv_umma_supported(const ClskdTapConv* d) {
 
 static inline int pad16(int v) { return (v + 15) & ~15; }
 
+// padded channel extent of source 1: a multiple of 16, and - when source 1 is narrower than the K chunk that source 0
+// alone would run with - that chunk (one zero-filled TMA box over the channels that exist), so that a narrow second
+// source does not drag the whole contraction down to 16- or 32-channel chunks (ABF conv1 data gradient with the folded
+// BatchNorm backward: 128 + 16 channels)
+static inline int umma_c1p(int c0, int c1) {
+  const int c0p = pad16(c0);
+  int c1p = pad16(c1), bk0 = 64;
+  while (bk0 > 16 && c0p % bk0) bk0 >>= 1;
+  if (c1 && c1p < bk0) c1p = bk0;
+  return c1p;
+}
+
+extern "C" int clskd_tapconv_umma_c1p(int c0, int c1) { return umma_c1p(c0, c1); }
+
 static int launch_cfg(const ClskdTapConv* d, const FwdCfg& cfg, void* stream) {
-  const bool padded = (d->c0 % 16) || (d->c1 % 16) || (d->N % 16);
+  const bool padded = (d->c0 % 16) || (d->N % 16) || umma_c1p(d->c0, d->c1) != d->c1;
   if (cfg.v1 && !d->accumulate) {        // (the round-1 kernel has no reduce-add epilogue)
     if (padded) { set_error("clskd_tapconv_fwd_umma: the round-1 kernel needs multiples of 16 channels"); return CLSKD_ERR_UNSUPPORTED; }
     return clskd_tapconv_fwd_umma_v1(d, stream);
   }
   EncodeTiledFn enc = get_encode();
   // padded extents: what the kernel contracts / produces (the packed weight is [ntaps][Np][c0p + c1p])
-  const int c0p = pad16(d->c0), c1p = pad16(d->c1), Np = pad16(d->N);
+  const int c0p = pad16(d->c0), c1p = umma_c1p(d->c0, d->c1), Np = pad16(d->N);
   const int Ctot = c0p + c1p;
 
   UmmaParams p;

@@ -62,6 +62,12 @@ class EmuLib:
     def clskd_has_tcgen05(self):
         return 0
 
+    def clskd_tapconv_umma_c1p(self, c0, c1):
+        c0p, c1p, bk0 = (c0 + 15) // 16 * 16, (c1 + 15) // 16 * 16, 64
+        while bk0 > 16 and c0p % bk0:
+            bk0 >>= 1
+        return bk0 if (c1 and c1p < bk0) else c1p
+
     def clskd_tapconv_umma_supported(self, d):
         return 0
 

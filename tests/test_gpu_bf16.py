@@ -445,6 +445,85 @@ def test_abf_rank2_mid_stage_vs_stored_z1_path(cuda_dev, mid, F, T, B, up):
         assert (a[k] - b[k]).abs().max().item() < 2e-2 * s, k
 
 
+@pytest.mark.parametrize("C,M", [(16, 70001), (32, 12345), (64, 4099), (128, 130), (128, 50000), (16, 7)])
+def test_colgram_vs_float64(cuda_dev, C, M):
+    """clskd_colgram (x^T x and column sums of a bf16 map in one mma.sync pass) against float64 torch on the same bf16
+    values; rows with a non-zero mean, M not a multiple of the 128-row tile."""
+    from clskd_b200 import _lib
+    g = torch.Generator().manual_seed(C + M)
+    x = (torch.randn(M, C, generator=g) + torch.randn(1, C, generator=g)).bfloat16().to(cuda_dev)
+    out = torch.full((C * C + C,), 7.0, dtype=torch.float64, device=cuda_dev)      # the call zeroes its outputs
+    assert _lib.load().clskd_colgram_supported(_lib.BF16, C) == 1
+    _lib.call("clskd_colgram", x.data_ptr(), _lib.BF16, M, C, out.data_ptr(), out[C * C:].data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
+    xd = x.double()
+    G, sx = xd.t() @ xd, xd.sum(0)
+    assert (out[:C * C].view(C, C) - G).abs().max().item() < 2e-6 * G.abs().max().item()      # fp32 partial sums
+    assert (out[C * C:] - sx).abs().max().item() < 2e-6 * max(sx.abs().max().item(), 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,mid,F,T,B,up,mode", [(16, 128, 128, 23, 2, True, "train"), (32, 128, 64, 31, 3, True, "train"),
+                                                   (64, 128, 32, 40, 2, False, "train"), (128, 128, 16, 33, 3, True, "train"),
+                                                   (16, 64, 32, 21, 2, True, "eval")])
+def test_abf_fold_vs_two_pass_backward(cuda_dev, cin, mid, F, T, B, up, mode):
+    """ops.AbfFoldFn (one-pass middle-stage backward, BatchNorm backward folded into conv1's two-source data gradient
+    and into dW1 through x^T dxp, x^T x and sum x) against the two-pass AbfMidFn path + conv1's own gradient launches.
+    x has a non-zero mean per channel (post-PReLU maps do), which is what the cancellation in the folded dW1 sees.
+    Both paths round dz1-sized intermediates to bf16 once; differences are those roundings."""
+    import clskd_b200
+    from clskd_b200 import framework as fw
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(mid + F + cin)
+    torch.manual_seed(mid + cin)
+    abf = fw.ABF(cin, mid, 32, True).to(cuda_dev)
+    abf = abf.train() if mode == "train" else abf.eval()
+    abf.conv1[1].weight.data.uniform_(0.5, 1.5)
+    abf.conv1[1].bias.data.normal_(0, 0.2)
+    abf.conv1[1].running_mean.normal_(0, 0.3)
+    abf.conv1[1].running_var.uniform_(0.5, 1.5)
+    abf.att_conv[0].bias.data.normal_(0, 0.2)
+    Fy = F // 2 if up else F
+    x0 = torch.randn(B, cin, F, T, generator=g) + torch.randn(1, cin, 1, 1, generator=g) * 1.5
+    y0 = torch.randn(B, mid, Fy, T, generator=g)
+    gw = torch.randn(B, mid, F, T, generator=g).to(cuda_dev)
+    clskd_b200.set_precision("bf16")
+    res = {}
+    calls = {}
+    for fold in (True, False):
+        ops.policy.abf_fold = fold
+        for p in abf.parameters():
+            p.grad = None
+        rm = abf.conv1[1].running_mean.clone()
+        x = x0.to(cuda_dev).bfloat16().requires_grad_(True)
+        y = y0.to(cuda_dev).bfloat16().requires_grad_(True)
+        out, fused = abf(x, y, F, None, "decoder")
+        names, frontier = set(), [fused.grad_fn]
+        for _ in range(4):                       # autograd nodes within four hops of the fused map
+            nxt = []
+            for fn in frontier:
+                if fn is not None:
+                    names.add(type(fn).__name__)
+                    nxt += [f for f, _ in fn.next_functions]
+            frontier = nxt
+        calls[fold] = " ".join(sorted(names))
+        (fused.float() * gw).sum().backward()
+        res[fold] = dict(fused=fused.detach().float().cpu(), dx=x.grad.float().cpu(), dy=y.grad.float().cpu(),
+                         dw1=abf.conv1[0].weight.grad.float().cpu().reshape(-1),
+                         dgamma=abf.conv1[1].weight.grad.float().cpu(), dbeta=abf.conv1[1].bias.grad.float().cpu(),
+                         dwatt=abf.att_conv[0].weight.grad.float().cpu().reshape(-1),
+                         rmean=abf.conv1[1].running_mean.clone().cpu())
+        abf.conv1[1].running_mean.copy_(rm)
+    ops.policy.abf_fold = True
+    assert "AbfFoldFn" in calls[True] and "AbfFoldFn" not in calls[False], calls
+    a, b = res[True], res[False]
+    rl2 = lambda u, v: float((u.double() - v.double()).norm() / max(float(v.double().norm()), 1e-30))
+    assert torch.equal(a["fused"], b["fused"]) and torch.equal(a["rmean"], b["rmean"])     # same forward launches
+    errs = {k: rl2(a[k], b[k]) for k in ("dx", "dy", "dw1", "dgamma", "dbeta", "dwatt")}
+    assert errs["dy"] < 1e-6 and errs["dwatt"] < 1e-5 and errs["dgamma"] < 1e-5 and errs["dbeta"] < 1e-5, errs
+    assert errs["dx"] < 1e-2 and errs["dw1"] < 1e-2, errs
+
+
 @pytest.mark.parametrize("cin,cout,F,T,B,ks", [(32, 64, 128, 9, 2, 3), (128, 32, 256, 5, 1, 3), (16, 128, 128, 7, 2, 1),
                                               (64, 48, 128, 6, 1, 3), (64, 128, 32, 21, 2, 3), (128, 256, 8, 70, 2, 3)])
 @pytest.mark.parametrize("tune", [(0, 0), (1, 1), (2, 1), (3, 1), (3, 0)])
