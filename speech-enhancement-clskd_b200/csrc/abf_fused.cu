@@ -22,15 +22,16 @@ __device__ __forceinline__ void ld8(const float* p, float* o) {
   float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
+// bf16 pair -> two floats: one shift, one mask (the bf16x2 -> float2 intrinsic compiles to PRMT + shift per high half;
+// these kernels are instruction-issue bound)
+__device__ __forceinline__ void unpack8(const uint4& u, float* o) {
+  o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
+  o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
+  o[4] = __uint_as_float(u.z << 16); o[5] = __uint_as_float(u.z & 0xffff0000u);
+  o[6] = __uint_as_float(u.w << 16); o[7] = __uint_as_float(u.w & 0xffff0000u);
+}
 __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* o) {
-  uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 f = __bfloat1622float2(h[i]);
-    o[2 * i] = f.x;
-    o[2 * i + 1] = f.y;
-  }
+  unpack8(*reinterpret_cast<const uint4*>(p), o);
 }
 __device__ __forceinline__ void st8(float* p, const float* v) {
   reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -46,7 +47,14 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
   u.w = *reinterpret_cast<uint32_t*>(&h3);
   *reinterpret_cast<uint4*>(p) = u;
 }
-__device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + __expf(-v)); }
+// 1 / (1 + 2^(-v log2 e)) on MUFU ex2 / rcp (approx, flush-to-zero: 4 instructions; the IEEE division and the denormal
+// range check of __expf were 12).  v -> -inf: ex2 = +inf, rcp = 0; v -> +inf: ex2 = 0, rcp(1) = 1
+__device__ __forceinline__ float sigm(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 
 constexpr int AT = 256;
 
@@ -76,14 +84,7 @@ __device__ __forceinline__ void cp_vec8(uint8_t* slot0, int slot_stride, const T
   for (int i = 0; i < Vec8<T>::NCP; ++i) cp16(slot0 + i * slot_stride, reinterpret_cast<const uint8_t*>(g) + 16 * i);
 }
 __device__ __forceinline__ void ld_vec8(const uint8_t* slot0, int slot_stride, const __nv_bfloat16*, float* o) {
-  const uint4 u = *reinterpret_cast<const uint4*>(slot0);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 f = __bfloat1622float2(h[i]);
-    o[2 * i] = f.x;
-    o[2 * i + 1] = f.y;
-  }
+  unpack8(*reinterpret_cast<const uint4*>(slot0), o);
 }
 __device__ __forceinline__ void ld_vec8(const uint8_t* slot0, int slot_stride, const float*, float* o) {
   const float4 a = *reinterpret_cast<const float4*>(slot0);
@@ -192,16 +193,28 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
   // the issue side runs PD-1 iterations ahead of the compute side; both walk rows incrementally
   int64_t mi = warp0 * rpw * RQ + sub;      // first row of this lane group in the iteration being issued
   int si = 0;                               // its pipeline stage
+  // running source pointers (rows mi, mi + rpw; stride and rpw * RQ are even, so the y_prev row m >> yshift advances by
+  // a constant too): 64-bit address arithmetic per load was a large part of the loop's integer instructions
+  const T* zp_i[RQ];
+  const T* yp_i[RQ];
+#pragma unroll
+  for (int q = 0; q < RQ; ++q) {
+    const int64_t m = mi + q * rpw;
+    zp_i[q] = XS ? z1 + 2 * m : z1 + (m << cs_) + coff;
+    yp_i[q] = y + (yrow(g, m) << cs_) + coff;
+  }
+  const int64_t inc_z = XS ? 2 * stride : stride << cs_, inc_y = yrow(g, stride) << cs_;
   auto issue = [&]() {
     uint8_t* st = pipe + (size_t)si * NSLOT * SLOT_STRIDE;
 #pragma unroll
     for (int q = 0; q < RQ; ++q) {
-      const int64_t m = mi + q * rpw;
-      if (m < g.M) {
-        if (XS) cp_xs<T>(st + (q * NCP) * SLOT_STRIDE, z1 + 2 * m, 1);
-        else cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, z1 + (m << cs_) + coff);
-        cp_vec8<T>(st + ((RQ + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, y + (yrow(g, m) << cs_) + coff);
+      if (mi + q * rpw < g.M) {
+        if (XS) cp_xs<T>(st + (q * NCP) * SLOT_STRIDE, zp_i[q], 1);
+        else cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, zp_i[q]);
+        cp_vec8<T>(st + ((RQ + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp_i[q]);
       }
+      zp_i[q] += inc_z;
+      yp_i[q] += inc_y;
     }
     cp_commit();
     mi += stride;
@@ -223,7 +236,9 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
     for (int q = 0; q < RQ; ++q) {
       const int64_t m = m0 + q * rpw;
       live[q] = m < g.M;
-      if (live[q]) {
+      // a row beyond M computes on whatever its slots hold: nothing is accumulated across rows here, the shuffles stay
+      // inside the row's own lane group, and the stores below are predicated
+      {
         if (XS) {
           float x0, x1, wa[8], wb[8];
           ld_xs(st + (q * NCP) * SLOT_STRIDE, (const T*)nullptr, 0, x0, x1);
@@ -235,9 +250,6 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
           ld_vec8(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, xv[q]);
         }
         ld_vec8(st + ((RQ + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, yv[q]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) xv[q][e] = yv[q][e] = 0.f;
       }
     }
     float l0[RQ], l1[RQ];
@@ -273,7 +285,7 @@ __global__ void __launch_bounds__(AT, 2) abf_mid_fwd_kernel(const T* __restrict_
     }
 #pragma unroll
     for (int q = 0; q < RQ; ++q) {
-      for (int o = g.tpr >> 1; o > 0; o >>= 1) {
+      _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) if (o < g.tpr) {
         l0[q] += __shfl_xor_sync(0xffffffffu, l0[q], o);
         l1[q] += __shfl_xor_sync(0xffffffffu, l1[q], o);
       }
@@ -324,6 +336,9 @@ __global__ void __launch_bounds__(NT, NT == AT ? 2 : 3) abf_mid_bwd_kernel(const
   uint8_t* pipe = smem_raw + ((sizeof(float) * ((NCONST + 6) * C + 2) + 15) & ~(size_t)15) + threadIdx.x * 16;
   if (MODE != 1 || XS)
     for (int i = threadIdx.x; i < 6 * C + 2; i += NT) red[i] = 0.f;
+  // the pipeline slots start as zeros: a lane group beyond the last row pair reads finite (stale or zero) data and only
+  // has to zero its gout rows to drop out of every sum (ordered before the first cp.async by stage_consts' barrier)
+  for (int i = 0; i < PD * NSLOT; ++i) *reinterpret_cast<uint4*>(pipe + (size_t)i * SLOT_STRIDE) = make_uint4(0u, 0u, 0u, 0u);
   stage_consts(cs, C, mean, invstd, gamma, beta, watt, MODE == 1 ? sums : nullptr, 1.0 / (double)g.M, training,
                XS ? w1 : nullptr);
   // XS apply pass: dW1[c][k] partial sums of this thread's 8 channels
@@ -347,26 +362,33 @@ __global__ void __launch_bounds__(NT, NT == AT ? 2 : 3) abf_mid_bwd_kernel(const
 
   int64_t pi = warp0 * rpw + sub;           // pair issued next by this lane group
   int si = 0;
+  // running source pointers of the pair being issued (64-bit address arithmetic per load was a quarter of the loop's
+  // integer instructions); row pair p = rows 2p, 2p+1; y_prev row of row m = m >> yshift
+  const int64_t one_row = (int64_t)1 << cs_;
+  const int64_t inc_g = (2 * stride) << cs_, inc_y = yrow(g, 2 * stride) << cs_;
+  const T* gp_i = gout + ((2 * pi) << cs_) + coff;
+  const T* zp_i = XS ? z1 + 4 * pi : z1 + ((2 * pi) << cs_) + coff;       // XS: two rows of the 2-channel input
+  const T* yp_i = y + (yrow(g, 2 * pi) << cs_) + coff;
+  const float* lp_i = logits + 4 * pi;                                    // logits of rows 2p and 2p+1 (16 bytes)
   auto issue = [&]() {
     if (pi < pairs) {
       uint8_t* st = pipe + (size_t)si * NSLOT * SLOT_STRIDE;
-      const int64_t m0 = 2 * pi;
-      const int64_t yr0 = yrow(g, m0);
-      const T* gp = gout + (m0 << cs_) + coff;
-      const T* zp = XS ? z1 : z1 + (m0 << cs_) + coff;
-      const T* yp = y + (yr0 << cs_) + coff;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, gp + ((int64_t)q << cs_));
-        if (!XS) cp_vec8<T>(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, zp + ((int64_t)q << cs_));
+        cp_vec8<T>(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, gp_i + q * one_row);
+        if (!XS) cp_vec8<T>(st + ((2 + q) * NCP) * SLOT_STRIDE, SLOT_STRIDE, zp_i + q * one_row);
       }
-      if (XS) cp_xs<T>(st + (2 * NCP) * SLOT_STRIDE, z1 + 2 * m0, 2);      // rows m0, m0+1 of the 2-channel input
-      cp_vec8<T>(st + (4 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp);
-      if (y_full) cp_vec8<T>(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp + ((int64_t)1 << cs_));
-      cp16(st + (6 * NCP) * SLOT_STRIDE, logits + 2 * m0);      // logits of rows m0 and m0+1 (16 bytes)
+      if (XS) cp_xs<T>(st + (2 * NCP) * SLOT_STRIDE, zp_i, 2);
+      cp_vec8<T>(st + (4 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp_i);
+      if (y_full) cp_vec8<T>(st + (5 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp_i + one_row);
+      cp16(st + (6 * NCP) * SLOT_STRIDE, lp_i);
     }
     cp_commit();
     pi += stride;
+    gp_i += inc_g;
+    zp_i += XS ? 4 * stride : inc_g;
+    yp_i += inc_y;
+    lp_i += 4 * stride;
     si = si + 1 == PD ? 0 : si + 1;
   };
 #pragma unroll
@@ -385,7 +407,7 @@ __global__ void __launch_bounds__(NT, NT == AT ? 2 : 3) abf_mid_bwd_kernel(const
     float gv[2][8], xv[2][8], yv[2][8];
     float2 lg[2];
     float xs0[2] = {0.f, 0.f}, xs1[2] = {0.f, 0.f};
-    if (live) {
+    if (live || !XS) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         ld_vec8(st + (q * NCP) * SLOT_STRIDE, SLOT_STRIDE, (const T*)nullptr, gv[q]);
@@ -411,6 +433,13 @@ __global__ void __launch_bounds__(NT, NT == AT ? 2 : 3) abf_mid_bwd_kernel(const
       const float4 l4 = *reinterpret_cast<const float4*>(st + (6 * NCP) * SLOT_STRIDE);
       lg[0] = make_float2(l4.x, l4.y);
       lg[1] = make_float2(l4.z, l4.w);
+      if (!XS) {
+        // a group beyond the last pair (tail of the grid-stride loop): every sum below is linear in gout
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gv[q][e] = live ? gv[q][e] : 0.f;
+      }
     } else {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -452,7 +481,7 @@ __global__ void __launch_bounds__(NT, NT == AT ? 2 : 3) abf_mid_bwd_kernel(const
         t0 = fmaf(gv[q][e], xp[q][e], t0);
         t1 = fmaf(gv[q][e], yv[q][e], t1);
       }
-      for (int o = g.tpr >> 1; o > 0; o >>= 1) {
+      _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) if (o < g.tpr) {
         t0 += __shfl_xor_sync(0xffffffffu, t0, o);
         t1 += __shfl_xor_sync(0xffffffffu, t1, o);
       }
@@ -544,7 +573,7 @@ __global__ void __launch_bounds__(NT, NT == AT ? 2 : 3) abf_mid_bwd_kernel(const
             a_w10[e] = fmaf(xp[q][e], xs0[q], a_w10[e]);
             a_w11[e] = fmaf(xp[q][e], xs1[q], a_w11[e]);
           }
-          for (int o = g.tpr >> 1; o > 0; o >>= 1) {
+          _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) if (o < g.tpr) {
             p0 += __shfl_xor_sync(0xffffffffu, p0, o);
             p1 += __shfl_xor_sync(0xffffffffu, p1, o);
           }
@@ -679,10 +708,12 @@ __device__ __forceinline__ void xs2_stage_consts(float* cs, int C, const float* 
 // n partial sums per lane -> totals over the tpr lanes of a row group (butterfly); tpr is a power of two
 template <int N>
 __device__ __forceinline__ void group_sum(float* v, int tpr) {
-  for (int o = tpr >> 1; o > 0; o >>= 1) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-  }
+  for (int o = 16; o > 0; o >>= 1)
+    if (o < tpr) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
 }
 
 template <typename T>

@@ -36,6 +36,14 @@ def work(name, shape):
         base = name.replace("clskd_", "")
         bound = "compute" if fl / 1416.6e12 > by / 6560e9 else "memory"
         return by, fl, "%s (%s-bound shapes)" % (base, bound)
+    if name == "clskd_abf_mid_bwd_fold":
+        B, T, F, Fy, C = (int(s[k]) for k in ("B", "T", "F", "Fy", "C"))
+        rows, yrows = B * T * F, B * T * Fy
+        # g, z1, logits, y_prev read once; dxp and dy_prev written
+        return rows * (2 * C + 2 * C + 8) + yrows * 2 * C + rows * 2 * C + yrows * 2 * C, 0.0, "abf_mid_bwd_fold (one pass)"
+    if name == "clskd_colgram":
+        M, C = int(s["M"]), int(s["C"])
+        return M * C * 2, 0.0, "colgram"
     if name in ("clskd_abf_mid_fwd", "clskd_abf_mid_bwd"):
         B, T, F, Fy, C = (int(s[k]) for k in ("B", "T", "F", "Fy", "C"))
         rows, yrows = B * T * F, B * T * Fy

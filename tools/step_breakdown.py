@@ -88,8 +88,10 @@ def main():
             shp = "B=%d K=%d %s" % (args[2], args[3], "bf16" if args[1] else "f32")
         elif name in ("clskd_abf_mid_fwd",):
             shp = "B=%d T=%d F=%d Fy=%d C=%d" % tuple(args[3:8])
-        elif name in ("clskd_abf_mid_bwd",):
+        elif name in ("clskd_abf_mid_bwd", "clskd_abf_mid_bwd_fold"):
             shp = "B=%d T=%d F=%d Fy=%d C=%d" % tuple(args[4:9])
+        elif name == "clskd_colgram":
+            shp = "M=%d C=%d %s" % (args[2], args[3], "bf16" if args[1] else "f32")
         elif name == "clskd_abf_mid_xs_fwd":
             shp = "B=%d T=%d F=%d Fy=%d C=%d" % tuple(args[4:9])
         elif name == "clskd_abf_mid_xs_bwd":
