@@ -832,8 +832,11 @@ __global__ void __launch_bounds__(AT, 2) abf_xs2_fwd_kernel(const T* __restrict_
 enum { R_D0 = 0, R_D1, R_D0X0, R_D0X1, R_D1X0, R_D1X1, R_X0, R_X1, R_X00, R_X01, R_X11, R_NSCAL };
 
 // acc layout (fp64, zeroed by the launcher): G0[C] G1[C] G2[C] WY0[C] WY1[C] scal[R_NSCAL]
+// 128-thread CTAs, three per SM (168 registers): at 128 registers the kernel spilled inside the row loop and its
+// dy_prev / workspace stores evicted the spill lines from L1 (as in the one-pass abf_mid_bwd_kernel)
+constexpr int XT = 128;
 template <typename T>
-__global__ void __launch_bounds__(AT, 2) abf_xs2_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ x,
+__global__ void __launch_bounds__(XT, 3) abf_xs2_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ x,
                                                             const T* __restrict__ y, AbfGeom g,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -846,15 +849,15 @@ __global__ void __launch_bounds__(AT, 2) abf_xs2_bwd_kernel(const T* __restrict_
   float* red = cs + X_NCONST * C + XS_NSCAL;              // [5*C + R_NSCAL]
   constexpr int NCP = Vec8<T>::NCP;
   constexpr int NSLOT = 4 * NCP + 2;                      // g[2], y[1..2] vectors, x pair, logits pair
-  constexpr int SLOT_STRIDE = AT * 16;
+  constexpr int SLOT_STRIDE = XT * 16;
   uint8_t* pipe = smem_raw + ((sizeof(float) * (X_NCONST * C + XS_NSCAL + 5 * C + R_NSCAL) + 15) & ~(size_t)15) + threadIdx.x * 16;
-  for (int i = threadIdx.x; i < 5 * C + R_NSCAL; i += AT) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 5 * C + R_NSCAL; i += XT) red[i] = 0.f;
   xs2_stage_consts(cs, C, mean, invstd, gamma, beta, watt, nullptr, w1);
   const int lane = threadIdx.x & 31;
   const int cg = lane & (g.tpr - 1), sub = lane / g.tpr, rpw = 32 / g.tpr;
   const int64_t pairs = g.M >> 1;
-  const int64_t warp0 = ((int64_t)blockIdx.x * AT + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * AT) >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * XT + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * XT) >> 5;
   const int64_t stride = nwarps * rpw;
   const int cs_ = g.cshift, coff = cg * 8;
   const bool y_full = g.yshift == 0;
@@ -866,21 +869,29 @@ __global__ void __launch_bounds__(AT, 2) abf_xs2_bwd_kernel(const T* __restrict_
 
   int64_t pi = warp0 * rpw + sub;
   int si = 0;
+  // running source pointers of the row pair being issued (rows 2p, 2p+1)
+  const int64_t one_row = (int64_t)1 << cs_;
+  const int64_t inc_g = (2 * stride) << cs_, inc_y = yrow(g, 2 * stride) << cs_;
+  const T* gp_i = gout + ((2 * pi) << cs_) + coff;
+  const T* yp_i = y + (yrow(g, 2 * pi) << cs_) + coff;
+  const T* xp_i = x + 4 * pi;
+  const float* lp_i = logits + 4 * pi;
   auto issue = [&]() {
     if (pi < pairs) {
       uint8_t* st = pipe + (size_t)si * NSLOT * SLOT_STRIDE;
-      const int64_t m0 = 2 * pi;
-      const T* gp = gout + (m0 << cs_) + coff;
-      const T* yp = y + (yrow(g, m0) << cs_) + coff;
-      cp_vec8<T>(st, SLOT_STRIDE, gp);
-      cp_vec8<T>(st + NCP * SLOT_STRIDE, SLOT_STRIDE, gp + ((int64_t)1 << cs_));
-      cp_vec8<T>(st + (2 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp);
-      if (y_full) cp_vec8<T>(st + (3 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp + ((int64_t)1 << cs_));
-      cp_xs<T>(st + (4 * NCP) * SLOT_STRIDE, x + 2 * m0, 2);
-      cp16(st + (4 * NCP + 1) * SLOT_STRIDE, logits + 2 * m0);
+      cp_vec8<T>(st, SLOT_STRIDE, gp_i);
+      cp_vec8<T>(st + NCP * SLOT_STRIDE, SLOT_STRIDE, gp_i + one_row);
+      cp_vec8<T>(st + (2 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp_i);
+      if (y_full) cp_vec8<T>(st + (3 * NCP) * SLOT_STRIDE, SLOT_STRIDE, yp_i + one_row);
+      cp_xs<T>(st + (4 * NCP) * SLOT_STRIDE, xp_i, 2);
+      cp16(st + (4 * NCP + 1) * SLOT_STRIDE, lp_i);
     }
     cp_commit();
     pi += stride;
+    gp_i += inc_g;
+    yp_i += inc_y;
+    xp_i += 4 * stride;
+    lp_i += 4 * stride;
     si = si + 1 == PD ? 0 : si + 1;
   };
 #pragma unroll
@@ -1011,7 +1022,7 @@ __global__ void __launch_bounds__(AT, 2) abf_xs2_bwd_kernel(const T* __restrict_
     for (int e = 0; e < R_NSCAL; ++e) atomicAdd(&red[5 * C + e], aS[e]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 5 * C + R_NSCAL; i += AT) atomicAdd(acc + i, (double)red[i]);
+  for (int i = threadIdx.x; i < 5 * C + R_NSCAL; i += XT) atomicAdd(acc + i, (double)red[i]);
 }
 
 // one block: batch sums -> dgamma / dbeta (sums), dW_att, db_att, dW1 and the 10 constants of the dx pass
@@ -1432,16 +1443,18 @@ extern "C" int clskd_abf_xs2_bwd(const void* gout, const void* x, const float* w
   if (g.M > 0) {
     const int64_t pairs = g.M / 2;
     const int ppw = 32 / g.tpr;
-    const int grid = abf_grid((pairs + ppw - 1) / ppw / 4);
+    int64_t blocks = ((pairs + ppw - 1) / ppw / 4 + XT / 32 - 1) / (XT / 32);
+    const int64_t cap = (int64_t)sm_count() * 3;
+    const int grid = (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
     const size_t cbytes = (sizeof(float) * (X_NCONST * (size_t)C + XS_NSCAL + 5 * (size_t)C + R_NSCAL) + 15) & ~(size_t)15;
-    const size_t sh = cbytes + (size_t)PD * (4 * (es / 2) + 2) * AT * 16;
+    const size_t sh = cbytes + (size_t)PD * (4 * (es / 2) + 2) * XT * 16;
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(abf_xs2_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(abf_xs2_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr = true;
     }
-    CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_xs2_bwd_kernel<TT><<<grid, AT, sh, st>>>(
+    CLSKD_DISPATCH_DTYPE(dtype, TT, (abf_xs2_bwd_kernel<TT><<<grid, XT, sh, st>>>(
                                         (const TT*)gout, (const TT*)x, (const TT*)y, g, mean, invstd, gamma, beta, watt, w1,
                                         logits, acc, rows, (TT*)dy)));
     CLSKD_CHECK_LAUNCH(who);
