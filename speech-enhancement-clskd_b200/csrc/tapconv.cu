@@ -900,6 +900,10 @@ extern "C" int clskd_tapconv_fwd(const ClskdTapConv* d, void* stream) {
     CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(pointwise)");
     return CLSKD_OK;
   }
+  if (c2mma::try_fwd(d, st)) {
+    CLSKD_CHECK_LAUNCH("clskd_tapconv_fwd(c2 mma)");
+    return CLSKD_OK;
+  }
   N2Geom g2;
   if (n2_ok(d, &g2) && g2.U > 128) {
     int tup2 = 1;                                     // lanes per row: power of two covering cpt, <= 32

@@ -445,6 +445,39 @@ def test_abf_rank2_mid_stage_vs_stored_z1_path(cuda_dev, mid, F, T, B, up):
         assert (a[k] - b[k]).abs().max().item() < 2e-2 * s, k
 
 
+@pytest.mark.parametrize("cout,F,T,B", [(16, 256, 45, 3), (32, 256, 33, 2), (24, 64, 130, 2), (64, 32, 300, 1)])
+def test_first_layer_mma_kernel_vs_oracle(cuda_dev, cout, F, T, B):
+    """First encoder layer under the bf16 policy (tapconv_c2_mma.cu: fp32 two-channel spectrogram -> bf16 maps on
+    mma.sync with split-bf16 inputs AND weights) against the oracle's complex conv in float64: only the bf16 rounding
+    of the stored output may differ (2^-9 relative), the contraction itself keeps ~2^-16."""
+    import clskd_b200
+    from clskd_b200 import ops
+    from clskd_b200 import tools_for_model as tm
+    from oracle import dccrn_oracle as D
+    g = torch.Generator().manual_seed(cout + F)
+    conv = tm.ComplexConv2d(2, cout, kernel_size=(5, 2), stride=(2, 1), padding=(2, 1))
+    conv.real_conv.bias.data.normal_(generator=g)
+    conv.imag_conv.bias.data.normal_(generator=g)
+    x0 = torch.randn(B, 2, F, T, generator=g) * torch.rand(B, 1, F, 1, generator=g) * 3
+    ref = D.complex_conv2d(x0.double(), conv.real_conv.weight.double(), conv.real_conv.bias.double(),
+                           conv.imag_conv.weight.double(), conv.imag_conv.bias.double())
+    clskd_b200.set_precision("bf16")
+    conv = conv.to(cuda_dev)
+    xp = ops.to_phys(x0.to(cuda_dev))                      # fp32 [B, T, F, 2] view
+    n0 = ops.core_launches
+    y = conv.forward_phys(ops.dense(xp), torch.bfloat16)
+    assert ops.core_launches == n0 + 1                     # the CUDA-core entry point (routes to the mma.sync kernel)
+    out = ops.to_logical(y).float().cpu().double()
+    assert out.shape == ref.shape
+    s = ref.abs().max().item()
+    err = (out - ref).abs()
+    assert err.max().item() < 6e-3 * s and err.mean().item() < 1.5e-3 * ref.abs().mean().item()
+    # against the same values rounded to bf16: the contraction error itself
+    assert (out - ref.float().bfloat16().double()).abs().max().item() < 1e-2 * s
+    exact = (out == ref.float().bfloat16().double()).double().mean().item()
+    assert exact > 0.97, exact
+
+
 @pytest.mark.parametrize("C,M", [(16, 70001), (32, 12345), (64, 4099), (128, 130), (128, 50000), (16, 7)])
 def test_colgram_vs_float64(cuda_dev, C, M):
     """clskd_colgram (x^T x and column sums of a bf16 map in one mma.sync pass) against float64 torch on the same bf16
