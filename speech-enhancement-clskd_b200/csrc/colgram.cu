@@ -8,7 +8,7 @@
 // SAME shared-memory tile [row][channel] read through ldmatrix.trans (A = x^T needs the transpose, and B is stored
 // k-major).  A CTA's 8 warps split as WI warps over the C/16 row blocks of G x WR warps over the rows of a tile, so a
 // warp keeps (C/8) x 4 accumulators; the column sums ride along as one extra MMA per column block with a constant A
-// fragment (a row of ones).  Tiles of 128 rows arrive through a double-buffered cp.async pipeline (rows beyond M are
+// fragment (a row of ones).  Tiles of 16384 / C rows arrive through a double-buffered cp.async pipeline (rows beyond M are
 // zero-filled); per-CTA partial sums are combined in shared memory, then added to the fp64 outputs.
 #include "common.cuh"
 
@@ -29,12 +29,15 @@ __device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uin
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-constexpr int CG_R = 128;        // rows per tile
 constexpr int CG_T = 256;        // threads per CTA
+// rows per tile: 16 K elements (32 KB) per stage whatever the channel count - with a fixed 128-row tile the narrow maps
+// (C = 16: 4 KB per stage) had far too few bytes in flight per SM to cover the HBM latency
+constexpr int cg_rows(int C) { return 16384 / C; }
 
 template <int C>
 __global__ void __launch_bounds__(CG_T, 2) colgram_kernel(const __nv_bfloat16* __restrict__ x, int64_t M,
                                                           double* __restrict__ G, double* __restrict__ sx) {
+  constexpr int CG_R = cg_rows(C);
   constexpr int PITCH = C * 2 + 16;                 // bytes per staged row (+16: conflict-free ldmatrix rows)
   constexpr int NIT = C / 16, NJT = C / 8;
   constexpr int WI = NIT < 8 ? NIT : 8, WR = 8 / WI;
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(CG_T, 2) colgram_kernel(const __nv_bfloat16* _
 template <int C>
 int colgram_launch(const void* x, int64_t M, double* G, double* sx, cudaStream_t st) {
   constexpr int PITCH = C * 2 + 16;
+  constexpr int CG_R = cg_rows(C);
   size_t sh = (size_t)2 * CG_R * PITCH;
   const size_t red = sizeof(float) * (C * C + C);
   if (red > sh) sh = red;
