@@ -201,16 +201,19 @@ def workload_config(args, batch):
 
 # ------------------------------------------------------------------------------------ GPU arm
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  nvidia-smi takes up to a second to print its
+    first line (longer on a multi-GPU box), so start() is called BEFORE the warm-up steps and begin() marks the start
+    of the timed region; stop() keeps the samples whose own timestamps fall inside [begin, stop]."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0 = [], None, index, None
 
     def start(self):
         try:
+            self.t_start = time.time()
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -219,24 +222,51 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    @staticmethod
+    def _ts(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            cols = [c.strip() for c in line.split(",")]
+            self.rows.append((self._ts(cols[0]) if cols else None, cols[1:]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time()
+        time.sleep(0.12)                       # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        self.th.join(timeout=2)
+        t0 = self.t0 if self.t0 is not None else self.t_start
+        inside = [r for ts, r in self.rows if ts is not None and t0 <= ts <= t1 + 0.1]
+        note = None
+        if not inside and self.rows:
+            # region shorter than the sampling period: the sample nearest to it (the GPU was under the same load
+            # during the warm-up steps just before)
+            near = min((abs((ts if ts is not None else t1) - t1), i) for i, (ts, _) in enumerate(self.rows))[1]
+            inside = [self.rows[near][1]]
+            note = "no sample inside the %.0f ms region: nearest sample used" % ((t1 - t0) * 1e3)
+        sm = sorted(int(r[0]) for r in inside if r and r[0].isdigit())
+        mx = [int(r[1]) for r in inside if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].startswith("Active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].startswith("Active") for r in inside)]
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
 
 
 class KernelTimer:
@@ -390,6 +420,9 @@ def run_ours(args):
         barrier()
         return e0.elapsed_time(e1), out
 
+    sampler = ClockSampler(local)
+    if rank == 0 and not args.profile_step:
+        sampler.start()                      # (before the warm-up: nvidia-smi needs up to a second to produce its first line)
     for _ in range(args.warmup):
         tr.train_step(X, y)
     barrier()
@@ -404,9 +437,8 @@ def run_ours(args):
         print(json.dumps({"profiled": "one %s step, %d x %.0f s" % (args.mode, B, args.seconds)}), flush=True)
         return
     # ---------------- timed region 1: inputs resident in HBM
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.begin()
     launches0 = _lib.launch_count
     ms, loss = timed(args.steps, X, y)
     launches = _lib.launch_count - launches0
@@ -450,11 +482,13 @@ def run_ours(args):
             torch.cuda.empty_cache()
             Xg_h, yg_h = host_batch(Bg)
             Xg, yg = Xg_h.to(dev), yg_h.to(dev)
-            for _ in range(2):
-                tr.train_step(Xg, yg)
             samp = ClockSampler(local)
             if rank == 0:
                 samp.start()
+            for _ in range(2):
+                tr.train_step(Xg, yg)
+            if rank == 0:
+                samp.begin()
             nst = 3
             msg, _ = timed(nst, Xg, yg)
             ck = samp.stop() if rank == 0 else None
@@ -575,11 +609,12 @@ def _short_step_bench(args, mode, student, faithful, steps=5, warmup=3, batch=64
     if faithful:
         teacher.train()
     tr = DistillTrainer(teacher, stu, mode=mode, faithful=faithful, example_input=X[:2])
+    samp = ClockSampler(0)
+    samp.start()
     for _ in range(warmup):
         tr.train_step(X, y)
     torch.cuda.synchronize()
-    samp = ClockSampler(0)
-    samp.start()
+    samp.begin()
     n0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
