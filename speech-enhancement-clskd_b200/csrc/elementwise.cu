@@ -81,6 +81,68 @@ strided_copy4d_vec_kernel(const TS* __restrict__ src, TD* __restrict__ dst, I n1
   }
 }
 
+// The (channel, frequency) transposes either side of the LSTM (DCCRN.py:178-199: [B,T,F,C] maps <-> [T,B,C*F] features)
+// have ONE dimension of extent 4 (the frequency bins left after the encoder).  The generic kernel above moves them one
+// element at a time with three 64-bit divisions each (0.65 TB/s); here a thread owns a 4 x 4 block - four 4-element vector
+// accesses on the strided side, 16 contiguous elements on the dense side - with one 32-bit index decode per block.
+//   DIR 0: shape [n0,n1,C,4], src (.., .., 1, Ls) -> dst (.., .., 4, 1)     src rows [f][c] (pitch Ls), dst dense [c][f]
+//   DIR 1: shape [n0,n1,4,C], src (.., .., 1, 4)  -> dst (.., .., Ld, 1)    src dense [c][f], dst rows [f][c] (pitch Ld)
+__device__ __forceinline__ void st16(float* p, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void st16(__nv_bfloat16* p, const float* v) {
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void ld16(const float* p, float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 a = reinterpret_cast<const float4*>(p)[j];
+    v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+  }
+}
+__device__ __forceinline__ void ld16(const __nv_bfloat16* p, float* v) {
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[2 * j] = __uint_as_float(w[j] << 16);
+    v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
+template <typename TS, typename TD, int DIR>
+__global__ void __launch_bounds__(256)
+transpose4_kernel(const TS* __restrict__ src, TD* __restrict__ dst, unsigned n1, unsigned cgroups, unsigned total,
+                  int64_t s0, int64_t s1, int64_t d0, int64_t d1, int64_t pitch) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned cg = i % cgroups, u = i / cgroups;
+    const unsigned i1 = u % n1, i0 = u / n1;
+    const TS* sp = src + (int64_t)i0 * s0 + (int64_t)i1 * s1;
+    TD* dp = dst + (int64_t)i0 * d0 + (int64_t)i1 * d1;
+    float v[16];
+    if (DIR == 0) {
+      float4 r[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) r[f] = ld4(sp + (int64_t)f * pitch + cg * 4);
+#pragma unroll
+      for (int f = 0; f < 4; ++f) { v[f] = r[f].x; v[4 + f] = r[f].y; v[8 + f] = r[f].z; v[12 + f] = r[f].w; }
+      st16(dp + cg * 16, v);
+    } else {
+      ld16(sp + cg * 16, v);
+#pragma unroll
+      for (int f = 0; f < 4; ++f) st4(dp + (int64_t)f * pitch + cg * 4, make_float4(v[f], v[4 + f], v[8 + f], v[12 + f]));
+    }
+  }
+}
+
 template <typename TD>
 __global__ void pack_gather_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                    const int32_t* __restrict__ table, int64_t n,
@@ -1082,6 +1144,39 @@ extern "C" int clskd_strided_copy4d(const void* src, int src_dtype, const int64_
 #undef LV3
     CLSKD_CHECK_LAUNCH("clskd_strided_copy4d(vec)");
     return CLSKD_OK;
+  }
+  {
+    // 4 x 4 block transposes (see transpose4_kernel): dir 0 = [.., .., C, 4] gathered from rows of pitch ss[3], dir 1 =
+    // [.., .., 4, C] scattered to rows of pitch ds[2]
+    const int se = src_dtype == CLSKD_F32 ? 4 : 2, de = dst_dtype == CLSKD_F32 ? 4 : 2;
+    int dir = -1;
+    int64_t C = 0, pitch = 0;
+    if (shape[3] == 4 && ss[2] == 1 && ds[3] == 1 && ds[2] == 4 && shape[2] % 4 == 0 && ss[3] >= shape[2]) {
+      dir = 0; C = shape[2]; pitch = ss[3];
+    } else if (shape[2] == 4 && ss[2] == 1 && ss[3] == 4 && ds[3] == 1 && shape[3] % 4 == 0 && ds[2] >= shape[3]) {
+      dir = 1; C = shape[3]; pitch = ds[2];
+    }
+    const int64_t items = dir >= 0 ? shape[0] * shape[1] * (C / 4) : 0;
+    const bool al = dir >= 0 && ss[0] % 4 == 0 && ss[1] % 4 == 0 && ds[0] % 4 == 0 && ds[1] % 4 == 0 && pitch % 4 == 0 &&
+                    ((uintptr_t)src % (4 * se)) == 0 && ((uintptr_t)dst % (4 * de)) == 0 &&
+                    (dir == 0 ? ((uintptr_t)dst % 16) == 0 : ((uintptr_t)src % 16) == 0) &&
+                    // the 16-element side is accessed with 16-byte vectors: its unit strides must keep that alignment
+                    (dir == 0 ? (ds[0] * de) % 16 == 0 && (ds[1] * de) % 16 == 0 : (ss[0] * se) % 16 == 0 && (ss[1] * se) % 16 == 0);
+    if (al && items > 0 && items < 2000000000LL && shape[1] < 2000000000LL) {
+      const int gridt = ew_grid(items, 256);
+#define LT2(TS, TD, DIR)                                                                                            \
+  transpose4_kernel<TS, TD, DIR><<<gridt, 256, 0, ST>>>((const TS*)src, (TD*)dst, (unsigned)shape[1], (unsigned)(C / 4), \
+                                                        (unsigned)items, ss[0], ss[1], ds[0], ds[1], pitch)
+#define LT(TS, TD) do { if (dir == 0) LT2(TS, TD, 0); else LT2(TS, TD, 1); } while (0)
+      if (src_dtype == CLSKD_F32 && dst_dtype == CLSKD_F32) LT(float, float);
+      else if (src_dtype == CLSKD_F32) LT(float, __nv_bfloat16);
+      else if (dst_dtype == CLSKD_F32) LT(__nv_bfloat16, float);
+      else LT(__nv_bfloat16, __nv_bfloat16);
+#undef LT
+#undef LT2
+      CLSKD_CHECK_LAUNCH("clskd_strided_copy4d(transpose4)");
+      return CLSKD_OK;
+    }
   }
   int grid = ew_grid(total, 256);
 #define L(TS, TD)                                                                               \

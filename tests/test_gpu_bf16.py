@@ -478,6 +478,29 @@ def test_first_layer_mma_kernel_vs_oracle(cuda_dev, cout, F, T, B):
     assert exact > 0.97, exact
 
 
+@pytest.mark.parametrize("sd,dd", [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16),
+                                   (torch.bfloat16, torch.float32), (torch.float32, torch.float32)])
+@pytest.mark.parametrize("B,T,F,Cc", [(3, 37, 4, 64), (2, 21, 4, 128), (2, 9, 4, 20), (2, 5, 3, 16)])
+def test_lstm_layout_transposes_vs_torch(cuda_dev, sd, dd, B, T, F, Cc):
+    """The (channel, frequency) transposes either side of the LSTM (DCCRN.py:178-199) through clskd_strided_copy4d: with
+    F = 4 they run on the 4 x 4 block transpose kernel (both directions, every dtype pair); F = 3 keeps the generic kernel."""
+    from clskd_b200 import ops
+    g = torch.Generator().manual_seed(B * T + Cc)
+    # direction 0: physical [B,T,F,2Cc] (one complex part) -> [T,B,Cc,F]
+    x = torch.randn(B, T, F, 2 * Cc, generator=g).to(cuda_dev).to(sd)
+    for part in range(2):
+        out = torch.full((T, B, Cc * F), 7.0, dtype=dd, device=cuda_dev)
+        ops.strided_copy_into(x[..., part * Cc:(part + 1) * Cc].permute(1, 0, 3, 2), out.view(T, B, Cc, F))
+        ref = x[..., part * Cc:(part + 1) * Cc].permute(1, 0, 3, 2).to(dd)
+        assert torch.equal(out.view(T, B, Cc, F), ref)
+    # direction 1: LSTM output [T,B,Cc*F] -> physical [B,T,F,2Cc] (one complex part)
+    y = torch.randn(T, B, Cc * F, generator=g).to(cuda_dev).to(sd)
+    phys = torch.full((B, T, F, 2 * Cc), -3.0, dtype=dd, device=cuda_dev)
+    for part in range(2):
+        ops.strided_copy_into(y.reshape(T, B, Cc, F).permute(1, 0, 3, 2), phys[..., part * Cc:(part + 1) * Cc])
+        assert torch.equal(phys[..., part * Cc:(part + 1) * Cc], y.reshape(T, B, Cc, F).permute(1, 0, 3, 2).to(dd))
+
+
 @pytest.mark.parametrize("C,M", [(16, 70001), (32, 12345), (64, 4099), (128, 130), (128, 50000), (16, 7)])
 def test_colgram_vs_float64(cuda_dev, C, M):
     """clskd_colgram (x^T x and column sums of a bf16 map in one mma.sync pass) against float64 torch on the same bf16
