@@ -158,7 +158,16 @@ class SPKDLoss(nn.Module):
         ops._require_cuda(zs, zt)
         B = zt.shape[0]
         scale = 1.0 / (B * B) if self.reduction == 'batchmean' else 1.0
-        return SPKDFn.apply(_any_order_flat(zs), _any_order_flat(zt.detach()), scale)
+        zs, zt = _any_order_flat(zs), _any_order_flat(zt.detach())
+        if ops.policy.use_umma:
+            # tensor-core policy: the fp32 taps (LSTM outputs) join the bf16 activations of every other tap, so their Gram
+            # matrices run on the tcgen05 kernels too (the fp32 CUDA-core Gram kernel reads 84 MB at 0.6 TB/s); the Gram
+            # entries are sums over >= 1e5 products, the roundings average out (2^-9 / sqrt(K) relative)
+            if zs.dtype == torch.float32 and zs[0].numel() >= 65536:
+                zs = dense(zs, torch.bfloat16)
+            if zt.dtype == torch.float32 and zt[0].numel() >= 65536:
+                zt = dense(zt, torch.bfloat16)
+        return SPKDFn.apply(zs, zt, scale)
 
 
 # ---------------------------------------------------------------------------------------------
