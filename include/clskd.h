@@ -418,7 +418,9 @@ int clskd_abf_mid_bwd(const void* gout, const void* z1, const void* y, int dtype
  *     G = x^T x (fp64 [Cin][Cin]) and sx = column sums of x (fp64 [Cin]) - both from clskd_colgram;
  *     G and sx may be NULL when training = 0.
  *   clskd_colgram: G and sx of a dense bf16 map x [M][C], C in {16, 32, 64, 128}, in one pass over x (mma.sync on
- *     ldmatrix.trans tiles; outputs zeroed by the call). */
+ *     ldmatrix.trans tiles; outputs zeroed by the call).
+ *   clskd_abf_fold_stats: column sums / sums of squares (fp64 [C] each) of z1 = bf16(W1) x from G and sx - the batch
+ *     statistics of conv1's BatchNorm without the statistics epilogue of the conv (or a pass over z1). */
 int clskd_abf_mid_bwd_fold(const void* gout, const void* z1, const void* y, int dtype, int B, int T, int F,
                            int Fy, int C, const float* mean, const float* invstd, const float* gamma,
                            const float* beta, const float* watt, const float* logits, double* sums,
@@ -428,6 +430,8 @@ int clskd_abf_fold_dgrad(const float* w1, const float* gamma, const float* mean,
                          float* bias, void* stream);
 int clskd_colgram_supported(int dtype, int C);
 int clskd_colgram(const void* x, int dtype, int64_t M, int C, double* G, double* sx, void* stream);
+int clskd_abf_fold_stats(const double* G, const double* sx, const float* w1, int C, int Cin, double* sum,
+                         double* sumsq, void* stream);
 int clskd_abf_fold_dw1(const float* P, const double* G, const double* sx, const float* w1, const float* gamma,
                        const float* mean, const float* invstd, const double* sums, int64_t M, int training,
                        int C, int Cin, float* dw1, void* stream);

@@ -1143,6 +1143,30 @@ __global__ void abf_fold_dgrad_kernel(const float* __restrict__ w1, const float*
   }
 }
 
+// Batch statistics of z1 = W1 x from the moments of x (clskd_colgram): sum_c = W1[c] . sx,  sumsq_c = W1[c]^T G W1[c].
+// W1 is rounded to bf16 first - the tcgen05 conv contracts the bf16 copy of the weight, and the statistics must belong to
+// the z1 it produces.  One warp per channel; fp64 throughout.
+__global__ void abf_fold_stats_kernel(const double* __restrict__ G, const double* __restrict__ sx, const float* __restrict__ w1,
+                                      int C, int Cin, double* __restrict__ sum, double* __restrict__ sumsq) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const float* w = w1 + (size_t)c * Cin;
+  double s = 0.0, q = 0.0;
+  for (int j = lane; j < Cin; j += 32) {
+    const double wj = (double)__bfloat162float(__float2bfloat16_rn(w[j]));
+    s += wj * sx[j];
+    double t = 0.0;
+    for (int k = 0; k < Cin; ++k) t += G[(size_t)j * Cin + k] * (double)__bfloat162float(__float2bfloat16_rn(w[k]));
+    q += wj * t;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    sum[c] = s;
+    sumsq[c] = q;
+  }
+}
+
 // P: fp32 [Cin][C] = x^T dxp;  G: fp64 [Cin][Cin] = x^T x;  sx: fp64 [Cin] column sums of x;  dw1: fp32 [C][Cin]
 __global__ void abf_fold_dw1_kernel(const float* __restrict__ P, const double* __restrict__ G, const double* __restrict__ sx,
                                     const float* __restrict__ w1, const float* __restrict__ gamma,
@@ -1338,6 +1362,15 @@ extern "C" int clskd_abf_fold_dgrad(const float* w1, const float* gamma, const f
   abf_fold_dgrad_kernel<<<Cin, 256, 0, (cudaStream_t)stream>>>(w1, gamma, mean, invstd, sums, 1.0 / (double)M, training, C,
                                                                Cin, c1p, (__nv_bfloat16*)weff, bias);
   CLSKD_CHECK_LAUNCH("clskd_abf_fold_dgrad");
+  return CLSKD_OK;
+}
+
+extern "C" int clskd_abf_fold_stats(const double* G, const double* sx, const float* w1, int C, int Cin, double* sum,
+                                    double* sumsq, void* stream) {
+  CLSKD_CHECK_ARG(G && sx && w1 && sum && sumsq, "clskd_abf_fold_stats: null pointer");
+  CLSKD_CHECK_ARG(C >= 1 && Cin >= 1 && Cin <= 1024, "clskd_abf_fold_stats: extents");
+  abf_fold_stats_kernel<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(G, sx, w1, C, Cin, sum, sumsq);
+  CLSKD_CHECK_LAUNCH("clskd_abf_fold_stats");
   return CLSKD_OK;
 }
 

@@ -574,9 +574,11 @@ def test_abf_fold_vs_two_pass_backward(cuda_dev, cin, mid, F, T, B, up, mode):
     assert "AbfFoldFn" in calls[True] and "AbfFoldFn" not in calls[False], calls
     a, b = res[True], res[False]
     rl2 = lambda u, v: float((u.double() - v.double()).norm() / max(float(v.double().norm()), 1e-30))
-    assert torch.equal(a["fused"], b["fused"]) and torch.equal(a["rmean"], b["rmean"])     # same forward launches
-    errs = {k: rl2(a[k], b[k]) for k in ("dx", "dy", "dw1", "dgamma", "dbeta", "dwatt")}
-    assert errs["dy"] < 1e-6 and errs["dwatt"] < 1e-5 and errs["dgamma"] < 1e-5 and errs["dbeta"] < 1e-5, errs
+    # forward: the same launches except for the batch statistics of z1 - from the moments of x (clskd_colgram ->
+    # clskd_abf_fold_stats: statistics of the un-rounded W1 x) instead of the conv epilogue (of the stored bf16 z1)
+    errs = {k: rl2(a[k], b[k]) for k in ("fused", "rmean", "dx", "dy", "dw1", "dgamma", "dbeta", "dwatt")}
+    assert errs["fused"] < 2e-3 and errs["rmean"] < 2e-4, errs
+    assert errs["dy"] < 2e-3 and errs["dwatt"] < 2e-3 and errs["dgamma"] < 2e-3 and errs["dbeta"] < 2e-3, errs
     assert errs["dx"] < 1e-2 and errs["dw1"] < 1e-2, errs
 
 
