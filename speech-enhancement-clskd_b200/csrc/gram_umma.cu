@@ -114,12 +114,18 @@ gram_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
         if (i < p.B) {
+          float* grow = p.G + (int64_t)(p.ro_a + i) * p.ldg + p.ro_b + c;
+          if (!p.cross) {
+            // (vector reductions: see red_add16)
+            red_add16(grow, v, p.Bb - c);
+          } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (c + e < p.Bb) {
-              atomicAdd(p.G + (int64_t)(p.ro_a + i) * p.ldg + p.ro_b + c + e, __uint_as_float(v[e]));
-              if (p.cross) atomicAdd(p.G + (int64_t)(p.ro_b + c + e) * p.ldg + p.ro_a + i, __uint_as_float(v[e]));
-            }
+            for (int e = 0; e < 16; ++e)
+              if (c + e < p.Bb) {
+                atomicAdd(grow + e, __uint_as_float(v[e]));
+                if (p.cross) atomicAdd(p.G + (int64_t)(p.ro_b + c + e) * p.ldg + p.ro_a + i, __uint_as_float(v[e]));
+              }
+          }
         }
       }
     }

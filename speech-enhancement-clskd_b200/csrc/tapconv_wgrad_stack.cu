@@ -207,9 +207,7 @@ tapconv_wgrad_stack_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.grp_col[gi] + s * p.Np + cc), v);
           if (valid && tap >= 0) {
             float* dst = p.dw + ((int64_t)tap * p.Ctot + c) * p.N + cc;
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (cc + e < p.N) atomicAdd(dst + e, __uint_as_float(v[e]));
+            red_add16(dst, v, p.N - cc);
           }
         }
       }

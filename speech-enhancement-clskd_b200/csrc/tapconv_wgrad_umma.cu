@@ -189,10 +189,7 @@ tapconv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid
       for (int c = 0; c < p.n_tile; c += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile + c), v);
-        if (valid) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) atomicAdd(dst + c + e, __uint_as_float(v[e]));
-        }
+        if (valid) red_add16(dst + c, v, 16);
       }
     }
   }

@@ -850,9 +850,12 @@ def test_batched_repack_after_optimizer_step_equals_lazy_pack(cuda_dev, mode):
                     assert torch.equal(fresh.view(torch.int16 if e.dtype == torch.bfloat16 else torch.int32),
                                        w.view(torch.int16 if e.dtype == torch.bfloat16 else torch.int32))
         losses[lazy] = out
-    # (atomic accumulation orders differ run to run: the two trainers agree to rounding, not bitwise)
+    # (atomic accumulation orders differ run to run: the two trainers agree to rounding, not bitwise - and Adam's first
+    # updates are sign-like, so that rounding noise grows step by step: the bitwise check above is the test of the re-pack,
+    # this one only catches a trainer that runs on stale weights)
+    assert abs(losses[False][0] - losses[True][0]) < 1e-5 * abs(losses[True][0]), losses
     for la, lb in zip(losses[False], losses[True]):
-        assert abs(la - lb) < 5e-4 * abs(lb), losses
+        assert abs(la - lb) < 3e-3 * abs(lb), losses
 
 
 def _shift_tf(x, dt, df):
