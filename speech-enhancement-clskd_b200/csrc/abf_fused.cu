@@ -1284,10 +1284,8 @@ static int abf_bwd_launch(const char* who, bool xs, const void* gout, const void
   g.M = (int64_t)B * T * F; g.F = F; g.Fy = Fy; g.C = C; g.tpr = C / 8;
   g.cshift = ilog2(C); g.yshift = Fy == F ? 0 : 1;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(dwatt, 0, sizeof(double) * 4 * C, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(dbatt, 0, sizeof(double) * 2, st);
-  if (e == cudaSuccess && xs) e = cudaMemsetAsync(dw1, 0, sizeof(double) * 2 * C, st);
+  cudaError_t e = zero_spans(st, sums, sizeof(double) * 2 * C, dwatt, sizeof(double) * 4 * C, dbatt, sizeof(double) * 2,
+                             xs ? dw1 : nullptr, sizeof(double) * 2 * C);
   if (e != cudaSuccess) { set_error("%s: memset: %s", who, cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
   if (g.M == 0) return CLSKD_OK;
   const int64_t pairs = g.M / 2;

@@ -172,8 +172,7 @@ extern "C" int clskd_colgram(const void* x, int dtype, int64_t M, int C, double*
   }
   CLSKD_CHECK_ARG(((uintptr_t)x % 16) == 0, "clskd_colgram: x must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(G, 0, sizeof(double) * C * C, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(sx, 0, sizeof(double) * C, st);
+  cudaError_t e = zero_spans(st, G, sizeof(double) * C * C, sx, sizeof(double) * C);
   if (e != cudaSuccess) { set_error("clskd_colgram: memset: %s", cudaGetErrorString(e)); return CLSKD_ERR_CUDA; }
   if (M == 0) return CLSKD_OK;
   switch (C) {

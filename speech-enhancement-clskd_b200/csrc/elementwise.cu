@@ -1257,8 +1257,7 @@ extern "C" int clskd_colstats(const void* x, int dtype, int64_t M, int C, double
   CLSKD_CHECK_ARG(colstats_geom(M, C, &g) == 0, "clskd_colstats: C=%d unsupported (1..1024)", C);
   {
     cudaError_t e__ = cudaSuccess;
-    e__ = cudaMemsetAsync(sum, 0, sizeof(double) * C, ST);
-    if (e__ == cudaSuccess) e__ = cudaMemsetAsync(sumsq, 0, sizeof(double) * C, ST);
+    e__ = zero_spans(ST, sum, sizeof(double) * C, sumsq, sizeof(double) * C);
     if (e__ != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e__)); return CLSKD_ERR_CUDA; }
   }
   if (M == 0) return CLSKD_OK;
@@ -1343,9 +1342,7 @@ extern "C" int clskd_bn_act_bwd_stats(const void* x, int x_dtype, const void* dy
   CLSKD_CHECK_ARG(colstats_geom(M, C, &g) == 0, "clskd_bn_act_bwd_stats: C=%d unsupported", C);
   {
     cudaError_t e__ = cudaSuccess;
-    e__ = cudaMemsetAsync(sum_dz, 0, sizeof(double) * C, ST);
-    if (e__ == cudaSuccess) e__ = cudaMemsetAsync(sum_dz_xhat, 0, sizeof(double) * C, ST);
-    if (e__ == cudaSuccess && dslope) e__ = cudaMemsetAsync(dslope, 0, sizeof(double), ST);
+    e__ = zero_spans(ST, sum_dz, sizeof(double) * C, sum_dz_xhat, sizeof(double) * C, dslope, sizeof(double));
     if (e__ != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e__)); return CLSKD_ERR_CUDA; }
   }
   if (M == 0) return CLSKD_OK;
