@@ -392,7 +392,11 @@ bool colstats(const void* x, const void* dy, int dtype, int mode, int64_t M, int
   if (C % 8 || C > 2048 || !al16(x) || (dy && !al16(dy)) || M < 1) return false;
   const int rows_par = VT / (C / 8);
   int grid = row_grid(M, rows_par * 4);
-  if (grid > 2 * sm_count()) grid = 2 * sm_count();
+  // one wave: the statistics-only pass (43 registers) holds four CTAs per SM - 1.04 -> 0.80 ms per step over two; the
+  // backward statistics pass (100 registers) two.  (The per-column fp64 atomics of a few hundred CTAs at the end cost
+  // 2-4 us: tools/hwtests/atomic_tail_test.cu.)
+  const int per_sm = mode == 0 ? 4 : 2;
+  if (grid > per_sm * sm_count()) grid = per_sm * sm_count();
   const size_t sh = sizeof(float) * (2 * (size_t)C + 1);
   if (mode == 0) {
     CLSKD_DISPATCH_DTYPE(dtype, T, (colstats_vec_kernel<T, 0><<<grid, VT, sh, st>>>(
