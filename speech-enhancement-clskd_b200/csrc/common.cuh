@@ -139,6 +139,7 @@ bool try_wgrad(const ClskdTapConv* d, cudaStream_t st);
 // first encoder layer (2-channel fp32 spectrogram -> bf16 maps) on mma.sync tensor cores (tapconv_c2_mma.cu); true = handled
 namespace c2mma {
 bool try_fwd(const ClskdTapConv* d, cudaStream_t st);
+bool try_wgrad(const ClskdTapConv* d, cudaStream_t st);
 }  // namespace c2mma
 
 // dispatch on a runtime dtype tag

@@ -1045,6 +1045,10 @@ extern "C" int clskd_tapconv_wgrad(const ClskdTapConv* d, void* stream) {
     CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad(n2)");
     return CLSKD_OK;
   }
+  if (c2mma::try_wgrad(d, st)) {
+    CLSKD_CHECK_LAUNCH("clskd_tapconv_wgrad(c2 mma)");
+    return CLSKD_OK;
+  }
   {
     int tmin, tspan, fmin, fspan;
     if (M >= 4096 && wgrad_c2_ok(d, &tmin, &tspan, &fmin, &fspan)) {

@@ -476,6 +476,22 @@ def test_first_layer_mma_kernel_vs_oracle(cuda_dev, cout, F, T, B):
     assert (out - ref.float().bfloat16().double()).abs().max().item() < 1e-2 * s
     exact = (out == ref.float().bfloat16().double()).double().mean().item()
     assert exact > 0.97, exact
+    # weight / bias gradients (tapconv_wgrad_c2_mma_kernel: x split into bf16 hi + lo, dY is bf16) against float64 autograd
+    # on the same bf16-representable output gradient
+    gw = torch.randn(ref.shape, generator=g).bfloat16()
+    for p in conv.parameters():
+        p.grad = None
+    n1 = ops.core_launches
+    y2 = conv.forward_phys(ops.dense(xp), torch.bfloat16)
+    (ops.to_logical(y2).float() * gw.to(cuda_dev).float()).sum().backward()
+    assert ops.core_launches >= n1 + 2                     # forward + weight gradient on the CUDA-core entry points
+    ws = [conv.real_conv.weight, conv.real_conv.bias, conv.imag_conv.weight, conv.imag_conv.bias]
+    wd = [w.detach().double().cpu().requires_grad_(True) for w in ws]
+    refo = D.complex_conv2d(x0.double(), wd[0], wd[1], wd[2], wd[3])
+    (refo * gw.double()).sum().backward()
+    for w, r in zip(ws, wd):
+        err = float((w.grad.double().cpu() - r.grad).norm() / r.grad.norm())
+        assert err < 1e-4, err
 
 
 @pytest.mark.parametrize("sd,dd", [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16),
