@@ -1145,19 +1145,30 @@ __global__ void abf_fold_dgrad_kernel(const float* __restrict__ w1, const float*
 
 // Batch statistics of z1 = W1 x from the moments of x (clskd_colgram): sum_c = W1[c] . sx,  sumsq_c = W1[c]^T G W1[c].
 // W1 is rounded to bf16 first - the tcgen05 conv contracts the bf16 copy of the weight, and the statistics must belong to
-// the z1 it produces.  One warp per channel; fp64 throughout.
-__global__ void abf_fold_stats_kernel(const double* __restrict__ G, const double* __restrict__ sx, const float* __restrict__ w1,
-                                      int C, int Cin, double* __restrict__ sum, double* __restrict__ sumsq) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+// the z1 it produces.  A block stages G as fp32 in shared memory once and serves 8 channels (one warp each): the Cin^2
+// inner products run as fp32 FMAs (the fp64 pipe of this GPU made the all-double version 28 us per launch), the final
+// sums over j in fp64.
+constexpr int FOLD_CPB = 8;      // channels per block
+__global__ void __launch_bounds__(256) abf_fold_stats_kernel(const double* __restrict__ G, const double* __restrict__ sx,
+                                                             const float* __restrict__ w1, int C, int Cin,
+                                                             double* __restrict__ sum, double* __restrict__ sumsq) {
+  extern __shared__ float fs_sm[];                 // Gf[Cin*Cin], wq[FOLD_CPB][Cin]
+  float* Gf = fs_sm;
+  float* wq = fs_sm + (size_t)Cin * Cin;
+  for (int i = threadIdx.x; i < Cin * Cin; i += blockDim.x) Gf[i] = (float)G[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * FOLD_CPB + warp;
+  if (c < C)
+    for (int j = lane; j < Cin; j += 32) wq[warp * Cin + j] = __bfloat162float(__float2bfloat16_rn(w1[(size_t)c * Cin + j]));
+  __syncthreads();
   if (c >= C) return;
-  const float* w = w1 + (size_t)c * Cin;
+  const float* w = wq + warp * Cin;
   double s = 0.0, q = 0.0;
   for (int j = lane; j < Cin; j += 32) {
-    const double wj = (double)__bfloat162float(__float2bfloat16_rn(w[j]));
-    s += wj * sx[j];
-    double t = 0.0;
-    for (int k = 0; k < Cin; ++k) t += G[(size_t)j * Cin + k] * (double)__bfloat162float(__float2bfloat16_rn(w[k]));
-    q += wj * t;
+    float t = 0.f;
+    for (int k = 0; k < Cin; ++k) t = fmaf(Gf[k * Cin + j], w[k], t);        // G is symmetric: column j, conflict free
+    s += (double)w[j] * sx[j];
+    q += (double)w[j] * (double)t;
   }
   s = warp_sum(s);
   q = warp_sum(q);
@@ -1167,24 +1178,35 @@ __global__ void abf_fold_stats_kernel(const double* __restrict__ G, const double
   }
 }
 
-// P: fp32 [Cin][C] = x^T dxp;  G: fp64 [Cin][Cin] = x^T x;  sx: fp64 [Cin] column sums of x;  dw1: fp32 [C][Cin]
-__global__ void abf_fold_dw1_kernel(const float* __restrict__ P, const double* __restrict__ G, const double* __restrict__ sx,
-                                    const float* __restrict__ w1, const float* __restrict__ gamma,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const double* __restrict__ sums, double invM, int training, int C, int Cin,
-                                    float* __restrict__ dw1) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * Cin) return;
-  const int c = i / Cin, k = i - c * Cin;
-  const double gi = (double)(gamma ? gamma[c] : 1.f) * (double)invstd[c];
-  double v = (double)P[(size_t)k * C + c];
+// P: fp32 [Cin][C] = x^T dxp;  G: fp64 [Cin][Cin] = x^T x;  sx: fp64 [Cin] column sums of x;  dw1: fp32 [C][Cin].
+// A block stages G as fp32 in shared memory and serves FOLD_CPB channels; W1 (x^T x) in fp32 FMAs, the rest in fp64.
+__global__ void __launch_bounds__(256) abf_fold_dw1_kernel(const float* __restrict__ P, const double* __restrict__ G,
+                                                           const double* __restrict__ sx, const float* __restrict__ w1,
+                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const double* __restrict__ sums,
+                                                           double invM, int training, int C, int Cin,
+                                                           float* __restrict__ dw1) {
+  extern __shared__ float fs_sm[];                 // Gf[Cin*Cin] (training only)
+  float* Gf = fs_sm;
   if (training) {
-    const double k1 = sums[c] * invM, k2 = sums[C + c] * invM;
-    double t = 0.0;
-    for (int j = 0; j < Cin; ++j) t += (double)w1[(size_t)c * Cin + j] * G[(size_t)j * Cin + k];
-    v -= k1 * sx[k] + k2 * (double)invstd[c] * (t - (double)mean[c] * sx[k]);
+    for (int i = threadIdx.x; i < Cin * Cin; i += blockDim.x) Gf[i] = (float)G[i];
+    __syncthreads();
   }
-  dw1[i] = (float)(gi * v);
+  const int c_beg = blockIdx.x * FOLD_CPB;
+  const int n = min(FOLD_CPB, C - c_beg) * Cin;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = c_beg + i / Cin, k = i % Cin;
+    const double gi = (double)(gamma ? gamma[c] : 1.f) * (double)invstd[c];
+    double v = (double)P[(size_t)k * C + c];
+    if (training) {
+      const double k1 = sums[c] * invM, k2 = sums[C + c] * invM;
+      const float* w = w1 + (size_t)c * Cin;
+      float t = 0.f;
+      for (int j = 0; j < Cin; ++j) t = fmaf(w[j], Gf[j * Cin + k], t);
+      v -= k1 * sx[k] + k2 * (double)invstd[c] * ((double)t - (double)mean[c] * sx[k]);
+    }
+    dw1[(size_t)c * Cin + k] = (float)(gi * v);
+  }
 }
 
 const char* abf_unsupported(int B, int T, int F, int Fy, int C, const void* a, const void* b, const void* c) {
@@ -1367,7 +1389,14 @@ extern "C" int clskd_abf_fold_stats(const double* G, const double* sx, const flo
                                     double* sumsq, void* stream) {
   CLSKD_CHECK_ARG(G && sx && w1 && sum && sumsq, "clskd_abf_fold_stats: null pointer");
   CLSKD_CHECK_ARG(C >= 1 && Cin >= 1 && Cin <= 1024, "clskd_abf_fold_stats: extents");
-  abf_fold_stats_kernel<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(G, sx, w1, C, Cin, sum, sumsq);
+  CLSKD_CHECK_ARG(Cin <= 128, "clskd_abf_fold_stats: Cin <= 128");
+  const size_t sh = sizeof(float) * ((size_t)Cin * Cin + (size_t)FOLD_CPB * Cin);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(abf_fold_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    attr = true;
+  }
+  abf_fold_stats_kernel<<<(C + FOLD_CPB - 1) / FOLD_CPB, 256, sh, (cudaStream_t)stream>>>(G, sx, w1, C, Cin, sum, sumsq);
   CLSKD_CHECK_LAUNCH("clskd_abf_fold_stats");
   return CLSKD_OK;
 }
@@ -1377,9 +1406,15 @@ extern "C" int clskd_abf_fold_dw1(const float* P, const double* G, const double*
                                   int C, int Cin, float* dw1, void* stream) {
   CLSKD_CHECK_ARG(P && w1 && mean && invstd && sums && dw1 && (!training || (G && sx)), "clskd_abf_fold_dw1: null pointer");
   CLSKD_CHECK_ARG(C >= 1 && C <= 256 && Cin >= 1 && Cin <= 256 && M >= 1, "clskd_abf_fold_dw1: extents");
-  const int n = C * Cin;
-  abf_fold_dw1_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, G, sx, w1, gamma, mean, invstd, sums,
-                                                                         1.0 / (double)M, training, C, Cin, dw1);
+  CLSKD_CHECK_ARG(!training || Cin <= 128, "clskd_abf_fold_dw1: Cin <= 128");
+  const size_t sh = training ? sizeof(float) * (size_t)Cin * Cin : 0;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(abf_fold_dw1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    attr = true;
+  }
+  abf_fold_dw1_kernel<<<(C + FOLD_CPB - 1) / FOLD_CPB, 256, sh, (cudaStream_t)stream>>>(P, G, sx, w1, gamma, mean, invstd, sums,
+                                                                                      1.0 / (double)M, training, C, Cin, dw1);
   CLSKD_CHECK_LAUNCH("clskd_abf_fold_dw1");
   return CLSKD_OK;
 }
