@@ -35,6 +35,30 @@ def test_argument_errors_are_reported_without_a_gpu():
         _lib.call("clskd_gram_fwd", None, 0, 4, 16, 16, None, 0, None)
 
 
+def test_second_source_padding_rule_and_new_entry_point_validation():
+    """Host-side pieces of this round's entry points that run without a GPU: the padded extent of a narrow second source in
+    the packed weight of clskd_tapconv_fwd_umma (the library and the CPU model of the ABI must agree: the Python side packs
+    with one, the kernel contracts with the other), and loud argument errors of the new calls."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cabi_emu import EmuLib
+    from clskd_b200 import _lib
+    lib, emu = _lib.load(), EmuLib()
+    for c0 in (8, 16, 24, 32, 48, 64, 96, 128, 192, 256):
+        for c1 in (0, 8, 16, 24, 32, 64, 128):
+            got = lib.clskd_tapconv_umma_c1p(c0, c1)
+            assert got == emu.clskd_tapconv_umma_c1p(c0, c1), (c0, c1)
+            assert got >= c1 and got % 16 == 0 and (c1 != 0 or got == 0)
+    assert lib.clskd_tapconv_umma_c1p(128, 16) == 64 and lib.clskd_tapconv_umma_c1p(128, 128) == 128
+    assert lib.clskd_tapconv_umma_c1p(32, 16) == 32 and lib.clskd_tapconv_umma_c1p(16, 16) == 16
+    assert lib.clskd_colgram_supported(_lib.BF16, 16) == 1 and lib.clskd_colgram_supported(_lib.BF16, 128) == 1
+    assert lib.clskd_colgram_supported(_lib.F32, 16) == 0 and lib.clskd_colgram_supported(_lib.BF16, 24) == 0
+    assert lib.clskd_colgram(None, _lib.BF16, 10, 16, None, None, None) == -1 and b"null" in lib.clskd_last_error()
+    assert lib.clskd_abf_fold_stats(None, None, None, 128, 16, None, None, None) == -1
+    assert lib.clskd_abf_fold_dgrad(None, None, None, None, None, 10, 1, 128, 16, 64, None, None, None) == -1
+    assert lib.clskd_abf_fold_dw1(None, None, None, None, None, None, None, None, 10, 1, 128, 16, None, None) == -1
+
+
 def test_no_cpu_fallback():
     import clskd_b200
     m = clskd_b200.DCCRN(rnn_units=16, use_clstm=True, kernel_num=[4, 8, 8, 16, 16, 16])
